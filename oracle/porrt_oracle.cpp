@@ -1,0 +1,891 @@
+// oracle/porrt_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see porrt_oracle.hpp).
+// CPU restatement of po-rrt's hot path; each block cites the reference file:line it follows.
+#include "porrt_oracle.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <queue>
+
+namespace orc {
+
+static const double INF = std::numeric_limits<double>::infinity();
+
+// ============================================================== RNG
+// rand_pcg 0.3 Lcg128Xsl64 (pcg128.rs): MULTIPLIER, step, output_xsl_rr, from_state_incr.
+static const unsigned __int128 PCG_MUL =
+    ((unsigned __int128)0x2360ED051FC65DA4ULL << 64) | (unsigned __int128)0x4385DF649FCCF645ULL;
+
+Pcg64 Pcg64::from_state_incr(unsigned __int128 state, unsigned __int128 incr) {
+  Pcg64 p;
+  p.state = state;
+  p.inc = incr;
+  p.state = p.state + p.inc;       // "move away from inital value"
+  p.state = p.state * PCG_MUL + p.inc;
+  return p;
+}
+
+// rand_core 0.6 SeedableRng::seed_from_u64: PCG32 stream fills the 32-byte seed, 4 bytes at a time;
+// Lcg128Xsl64::from_seed reads four LE u64: state = s0|s1<<64, incr = (s2|s3<<64) | 1.
+Pcg64 Pcg64::seed_from_u64(uint64_t st) {
+  const uint64_t MUL = 6364136223846793005ULL, INC = 11634580027462260723ULL;
+  uint32_t w[8];
+  for (int c = 0; c < 8; ++c) {
+    st = st * MUL + INC;
+    uint32_t xorshifted = (uint32_t)(((st >> 18) ^ st) >> 27);
+    uint32_t rot = (uint32_t)(st >> 59);
+    w[c] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+  }
+  uint64_t s[4];
+  for (int k = 0; k < 4; ++k) s[k] = (uint64_t)w[2 * k] | ((uint64_t)w[2 * k + 1] << 32);
+  unsigned __int128 state = (unsigned __int128)s[0] | ((unsigned __int128)s[1] << 64);
+  unsigned __int128 incr = (unsigned __int128)s[2] | ((unsigned __int128)s[3] << 64);
+  return from_state_incr(state, incr | 1);
+}
+
+uint64_t Pcg64::next_u64() {
+  state = state * PCG_MUL + inc;
+  uint32_t rot = (uint32_t)(state >> 122);
+  uint64_t xsl = (uint64_t)(state >> 64) ^ (uint64_t)state;
+  return (xsl >> rot) | (xsl << ((64 - rot) & 63));
+}
+
+// rand 0.8 distributions/uniform.rs UniformFloat<f64>::sample_single (sample_space.rs:33).
+double Pcg64::gen_range_f64(double low, double high) {
+  double scale = high - low;
+  for (;;) {
+    uint64_t bits = (next_u64() >> 12) | 0x3FF0000000000000ULL;  // into_float_with_exponent(0): [1,2)
+    double value1_2;
+    std::memcpy(&value1_2, &bits, 8);
+    double value0_1 = value1_2 - 1.0;
+    double res = value0_1 * scale + low;
+    if (res < high) return res;
+    // rand's edge-case branch shrinks `scale` by one ulp and retries
+    uint64_t sb;
+    std::memcpy(&sb, &scale, 8);
+    sb -= 1;
+    std::memcpy(&scale, &sb, 8);
+  }
+}
+
+// rand 0.8 UniformInt<usize>::sample_single_inclusive(0, n-1) (sample_space.rs:58).
+uint64_t Pcg64::gen_range_usize(uint64_t range) {
+  if (range == 0) return next_u64();
+  uint64_t zone = (range << __builtin_clzll(range)) - 1;
+  for (;;) {
+    uint64_t v = next_u64();
+    unsigned __int128 m = (unsigned __int128)v * range;
+    uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+    if (lo <= zone) return hi;
+  }
+}
+
+State ContinuousSampler::sample() {  // sample_space.rs:30-37
+  State s;
+  for (int d = 0; d < 2; ++d) s[d] = rng.gen_range_f64(low[d], up[d]);
+  return s;
+}
+
+// ============================================================== common.rs
+double norm1(const State& a, const State& b) {
+  double d = 0.0;
+  for (int k = 0; k < 2; ++k) d += std::fabs(b[k] - a[k]);
+  return d;
+}
+double norm2(const State& a, const State& b) {
+  double d2 = 0.0;
+  for (int k = 0; k < 2; ++k) {
+    double dx = b[k] - a[k];
+    d2 += dx * dx;
+  }
+  return std::sqrt(d2);
+}
+void steer(const State& from, State& to, double max_step) {
+  double step = norm1(from, to);
+  if (step > max_step) {
+    double lambda = max_step / step;
+    for (int i = 0; i < 2; ++i) to[i] = from[i] + (to[i] - from[i]) * lambda;
+  }
+}
+double heuristic_radius(size_t n_nodes, double max_step, double search_radius, size_t dim) {
+  double n = (double)n_nodes;
+  double s = search_radius * std::pow(std::log(n) / n, 1.0 / (double)dim);
+  return s < max_step ? s : max_step;
+}
+double transition_probability(const BeliefState& parent, const BeliefState& child) {
+  double s = 0.0;
+  size_t n = std::min(parent.size(), child.size());
+  for (size_t i = 0; i < n; ++i) s = s + (child[i] > 0.0 ? parent[i] : 0.0);
+  return s;
+}
+bool is_compatible(const BeliefState& b, const WorldMask& validity) {
+  size_t n = std::min(b.size(), validity.size());
+  for (size_t i = 0; i < n; ++i)
+    if (b[i] > 0.0 && !validity[i]) return false;
+  return true;
+}
+// common.rs:352-355; usize arithmetic wraps in release builds (overflow from 18 worlds up).
+uint64_t belief_hash(const BeliefState& bs) {
+  uint64_t h = 0, p10 = 1;
+  for (size_t i = 0; i < bs.size(); ++i) {
+    double r = std::round(bs[i] * 1000.0);  // f64::round = half away from zero = C round()
+    uint64_t v = r <= 0.0 || std::isnan(r) ? 0 : (r >= 18446744073709551615.0 ? UINT64_MAX : (uint64_t)r);
+    h += (p10 + 1) * v;
+    p10 *= 10;
+  }
+  return h;
+}
+
+// ============================================================== Bresenham (line_drawing 0.8)
+static inline void octant_to(int o, int32_t x, int32_t y, int32_t& ox, int32_t& oy) {
+  switch (o) {
+    case 0: ox = x; oy = y; break;
+    case 1: ox = y; oy = x; break;
+    case 2: ox = y; oy = -x; break;
+    case 3: ox = -x; oy = y; break;
+    case 4: ox = -x; oy = -y; break;
+    case 5: ox = -y; oy = -x; break;
+    case 6: ox = -y; oy = x; break;
+    default: ox = x; oy = -y; break;
+  }
+}
+static inline void octant_from(int o, int32_t x, int32_t y, int32_t& ox, int32_t& oy) {
+  switch (o) {
+    case 0: ox = x; oy = y; break;
+    case 1: ox = y; oy = x; break;
+    case 2: ox = -y; oy = x; break;
+    case 3: ox = -x; oy = y; break;
+    case 4: ox = -x; oy = -y; break;
+    case 5: ox = -y; oy = -x; break;
+    case 6: ox = y; oy = -x; break;
+    default: ox = x; oy = -y; break;
+  }
+}
+Bresenham::Bresenham(int32_t ax, int32_t ay, int32_t bx, int32_t by) {
+  int value = 0;
+  int32_t ddx = bx - ax, ddy = by - ay;
+  if (ddy < 0) { ddx = -ddx; ddy = -ddy; value += 4; }
+  if (ddx < 0) { int32_t t = ddx; ddx = ddy; ddy = -t; value += 2; }
+  if (ddx < ddy) value += 1;
+  octant = value;
+  int32_t sx, sy, ex, ey;
+  octant_to(octant, ax, ay, sx, sy);
+  octant_to(octant, bx, by, ex, ey);
+  dx = ex - sx;
+  dy = ey - sy;
+  px = sx; py = sy; end_x = ex;
+  err = dy - dx;
+}
+bool Bresenham::next(int32_t& ox, int32_t& oy) {
+  if (px <= end_x) {
+    octant_from(octant, px, py, ox, oy);
+    if (err >= 0) { py += 1; err -= dx; }
+    px += 1;
+    err += dy;
+    return true;
+  }
+  return false;
+}
+
+// ============================================================== maps
+static inline uint32_t f64_as_u32(double v) {  // Rust `as u32`: saturating, NaN -> 0
+  if (!(v > 0.0)) return 0;
+  if (v >= 4294967295.0) return 4294967295u;
+  return (uint32_t)v;
+}
+
+bool GridMap::build(const uint8_t* occ, const uint8_t* zone, uint32_t h, uint32_t w, State lo, State up,
+                    int k, double visibility) {
+  kind = k; H = h; W = w; low = lo;
+  ppm = (double)w / (up[0] - lo[0]);  // map_io.rs:91
+  img.assign(occ, occ + (size_t)h * w);
+  zones.clear(); zones_to_worlds.clear(); world_validities.clear(); zone_positions.clear();
+  n_zones = 0; n_worlds = 0; visibility_distance = 0.0;
+  if (!zone) {
+    if (kind == DOOR) {  // Map::init_without_zones, map_io.rs:108-111
+      n_worlds = 1;
+      world_validities.push_back(WorldMask(1, 1));
+    }
+    return true;
+  }
+  zones.assign(zone, zone + (size_t)h * w);
+  // init_zone_ids (map_io.rs:130-145): n_zones = max id + 1 (1 even when no zone pixel exists)
+  size_t max_id = 0;
+  for (size_t p = 0; p < zones.size(); ++p)
+    if (zones[p] != 255 && zones[p] > max_id) max_id = zones[p];
+  n_zones = max_id + 1;
+  if (kind == DOOR) {
+    if (n_zones >= 32) { error = "2_u32.pow(n_zones) overflows"; return false; }
+    n_worlds = (size_t)1 << n_zones;
+  } else {
+    n_worlds = n_zones;  // map_shelves_io.rs:460-462
+  }
+  // init_zone_positions (map_io.rs:147-163): u32 sums (wrapping as in a release build), integer mean
+  std::vector<uint32_t> si(n_zones, 0), sj(n_zones, 0), cnt(n_zones, 0);
+  for (uint32_t i = 0; i < h; ++i)
+    for (uint32_t j = 0; j < w; ++j) {
+      uint8_t z = zones[(size_t)i * w + j];
+      if (z != 255) { si[z] += i; sj[z] += j; cnt[z] += 1; }
+    }
+  for (size_t z = 0; z < n_zones; ++z) {
+    if (cnt[z] == 0) { error = "zone without pixels: division by zero panic (map_io.rs:160)"; return false; }
+    zone_positions.push_back(to_coordinates(si[z] / cnt[z], sj[z] / cnt[z]));
+  }
+  visibility_distance = visibility;
+  if (kind == DOOR) {
+    for (size_t z = 0; z < n_zones; ++z) {  // zone_index_to_world_mask, map_io.rs:198-214
+      WorldMask m(n_worlds, 1);
+      for (size_t wd = 0; wd < n_worlds; ++wd)
+        if ((wd & ((size_t)1 << z)) == 0) m[wd] = 0;
+      zones_to_worlds.push_back(m);
+    }
+    world_validities = zones_to_worlds;
+    world_validities.push_back(WorldMask(n_worlds, 1));  // all-ones mask is LAST (map_io.rs:125-126)
+  } else {
+    world_validities.push_back(WorldMask(n_zones, 1));   // map_shelves_io.rs:113
+  }
+  return true;
+}
+
+void GridMap::to_pixel(const State& xy, uint32_t& i, uint32_t& j) const {
+  i = f64_as_u32((double)(H - 1) - (xy[1] - low[1]) * ppm);
+  j = f64_as_u32((xy[0] - low[0]) * ppm);
+}
+State GridMap::to_coordinates(uint32_t i, uint32_t j) const {  // note the swapped low[] indices, as in the reference
+  State s;
+  s[0] = (double)j / ppm + low[1];
+  s[1] = (double)(H - 1 - i) / ppm + low[0];
+  return s;
+}
+
+static inline Space shelf_class(uint8_t p) {  // pixel_to_occupation, map_shelves_io.rs:150-156
+  return p == 255 ? FREE : (p >= 127 ? LOW_OBSTACLE : HIGH_OBSTACLE);
+}
+
+Traversed GridMap::is_state_valid(const State& xy) const {
+  uint32_t i, j;
+  to_pixel(xy, i, j);
+  if (i >= H || j >= W) return {SPACE_PANIC, PANIC_OOB};
+  uint8_t p = img[(size_t)i * W + j];
+  if (kind == SHELF) return {shelf_class(p), 0};
+  if (p == 255) return {FREE, 0};
+  if (p == 0) return {OBSTACLE, 0};
+  if (zones.empty() || zones[(size_t)i * W + j] == 255) return {SPACE_PANIC, PANIC_ZONE_UNWRAP};
+  return {ZONE, (int64_t)zones[(size_t)i * W + j]};
+}
+
+Traversed GridMap::get_traversed_space(const State& a, const State& b) const {
+  uint32_t ai, aj, bi, bj;
+  to_pixel(a, ai, aj);
+  to_pixel(b, bi, bj);
+  Bresenham line((int32_t)ai, (int32_t)aj, (int32_t)bi, (int32_t)bj);
+  int32_t i, j;
+  if (kind == SHELF) {
+    uint8_t lowest = 255;
+    while (line.next(i, j)) {
+      if ((uint32_t)i >= H || (uint32_t)j >= W) return {SPACE_PANIC, PANIC_OOB};
+      uint8_t p = img[(size_t)(uint32_t)i * W + (uint32_t)j];
+      lowest = std::min(lowest, p);
+      if (lowest == 0) return {HIGH_OBSTACLE, 0};
+    }
+    return {shelf_class(lowest), 0};
+  }
+  Traversed t = {FREE, 0};
+  while (line.next(i, j)) {
+    if ((uint32_t)i >= H || (uint32_t)j >= W) return {SPACE_PANIC, PANIC_OOB};
+    size_t at = (size_t)(uint32_t)i * W + (uint32_t)j;
+    uint8_t p = img[at];
+    if (p == 255) continue;
+    if (p == 0) return {OBSTACLE, 0};
+    if (zones.empty() || zones[at] == 255) return {SPACE_PANIC, PANIC_ZONE_UNWRAP};
+    int64_t z = zones[at];
+    if (t.space == ZONE && t.zone_or_panic != z) return {SPACE_PANIC, PANIC_MULTI_ZONE};
+    t = {ZONE, z};
+  }
+  return t;
+}
+
+static int64_t space_to_validity(const GridMap& m, const Traversed& t) {
+  switch (t.space) {
+    case SPACE_PANIC: return t.zone_or_panic;
+    case FREE: return (int64_t)m.world_validities.size() - 1;
+    case ZONE: return t.zone_or_panic;
+    default: return NONE;
+  }
+}
+int64_t GridMap::state_validity(const State& xy) const { return space_to_validity(*this, is_state_valid(xy)); }
+int64_t GridMap::transition_validator(const State& from, const State& to) const {
+  return space_to_validity(*this, get_traversed_space(from, to));
+}
+
+static void normalize(BeliefState& b) {
+  double sum = 0.0;
+  for (double p : b) sum = sum + p;
+  for (double& p : b) p /= sum;
+}
+static bool any_nan(const BeliefState& b) {
+  for (double p : b)
+    if (std::isnan(p)) return true;
+  return false;
+}
+std::vector<BeliefState> GridMap::successor_beliefs(const BeliefState& b, size_t zone) const {
+  std::vector<BeliefState> out;
+  if (kind == DOOR) {
+    const WorldMask& mask = zones_to_worlds[zone];
+    BeliefState closed = b, open = b;
+    for (size_t w = 0; w < mask.size(); ++w) closed[w] = mask[w] ? 0.0 : b[w];
+    normalize(closed);
+    if (!any_nan(closed)) out.push_back(closed);
+    for (size_t w = 0; w < mask.size(); ++w) open[w] = mask[w] ? b[w] : 0.0;
+    normalize(open);
+    if (!any_nan(open)) out.push_back(open);
+  } else {
+    BeliefState there = b, not_there = b;
+    for (size_t w = 0; w < there.size(); ++w) there[w] = (w == zone) ? there[w] : 0.0;
+    normalize(there);
+    if (!any_nan(there)) out.push_back(there);
+    for (size_t w = 0; w < not_there.size(); ++w) not_there[w] = (w == zone) ? 0.0 : b[w];
+    normalize(not_there);
+    if (!any_nan(not_there)) out.push_back(not_there);
+  }
+  return out;
+}
+
+bool GridMap::visible_zones(const State& s, uint64_t* mask, int64_t* panic) const {
+  uint64_t m = 0;
+  for (size_t z = 0; z < n_zones; ++z) {
+    if (norm2(s, zone_positions[z]) < visibility_distance) {
+      Traversed t = get_traversed_space(s, zone_positions[z]);
+      if (t.space == SPACE_PANIC) { if (panic) *panic = t.zone_or_panic; return false; }
+      bool fov = kind == DOOR ? (t.space != OBSTACLE) : (t.space != HIGH_OBSTACLE);
+      if (fov) m |= (uint64_t)1 << z;
+    }
+  }
+  *mask = m;
+  return true;
+}
+
+bool GridMap::observe(const State& s, const BeliefState& b, std::vector<BeliefState>& out, int64_t* panic) const {
+  out.clear();
+  out.push_back(b);
+  for (size_t z = 0; z < n_zones; ++z) {
+    if (norm2(s, zone_positions[z]) < visibility_distance) {
+      Traversed t = get_traversed_space(s, zone_positions[z]);
+      if (t.space == SPACE_PANIC) { if (panic) *panic = t.zone_or_panic; return false; }
+      bool fov = kind == DOOR ? (t.space != OBSTACLE) : (t.space != HIGH_OBSTACLE);
+      if (fov) {
+        std::vector<BeliefState> beliefs = out;
+        out.clear();
+        for (const BeliefState& bel : beliefs) {
+          std::vector<BeliefState> succ = successor_beliefs(bel, z);
+          out.insert(out.end(), succ.begin(), succ.end());
+        }
+      }
+    }
+  }
+  return true;
+}
+
+std::vector<BeliefState> GridMap::reachable_belief_states(const BeliefState& b0) const {
+  std::vector<BeliefState> reachable;
+  std::unordered_set<uint64_t> hashes;
+  std::vector<std::pair<BeliefState, std::vector<size_t>>> lifo;
+  reachable.push_back(b0);
+  std::vector<size_t> all(n_zones);
+  for (size_t z = 0; z < n_zones; ++z) all[z] = z;
+  lifo.push_back({b0, all});
+  while (!lifo.empty()) {
+    std::pair<BeliefState, std::vector<size_t>> top = lifo.back();
+    lifo.pop_back();
+    for (size_t zone_id : top.second) {
+      std::vector<size_t> remaining;
+      for (size_t id : top.second)
+        if (id != zone_id) remaining.push_back(id);
+      std::vector<BeliefState> succ = successor_beliefs(top.first, zone_id);
+      for (const BeliefState& s : succ) {
+        if (std::find(reachable.begin(), reachable.end(), s) == reachable.end()) {
+          uint64_t h = belief_hash(s);
+          if (!hashes.count(h)) {
+            reachable.push_back(s);
+            hashes.insert(h);
+          }
+          lifo.push_back({s, remaining});
+        }
+      }
+    }
+  }
+  return reachable;
+}
+
+// ============================================================== kd-tree
+void KdTree::add(State s, size_t id) {
+  int32_t cur = 0;
+  for (size_t axis = 0;; axis = (axis + 1) % 2) {
+    int32_t* next = s[axis] < nodes[cur].state[axis] ? &nodes[cur].left : &nodes[cur].right;
+    if (*next >= 0) {
+      cur = *next;
+    } else {
+      *next = (int32_t)nodes.size();
+      nodes.push_back({id, s, -1, -1});
+      return;
+    }
+  }
+}
+
+template <class F>
+static void nn_inner(const KdTree& t, const State& q, double& dmin, int32_t& nearest, int32_t from, size_t axis, F& validator) {
+  const KdTree::Node& n = t.nodes[from];
+  double d = norm2(n.state, q);
+  if (d < dmin && validator(n.id)) { dmin = d; nearest = from; }
+  size_t next_axis = (axis + 1) % 2;
+  if (q[axis] < n.state[axis]) {
+    if (q[axis] - dmin < n.state[axis] && n.left >= 0) nn_inner(t, q, dmin, nearest, n.left, next_axis, validator);
+    if (q[axis] + dmin >= n.state[axis] && n.right >= 0) nn_inner(t, q, dmin, nearest, n.right, next_axis, validator);
+  } else {
+    if (q[axis] + dmin >= n.state[axis] && n.right >= 0) nn_inner(t, q, dmin, nearest, n.right, next_axis, validator);
+    if (q[axis] - dmin < n.state[axis] && n.left >= 0) nn_inner(t, q, dmin, nearest, n.left, next_axis, validator);
+  }
+}
+template <class F>
+static const KdTree::Node& nn_filtered(const KdTree& t, State q, F validator) {
+  double dmin = INF;
+  int32_t nearest = 0;  // root when nothing passes the filter (nearest_neighbor.rs:89)
+  nn_inner(t, q, dmin, nearest, 0, 0, validator);
+  return t.nodes[nearest];
+}
+const KdTree::Node& KdTree::nearest_neighbor_filtered(State q, const std::function<bool(size_t)>& validator) const {
+  return nn_filtered(*this, q, validator);
+}
+const KdTree::Node& KdTree::nearest_neighbor(State q) const {
+  return nn_filtered(*this, q, [](size_t) { return true; });
+}
+
+template <class F>
+static void radius_inner(const KdTree& t, const State& q, double radius, std::vector<const KdTree::Node*>& out,
+                         int32_t from, size_t axis, F& validator) {
+  const KdTree::Node& n = t.nodes[from];
+  double d = norm2(n.state, q);
+  if (d <= radius && validator(n.id)) out.push_back(&n);
+  size_t next_axis = (axis + 1) % 2;
+  if (q[axis] - radius <= n.state[axis] && n.left >= 0) radius_inner(t, q, radius, out, n.left, next_axis, validator);
+  if (q[axis] + radius >= n.state[axis] && n.right >= 0) radius_inner(t, q, radius, out, n.right, next_axis, validator);
+}
+std::vector<const KdTree::Node*> KdTree::nearest_neighbors_filtered(State q, double r, const std::function<bool(size_t)>& validator) const {
+  std::vector<const Node*> out;
+  radius_inner(*this, q, r, out, 0, 0, validator);
+  return out;
+}
+std::vector<const KdTree::Node*> KdTree::nearest_neighbors(State q, double r) const {
+  std::vector<const Node*> out;
+  auto all = [](size_t) { return true; };
+  radius_inner(*this, q, r, out, 0, 0, all);
+  return out;
+}
+
+// ============================================================== dijkstra
+struct HeapItem {
+  double prio; size_t id;
+  bool operator<(const HeapItem& o) const { return prio > o.prio; }  // min-heap (Priority reverses the order, common.rs:235-239)
+};
+
+static inline bool node_valid_in_world(const PTOGraph& g, size_t id, int world) {
+  return world < 0 || g.validities[g.nodes[id].validity_id][(size_t)world];
+}
+
+std::vector<double> dijkstra(const PTOGraph& g, int world, const std::vector<size_t>& finals) {
+  std::vector<double> dist(g.nodes.size(), INF);
+  std::priority_queue<HeapItem> q;
+  for (size_t id : finals) { dist[id] = 0.0; q.push({0.0, id}); }
+  while (!q.empty()) {
+    HeapItem it = q.top();
+    q.pop();
+    size_t v = it.id;
+    for (const PTOEdge& e : g.nodes[v].parents) {
+      size_t u = e.id;
+      if (!node_valid_in_world(g, u, world)) continue;  // PTOGraphWorldView::parents, pto_graph.rs:264-270
+      double alt = dist[v] + norm2(g.nodes[u].state, g.nodes[v].state);
+      if (alt < dist[u]) { dist[u] = alt; q.push({alt, u}); }
+    }
+  }
+  return dist;
+}
+
+std::vector<State> extract_path(const PTOGraph& g, int world, size_t start, const std::vector<double>& costs) {
+  std::vector<State> path;
+  size_t node_id = start;
+  path.push_back(g.nodes[node_id].state);
+  while (costs[node_id] != 0.0) {
+    bool found = false;
+    size_t best = 0;
+    double best_c = 0.0;
+    for (const PTOEdge& e : g.nodes[node_id].parents) {   // sic: the reference walks `parents`
+      if (!node_valid_in_world(g, e.id, world)) continue;
+      double c = costs[e.id] + norm2(g.nodes[e.id].state, g.nodes[node_id].state);
+      if (!found || c < best_c) { found = true; best = e.id; best_c = c; }  // Iterator::min_by keeps the first minimum
+    }
+    if (!found) break;  // reference: unwrap() panic on an empty parent list
+    node_id = best;
+    path.push_back(g.nodes[node_id].state);
+  }
+  return path;
+}
+
+// ============================================================== reachability
+void Reachability::set_root(const WorldMask& v) {
+  n_worlds = v.size();
+  validities.push_back(v);
+  reachabilities.push_back(v);
+  finality.assign(n_worlds, 0);
+}
+void Reachability::add_node(const WorldMask& v) {
+  validities.push_back(v);
+  reachabilities.push_back(WorldMask(v.size(), 0));
+}
+void Reachability::add_final_node(size_t id, const WorldMask& f) {
+  final_node_ids.push_back(id);
+  final_set.insert(id);
+  finalities.push_back(f);
+  dirty = true;
+}
+void Reachability::add_edge(size_t from, size_t to, const WorldMask& ev) {
+  for (size_t i = 0; i < reachabilities[to].size(); ++i) {
+    bool r_to = reachabilities[to][i], r_from = reachabilities[from][i], v = ev[i];
+    reachabilities[to][i] = r_to || (r_from && v);
+    if (final_set.count(to)) dirty = true;
+  }
+}
+std::vector<size_t> Reachability::get_final_nodes_for_world(size_t world) const {
+  std::vector<size_t> out;
+  for (size_t i = 0; i < final_node_ids.size(); ++i) {
+    size_t id = final_node_ids[i];
+    if (reachabilities[id][world] && finalities[i][world]) out.push_back(id);
+  }
+  return out;
+}
+bool Reachability::is_final_set_complete() {
+  if (final_node_ids.empty()) return false;
+  if (dirty) {
+    for (size_t k = 0; k < final_node_ids.size(); ++k) {
+      const WorldMask& r = reachabilities[final_node_ids[k]];
+      for (size_t i = 0; i < r.size(); ++i) finality[i] = finality[i] || (r[i] && finalities[k][i]);
+    }
+    dirty = false;
+  }
+  for (uint8_t b : finality)
+    if (!b) return false;
+  return true;
+}
+
+// ============================================================== goals
+bool SquareGoal::init(const std::vector<std::pair<State, WorldMask>>& g, double md) {
+  if (g.empty()) return false;
+  goal_to_validity = g;
+  max_dist = md;
+  size_t nw = g[0].second.size();
+  world_to_goal.assign(nw, State{0.0, 0.0});
+  std::vector<bool> has(nw, false);
+  for (size_t w = 0; w < nw; ++w)
+    for (const auto& gv : g)
+      if (gv.second[w]) {
+        if (has[w]) return false;  // assert: validities shouldn't overlap (common.rs:320)
+        world_to_goal[w] = gv.first;
+        has[w] = true;
+      }
+  return true;
+}
+bool SquareGoal::goal(const State& s, WorldMask* out) const {
+  for (const auto& gv : goal_to_validity)
+    if (norm1(s, gv.first) < max_dist) { *out = gv.second; return true; }
+  return false;
+}
+
+// ============================================================== belief graph DP
+bool conditional_dijkstra(const BeliefGraph& g, const std::vector<size_t>& finals, std::vector<double>& dist) {
+  dist.assign(g.nodes.size(), INF);
+  std::priority_queue<HeapItem> q;
+  for (size_t id : finals) { dist[id] = 0.0; q.push({0.0, id}); }
+  while (!q.empty()) {
+    HeapItem it = q.top();
+    q.pop();
+    size_t v_id = it.id;
+    for (size_t u_id : g.nodes[v_id].parents) {
+      const BeliefNode& u = g.nodes[u_id];
+      double alt = 0.0;
+      if (u.node_type == ACTION) {
+        alt += norm2(u.state, g.nodes[v_id].state) + dist[v_id];
+      } else if (u.node_type == OBSERVATION) {
+        for (size_t vv_id : u.children) {
+          const BeliefNode& vv = g.nodes[vv_id];
+          double p = transition_probability(g.belief_state(u_id), g.belief_state(vv_id));
+          if (!(p > 0.0)) return false;  // assert!(p > 0.0), belief_graph.rs:130
+          alt += p * (norm2(u.state, vv.state) + dist[vv_id]);
+        }
+      } else {
+        return false;  // panic "node type should be know at this stage!"
+      }
+      if (alt < dist[u_id]) { dist[u_id] = alt; q.push({alt, u_id}); }
+    }
+  }
+  return true;
+}
+
+static bool best_expected_children(const BeliefGraph& g, size_t node_id, const std::vector<double>& costs,
+                                   std::vector<size_t>& best_children) {
+  struct C { size_t child_id; double cost_to_child, expected_from_child; };
+  std::map<size_t, std::vector<C>> by_belief;  // BTreeMap: ascending belief_id
+  const BeliefNode& n = g.nodes[node_id];
+  for (size_t child_id : n.children) {
+    const BeliefNode& c = g.nodes[child_id];
+    by_belief[c.belief_id].push_back({child_id, norm2(n.state, c.state), costs[child_id]});
+  }
+  best_children.clear();
+  for (auto& kv : by_belief) {
+    size_t best_id = kv.second[0].child_id;
+    double p = transition_probability(g.belief_state(node_id), g.belief_state(best_id));
+    if (!(p > 0.0)) return false;
+    double best_cost = INF;
+    for (const C& c : kv.second) {
+      double cost = p * (c.cost_to_child + c.expected_from_child);
+      if (cost < best_cost) { best_cost = cost; best_id = c.child_id; }
+    }
+    if (!(p * costs[best_id] <= costs[node_id])) return false;  // assert, belief_graph.rs:261
+    best_children.push_back(best_id);
+  }
+  return true;
+}
+
+bool extract_policy(const BeliefGraph& g, const std::vector<double>& costs, Policy& policy) {
+  if (g.nodes.empty()) return false;
+  policy = Policy();
+  std::vector<std::pair<size_t, size_t>> lifo;
+  policy.nodes.push_back({g.nodes[0].state, g.nodes[0].belief_id, -1, {}, 0});
+  lifo.push_back({0, 0});
+  std::vector<size_t> children;
+  while (!lifo.empty()) {
+    std::pair<size_t, size_t> top = lifo.back();
+    lifo.pop_back();
+    if (!best_expected_children(g, top.second, costs, children)) return false;
+    for (size_t child_id : children) {
+      bool is_leaf = costs[child_id] == 0.0;
+      size_t pid = policy.nodes.size();
+      policy.nodes.push_back({g.nodes[child_id].state, g.nodes[child_id].belief_id, (int64_t)top.first, {}, child_id});
+      if (is_leaf) policy.leafs.push_back(pid);
+      policy.nodes[top.first].children.push_back(pid);
+      if (!is_leaf) lifo.push_back({pid, child_id});
+    }
+  }
+  policy.expected_costs = costs[0];
+  return true;
+}
+
+// ============================================================== PRM
+PRM::PRM(const GridMap* m, State low, State up, uint64_t seed)
+    : fns(m), sampler(low, up, seed), kdtree(State{0.0, 0.0}) {
+  graph.validities = m->world_validities;
+}
+void PRM::init(State start) {
+  graph.add_node(start, 0);
+  kdtree.reset(start);
+}
+void PRM::grow_graph(double max_step, double search_radius, size_t n_iter) {
+  for (size_t i = 0; i < n_iter; ++i) {
+    State s = sampler.sample();
+    add_sample(s, max_step, search_radius);
+    n_it += 1;
+  }
+}
+size_t PRM::add_sample(State s, double max_step, double search_radius) {
+  if (graph.nodes.empty()) {
+    graph.add_node(s, 0);
+    kdtree.reset(s);
+    return 0;
+  }
+  size_t new_id = graph.add_node(s, 0);
+  double radius = heuristic_radius(graph.nodes.size(), max_step, search_radius, 2);
+  std::vector<size_t> neighbours;
+  for (const KdTree::Node* n : kdtree.nearest_neighbors(s, radius)) neighbours.push_back(n->id);
+  kdtree.add(s, new_id);
+  if (neighbours.empty()) return new_id;
+  std::vector<size_t> edges;
+  for (size_t id : neighbours)
+    if (fns->transition_validator(graph.nodes[id].state, graph.nodes[new_id].state) >= 0) edges.push_back(id);
+  for (size_t id : edges) graph.add_edge(id, new_id, 0);
+  for (size_t id : edges) graph.add_edge(new_id, id, 0);
+  return new_id;
+}
+std::vector<State> PRM::plan_path(State start, State goal) {
+  size_t s = kdtree.nearest_neighbor(start).id, gl = kdtree.nearest_neighbor(goal).id;
+  std::vector<double> cost = dijkstra(graph, -1, {gl});
+  if (std::isinf(cost[s])) return {};
+  return extract_path(graph, -1, s, cost);
+}
+
+// ============================================================== PTO
+PTO::PTO(const GridMap* m, State low, State up, uint64_t seed)
+    : fns(m), continuous(low, up, seed), discrete(seed), kdtree(State{0.0, 0.0}), n_worlds(m->n_worlds) {
+  graph.validities = m->world_validities;
+}
+
+int PTO::grow_graph(State start, const SquareGoal& goal, double max_step, double search_radius,
+                    size_t n_iter_min, size_t n_iter_max) {
+  int64_t root_vid = fns->state_validity(start);
+  if (root_vid < 0) return root_vid == NONE ? -100 : (int)root_vid;  // expect("Start from a valid state!")
+  graph.add_node(start, (size_t)root_vid);
+  reach.set_root(graph.validities[(size_t)root_vid]);
+  kdtree.reset(start);
+  size_t i = 0;
+  while (i < n_iter_min || (!reach.is_final_set_complete() && i < n_iter_max)) {
+    i += 1;
+    // sample(), pto.rs:141-149
+    size_t world = discrete.sample(n_worlds);
+    State new_state = (i % 100 == 0) ? goal.goal_example(world) : continuous.sample();
+    const KdTree::Node& kd_from = nn_filtered(kdtree, new_state, [&](size_t id) { return reach.reachabilities[id][world] != 0; });
+    State from_state = kd_from.state;
+    size_t from_id = kd_from.id;
+    steer(from_state, new_state, max_step);
+    int64_t svid = fns->state_validity(new_state);
+    if (svid < NONE) return (int)svid;
+    if (svid >= 0) {
+      size_t new_id = graph.add_node(new_state, (size_t)svid);
+      reach.add_node(graph.validities[(size_t)svid]);
+      double radius = heuristic_radius(graph.nodes.size(), max_step, search_radius, 2);
+      std::vector<size_t> neighbours;
+      for (const KdTree::Node* n : kdtree.nearest_neighbors(new_state, radius)) neighbours.push_back(n->id);
+      if (neighbours.empty()) neighbours.push_back(from_id);
+      std::vector<std::pair<size_t, size_t>> edges;
+      for (size_t id : neighbours) {
+        int64_t v = fns->transition_validator(graph.nodes[id].state, graph.nodes[new_id].state);
+        if (v < NONE) return (int)v;
+        if (v >= 0) edges.push_back({id, (size_t)v});
+      }
+      for (auto& e : edges) {
+        reach.add_edge(e.first, new_id, graph.validities[e.second]);
+        graph.add_edge(e.first, new_id, e.second);
+      }
+      for (auto& e : edges) {
+        reach.add_edge(new_id, e.first, graph.validities[e.second]);
+        graph.add_edge(new_id, e.first, e.second);
+      }
+      WorldMask finality;
+      if (goal.goal(new_state, &finality)) reach.add_final_node(new_id, finality);
+      kdtree.add(new_state, new_id);
+    }
+  }
+  n_it = i;
+  return reach.is_final_set_complete() ? 0 : 1;
+}
+
+bool PTO::build_belief_graph(const BeliefState& b0) {  // pto.rs:185-259
+  std::vector<BeliefState> beliefs = fns->reachable_belief_states(b0);
+  const std::vector<WorldMask>& wv = graph.validities;
+  size_t B = beliefs.size(), V = graph.nodes.size();
+  std::vector<std::vector<bool>> compat(B, std::vector<bool>(wv.size(), false));  // compute_compatibility, common.rs:266-276
+  for (size_t b = 0; b < B; ++b)
+    for (size_t v = 0; v < wv.size(); ++v) compat[b][v] = is_compatible(beliefs[b], wv[v]);
+  belief_graph = BeliefGraph();
+  belief_graph.reachable_belief_states = beliefs;
+  for (size_t b = 0; b < B; ++b) belief_graph.belief_states_to_id[belief_hash(beliefs[b])] = b;
+  if (belief_graph.belief_states_to_id.size() != B) return false;  // "collision when hashing the belief states!"
+  node_to_belief_nodes.assign(V, std::vector<int64_t>(B, -1));
+  for (size_t id = 0; id < V; ++id)
+    for (size_t b = 0; b < B; ++b) {
+      size_t bn = belief_graph.add_node(graph.nodes[id].state, b, UNKNOWN);
+      if (compat[b][graph.nodes[id].validity_id]) node_to_belief_nodes[id][b] = (int64_t)bn;
+    }
+  std::vector<BeliefState> children;
+  for (size_t id = 0; id < V; ++id)
+    for (size_t b = 0; b < B; ++b) {
+      if (!fns->observe(graph.nodes[id].state, beliefs[b], children, &panic)) return false;
+      int64_t parent = node_to_belief_nodes[id][b];
+      for (const BeliefState& cb : children) {
+        if (belief_hash(beliefs[b]) != belief_hash(cb)) {
+          auto it = belief_graph.belief_states_to_id.find(belief_hash(cb));
+          if (it == belief_graph.belief_states_to_id.end()) return false;  // panic "no if corresponding to this belief state!"
+          int64_t child = node_to_belief_nodes[id][it->second];
+          if (parent >= 0 && child >= 0) {
+            belief_graph.nodes[(size_t)parent].node_type = OBSERVATION;
+            belief_graph.add_edge((size_t)parent, (size_t)child);
+          }
+        }
+      }
+    }
+  for (size_t id = 0; id < V; ++id)
+    for (size_t b = 0; b < B; ++b) {
+      int64_t parent = node_to_belief_nodes[id][b];
+      if (parent < 0) continue;
+      if (belief_graph.nodes[(size_t)parent].node_type == OBSERVATION) continue;
+      for (const PTOEdge& ce : graph.nodes[id].children) {
+        int64_t child = node_to_belief_nodes[ce.id][b];
+        if (child < 0) continue;
+        if (compat[belief_graph.nodes[(size_t)parent].belief_id][ce.validity_id]) {
+          belief_graph.nodes[(size_t)parent].node_type = ACTION;
+          belief_graph.add_edge((size_t)parent, (size_t)child);
+        }
+      }
+    }
+  return true;
+}
+
+bool PTO::compute_expected_costs_to_goals() {  // pto.rs:261-275
+  final_belief_nodes.clear();
+  for (size_t k = 0; k < reach.final_node_ids.size(); ++k) {
+    size_t final_id = reach.final_node_ids[k];
+    for (int64_t bn : node_to_belief_nodes[final_id]) {
+      if (bn < 0) continue;
+      if (is_compatible(belief_graph.belief_state((size_t)bn), reach.finalities[k])) final_belief_nodes.push_back((size_t)bn);
+    }
+  }
+  return conditional_dijkstra(belief_graph, final_belief_nodes, expected_costs);
+}
+
+int PTO::plan_qmdp() {  // qmdp_policy_extractor.rs:23-35
+  cost_to_goals.assign(n_worlds, {});
+  for (size_t w = 0; w < n_worlds; ++w) {
+    std::vector<size_t> finals = reach.get_final_nodes_for_world(w);
+    if (finals.empty()) return 1;
+    cost_to_goals[w] = dijkstra(graph, (int)w, finals);
+  }
+  return 0;
+}
+
+bool PTO::react_qmdp(State start, const BeliefState& belief, double horizon, std::vector<std::vector<State>>& paths) {
+  // qmdp_policy_extractor.rs:38-123
+  if (belief.size() != n_worlds) return false;
+  size_t id = kdtree.nearest_neighbor(start).id;
+  std::vector<State> common;
+  double smallest = INF, acc = 0.0;
+  size_t guard = 0;
+  while (acc < horizon && smallest > 0.0) {
+    common.push_back(graph.nodes[id].state);
+    size_t best = 0;
+    double best_c = INF;
+    for (const PTOEdge& ce : graph.nodes[id].children) {
+      double c = 0.0;
+      for (size_t w = 0; w < n_worlds; ++w) c += cost_to_goals[w][ce.id] * belief[w];
+      if (c < best_c) { best = ce.id; best_c = c; }
+    }
+    acc += norm2(graph.nodes[id].state, graph.nodes[best].state);
+    id = best;
+    smallest = best_c;
+    if (++guard > 10 * graph.nodes.size() + 10) return false;  // the reference would loop forever
+  }
+  paths.assign(n_worlds, {});
+  for (size_t w = 0; w < n_worlds; ++w) {
+    paths[w] = common;
+    size_t cur = id;
+    guard = 0;
+    while (cost_to_goals[w][cur] > 0.0) {
+      paths[w].push_back(graph.nodes[cur].state);
+      size_t best = 0;
+      double smaller = INF;
+      for (const PTOEdge& ce : graph.nodes[cur].children)
+        if (cost_to_goals[w][ce.id] < smaller) { smaller = cost_to_goals[w][ce.id]; best = ce.id; }
+      cur = best;
+      if (++guard > 10 * graph.nodes.size() + 10) return false;
+    }
+  }
+  return true;
+}
+
+}  // namespace orc
