@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the po-rrt hot path on B200 (BASELINE.json metric, config c5).
+
+A "step" is one pass of batched edge-world validity over one batch of E synthetic edges against the synthetic
+8192 x 8192 door map (6 zones => 64 worlds).  One process per GPU; ranks shard the edges (independent units, map
+replicated, no data-path collective => weak scaling).
+
+  value  : edge-world validity checks/s, inputs resident in HBM, kernel launched through porrt_edge_validity_dev
+  e2e    : the same metric through the host-buffer C-ABI call porrt_edge_validity (pinned host buffers, H2D + D2H inside)
+  --impl reference : the reference's CPU path (oracle restatement; the Rust crate cannot be built here) on host cores
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "edge_world_validity_checks_per_s"
+UNIT = "edge-world checks/s"
+N_WORLDS = 64
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--edges", type=int, default=1 << 24, help="edges per GPU per step")
+    ap.add_argument("--map-size", type=int, default=8192)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="edges in the CPU-baseline sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip the kNN / PRM-build side measurements")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {"workload": "c5: synthetic %dx%d occupancy grid, 6 door zones = 64 worlds, edges a->b with |ab| ~ U[0,0.1] in [-1,1]^2"
+                        % (args.map_size, args.map_size),
+            "edges_per_gpu_per_step": args.edges, "map_seed": 1, "edge_seed": "2+rank",
+            "l2": "edge streams (32 B in + 12 B out per edge, %.0f MB per step) exceed L2; the 64 MiB fused grid is meant to stay L2-resident"
+                  % (args.edges * 44 / 1e6)}
+
+
+def make_inputs(args, rank):
+    from po_rrt_b200 import synth
+    occ, zones = synth.door_map(size=args.map_size, n_zones=6, seed=1)
+    a, b = synth.edges(args.edges, seed=2 + rank)
+    return occ, zones, a, b
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in rows for k in range(4) if len(r) >= 7 and r[3 + k].lower().startswith("active")})
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows)}
+
+
+def cpu_baseline(args, occ, zones, a, b, all_threads=True):
+    """the reference's CPU path restated (oracle/), timed on a bounded sample of the same workload"""
+    from oracle import pyoracle as O
+    omap = O.GridMap(occ, zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
+    n = min(args.cpu_sample, len(a))
+    sa, sb = np.ascontiguousarray(a[:n]), np.ascontiguousarray(b[:n])
+    threads = O.lib().orc_num_threads() if all_threads else 1
+    omap.edge_validity_timed(sa[:100000], sb[:100000], threads)  # warm-up
+    out, t = omap.edge_validity_timed(sa, sb, threads)
+    n1 = min(n, 400_000)
+    _, t1 = omap.edge_validity_timed(sa[:n1], sb[:n1], 1)
+    return {"value": n * N_WORLDS / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d of the step's edges, oracle C++ restatement (-O3, OpenMP over edges); the Rust reference is single-threaded "
+                      "and cannot be built here" % n,
+            "value_1thread": n1 * N_WORLDS / t1, "edges_per_s": n / t}, out, omap
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    occ, zones, a, b = make_inputs(args, 0)
+    from oracle import pyoracle as O
+    omap = O.GridMap(occ, zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
+    threads = O.lib().orc_num_threads()
+    n = min(args.cpu_sample, len(a))
+    sa, sb = np.ascontiguousarray(a[:n]), np.ascontiguousarray(b[:n])
+    for _ in range(max(1, args.warmup)):
+        omap.edge_validity_timed(sa[: n // 4], sb[: n // 4], threads)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = omap.edge_validity_timed(sa, sb, threads)
+        t += dt
+    value = n * N_WORLDS * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "each step = %d edges of the workload through the oracle C++ restatement with OpenMP "
+                                       "(reference Rust crate not buildable here: no cargo/rustc)" % n},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import po_rrt_b200 as P
+    from po_rrt_b200.api import _p
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: po_rrt_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    occ, zones, a, b = make_inputs(args, rank)
+    ctx = P.Context(local_rank)
+    pmap = P.Map(ctx, occ, [-1.0, -1.0], [1.0, 1.0])
+    pmap.add_zones(zones, 0.3)
+    assert pmap.n_worlds() == N_WORLDS
+    E = args.edges
+
+    # ---- device-resident arm
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    d_a, d_b = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    d_vid = torch.empty(E, dtype=torch.int32, device=dev)
+    d_mask = torch.empty(E, dtype=torch.int64, device=dev)
+    lib, h = ctx.lib, ctx.h
+
+    def step_dev():
+        ctx.check(lib.porrt_edge_validity_dev(h, d_a.data_ptr(), d_b.data_ptr(), E, d_vid.data_ptr(), d_mask.data_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    launches = ctx.launch_count() - launches0
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = E * world * N_WORLDS * args.steps / (ms_max * 1e-3)
+
+    # algorithmic bytes of one launch: 32 B endpoints + 8 B mask + 4 B id + 1 B per line pixel
+    ppm = args.map_size / 2.0
+    ai = torch.floor((args.map_size - 1) - (d_a[:, 1] + 1.0) * ppm); aj = torch.floor((d_a[:, 0] + 1.0) * ppm)
+    bi = torch.floor((args.map_size - 1) - (d_b[:, 1] + 1.0) * ppm); bj = torch.floor((d_b[:, 0] + 1.0) * ppm)
+    n_px = float((torch.maximum((ai - bi).abs(), (aj - bj).abs()) + 1).sum().item())
+    alg_bytes = 44.0 * E + n_px
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": alg_bytes, "mean_pixels_per_edge": n_px / E, "kernel": "edge_validity_kernel<DOOR>",
+                "kernel_ms": ms / args.steps}
+
+    # ---- end-to-end arm: host (pinned) buffers through the C ABI, H2D + kernel + D2H inside the timed region
+    ctx.set_stream(None)
+    h_a, h_b = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    h_vid = torch.empty(E, dtype=torch.int32).pin_memory()
+    h_mask = torch.empty(E, dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        ctx.check(lib.porrt_edge_validity(h, h_a.data_ptr(), h_b.data_ptr(), E, h_vid.data_ptr(), h_mask.data_ptr()))
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = E * world * N_WORLDS * e2e_steps / float(t_e2e.item())
+    # the e2e result must equal the device-resident one
+    assert torch.equal(h_vid, d_vid.cpu()) and torch.equal(h_mask, d_mask.cpu())
+
+    line = None
+    if rank == 0:
+        base, oracle_vid, _ = cpu_baseline(args, occ, zones, a, b)
+        n = len(oracle_vid)
+        assert np.array_equal(h_vid.numpy()[:n].astype(np.int64), oracle_vid), "GPU result differs from the oracle"
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+                "edges_per_s": value / N_WORLDS,
+                "roofline": roofline, "cpu_baseline": base,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * E, "d2h_bytes_per_step": 12 * E,
+                        "steps": e2e_steps, "edges_per_s": e2e_value / N_WORLDS},
+                "gpu_launches": int(launches), "clocks": clocks, "parity_checked_edges": n}
+
+    # ---- side measurements of the other BASELINE metrics (one shot each; not part of `value`)
+    if rank == 0 and not args.no_extras:
+        from po_rrt_b200 import synth
+        extras = {}
+        try:
+            V = Q = 1_000_000
+            pts, qs = synth.points(V, seed=3), synth.points(Q, seed=4)
+            r = 2.0 * (np.log(V) / V) ** 0.5
+            tree = P.KdTree(ctx, pts, cell_size=r)
+            tree.nearest_neighbors(qs[:1000], r)
+            t0 = time.perf_counter(); offs, ids = tree.nearest_neighbors(qs, r, cap=64 * Q); t1 = time.perf_counter()
+            extras["radius_queries_per_s_e2e"] = Q / (t1 - t0)
+            extras["radius_hits_per_query"] = len(ids) / Q
+            t0 = time.perf_counter(); tree.nearest_neighbor(qs); t1 = time.perf_counter()
+            extras["nearest_queries_per_s_e2e"] = Q / (t1 - t0)
+            t0 = time.perf_counter(); tree.knn(qs, 16); t1 = time.perf_counter()
+            extras["knn16_queries_per_s_e2e"] = Q / (t1 - t0)
+            for n_nodes in (10_000, 100_000):
+                prm = P.PRM(pmap)
+                t0 = time.perf_counter(); prm.grow_graph(pts[:n_nodes], 0.1, 2.0); t1 = time.perf_counter()
+                extras["prm_build_ms_V%d" % n_nodes] = 1e3 * (t1 - t0)
+                extras["prm_edges_V%d" % n_nodes] = int(len(prm.col))
+                extras["prm_phase_ms_V%d" % n_nodes] = [round(float(x), 3) for x in prm.phase_ms]
+        except Exception as e:  # side numbers must never take the headline down
+            extras["error"] = repr(e)
+        line["extras"] = extras
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

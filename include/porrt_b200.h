@@ -1,0 +1,172 @@
+/* porrt_b200.h -- C ABI of libporrt_b200.so: the B200 (sm_100a) implementation of po-rrt's data-parallel
+ * planning inner loop.  This is the drop-in boundary: a Rust `extern "C"` block
+ *  binds exactly these symbols behind a cargo feature; nothing here uses torch or C++ types.
+ *
+ * Conventions (modelled on the reference's only FFI, src/pto_c.rs):
+ *  - opaque handle created by porrt_ctx_create / freed by porrt_ctx_destroy     (pto_c.rs:63-103 new_xxx, delete_xxx)
+ *  - arrays are (pointer, length) pairs BORROWED from the caller, never freed    (pto_c.rs:33-41)
+ *  - validity results are signed: >= 0 validity id, < 0 invalid                  (pto_c.rs:17-18, :401-409)
+ *  - every call returns an int32 status (PORRT_OK == 0) and never aborts/unwinds; where the reference would
+ *    panic per element, the element's result carries the panic code instead.
+ *  - one ctx per host thread; calls on a ctx serialise on its CUDA stream.
+ *  - states are N = 2 (x, y) doubles, interleaved (AoS) exactly like the reference's [f64; 2].
+ *  - `*_dev` entry points take DEVICE pointers, enqueue on the ctx stream and do not synchronise.
+ *  - there is NO CPU fallback: every entry point fails with PORRT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PORRT_B200_H
+#define PORRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define PORRT_OK 0
+#define PORRT_ERR_INVALID_ARG 1
+#define PORRT_ERR_CUDA 2
+#define PORRT_ERR_NO_MAP 3      /* validity call before porrt_map_upload */
+#define PORRT_ERR_CAPACITY 4    /* output buffer too small; *out_total holds the required size */
+#define PORRT_ERR_PANIC 5       /* the reference would panic on this input as a whole (see porrt_last_error) */
+#define PORRT_ERR_UNSUPPORTED 6
+#define PORRT_ERR_NO_VERTICES 7 /* NN call before porrt_vertices_set */
+
+/* per-element validity codes (int32): >= 0 is a validity id into the world-validity table */
+#define PORRT_INVALID (-1)            /* Option::None: obstacle                          map_io.rs:491,511 */
+#define PORRT_PANIC_OOB (-2)          /* image::get_pixel out of bounds                  map_io.rs:167,226 */
+#define PORRT_PANIC_ZONE_UNWRAP (-3)  /* gray pixel without zone id: unwrap() on None    map_io.rs:172,231 */
+#define PORRT_PANIC_MULTI_ZONE (-4)   /* "multiple zone traversal not supported"         map_io.rs:233     */
+
+/* domain kinds */
+#define PORRT_DOMAIN_DOOR 0   /* map_io.rs `Map`: Z door zones, 2^Z worlds            */
+#define PORRT_DOMAIN_SHELF 1  /* map_shelves_io.rs `MapShelfDomain`: Z shelves, Z worlds */
+
+/* belief-graph node types (belief_graph.rs:12-17) */
+#define PORRT_NODE_UNKNOWN 0
+#define PORRT_NODE_ACTION 1
+#define PORRT_NODE_OBSERVATION 2
+
+typedef struct porrt_ctx porrt_ctx;
+
+/* ------------------------------------------------------------------ context */
+int32_t porrt_ctx_create(int32_t device, porrt_ctx** out_ctx);
+int32_t porrt_ctx_destroy(porrt_ctx* ctx);
+/* run all subsequent work of this ctx on an existing CUDA stream (e.g. torch's current stream); NULL = own stream */
+int32_t porrt_ctx_set_stream(porrt_ctx* ctx, void* cuda_stream);
+int32_t porrt_ctx_synchronize(porrt_ctx* ctx);
+const char* porrt_last_error(porrt_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t porrt_ctx_launch_count(porrt_ctx* ctx);
+const char* porrt_version(void);
+
+/* ------------------------------------------------------------------ maps
+ * Replaces Map::open + add_zones / init_without_zones (map_io.rs:82-145) and MapShelfDomain::open + add_zones
+ * (map_shelves_io.rs:80-148) for already-decoded 8-bit gray images (row-major, row 0 = top).
+ * zone == NULL: DOOR -> init_without_zones (1 world); SHELF -> no zones.  ppm = W / (up[0]-low[0]).
+ * Computes n_zones, n_worlds, zone centroids (integer mean, map_io.rs:147-163), the world-validity table
+ * (map_io.rs:120-126,198-214 / map_shelves_io.rs:113) and uploads a fused occupancy+zone grid to HBM. */
+int32_t porrt_map_upload(porrt_ctx* ctx, const uint8_t* occ, const uint8_t* zone, int32_t H, int32_t W,
+                         const double low[2], const double up[2], int32_t domain_kind, double visibility_distance);
+int32_t porrt_map_info(porrt_ctx* ctx, int32_t* n_zones, int32_t* n_worlds, int32_t* n_validities, int32_t* mask_words);
+int32_t porrt_map_zone_positions(porrt_ctx* ctx, double* out_xy /* [2*n_zones] */);
+/* world_validities(): out[n_validities * mask_words], bit w of word w/64 = world w (bitvec Lsb0)  map_io.rs:548-550 */
+int32_t porrt_map_world_validities(porrt_ctx* ctx, uint64_t* out_masks);
+
+/* PTOFuncs::state_validity, batched (map_io.rs:487-493, map_shelves_io.rs:464-469) */
+int32_t porrt_state_validity(porrt_ctx* ctx, const double* xy, int64_t n, int32_t* out_validity_id);
+/* PTOFuncs::transition_validator, batched (map_io.rs:495-513, map_shelves_io.rs:471-488): edge i runs
+ * from from_xy[2i..] to to_xy[2i..] IN THAT DIRECTION (Bresenham is direction dependent).
+ * out_world_mask (nullable): [n * mask_words] per-world validity bitvec = world_validities[id], 0 if invalid. */
+int32_t porrt_edge_validity(porrt_ctx* ctx, const double* from_xy, const double* to_xy, int64_t n,
+                            int32_t* out_validity_id, uint64_t* out_world_mask);
+/* geometric part of PTOFuncs::observe (map_io.rs:281-300, map_shelves_io.rs:242-265): bit z of out_zone_mask[i]
+ * = norm2(state_i, zone_pos[z]) < visibility && line of sight.  out_status[i] = 0 or the panic code (< -1). */
+int32_t porrt_visibility(porrt_ctx* ctx, const double* xy, int64_t n, uint64_t* out_zone_mask, int32_t* out_status);
+
+int32_t porrt_state_validity_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_validity_id_dev);
+int32_t porrt_edge_validity_dev(porrt_ctx* ctx, const double* from_xy_dev, const double* to_xy_dev, int64_t n,
+                                int32_t* out_validity_id_dev, uint64_t* out_world_mask_dev);
+int32_t porrt_visibility_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, uint64_t* out_zone_mask_dev,
+                             int32_t* out_status_dev);
+
+/* ------------------------------------------------------------------ nearest neighbours (nearest_neighbor.rs)
+ * The vertex set replaces the KdTree's contents: vertex i has id i (KdTree::add(state, id) with ids 0..n-1).
+ * cell_size <= 0 picks one from the vertex density. */
+int32_t porrt_vertices_set(porrt_ctx* ctx, const double* xy, int64_t n, double cell_size);
+int32_t porrt_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size,
+                               const double bbox_lo[2], const double bbox_hi[2]);
+int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n);
+
+/* KdTree::nearest_neighbors[_filtered] (nearest_neighbor.rs:94-126), batched: all ids j with
+ *   norm2(vertex_j, q_i) <= radius[i]   (inclusive, on the sqrt-ed f64 value)
+ *   and j < prefix_limit[i]             (if prefix_limit != NULL: the tree as it was before vertex prefix_limit[i] was added)
+ *   and bit world[i] of reach_mask[j]   (if reach_mask != NULL: the validator closure of pto.rs:74-77)
+ * Result: CSR -- out_offsets[m+1], out_ids ascending per query (the SET contract; kd pre-order is restored by
+ * porrt_kd_preorder_rank + porrt_segments_sort_by_key).  If the hits exceed cap: PORRT_ERR_CAPACITY, *out_total = needed. */
+int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const double* radius, int64_t m,
+                           const uint32_t* prefix_limit, const uint64_t* reach_mask, const uint32_t* world,
+                           int64_t* out_offsets, int32_t* out_ids, int64_t cap, int64_t* out_total);
+/* KdTree::nearest_neighbor[_filtered] (nearest_neighbor.rs:48-92), batched: argmin over (d2, id); out_id = -1 when
+ * nothing passes the filter (the reference then returns the root).  out_dist = norm2 of the winner.
+ * out_ties (nullable): number of vertices at exactly the winning squared distance (>1 = tie the kd order decides). */
+int32_t porrt_nearest(porrt_ctx* ctx, const double* q_xy, int64_t m, const uint64_t* reach_mask, const uint32_t* world,
+                      int32_t* out_id, double* out_dist, int32_t* out_ties);
+/* k nearest (no reference counterpart; BASELINE metric "kNN queries/sec"): ids/dists ascending by (d2, id), -1/inf padded */
+int32_t porrt_knn(porrt_ctx* ctx, const double* q_xy, int64_t m, int32_t k, int32_t* out_ids, double* out_dist);
+
+/* The kd-tree's pre-order rank of every vertex (the order KdTree::nearest_neighbors returns hits in):
+ * rank[i] = position of vertex i in a node-left-right walk of the tree obtained by inserting 0,1,..,n-1 in order. */
+int32_t porrt_kd_preorder_rank(porrt_ctx* ctx, const double* xy, int64_t n, int32_t* out_rank);
+
+/* ------------------------------------------------------------------ PRM (prm.rs)
+ * PRM::grow_graph for a given sample stream: node k = samples[k]; node 0 is the start (PRM::init or first sample).
+ * Reproduces add_sample (prm.rs:52-109): radius = heuristic_radius(k+1, ...) (computed on the host with libm),
+ * neighbours = vertices j < k within radius in kd pre-order, edges validated from neighbour -> new node.
+ * Output: children adjacency as CSR in the reference's insertion order (row k = valid earlier neighbours in kd
+ * pre-order, then later nodes ascending).  parents(k) == children(k) as sequences (prm.rs:99-106).
+ * out_col may be NULL to query *out_n_edges first. */
+int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
+                        int64_t* out_row_ptr /* [n+1] */, int32_t* out_col, int64_t cap, int64_t* out_n_edges,
+                        double* out_phase_ms /* nullable [8] */);
+
+/* ------------------------------------------------------------------ value backups
+ * CSR graph = children adjacency of a PTOGraph (pto_graph.rs:171-228): row_ptr[V+1], col[E], edge_vid[E], xy[2V],
+ * node_vid[V]; validities[n_validities * mask_words] as returned by porrt_map_world_validities. */
+
+/* QMdpPolicyExtractor::plan_qmdp (qmdp_policy_extractor.rs:23-35): for each world w a multi-source `dijkstra`
+ * (pto_graph.rs:275-303) over PTOGraphWorldView{world w} (:245-271) towards finals_ids[finals_ptr[w]..finals_ptr[w+1]].
+ * n_worlds == 0 with world_filter == 0 runs the plain-graph dijkstra once (finals_ptr[0..1]).
+ * out_dist[w * V + v], bit-identical to the reference's f64 results. out_sweeps (nullable) = relaxation sweeps used. */
+int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy,
+                          const int32_t* node_vid, const uint64_t* validities, int32_t n_validities, int32_t mask_words,
+                          int32_t n_worlds, const int64_t* finals_ptr, const int32_t* finals_ids,
+                          double* out_dist, int32_t* out_sweeps);
+
+/* PTO::build_belief_graph + compute_expected_costs_to_goals (pto.rs:185-275, belief_graph.rs:89-182) on the IMPLICIT
+ * belief graph (belief node id = node * B + belief):
+ *   beliefs[B * n_worlds]                reachable_belief_states, belief 0 = start belief (pto.rs:187)
+ *   visible_zone_mask[V]                 from porrt_visibility
+ *   finals: node ids + their finality masks [n_finals * mask_words]   (pto_reachability.rs:77-79)
+ * out_dist[V * B] = expected_costs_to_goals (inf where unreachable / non-existent), out_type[V * B] node types. */
+int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const int32_t* edge_vid,
+                        const double* xy, const int32_t* node_vid, const uint64_t* validities, int32_t n_validities,
+                        int32_t mask_words, int32_t n_worlds, const double* beliefs, int32_t B,
+                        const uint64_t* visible_zone_mask, const int32_t* finals_ids, const uint64_t* finals_masks,
+                        int32_t n_finals, double* out_dist, uint8_t* out_type, int32_t* out_sweeps,
+                        double* out_phase_ms /* nullable [4] */);
+
+/* belief_graph.rs:184-267 extract_policy on the implicit graph, walking out_dist/out_type of porrt_belief_vi.
+ * Policy nodes in creation order: out_node[k] = graph node, out_belief[k], out_parent[k] (-1 root), out_is_leaf[k].
+ * Returns PORRT_ERR_PANIC where the reference's asserts would fire; PORRT_ERR_CAPACITY when cap is too small. */
+int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_t* out_belief, int32_t* out_parent,
+                             uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost);
+
+/* reachable_belief_states (map_io.rs:515-546 / map_shelves_io.rs:490-520): host-side closure over the uploaded map's
+ * zones; out[cap * n_worlds]; *out_B = count (PORRT_ERR_CAPACITY if > cap). */
+int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PORRT_B200_H */

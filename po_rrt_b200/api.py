@@ -1,0 +1,374 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI (include/porrt_b200.h).
+
+Names follow the reference crate so that parity tests read like its own tests:
+  Map / MapShelfDomain      src/map_io.rs, src/map_shelves_io.rs  (PTOFuncs<2>: state_validity, transition_validator,
+                            world_validities, observe's visibility test, reachable_belief_states)
+  KdTree                    src/nearest_neighbor.rs               (nearest_neighbor[_filtered], nearest_neighbors)
+  PRM                       src/prm.rs                            (grow_graph)
+  plan_qmdp                 src/qmdp_policy_extractor.rs:23-35
+  plan_belief_space         src/pto.rs:152-182
+Everything is batched (numpy arrays in, numpy arrays out); a batch of one is the per-query trait method.
+Python here is only the driver: all computation happens in libporrt_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+INVALID, PANIC_OOB, PANIC_ZONE_UNWRAP, PANIC_MULTI_ZONE = -1, -2, -3, -4
+DOOR, SHELF = 0, 1
+NODE_UNKNOWN, NODE_ACTION, NODE_OBSERVATION = 0, 1, 2
+ERR_CAPACITY = 4
+
+
+class PorrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("porrt_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(x, cols=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+class Context:
+    """One GPU context (porrt_ctx).  Fails loudly when the library or a B200-class device is missing."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.porrt_ctx_create(device, C.byref(h))
+        if rc:
+            raise PorrtError(rc, "porrt_ctx_create failed (no sm_100 CUDA device? there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.porrt_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc:
+            raise PorrtError(rc, (self.lib.porrt_last_error(self.h) or b"").decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.porrt_ctx_set_stream(self.h, cuda_stream_ptr))
+
+    def synchronize(self):
+        self.check(self.lib.porrt_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return self.lib.porrt_ctx_launch_count(self.h)
+
+
+class _GridDomain:
+    KIND = DOOR
+
+    def __init__(self, ctx, occ, low, up):
+        self.ctx = ctx
+        self.occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        self.low, self.up = _f64(low), _f64(up)
+        self.zones = None
+        self.visibility_distance = 0.0
+        self._uploaded = False
+
+    # -- construction (Map::open / add_zones / init_without_zones)
+    @classmethod
+    def open(cls, ctx, filepath, low, up):
+        from .pgm import read_pgm
+        return cls(ctx, read_pgm(filepath), low, up)
+
+    def add_zones(self, zones, visibility_distance):
+        if isinstance(zones, str):
+            from .pgm import read_pgm
+            zones = read_pgm(zones)
+        self.zones = np.ascontiguousarray(zones, dtype=np.uint8)
+        assert self.zones.shape == self.occ.shape
+        self.visibility_distance = float(visibility_distance)
+        self._upload()
+
+    def init_without_zones(self):
+        self.zones = None
+        self._upload()
+
+    def _upload(self):
+        H, W = self.occ.shape
+        c = self.ctx
+        c.check(c.lib.porrt_map_upload(c.h, _p(self.occ), _p(self.zones), H, W, _p(self.low), _p(self.up), self.KIND,
+                                       self.visibility_distance))
+        nz, nw, nv, mw = (C.c_int32() for _ in range(4))
+        c.check(c.lib.porrt_map_info(c.h, C.byref(nz), C.byref(nw), C.byref(nv), C.byref(mw)))
+        self.n_zones, self._n_worlds, self.n_validities, self.mask_words = nz.value, nw.value, nv.value, mw.value
+        self._uploaded = True
+
+    def _need(self):
+        if not self._uploaded:
+            self._upload()
+
+    # -- PTOFuncs<2>
+    def n_worlds(self):
+        self._need()
+        return self._n_worlds
+
+    def world_validities_words(self):
+        self._need()
+        out = np.zeros((self.n_validities, self.mask_words), np.uint64)
+        self.ctx.check(self.ctx.lib.porrt_map_world_validities(self.ctx.h, _p(out)))
+        return out
+
+    def world_validities(self):
+        """Vec<WorldMask> as a [n_validities, n_worlds] 0/1 array"""
+        w = self.world_validities_words()
+        bits = np.zeros((self.n_validities, self._n_worlds), np.uint8)
+        for k in range(self._n_worlds):
+            bits[:, k] = (w[:, k // 64] >> np.uint64(k % 64)) & np.uint64(1)
+        return bits
+
+    def zone_positions(self):
+        self._need()
+        out = np.zeros((self.n_zones, 2))
+        self.ctx.check(self.ctx.lib.porrt_map_zone_positions(self.ctx.h, _p(out)))
+        return out
+
+    def state_validity(self, xy):
+        """Option<usize> per state: >= 0 validity id, -1 None, < -1 the reference's panic"""
+        self._need()
+        xy = _f64(xy, 2)
+        out = np.empty(len(xy), np.int32)
+        self.ctx.check(self.ctx.lib.porrt_state_validity(self.ctx.h, _p(xy), len(xy), _p(out)))
+        return out
+
+    def transition_validator(self, from_xy, to_xy, want_masks=False):
+        self._need()
+        f, t = _f64(from_xy, 2), _f64(to_xy, 2)
+        assert len(f) == len(t)
+        out = np.empty(len(f), np.int32)
+        masks = np.empty((len(f), self.mask_words), np.uint64) if want_masks else None
+        self.ctx.check(self.ctx.lib.porrt_edge_validity(self.ctx.h, _p(f), _p(t), len(f), _p(out), _p(masks)))
+        return (out, masks) if want_masks else out
+
+    def visible_zones(self, xy):
+        """geometric part of observe(): (zone bitmask, status) per state"""
+        self._need()
+        xy = _f64(xy, 2)
+        mask = np.empty(len(xy), np.uint64)
+        status = np.empty(len(xy), np.int32)
+        self.ctx.check(self.ctx.lib.porrt_visibility(self.ctx.h, _p(xy), len(xy), _p(mask), _p(status)))
+        return mask, status
+
+    def reachable_belief_states(self, start_belief, cap=1 << 16):
+        self._need()
+        b0 = _f64(start_belief)
+        out = np.empty((cap, self._n_worlds))
+        n = C.c_int32()
+        self.ctx.check(self.ctx.lib.porrt_reachable_belief_states(self.ctx.h, _p(b0), _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+class Map(_GridDomain):
+    """door/zone domain, 2^Z worlds (src/map_io.rs)"""
+    KIND = DOOR
+
+
+class MapShelfDomain(_GridDomain):
+    """object-in-one-of-Z-shelves domain, Z worlds (src/map_shelves_io.rs)"""
+    KIND = SHELF
+
+
+class KdTree:
+    """Batched stand-in for KdTree<2> (src/nearest_neighbor.rs): vertex i carries id i."""
+
+    def __init__(self, ctx, xy=None, cell_size=0.0):
+        self.ctx = ctx
+        self.n = 0
+        if xy is not None:
+            self.set(xy, cell_size)
+
+    def set(self, xy, cell_size=0.0):
+        xy = _f64(xy, 2)
+        self.xy = xy
+        self.n = len(xy)
+        self.ctx.check(self.ctx.lib.porrt_vertices_set(self.ctx.h, _p(xy), len(xy), float(cell_size)))
+
+    def nearest_neighbors(self, q, radius, prefix_limit=None, reach_mask=None, world=None, cap=None):
+        """radius search -> (offsets[m+1], ids) with ids ascending per query"""
+        q = _f64(q, 2)
+        m = len(q)
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float64), (m,)))
+        pl = None if prefix_limit is None else np.ascontiguousarray(prefix_limit, np.uint32)
+        rm = None if reach_mask is None else np.ascontiguousarray(reach_mask, np.uint64)
+        w = None if world is None else np.ascontiguousarray(world, np.uint32)
+        offs = np.empty(m + 1, np.int64)
+        cap = cap if cap is not None else max(1024, 64 * m)
+        total = C.c_int64()
+        while True:
+            ids = np.empty(cap, np.int32)
+            rc = self.ctx.lib.porrt_radius_query(self.ctx.h, _p(q), _p(r), m, _p(pl), _p(rm), _p(w), _p(offs), _p(ids), cap,
+                                                 C.byref(total))
+            if rc == ERR_CAPACITY:
+                cap = total.value
+                continue
+            self.ctx.check(rc)
+            return offs, ids[:total.value]
+
+    def nearest_neighbor(self, q, reach_mask=None, world=None):
+        """-> (id, dist, ties); id = -1 when the filter rejects everything (the reference returns the root)"""
+        q = _f64(q, 2)
+        m = len(q)
+        rm = None if reach_mask is None else np.ascontiguousarray(reach_mask, np.uint64)
+        w = None if world is None else np.ascontiguousarray(world, np.uint32)
+        ids, dist, ties = np.empty(m, np.int32), np.empty(m), np.empty(m, np.int32)
+        self.ctx.check(self.ctx.lib.porrt_nearest(self.ctx.h, _p(q), m, _p(rm), _p(w), _p(ids), _p(dist), _p(ties)))
+        return ids, dist, ties
+
+    def knn(self, q, k):
+        q = _f64(q, 2)
+        m = len(q)
+        ids, dist = np.empty((m, k), np.int32), np.empty((m, k))
+        self.ctx.check(self.ctx.lib.porrt_knn(self.ctx.h, _p(q), m, k, _p(ids), _p(dist)))
+        return ids, dist
+
+    def preorder_rank(self):
+        out = np.empty(self.n, np.int32)
+        self.ctx.check(self.ctx.lib.porrt_kd_preorder_rank(self.ctx.h, _p(self.xy), self.n, _p(out)))
+        return out
+
+
+class PRM:
+    """src/prm.rs: the fully batchable planner.  `fns` is an uploaded Map / MapShelfDomain."""
+
+    def __init__(self, fns):
+        self.fns = fns
+        self.ctx = fns.ctx
+        self.states = np.zeros((0, 2))
+        self.row_ptr = np.zeros(1, np.int64)
+        self.col = np.zeros(0, np.int32)
+        self.phase_ms = np.zeros(8)
+
+    def init(self, start):
+        self.states = _f64(start, 2)
+
+    def grow_graph(self, samples, max_step, search_radius):
+        """samples: the ContinuousSampler stream (n_iter states); nodes = [init state] + samples"""
+        self.fns._need()
+        xy = np.ascontiguousarray(np.vstack([self.states, _f64(samples, 2)]))
+        n = len(xy)
+        row_ptr = np.empty(n + 1, np.int64)
+        n_edges = C.c_int64()
+        cap = max(1024, 48 * n)
+        while True:
+            col = np.empty(cap, np.int32)
+            rc = self.ctx.lib.porrt_prm_build(self.ctx.h, _p(xy), n, max_step, search_radius, _p(row_ptr), _p(col), cap,
+                                              C.byref(n_edges), _p(self.phase_ms))
+            if rc == ERR_CAPACITY:
+                cap = n_edges.value
+                continue
+            self.ctx.check(rc)
+            break
+        self.states, self.row_ptr, self.col = xy, row_ptr, col[:n_edges.value].copy()
+        return self
+
+
+def dijkstra_worlds(ctx, row_ptr, col, xy, node_vid, validities_words, finals_per_world):
+    """plan_qmdp's loop: one dijkstra per world over PTOGraphWorldView -> cost_to_goals[W][V] (+ sweeps).
+    finals_per_world=None with validities_words=None runs the plain-graph dijkstra (pass finals as a flat list)."""
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    col = np.ascontiguousarray(col, np.int32)
+    xy = _f64(xy, 2)
+    V = len(xy)
+    sweeps = C.c_int32()
+    if validities_words is None:
+        fin = np.ascontiguousarray(finals_per_world, np.int32)
+        fptr = np.array([0, len(fin)], np.int64)
+        out = np.empty((1, V))
+        ctx.check(ctx.lib.porrt_sssp_worlds(ctx.h, V, _p(row_ptr), _p(col), _p(xy), None, None, 0, 0, 0, _p(fptr), _p(fin), _p(out),
+                                            C.byref(sweeps)))
+        return out[0], sweeps.value
+    vw = np.ascontiguousarray(validities_words, np.uint64)
+    nvid = np.ascontiguousarray(node_vid, np.int32)
+    W = len(finals_per_world)
+    fptr = np.zeros(W + 1, np.int64)
+    for w, f in enumerate(finals_per_world):
+        fptr[w + 1] = fptr[w] + len(f)
+    fin = np.ascontiguousarray(np.concatenate([np.asarray(f, np.int32) for f in finals_per_world]) if fptr[-1] else np.zeros(0, np.int32))
+    out = np.empty((W, V))
+    ctx.check(ctx.lib.porrt_sssp_worlds(ctx.h, V, _p(row_ptr), _p(col), _p(xy), _p(nvid), _p(vw), vw.shape[0], vw.shape[1], W,
+                                        _p(fptr), _p(fin), _p(out), C.byref(sweeps)))
+    return out, sweeps.value
+
+
+class BeliefPlan:
+    pass
+
+
+def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, final_ids, final_masks_words, beliefs=None):
+    """PTO::plan_belief_space (src/pto.rs:152-182) for a grown roadmap given as CSR (children adjacency).
+    Returns a BeliefPlan with beliefs, visible (zone masks), dist[V,B], type[V,B], policy arrays, expected_cost."""
+    ctx = fns.ctx
+    fns._need()
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    col = np.ascontiguousarray(col, np.int32)
+    edge_vid = np.ascontiguousarray(edge_vid, np.int32)
+    xy = _f64(xy, 2)
+    node_vid = np.ascontiguousarray(node_vid, np.int32)
+    V = len(xy)
+    plan = BeliefPlan()
+    plan.beliefs = fns.reachable_belief_states(start_belief) if beliefs is None else _f64(beliefs, fns.n_worlds())
+    B = len(plan.beliefs)
+    plan.visible, status = fns.visible_zones(xy)
+    if (status != 0).any():
+        raise PorrtError(5, "observe() would panic at node %d (code %d)" % (int(np.nonzero(status)[0][0]), int(status[status != 0][0])))
+    vw = fns.world_validities_words()
+    fin = np.ascontiguousarray(final_ids, np.int32)
+    fmask = np.ascontiguousarray(final_masks_words, np.uint64).reshape(len(fin), fns.mask_words)
+    plan.dist = np.empty((V, B))
+    plan.type = np.empty((V, B), np.uint8)
+    sweeps = C.c_int32()
+    plan.phase_ms = np.zeros(4)
+    ctx.check(ctx.lib.porrt_belief_vi(ctx.h, V, _p(row_ptr), _p(col), _p(edge_vid), _p(xy), _p(node_vid), _p(vw), vw.shape[0],
+                                      vw.shape[1], fns.n_worlds(), _p(plan.beliefs), B, _p(plan.visible), _p(fin), _p(fmask),
+                                      len(fin), _p(plan.dist), _p(plan.type), C.byref(sweeps), _p(plan.phase_ms)))
+    plan.sweeps = sweeps.value
+    cap = 4096
+    n, cost = C.c_int64(), C.c_double()
+    while True:
+        node, belief, parent = (np.empty(cap, np.int32) for _ in range(3))
+        leaf = np.empty(cap, np.uint8)
+        rc = ctx.lib.porrt_extract_policy(ctx.h, _p(node), _p(belief), _p(parent), _p(leaf), cap, C.byref(n), C.byref(cost))
+        if rc == ERR_CAPACITY:
+            cap = n.value
+            continue
+        ctx.check(rc)
+        break
+    k = n.value
+    plan.policy_node, plan.policy_belief, plan.policy_parent = node[:k].copy(), belief[:k].copy(), parent[:k].copy()
+    plan.policy_leaf = leaf[:k].copy()
+    plan.expected_cost = cost.value
+    return plan
+
+
+def words_from_bits(bits):
+    """[n, n_worlds] 0/1 -> [n, ceil(n_worlds/64)] u64 (bit w of word w/64 = world w)"""
+    bits = np.atleast_2d(np.asarray(bits, np.uint8))
+    n, nw = bits.shape
+    out = np.zeros((n, (nw + 63) // 64), np.uint64)
+    for w in range(nw):
+        out[:, w // 64] |= bits[:, w].astype(np.uint64) << np.uint64(w % 64)
+    return out

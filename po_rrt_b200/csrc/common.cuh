@@ -1,0 +1,152 @@
+// common.cuh -- context, error handling and device-buffer plumbing shared by the libporrt_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/porrt_b200.h"
+
+#define PORRT_API extern "C" __attribute__((visibility("default")))
+
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinBuf {  // grow-only pinned host staging
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+// Device-side description of an uploaded map (passed by value to kernels).
+struct MapDev {
+  const uint8_t* grid;  // fused code grid, tiled (see map.cu: tile_addr)
+  int32_t H, W;         // logical size
+  int32_t tiles_x;      // 128-byte tiles (16 x 8 px) per tile row
+  int32_t kind;         // PORRT_DOMAIN_*
+  int32_t free_vid;     // validity id of free space (n_validities - 1)
+  int32_t mask_words;
+  double low0, low1, ppm, hm1;  // hm1 = (double)(H - 1)
+};
+
+static const int MAX_SLOTS = 3;
+
+struct porrt_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;      // compute stream (own or borrowed)
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[MAX_SLOTS] = {}, ev_k[MAX_SLOTS] = {}, ev_out[MAX_SLOTS] = {};
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- map
+  bool has_map = false;
+  MapDev map = {};
+  int n_zones = 0, n_worlds = 0, n_validities = 0, mask_words = 1;
+  double visibility = 0.0;
+  std::vector<uint64_t> validities;     // [n_validities * mask_words]
+  std::vector<double> zone_pos;         // [2 * n_zones]
+  std::vector<uint64_t> zone_world_masks;  // DOOR: zones_to_worlds [n_zones * mask_words]
+  DevBuf d_grid, d_validities, d_zone_pos;
+  // host copies of the raw images are NOT kept: the product never walks pixels on the CPU.
+
+  // ---- vertices / cell grid (nn.cu)
+  int64_t n_vertices = 0;
+  double cell = 0, inv_cell = 0, org_x = 0, org_y = 0;
+  int32_t cells_x = 0, cells_y = 0;
+  DevBuf d_vxy_sorted, d_vid_sorted, d_cell_start, d_vxy, d_vcell;
+
+  // ---- last belief VI result (graph.cu), kept for porrt_extract_policy
+  struct BeliefState_ {
+    int64_t V = 0; int32_t B = 0, n_worlds = 0;
+    std::vector<int64_t> row_ptr; std::vector<int32_t> col, edge_vid; std::vector<double> xy;
+    std::vector<double> beliefs, dist; std::vector<uint8_t> type;
+    std::vector<uint8_t> exists;                  // [V*B]
+    std::vector<int32_t> node_obs_set;            // [V] index into obs tables
+    std::vector<int64_t> succ_ptr;                // [(n_sets*B)+1]
+    std::vector<int32_t> succ_belief;             // successor belief ids
+    std::vector<uint8_t> compat;                  // [B * n_validities]
+    int32_t n_validities = 0;
+  } bel;
+  std::vector<int32_t> bel_node_vid;
+
+  // ---- scratch
+  DevBuf scratch[12];
+  PinBuf pin[6];
+};
+
+#define CTX_CHECK(ctx) do { if (!(ctx)) return PORRT_ERR_INVALID_ARG; } while (0)
+
+static inline int32_t porrt_fail(porrt_ctx* ctx, int32_t code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                        \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _b[512];                                                                                \
+      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return porrt_fail(ctx, PORRT_ERR_CUDA, _b);                                                  \
+    }                                                                                              \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                          \
+  do {                                                                                             \
+    (ctx)->launches += 1;                                                                          \
+    CUDA_TRY(ctx, cudaGetLastError());                                                             \
+  } while (0)
+
+static inline bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// map.cu
+int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
+                              int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st);
+int32_t map_edge_validity_indexed_dev(porrt_ctx* ctx, const double* xy_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev,
+                                      int64_t n, int32_t* out_vid_dev, cudaStream_t st);
+// nn.cu helpers used by graph.cu
+int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi);
+int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
+                                 const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
+                                 int64_t* offsets_dev /* [m+1] */, DevBuf* ids_buf, int64_t* total_out);
+int32_t scan_exclusive_i64(porrt_ctx* ctx, const int32_t* counts_dev, int64_t n, int64_t* out_dev /* [n+1] */);
+int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev,
+                                 const int32_t* key_of_id_dev, int64_t key_limit);
+int32_t radix_sort_pairs(porrt_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);
+int bits_for(uint64_t max_value);
+int32_t kd_preorder_rank_host(const double* xy, int64_t n, int32_t* out_rank);

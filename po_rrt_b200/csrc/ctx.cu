@@ -1,0 +1,69 @@
+// ctx.cu -- context lifetime, stream plumbing (no compute kernels here).
+#include "common.cuh"
+
+PORRT_API const char* porrt_version(void) { return "porrt_b200 0.1 (sm_100a)"; }
+
+PORRT_API int32_t porrt_ctx_create(int32_t device, porrt_ctx** out_ctx) {
+  if (!out_ctx) return PORRT_ERR_INVALID_ARG;
+  *out_ctx = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return PORRT_ERR_CUDA;  // no CPU fallback: the library is unusable without a device
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PORRT_ERR_CUDA;
+  if (prop.major != 10) return PORRT_ERR_UNSUPPORTED;  // built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return PORRT_ERR_CUDA;
+  porrt_ctx* ctx = new porrt_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+  for (int s = 0; ok && s < MAX_SLOTS; ++s)
+    ok = cudaEventCreateWithFlags(&ctx->ev_in[s], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_k[s], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { delete ctx; return PORRT_ERR_CUDA; }
+  ctx->stream = ctx->own_stream;
+  *out_ctx = ctx;
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
+  CTX_CHECK(ctx);
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->d_grid.release(); ctx->d_validities.release(); ctx->d_zone_pos.release();
+  ctx->d_vxy_sorted.release(); ctx->d_vid_sorted.release(); ctx->d_cell_start.release();
+  ctx->d_vxy.release(); ctx->d_vcell.release();
+  for (DevBuf& b : ctx->scratch) b.release();
+  for (PinBuf& b : ctx->pin) b.release();
+  for (int s = 0; s < MAX_SLOTS; ++s) {
+    if (ctx->ev_in[s]) cudaEventDestroy(ctx->ev_in[s]);
+    if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);
+    if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  delete ctx;
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_ctx_set_stream(porrt_ctx* ctx, void* cuda_stream) {
+  CTX_CHECK(ctx);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_ctx_synchronize(porrt_ctx* ctx) {
+  CTX_CHECK(ctx);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PORRT_OK;
+}
+
+PORRT_API const char* porrt_last_error(porrt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+PORRT_API int64_t porrt_ctx_launch_count(porrt_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,762 @@
+// graph.cu -- roadmap construction and value backups.
+//
+//  * porrt_prm_build      : PRM::grow_graph / add_sample (reference src/prm.rs:38-109) as two device batches
+//                           (prefix-restricted radius queries, then edge checks) + CSR assembly in insertion order.
+//  * porrt_sssp_worlds    : dijkstra over PTOGraphWorldView per world (src/pto_graph.rs:245-303,
+//                           src/qmdp_policy_extractor.rs:23-35) as monotone pull relaxations to the fixed point.
+//  * porrt_belief_vi      : PTO::build_belief_graph + conditional_dijkstra (src/pto.rs:185-275,
+//                           src/belief_graph.rs:89-182) on the IMPLICIT belief graph (node*B + belief), never materialised.
+//  * porrt_extract_policy : extract_policy / get_best_expected_children (src/belief_graph.rs:184-267), host walk.
+//
+// Bit-exactness: dist values are the greatest fixed point of a monotone min-plus operator evaluated with the reference's
+// operand order (SURVEY 8(g) note 5), so any relaxation schedule that runs to quiescence yields identical f64 bit patterns.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <map>
+#include <thread>
+#include <unordered_map>
+
+#include "common.cuh"
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ================================================================================================ kd pre-order rank
+// The reference returns radius-search hits in node-left-right order of its incremental kd-tree
+// (nearest_neighbor.rs:101-117).  Inserting a leaf never reorders existing nodes, so the pre-order rank in the FINAL tree
+// orders every prefix correctly (SURVEY 8(g) note 4).  Host: O(n depth) descent with index links, then one walk.
+int32_t kd_preorder_rank_host(const double* xy, int64_t n, int32_t* out_rank) {
+  if (n <= 0) return PORRT_OK;
+  std::vector<int32_t> left((size_t)n, -1), right((size_t)n, -1);
+  for (int64_t i = 1; i < n; ++i) {
+    const double s[2] = {xy[2 * i], xy[2 * i + 1]};
+    int32_t cur = 0;
+    for (int axis = 0;; axis ^= 1) {  // KdTree::add, nearest_neighbor.rs:29-46: strictly-less goes left
+      int32_t* next = s[axis] < xy[2 * (int64_t)cur + axis] ? &left[cur] : &right[cur];
+      if (*next >= 0) cur = *next;
+      else { *next = (int32_t)i; break; }
+    }
+  }
+  std::vector<int32_t> stack;
+  stack.push_back(0);
+  int32_t r = 0;
+  while (!stack.empty()) {
+    int32_t v = stack.back();
+    stack.pop_back();
+    out_rank[v] = r++;
+    if (right[v] >= 0) stack.push_back(right[v]);
+    if (left[v] >= 0) stack.push_back(left[v]);
+  }
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_kd_preorder_rank(porrt_ctx* ctx, const double* xy, int64_t n, int32_t* out_rank) {
+  CTX_CHECK(ctx);
+  if (n < 0 || (n > 0 && (!xy || !out_rank))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "kd_preorder_rank: bad arguments");
+  return kd_preorder_rank_host(xy, n, out_rank);
+}
+
+// heuristic_radius (common.rs:357-369): host libm ln/pow like Rust's f64::ln/powf; never evaluated on the device.
+static double heuristic_radius(size_t n_nodes, double max_step, double search_radius, size_t dim) {
+  double n = (double)n_nodes;
+  double s = search_radius * std::pow(std::log(n) / n, 1.0 / (double)dim);
+  return s < max_step ? s : max_step;
+}
+
+// ================================================================================================ PRM build
+__global__ void seg_owner_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ owner) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= m) return;
+  const int64_t s = offsets[seg], e = offsets[seg + 1];
+  for (int64_t k = s + lane; k < e; k += 32) owner[k] = (int32_t)seg;
+}
+
+// ordered compaction of the valid hits of every segment + counts; one warp per segment
+__global__ void prm_compact_kernel(const int64_t* __restrict__ offsets, int64_t m, const int32_t* ids,
+                                   const int32_t* __restrict__ vid, int32_t* __restrict__ early_cnt,
+                                   int32_t* compact /* may alias ids: compaction in place */, int32_t* __restrict__ panic_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= m) return;
+  const int64_t s = offsets[seg], e = offsets[seg + 1];
+  int32_t cnt = 0;
+  for (int64_t k0 = s; k0 < e; k0 += 32) {
+    const int64_t k = k0 + lane;
+    int32_t v = k < e ? vid[k] : -1;
+    int32_t id = k < e ? ids[k] : 0;
+    if (v < -1) atomicExch(panic_flag, v);
+    unsigned ok = __ballot_sync(0xffffffffu, v >= 0);
+    __syncwarp();
+    if (v >= 0) compact[s + cnt + __popc(ok & ((1u << lane) - 1u))] = id;  // writes land at or before the reads of this round
+    cnt += __popc(ok);
+    __syncwarp();
+  }
+  if (lane == 0) early_cnt[seg] = cnt;
+}
+
+__global__ void prm_pairs_kernel(const int64_t* __restrict__ offsets, int64_t m, const int32_t* __restrict__ compact,
+                                 const int32_t* __restrict__ early_cnt, const int64_t* __restrict__ early_off,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* __restrict__ late_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= m) return;
+  const int64_t s = offsets[seg], o = early_off[seg];
+  const int32_t c = early_cnt[seg];
+  for (int32_t k = lane; k < c; k += 32) {
+    const int32_t j = compact[s + k];
+    keys[o + k] = (uint64_t)(uint32_t)j;   // sort key: the earlier node j ...
+    vals[o + k] = (uint32_t)seg;           // ... receives the later node as a child
+    atomicAdd(&late_cnt[j], 1);
+  }
+}
+
+__global__ void prm_rowptr_kernel(const int64_t* __restrict__ early_off, const int64_t* __restrict__ late_off, int64_t m,
+                                  int64_t* __restrict__ row_ptr) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= m) row_ptr[i] = early_off[i] + late_off[i];
+}
+
+__global__ void prm_fill_kernel(const int64_t* __restrict__ offsets, int64_t m, const int32_t* __restrict__ compact,
+                                const int32_t* __restrict__ early_cnt, const int64_t* __restrict__ late_off,
+                                const uint32_t* __restrict__ late_vals, const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= m) return;
+  const int64_t s = offsets[seg], r = row_ptr[seg];
+  const int32_t c = early_cnt[seg];
+  for (int32_t k = lane; k < c; k += 32) col[r + k] = compact[s + k];
+  const int64_t ls = late_off[seg], le = late_off[seg + 1];
+  for (int64_t k = ls + lane; k < le; k += 32) col[r + c + (k - ls)] = (int32_t)late_vals[k];
+}
+
+PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
+                                  int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n <= 0 || !samples_xy || !out_row_ptr || !out_n_edges) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "prm_build: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  double t0 = now_ms(), t1;
+  double ph[8] = {0};
+
+  // kd pre-order ranks on a host thread while the device does the geometric work
+  std::vector<int32_t> rank((size_t)n);
+  std::thread kd_thread([&]() { kd_preorder_rank_host(samples_xy, n, rank.data()); });
+
+  // radii: node k (k >= 1) queries with heuristic_radius(k + 1) -- n_nodes AFTER adding the new node (prm.rs:61-65)
+  std::vector<double> radius((size_t)n, 0.0);
+  std::vector<uint32_t> prefix((size_t)n);
+  {
+    int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (n < 20000) nt = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        for (int64_t k = t; k < n; k += nt) {
+          radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, max_step, search_radius, 2);
+          prefix[k] = (uint32_t)k;
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;
+
+  // device inputs
+  CUDA_TRY(ctx, ctx->d_vxy.ensure((size_t)n * 16));
+  DevBuf& aux = ctx->scratch[3];
+  CUDA_TRY(ctx, aux.ensure((size_t)n * (8 + 4 + 8 + 4 + 4 + 8 + 8 + 8) + 256));
+  char* b = aux.as<char>();
+  double* d_radius = (double*)b; b += (size_t)n * 8;
+  int64_t* d_off = (int64_t*)b; b += (size_t)(n + 1) * 8;
+  int64_t* d_early_off = (int64_t*)b; b += (size_t)(n + 1) * 8;
+  int64_t* d_late_off = (int64_t*)b; b += (size_t)(n + 1) * 8;
+  int64_t* d_row_ptr = (int64_t*)b; b += (size_t)(n + 1) * 8;
+  uint32_t* d_prefix = (uint32_t*)b; b += (size_t)n * 4;
+  int32_t* d_rank = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* d_early_cnt = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* d_late_cnt = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* d_flag = (int32_t*)b; b += 16;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vxy.p, samples_xy, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_radius, radius.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_prefix, prefix.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_late_cnt, 0, (size_t)n * 4, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
+
+  // 1. bin vertices; cell = the smallest radius in use (the last one) so late queries touch 3x3 cells
+  double cell = radius[n - 1] > 0 ? radius[n - 1] : max_step;
+  int32_t rc = nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell, nullptr, nullptr);
+  if (rc) { kd_thread.join(); return rc; }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
+
+  // 2. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
+  int64_t total = 0;
+  rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>(), d_radius, n, d_prefix, nullptr, nullptr, d_off, &ctx->scratch[2], &total);
+  if (rc) { kd_thread.join(); return rc; }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
+
+  // 3. restore the kd pre-order inside every neighbour list
+  kd_thread.join();
+  t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_rank, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  int32_t* d_ids = ctx->scratch[2].as<int32_t>();
+  rc = segments_sort_by_key_dev(ctx, d_off, n, d_ids, d_rank, n);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  t1 = now_ms(); ph[4] = t1 - t0; t0 = t1;
+
+  // 4. edge checks neighbour -> new node (prm.rs:91-96)
+  const int64_t tot1 = std::max<int64_t>(total, 1);
+  CUDA_TRY(ctx, ctx->scratch[0].ensure((size_t)tot1 * 4));  // owner (= new node id)
+  CUDA_TRY(ctx, ctx->scratch[1].ensure((size_t)tot1 * 4));  // validity ids
+  int32_t* d_owner = ctx->scratch[0].as<int32_t>();
+  int32_t* d_vid = ctx->scratch[1].as<int32_t>();
+  if (total > 0) {
+    seg_owner_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_owner);
+    LAUNCH_CHECK(ctx);
+    rc = map_edge_validity_indexed_dev(ctx, ctx->d_vxy.as<double>(), d_ids, d_owner, total, d_vid, st);
+    if (rc) return rc;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  t1 = now_ms(); ph[5] = t1 - t0; t0 = t1;
+
+  // 5. CSR in insertion order: row k = valid earlier neighbours (kd order), then later nodes ascending (prm.rs:99-106)
+  prm_compact_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_ids, d_vid, d_early_cnt, d_ids, d_flag);
+  LAUNCH_CHECK(ctx);
+  rc = scan_exclusive_i64(ctx, d_early_cnt, n, d_early_off);
+  if (rc) return rc;
+  int64_t n_half = 0;
+  int32_t flag = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&n_half, d_early_off + n, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (flag < -1) return porrt_fail(ctx, PORRT_ERR_PANIC, "prm_build: an edge check hit a reference panic (code " + std::to_string(flag) + ")");
+  const int64_t n_edges = 2 * n_half;
+  *out_n_edges = n_edges;
+  const int64_t half1 = std::max<int64_t>(n_half, 1);
+  CUDA_TRY(ctx, ctx->scratch[5].ensure((size_t)half1 * 8));
+  CUDA_TRY(ctx, ctx->scratch[6].ensure((size_t)half1 * 4));
+  CUDA_TRY(ctx, ctx->scratch[7].ensure((size_t)std::max<int64_t>(n_edges, 1) * 4));
+  uint64_t* d_keys = ctx->scratch[5].as<uint64_t>();
+  uint32_t* d_vals = ctx->scratch[6].as<uint32_t>();
+  int32_t* d_col = ctx->scratch[7].as<int32_t>();
+  prm_pairs_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_ids, d_early_cnt, d_early_off, d_keys, d_vals, d_late_cnt);
+  LAUNCH_CHECK(ctx);
+  rc = scan_exclusive_i64(ctx, d_late_cnt, n, d_late_off);
+  if (rc) return rc;
+  rc = radix_sort_pairs(ctx, d_keys, d_vals, n_half, bits_for((uint64_t)std::max<int64_t>(n - 1, 1)));  // stable: later nodes stay ascending
+  if (rc) return rc;
+  prm_rowptr_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(d_early_off, d_late_off, n, d_row_ptr);
+  LAUNCH_CHECK(ctx);
+  prm_fill_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_ids, d_early_cnt, d_late_off, d_vals, d_row_ptr, d_col);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, d_row_ptr, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  int32_t status = PORRT_OK;
+  if (out_col && cap >= n_edges) {
+    if (n_edges > 0) CUDA_TRY(ctx, cudaMemcpyAsync(out_col, d_col, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+  } else {
+    status = porrt_fail(ctx, PORRT_ERR_CAPACITY, "prm_build: out_col too small");
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  t1 = now_ms(); ph[6] = t1 - t0;
+  ph[7] = (double)total;
+  if (out_phase_ms) memcpy(out_phase_ms, ph, sizeof(ph));
+  return status;
+}
+
+// ================================================================================================ SSSP per world
+__global__ void edge_cost_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy,
+                                 int64_t V, double* __restrict__ cost) {
+  // norm2(u, v) (common.rs:203-213) for every CSR edge u -> v; one warp per row
+  const int lane = threadIdx.x & 31;
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= V) return;
+  const double2 a = xy[u];
+  for (int64_t e = row_ptr[u] + lane; e < row_ptr[u + 1]; e += 32) {
+    const double2 c = xy[col[e]];
+    const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
+    cost[e] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  }
+}
+
+// One pull sweep: dist[u][w] = min(dist[u][w], min_{v in children(u)} dist[v][w] + cost(u,v)) for u valid in world w.
+// Layout dist[u * W + w]: the W threads of a node read its CSR row once (broadcast) and the children's rows coalesced.
+__global__ void __launch_bounds__(256) sssp_sweep_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                         const double* __restrict__ cost, const uint8_t* __restrict__ node_ok /* [V*W] */,
+                                                         int64_t V, int W, double* __restrict__ dist, int32_t* __restrict__ changed) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V * W) return;
+  const int64_t u = t / W;
+  const int w = (int)(t - u * W);
+  if (!node_ok[t]) return;  // PTOGraphWorldView::parents filters by the PARENT node's validity (pto_graph.rs:264-270)
+  double best = dist[t];
+  const double old = best;
+  for (int64_t e = row_ptr[u]; e < row_ptr[u + 1]; ++e) {
+    const double alt = __dadd_rn(dist[(int64_t)col[e] * W + w], cost[e]);  // dist[v] + cost(u, v), pto_graph.rs:293
+    if (alt < best) best = alt;
+  }
+  if (best < old) { dist[t] = best; *changed = 1; }
+}
+
+__global__ void transpose_dist_kernel(const double* __restrict__ in /* [V][W] */, int64_t V, int W, double* __restrict__ out /* [W][V] */) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V * W) return;
+  const int64_t u = t / W;
+  const int w = (int)(t - u * W);
+  out[(int64_t)w * V + u] = in[t];
+}
+
+PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy,
+                                    const int32_t* node_vid, const uint64_t* validities, int32_t n_validities, int32_t mask_words,
+                                    int32_t n_worlds, const int64_t* finals_ptr, const int32_t* finals_ids,
+                                    double* out_dist, int32_t* out_sweeps) {
+  CTX_CHECK(ctx);
+  if (V <= 0 || !row_ptr || !xy || !finals_ptr || !out_dist || n_worlds < 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: bad arguments");
+  const bool world_view = n_worlds > 0;
+  if (world_view && (!node_vid || !validities || n_validities <= 0 || mask_words <= 0)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: world view needs validities");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int W = world_view ? n_worlds : 1;
+  const int64_t E = row_ptr[V];
+  if (E > 0 && !col) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: null col");
+  // host prep: validity per (node, world) and the initial distances (inf, 0 at the finals)
+  const double INF = std::numeric_limits<double>::infinity();
+  std::vector<uint8_t> ok((size_t)V * W, 1);
+  std::vector<double> dist0((size_t)V * W, INF);
+  if (world_view)
+    for (int64_t u = 0; u < V; ++u) {
+      const int32_t vid = node_vid[u];
+      if (vid < 0 || vid >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: node validity id out of range");
+      for (int w = 0; w < W; ++w) ok[(size_t)u * W + w] = (validities[(size_t)vid * mask_words + w / 64] >> (w % 64)) & 1;
+    }
+  for (int w = 0; w < W; ++w)
+    for (int64_t k = finals_ptr[w]; k < finals_ptr[w + 1]; ++k) {
+      const int32_t f = finals_ids[k];
+      if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: final id out of range");
+      dist0[(size_t)f * W + w] = 0.0;
+    }
+  DevBuf& g = ctx->scratch[3];
+  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 16 + (size_t)V * W * 17 + 256;
+  CUDA_TRY(ctx, g.ensure(need));
+  char* b = g.as<char>();
+  int64_t* d_row = (int64_t*)b; b += (size_t)(V + 1) * 8;
+  double* d_cost = (double*)b; b += (size_t)E * 8;
+  double* d_xy = (double*)b; b += (size_t)V * 16;
+  double* d_dist = (double*)b; b += (size_t)V * W * 8;
+  double* d_out = (double*)b; b += (size_t)V * W * 8;
+  int32_t* d_col = (int32_t*)b; b += (size_t)E * 4;
+  int32_t* d_changed = (int32_t*)b; b += 16;
+  uint8_t* d_ok = (uint8_t*)b;
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_dist, dist0.data(), (size_t)V * W * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_ok, ok.data(), (size_t)V * W, cudaMemcpyHostToDevice, st));
+  edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
+  LAUNCH_CHECK(ctx);
+  int sweeps = 0;
+  const int BATCH = 8;  // sweeps between two convergence checks
+  for (;;) {
+    CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
+    for (int k = 0; k < BATCH; ++k) {
+      sssp_sweep_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_row, d_col, d_cost, d_ok, V, W, d_dist, d_changed);
+      LAUNCH_CHECK(ctx);
+    }
+    sweeps += BATCH;
+    int32_t changed = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (!changed) break;
+    if (sweeps > 4 * V + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp_worlds: no convergence");
+  }
+  transpose_dist_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_dist, V, W, d_out);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_out, (size_t)V * W * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (out_sweeps) *out_sweeps = sweeps;
+  return PORRT_OK;
+}
+
+// ================================================================================================ belief-space VI
+// host-side belief algebra (common.rs:188-190,256-264,352-355; map_io.rs:244-278; map_shelves_io.rs:206-239)
+typedef std::vector<double> Belief;
+static double transition_probability(const double* parent, const double* child, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s = s + (child[i] > 0.0 ? parent[i] : 0.0);
+  return s;
+}
+static bool is_compatible(const double* b, const uint64_t* mask, int n) {
+  for (int i = 0; i < n; ++i)
+    if (b[i] > 0.0 && !((mask[i / 64] >> (i % 64)) & 1)) return false;
+  return true;
+}
+static uint64_t belief_hash(const double* bs, int n) {
+  uint64_t h = 0, p10 = 1;
+  for (int i = 0; i < n; ++i) {
+    double r = std::round(bs[i] * 1000.0);
+    uint64_t v = (r <= 0.0 || std::isnan(r)) ? 0 : (r >= 18446744073709551615.0 ? UINT64_MAX : (uint64_t)r);
+    h += (p10 + 1) * v;  // wraps like a release build of the reference
+    p10 *= 10;
+  }
+  return h;
+}
+static void successor_beliefs(const porrt_ctx* ctx, const Belief& b, int zone, std::vector<Belief>& out) {
+  const int n = (int)b.size();
+  Belief first = b, second = b;
+  for (int w = 0; w < n; ++w) {
+    bool in_zone_world;
+    if (ctx->map.kind == PORRT_DOMAIN_DOOR) in_zone_world = (ctx->zone_world_masks[(size_t)zone * ctx->mask_words + w / 64] >> (w % 64)) & 1;
+    else in_zone_world = (w == zone);
+    if (ctx->map.kind == PORRT_DOMAIN_DOOR) {  // [closed, open]
+      first[w] = in_zone_world ? 0.0 : b[w];
+      second[w] = in_zone_world ? b[w] : 0.0;
+    } else {                                   // [there, not there]
+      first[w] = in_zone_world ? b[w] : 0.0;
+      second[w] = in_zone_world ? 0.0 : b[w];
+    }
+  }
+  for (Belief* c : {&first, &second}) {
+    double sum = 0.0;
+    for (double p : *c) sum = sum + p;
+    bool nan = false;
+    for (double& p : *c) { p /= sum; nan |= std::isnan(p); }
+    if (!nan) out.push_back(*c);
+  }
+}
+
+PORRT_API int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (!start_belief || !out_B) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "reachable_belief_states: bad arguments");
+  const int nw = ctx->n_worlds, nz = ctx->n_zones;
+  std::vector<Belief> reachable;
+  std::unordered_map<uint64_t, int> hashes;
+  std::vector<std::pair<Belief, std::vector<int>>> lifo;
+  Belief b0(start_belief, start_belief + nw);
+  reachable.push_back(b0);
+  std::vector<int> all(nz);
+  for (int z = 0; z < nz; ++z) all[z] = z;
+  lifo.push_back({b0, all});
+  std::vector<Belief> succ;
+  while (!lifo.empty()) {
+    auto top = lifo.back();
+    lifo.pop_back();
+    for (int zone : top.second) {
+      std::vector<int> remaining;
+      for (int z : top.second) if (z != zone) remaining.push_back(z);
+      succ.clear();
+      successor_beliefs(ctx, top.first, zone, succ);
+      for (const Belief& s : succ) {
+        bool known = false;  // `reachable_beliefs.contains(successor)`: exact f64 equality
+        for (const Belief& r : reachable) if (r == s) { known = true; break; }
+        if (!known) {
+          uint64_t h = belief_hash(s.data(), nw);
+          if (!hashes.count(h)) { hashes[h] = 1; reachable.push_back(s); }
+          lifo.push_back({s, remaining});
+        }
+      }
+    }
+  }
+  *out_B = (int32_t)reachable.size();
+  if ((int)reachable.size() > cap || !out) return porrt_fail(ctx, PORRT_ERR_CAPACITY, "reachable_belief_states: cap too small");
+  for (size_t k = 0; k < reachable.size(); ++k) memcpy(out + k * nw, reachable[k].data(), (size_t)nw * 8);
+  return PORRT_OK;
+}
+
+struct BeliefDev {
+  const int64_t* row_ptr; const int32_t* col; const int32_t* edge_vid; const double* cost;
+  const int32_t* node_vid; const int32_t* node_set;
+  const uint8_t* compat;      // [B][n_validities]
+  const int64_t* succ_ptr;    // [n_sets * B + 1]
+  const int32_t* succ_belief; const double* succ_p;
+  int64_t V; int32_t B, n_validities;
+};
+
+// node typing (pto.rs:209-255): Observation iff an observation edge to an EXISTING successor belief node exists,
+// else Action iff some admissible geometric child exists, else Unknown.
+__global__ void belief_type_kernel(BeliefDev g, uint8_t* __restrict__ type) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.V * g.B) return;
+  const int64_t n = t / g.B;
+  const int b = (int)(t - n * g.B);
+  const int32_t nv = g.node_vid[n];
+  uint8_t ty = PORRT_NODE_UNKNOWN;
+  if (g.compat[(int64_t)b * g.n_validities + nv]) {
+    const int64_t sp = (int64_t)g.node_set[n] * g.B + b;
+    for (int64_t k = g.succ_ptr[sp]; k < g.succ_ptr[sp + 1]; ++k)
+      if (g.compat[(int64_t)g.succ_belief[k] * g.n_validities + nv]) { ty = PORRT_NODE_OBSERVATION; break; }
+    if (ty == PORRT_NODE_UNKNOWN)
+      for (int64_t e = g.row_ptr[n]; e < g.row_ptr[n + 1]; ++e)
+        if (g.compat[(int64_t)b * g.n_validities + g.node_vid[g.col[e]]] && g.compat[(int64_t)b * g.n_validities + g.edge_vid[e]]) { ty = PORRT_NODE_ACTION; break; }
+  } else {
+    ty = 255;  // belief node does not exist (node_to_belief_nodes[id][belief] == None)
+  }
+  type[t] = ty;
+}
+
+// One pull sweep of conditional_dijkstra's backup (belief_graph.rs:117-146):
+//   Action     : alt = min_v  norm2(u,v) + dist[v]                      (:121-124)
+//   Observation: alt = sum_vv p(u->vv) * (0.0 + dist[vv]) in stored order (:125-135; obs edges keep the state => cost 0.0)
+__global__ void __launch_bounds__(256) belief_sweep_kernel(BeliefDev g, const uint8_t* __restrict__ type, double* __restrict__ dist,
+                                                           int32_t* __restrict__ changed) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.V * g.B) return;
+  const uint8_t ty = type[t];
+  if (ty != PORRT_NODE_ACTION && ty != PORRT_NODE_OBSERVATION) return;
+  const int64_t n = t / g.B;
+  const int b = (int)(t - n * g.B);
+  const double old = dist[t];
+  double alt;
+  if (ty == PORRT_NODE_OBSERVATION) {
+    const int32_t nv = g.node_vid[n];
+    const int64_t sp = (int64_t)g.node_set[n] * g.B + b;
+    alt = 0.0;
+    for (int64_t k = g.succ_ptr[sp]; k < g.succ_ptr[sp + 1]; ++k) {
+      const int32_t cb = g.succ_belief[k];
+      if (!g.compat[(int64_t)cb * g.n_validities + nv]) continue;
+      alt = __dadd_rn(alt, __dmul_rn(g.succ_p[k], __dadd_rn(0.0, dist[n * g.B + cb])));
+    }
+  } else {
+    alt = INFINITY;
+    const uint8_t* cm = g.compat + (int64_t)b * g.n_validities;
+    for (int64_t e = g.row_ptr[n]; e < g.row_ptr[n + 1]; ++e) {
+      const int32_t c = g.col[e];
+      if (!cm[g.node_vid[c]] || !cm[g.edge_vid[e]]) continue;
+      const double a = __dadd_rn(g.cost[e], dist[(int64_t)c * g.B + b]);
+      if (a < alt) alt = a;
+    }
+  }
+  if (alt < old) { dist[t] = alt; *changed = 1; }
+}
+
+PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const int32_t* edge_vid,
+                                  const double* xy, const int32_t* node_vid, const uint64_t* validities, int32_t n_validities,
+                                  int32_t mask_words, int32_t n_worlds, const double* beliefs, int32_t B,
+                                  const uint64_t* visible_zone_mask, const int32_t* finals_ids, const uint64_t* finals_masks,
+                                  int32_t n_finals, double* out_dist, uint8_t* out_type, int32_t* out_sweeps, double* out_phase_ms) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (V <= 0 || B <= 0 || !row_ptr || !xy || !node_vid || !validities || !beliefs || !visible_zone_mask || !out_dist || n_worlds != ctx->n_worlds ||
+      mask_words != ctx->mask_words || n_validities <= 0 || (n_finals > 0 && (!finals_ids || !finals_masks)))
+    return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  double t0 = now_ms(), t1, ph[4] = {0};
+  const int64_t E = row_ptr[V];
+  if (E > 0 && (!col || !edge_vid)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: null col/edge_vid");
+  const int nw = n_worlds;
+  // compute_compatibility (common.rs:266-276)
+  std::vector<uint8_t> compat((size_t)B * n_validities);
+  for (int b = 0; b < B; ++b)
+    for (int v = 0; v < n_validities; ++v) compat[(size_t)b * n_validities + v] = is_compatible(beliefs + (size_t)b * nw, validities + (size_t)v * mask_words, nw);
+  // belief ids by hash (belief_graph.rs:75-87); collisions are a reference panic
+  std::unordered_map<uint64_t, int> hash_to_id;
+  std::vector<uint64_t> bhash(B);
+  for (int b = 0; b < B; ++b) { bhash[b] = belief_hash(beliefs + (size_t)b * nw, nw); hash_to_id[bhash[b]] = b; }
+  if ((int)hash_to_id.size() != B) return porrt_fail(ctx, PORRT_ERR_PANIC, "collision when hashing the belief states! (belief_graph.rs:84)");
+  // observation successor tables, one per distinct set of visible zones (observe_impl is a function of that set only)
+  std::map<uint64_t, int> set_index;
+  std::vector<int32_t> node_set((size_t)V);
+  std::vector<uint64_t> sets;
+  for (int64_t n = 0; n < V; ++n) {
+    auto it = set_index.find(visible_zone_mask[n]);
+    if (it == set_index.end()) { it = set_index.emplace(visible_zone_mask[n], (int)sets.size()).first; sets.push_back(visible_zone_mask[n]); }
+    node_set[n] = it->second;
+  }
+  std::vector<int64_t> succ_ptr(sets.size() * (size_t)B + 1, 0);
+  std::vector<int32_t> succ_belief;
+  std::vector<double> succ_p;
+  std::vector<Belief> cur, nxt;
+  for (size_t s = 0; s < sets.size(); ++s)
+    for (int b = 0; b < B; ++b) {
+      cur.assign(1, Belief(beliefs + (size_t)b * nw, beliefs + (size_t)(b + 1) * nw));
+      for (int z = 0; z < ctx->n_zones; ++z)
+        if ((sets[s] >> z) & 1) {  // zones ascending, every current belief split in turn (map_io.rs:285-297)
+          nxt.clear();
+          for (const Belief& bel : cur) successor_beliefs(ctx, bel, z, nxt);
+          cur.swap(nxt);
+        }
+      for (const Belief& child : cur) {
+        const uint64_t h = belief_hash(child.data(), nw);
+        if (h == bhash[b]) continue;  // pto.rs:216
+        auto it = hash_to_id.find(h);
+        if (it == hash_to_id.end()) return porrt_fail(ctx, PORRT_ERR_PANIC, "no id corresponding to this belief state! (belief_graph.rs:69)");
+        succ_belief.push_back(it->second);
+        // transition_probability on the STORED reachable belief states (belief_graph.rs:128)
+        succ_p.push_back(transition_probability(beliefs + (size_t)b * nw, beliefs + (size_t)it->second * nw, nw));
+      }
+      succ_ptr[s * (size_t)B + b + 1] = (int64_t)succ_belief.size();
+    }
+  for (double p : succ_p)
+    if (!(p > 0.0)) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p > 0.0) (belief_graph.rs:130)");
+  // initial distances: 0 at final belief nodes (pto.rs:261-271)
+  const double INF = std::numeric_limits<double>::infinity();
+  std::vector<double> dist0((size_t)V * B, INF);
+  for (int k = 0; k < n_finals; ++k) {
+    const int32_t f = finals_ids[k];
+    if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: final id out of range");
+    for (int b = 0; b < B; ++b)
+      if (compat[(size_t)b * n_validities + node_vid[f]] && is_compatible(beliefs + (size_t)b * nw, finals_masks + (size_t)k * mask_words, nw)) dist0[(size_t)f * B + b] = 0.0;
+  }
+  t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;
+
+  DevBuf& g = ctx->scratch[3];
+  const size_t n_succ = succ_belief.size();
+  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 16 + (size_t)V * 24 + succ_ptr.size() * 8 + n_succ * 12 + compat.size() + (size_t)V * B * 9 + 512;
+  CUDA_TRY(ctx, g.ensure(need));
+  char* b = g.as<char>();
+  auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
+  int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
+  double* d_cost = (double*)take((size_t)E * 8);
+  double* d_xy = (double*)take((size_t)V * 16);
+  int64_t* d_succ_ptr = (int64_t*)take(succ_ptr.size() * 8);
+  double* d_succ_p = (double*)take(n_succ * 8);
+  double* d_dist = (double*)take((size_t)V * B * 8);
+  int32_t* d_col = (int32_t*)take((size_t)E * 4);
+  int32_t* d_evid = (int32_t*)take((size_t)E * 4);
+  int32_t* d_nvid = (int32_t*)take((size_t)V * 4);
+  int32_t* d_nset = (int32_t*)take((size_t)V * 4);
+  int32_t* d_succ_b = (int32_t*)take(n_succ * 4);
+  int32_t* d_changed = (int32_t*)take(16);
+  uint8_t* d_compat = (uint8_t*)take(compat.size());
+  uint8_t* d_type = (uint8_t*)take((size_t)V * B);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (E) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_evid, edge_vid, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_nvid, node_vid, (size_t)V * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_nset, node_set.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_ptr, succ_ptr.data(), succ_ptr.size() * 8, cudaMemcpyHostToDevice, st));
+  if (n_succ) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_b, succ_belief.data(), n_succ * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_p, succ_p.data(), n_succ * 8, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, compat.data(), compat.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_dist, dist0.data(), (size_t)V * B * 8, cudaMemcpyHostToDevice, st));
+  edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
+  LAUNCH_CHECK(ctx);
+  BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, d_succ_ptr, d_succ_b, d_succ_p, V, B, n_validities};
+  const int blocks = div_up(V * (int64_t)B, 256);
+  belief_type_kernel<<<blocks, 256, 0, st>>>(gd, d_type);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
+  int sweeps = 0;
+  const int BATCH = 8;
+  for (;;) {
+    CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
+    for (int k = 0; k < BATCH; ++k) {
+      belief_sweep_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_dist, d_changed);
+      LAUNCH_CHECK(ctx);
+    }
+    sweeps += BATCH;
+    int32_t changed = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (!changed) break;
+    if (sweeps > 4 * V * (int64_t)B + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "belief_vi: no convergence");
+  }
+  t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
+  // results: to the caller and retained for porrt_extract_policy
+  auto& R = ctx->bel;
+  R.V = V; R.B = B; R.n_worlds = nw; R.n_validities = n_validities;
+  R.row_ptr.assign(row_ptr, row_ptr + V + 1);
+  R.col.assign(col, col + E); R.edge_vid.assign(edge_vid, edge_vid + E);
+  R.xy.assign(xy, xy + 2 * V);
+  R.beliefs.assign(beliefs, beliefs + (size_t)B * nw);
+  R.dist.resize((size_t)V * B); R.type.resize((size_t)V * B);
+  R.node_obs_set = node_set; R.succ_ptr = succ_ptr; R.succ_belief = succ_belief; R.compat = compat;
+  R.exists.assign((size_t)V * B, 0);
+  CUDA_TRY(ctx, cudaMemcpyAsync(R.dist.data(), d_dist, (size_t)V * B * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(R.type.data(), d_type, (size_t)V * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  std::vector<int32_t> nvid(node_vid, node_vid + V);
+  for (int64_t n = 0; n < V; ++n)
+    for (int bb = 0; bb < B; ++bb) {
+      R.exists[(size_t)n * B + bb] = compat[(size_t)bb * n_validities + nvid[n]];
+      if (R.type[(size_t)n * B + bb] == 255) R.type[(size_t)n * B + bb] = PORRT_NODE_UNKNOWN;  // the reference adds the node anyway, typed Unknown (pto.rs:199)
+    }
+  memcpy(out_dist, R.dist.data(), (size_t)V * B * 8);
+  if (out_type) memcpy(out_type, R.type.data(), (size_t)V * B);
+  if (out_sweeps) *out_sweeps = sweeps;
+  t1 = now_ms(); ph[3] = t1 - t0;
+  if (out_phase_ms) memcpy(out_phase_ms, ph, sizeof(ph));
+  // keep node/edge validity ids for the policy walk
+  R.edge_vid.assign(edge_vid, edge_vid + E);
+  ctx->bel_node_vid = nvid;
+  return PORRT_OK;
+}
+
+// ================================================================================================ policy extraction
+PORRT_API int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_t* out_belief, int32_t* out_parent,
+                                       uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost) {
+  CTX_CHECK(ctx);
+  auto& R = ctx->bel;
+  if (R.V <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "extract_policy: run porrt_belief_vi first");
+  const int B = R.B, nw = R.n_worlds, nv = R.n_validities;
+  const std::vector<int32_t>& nvid = ctx->bel_node_vid;
+  auto state = [&](int64_t n) { return &R.xy[2 * n]; };
+  auto norm2 = [&](const double* a, const double* b) {
+    double d2 = 0.0;
+    for (int k = 0; k < 2; ++k) { double dx = b[k] - a[k]; d2 += dx * dx; }
+    return std::sqrt(d2);
+  };
+  struct PN { int32_t node, belief, parent; uint8_t leaf; };
+  std::vector<PN> pol;
+  std::vector<std::pair<int64_t, int64_t>> lifo;  // (policy node, belief node id)
+  pol.push_back({0, 0, -1, 0});
+  lifo.push_back({0, 0});
+  struct Child { int64_t id; double cost_to_child, expected_from_child; };
+  while (!lifo.empty()) {
+    auto top = lifo.back();
+    lifo.pop_back();
+    const int64_t bn = top.second, n = bn / B;
+    const int b = (int)(bn % B);
+    // children of the belief node in stored order (observation edges first if Observation, else action edges)
+    std::map<int32_t, std::vector<Child>> by_belief;  // BTreeMap keyed by child.belief_id (belief_graph.rs:228-241)
+    const uint8_t ty = R.type[(size_t)bn];
+    if (ty == PORRT_NODE_OBSERVATION) {
+      const int64_t sp = (int64_t)R.node_obs_set[n] * B + b;
+      for (int64_t k = R.succ_ptr[sp]; k < R.succ_ptr[sp + 1]; ++k) {
+        const int32_t cb = R.succ_belief[k];
+        if (!R.compat[(size_t)cb * nv + nvid[n]]) continue;
+        const int64_t cid = n * B + cb;
+        by_belief[cb].push_back({cid, norm2(state(n), state(n)), R.dist[(size_t)cid]});
+      }
+    } else if (ty == PORRT_NODE_ACTION) {
+      for (int64_t e = R.row_ptr[n]; e < R.row_ptr[n + 1]; ++e) {
+        const int32_t c = R.col[e];
+        if (!R.compat[(size_t)b * nv + nvid[c]] || !R.compat[(size_t)b * nv + R.edge_vid[e]]) continue;
+        const int64_t cid = (int64_t)c * B + b;
+        by_belief[b].push_back({cid, norm2(state(n), state(c)), R.dist[(size_t)cid]});
+      }
+    }
+    for (auto& kv : by_belief) {
+      int64_t best_id = kv.second[0].id;
+      const double p = transition_probability(&R.beliefs[(size_t)b * nw], &R.beliefs[(size_t)(best_id % B) * nw], nw);
+      if (!(p > 0.0)) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p > 0.0) (belief_graph.rs:250)");
+      double best_cost = std::numeric_limits<double>::infinity();
+      for (const Child& c : kv.second) {
+        const double cost = p * (c.cost_to_child + c.expected_from_child);
+        if (cost < best_cost) { best_cost = cost; best_id = c.id; }
+      }
+      if (!(p * R.dist[(size_t)best_id] <= R.dist[(size_t)bn])) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p * cost[best] <= cost[node]) (belief_graph.rs:261)");
+      const bool leaf = R.dist[(size_t)best_id] == 0.0;
+      const int64_t pid = (int64_t)pol.size();
+      pol.push_back({(int32_t)(best_id / B), (int32_t)(best_id % B), (int32_t)top.first, (uint8_t)leaf});
+      if (!leaf) lifo.push_back({pid, best_id});
+      if ((int64_t)pol.size() > 64 * R.V * (int64_t)B + 1024) return porrt_fail(ctx, PORRT_ERR_PANIC, "extract_policy: policy does not terminate");
+    }
+  }
+  if (out_n) *out_n = (int64_t)pol.size();
+  if (out_expected_cost) *out_expected_cost = R.dist[0];
+  if ((int64_t)pol.size() > cap || !out_node || !out_belief || !out_parent || !out_is_leaf) return porrt_fail(ctx, PORRT_ERR_CAPACITY, "extract_policy: cap too small");
+  for (size_t k = 0; k < pol.size(); ++k) { out_node[k] = pol[k].node; out_belief[k] = pol[k].belief; out_parent[k] = pol[k].parent; out_is_leaf[k] = pol[k].leaf; }
+  return PORRT_OK;
+}

@@ -1,0 +1,614 @@
+// map.cu -- occupancy-grid validity kernels.
+//
+// Replaces, batched:  Map::to_pixel_coordinates / is_state_valid / get_traversed_space / observe_impl's
+// line-of-sight test (reference src/map_io.rs:165-241,281-300) and the MapShelfDomain equivalents
+// (src/map_shelves_io.rs:150-203,259-265), plus line_drawing::Bresenham (crate line_drawing 0.8).
+//
+// HBM layout: ONE fused code byte per pixel (occupancy + zone id), stored in 128-byte tiles of 16 x 8 px made of
+// four 32-byte sectors of 8 x 4 px, so that a 32-pixel stretch of a line touches ~3 cache lines whatever its
+// direction (a row-major grid costs up to 32 lines for a vertical stretch).
+//   DOOR : 255 free | 0 obstacle | 1..253 zone id + 1 | 254 gray pixel without zone id (reference panics)
+//   SHELF: the raw gray value (class = 255 free, 127..254 low obstacle, 0..126 high obstacle)
+//
+// Kernel shape (edge validity): a warp takes 32 edges, every lane sets up one of them (pixel endpoints, octant,
+// exact-division magic), then the warp walks the 32 edges one after the other with its lanes striding the
+// Bresenham parameter k (pixel k of the line in closed form, A5), four 32-pixel chunks in flight per lane,
+// and reduces each chunk with __ballot_sync / __reduce_min_sync / __reduce_max_sync.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ uint32_t tile_addr(int i, int j, int tiles_x) {
+  return ((uint32_t)((i >> 3) * tiles_x + (j >> 4)) << 7) | ((uint32_t)(i & 4) << 4) | ((uint32_t)(j & 8) << 2) |
+         ((uint32_t)(i & 3) << 3) | (uint32_t)(j & 7);
+}
+
+// Map::to_pixel_coordinates (map_io.rs:176-181): one sub, one mul, one sub, saturating cast -- in that order, no FMA
+// (the library is compiled with -fmad=false; __dmul_rn/__dsub_rn make the intent explicit).
+__device__ __forceinline__ void to_pixel(const MapDev& m, double x, double y, uint32_t& i, uint32_t& j) {
+  i = __double2uint_rz(__dsub_rn(m.hm1, __dmul_rn(__dsub_rn(y, m.low1), m.ppm)));  // cvt.rzi.u32.f64 saturates, NaN -> 0 (= Rust `as u32`)
+  j = __double2uint_rz(__dmul_rn(__dsub_rn(x, m.low0), m.ppm));
+}
+
+// walk results (internal): >= 0 zone id | R_* below | PORRT_PANIC_* codes
+#define R_BLOCKED (-1)  // DOOR: Obstacle, SHELF: HighObstacle
+#define R_FREE (-5)
+#define R_LOW (-6)      // SHELF: LowObstacle
+
+struct EdgeSetup {      // 32 bytes, one per lane, broadcast through shared memory
+  int32_t ai, aj;       // start pixel
+  int32_t dxo, dyo;     // octant-space deltas (dxo >= dyo >= 0)
+  uint32_t m_lo, m_hi;  // floor(2^64 / dxo) + 1 : exact floor(k*dyo/dxo) by one 64-bit mulhi
+  int32_t steps;        // packed unit steps: U (major) and V (minor) as (di,dj) in {-1,0,1}, 2 bits each, biased by 1
+  int32_t flags;        // bit0: start out of bounds, bit1: end out of bounds
+};
+
+// line_drawing::Octant::new + to/from (crate line_drawing 0.8, octant.rs) folded into the two unit steps of the
+// closed form  pixel_k = a + k*U + floor(k*dyo/dxo)*V   (checked against the iterator in tests).
+__device__ __forceinline__ EdgeSetup make_setup(const MapDev& m, double ax, double ay, double bx, double by) {
+  uint32_t ai, aj, bi, bj;
+  to_pixel(m, ax, ay, ai, aj);
+  to_pixel(m, bx, by, bi, bj);
+  EdgeSetup s;
+  s.ai = (int32_t)ai; s.aj = (int32_t)aj;
+  s.flags = ((ai >= (uint32_t)m.H || aj >= (uint32_t)m.W) ? 1 : 0) | ((bi >= (uint32_t)m.H || bj >= (uint32_t)m.W) ? 2 : 0);
+  int32_t dx = (int32_t)bi - (int32_t)ai, dy = (int32_t)bj - (int32_t)aj;
+  int oct = 0;
+  if (dy < 0) { dx = -dx; dy = -dy; oct += 4; }
+  if (dx < 0) { int32_t t = dx; dx = dy; dy = -t; oct += 2; }
+  if (dx < dy) { int32_t t = dx; dx = dy; dy = t; oct += 1; }
+  s.dxo = dx; s.dyo = dy;
+  // from_octant(1,0) and from_octant(0,1) per octant, as (di,dj):
+  //  o0 U(1,0) V(0,1) | o1 U(0,1) V(1,0) | o2 U(0,1) V(-1,0) | o3 U(-1,0) V(0,1)
+  //  o4 U(-1,0) V(0,-1) | o5 U(0,-1) V(-1,0) | o6 U(0,-1) V(1,0) | o7 U(1,0) V(0,-1)
+  int ui, uj, vi, vj;
+  switch (oct) {
+    case 0: ui = 1; uj = 0; vi = 0; vj = 1; break;
+    case 1: ui = 0; uj = 1; vi = 1; vj = 0; break;
+    case 2: ui = 0; uj = 1; vi = -1; vj = 0; break;
+    case 3: ui = -1; uj = 0; vi = 0; vj = 1; break;
+    case 4: ui = -1; uj = 0; vi = 0; vj = -1; break;
+    case 5: ui = 0; uj = -1; vi = -1; vj = 0; break;
+    case 6: ui = 0; uj = -1; vi = 1; vj = 0; break;
+    default: ui = 1; uj = 0; vi = 0; vj = -1; break;
+  }
+  s.steps = (ui + 1) | ((uj + 1) << 2) | ((vi + 1) << 4) | ((vj + 1) << 6);
+  uint64_t M = dx > 1 ? (0xFFFFFFFFFFFFFFFFull / (uint64_t)dx) + 1ull : 0ull;
+  s.m_lo = (uint32_t)M; s.m_hi = (uint32_t)(M >> 32);
+  return s;
+}
+
+struct Walker {  // per-edge state shared by all lanes of the warp
+  int32_t ai, aj, dxo, dyo, ui, uj, vi, vj;
+  uint64_t M;
+  __device__ __forceinline__ void load(const EdgeSetup& s) {
+    ai = s.ai; aj = s.aj; dxo = s.dxo; dyo = s.dyo;
+    ui = (s.steps & 3) - 1; uj = ((s.steps >> 2) & 3) - 1; vi = ((s.steps >> 4) & 3) - 1; vj = ((s.steps >> 6) & 3) - 1;
+    M = ((uint64_t)s.m_hi << 32) | s.m_lo;
+  }
+  __device__ __forceinline__ void pixel(int32_t k, int32_t& i, int32_t& j) const {
+    // floor(k*dyo/dxo); dxo == 1 -> k*dyo, dxo == 0 -> only k == 0 exists
+    int32_t mnr = dxo > 1 ? (int32_t)__umul64hi((uint64_t)((uint32_t)k * (uint32_t)dyo), M) : k * dyo;
+    i = ai + k * ui + mnr * vi;
+    j = aj + k * uj + mnr * vj;
+  }
+};
+
+// Exact sequential semantics, including the order of the reference's panics; one lane, rare.
+template <int KIND>
+__device__ __noinline__ int32_t walk_sequential(const MapDev& m, const Walker& w) {
+  int32_t prev = -1;
+  uint32_t lowest = 255;
+  for (int32_t k = 0; k <= w.dxo; ++k) {
+    int32_t i, j;
+    w.pixel(k, i, j);
+    if ((uint32_t)i >= (uint32_t)m.H || (uint32_t)j >= (uint32_t)m.W) return PORRT_PANIC_OOB;
+    uint32_t c = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
+    if (KIND == PORRT_DOMAIN_SHELF) {
+      lowest = min(lowest, c);
+      if (lowest == 0) return R_BLOCKED;   // map_shelves_io.rs:199
+    } else {
+      if (c == 255) continue;
+      if (c == 0) return R_BLOCKED;        // map_io.rs:229
+      if (c == 254) return PORRT_PANIC_ZONE_UNWRAP;
+      int32_t z = (int32_t)c - 1;
+      if (prev >= 0 && prev != z) return PORRT_PANIC_MULTI_ZONE;  // map_io.rs:233
+      prev = z;
+    }
+  }
+  if (KIND == PORRT_DOMAIN_SHELF) return lowest == 255 ? R_FREE : (lowest >= 127 ? R_LOW : R_BLOCKED);
+  return prev >= 0 ? prev : R_FREE;
+}
+
+// Warp-cooperative walk of one edge; every lane returns the same result.
+template <int KIND>
+__device__ __forceinline__ int32_t walk_warp(const MapDev& m, const EdgeSetup& s, int lane) {
+  if (s.flags & 1) return PORRT_PANIC_OOB;  // the first pixel read already panics
+  Walker w;
+  w.load(s);
+  bool slow = (s.flags & 2) != 0;           // end pixel outside: order of events matters -> sequential
+  int32_t result = R_FREE;
+  if (!slow) {
+    const int32_t n_px = w.dxo + 1;
+    int32_t zone_seen = -1;
+    uint32_t lowest = 255;
+    bool done = false;
+    for (int32_t k0 = 0; k0 < n_px && !done; k0 += 128) {
+      uint32_t code[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int32_t k = k0 + c * 32 + lane;
+        code[c] = 255;
+        if (k < n_px) {
+          int32_t i, j;
+          w.pixel(k, i, j);
+          code[c] = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (done) break;
+        if (KIND == PORRT_DOMAIN_SHELF) {
+          lowest = min(lowest, __reduce_min_sync(0xffffffffu, code[c]));
+          if (lowest == 0) done = true;
+        } else {
+          uint32_t ob = __ballot_sync(0xffffffffu, code[c] == 0);
+          uint32_t before = ob ? ((1u << (__ffs(ob) - 1)) - 1u) : 0xffffffffu;  // lanes ahead of the first obstacle
+          bool is_gray = code[c] != 0 && code[c] != 255 && ((before >> lane) & 1u);
+          uint32_t gray = __ballot_sync(0xffffffffu, is_gray);
+          if (gray) {
+            uint32_t zmin = __reduce_min_sync(0xffffffffu, is_gray ? code[c] : 255u);
+            uint32_t zmax = __reduce_max_sync(0xffffffffu, is_gray ? code[c] : 0u);
+            if (zmin != zmax || zmax == 254u || (zone_seen >= 0 && zone_seen != (int32_t)zmin - 1)) { slow = true; done = true; }
+            zone_seen = (int32_t)zmin - 1;
+          }
+          if (ob && !slow) { result = R_BLOCKED; done = true; }
+        }
+      }
+    }
+    if (!slow) {
+      if (KIND == PORRT_DOMAIN_SHELF) result = lowest == 255 ? R_FREE : (lowest >= 127 ? R_LOW : R_BLOCKED);
+      else if (result != R_BLOCKED) result = zone_seen >= 0 ? zone_seen : R_FREE;
+    }
+  }
+  if (slow) {
+    int32_t r = 0;
+    if (lane == 0) r = walk_sequential<KIND>(m, w);
+    result = __shfl_sync(0xffffffffu, r, 0);
+  }
+  return result;
+}
+
+__device__ __forceinline__ int32_t walk_to_validity(const MapDev& m, int32_t r) {
+  if (r >= 0) return r;                    // Zone(z) -> Some(z)
+  if (r == R_FREE) return m.free_vid;      // Free -> Some(world_validities.len() - 1)
+  if (r == R_LOW) return PORRT_INVALID;
+  return r;                                // blocked (-1) or panic code
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+#define EDGE_BLOCK 256
+
+// INDEXED: endpoints are gathered from a vertex buffer, from[e] = xy[from_idx[e]], to[e] = xy[to_idx[e]] (PRM build).
+template <int KIND, bool INDEXED>
+__global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_kernel(MapDev m, const double2* __restrict__ from,
+                                                                   const double2* __restrict__ to, int64_t n,
+                                                                   int32_t* __restrict__ out_vid,
+                                                                   uint64_t* __restrict__ out_mask,
+                                                                   const uint64_t* __restrict__ validities,
+                                                                   const int32_t* __restrict__ from_idx,
+                                                                   const int32_t* __restrict__ to_idx) {
+  __shared__ EdgeSetup s_setup[EDGE_BLOCK / 32][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * EDGE_BLOCK + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * EDGE_BLOCK) >> 5;
+  for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
+    const int64_t e = base + lane;
+    const int n_here = (int)min((int64_t)32, n - base);
+    if (e < n) {
+      double2 a = INDEXED ? from[from_idx[e]] : from[e];
+      double2 b = INDEXED ? to[to_idx[e]] : to[e];
+      s_setup[wib][lane] = make_setup(m, a.x, a.y, b.x, b.y);
+    }
+    __syncwarp();
+    int32_t mine = PORRT_INVALID;
+    for (int q = 0; q < n_here; ++q) {
+      EdgeSetup s = s_setup[wib][q];
+      int32_t r = walk_warp<KIND>(m, s, lane);
+      if (q == lane) mine = r;
+    }
+    __syncwarp();
+    if (e < n) {
+      int32_t vid = walk_to_validity(m, mine);
+      out_vid[e] = vid;
+      if (out_mask) {
+        if (m.mask_words == 1) out_mask[e] = vid >= 0 ? validities[vid] : 0ull;
+        else
+          for (int wd = 0; wd < m.mask_words; ++wd)
+            out_mask[e * m.mask_words + wd] = vid >= 0 ? validities[(int64_t)vid * m.mask_words + wd] : 0ull;
+      }
+    }
+  }
+}
+
+// is_state_valid + state_validity (map_io.rs:165-174,487-493 / map_shelves_io.rs:158-163,464-469); thread per state
+__global__ void state_validity_kernel(MapDev m, const double2* __restrict__ xy, int64_t n, int32_t* __restrict__ out_vid) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double2 p = xy[t];
+  uint32_t i, j;
+  to_pixel(m, p.x, p.y, i, j);
+  int32_t vid;
+  if (i >= (uint32_t)m.H || j >= (uint32_t)m.W) vid = PORRT_PANIC_OOB;
+  else {
+    uint32_t c = __ldg(m.grid + tile_addr((int)i, (int)j, m.tiles_x));
+    if (m.kind == PORRT_DOMAIN_SHELF) vid = c == 255 ? m.free_vid : PORRT_INVALID;
+    else vid = c == 255 ? m.free_vid : (c == 0 ? PORRT_INVALID : (c == 254 ? PORRT_PANIC_ZONE_UNWRAP : (int32_t)c - 1));
+  }
+  out_vid[t] = vid;
+}
+
+// observe_impl's geometric test (map_io.rs:285-288 / map_shelves_io.rs:259-265); one warp per state, zones in turn
+template <int KIND>
+__global__ void __launch_bounds__(256) visibility_kernel(MapDev m, const double2* __restrict__ xy, int64_t n,
+                                                         const double2* __restrict__ zone_pos, int n_zones, double visibility,
+                                                         uint64_t* __restrict__ out_mask, int32_t* __restrict__ out_status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= n) return;
+  double2 p = xy[warp];
+  uint64_t mask = 0;
+  int32_t status = 0;
+  for (int z = 0; z < n_zones && status == 0; ++z) {
+    double2 zp = zone_pos[z];
+    // norm2(state, zone_pos) (common.rs:203-213): (b - a), squares summed in dimension order, IEEE sqrt
+    double dx = __dsub_rn(zp.x, p.x), dy = __dsub_rn(zp.y, p.y);
+    double d = __dsqrt_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(dx, dx)), __dmul_rn(dy, dy)));
+    if (d < visibility) {
+      EdgeSetup s = make_setup(m, p.x, p.y, zp.x, zp.y);
+      int32_t r = walk_warp<KIND>(m, s, lane);
+      if (r < -1 && r != R_FREE && r != R_LOW) status = r;  // the reference panics here
+      else if (r != R_BLOCKED) mask |= 1ull << z;
+    }
+  }
+  if (lane == 0) { out_mask[warp] = status ? 0ull : mask; out_status[warp] = status; }
+}
+
+// ------------------------------------------------------------------------------------------------ map build kernels
+__global__ void zone_stats_kernel(const uint8_t* __restrict__ zone, int H, int W, uint32_t* __restrict__ stats /* [256*3] */) {
+  __shared__ uint32_t s[256 * 3];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) s[t] = 0;
+  __syncthreads();
+  int64_t total = (int64_t)H * W;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t z = zone[p];
+    if (z != 255) {
+      atomicAdd(&s[z * 3], 1u);
+      atomicAdd(&s[z * 3 + 1], (uint32_t)(p / W));  // u32 sums wrap exactly like the reference's release build
+      atomicAdd(&s[z * 3 + 2], (uint32_t)(p % W));
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 768; t += blockDim.x)
+    if (s[t]) atomicAdd(&stats[t], s[t]);
+}
+
+__global__ void fuse_tile_kernel(const uint8_t* __restrict__ occ, const uint8_t* __restrict__ zone, int H, int W,
+                                 int tiles_x, int tiles_y, int kind, uint8_t* __restrict__ grid) {
+  // one thread per output byte, output-coalesced
+  int64_t total = (int64_t)tiles_x * tiles_y * 128;
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < total; a += (int64_t)gridDim.x * blockDim.x) {
+    int64_t tile = a >> 7;
+    int in = (int)(a & 127);
+    int ti = (int)(tile / tiles_x), tj = (int)(tile % tiles_x);
+    int i = ti * 8 + ((in >> 6) & 1) * 4 + ((in >> 3) & 3);
+    int j = tj * 16 + ((in >> 5) & 1) * 8 + (in & 7);
+    uint8_t code = 0;
+    if (i < H && j < W) {
+      uint8_t o = occ[(int64_t)i * W + j];
+      if (kind == PORRT_DOMAIN_SHELF) code = o;
+      else if (o == 255 || o == 0) code = o;
+      else {
+        uint8_t z = zone ? zone[(int64_t)i * W + j] : 255;
+        code = z == 255 ? 254 : (uint8_t)(z + 1);
+      }
+    }
+    grid[a] = code;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host API
+PORRT_API int32_t porrt_map_upload(porrt_ctx* ctx, const uint8_t* occ, const uint8_t* zone, int32_t H, int32_t W,
+                                   const double low[2], const double up[2], int32_t kind, double visibility) {
+  CTX_CHECK(ctx);
+  if (!occ || !low || !up || H <= 0 || W <= 0 || H > 32768 || W > 32768 || (kind != PORRT_DOMAIN_DOOR && kind != PORRT_DOMAIN_SHELF))
+    return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_map_upload: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->has_map = false;
+  cudaStream_t st = ctx->stream;
+  const size_t px = (size_t)H * W;
+  CUDA_TRY(ctx, ctx->scratch[0].ensure(px));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scratch[0].p, occ, px, cudaMemcpyHostToDevice, st));
+  const uint8_t* d_zone = nullptr;
+  int n_zones = 0, n_worlds = 0;
+  std::vector<double> zone_pos;
+  const double ppm = (double)W / (up[0] - low[0]);  // map_io.rs:91
+  if (zone) {
+    CUDA_TRY(ctx, ctx->scratch[1].ensure(px));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scratch[1].p, zone, px, cudaMemcpyHostToDevice, st));
+    d_zone = ctx->scratch[1].as<uint8_t>();
+    CUDA_TRY(ctx, ctx->scratch[2].ensure(768 * 4));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->scratch[2].p, 0, 768 * 4, st));
+    zone_stats_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_zone, H, W, ctx->scratch[2].as<uint32_t>());
+    LAUNCH_CHECK(ctx);
+    uint32_t stats[768];
+    CUDA_TRY(ctx, cudaMemcpyAsync(stats, ctx->scratch[2].p, sizeof(stats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int max_id = 0;  // init_zone_ids (map_io.rs:130-145): n_zones = max id + 1, 1 even without any zone pixel
+    for (int z = 0; z < 255; ++z)
+      if (stats[z * 3]) max_id = z;
+    n_zones = max_id + 1;
+    for (int z = 0; z < n_zones; ++z) {
+      if (!stats[z * 3]) return porrt_fail(ctx, PORRT_ERR_PANIC, "zone without pixels: the reference divides by zero (map_io.rs:160)");
+      uint32_t ci = stats[z * 3 + 1] / stats[z * 3], cj = stats[z * 3 + 2] / stats[z * 3];
+      // to_coordinates (map_io.rs:183-188), including its swapped low[] indices
+      zone_pos.push_back((double)cj / ppm + low[1]);
+      zone_pos.push_back((double)(uint32_t)(H - 1 - (int)ci) / ppm + low[0]);
+    }
+  }
+  std::vector<uint64_t> validities, zone_masks;
+  int n_validities = 0, words = 1;
+  if (kind == PORRT_DOMAIN_DOOR) {
+    if (zone) {
+      if (n_zones > 16) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "door domain: more than 16 zones (65536 worlds) is not supported");
+      n_worlds = 1 << n_zones;                       // map_io.rs:144
+      words = (n_worlds + 63) / 64;
+      zone_masks.assign((size_t)n_zones * words, 0);
+      for (int z = 0; z < n_zones; ++z)              // zone_index_to_world_mask (map_io.rs:198-214)
+        for (int w = 0; w < n_worlds; ++w)
+          if (w & (1 << z)) zone_masks[(size_t)z * words + w / 64] |= 1ull << (w % 64);
+      validities = zone_masks;                       // world_validities = zones_to_worlds + [all ones] (map_io.rs:125-126)
+      n_validities = n_zones + 1;
+    } else {
+      n_worlds = 1; n_validities = 1;                // init_without_zones (map_io.rs:108-111)
+    }
+    validities.resize((size_t)n_validities * words, 0);
+    for (int w = 0; w < n_worlds; ++w) validities[(size_t)(n_validities - 1) * words + w / 64] |= 1ull << (w % 64);
+  } else {
+    if (!zone) return porrt_fail(ctx, PORRT_ERR_PANIC, "MapShelfDomain without zones: world_validities.len()-1 underflows (map_shelves_io.rs:466)");
+    n_worlds = n_zones;                              // map_shelves_io.rs:460-462
+    words = (n_worlds + 63) / 64;
+    n_validities = 1;                                // single all-ones mask (map_shelves_io.rs:113)
+    validities.assign(words, 0);
+    for (int w = 0; w < n_worlds; ++w) validities[w / 64] |= 1ull << (w % 64);
+  }
+  if (n_zones > 64) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "more than 64 zones is not supported");
+
+  const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8;
+  const size_t grid_bytes = (size_t)tiles_x * tiles_y * 128;
+  CUDA_TRY(ctx, ctx->d_grid.ensure(grid_bytes));
+  fuse_tile_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->scratch[0].as<uint8_t>(), d_zone, H, W, tiles_x, tiles_y, kind,
+                                                      ctx->d_grid.as<uint8_t>());
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, ctx->d_validities.ensure(validities.size() * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_validities.p, validities.data(), validities.size() * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, ctx->d_zone_pos.ensure(zone_pos.size() * 8 + 16));
+  if (!zone_pos.empty())
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zone_pos.p, zone_pos.data(), zone_pos.size() * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+
+  MapDev& m = ctx->map;
+  m.grid = ctx->d_grid.as<uint8_t>();
+  m.H = H; m.W = W; m.tiles_x = tiles_x; m.kind = kind; m.free_vid = n_validities - 1; m.mask_words = words;
+  m.low0 = low[0]; m.low1 = low[1]; m.ppm = ppm; m.hm1 = (double)(H - 1);
+  ctx->n_zones = n_zones; ctx->n_worlds = n_worlds; ctx->n_validities = n_validities; ctx->mask_words = words;
+  ctx->visibility = zone ? visibility : 0.0;
+  ctx->validities = validities; ctx->zone_pos = zone_pos; ctx->zone_world_masks = zone_masks;
+  ctx->has_map = true;
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_map_info(porrt_ctx* ctx, int32_t* n_zones, int32_t* n_worlds, int32_t* n_validities, int32_t* mask_words) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n_zones) *n_zones = ctx->n_zones;
+  if (n_worlds) *n_worlds = ctx->n_worlds;
+  if (n_validities) *n_validities = ctx->n_validities;
+  if (mask_words) *mask_words = ctx->mask_words;
+  return PORRT_OK;
+}
+PORRT_API int32_t porrt_map_zone_positions(porrt_ctx* ctx, double* out_xy) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (!ctx->zone_pos.empty()) memcpy(out_xy, ctx->zone_pos.data(), ctx->zone_pos.size() * 8);
+  return PORRT_OK;
+}
+PORRT_API int32_t porrt_map_world_validities(porrt_ctx* ctx, uint64_t* out) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  memcpy(out, ctx->validities.data(), ctx->validities.size() * 8);
+  return PORRT_OK;
+}
+
+static int edge_grid(porrt_ctx* ctx, int64_t n) {
+  int64_t warps = (n + 31) / 32;
+  int64_t blocks = (warps + (EDGE_BLOCK / 32) - 1) / (EDGE_BLOCK / 32);
+  int64_t cap = (int64_t)ctx->sm_count * 8;  // persistent: 8 CTAs of 256 threads per SM = full occupancy
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
+                              int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st) {
+  if (n == 0) return PORRT_OK;
+  const uint64_t* val = ctx->d_validities.as<uint64_t>();
+  if (ctx->map.kind == PORRT_DOMAIN_SHELF)
+    edge_validity_kernel<PORRT_DOMAIN_SHELF, false><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)from_dev, (const double2*)to_dev, n, out_vid_dev, out_mask_dev, val, nullptr, nullptr);
+  else
+    edge_validity_kernel<PORRT_DOMAIN_DOOR, false><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)from_dev, (const double2*)to_dev, n, out_vid_dev, out_mask_dev, val, nullptr, nullptr);
+  LAUNCH_CHECK(ctx);
+  return PORRT_OK;
+}
+
+int32_t map_edge_validity_indexed_dev(porrt_ctx* ctx, const double* xy_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev,
+                                      int64_t n, int32_t* out_vid_dev, cudaStream_t st) {
+  if (n == 0) return PORRT_OK;
+  const uint64_t* val = ctx->d_validities.as<uint64_t>();
+  if (ctx->map.kind == PORRT_DOMAIN_SHELF)
+    edge_validity_kernel<PORRT_DOMAIN_SHELF, true><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)xy_dev, (const double2*)xy_dev, n, out_vid_dev, nullptr, val, from_idx_dev, to_idx_dev);
+  else
+    edge_validity_kernel<PORRT_DOMAIN_DOOR, true><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)xy_dev, (const double2*)xy_dev, n, out_vid_dev, nullptr, val, from_idx_dev, to_idx_dev);
+  LAUNCH_CHECK(ctx);
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
+                                          int32_t* out_vid_dev, uint64_t* out_mask_dev) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n < 0 || (n > 0 && (!from_dev || !to_dev || !out_vid_dev))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_dev: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return map_edge_validity_dev(ctx, from_dev, to_dev, n, out_vid_dev, out_mask_dev, ctx->stream);
+}
+
+// Host-buffer entry point: chunks the batch and overlaps H2D(c+1) | kernel(c) | D2H(c-1) on three streams.
+// Caller buffers that are pinned (cudaHostAlloc / torch pin_memory) are DMA'd directly, pageable ones are staged.
+PORRT_API int32_t porrt_edge_validity(porrt_ctx* ctx, const double* from_xy, const double* to_xy, int64_t n,
+                                      int32_t* out_vid, uint64_t* out_mask) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n < 0 || (n > 0 && (!from_xy || !to_xy || !out_vid))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity: bad arguments");
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int words = ctx->mask_words;
+  const int64_t CH = 1 << 20;  // edges per chunk: 16 MiB per endpoint array
+  const int64_t ch = n < CH ? n : CH;
+  const bool pinned = is_pinned_host(from_xy) && is_pinned_host(to_xy) && is_pinned_host(out_vid) && (!out_mask || is_pinned_host(out_mask));
+  const int slots = MAX_SLOTS;
+  // device slots: from | to | vid | mask
+  const size_t slot_bytes = (size_t)ch * (16 + 16 + 4 + 8 * (size_t)words);
+  CUDA_TRY(ctx, ctx->scratch[3].ensure(slot_bytes * slots));
+  if (!pinned) CUDA_TRY(ctx, ctx->pin[0].ensure(slot_bytes * slots));
+  cudaStream_t st = ctx->stream;
+  const int64_t n_chunks = (n + ch - 1) / ch;
+  // the copy streams must not run ahead of work already queued on the compute stream
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[0], st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int s = (int)(c % slots);
+    const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
+    char* dbase = ctx->scratch[3].as<char>() + slot_bytes * s;
+    double* d_from = (double*)dbase;
+    double* d_to = (double*)(dbase + (size_t)ch * 16);
+    uint64_t* d_mask = (uint64_t*)(dbase + (size_t)ch * 32);
+    int32_t* d_vid = (int32_t*)(dbase + (size_t)ch * (32 + 8 * (size_t)words));
+    if (c >= slots) {
+      // slot reuse: its previous D2H must be complete (also frees the pinned staging of that slot)
+      CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_out[s]));
+      if (!pinned) {
+        const int64_t poff = (c - slots) * ch, pcnt = (n - poff) < ch ? (n - poff) : ch;
+        char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+        memcpy(out_vid + poff, hb + (size_t)ch * (32 + 8 * (size_t)words), (size_t)pcnt * 4);
+        if (out_mask) memcpy(out_mask + poff * words, hb + (size_t)ch * 32, (size_t)pcnt * 8 * words);
+      }
+    }
+    const double *h_from = from_xy + 2 * off, *h_to = to_xy + 2 * off;
+    if (!pinned) {
+      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+      memcpy(hb, h_from, (size_t)cnt * 16);
+      memcpy(hb + (size_t)ch * 16, h_to, (size_t)cnt * 16);
+      h_from = (const double*)hb; h_to = (const double*)(hb + (size_t)ch * 16);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_from, h_from, (size_t)cnt * 16, cudaMemcpyHostToDevice, ctx->copy_in));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_to, h_to, (size_t)cnt * 16, cudaMemcpyHostToDevice, ctx->copy_in));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_in[s], 0));
+    int32_t rc = map_edge_validity_dev(ctx, d_from, d_to, cnt, d_vid, out_mask ? d_mask : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[s], st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[s], 0));
+    int32_t* h_vid = out_vid + off;
+    uint64_t* h_mask = out_mask ? out_mask + off * words : nullptr;
+    if (!pinned) {
+      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+      h_vid = (int32_t*)(hb + (size_t)ch * (32 + 8 * (size_t)words));
+      h_mask = (uint64_t*)(hb + (size_t)ch * 32);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_vid, d_vid, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(h_mask, d_mask, (size_t)cnt * 8 * words, cudaMemcpyDeviceToHost, ctx->copy_out));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (!pinned) {
+    int64_t first = n_chunks > slots ? n_chunks - slots : 0;
+    for (int64_t c = first; c < n_chunks; ++c) {
+      const int s = (int)(c % slots);
+      const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
+      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+      memcpy(out_vid + off, hb + (size_t)ch * (32 + 8 * (size_t)words), (size_t)cnt * 4);
+      if (out_mask) memcpy(out_mask + off * words, hb + (size_t)ch * 32, (size_t)cnt * 8 * words);
+    }
+  }
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_state_validity_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_dev) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n < 0 || (n > 0 && (!xy_dev || !out_dev))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_state_validity_dev: bad arguments");
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  state_validity_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(ctx->map, (const double2*)xy_dev, n, out_dev);
+  LAUNCH_CHECK(ctx);
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_state_validity(porrt_ctx* ctx, const double* xy, int64_t n, int32_t* out_vid) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n < 0 || (n > 0 && (!xy || !out_vid))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_state_validity: bad arguments");
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, ctx->scratch[3].ensure((size_t)n * 20));
+  double* d_xy = ctx->scratch[3].as<double>();
+  int32_t* d_out = (int32_t*)(ctx->scratch[3].as<char>() + (size_t)n * 16);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc = porrt_state_validity_dev(ctx, d_xy, n, d_out);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_vid, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_visibility_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, uint64_t* out_mask_dev, int32_t* out_status_dev) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n < 0 || (n > 0 && (!xy_dev || !out_mask_dev || !out_status_dev))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_visibility_dev: bad arguments");
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int blocks = div_up(n * 32, 256);
+  if (ctx->map.kind == PORRT_DOMAIN_SHELF)
+    visibility_kernel<PORRT_DOMAIN_SHELF><<<blocks, 256, 0, ctx->stream>>>(ctx->map, (const double2*)xy_dev, n, ctx->d_zone_pos.as<double2>(), ctx->n_zones, ctx->visibility, out_mask_dev, out_status_dev);
+  else
+    visibility_kernel<PORRT_DOMAIN_DOOR><<<blocks, 256, 0, ctx->stream>>>(ctx->map, (const double2*)xy_dev, n, ctx->d_zone_pos.as<double2>(), ctx->n_zones, ctx->visibility, out_mask_dev, out_status_dev);
+  LAUNCH_CHECK(ctx);
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_visibility(porrt_ctx* ctx, const double* xy, int64_t n, uint64_t* out_mask, int32_t* out_status) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n < 0 || (n > 0 && (!xy || !out_mask || !out_status))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_visibility: bad arguments");
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, ctx->scratch[3].ensure((size_t)n * 28));
+  double* d_xy = ctx->scratch[3].as<double>();
+  uint64_t* d_mask = (uint64_t*)(ctx->scratch[3].as<char>() + (size_t)n * 16);
+  int32_t* d_status = (int32_t*)(ctx->scratch[3].as<char>() + (size_t)n * 24);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc = porrt_visibility_dev(ctx, d_xy, n, d_mask, d_status);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_mask, d_mask, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PORRT_OK;
+}

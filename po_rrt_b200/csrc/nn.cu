@@ -1,0 +1,666 @@
+// nn.cu -- batched nearest-neighbour search (+ k-NN), replacing the per-query walks of
+// KdTree<N> (reference src/nearest_neighbor.rs:48-126) and norm2 (src/common.rs:203-213).
+//
+// B200 design: the unbalanced boxed kd-tree is pointer chasing; here the vertex set is binned once into a uniform
+// cell grid (cell >= typical radius) stored as a cell-sorted AoS buffer {x,y} (16 B, one LDG.128 per candidate) plus a
+// parallel id array, both ordered (cell row-major, id ascending).  The three cell rows a radius query overlaps are
+// three CONTIGUOUS ranges of that buffer.  All distance arithmetic is the reference's f64 sequence (no FMA);
+// the inclusive test sqrt(d2) <= r is evaluated as d2 <= T(r) with T(r) = max{t : sqrt(t) <= r} (exact).
+//
+// Also here: the library's scan and stable LSD radix sort (used for binning and for restoring per-query orders).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+// ================================================================================================ scan
+// exclusive scan of u32 counts into i64 offsets; three-phase (block scan, scan of block sums, add).
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_block_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out,
+                                                                int64_t* __restrict__ block_sums) {
+  __shared__ int64_t s_warp[SCAN_BLOCK / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int64_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? (int64_t)(uint32_t)in[base + k] : 0;
+    sum += v[k];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int64_t w = lane < SCAN_BLOCK / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < SCAN_BLOCK / 32) s_warp[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int64_t excl = incl - sum + (wid ? s_warp[wid - 1] : 0);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = s_warp[SCAN_BLOCK / 32 - 1];
+}
+
+__global__ void scan_sums_kernel(int64_t* __restrict__ sums, int64_t nb, int64_t* __restrict__ total_out) {
+  // single block, sequential over tiles of blockDim: nb is small (n / 2048)
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nb; base += blockDim.x) {
+    int64_t i = base + threadIdx.x;
+    int64_t v = i < nb ? sums[i] : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int64_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    int64_t carry = s_carry;
+    int64_t excl = carry + incl - v + (wid ? s_warp[wid - 1] : 0);
+    if (i < nb) sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = s_carry;
+}
+
+__global__ void scan_add_kernel(int64_t* __restrict__ out, int64_t n, const int64_t* __restrict__ sums, int64_t* __restrict__ tail) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  const int64_t add = sums[blockIdx.x];
+  for (int k = threadIdx.x; k < SCAN_TILE; k += SCAN_BLOCK)
+    if (base + k < n) out[base + k] += add;
+  (void)tail;
+}
+
+// out[0..n) = exclusive offsets, out[n] = total
+int32_t scan_exclusive_i64(porrt_ctx* ctx, const int32_t* counts_dev, int64_t n, int64_t* out_dev) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0) { CUDA_TRY(ctx, cudaMemsetAsync(out_dev, 0, 8, st)); return PORRT_OK; }
+  const int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  CUDA_TRY(ctx, ctx->scratch[11].ensure((size_t)nb * 8 + 8));
+  int64_t* sums = ctx->scratch[11].as<int64_t>();
+  scan_block_kernel<<<(int)nb, SCAN_BLOCK, 0, st>>>(counts_dev, n, out_dev, sums);
+  LAUNCH_CHECK(ctx);
+  scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, out_dev + n);
+  LAUNCH_CHECK(ctx);
+  scan_add_kernel<<<(int)nb, SCAN_BLOCK, 0, st>>>(out_dev, n, sums, nullptr);
+  LAUNCH_CHECK(ctx);
+  return PORRT_OK;
+}
+
+// ================================================================================================ radix sort
+// Stable LSD radix sort of (u64 key, u32 value) pairs, 8 bits per pass.  One warp owns a tile of RS_TILE consecutive
+// elements and walks it 32 at a time in order, so ranks inside a digit follow the input order (stability) by
+// __match_any_sync + popc; no cross-warp ordering problem arises because tile bases come from the scan.
+#define RS_TILE 2048
+#define RS_WARPS 4
+
+__global__ void __launch_bounds__(RS_WARPS * 32) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                                int64_t n_tiles, int32_t* __restrict__ hist /* [256][n_tiles] */) {
+  __shared__ int32_t s_h[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * RS_WARPS + wib;
+  for (int b = lane; b < 256; b += 32) s_h[wib][b] = 0;
+  __syncwarp();
+  if (tile < n_tiles) {
+    const int64_t lo = tile * RS_TILE, hi = min(n, lo + RS_TILE);
+    for (int64_t i = lo + lane; i < hi; i += 32) atomicAdd(&s_h[wib][(int)((keys[i] >> shift) & 255)], 1);
+    __syncwarp();
+    for (int b = lane; b < 256; b += 32) hist[(int64_t)b * n_tiles + tile] = s_h[wib][b];
+  }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32) rs_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                                   int64_t n, int shift, int64_t n_tiles,
+                                                                   const int64_t* __restrict__ bases /* [256][n_tiles] */,
+                                                                   uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals) {
+  __shared__ int64_t s_b[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * RS_WARPS + wib;
+  if (tile >= n_tiles) return;
+  for (int b = lane; b < 256; b += 32) s_b[wib][b] = bases[(int64_t)b * n_tiles + tile];
+  __syncwarp();
+  const int64_t lo = tile * RS_TILE, hi = min(n, lo + RS_TILE);
+  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const bool valid = i < hi;
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const uint64_t k = keys[i];
+      const uint32_t v = vals[i];
+      const int d = (int)((k >> shift) & 255);
+      const unsigned peers = __match_any_sync(active, d);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int64_t b = s_b[wib][d];
+      __syncwarp(active);
+      if (rank == 0) s_b[wib][d] = b + __popc(peers);
+      __syncwarp(active);
+      out_keys[b + rank] = k;
+      out_vals[b + rank] = v;
+    }
+  }
+}
+
+// sorts in place (result ends in keys/vals); tmp buffers from ctx scratch 8..10
+int32_t radix_sort_pairs(porrt_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits) {
+  if (n <= 1) return PORRT_OK;
+  cudaStream_t st = ctx->stream;
+  const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+  CUDA_TRY(ctx, ctx->scratch[8].ensure((size_t)n * 8));
+  CUDA_TRY(ctx, ctx->scratch[9].ensure((size_t)n * 4));
+  CUDA_TRY(ctx, ctx->scratch[10].ensure((size_t)n_tiles * 256 * 12 + 16));
+  uint64_t* k2 = ctx->scratch[8].as<uint64_t>();
+  uint32_t* v2 = ctx->scratch[9].as<uint32_t>();
+  int64_t* bases = ctx->scratch[10].as<int64_t>();
+  int32_t* hist = (int32_t*)(ctx->scratch[10].as<char>() + ((size_t)n_tiles * 256 + 1) * 8);
+  uint64_t *ki = keys, *ko = k2;
+  uint32_t *vi = vals, *vo = v2;
+  const int blocks = (int)((n_tiles + RS_WARPS - 1) / RS_WARPS);
+  int passes = (key_bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  for (int p = 0; p < passes; ++p) {
+    rs_hist_kernel<<<blocks, RS_WARPS * 32, 0, st>>>(ki, n, p * 8, n_tiles, hist);
+    LAUNCH_CHECK(ctx);
+    int32_t rc = scan_exclusive_i64(ctx, hist, n_tiles * 256, bases);
+    if (rc) return rc;
+    rs_scatter_kernel<<<blocks, RS_WARPS * 32, 0, st>>>(ki, vi, n, p * 8, n_tiles, bases, ko, vo);
+    LAUNCH_CHECK(ctx);
+    std::swap(ki, ko);
+    std::swap(vi, vo);
+  }
+  if (ki != keys) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(keys, ki, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(vals, vi, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return PORRT_OK;
+}
+
+int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b)) ++b;
+  return b;
+}
+
+// ================================================================================================ cell grid
+struct GridDev {
+  const double2* vxy;       // cell-sorted vertex coordinates
+  const int32_t* vid;       // their ids
+  const int64_t* cell_start;  // [cells_x*cells_y + 1]
+  double org_x, org_y, inv_cell, cell;
+  int32_t cells_x, cells_y;
+  int64_t n;
+};
+
+__device__ __forceinline__ int cell_coord(double v, double org, double inv_cell, int n_cells) {
+  double c = floor(__dmul_rn(__dsub_rn(v, org), inv_cell));
+  if (!(c > 0.0)) return 0;
+  if (c >= (double)(n_cells - 1)) return n_cells - 1;
+  return (int)c;
+}
+
+__global__ void bbox_kernel(const double2* __restrict__ xy, int64_t n, double* __restrict__ out /* minx,miny,maxx,maxy as ordered u64 */) {
+  double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 p = xy[i];
+    mnx = fmin(mnx, p.x); mny = fmin(mny, p.y); mxx = fmax(mxx, p.x); mxy = fmax(mxy, p.y);
+  }
+  for (int o = 16; o; o >>= 1) {
+    mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // order-preserving map double -> u64 so that atomicMin/Max on integers work for negative values too
+    auto enc = [](double d) { unsigned long long b = (unsigned long long)__double_as_longlong(d); return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull); };
+    unsigned long long* o = (unsigned long long*)out;
+    atomicMin(&o[0], enc(mnx)); atomicMin(&o[1], enc(mny)); atomicMax(&o[2], enc(mxx)); atomicMax(&o[3], enc(mxy));
+  }
+}
+
+__global__ void cell_key_kernel(const double2* __restrict__ xy, int64_t n, double org_x, double org_y, double inv_cell,
+                                int cells_x, int cells_y, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                int32_t* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2 p = xy[i];
+  int cx = cell_coord(p.x, org_x, inv_cell, cells_x), cy = cell_coord(p.y, org_y, inv_cell, cells_y);
+  uint32_t c = (uint32_t)cy * (uint32_t)cells_x + (uint32_t)cx;
+  keys[i] = c;
+  vals[i] = (uint32_t)i;
+  atomicAdd(&counts[c], 1);
+}
+
+__global__ void gather_vertices_kernel(const double2* __restrict__ xy, const uint32_t* __restrict__ order, int64_t n,
+                                       double2* __restrict__ out_xy, int32_t* __restrict__ out_id) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t id = order[i];
+  out_xy[i] = xy[id];
+  out_id[i] = (int32_t)id;
+}
+
+static GridDev grid_dev(porrt_ctx* ctx) {
+  GridDev g;
+  g.vxy = ctx->d_vxy_sorted.as<double2>(); g.vid = ctx->d_vid_sorted.as<int32_t>(); g.cell_start = ctx->d_cell_start.as<int64_t>();
+  g.org_x = ctx->org_x; g.org_y = ctx->org_y; g.inv_cell = ctx->inv_cell; g.cell = ctx->cell;
+  g.cells_x = ctx->cells_x; g.cells_y = ctx->cells_y; g.n = ctx->n_vertices;
+  return g;
+}
+
+int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi) {
+  cudaStream_t st = ctx->stream;
+  ctx->n_vertices = 0;
+  if (n <= 0 || n > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_set: n out of range");
+  double blo[2], bhi[2];
+  if (lo && hi) { blo[0] = lo[0]; blo[1] = lo[1]; bhi[0] = hi[0]; bhi[1] = hi[1]; }
+  else {
+    CUDA_TRY(ctx, ctx->scratch[4].ensure(32));
+    unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scratch[4].p, init, 32, cudaMemcpyHostToDevice, st));
+    bbox_kernel<<<ctx->sm_count * 4, 256, 0, st>>>((const double2*)xy_dev, n, ctx->scratch[4].as<double>());
+    LAUNCH_CHECK(ctx);
+    unsigned long long enc[4];
+    CUDA_TRY(ctx, cudaMemcpyAsync(enc, ctx->scratch[4].p, 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    double dec[4];
+    for (int k = 0; k < 4; ++k) {
+      unsigned long long b = (enc[k] & 0x8000000000000000ull) ? (enc[k] & 0x7fffffffffffffffull) : ~enc[k];
+      memcpy(&dec[k], &b, 8);
+    }
+    blo[0] = dec[0]; blo[1] = dec[1]; bhi[0] = dec[2]; bhi[1] = dec[3];
+  }
+  if (!(blo[0] <= bhi[0]) || !(blo[1] <= bhi[1]) || !std::isfinite(blo[0]) || !std::isfinite(bhi[0]) || !std::isfinite(blo[1]) || !std::isfinite(bhi[1]))
+    return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_set: non-finite coordinates");
+  double ex = bhi[0] - blo[0], ey = bhi[1] - blo[1];
+  double cell = cell_size;
+  if (!(cell > 0.0)) cell = std::sqrt(std::max(ex * ey, 1e-300) * 2.0 / (double)n);  // ~2 vertices per cell
+  if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
+  const double MAX_CELLS = 16777216.0;  // 2^24 -> 3 radix passes, 128 MiB of cell_start at most
+  for (;;) {
+    double cxs = std::floor(ex / cell) + 1.0, cys = std::floor(ey / cell) + 1.0;
+    if (cxs * cys <= MAX_CELLS) { ctx->cells_x = (int)cxs; ctx->cells_y = (int)cys; break; }
+    cell *= 1.5;
+  }
+  ctx->cell = cell; ctx->inv_cell = 1.0 / cell; ctx->org_x = blo[0]; ctx->org_y = blo[1];
+  const int64_t n_cells = (int64_t)ctx->cells_x * ctx->cells_y;
+  CUDA_TRY(ctx, ctx->scratch[5].ensure((size_t)n * 8));       // keys
+  CUDA_TRY(ctx, ctx->scratch[6].ensure((size_t)n * 4));       // vals
+  CUDA_TRY(ctx, ctx->scratch[7].ensure((size_t)n_cells * 4)); // counts
+  CUDA_TRY(ctx, ctx->d_cell_start.ensure((size_t)(n_cells + 1) * 8));
+  CUDA_TRY(ctx, ctx->d_vxy_sorted.ensure((size_t)n * 16));
+  CUDA_TRY(ctx, ctx->d_vid_sorted.ensure((size_t)n * 4));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->scratch[7].p, 0, (size_t)n_cells * 4, st));
+  cell_key_kernel<<<div_up(n, 256), 256, 0, st>>>((const double2*)xy_dev, n, ctx->org_x, ctx->org_y, ctx->inv_cell, ctx->cells_x, ctx->cells_y,
+                                                  ctx->scratch[5].as<uint64_t>(), ctx->scratch[6].as<uint32_t>(), ctx->scratch[7].as<int32_t>());
+  LAUNCH_CHECK(ctx);
+  int32_t rc = scan_exclusive_i64(ctx, ctx->scratch[7].as<int32_t>(), n_cells, ctx->d_cell_start.as<int64_t>());
+  if (rc) return rc;
+  rc = radix_sort_pairs(ctx, ctx->scratch[5].as<uint64_t>(), ctx->scratch[6].as<uint32_t>(), n, bits_for((uint64_t)n_cells - 1));
+  if (rc) return rc;
+  gather_vertices_kernel<<<div_up(n, 256), 256, 0, st>>>((const double2*)xy_dev, ctx->scratch[6].as<uint32_t>(), n,
+                                                         ctx->d_vxy_sorted.as<double2>(), ctx->d_vid_sorted.as<int32_t>());
+  LAUNCH_CHECK(ctx);
+  ctx->n_vertices = n;
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double lo[2], const double hi[2]) {
+  CTX_CHECK(ctx);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!xy_dev) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_set_dev: null");
+  return nn_vertices_set_dev(ctx, xy_dev, n, cell_size, lo, hi);
+}
+
+PORRT_API int32_t porrt_vertices_set(porrt_ctx* ctx, const double* xy, int64_t n, double cell_size) {
+  CTX_CHECK(ctx);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!xy || n <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_set: bad arguments");
+  CUDA_TRY(ctx, ctx->d_vxy.ensure((size_t)n * 16));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vxy.p, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  return nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell_size, nullptr, nullptr);
+}
+
+PORRT_API int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n) {
+  CTX_CHECK(ctx);
+  if (out_n) *out_n = ctx->n_vertices;
+  return PORRT_OK;
+}
+
+// ================================================================================================ radius query
+// T(r) = max{ t : sqrt_rn(t) <= r }  (SURVEY 8(g) note 3): the reference tests `norm2(..) <= radius` on the sqrt-ed value.
+__device__ __forceinline__ double radius_threshold(double r) {
+  if (!(r >= 0.0)) return -1.0;  // negative or NaN radius: nothing passes `d <= radius`
+  double t = __dmul_rn(r, r);
+  if (isinf(t)) return t;
+  while (t > 0.0 && __dsqrt_rn(t) > r) t = __longlong_as_double(__double_as_longlong(t) - 1);
+  for (;;) {
+    double u = __longlong_as_double(__double_as_longlong(t) + 1);
+    if (isfinite(u) && __dsqrt_rn(u) <= r) t = u; else break;
+  }
+  return t;
+}
+
+__device__ __forceinline__ double dist2(double2 v, double qx, double qy) {
+  double dx = __dsub_rn(qx, v.x), dy = __dsub_rn(qy, v.y);
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));  // 0.0 + dx*dx is exact, so this is the reference's sum
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius, int64_t m,
+                                                     const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
+                                                     const uint32_t* __restrict__ world, int32_t* __restrict__ counts,
+                                                     const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const double2 p = q[t];
+  const double r = radius[t];
+  const double T = radius_threshold(r);
+  int32_t cnt = 0;
+  if (T >= 0.0 && p.x == p.x && p.y == p.y) {
+    const uint32_t limit = prefix ? prefix[t] : 0xffffffffu;
+    const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+    const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);  // conservative cell cover
+    const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
+    const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
+    int32_t* out = FILL ? out_ids + offsets[t] : nullptr;
+    for (int cy = cy0; cy <= cy1; ++cy) {
+      if (prefix) {
+        // cell lists are id-ascending: stop at the first id >= limit (the tree as it was when vertex `limit` arrived)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+          const int64_t c = (int64_t)cy * g.cells_x + cx;
+          const int64_t e = g.cell_start[c + 1];
+          for (int64_t k = g.cell_start[c]; k < e; ++k) {
+            const uint32_t id = (uint32_t)g.vid[k];
+            if (id >= limit) break;
+            if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || ((reach[id] >> wbit) & 1ull))) {
+              if (FILL) out[cnt] = (int32_t)id;
+              ++cnt;
+            }
+          }
+        }
+      } else {
+        const int64_t s = g.cell_start[(int64_t)cy * g.cells_x + cx0], e = g.cell_start[(int64_t)cy * g.cells_x + cx1 + 1];
+        for (int64_t k = s; k < e; ++k) {
+          if (dist2(g.vxy[k], p.x, p.y) <= T) {
+            const uint32_t id = (uint32_t)g.vid[k];
+            if (!reach || ((reach[id] >> wbit) & 1ull)) {
+              if (FILL) out[cnt] = (int32_t)id;
+              ++cnt;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!FILL) counts[t] = cnt;
+}
+
+// offsets_dev[m+1] filled; ids_buf grown to the total; *total_out = total hits (host value; synchronises once)
+int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
+                                 const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
+                                 int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out) {
+  cudaStream_t st = ctx->stream;
+  GridDev g = grid_dev(ctx);
+  CUDA_TRY(ctx, ctx->scratch[4].ensure((size_t)m * 4 + 16));
+  int32_t* counts = ctx->scratch[4].as<int32_t>();
+  radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr);
+  LAUNCH_CHECK(ctx);
+  int32_t rc = scan_exclusive_i64(ctx, counts, m, offsets_dev);
+  if (rc) return rc;
+  int64_t total = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  *total_out = total;
+  CUDA_TRY(ctx, ids_buf->ensure((size_t)std::max<int64_t>(total, 1) * 4));
+  if (total > 0) {
+    radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>());
+    LAUNCH_CHECK(ctx);
+  }
+  return PORRT_OK;
+}
+
+// ---- per-segment ordering: sort ids inside each CSR segment by key_of_id (NULL: by id) with one global stable radix sort
+__global__ void seg_key_kernel(const int64_t* __restrict__ offsets, int64_t m, const int32_t* __restrict__ ids,
+                               const int32_t* __restrict__ key_of_id, int key_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  // one warp per segment
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= m) return;
+  const int64_t s = offsets[seg], e = offsets[seg + 1];
+  for (int64_t k = s + lane; k < e; k += 32) {
+    const int32_t id = ids[k];
+    const uint64_t key = key_of_id ? (uint64_t)(uint32_t)key_of_id[id] : (uint64_t)(uint32_t)id;
+    keys[k] = ((uint64_t)seg << key_bits) | key;
+    vals[k] = (uint32_t)id;
+  }
+}
+__global__ void copy_u32_i32_kernel(const uint32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)in[i];
+}
+
+// key_limit: all keys (ids or key_of_id values) are < key_limit
+int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev, const int32_t* key_of_id_dev, int64_t key_limit) {
+  cudaStream_t st = ctx->stream;
+  int64_t total = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (total <= 1) return PORRT_OK;
+  const int key_bits = bits_for((uint64_t)(key_limit > 1 ? key_limit - 1 : 1));
+  const int seg_bits = bits_for((uint64_t)(m > 1 ? m - 1 : 1));
+  CUDA_TRY(ctx, ctx->scratch[5].ensure((size_t)total * 8));
+  CUDA_TRY(ctx, ctx->scratch[6].ensure((size_t)total * 4));
+  uint64_t* keys = ctx->scratch[5].as<uint64_t>();
+  uint32_t* vals = ctx->scratch[6].as<uint32_t>();
+  seg_key_kernel<<<div_up(m * 32, 256), 256, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, key_bits, keys, vals);
+  LAUNCH_CHECK(ctx);
+  // segments are already contiguous and in order: only the low (key) bits need sorting, LSD passes over them suffice
+  // because a stable sort on the key bits followed by stable passes on the segment bits == full sort; since the
+  // input is segment-ordered we still need the segment passes to undo the mixing of the key passes.
+  int32_t rc = radix_sort_pairs(ctx, keys, vals, total, key_bits + seg_bits);
+  if (rc) return rc;
+  copy_u32_i32_kernel<<<div_up(total, 256), 256, 0, st>>>(vals, total, ids_dev);
+  LAUNCH_CHECK(ctx);
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const double* radius, int64_t m,
+                                     const uint32_t* prefix_limit, const uint64_t* reach_mask, const uint32_t* world,
+                                     int64_t* out_offsets, int32_t* out_ids, int64_t cap, int64_t* out_total) {
+  CTX_CHECK(ctx);
+  if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
+  if (m < 0 || (m > 0 && (!q_xy || !radius || !out_offsets)) || (reach_mask && !world)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "radius_query: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (m == 0) { if (out_offsets) out_offsets[0] = 0; if (out_total) *out_total = 0; return PORRT_OK; }
+  const int64_t V = ctx->n_vertices;
+  // device inputs: q | radius | prefix | world | reach | offsets
+  size_t need = (size_t)m * (16 + 8 + 4 + 4 + 8) + 64 + (reach_mask ? (size_t)V * 8 : 0);
+  CUDA_TRY(ctx, ctx->scratch[3].ensure(need));
+  char* b = ctx->scratch[3].as<char>();
+  double* d_q = (double*)b; b += (size_t)m * 16;
+  double* d_r = (double*)b; b += (size_t)m * 8;
+  int64_t* d_off = (int64_t*)b; b += (size_t)(m + 1) * 8;
+  uint64_t* d_reach = nullptr;
+  if (reach_mask) { d_reach = (uint64_t*)b; b += (size_t)V * 8; }
+  uint32_t* d_prefix = nullptr; uint32_t* d_world = nullptr;
+  if (prefix_limit) { d_prefix = (uint32_t*)b; b += (size_t)m * 4; }
+  if (world) { d_world = (uint32_t*)b; b += (size_t)m * 4; }
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_q, q_xy, (size_t)m * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_r, radius, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  if (d_prefix) CUDA_TRY(ctx, cudaMemcpyAsync(d_prefix, prefix_limit, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+  if (d_world) CUDA_TRY(ctx, cudaMemcpyAsync(d_world, world, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+  if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
+  int64_t total = 0;
+  int32_t rc = nn_radius_count_fill_dev(ctx, d_q, d_r, m, d_prefix, d_reach, d_world, d_off, &ctx->scratch[2], &total);
+  if (rc) return rc;
+  if (out_total) *out_total = total;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (total > cap || (total > 0 && !out_ids)) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return porrt_fail(ctx, PORRT_ERR_CAPACITY, "radius_query: out_ids too small");
+  }
+  rc = segments_sort_by_key_dev(ctx, d_off, m, ctx->scratch[2].as<int32_t>(), nullptr, V);
+  if (rc) return rc;
+  if (total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(out_ids, ctx->scratch[2].p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return PORRT_OK;
+}
+
+// ================================================================================================ nearest / k-NN
+// ring search around the query's cell; exact: stops only when every unvisited cell is provably farther.
+template <int KMAX>
+struct TopK {
+  double d2[KMAX];
+  int32_t id[KMAX];
+  int k, cnt;
+  __device__ __forceinline__ void init(int kk) { k = kk; cnt = 0; }
+  __device__ __forceinline__ double worst() const { return cnt < k ? INFINITY : d2[k - 1]; }
+  __device__ __forceinline__ void push(double d, int32_t i) {
+    // keep ascending by (d2, id)
+    if (cnt == k && !(d < d2[k - 1] || (d == d2[k - 1] && i < id[k - 1]))) return;
+    int pos = cnt < k ? cnt : k - 1;
+    while (pos > 0 && (d < d2[pos - 1] || (d == d2[pos - 1] && i < id[pos - 1]))) {
+      d2[pos] = d2[pos - 1]; id[pos] = id[pos - 1]; --pos;
+    }
+    d2[pos] = d; id[pos] = i;
+    if (cnt < k) ++cnt;
+  }
+};
+
+__device__ __forceinline__ double ring_lower_bound2(const GridDev& g, double qx, double qy, int cx, int cy, int R) {
+  // squared distance from q to the nearest point outside the square of cells [cx-R,cx+R] x [cy-R,cy+R];
+  // sides beyond the grid have nothing behind them.  Shrunk by 1e-9 relative to stay conservative.
+  double lb = INFINITY;
+  if (cx - R > 0) lb = fmin(lb, qx - (g.org_x + (double)(cx - R) * g.cell));
+  if (cx + R < g.cells_x - 1) lb = fmin(lb, (g.org_x + (double)(cx + R + 1) * g.cell) - qx);
+  if (cy - R > 0) lb = fmin(lb, qy - (g.org_y + (double)(cy - R) * g.cell));
+  if (cy + R < g.cells_y - 1) lb = fmin(lb, (g.org_y + (double)(cy + R + 1) * g.cell) - qy);
+  if (isinf(lb)) return INFINITY;
+  if (!(lb > 0.0)) return 0.0;
+  lb *= (1.0 - 1e-9);
+  return lb * lb;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) knn_kernel(GridDev g, const double2* __restrict__ q, int64_t m, int k,
+                                                  const uint64_t* __restrict__ reach, const uint32_t* __restrict__ world,
+                                                  int32_t* __restrict__ out_ids, double* __restrict__ out_dist, int32_t* __restrict__ out_ties) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const double2 p = q[t];
+  TopK<KMAX> top;
+  top.init(k);
+  int32_t ties = 0;  // KMAX == 1 only: vertices at exactly the winning d2
+  const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+  if (p.x == p.x && p.y == p.y) {
+    const int cx = cell_coord(p.x, g.org_x, g.inv_cell, g.cells_x), cy = cell_coord(p.y, g.org_y, g.inv_cell, g.cells_y);
+    const int maxR = max(max(cx, g.cells_x - 1 - cx), max(cy, g.cells_y - 1 - cy));
+    for (int R = 0; R <= maxR; ++R) {
+      for (int dy = -R; dy <= R; ++dy) {
+        const int yy = cy + dy;
+        if (yy < 0 || yy >= g.cells_y) continue;
+        const bool full_row = (dy == -R || dy == R);
+        for (int side = 0; side < (full_row || R == 0 ? 1 : 2); ++side) {
+          int x0, x1;
+          if (full_row || R == 0) { x0 = max(cx - R, 0); x1 = min(cx + R, g.cells_x - 1); }
+          else { x0 = x1 = side ? cx + R : cx - R; if (x0 < 0 || x0 >= g.cells_x) continue; }
+          const int64_t s = g.cell_start[(int64_t)yy * g.cells_x + x0], e = g.cell_start[(int64_t)yy * g.cells_x + x1 + 1];
+          for (int64_t kk = s; kk < e; ++kk) {
+            const double d = dist2(g.vxy[kk], p.x, p.y);
+            if (d <= top.worst() || top.cnt < k) {
+              const int32_t id = g.vid[kk];
+              if (!reach || ((reach[id] >> wbit) & 1ull)) {
+                if (KMAX == 1) {
+                  if (top.cnt == 0 || d < top.d2[0]) ties = 1;
+                  else if (d == top.d2[0]) ++ties;
+                }
+                if (d == d) top.push(d, id);
+              }
+            }
+          }
+        }
+      }
+      if (top.cnt == k && top.worst() < ring_lower_bound2(g, p.x, p.y, cx, cy, R)) break;
+    }
+  }
+  for (int j = 0; j < k; ++j) {
+    const bool ok = j < top.cnt;
+    out_ids[t * k + j] = ok ? top.id[j] : -1;
+    if (out_dist) out_dist[t * k + j] = ok ? __dsqrt_rn(top.d2[j]) : INFINITY;
+  }
+  if (KMAX == 1 && out_ties) out_ties[t] = ties;
+}
+
+static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, const uint64_t* reach_mask, const uint32_t* world,
+                        int32_t* out_ids, double* out_dist, int32_t* out_ties) {
+  if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
+  if (m < 0 || (m > 0 && (!q_xy || !out_ids)) || k < 1 || k > 32 || (reach_mask && !world)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "nearest/knn: bad arguments (1 <= k <= 32)");
+  if (m == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int64_t V = ctx->n_vertices;
+  size_t need = (size_t)m * (16 + 4 + 4) + (size_t)m * k * 12 + (reach_mask ? (size_t)V * 8 : 0) + 64;
+  CUDA_TRY(ctx, ctx->scratch[3].ensure(need));
+  char* b = ctx->scratch[3].as<char>();
+  double* d_q = (double*)b; b += (size_t)m * 16;
+  double* d_dist = (double*)b; b += (size_t)m * k * 8;
+  uint64_t* d_reach = nullptr;
+  if (reach_mask) { d_reach = (uint64_t*)b; b += (size_t)V * 8; }
+  int32_t* d_ids = (int32_t*)b; b += (size_t)m * k * 4;
+  int32_t* d_ties = (int32_t*)b; b += (size_t)m * 4;
+  uint32_t* d_world = nullptr;
+  if (world) { d_world = (uint32_t*)b; b += (size_t)m * 4; }
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_q, q_xy, (size_t)m * 16, cudaMemcpyHostToDevice, st));
+  if (d_world) CUDA_TRY(ctx, cudaMemcpyAsync(d_world, world, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+  if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
+  GridDev g = grid_dev(ctx);
+  if (k == 1) knn_kernel<1><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, 1, d_reach, d_world, d_ids, d_dist, d_ties);
+  else if (k <= 8) knn_kernel<8><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, k, d_reach, d_world, d_ids, d_dist, nullptr);
+  else knn_kernel<32><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, k, d_reach, d_world, d_ids, d_dist, nullptr);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_ids, d_ids, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_dist) CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_dist, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
+  if (out_ties && k == 1) CUDA_TRY(ctx, cudaMemcpyAsync(out_ties, d_ties, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_nearest(porrt_ctx* ctx, const double* q_xy, int64_t m, const uint64_t* reach_mask, const uint32_t* world,
+                                int32_t* out_id, double* out_dist, int32_t* out_ties) {
+  CTX_CHECK(ctx);
+  return knn_host(ctx, q_xy, m, 1, reach_mask, world, out_id, out_dist, out_ties);
+}
+PORRT_API int32_t porrt_knn(porrt_ctx* ctx, const double* q_xy, int64_t m, int32_t k, int32_t* out_ids, double* out_dist) {
+  CTX_CHECK(ctx);
+  return knn_host(ctx, q_xy, m, k, nullptr, nullptr, out_ids, out_dist, nullptr);
+}

@@ -1,0 +1,68 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/porrt_b200.h
+declares (no compute calls -- there is no GPU here), and the product fails loudly without a device."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "porrt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(porrt_[a-z0-9_]+)\s*\(", src)))
+
+
+def _ensure_built():
+    so = os.path.join(ROOT, "po_rrt_b200", "libporrt_b200.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "po_rrt_b200", "csrc"), "-j4"], check=True, capture_output=True)
+    return so
+
+
+def test_header_is_plain_c():
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "porrt_b200.h")], check=True)
+
+
+def test_library_exports_every_declared_symbol():
+    so = _ensure_built()
+    out = subprocess.run(["nm", "-D", "--defined-only", so], check=True, capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (porrt_[a-z0-9_]+)", out))
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    missing = [s for s in declared if s not in exported]
+    assert not missing, "declared in include/porrt_b200.h but not exported: %s" % missing
+
+
+def test_ctypes_signatures_cover_header():
+    from po_rrt_b200 import _lib
+    _ensure_built()
+    _lib.load()  # AttributeError if a typed symbol is missing from the .so
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+
+
+def test_sm100a_code_present():
+    so = _ensure_built()
+    out = subprocess.run(["cuobjdump", "--list-elf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback():
+    import torch
+    import po_rrt_b200 as P
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    _ensure_built()
+    with pytest.raises(P.PorrtError):
+        P.Context()
+
+
+def test_product_does_not_touch_oracle():
+    pkg = os.path.join(ROOT, "po_rrt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in text and "liboracle" not in text and "porrt_oracle" not in text, f

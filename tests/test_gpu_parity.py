@@ -1,0 +1,434 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Integer / index results must be bit-exact; f64 values are compared for exact equality unless stated."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+import po_rrt_b200 as P
+from po_rrt_b200 import synth
+import porrt_testutil as util
+
+pytestmark = pytest.mark.gpu
+INF = float("inf")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = P.Context(0)
+    yield c
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------------- maps
+def _check_edges(omap, pmap, a, b):
+    want = omap.edge_validity(a, b)
+    got, masks = pmap.transition_validator(a, b, want_masks=True)
+    assert got.dtype == np.int32
+    np.testing.assert_array_equal(got.astype(np.int64), want)
+    wv = pmap.world_validities_words()
+    exp_masks = np.where((want >= 0)[:, None], wv[np.clip(want, 0, None)], 0)
+    np.testing.assert_array_equal(masks, exp_masks)
+    return want
+
+
+def test_door_map_info_and_validities(ctx):
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    assert (pmap.n_zones, pmap.n_worlds(), pmap.n_validities) == (omap.n_zones, omap.n_worlds, omap.n_validities) == (3, 8, 4)
+    np.testing.assert_array_equal(pmap.world_validities(), omap.world_validities())
+    np.testing.assert_array_equal(pmap.zone_positions(), omap.zone_positions())
+
+
+def test_door_edges_random(ctx):
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    a, b = synth.edges(200_000, seed=2, max_len=0.1)
+    want = _check_edges(omap, pmap, a, b)
+    # the batch exercises every outcome
+    assert (want == -1).any() and (want == omap.n_validities - 1).any() and ((want >= 0) & (want < 3)).any()
+
+
+def test_door_edges_long_and_degenerate(ctx):
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    a, b = synth.edges(50_000, seed=7, max_len=2.5)      # up to the whole map: many 128-pixel rounds
+    _check_edges(omap, pmap, a, b)
+    p = synth.points(5_000, seed=8)
+    _check_edges(omap, pmap, p, p)                        # zero-length edges (dx_oct == 0)
+    q = p + np.array([1.0 / 256, 0.0])                    # one-pixel steps (dx_oct == 1)
+    _check_edges(omap, pmap, p, np.clip(q, -1, 1 - 2.0 ** -20))
+
+
+def test_door_edges_direction_matters(ctx):
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    a, b = synth.edges(100_000, seed=9, max_len=0.3)
+    fwd = _check_edges(omap, pmap, a, b)
+    bwd = _check_edges(omap, pmap, b, a)
+    assert (fwd != bwd).any()  # a->b and b->a visit different pixels
+
+
+def test_door_edges_panics(ctx):
+    """adjacent zones (multi-zone assert), gray pixels without zone id (unwrap), out-of-bounds endpoints"""
+    size = 256
+    occ = np.full((size, size), 255, np.uint8)
+    zones = np.full((size, size), 255, np.uint8)
+    occ[100:140, 60:70] = 128; zones[100:140, 60:70] = 0
+    occ[100:140, 70:80] = 128; zones[100:140, 70:80] = 1     # touches zone 0
+    occ[100:140, 84:90] = 0                                   # obstacle right after
+    occ[30:40, 30:200] = 90                                   # gray without zone id
+    occ[200:210, :] = 0
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    rng = np.random.default_rng(4)
+    a = rng.uniform(-1.2, 1.2, (150_000, 2))                  # some endpoints outside the map
+    b = a + rng.uniform(-0.4, 0.4, (150_000, 2))
+    want = _check_edges(omap, pmap, a, b)
+    for code in (O.PANIC_OOB, O.PANIC_ZONE_UNWRAP, O.PANIC_MULTI_ZONE, O.NONE):
+        assert (want == code).any(), code
+    sv = omap.state_validity(a)
+    np.testing.assert_array_equal(pmap.state_validity(a).astype(np.int64), sv)
+    assert (sv == O.PANIC_OOB).any() and (sv == O.PANIC_ZONE_UNWRAP).any()
+
+
+def test_door_without_zones(ctx):
+    occ, _ = util.small_door_map(256, 1)
+    occ[occ == 128] = 255
+    omap, pmap = util.make_pair(ctx, occ, None, P.DOOR)
+    assert pmap.n_worlds() == 1 and pmap.n_validities == 1
+    a, b = synth.edges(50_000, seed=3, max_len=0.2)
+    _check_edges(omap, pmap, a, b)
+    np.testing.assert_array_equal(pmap.state_validity(a).astype(np.int64), omap.state_validity(a))
+
+
+def test_shelf_edges_states_visibility(ctx):
+    occ, zones = synth.shelf_map(400, n_rects=20, n_zones=5, seed=6)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.6)
+    assert pmap.n_worlds() == omap.n_worlds == 5 and pmap.n_validities == 1
+    np.testing.assert_array_equal(pmap.world_validities(), omap.world_validities())
+    a, b = synth.edges(150_000, seed=12, max_len=0.5)
+    want = _check_edges(omap, pmap, a, b)
+    assert (want == 0).any() and (want == -1).any()
+    np.testing.assert_array_equal(pmap.state_validity(a).astype(np.int64), omap.state_validity(a))
+    pts = synth.points(20_000, seed=13)
+    wm, wp = omap.visible_zones(pts)
+    gm, gs = pmap.visible_zones(pts)
+    np.testing.assert_array_equal(gm, wm)
+    np.testing.assert_array_equal(gs.astype(np.int64), wp)
+    assert (wm != 0).any()
+
+
+def test_door_visibility(ctx):
+    occ, zones = util.planning_door_map(200)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.5)
+    pts = synth.points(30_000, seed=14)
+    wm, wp = omap.visible_zones(pts)
+    gm, gs = pmap.visible_zones(pts)
+    np.testing.assert_array_equal(gm, wm)
+    np.testing.assert_array_equal(gs.astype(np.int64), wp)
+    assert len(np.unique(wm)) >= 3
+
+
+def test_edges_host_pipeline_multi_chunk(ctx):
+    """> 1 Mi edges: exercises the chunked H2D | kernel | D2H pipeline and pageable staging"""
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    a, b = synth.edges(3_500_000, seed=21, max_len=0.05)
+    _check_edges(omap, pmap, a, b)
+
+
+def test_reachable_belief_states(ctx):
+    occ, zones = util.planning_door_map(200)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.5)
+    for b0 in ([0.25] * 4, [0.1, 0.1, 0.1, 0.7], [0.5, 0.5, 0.0, 0.0]):
+        np.testing.assert_array_equal(pmap.reachable_belief_states(b0), omap.reachable_belief_states(b0))
+    assert len(pmap.reachable_belief_states([0.25] * 4)) == 9      # map_io.rs:711-712
+    occ, zones = synth.shelf_map(200, n_zones=4)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    np.testing.assert_array_equal(pmap.reachable_belief_states([0.25] * 4), omap.reachable_belief_states([0.25] * 4))
+
+
+# ---------------------------------------------------------------------------------------------- nearest neighbours
+NODES = [[3.0, 6.0], [17.0, 15.0], [13.0, 15.0], [6.0, 12.0], [9.0, 1.0], [2.0, 7.0], [10.0, 19.0]]
+CENTERS = [[17.0, 15.0], [9.1, 1.0], [2.0, 8.0], [15.0, 13.0], [3.0, 5.0], [13.0, 7.0]]
+
+
+def test_kdtree_golden_through_gpu(ctx):  # nearest_neighbor.rs:237-311
+    tree = P.KdTree(ctx, NODES)
+    for c in CENTERS:
+        d = sorted(((math.sqrt((n[0] - c[0]) ** 2 + (n[1] - c[1]) ** 2), i) for i, n in enumerate(NODES)))
+        ids, dist, _ = tree.nearest_neighbor([c])
+        assert ids[0] == d[0][1] and dist[0] == d[0][0]
+        for radius in range(1, 10):
+            offs, hits = tree.nearest_neighbors([c], float(radius))
+            assert list(hits) == sorted(i for dd, i in d if dd <= radius)
+    # filtered sequences (:267-311): validator = reach bit
+    def filt(q, excluded):
+        reach = np.ones(len(NODES), np.uint64)
+        reach[list(excluded)] = 0
+        return int(tree.nearest_neighbor([q], reach, [0])[0][0])
+    seq = [(0, []), (5, [0]), (3, [0, 5]), (4, [0, 5, 3]), (2, [0, 5, 3, 4]), (6, [0, 5, 3, 4, 2]), (1, [0, 5, 3, 4, 2, 6])]
+    for expect, excl in seq:
+        assert filt([3.1, 6.0], excl) == expect
+    for expect, excl in [(2, []), (1, [2]), (6, [2, 1]), (3, [2, 1, 6])]:
+        assert filt([13.0, 15.1], excl) == expect
+    assert filt([3.1, 6.0], range(7)) == -1
+
+
+def _oracle_tree(pts):
+    t = O.KdTree(pts[0], 0)
+    t.add_batch(pts[1:], 1)
+    return t
+
+
+def test_radius_query_vs_oracle(ctx):
+    pts = synth.points(50_000, seed=3)
+    q = synth.points(4_000, seed=4)
+    otree = _oracle_tree(pts)
+    tree = P.KdTree(ctx, pts, cell_size=0.02)
+    rng = np.random.default_rng(5)
+    radius = rng.uniform(0.0, 0.05, len(q))
+    radius[:10] = 0.0
+    q[:5] = pts[:5]                                           # exact duplicates at radius 0
+    offs, ids = tree.nearest_neighbors(q, radius)
+    ooffs, oids, tot = otree.radius_batch(q, radius, cap=len(ids) + 10)
+    assert tot == len(ids)
+    np.testing.assert_array_equal(offs, ooffs)
+    for k in range(len(q)):
+        got = ids[offs[k]:offs[k + 1]]
+        assert (np.diff(got) > 0).all()
+        np.testing.assert_array_equal(got, np.sort(oids[ooffs[k]:ooffs[k + 1]]))
+    assert list(ids[offs[0]:offs[1]]) == [0]
+    # kd pre-order restored by rank
+    rank = tree.preorder_rank()
+    for k in range(0, len(q), 37):
+        got = ids[offs[k]:offs[k + 1]]
+        np.testing.assert_array_equal(got[np.argsort(rank[got], kind="stable")], oids[ooffs[k]:ooffs[k + 1]])
+
+
+def test_radius_threshold_boundary(ctx):
+    """inclusive `<=` on the sqrt-ed distance: hits at exactly r, misses one ulp below"""
+    pts = np.array([[0.0, 0.0], [3.0, 4.0], [1.0, 1.0], [-0.3, 0.4]])
+    tree = P.KdTree(ctx, pts)
+    q = np.zeros((6, 2))
+    r = np.array([5.0, np.nextafter(5.0, 0), math.sqrt(2.0), np.nextafter(math.sqrt(2.0), 0), 0.5, np.nextafter(0.5, 0)])
+    offs, ids = tree.nearest_neighbors(q, r)
+    otree = _oracle_tree(pts)
+    for k in range(6):
+        assert sorted(otree.nearest_neighbors(q[k], r[k])) == list(ids[offs[k]:offs[k + 1]])
+    assert list(ids[offs[0]:offs[1]]) == [0, 1, 2, 3] and list(ids[offs[1]:offs[2]]) == [0, 2, 3]
+
+
+def test_prefix_and_filtered_radius(ctx):
+    pts = synth.points(20_000, seed=31)
+    tree = P.KdTree(ctx, pts, cell_size=0.03)
+    k = np.arange(1, 20_000, 7)
+    offs, ids = tree.nearest_neighbors(pts[k], 0.04, prefix_limit=k)
+    d = None
+    for n, kk in enumerate(k[:200]):
+        got = ids[offs[n]:offs[n + 1]]
+        dd = np.sqrt(((pts[:kk] - pts[kk]) ** 2).sum(1))
+        np.testing.assert_array_equal(got, np.nonzero(dd <= 0.04)[0])
+    rng = np.random.default_rng(2)
+    reach = rng.integers(0, 2 ** 63, len(pts), dtype=np.uint64)
+    world = rng.integers(0, 63, 300).astype(np.uint32)
+    offs, ids = tree.nearest_neighbors(pts[:300], 0.05, reach_mask=reach, world=world)
+    for n in range(300):
+        dd = np.sqrt(((pts - pts[n]) ** 2).sum(1))
+        ok = ((reach >> np.uint64(world[n])) & np.uint64(1)).astype(bool)
+        np.testing.assert_array_equal(ids[offs[n]:offs[n + 1]], np.nonzero((dd <= 0.05) & ok)[0])
+
+
+def test_nearest_vs_oracle(ctx):
+    pts = synth.points(30_000, seed=41)
+    q = np.vstack([synth.points(5_000, seed=42), synth.points(200, seed=43, low=-1.5, up=1.5)])
+    otree = _oracle_tree(pts)
+    tree = P.KdTree(ctx, pts)
+    ids, dist, ties = tree.nearest_neighbor(q)
+    want = otree.nearest_batch(q)
+    assert (ties == 1).all()
+    np.testing.assert_array_equal(ids.astype(np.int64), want)
+    np.testing.assert_array_equal(dist, np.sqrt(((pts[want] - q) ** 2).sum(1)))
+    # filtered: random reachability bits, world per query (pto.rs:74-77)
+    rng = np.random.default_rng(44)
+    reach = rng.integers(0, 2 ** 63, len(pts), dtype=np.uint64)
+    world = rng.integers(0, 63, len(q)).astype(np.uint32)
+    ids, _, ties = tree.nearest_neighbor(q, reach, world)
+    want = otree.nearest_batch(q, reach, world)
+    np.testing.assert_array_equal(ids[ties == 1].astype(np.int64), want[ties == 1])
+    assert (ties == 1).all()
+
+
+def test_knn_vs_bruteforce(ctx):
+    pts = synth.points(8_000, seed=51)
+    q = synth.points(500, seed=52)
+    tree = P.KdTree(ctx, pts)
+    for k in (1, 5, 16, 32):
+        ids, dist = tree.knn(q, k)
+        d2 = ((pts[None, :, :] - q[:, None, :]) ** 2).sum(2)
+        order = np.lexsort((np.broadcast_to(np.arange(len(pts)), d2.shape), d2), axis=1)[:, :k]
+        np.testing.assert_array_equal(ids, order)
+        np.testing.assert_array_equal(dist, np.sqrt(np.take_along_axis(d2, order, 1)))
+    ids, dist = P.KdTree(ctx, pts[:3]).knn(q[:4], 5)   # fewer vertices than k: padded
+    assert (ids[:, 3:] == -1).all() and np.isinf(dist[:, 3:]).all()
+
+
+# ---------------------------------------------------------------------------------------------- PRM
+def _prm_compare(ctx, occ, zones, kind, n_iter, max_step, search_radius, start=(0.0, 0.0)):
+    omap, pmap = util.make_pair(ctx, occ, zones, kind, 0.3)
+    oprm = O.PRM(omap, util.LOW, util.UP, seed=0)
+    oprm.init(start)
+    oprm.grow_graph(max_step, search_radius, n_iter)
+    samples = O.Pcg64(0).sample_states(util.LOW, util.UP, n_iter)   # the ContinuousSampler stream the oracle consumed
+    prm = P.PRM(pmap)
+    prm.init(start)
+    prm.grow_graph(samples, max_step, search_radius)
+    xy, _, rp, col, _ = oprm.graph.export(0)
+    np.testing.assert_array_equal(prm.states, xy)
+    np.testing.assert_array_equal(prm.row_ptr, rp)
+    np.testing.assert_array_equal(prm.col, col)                      # children in the reference's insertion order
+    _, _, rpp, colp, _ = oprm.graph.export(1)
+    np.testing.assert_array_equal(prm.row_ptr, rpp)
+    np.testing.assert_array_equal(prm.col, colp)                     # parents(k) == children(k) as sequences
+    return prm, oprm
+
+
+def test_prm_build_door(ctx):
+    occ, zones = util.small_door_map(512, 3)
+    prm, _ = _prm_compare(ctx, occ, zones, P.DOOR, 6000, 0.1, 2.0)
+    assert len(prm.col) > 20_000
+
+
+def test_prm_build_shelf_reference_params(ctx):  # prm.rs:136-155: grow_graph(0.1, 5.0, 1500)
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    _prm_compare(ctx, occ, zones, P.SHELF, 1500, 0.1, 5.0)
+
+
+def test_prm_plan_path(ctx):
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    prm, oprm = _prm_compare(ctx, occ, zones, P.SHELF, 2500, 0.1, 5.0)
+    # PRM::plan_path (prm.rs:111-122): nearest start/goal vertex, dijkstra towards the goal
+    tree = P.KdTree(ctx, prm.states)
+    ids, _, _ = tree.nearest_neighbor([[0.0, 0.0], [-0.7, 0.8]])
+    dist, sweeps = P.dijkstra_worlds(ctx, prm.row_ptr, prm.col, prm.states, None, None, [int(ids[1])])
+    want = oprm.graph.dijkstra([int(ids[1])])
+    np.testing.assert_array_equal(dist, want)
+    assert np.isfinite(dist[ids[0]])
+
+
+# ---------------------------------------------------------------------------------------------- SSSP
+def test_dijkstra_golden_through_gpu(ctx):  # pto_graph.rs:625-678
+    def run(g, finals, **kw):
+        xy, nvid, rp, col, ev = g.export(0)
+        d, _ = P.dijkstra_worlds(ctx, rp, col, xy, None, None, finals)
+        return list(d)
+    from test_oracle_golden import minimal_graph, grid_graph, oriented_grid_graph, diamond_graph_2_worlds
+    assert run(minimal_graph(), [1]) == [1.0, 0.0]
+    assert run(grid_graph(), [8]) == [4.0, 3.0, 2.0, 3.0, 2.0, 1.0, 2.0, 1.0, 0.0]
+    assert run(grid_graph(), [7, 5]) == [3.0, 2.0, 1.0, 2.0, 1.0, 0.0, 1.0, 0.0, 1.0]
+    assert run(grid_graph(), []) == [INF] * 9
+    assert run(oriented_grid_graph(), [3]) == [2.0, 1.0, INF, 0.0]
+    g = diamond_graph_2_worlds()
+    xy, nvid, rp, col, ev = g.export(0)
+    d, _ = P.dijkstra_worlds(ctx, rp, col, xy, nvid, P.words_from_bits([[1, 0], [0, 1], [1, 1]]), [[3], [3]])
+    s2 = math.sqrt(2.0)
+    assert d.tolist() == [[s2 + s2, INF, s2, 0.0], [s2 + s2, s2, INF, 0.0]]
+
+
+def _grow_pto(omap, start, goals, max_step, search_radius, n_min, n_max=100000):
+    goal = O.SquareGoal(goals, 0.05)
+    pto = O.PTO(omap, util.LOW, util.UP, seed=0)
+    rc = pto.grow_graph(start, goal, max_step, search_radius, n_min, n_max)
+    assert rc == 0, rc
+    return pto
+
+
+def test_qmdp_costs_shelf_config2(ctx):
+    """BASELINE config 2 shape: PTO growth (sequential, CPU side) on a 2-shelf map, then plan_qmdp on the GPU"""
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    zp = omap.zone_positions()
+    goals = [((float(zp[0][0]) - 0.06, float(zp[0][1])), [1, 0]), ((float(zp[1][0]) - 0.06, float(zp[1][1])), [0, 1])]
+    pto = _grow_pto(omap, (-0.8, -0.8), goals, 0.05, 5.0, 2000)
+    want = pto.plan_qmdp()
+    xy, nvid, rp, col, ev = pto.graph.export(0)
+    finals = [pto.reach.get_final_nodes_for_world(w) for w in range(2)]
+    got, sweeps = P.dijkstra_worlds(ctx, rp, col, xy, nvid, pmap.world_validities_words(), finals)
+    np.testing.assert_array_equal(got, want)   # bit-exact f64
+    assert np.isfinite(want).any()
+
+
+def test_qmdp_costs_door(ctx):
+    occ, zones = util.planning_door_map(200)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    pto = _grow_pto(omap, (-0.8, -0.8), [((0.8, 0.8), [1, 1, 1, 1])], 0.05, 5.0, 3000)
+    want = pto.plan_qmdp()
+    xy, nvid, rp, col, ev = pto.graph.export(0)
+    finals = [pto.reach.get_final_nodes_for_world(w) for w in range(4)]
+    got, _ = P.dijkstra_worlds(ctx, rp, col, xy, nvid, pmap.world_validities_words(), finals)
+    np.testing.assert_array_equal(got, want)
+    assert not np.array_equal(want[0], want[3])
+
+
+# ---------------------------------------------------------------------------------------------- belief space
+def _belief_compare(ctx, omap, pmap, pto, b0):
+    pto.build_belief_graph(b0)
+    want = pto.compute_expected_costs_to_goals()
+    typ, bid, rp_b, col_b = pto.belief_graph.export()
+    opol = pto.extract_policy()
+    xy, nvid, rp, col, ev = pto.graph.export(0)
+    fin_ids, fin_bits = pto.reach.finals()
+    plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
+    B = len(plan.beliefs)
+    np.testing.assert_array_equal(plan.beliefs, pto.beliefs())
+    np.testing.assert_array_equal(plan.dist.reshape(-1), want)                 # bit-exact expected costs
+    np.testing.assert_array_equal(plan.type.reshape(-1).astype(np.int32), typ)  # Unknown / Action / Observation
+    assert plan.expected_cost == opol.expected_costs
+    np.testing.assert_array_equal(plan.policy_node.astype(np.int64) * B + plan.policy_belief, opol.original)
+    np.testing.assert_array_equal(plan.policy_parent.astype(np.int64), opol.parent)
+    np.testing.assert_array_equal(np.nonzero(plan.policy_leaf)[0], opol.leafs)
+    return plan, want, typ
+
+
+def test_belief_planning_door(ctx):
+    occ, zones = util.planning_door_map(200)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    pto = _grow_pto(omap, (-0.8, -0.8), [((0.8, 0.8), [1, 1, 1, 1])], 0.05, 5.0, 3000)
+    plan, want, typ = _belief_compare(ctx, omap, pmap, pto, [0.1, 0.1, 0.1, 0.7])
+    assert (typ == O.OBSERVATION).any() and (typ == O.ACTION).any() and np.isfinite(want[0])
+    assert plan.policy_leaf.sum() >= 2
+
+
+def test_belief_planning_shelf_config2(ctx):
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    zp = omap.zone_positions()
+    goals = [((float(zp[0][0]) - 0.06, float(zp[0][1])), [1, 0]), ((float(zp[1][0]) - 0.06, float(zp[1][1])), [0, 1])]
+    pto = _grow_pto(omap, (-0.8, -0.8), goals, 0.05, 5.0, 2000)
+    plan, want, typ = _belief_compare(ctx, omap, pmap, pto, [0.2, 0.8])
+    assert np.isfinite(want[0])
+
+
+def test_build_belief_graph_mock(ctx):
+    """pto.rs:548-590 'mock graph growth' on a stand-in map: node 2 sees the door, belief jump only there"""
+    size = 200
+    occ = np.full((size, size), 255, np.uint8)
+    zones = np.full((size, size), 255, np.uint8)
+    occ[85:95, 150:160] = 128        # the door, around (0.55, 0.1)
+    zones[85:95, 150:160] = 0
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.15)
+    pto = O.PTO(omap, util.LOW, util.UP)
+    pto.set_mock(2, [[0, 1], [1, 1]])
+    for s, v in [([0.55, -0.8], 1), ([-0.42, -0.38], 1), ([0.54, 0.0], 1), ([0.54, 0.1], 0), ([-0.97, 0.65], 1), ([0.55, 0.9], 1)]:
+        pto.graph.add_node(s, v)
+    for a, b, v in [(0, 1, 1), (1, 2, 1), (2, 3, 0), (3, 5, 0), (1, 4, 1), (4, 5, 1)]:
+        pto.graph.add_bi_edge(a, b, v)
+    pto.reach.set_root([1, 1])
+    for _ in range(5):
+        pto.reach.add_node([1, 1])
+    pto.reach.add_final_node(5, [1, 1])
+    plan, want, typ = _belief_compare(ctx, omap, pmap, pto, [0.5, 0.5])
+    typ_o, bid, rp_b, col_b = pto.belief_graph.export()
+    assert list(col_b[rp_b[6]:rp_b[7]]) == [7, 8]       # observation transitions (pto.rs:579)
+    assert plan.type[2, 0] == P.NODE_OBSERVATION
