@@ -31,7 +31,7 @@ N_WORLDS = 64
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--edges", type=int, default=1 << 24, help="edges per GPU per step")
@@ -64,7 +64,7 @@ class ClockSampler:
         self.rows = []
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -161,7 +161,8 @@ def main():
     E = args.edges
 
     # ---- device-resident arm
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: kernels and the timing events share it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     d_a, d_b = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     d_vid = torch.empty(E, dtype=torch.int32, device=dev)
@@ -176,11 +177,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step_dev()
     barrier()
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record(stream)

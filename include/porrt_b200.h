@@ -52,7 +52,8 @@ typedef struct porrt_ctx porrt_ctx;
 /* ------------------------------------------------------------------ context */
 int32_t porrt_ctx_create(int32_t device, porrt_ctx** out_ctx);
 int32_t porrt_ctx_destroy(porrt_ctx* ctx);
-/* run all subsequent work of this ctx on an existing CUDA stream (e.g. torch's current stream); NULL = own stream */
+/* run all subsequent work of this ctx on an existing CUDA stream (e.g. a torch.cuda.Stream); NULL = the ctx's own
+ * stream.  Pass cudaStreamLegacy ((void*)1) to address the legacy default stream explicitly. */
 int32_t porrt_ctx_set_stream(porrt_ctx* ctx, void* cuda_stream);
 int32_t porrt_ctx_synchronize(porrt_ctx* ctx);
 const char* porrt_last_error(porrt_ctx* ctx);

@@ -340,17 +340,18 @@ PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* ro
       dist0[(size_t)f * W + w] = 0.0;
     }
   DevBuf& g = ctx->scratch[3];
-  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 16 + (size_t)V * W * 17 + 256;
+  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 16 + (size_t)V * W * 17 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
-  int64_t* d_row = (int64_t*)b; b += (size_t)(V + 1) * 8;
-  double* d_cost = (double*)b; b += (size_t)E * 8;
-  double* d_xy = (double*)b; b += (size_t)V * 16;
-  double* d_dist = (double*)b; b += (size_t)V * W * 8;
-  double* d_out = (double*)b; b += (size_t)V * W * 8;
-  int32_t* d_col = (int32_t*)b; b += (size_t)E * 4;
-  int32_t* d_changed = (int32_t*)b; b += 16;
-  uint8_t* d_ok = (uint8_t*)b;
+  auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };  // keeps double2 loads aligned
+  int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
+  double* d_cost = (double*)take((size_t)E * 8);
+  double* d_xy = (double*)take((size_t)V * 16);
+  double* d_dist = (double*)take((size_t)V * W * 8);
+  double* d_out = (double*)take((size_t)V * W * 8);
+  int32_t* d_col = (int32_t*)take((size_t)E * 4);
+  int32_t* d_changed = (int32_t*)take(16);
+  uint8_t* d_ok = (uint8_t*)take((size_t)V * W);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
   if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
