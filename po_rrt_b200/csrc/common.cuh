@@ -47,6 +47,8 @@ struct PinBuf {  // grow-only pinned host staging
 // Device-side description of an uploaded map (passed by value to kernels).
 struct MapDev {
   const uint8_t* grid;  // fused code grid, tiled (see map.cu: tile_addr)
+  const uint8_t* coarse[3]; // one class byte per 8x8 / 16x16 / 32x32 block, row-major (map.cu: C_* flags)
+  int32_t cw[3];            // their row pitches
   int32_t H, W;         // logical size
   int32_t tiles_x;      // 128-byte tiles (16 x 8 px) per tile row
   int32_t kind;         // PORRT_DOMAIN_*
@@ -75,7 +77,8 @@ struct porrt_ctx {
   std::vector<uint64_t> validities;     // [n_validities * mask_words]
   std::vector<double> zone_pos;         // [2 * n_zones]
   std::vector<uint64_t> zone_world_masks;  // DOOR: zones_to_worlds [n_zones * mask_words]
-  DevBuf d_grid, d_validities, d_zone_pos;
+  DevBuf d_grid, d_coarse[3], d_validities, d_zone_pos;
+  int edge_variant = 3;  // 1: byte-grid warp walk; 2/3/4: class bytes + flattened strips with 8/16/32-px blocks
   // host copies of the raw images are NOT kept: the product never walks pixels on the CPU.
 
   // ---- vertices / cell grid (nn.cu)

@@ -14,6 +14,8 @@
 // exact-division magic), then the warp walks the 32 edges one after the other with its lanes striding the
 // Bresenham parameter k (pixel k of the line in closed form, A5), four 32-pixel chunks in flight per lane,
 // and reduces each chunk with __ballot_sync / __reduce_min_sync / __reduce_max_sync.
+#include <cstdlib>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -230,6 +232,271 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_kernel(MapDev m, con
   }
 }
 
+
+// ================================================================================================ edge validity, v2
+// Hierarchical, work-flattened variant.  v1 above is instruction-issue bound (ncu r1: 322 warp instructions per edge,
+// IPC 3.0 of 4): every pixel costs address arithmetic + a byte load + ballots.  v2 adds one CLASS byte per BS x BS
+// block (all free / all obstacle / all low / needs-per-pixel [+ contains gray]) and cuts the line into strips of <= BS
+// pixels aligned to the block grid along the major axis; a strip touches at most two blocks (slope <= 1 in octant
+// space), so two class bytes settle it unless a block is mixed.  Only mixed strips are queued (shared memory) and
+// resolved per pixel afterwards, 32/BS strips per warp round, and strips of edges already known to be blocked are
+// dropped.  Work is flattened: the strips of the warp's 32 edges form one sequence that is cut into 32 equal
+// contiguous shares, one per lane, so lanes stay busy whatever the mix of edge lengths.
+// Exactness: any_obstacle / any_low / zone min-max are order-free reductions; whenever order could matter (two
+// different zones, a gray pixel without zone id, an end point outside the map) the edge is re-walked sequentially.
+#define C_OBST 1   // every pixel of the block is obstacle (DOOR: 0, SHELF: < 127)
+#define C_FINE 2   // block is not uniform: look at the pixels
+#define C_LOW 4    // SHELF: every pixel is a low obstacle (127..254)
+#define C_GRAY 8   // DOOR: block contains gray pixels (zone ids needed) -- implies C_FINE
+
+#define F_OBST 1
+#define F_LOW 2
+
+
+template <int KIND>
+__global__ void coarse_build_kernel(const uint8_t* __restrict__ grid, int H, int W, int tiles_x, int log_bs, int cw, int ch,
+                                    uint8_t* __restrict__ coarse) {
+  // one warp per block
+  const int lane = threadIdx.x & 31;
+  const int64_t blk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blk >= (int64_t)cw * ch) return;
+  const int bi = (int)(blk / cw), bj = (int)(blk % cw), bs = 1 << log_bs;
+  int n = 0, n_obst = 0, n_free = 0, n_low = 0, n_gray = 0;
+  for (int p = lane; p < bs * bs; p += 32) {
+    const int i = (bi << log_bs) + (p >> log_bs), j = (bj << log_bs) + (p & (bs - 1));
+    if (i < H && j < W) {
+      const uint32_t c = grid[tile_addr(i, j, tiles_x)];
+      ++n;
+      if (c == 255) ++n_free;
+      else if (KIND == PORRT_DOMAIN_SHELF) { if (c < 127) ++n_obst; else ++n_low; }
+      else { if (c == 0) ++n_obst; else ++n_gray; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, o); n_obst += __shfl_xor_sync(0xffffffffu, n_obst, o);
+    n_free += __shfl_xor_sync(0xffffffffu, n_free, o); n_low += __shfl_xor_sync(0xffffffffu, n_low, o);
+    n_gray += __shfl_xor_sync(0xffffffffu, n_gray, o);
+  }
+  if (lane == 0) {
+    uint8_t cls;
+    if (n_free == n) cls = 0;
+    else if (n_obst == n) cls = C_OBST;
+    else if (KIND == PORRT_DOMAIN_SHELF && n_low == n) cls = C_LOW;
+    else cls = C_FINE | (n_gray ? C_GRAY : 0);
+    coarse[blk] = cls;
+  }
+}
+
+struct EdgeRec {        // 32 bytes per edge, shared memory, already unpacked for the strip arithmetic
+  int32_t c0, n0;       // start pixel: major-axis coordinate, minor-axis coordinate
+  int32_t dxo, dyo;     // octant-space deltas (major, minor)
+  uint32_t m_lo, m_hi;  // exact-division magic (see EdgeSetup)
+  int32_t dirs;         // bit0: major axis is i (rows), bit1: major step is -1, bit2: minor step is -1, bit3: no-op edge
+  int32_t n_items;      // strips (>= 1; a no-op edge owns one empty strip so that prefix sums stay strictly increasing)
+};
+
+__device__ __forceinline__ int32_t rec_minor(const EdgeRec& r, int32_t k) {
+  return r.dxo > 1 ? (int32_t)__umul64hi((uint64_t)((uint32_t)k * (uint32_t)r.dyo), ((uint64_t)r.m_hi << 32) | r.m_lo) : k * r.dyo;
+}
+__device__ __forceinline__ uint32_t rec_pixel_addr(const MapDev& m, const EdgeRec& r, int32_t k, int32_t mnr) {
+  const int32_t major = r.c0 + ((r.dirs & 2) ? -k : k), minor = r.n0 + ((r.dirs & 4) ? -mnr : mnr);
+  return (r.dirs & 1) ? tile_addr(major, minor, m.tiles_x) : tile_addr(minor, major, m.tiles_x);
+}
+
+#define V2_QCAP 480  // queue entries per warp (a batch of 32 edges of <= 410 px needs at most ~32*27 at BS = 16)
+
+template <int KIND, int LOG_BS, bool INDEXED>
+__global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, const double2* __restrict__ from,
+                                                                      const double2* __restrict__ to, int64_t n,
+                                                                      int32_t* __restrict__ out_vid,
+                                                                      uint64_t* __restrict__ out_mask,
+                                                                      const uint64_t* __restrict__ validities,
+                                                                      const int32_t* __restrict__ from_idx,
+                                                                      const int32_t* __restrict__ to_idx) {
+  constexpr int BS = 1 << LOG_BS;
+  constexpr int WARPS = EDGE_BLOCK / 32;
+  __shared__ EdgeRec s_rec[WARPS][32];
+  __shared__ uint32_t s_flags[WARPS][32];     // F_* per edge
+  __shared__ uint32_t s_zmin[WARPS][32], s_zmax[WARPS][32];
+  __shared__ uint32_t s_queue[WARPS][V2_QCAP];
+  __shared__ int32_t s_qcount[WARPS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint8_t* __restrict__ coarse = m.coarse[LOG_BS - 3];
+  const int cw = m.cw[LOG_BS - 3];
+  const int64_t warp = ((int64_t)blockIdx.x * EDGE_BLOCK + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * EDGE_BLOCK) >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // pass 2: per-pixel resolution of the queued strips; one lane per strip, pixels in order, minor coordinate stepped
+  // incrementally; strips of edges that are already blocked are dropped first (unless zone ids are at stake)
+  auto drain = [&]() {
+    __syncwarp();
+    const int qn = s_qcount[wib];
+    int live_n = 0;
+    for (int q0 = 0; q0 < qn; q0 += 32) {          // in-place compaction of the live entries
+      const int q = q0 + lane;
+      uint32_t ent = 0;
+      bool live = false;
+      if (q < qn) {
+        ent = s_queue[wib][q];
+        live = !(s_flags[wib][ent & 31] & F_OBST) || (ent & (1u << 25));
+      }
+      const unsigned lv = __ballot_sync(0xffffffffu, live);
+      __syncwarp();
+      if (live) s_queue[wib][live_n + __popc(lv & lt_mask)] = ent;
+      live_n += __popc(lv);
+      __syncwarp();
+    }
+    for (int q0 = 0; q0 < live_n; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < live_n) {
+        const uint32_t ent = s_queue[wib][q];
+        const int e = ent & 31;
+        const EdgeRec r = s_rec[wib][e];
+        int k = (int)((ent >> 5) & 0x7fff);
+        const int k_end = k + (int)((ent >> 20) & 31);
+        int32_t mnr = rec_minor(r, k);
+        int32_t rem = k * r.dyo - mnr * r.dxo;   // k*dyo = mnr*dxo + rem, 0 <= rem < dxo (fits: both products < 2^31)
+        uint32_t f = 0, zmin = 255, zmax = 0;
+        for (; k <= k_end; ++k) {
+          const uint32_t code = __ldg(m.grid + rec_pixel_addr(m, r, k, mnr));
+          if (code != 255) {
+            if (KIND == PORRT_DOMAIN_SHELF) { f |= code < 127 ? F_OBST : F_LOW; }
+            else if (code == 0) f |= F_OBST;
+            else { zmin = min(zmin, code); zmax = max(zmax, code); }
+          }
+          rem += r.dyo;
+          if (rem >= r.dxo && r.dxo > 0) { rem -= r.dxo; ++mnr; }
+        }
+        if (f) atomicOr(&s_flags[wib][e], f);
+        if (zmax) { atomicMin(&s_zmin[wib][e], zmin); atomicMax(&s_zmax[wib][e], zmax); }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) s_qcount[wib] = 0;
+    __syncwarp();
+  };
+
+  for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
+    const int64_t eidx = base + lane;
+    // ---- per-lane setup of one edge
+    EdgeRec mine;
+    int my_flags = 0;  // bit0 start OOB, bit1 end OOB
+    mine.n_items = 1; mine.dirs = 8; mine.c0 = mine.n0 = mine.dxo = mine.dyo = 0; mine.m_lo = mine.m_hi = 0;
+    if (eidx < n) {
+      const double2 a = INDEXED ? from[from_idx[eidx]] : from[eidx];
+      const double2 b = INDEXED ? to[to_idx[eidx]] : to[eidx];
+      const EdgeSetup s = make_setup(m, a.x, a.y, b.x, b.y);
+      const int ui = (s.steps & 3) - 1, uj = ((s.steps >> 2) & 3) - 1, vi = ((s.steps >> 4) & 3) - 1, vj = ((s.steps >> 6) & 3) - 1;
+      mine.c0 = ui ? s.ai : s.aj; mine.n0 = ui ? s.aj : s.ai;
+      mine.dxo = s.dxo; mine.dyo = s.dyo; mine.m_lo = s.m_lo; mine.m_hi = s.m_hi;
+      mine.dirs = (ui ? 1 : 0) | ((ui + uj) < 0 ? 2 : 0) | ((vi + vj) < 0 ? 4 : 0);
+      my_flags = s.flags;
+      if (my_flags) mine.dirs |= 8;
+      else {
+        const int sgn = (mine.dirs & 2) ? -1 : 1;
+        const int b0 = mine.c0 >> LOG_BS, b1 = (mine.c0 + sgn * mine.dxo) >> LOG_BS;
+        mine.n_items = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;
+      }
+    }
+    s_rec[wib][lane] = mine;
+    s_flags[wib][lane] = 0; s_zmin[wib][lane] = 255; s_zmax[wib][lane] = 0;
+    int incl = mine.n_items;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 0) s_qcount[wib] = 0;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const bool may_overflow = total > V2_QCAP;     // warp-uniform
+    __syncwarp();
+
+    // ---- pass 1: strip w = 32*it + lane of the flattened sequence; neighbouring lanes work on neighbouring strips
+    for (int w0 = 0; w0 < total; w0 += 32) {
+      if (may_overflow && s_qcount[wib] > V2_QCAP - 32) drain();
+      // which edge owns flattened position w0 + lane: incl is strictly increasing over lanes, so the positions where
+      // an edge ends inside this window form a bitmask and a popcount ranks them (no search loop)
+      const int d = incl - w0;                                    // edge `lane` ends before window position d
+      const int e_base = __popc(__ballot_sync(0xffffffffu, d <= 0));
+      const unsigned marks = __reduce_or_sync(0xffffffffu, (d >= 1 && d <= 32) ? (1u << (d - 1)) : 0u);
+      const int e = min(31, e_base + __popc(marks & lt_mask));
+      const int p_prev = __shfl_sync(0xffffffffu, incl, (e + 31) & 31);
+      const int w = w0 + lane;
+      bool want = false;
+      uint32_t entry = 0;
+      if (w < total) {
+        const EdgeRec r = s_rec[wib][e];
+        if (!(r.dirs & 8)) {
+          const int t = w - (e ? p_prev : 0);
+          const int sgn = (r.dirs & 2) ? -1 : 1;
+          const int bm = (r.c0 >> LOG_BS) + sgn * t;
+          const int lo_raw = sgn * ((bm << LOG_BS) - r.c0) - ((r.dirs & 2) ? BS - 1 : 0);
+          const int k_lo = max(0, lo_raw), k_hi = min(r.dxo, lo_raw + BS - 1);
+          const int m_a = rec_minor(r, k_lo), m_b = rec_minor(r, k_hi);
+          const int bn_a = (r.n0 + ((r.dirs & 4) ? -m_a : m_a)) >> LOG_BS, bn_b = (r.n0 + ((r.dirs & 4) ? -m_b : m_b)) >> LOG_BS;
+          const int ia = (r.dirs & 1) ? bm * cw + bn_a : bn_a * cw + bm;
+          const int ib = (r.dirs & 1) ? bm * cw + bn_b : bn_b * cw + bm;
+          uint32_t c = coarse[ia];
+          if (ib != ia) c |= coarse[ib];
+          if (c) {
+            const uint32_t f = ((c & C_OBST) ? F_OBST : 0) | ((c & C_LOW) ? F_LOW : 0);
+            if (f) atomicOr(&s_flags[wib][e], f);
+            if ((c & C_FINE) && (!(f & F_OBST) || (c & C_GRAY))) {
+              want = true;
+              entry = (uint32_t)e | ((uint32_t)k_lo << 5) | ((uint32_t)(k_hi - k_lo) << 20) | ((c & C_GRAY) ? (1u << 25) : 0u);
+            }
+          }
+        }
+      }
+      const unsigned wants = __ballot_sync(0xffffffffu, want);
+      if (wants) {
+        const int qb = s_qcount[wib];
+        if (want) s_queue[wib][qb + __popc(wants & lt_mask)] = entry;
+        __syncwarp();
+        if (lane == 0) s_qcount[wib] = qb + __popc(wants);
+        __syncwarp();
+      }
+    }
+    // ---- pass 2: pixels of the strips that are still undecided
+    drain();
+
+    // ---- results
+    if (eidx < n) {
+      int32_t r;
+      bool slow = false;
+      if (my_flags & 1) r = PORRT_PANIC_OOB;
+      else if (my_flags & 2) slow = true;
+      else {
+        const uint32_t f = s_flags[wib][lane];
+        if (KIND == PORRT_DOMAIN_SHELF) r = (f & F_OBST) ? R_BLOCKED : ((f & F_LOW) ? R_LOW : R_FREE);
+        else {
+          const uint32_t zmin = s_zmin[wib][lane], zmax = s_zmax[wib][lane];
+          if (zmax != 0 && (zmin != zmax || zmax == 254)) slow = true;   // order of events decides: re-walk
+          else r = (f & F_OBST) ? R_BLOCKED : (zmax ? (int32_t)zmin - 1 : R_FREE);
+        }
+      }
+      if (slow) {
+        Walker wk;
+        const int sm = (mine.dirs & 2) ? -1 : 1, sn = (mine.dirs & 4) ? -1 : 1;
+        wk.dxo = mine.dxo; wk.dyo = mine.dyo; wk.M = ((uint64_t)mine.m_hi << 32) | mine.m_lo;
+        if (mine.dirs & 1) { wk.ai = mine.c0; wk.aj = mine.n0; wk.ui = sm; wk.uj = 0; wk.vi = 0; wk.vj = sn; }
+        else { wk.ai = mine.n0; wk.aj = mine.c0; wk.ui = 0; wk.uj = sm; wk.vi = sn; wk.vj = 0; }
+        r = walk_sequential<KIND>(m, wk);
+      }
+      const int32_t vid = walk_to_validity(m, r);
+      out_vid[eidx] = vid;
+      if (out_mask) {
+        if (m.mask_words == 1) out_mask[eidx] = vid >= 0 ? validities[vid] : 0ull;
+        else
+          for (int wd = 0; wd < m.mask_words; ++wd)
+            out_mask[eidx * m.mask_words + wd] = vid >= 0 ? validities[(int64_t)vid * m.mask_words + wd] : 0ull;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // is_state_valid + state_validity (map_io.rs:165-174,487-493 / map_shelves_io.rs:158-163,464-469); thread per state
 __global__ void state_validity_kernel(MapDev m, const double2* __restrict__ xy, int64_t n, int32_t* __restrict__ out_vid) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,6 +656,17 @@ PORRT_API int32_t porrt_map_upload(porrt_ctx* ctx, const uint8_t* occ, const uin
   fuse_tile_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->scratch[0].as<uint8_t>(), d_zone, H, W, tiles_x, tiles_y, kind,
                                                       ctx->d_grid.as<uint8_t>());
   LAUNCH_CHECK(ctx);
+  for (int lvl = 0; lvl < 3; ++lvl) {  // class bytes for 8x8, 16x16, 32x32 blocks
+    const int lg = 3 + lvl, bs = 1 << lg, cwl = (W + bs - 1) / bs, chl = (H + bs - 1) / bs;
+    CUDA_TRY(ctx, ctx->d_coarse[lvl].ensure((size_t)cwl * chl));
+    if (kind == PORRT_DOMAIN_SHELF)
+      coarse_build_kernel<PORRT_DOMAIN_SHELF><<<div_up((int64_t)cwl * chl * 32, 256), 256, 0, st>>>(ctx->d_grid.as<uint8_t>(), H, W, tiles_x, lg, cwl, chl, ctx->d_coarse[lvl].as<uint8_t>());
+    else
+      coarse_build_kernel<PORRT_DOMAIN_DOOR><<<div_up((int64_t)cwl * chl * 32, 256), 256, 0, st>>>(ctx->d_grid.as<uint8_t>(), H, W, tiles_x, lg, cwl, chl, ctx->d_coarse[lvl].as<uint8_t>());
+    LAUNCH_CHECK(ctx);
+    ctx->map.coarse[lvl] = ctx->d_coarse[lvl].as<uint8_t>();
+    ctx->map.cw[lvl] = cwl;
+  }
   CUDA_TRY(ctx, ctx->d_validities.ensure(validities.size() * 8));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_validities.p, validities.data(), validities.size() * 8, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, ctx->d_zone_pos.ensure(zone_pos.size() * 8 + 16));
@@ -398,6 +676,7 @@ PORRT_API int32_t porrt_map_upload(porrt_ctx* ctx, const uint8_t* occ, const uin
 
   MapDev& m = ctx->map;
   m.grid = ctx->d_grid.as<uint8_t>();
+  if (const char* v = getenv("PORRT_EDGE_VARIANT")) ctx->edge_variant = atoi(v);
   m.H = H; m.W = W; m.tiles_x = tiles_x; m.kind = kind; m.free_vid = n_validities - 1; m.mask_words = words;
   m.low0 = low[0]; m.low1 = low[1]; m.ppm = ppm; m.hm1 = (double)(H - 1);
   ctx->n_zones = n_zones; ctx->n_worlds = n_worlds; ctx->n_validities = n_validities; ctx->mask_words = words;
@@ -436,28 +715,35 @@ static int edge_grid(porrt_ctx* ctx, int64_t n) {
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
-int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
-                              int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st) {
+template <bool INDEXED>
+static int32_t launch_edges(porrt_ctx* ctx, const double2* from, const double2* to, int64_t n, int32_t* out_vid, uint64_t* out_mask,
+                            const int32_t* from_idx, const int32_t* to_idx, cudaStream_t st) {
   if (n == 0) return PORRT_OK;
   const uint64_t* val = ctx->d_validities.as<uint64_t>();
-  if (ctx->map.kind == PORRT_DOMAIN_SHELF)
-    edge_validity_kernel<PORRT_DOMAIN_SHELF, false><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)from_dev, (const double2*)to_dev, n, out_vid_dev, out_mask_dev, val, nullptr, nullptr);
-  else
-    edge_validity_kernel<PORRT_DOMAIN_DOOR, false><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)from_dev, (const double2*)to_dev, n, out_vid_dev, out_mask_dev, val, nullptr, nullptr);
+  const int grid = edge_grid(ctx, n);
+  const bool shelf = ctx->map.kind == PORRT_DOMAIN_SHELF;
+#define LAUNCH_V2(K, L) edge_validity_v2_kernel<K, L, INDEXED><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out_vid, out_mask, val, from_idx, to_idx)
+#define LAUNCH_V1(K) edge_validity_kernel<K, INDEXED><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out_vid, out_mask, val, from_idx, to_idx)
+  switch (ctx->edge_variant) {
+    case 1: if (shelf) LAUNCH_V1(PORRT_DOMAIN_SHELF); else LAUNCH_V1(PORRT_DOMAIN_DOOR); break;
+    case 2: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 3); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 3); break;
+    case 4: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 5); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 5); break;
+    default: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4); break;
+  }
+#undef LAUNCH_V1
+#undef LAUNCH_V2
   LAUNCH_CHECK(ctx);
   return PORRT_OK;
 }
 
+int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
+                              int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st) {
+  return launch_edges<false>(ctx, (const double2*)from_dev, (const double2*)to_dev, n, out_vid_dev, out_mask_dev, nullptr, nullptr, st);
+}
+
 int32_t map_edge_validity_indexed_dev(porrt_ctx* ctx, const double* xy_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev,
                                       int64_t n, int32_t* out_vid_dev, cudaStream_t st) {
-  if (n == 0) return PORRT_OK;
-  const uint64_t* val = ctx->d_validities.as<uint64_t>();
-  if (ctx->map.kind == PORRT_DOMAIN_SHELF)
-    edge_validity_kernel<PORRT_DOMAIN_SHELF, true><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)xy_dev, (const double2*)xy_dev, n, out_vid_dev, nullptr, val, from_idx_dev, to_idx_dev);
-  else
-    edge_validity_kernel<PORRT_DOMAIN_DOOR, true><<<edge_grid(ctx, n), EDGE_BLOCK, 0, st>>>(ctx->map, (const double2*)xy_dev, (const double2*)xy_dev, n, out_vid_dev, nullptr, val, from_idx_dev, to_idx_dev);
-  LAUNCH_CHECK(ctx);
-  return PORRT_OK;
+  return launch_edges<true>(ctx, (const double2*)xy_dev, (const double2*)xy_dev, n, out_vid_dev, nullptr, from_idx_dev, to_idx_dev, st);
 }
 
 PORRT_API int32_t porrt_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
