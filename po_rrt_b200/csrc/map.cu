@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_kernel(MapDev m, con
 // contiguous shares, one per lane, so lanes stay busy whatever the mix of edge lengths.
 // Exactness: any_obstacle / any_low / zone min-max are order-free reductions; whenever order could matter (two
 // different zones, a gray pixel without zone id, an end point outside the map) the edge is re-walked sequentially.
-#define C_OBST 1   // every pixel of the block is obstacle (DOOR: 0, SHELF: < 127)
-#define C_FINE 2   // block is not uniform: look at the pixels
-#define C_LOW 4    // SHELF: every pixel is a low obstacle (127..254)
+#define C_OBST 1   // every pixel of the block is obstacle (DOOR: 0, SHELF: < 127)          == F_OBST
+#define C_LOW 2    // SHELF: every pixel is a low obstacle (127..254)                       == F_LOW
+#define C_FINE 4   // block is not uniform: look at the pixels
 #define C_GRAY 8   // DOOR: block contains gray pixels (zone ids needed) -- implies C_FINE
 
 #define F_OBST 1
@@ -303,7 +303,8 @@ __device__ __forceinline__ uint32_t rec_pixel_addr(const MapDev& m, const EdgeRe
   return (r.dirs & 1) ? tile_addr(major, minor, m.tiles_x) : tile_addr(minor, major, m.tiles_x);
 }
 
-#define V2_QCAP 480  // queue entries per warp (a batch of 32 edges of <= 410 px needs at most ~32*27 at BS = 16)
+#define V2_QCAP 512  // queue entries per warp
+#define V2_G 4       // consecutive strips of one edge handled by a lane per round (amortises the owner search)
 
 template <int KIND, int LOG_BS, bool INDEXED>
 __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, const double2* __restrict__ from,
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, 
                                                                       const int32_t* __restrict__ to_idx) {
   constexpr int BS = 1 << LOG_BS;
   constexpr int WARPS = EDGE_BLOCK / 32;
-  __shared__ EdgeRec s_rec[WARPS][32];
+  __shared__ EdgeRec s_rec[WARPS][32];        // n_items holds the STRIP count here
   __shared__ uint32_t s_flags[WARPS][32];     // F_* per edge
   __shared__ uint32_t s_zmin[WARPS][32], s_zmax[WARPS][32];
   __shared__ uint32_t s_queue[WARPS][V2_QCAP];
@@ -327,8 +328,8 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, 
   const int64_t n_warps = ((int64_t)gridDim.x * EDGE_BLOCK) >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  // pass 2: per-pixel resolution of the queued strips; one lane per strip, pixels in order, minor coordinate stepped
-  // incrementally; strips of edges that are already blocked are dropped first (unless zone ids are at stake)
+  // pass 2: per-pixel resolution of the queued strips; one lane per strip, pixels in order, pixel coordinates and the
+  // Bresenham remainder stepped incrementally; strips of edges that are already blocked are dropped first
   auto drain = [&]() {
     __syncwarp();
     const int qn = s_qcount[wib];
@@ -353,20 +354,26 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, 
         const uint32_t ent = s_queue[wib][q];
         const int e = ent & 31;
         const EdgeRec r = s_rec[wib][e];
-        int k = (int)((ent >> 5) & 0x7fff);
-        const int k_end = k + (int)((ent >> 20) & 31);
-        int32_t mnr = rec_minor(r, k);
-        int32_t rem = k * r.dyo - mnr * r.dxo;   // k*dyo = mnr*dxo + rem, 0 <= rem < dxo (fits: both products < 2^31)
+        const int k0 = (int)((ent >> 5) & 0x7fff);
+        int left = (int)((ent >> 20) & 31) + 1;
+        const int32_t mnr = rec_minor(r, k0);
+        int32_t rem = k0 * r.dyo - mnr * r.dxo;   // k*dyo = mnr*dxo + rem, 0 <= rem < dxo
+        const int sm = (r.dirs & 2) ? -1 : 1, sn = (r.dirs & 4) ? -1 : 1;
+        const int major = r.c0 + sm * k0, minor = r.n0 + sn * mnr;
+        int i = (r.dirs & 1) ? major : minor, j = (r.dirs & 1) ? minor : major;
+        const int di_u = (r.dirs & 1) ? sm : 0, dj_u = (r.dirs & 1) ? 0 : sm;   // major step
+        const int di_v = (r.dirs & 1) ? 0 : sn, dj_v = (r.dirs & 1) ? sn : 0;   // minor step
         uint32_t f = 0, zmin = 255, zmax = 0;
-        for (; k <= k_end; ++k) {
-          const uint32_t code = __ldg(m.grid + rec_pixel_addr(m, r, k, mnr));
+        for (; left > 0; --left) {
+          const uint32_t code = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
           if (code != 255) {
             if (KIND == PORRT_DOMAIN_SHELF) { f |= code < 127 ? F_OBST : F_LOW; }
             else if (code == 0) f |= F_OBST;
             else { zmin = min(zmin, code); zmax = max(zmax, code); }
           }
+          i += di_u; j += dj_u;
           rem += r.dyo;
-          if (rem >= r.dxo && r.dxo > 0) { rem -= r.dxo; ++mnr; }
+          if (rem >= r.dxo) { rem -= r.dxo; i += di_v; j += dj_v; }   // dxo == 0 only for single-pixel edges (left == 1)
         }
         if (f) atomicOr(&s_flags[wib][e], f);
         if (zmax) { atomicMin(&s_zmin[wib][e], zmin); atomicMax(&s_zmax[wib][e], zmax); }
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, 
     // ---- per-lane setup of one edge
     EdgeRec mine;
     int my_flags = 0;  // bit0 start OOB, bit1 end OOB
-    mine.n_items = 1; mine.dirs = 8; mine.c0 = mine.n0 = mine.dxo = mine.dyo = 0; mine.m_lo = mine.m_hi = 0;
+    mine.n_items = 0; mine.dirs = 8; mine.c0 = mine.n0 = mine.dxo = mine.dyo = 0; mine.m_lo = mine.m_hi = 0;
     if (eidx < n) {
       const double2 a = INDEXED ? from[from_idx[eidx]] : from[eidx];
       const double2 b = INDEXED ? to[to_idx[eidx]] : to[eidx];
@@ -396,12 +403,14 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, 
       else {
         const int sgn = (mine.dirs & 2) ? -1 : 1;
         const int b0 = mine.c0 >> LOG_BS, b1 = (mine.c0 + sgn * mine.dxo) >> LOG_BS;
-        mine.n_items = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;
+        mine.n_items = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;   // strips
       }
     }
     s_rec[wib][lane] = mine;
     s_flags[wib][lane] = 0; s_zmin[wib][lane] = 255; s_zmax[wib][lane] = 0;
-    int incl = mine.n_items;
+    // items = groups of V2_G strips; every lane owns at least one (possibly empty) item so that the inclusive prefix
+    // sums are strictly increasing and the owner of a flattened position can be ranked with a bitmask
+    int incl = max(1, (mine.n_items + V2_G - 1) / V2_G);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -409,54 +418,56 @@ __global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, 
     }
     if (lane == 0) s_qcount[wib] = 0;
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const bool may_overflow = total > V2_QCAP;     // warp-uniform
+    const bool may_overflow = total * V2_G > V2_QCAP;     // warp-uniform
     __syncwarp();
 
-    // ---- pass 1: strip w = 32*it + lane of the flattened sequence; neighbouring lanes work on neighbouring strips
+    // ---- pass 1: item w = w0 + lane of the flattened sequence; neighbouring lanes work on neighbouring strips
     for (int w0 = 0; w0 < total; w0 += 32) {
-      if (may_overflow && s_qcount[wib] > V2_QCAP - 32) drain();
-      // which edge owns flattened position w0 + lane: incl is strictly increasing over lanes, so the positions where
-      // an edge ends inside this window form a bitmask and a popcount ranks them (no search loop)
+      if (may_overflow && s_qcount[wib] > V2_QCAP - 32 * V2_G) drain();
       const int d = incl - w0;                                    // edge `lane` ends before window position d
       const int e_base = __popc(__ballot_sync(0xffffffffu, d <= 0));
       const unsigned marks = __reduce_or_sync(0xffffffffu, (d >= 1 && d <= 32) ? (1u << (d - 1)) : 0u);
       const int e = min(31, e_base + __popc(marks & lt_mask));
       const int p_prev = __shfl_sync(0xffffffffu, incl, (e + 31) & 31);
       const int w = w0 + lane;
-      bool want = false;
-      uint32_t entry = 0;
       if (w < total) {
         const EdgeRec r = s_rec[wib][e];
-        if (!(r.dirs & 8)) {
-          const int t = w - (e ? p_prev : 0);
-          const int sgn = (r.dirs & 2) ? -1 : 1;
-          const int bm = (r.c0 >> LOG_BS) + sgn * t;
-          const int lo_raw = sgn * ((bm << LOG_BS) - r.c0) - ((r.dirs & 2) ? BS - 1 : 0);
-          const int k_lo = max(0, lo_raw), k_hi = min(r.dxo, lo_raw + BS - 1);
-          const int m_a = rec_minor(r, k_lo), m_b = rec_minor(r, k_hi);
-          const int bn_a = (r.n0 + ((r.dirs & 4) ? -m_a : m_a)) >> LOG_BS, bn_b = (r.n0 + ((r.dirs & 4) ? -m_b : m_b)) >> LOG_BS;
-          const int ia = (r.dirs & 1) ? bm * cw + bn_a : bn_a * cw + bm;
-          const int ib = (r.dirs & 1) ? bm * cw + bn_b : bn_b * cw + bm;
-          uint32_t c = coarse[ia];
-          if (ib != ia) c |= coarse[ib];
-          if (c) {
-            const uint32_t f = ((c & C_OBST) ? F_OBST : 0) | ((c & C_LOW) ? F_LOW : 0);
-            if (f) atomicOr(&s_flags[wib][e], f);
-            if ((c & C_FINE) && (!(f & F_OBST) || (c & C_GRAY))) {
-              want = true;
-              entry = (uint32_t)e | ((uint32_t)k_lo << 5) | ((uint32_t)(k_hi - k_lo) << 20) | ((c & C_GRAY) ? (1u << 25) : 0u);
-            }
+        const int ts0 = (w - (e ? p_prev : 0)) * V2_G;
+        const int sgn = (r.dirs & 2) ? -1 : 1;
+        const int b0 = r.c0 >> LOG_BS;
+        uint32_t cls[V2_G];
+        int klo[V2_G], klen[V2_G];
+#pragma unroll
+        for (int g = 0; g < V2_G; ++g) {
+          const int ts = ts0 + g;
+          cls[g] = 0; klo[g] = 0; klen[g] = 0;
+          if (ts < r.n_items) {
+            const int bm = b0 + sgn * ts;
+            const int lo_raw = sgn * ((bm << LOG_BS) - r.c0) - ((r.dirs & 2) ? BS - 1 : 0);
+            const int k_lo = max(0, lo_raw), k_hi = min(r.dxo, lo_raw + BS - 1);
+            const int m_a = rec_minor(r, k_lo), m_b = rec_minor(r, k_hi);
+            const int bn_a = (r.n0 + ((r.dirs & 4) ? -m_a : m_a)) >> LOG_BS, bn_b = (r.n0 + ((r.dirs & 4) ? -m_b : m_b)) >> LOG_BS;
+            const int ia = (r.dirs & 1) ? bm * cw + bn_a : bn_a * cw + bm;
+            const int ib = (r.dirs & 1) ? bm * cw + bn_b : bn_b * cw + bm;
+            uint32_t c = coarse[ia];
+            if (ib != ia) c |= coarse[ib];
+            cls[g] = c; klo[g] = k_lo; klen[g] = k_hi - k_lo;
           }
         }
+        uint32_t f = 0;
+#pragma unroll
+        for (int g = 0; g < V2_G; ++g) f |= cls[g];
+        if (f & 3) atomicOr(&s_flags[wib][e], f & 3);
+        if (f & C_FINE) {
+#pragma unroll
+          for (int g = 0; g < V2_G; ++g)
+            if ((cls[g] & C_FINE) && (!(f & C_OBST) || (cls[g] & C_GRAY))) {
+              const int pos = atomicAdd(&s_qcount[wib], 1);
+              s_queue[wib][pos] = (uint32_t)e | ((uint32_t)klo[g] << 5) | ((uint32_t)klen[g] << 20) | ((cls[g] & C_GRAY) ? (1u << 25) : 0u);
+            }
+        }
       }
-      const unsigned wants = __ballot_sync(0xffffffffu, want);
-      if (wants) {
-        const int qb = s_qcount[wib];
-        if (want) s_queue[wib][qb + __popc(wants & lt_mask)] = entry;
-        __syncwarp();
-        if (lane == 0) s_qcount[wib] = qb + __popc(wants);
-        __syncwarp();
-      }
+      __syncwarp();
     }
     // ---- pass 2: pixels of the strips that are still undecided
     drain();
