@@ -304,10 +304,13 @@ __device__ __forceinline__ uint32_t rec_pixel_addr(const MapDev& m, const EdgeRe
 }
 
 #define V2_QCAP 512  // queue entries per warp
-#define V2_G 4       // consecutive strips of one edge handled by a lane per round (amortises the owner search)
+#ifndef V2_MINB
+#define V2_MINB 4
+#endif
 
-template <int KIND, int LOG_BS, bool INDEXED>
-__global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_v2_kernel(MapDev m, const double2* __restrict__ from,
+// V2_G: consecutive strips of one edge handled by a lane per round (amortises the owner search)
+template <int KIND, int LOG_BS, int V2_G, bool INDEXED>
+__global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(MapDev m, const double2* __restrict__ from,
                                                                       const double2* __restrict__ to, int64_t n,
                                                                       int32_t* __restrict__ out_vid,
                                                                       uint64_t* __restrict__ out_mask,
@@ -733,13 +736,16 @@ static int32_t launch_edges(porrt_ctx* ctx, const double2* from, const double2* 
   const uint64_t* val = ctx->d_validities.as<uint64_t>();
   const int grid = edge_grid(ctx, n);
   const bool shelf = ctx->map.kind == PORRT_DOMAIN_SHELF;
-#define LAUNCH_V2(K, L) edge_validity_v2_kernel<K, L, INDEXED><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out_vid, out_mask, val, from_idx, to_idx)
+#define LAUNCH_V2(K, L, G) edge_validity_v2_kernel<K, L, G, INDEXED><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out_vid, out_mask, val, from_idx, to_idx)
 #define LAUNCH_V1(K) edge_validity_kernel<K, INDEXED><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out_vid, out_mask, val, from_idx, to_idx)
   switch (ctx->edge_variant) {
     case 1: if (shelf) LAUNCH_V1(PORRT_DOMAIN_SHELF); else LAUNCH_V1(PORRT_DOMAIN_DOOR); break;
-    case 2: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 3); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 3); break;
-    case 4: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 5); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 5); break;
-    default: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4); break;
+    case 2: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 3, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 3, 4); break;
+    case 4: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 5, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 5, 4); break;
+    case 5: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4, 2); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4, 2); break;
+    case 6: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4, 8); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4, 8); break;
+    case 7: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 3, 8); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 3, 8); break;
+    default: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4, 4); break;
   }
 #undef LAUNCH_V1
 #undef LAUNCH_V2
