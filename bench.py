@@ -94,7 +94,7 @@ def cpu_baseline(args, occ, zones, a, b, all_threads=True):
     omap = O.GridMap(occ, zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
     n = min(args.cpu_sample, len(a))
     sa, sb = np.ascontiguousarray(a[:n]), np.ascontiguousarray(b[:n])
-    threads = O.lib().orc_num_threads() if all_threads else 1
+    threads = host_threads() if all_threads else 1
     omap.edge_validity_timed(sa[:100000], sb[:100000], threads)  # warm-up
     out, t = omap.edge_validity_timed(sa, sb, threads)
     n1 = min(n, 400_000)
@@ -112,7 +112,7 @@ def run_reference(args):
     occ, zones, a, b = make_inputs(args, 0)
     from oracle import pyoracle as O
     omap = O.GridMap(occ, zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
-    threads = O.lib().orc_num_threads()
+    threads = host_threads()
     n = min(args.cpu_sample, len(a))
     sa, sb = np.ascontiguousarray(a[:n]), np.ascontiguousarray(b[:n])
     for _ in range(max(1, args.warmup)):
@@ -130,10 +130,27 @@ def run_reference(args):
                                        "(reference Rust crate not buildable here: no cargo/rustc)" % n},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was diverted to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+def host_threads():
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use the box's cores
+    return max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -281,7 +298,7 @@ def main():
             extras["error"] = repr(e)
         line["extras"] = extras
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
