@@ -287,20 +287,20 @@ __global__ void coarse_build_kernel(const uint8_t* __restrict__ grid, int H, int
   }
 }
 
-struct EdgeRec {        // 32 bytes per edge, shared memory, already unpacked for the strip arithmetic
+struct EdgeRec {        // 48 bytes per edge in shared memory, unpacked for the strip arithmetic of pass 1
   int32_t c0, n0;       // start pixel: major-axis coordinate, minor-axis coordinate
   int32_t dxo, dyo;     // octant-space deltas (major, minor)
-  uint32_t m_lo, m_hi;  // exact-division magic (see EdgeSetup)
+  uint32_t m_lo, m_hi;  // M' = floor(2^63/dxo) + 1: floor(k*dyo/dxo) == umul64hi(2*k*dyo, M') exactly, for every dxo >= 1
   int32_t dirs;         // bit0: major axis is i (rows), bit1: major step is -1, bit2: minor step is -1, bit3: no-op edge
-  int32_t n_items;      // strips (>= 1; a no-op edge owns one empty strip so that prefix sums stay strictly increasing)
+  int32_t n_strips;     // strips of <= BS pixels (0 for a no-op edge)
+  int32_t lo_raw0;      // k of the first pixel of strip 0's block column (<= 0); strip ts starts at lo_raw0 + ts*BS
+  int32_t idx0;         // class-byte index of (major block of strip 0, minor block 0)
+  int32_t stride_major; // class-byte index step per strip (signed)
+  int32_t stride_minor; // class-byte index step per minor block
 };
 
 __device__ __forceinline__ int32_t rec_minor(const EdgeRec& r, int32_t k) {
-  return r.dxo > 1 ? (int32_t)__umul64hi((uint64_t)((uint32_t)k * (uint32_t)r.dyo), ((uint64_t)r.m_hi << 32) | r.m_lo) : k * r.dyo;
-}
-__device__ __forceinline__ uint32_t rec_pixel_addr(const MapDev& m, const EdgeRec& r, int32_t k, int32_t mnr) {
-  const int32_t major = r.c0 + ((r.dirs & 2) ? -k : k), minor = r.n0 + ((r.dirs & 4) ? -mnr : mnr);
-  return (r.dirs & 1) ? tile_addr(major, minor, m.tiles_x) : tile_addr(minor, major, m.tiles_x);
+  return (int32_t)__umul64hi((uint64_t)(2u * (uint32_t)k * (uint32_t)r.dyo), ((uint64_t)r.m_hi << 32) | r.m_lo);
 }
 
 #define V2_QCAP 512  // queue entries per warp
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
                                                                       const int32_t* __restrict__ to_idx) {
   constexpr int BS = 1 << LOG_BS;
   constexpr int WARPS = EDGE_BLOCK / 32;
-  __shared__ EdgeRec s_rec[WARPS][32];        // n_items holds the STRIP count here
+  __shared__ EdgeRec s_rec[WARPS][32];
   __shared__ uint32_t s_flags[WARPS][32];     // F_* per edge
   __shared__ uint32_t s_zmin[WARPS][32], s_zmax[WARPS][32];
   __shared__ uint32_t s_queue[WARPS][V2_QCAP];
@@ -356,16 +356,17 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
       if (q < live_n) {
         const uint32_t ent = s_queue[wib][q];
         const int e = ent & 31;
-        const EdgeRec r = s_rec[wib][e];
+        const EdgeRec& r = s_rec[wib][e];
+        const int dxo = r.dxo, dyo = r.dyo, dirs = r.dirs;
         const int k0 = (int)((ent >> 5) & 0x7fff);
         int left = (int)((ent >> 20) & 31) + 1;
         const int32_t mnr = rec_minor(r, k0);
-        int32_t rem = k0 * r.dyo - mnr * r.dxo;   // k*dyo = mnr*dxo + rem, 0 <= rem < dxo
-        const int sm = (r.dirs & 2) ? -1 : 1, sn = (r.dirs & 4) ? -1 : 1;
+        int32_t rem = k0 * dyo - mnr * dxo;   // k*dyo = mnr*dxo + rem, 0 <= rem < dxo
+        const int sm = (dirs & 2) ? -1 : 1, sn = (dirs & 4) ? -1 : 1;
         const int major = r.c0 + sm * k0, minor = r.n0 + sn * mnr;
-        int i = (r.dirs & 1) ? major : minor, j = (r.dirs & 1) ? minor : major;
-        const int di_u = (r.dirs & 1) ? sm : 0, dj_u = (r.dirs & 1) ? 0 : sm;   // major step
-        const int di_v = (r.dirs & 1) ? 0 : sn, dj_v = (r.dirs & 1) ? sn : 0;   // minor step
+        int i = (dirs & 1) ? major : minor, j = (dirs & 1) ? minor : major;
+        const int di_u = (dirs & 1) ? sm : 0, dj_u = (dirs & 1) ? 0 : sm;   // major step
+        const int di_v = (dirs & 1) ? 0 : sn, dj_v = (dirs & 1) ? sn : 0;   // minor step
         uint32_t f = 0, zmin = 255, zmax = 0;
         for (; left > 0; --left) {
           const uint32_t code = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
@@ -375,8 +376,8 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
             else { zmin = min(zmin, code); zmax = max(zmax, code); }
           }
           i += di_u; j += dj_u;
-          rem += r.dyo;
-          if (rem >= r.dxo) { rem -= r.dxo; i += di_v; j += dj_v; }   // dxo == 0 only for single-pixel edges (left == 1)
+          rem += dyo;
+          if (rem >= dxo) { rem -= dxo; i += di_v; j += dj_v; }   // dxo == 0 only for single-pixel edges (left == 1)
         }
         if (f) atomicOr(&s_flags[wib][e], f);
         if (zmax) { atomicMin(&s_zmin[wib][e], zmin); atomicMax(&s_zmax[wib][e], zmax); }
@@ -392,28 +393,35 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
     // ---- per-lane setup of one edge
     EdgeRec mine;
     int my_flags = 0;  // bit0 start OOB, bit1 end OOB
-    mine.n_items = 0; mine.dirs = 8; mine.c0 = mine.n0 = mine.dxo = mine.dyo = 0; mine.m_lo = mine.m_hi = 0;
+    mine.n_strips = 0; mine.dirs = 8; mine.c0 = mine.n0 = mine.dxo = mine.dyo = 0; mine.m_lo = mine.m_hi = 0;
+    mine.lo_raw0 = mine.idx0 = mine.stride_major = mine.stride_minor = 0;
     if (eidx < n) {
       const double2 a = INDEXED ? from[from_idx[eidx]] : from[eidx];
       const double2 b = INDEXED ? to[to_idx[eidx]] : to[eidx];
       const EdgeSetup s = make_setup(m, a.x, a.y, b.x, b.y);
       const int ui = (s.steps & 3) - 1, uj = ((s.steps >> 2) & 3) - 1, vi = ((s.steps >> 4) & 3) - 1, vj = ((s.steps >> 6) & 3) - 1;
       mine.c0 = ui ? s.ai : s.aj; mine.n0 = ui ? s.aj : s.ai;
-      mine.dxo = s.dxo; mine.dyo = s.dyo; mine.m_lo = s.m_lo; mine.m_hi = s.m_hi;
+      mine.dxo = s.dxo; mine.dyo = s.dyo;
+      const uint64_t M = s.dxo > 0 ? (0x8000000000000000ull / (uint64_t)s.dxo) + 1ull : 0ull;
+      mine.m_lo = (uint32_t)M; mine.m_hi = (uint32_t)(M >> 32);
       mine.dirs = (ui ? 1 : 0) | ((ui + uj) < 0 ? 2 : 0) | ((vi + vj) < 0 ? 4 : 0);
       my_flags = s.flags;
       if (my_flags) mine.dirs |= 8;
       else {
         const int sgn = (mine.dirs & 2) ? -1 : 1;
         const int b0 = mine.c0 >> LOG_BS, b1 = (mine.c0 + sgn * mine.dxo) >> LOG_BS;
-        mine.n_items = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;   // strips
+        mine.n_strips = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;
+        mine.lo_raw0 = sgn * ((b0 << LOG_BS) - mine.c0) - ((mine.dirs & 2) ? BS - 1 : 0);
+        mine.stride_major = sgn * ((mine.dirs & 1) ? cw : 1);
+        mine.stride_minor = (mine.dirs & 1) ? 1 : cw;
+        mine.idx0 = b0 * ((mine.dirs & 1) ? cw : 1);
       }
     }
     s_rec[wib][lane] = mine;
     s_flags[wib][lane] = 0; s_zmin[wib][lane] = 255; s_zmax[wib][lane] = 0;
     // items = groups of V2_G strips; every lane owns at least one (possibly empty) item so that the inclusive prefix
     // sums are strictly increasing and the owner of a flattened position can be ranked with a bitmask
-    int incl = max(1, (mine.n_items + V2_G - 1) / V2_G);
+    int incl = max(1, (mine.n_strips + V2_G - 1) / V2_G);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -434,40 +442,47 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
       const int p_prev = __shfl_sync(0xffffffffu, incl, (e + 31) & 31);
       const int w = w0 + lane;
       if (w < total) {
-        const EdgeRec r = s_rec[wib][e];
+        const EdgeRec& r = s_rec[wib][e];
+        const int n_strips = r.n_strips, dxo = r.dxo, n0 = r.n0, stride_minor = r.stride_minor;
+        const uint32_t dy2 = 2u * (uint32_t)r.dyo;
+        const uint64_t M = ((uint64_t)r.m_hi << 32) | r.m_lo;
+        const bool neg_minor = (r.dirs & 4) != 0;
         const int ts0 = (w - (e ? p_prev : 0)) * V2_G;
-        const int sgn = (r.dirs & 2) ? -1 : 1;
-        const int b0 = r.c0 >> LOG_BS;
+        int lo_raw = r.lo_raw0 + ts0 * BS;
+        int idx_m = r.idx0 + ts0 * r.stride_major;
+        const int stride_major = r.stride_major;
         uint32_t cls[V2_G];
         int klo[V2_G], klen[V2_G];
 #pragma unroll
         for (int g = 0; g < V2_G; ++g) {
-          const int ts = ts0 + g;
-          cls[g] = 0; klo[g] = 0; klen[g] = 0;
-          if (ts < r.n_items) {
-            const int bm = b0 + sgn * ts;
-            const int lo_raw = sgn * ((bm << LOG_BS) - r.c0) - ((r.dirs & 2) ? BS - 1 : 0);
-            const int k_lo = max(0, lo_raw), k_hi = min(r.dxo, lo_raw + BS - 1);
-            const int m_a = rec_minor(r, k_lo), m_b = rec_minor(r, k_hi);
-            const int bn_a = (r.n0 + ((r.dirs & 4) ? -m_a : m_a)) >> LOG_BS, bn_b = (r.n0 + ((r.dirs & 4) ? -m_b : m_b)) >> LOG_BS;
-            const int ia = (r.dirs & 1) ? bm * cw + bn_a : bn_a * cw + bm;
-            const int ib = (r.dirs & 1) ? bm * cw + bn_b : bn_b * cw + bm;
+          cls[g] = 0;
+          const int k_lo = max(0, lo_raw), k_hi = min(dxo, lo_raw + BS - 1);
+          klo[g] = k_lo; klen[g] = k_hi - k_lo;
+          if (ts0 + g < n_strips) {
+            const int m_a = (int)__umul64hi((uint64_t)((uint32_t)k_lo * dy2), M), m_b = (int)__umul64hi((uint64_t)((uint32_t)k_hi * dy2), M);
+            const int bn_a = (neg_minor ? n0 - m_a : n0 + m_a) >> LOG_BS, bn_b = (neg_minor ? n0 - m_b : n0 + m_b) >> LOG_BS;
+            const int ia = idx_m + bn_a * stride_minor;
             uint32_t c = coarse[ia];
-            if (ib != ia) c |= coarse[ib];
-            cls[g] = c; klo[g] = k_lo; klen[g] = k_hi - k_lo;
+            if (bn_b != bn_a) c |= coarse[idx_m + bn_b * stride_minor];
+            cls[g] = c;
           }
+          lo_raw += BS; idx_m += stride_major;
         }
         uint32_t f = 0;
 #pragma unroll
         for (int g = 0; g < V2_G; ++g) f |= cls[g];
         if (f & 3) atomicOr(&s_flags[wib][e], f & 3);
         if (f & C_FINE) {
+          int n_want = 0;
 #pragma unroll
-          for (int g = 0; g < V2_G; ++g)
-            if ((cls[g] & C_FINE) && (!(f & C_OBST) || (cls[g] & C_GRAY))) {
-              const int pos = atomicAdd(&s_qcount[wib], 1);
-              s_queue[wib][pos] = (uint32_t)e | ((uint32_t)klo[g] << 5) | ((uint32_t)klen[g] << 20) | ((cls[g] & C_GRAY) ? (1u << 25) : 0u);
-            }
+          for (int g = 0; g < V2_G; ++g) n_want += ((cls[g] & C_FINE) && (!(f & C_OBST) || (cls[g] & C_GRAY))) ? 1 : 0;
+          if (n_want) {
+            int pos = atomicAdd(&s_qcount[wib], n_want);
+#pragma unroll
+            for (int g = 0; g < V2_G; ++g)
+              if ((cls[g] & C_FINE) && (!(f & C_OBST) || (cls[g] & C_GRAY)))
+                s_queue[wib][pos++] = (uint32_t)e | ((uint32_t)klo[g] << 5) | ((uint32_t)klen[g] << 20) | ((cls[g] & C_GRAY) ? (1u << 25) : 0u);
+          }
         }
       }
       __syncwarp();
@@ -493,7 +508,8 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
       if (slow) {
         Walker wk;
         const int sm = (mine.dirs & 2) ? -1 : 1, sn = (mine.dirs & 4) ? -1 : 1;
-        wk.dxo = mine.dxo; wk.dyo = mine.dyo; wk.M = ((uint64_t)mine.m_hi << 32) | mine.m_lo;
+        wk.dxo = mine.dxo; wk.dyo = mine.dyo;
+        wk.M = mine.dxo > 1 ? (0xFFFFFFFFFFFFFFFFull / (uint64_t)mine.dxo) + 1ull : 0ull;
         if (mine.dirs & 1) { wk.ai = mine.c0; wk.aj = mine.n0; wk.ui = sm; wk.uj = 0; wk.vi = 0; wk.vj = sn; }
         else { wk.ai = mine.n0; wk.aj = mine.c0; wk.ui = 0; wk.uj = sm; wk.vi = sn; wk.vj = 0; }
         r = walk_sequential<KIND>(m, wk);
