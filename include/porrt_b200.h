@@ -60,6 +60,8 @@ const char* porrt_last_error(porrt_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t porrt_ctx_launch_count(porrt_ctx* ctx);
 const char* porrt_version(void);
+/* device time (ms, CUDA events) of the phases of the last host-buffer NN call on this ctx; see the call's docs */
+int32_t porrt_ctx_last_phase_ms(porrt_ctx* ctx, double* out_ms, int32_t cap, int32_t* out_n);
 
 /* ------------------------------------------------------------------ maps
  * Replaces Map::open + add_zones / init_without_zones (map_io.rs:82-145) and MapShelfDomain::open + add_zones
@@ -126,10 +128,13 @@ int32_t porrt_kd_preorder_rank(porrt_ctx* ctx, const double* xy, int64_t n, int3
  * neighbours = vertices j < k within radius in kd pre-order, edges validated from neighbour -> new node.
  * Output: children adjacency as CSR in the reference's insertion order (row k = valid earlier neighbours in kd
  * pre-order, then later nodes ascending).  parents(k) == children(k) as sequences (prm.rs:99-106).
- * out_col may be NULL to query *out_n_edges first. */
+ * out_col may be NULL / cap too small: the call then returns PORRT_ERR_CAPACITY with *out_n_edges set and KEEPS the result
+ * on the device; porrt_prm_fetch copies it out without recomputing (valid until the next call on this ctx). */
 int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
                         int64_t* out_row_ptr /* [n+1] */, int32_t* out_col, int64_t cap, int64_t* out_n_edges,
                         double* out_phase_ms /* nullable [8] */);
+
+int32_t porrt_prm_fetch(porrt_ctx* ctx, int64_t* out_row_ptr /* nullable */, int32_t* out_col, int64_t cap);
 
 /* ------------------------------------------------------------------ value backups
  * CSR graph = children adjacency of a PTOGraph (pto_graph.rs:171-228): row_ptr[V+1], col[E], edge_vid[E], xy[2V],

@@ -425,6 +425,12 @@ API double orc_prm_grow_graph(void* p, double max_step, double search_radius, ui
 API uint64_t orc_prm_add_sample(void* p, const double* s, double max_step, double search_radius) {
   return ((PRM*)p)->add_sample({s[0], s[1]}, max_step, search_radius);
 }
+// PRM::add_sample over a given sample stream (same samples as the GPU build); returns wall seconds
+API double orc_prm_add_samples(void* p, const double* xy, uint64_t n, double max_step, double search_radius) {
+  auto t0 = std::chrono::steady_clock::now();
+  for (uint64_t k = 0; k < n; ++k) ((PRM*)p)->add_sample({xy[2 * k], xy[2 * k + 1]}, max_step, search_radius);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 API void* orc_prm_graph(void* p) { return &((PRM*)p)->graph; }
 API void* orc_prm_kdtree(void* p) { return &((PRM*)p)->kdtree; }
 API int64_t orc_prm_plan_path(void* p, const double* start, const double* goal, double* out_xy, int64_t cap) {

@@ -61,7 +61,7 @@ _SIGS = {
     "orc_policy_sizes": (None, [vp, vp, vp, vp]), "orc_policy_export": (None, [vp, vp, vp, vp, vp, vp]),
     "orc_prm_new": (vp, [vp, vp, vp, u64]), "orc_prm_free": (None, [vp]), "orc_prm_init": (None, [vp, vp]),
     "orc_prm_grow_graph": (f64, [vp, f64, f64, u64]), "orc_prm_add_sample": (u64, [vp, vp, f64, f64]),
-    "orc_prm_graph": (vp, [vp]), "orc_prm_kdtree": (vp, [vp]), "orc_prm_plan_path": (i64, [vp, vp, vp, vp, i64]),
+    "orc_prm_add_samples": (f64, [vp, vp, u64, f64, f64]), "orc_prm_graph": (vp, [vp]), "orc_prm_kdtree": (vp, [vp]), "orc_prm_plan_path": (i64, [vp, vp, vp, vp, i64]),
     "orc_pto_new": (vp, [vp, vp, vp, u64]), "orc_pto_free": (None, [vp]),
     "orc_pto_grow_graph": (C.c_int, [vp, vp, vp, f64, f64, u64, u64]),
     "orc_pto_graph": (vp, [vp]), "orc_pto_kdtree": (vp, [vp]), "orc_pto_reach": (vp, [vp]),
@@ -525,6 +525,11 @@ class PRM:
 
     def add_sample(self, s, max_step, search_radius):
         return lib().orc_prm_add_sample(self.h, P(f64a(s)), max_step, search_radius)
+
+    def add_samples(self, xy, max_step, search_radius):
+        """PRM::add_sample for each row of xy; returns wall seconds"""
+        xy = f64a(xy).reshape(-1, 2)
+        return lib().orc_prm_add_samples(self.h, P(xy), len(xy), max_step, search_radius)
 
     def plan_path(self, start, goal):
         cap = self.graph.n_nodes() + 1

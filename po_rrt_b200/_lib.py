@@ -21,6 +21,7 @@ SIGNATURES = {
     "porrt_ctx_synchronize": (i32, [vp]),
     "porrt_last_error": (C.c_char_p, [vp]),
     "porrt_ctx_launch_count": (i64, [vp]),
+    "porrt_ctx_last_phase_ms": (i32, [vp, vp, i32, pp(i32)]),
     "porrt_map_upload": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, f64]),
     "porrt_map_info": (i32, [vp, pp(i32), pp(i32), pp(i32), pp(i32)]),
     "porrt_map_zone_positions": (i32, [vp, vp]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "porrt_knn": (i32, [vp, vp, i64, i32, vp, vp]),
     "porrt_kd_preorder_rank": (i32, [vp, vp, i64, vp]),
     "porrt_prm_build": (i32, [vp, vp, i64, f64, f64, vp, vp, i64, pp(i64), vp]),
+    "porrt_prm_fetch": (i32, [vp, vp, vp, i64]),
     "porrt_sssp_worlds": (i32, [vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, pp(i32)]),
     "porrt_belief_vi": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, pp(i32), vp]),
     "porrt_extract_policy": (i32, [vp, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),

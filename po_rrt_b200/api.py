@@ -77,6 +77,12 @@ class Context:
     def launch_count(self):
         return self.lib.porrt_ctx_launch_count(self.h)
 
+    def last_phase_ms(self):
+        out = np.zeros(16)
+        n = C.c_int32()
+        self.check(self.lib.porrt_ctx_last_phase_ms(self.h, _p(out), 16, C.byref(n)))
+        return [float(x) for x in out[:n.value]]
+
 
 class _GridDomain:
     KIND = DOOR
@@ -207,8 +213,9 @@ class KdTree:
         self.n = len(xy)
         self.ctx.check(self.ctx.lib.porrt_vertices_set(self.ctx.h, _p(xy), len(xy), float(cell_size)))
 
-    def nearest_neighbors(self, q, radius, prefix_limit=None, reach_mask=None, world=None, cap=None):
-        """radius search -> (offsets[m+1], ids) with ids ascending per query"""
+    def nearest_neighbors(self, q, radius, prefix_limit=None, reach_mask=None, world=None, cap=None, ids_out=None):
+        """radius search -> (offsets[m+1], ids) with ids ascending per query.  ids_out: optional preallocated int32 buffer
+        (e.g. pinned host memory) of at least `cap` entries"""
         q = _f64(q, 2)
         m = len(q)
         r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float64), (m,)))
@@ -219,7 +226,7 @@ class KdTree:
         cap = cap if cap is not None else max(1024, 64 * m)
         total = C.c_int64()
         while True:
-            ids = np.empty(cap, np.int32)
+            ids = ids_out if (ids_out is not None and len(ids_out) >= cap) else np.empty(cap, np.int32)
             rc = self.ctx.lib.porrt_radius_query(self.ctx.h, _p(q), _p(r), m, _p(pl), _p(rm), _p(w), _p(offs), _p(ids), cap,
                                                  C.byref(total))
             if rc == ERR_CAPACITY:
@@ -238,10 +245,11 @@ class KdTree:
         self.ctx.check(self.ctx.lib.porrt_nearest(self.ctx.h, _p(q), m, _p(rm), _p(w), _p(ids), _p(dist), _p(ties)))
         return ids, dist, ties
 
-    def knn(self, q, k):
+    def knn(self, q, k, ids_out=None, dist_out=None):
         q = _f64(q, 2)
         m = len(q)
-        ids, dist = np.empty((m, k), np.int32), np.empty((m, k))
+        ids = ids_out if ids_out is not None else np.empty((m, k), np.int32)
+        dist = dist_out if dist_out is not None else np.empty((m, k))
         self.ctx.check(self.ctx.lib.porrt_knn(self.ctx.h, _p(q), m, k, _p(ids), _p(dist)))
         return ids, dist
 
@@ -265,24 +273,20 @@ class PRM:
     def init(self, start):
         self.states = _f64(start, 2)
 
-    def grow_graph(self, samples, max_step, search_radius):
+    def grow_graph(self, samples, max_step, search_radius, col_out=None):
         """samples: the ContinuousSampler stream (n_iter states); nodes = [init state] + samples"""
         self.fns._need()
         xy = np.ascontiguousarray(np.vstack([self.states, _f64(samples, 2)]))
         n = len(xy)
         row_ptr = np.empty(n + 1, np.int64)
         n_edges = C.c_int64()
-        cap = max(1024, 48 * n)
-        while True:
-            col = np.empty(cap, np.int32)
-            rc = self.ctx.lib.porrt_prm_build(self.ctx.h, _p(xy), n, max_step, search_radius, _p(row_ptr), _p(col), cap,
-                                              C.byref(n_edges), _p(self.phase_ms))
-            if rc == ERR_CAPACITY:
-                cap = n_edges.value
-                continue
+        rc = self.ctx.lib.porrt_prm_build(self.ctx.h, _p(xy), n, max_step, search_radius, _p(row_ptr), None, 0,
+                                          C.byref(n_edges), _p(self.phase_ms))
+        if rc != ERR_CAPACITY:
             self.ctx.check(rc)
-            break
-        self.states, self.row_ptr, self.col = xy, row_ptr, col[:n_edges.value].copy()
+        col = np.empty(n_edges.value, np.int32) if col_out is None else col_out
+        self.ctx.check(self.ctx.lib.porrt_prm_fetch(self.ctx.h, None, _p(col), len(col)))
+        self.states, self.row_ptr, self.col = xy, row_ptr, col[:n_edges.value]
         return self
 
 

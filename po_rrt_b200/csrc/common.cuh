@@ -68,6 +68,10 @@ struct porrt_ctx {
   cudaEvent_t ev_in[MAX_SLOTS] = {}, ev_k[MAX_SLOTS] = {}, ev_out[MAX_SLOTS] = {};
   std::string err;
   int64_t launches = 0;
+  // device-side phase timing of the last host-buffer call (CUDA events on the compute stream)
+  cudaEvent_t ev_t[16] = {};
+  int n_marks = 0, n_last = 0;
+  double last_ms[16] = {};
 
   // ---- map
   bool has_map = false;
@@ -100,6 +104,10 @@ struct porrt_ctx {
     int32_t n_validities = 0;
   } bel;
   std::vector<int32_t> bel_node_vid;
+  // last PRM result, kept on the device (valid until the next call on this ctx)
+  int64_t prm_n = 0, prm_edges = 0;
+  const int64_t* prm_row_ptr = nullptr;
+  const int32_t* prm_col = nullptr;
 
   // ---- scratch
   DevBuf scratch[12];
@@ -135,6 +143,17 @@ static inline bool is_pinned_host(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+static inline void tstart(porrt_ctx* ctx) { ctx->n_marks = 0; if (ctx->ev_t[0]) cudaEventRecord(ctx->ev_t[ctx->n_marks++], ctx->stream); }
+static inline void tmark(porrt_ctx* ctx) { if (ctx->ev_t[0] && ctx->n_marks < 16) cudaEventRecord(ctx->ev_t[ctx->n_marks++], ctx->stream); }
+static inline void tfinish(porrt_ctx* ctx) {  // call after the stream has been synchronised
+  ctx->n_last = 0;
+  for (int k = 0; k + 1 < ctx->n_marks; ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_t[k], ctx->ev_t[k + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+    ctx->last_ms[ctx->n_last++] = ms;
+  }
+}
+
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // map.cu
@@ -152,4 +171,4 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
                                  const int32_t* key_of_id_dev, int64_t key_limit);
 int32_t radix_sort_pairs(porrt_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);
 int bits_for(uint64_t max_value);
-int32_t kd_preorder_rank_host(const double* xy, int64_t n, int32_t* out_rank);
+int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev);

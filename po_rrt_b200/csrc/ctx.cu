@@ -25,6 +25,7 @@ PORRT_API int32_t porrt_ctx_create(int32_t device, porrt_ctx** out_ctx) {
     ok = cudaEventCreateWithFlags(&ctx->ev_in[s], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_k[s], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
+  for (int s = 0; ok && s < 16; ++s) ok = cudaEventCreate(&ctx->ev_t[s]) == cudaSuccess;
   if (!ok) { delete ctx; return PORRT_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
   *out_ctx = ctx;
@@ -45,6 +46,7 @@ PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
     if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);
     if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
   }
+  for (int s = 0; s < 16; ++s) if (ctx->ev_t[s]) cudaEventDestroy(ctx->ev_t[s]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -67,3 +69,11 @@ PORRT_API int32_t porrt_ctx_synchronize(porrt_ctx* ctx) {
 
 PORRT_API const char* porrt_last_error(porrt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 PORRT_API int64_t porrt_ctx_launch_count(porrt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+PORRT_API int32_t porrt_ctx_last_phase_ms(porrt_ctx* ctx, double* out_ms, int32_t cap, int32_t* out_n) {
+  CTX_CHECK(ctx);
+  int n = ctx->n_last < cap ? ctx->n_last : cap;
+  for (int k = 0; k < n; ++k) out_ms[k] = ctx->last_ms[k];
+  if (out_n) *out_n = n;
+  return PORRT_OK;
+}

@@ -24,30 +24,90 @@ static double now_ms() {
 }
 
 // ================================================================================================ kd pre-order rank
-// The reference returns radius-search hits in node-left-right order of its incremental kd-tree
-// (nearest_neighbor.rs:101-117).  Inserting a leaf never reorders existing nodes, so the pre-order rank in the FINAL tree
-// orders every prefix correctly (SURVEY 8(g) note 4).  Host: O(n depth) descent with index links, then one walk.
-int32_t kd_preorder_rank_host(const double* xy, int64_t n, int32_t* out_rank) {
-  if (n <= 0) return PORRT_OK;
-  std::vector<int32_t> left((size_t)n, -1), right((size_t)n, -1);
-  for (int64_t i = 1; i < n; ++i) {
-    const double s[2] = {xy[2 * i], xy[2 * i + 1]};
-    int32_t cur = 0;
-    for (int axis = 0;; axis ^= 1) {  // KdTree::add, nearest_neighbor.rs:29-46: strictly-less goes left
-      int32_t* next = s[axis] < xy[2 * (int64_t)cur + axis] ? &left[cur] : &right[cur];
-      if (*next >= 0) cur = *next;
-      else { *next = (int32_t)i; break; }
-    }
+// The reference returns radius-search hits in node-left-right order of its incremental, unbalanced kd-tree
+// (nearest_neighbor.rs:29-46 add, :101-117 visit order).  Inserting a leaf never reorders existing nodes, so the
+// pre-order rank in the FINAL tree orders every prefix correctly (SURVEY 8(g) note 4).
+// Device construction, level-synchronous: every not-yet-placed point sits at the node it would currently be compared
+// with; all of them descend one level per round (so the split axis is the round parity), and the child slot (node, side)
+// goes to the smallest id that wants it (atomicMin) -- exactly the point that sequential insertion would have put there.
+// Subtree sizes are counted on the way down; ranks follow top-down, one depth per launch.
+__global__ void kd_descend_kernel(const double2* __restrict__ xy, int64_t n, int axis, const int32_t* __restrict__ cur,
+                                  int32_t* __restrict__ child, int32_t* __restrict__ size, uint8_t* __restrict__ side) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = cur[i];
+  if (c < 0) return;
+  const double2 p = xy[i], q = xy[c];
+  const int s = (axis ? p.y < q.y : p.x < q.x) ? 0 : 1;   // strictly-less goes left (nearest_neighbor.rs:32)
+  atomicMin(&child[2 * (int64_t)c + s], (int32_t)i);
+  atomicAdd(&size[c], 1);
+  side[i] = (uint8_t)s;
+}
+__global__ void kd_place_kernel(int64_t n, int depth, int32_t* __restrict__ cur, const int32_t* __restrict__ child,
+                                const uint8_t* __restrict__ side, int32_t* __restrict__ parent, int32_t* __restrict__ node_depth,
+                                int32_t* __restrict__ remaining) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = cur[i];
+  if (c < 0) return;
+  const int32_t w = child[2 * (int64_t)c + side[i]];
+  if (w == (int32_t)i) { parent[i] = c; node_depth[i] = depth + 1; cur[i] = -1; }
+  else { cur[i] = w; atomicAdd(remaining, 1); }
+}
+__global__ void kd_rank_kernel(int64_t n, int depth, const int32_t* __restrict__ node_depth, const int32_t* __restrict__ parent,
+                               const uint8_t* __restrict__ side, const int32_t* __restrict__ child, const int32_t* __restrict__ size,
+                               int32_t* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || node_depth[i] != depth) return;
+  const int32_t p = parent[i];
+  int32_t r = rank[p] + 1;
+  if (side[i]) {                                    // right child: the whole left subtree of the parent comes first
+    const int32_t l = child[2 * (int64_t)p];
+    if (l != 0x7fffffff) r += size[l] + 1;
   }
-  std::vector<int32_t> stack;
-  stack.push_back(0);
-  int32_t r = 0;
-  while (!stack.empty()) {
-    int32_t v = stack.back();
-    stack.pop_back();
-    out_rank[v] = r++;
-    if (right[v] >= 0) stack.push_back(right[v]);
-    if (left[v] >= 0) stack.push_back(left[v]);
+  rank[i] = r;
+}
+__global__ void kd_init_kernel(int64_t n, int32_t* __restrict__ cur, int32_t* __restrict__ child, int32_t* __restrict__ size,
+                               int32_t* __restrict__ node_depth, int32_t* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cur[i] = i == 0 ? -1 : 0;
+  child[2 * i] = 0x7fffffff; child[2 * i + 1] = 0x7fffffff;
+  size[i] = 0; node_depth[i] = i == 0 ? 0 : -1; rank[i] = 0;
+}
+
+// xy_dev: n vertices (device); out_rank_dev[n]; uses ctx->scratch[8..10]
+int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev) {
+  cudaStream_t st = ctx->stream;
+  if (n <= 0) return PORRT_OK;
+  CUDA_TRY(ctx, ctx->scratch[8].ensure((size_t)n * 4 * 6 + (size_t)n + 64));
+  char* b = ctx->scratch[8].as<char>();
+  int32_t* cur = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* child = (int32_t*)b; b += (size_t)n * 8;
+  int32_t* size = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* parent = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* node_depth = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* remaining = (int32_t*)b; b += 16;
+  uint8_t* side = (uint8_t*)b;
+  const int blocks = div_up(n, 256);
+  kd_init_kernel<<<blocks, 256, 0, st>>>(n, cur, child, size, node_depth, out_rank_dev);
+  LAUNCH_CHECK(ctx);
+  int depth = 0;
+  for (;; ++depth) {
+    CUDA_TRY(ctx, cudaMemsetAsync(remaining, 0, 4, st));
+    kd_descend_kernel<<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
+    LAUNCH_CHECK(ctx);
+    kd_place_kernel<<<blocks, 256, 0, st>>>(n, depth, cur, child, side, parent, node_depth, remaining);
+    LAUNCH_CHECK(ctx);
+    int32_t rem = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&rem, remaining, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (rem == 0) break;
+    if (depth > n) return porrt_fail(ctx, PORRT_ERR_CUDA, "kd_preorder_rank: no convergence");
+  }
+  for (int d = 1; d <= depth + 1; ++d) {
+    kd_rank_kernel<<<blocks, 256, 0, st>>>(n, d, node_depth, parent, side, child, size, out_rank_dev);
+    LAUNCH_CHECK(ctx);
   }
   return PORRT_OK;
 }
@@ -55,7 +115,17 @@ int32_t kd_preorder_rank_host(const double* xy, int64_t n, int32_t* out_rank) {
 PORRT_API int32_t porrt_kd_preorder_rank(porrt_ctx* ctx, const double* xy, int64_t n, int32_t* out_rank) {
   CTX_CHECK(ctx);
   if (n < 0 || (n > 0 && (!xy || !out_rank))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "kd_preorder_rank: bad arguments");
-  return kd_preorder_rank_host(xy, n, out_rank);
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, ctx->scratch[9].ensure((size_t)n * 20));
+  double* d_xy = ctx->scratch[9].as<double>();
+  int32_t* d_rank = (int32_t*)(ctx->scratch[9].as<char>() + (size_t)n * 16);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc = kd_preorder_rank_dev(ctx, d_xy, n, d_rank);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_rank, d_rank, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PORRT_OK;
 }
 
 // heuristic_radius (common.rs:357-369): host libm ln/pow like Rust's f64::ln/powf; never evaluated on the device.
@@ -135,16 +205,13 @@ __global__ void prm_fill_kernel(const int64_t* __restrict__ offsets, int64_t m, 
 PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
                                   int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms) {
   CTX_CHECK(ctx);
+  ctx->prm_n = 0;
   if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
   if (n <= 0 || !samples_xy || !out_row_ptr || !out_n_edges) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "prm_build: bad arguments");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   double t0 = now_ms(), t1;
   double ph[8] = {0};
-
-  // kd pre-order ranks on a host thread while the device does the geometric work
-  std::vector<int32_t> rank((size_t)n);
-  std::thread kd_thread([&]() { kd_preorder_rank_host(samples_xy, n, rank.data()); });
 
   // radii: node k (k >= 1) queries with heuristic_radius(k + 1) -- n_nodes AFTER adding the new node (prm.rs:61-65)
   std::vector<double> radius((size_t)n, 0.0);
@@ -188,21 +255,22 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   // 1. bin vertices; cell = the smallest radius in use (the last one) so late queries touch 3x3 cells
   double cell = radius[n - 1] > 0 ? radius[n - 1] : max_step;
   int32_t rc = nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell, nullptr, nullptr);
-  if (rc) { kd_thread.join(); return rc; }
+  if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
 
   // 2. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
   int64_t total = 0;
   rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>(), d_radius, n, d_prefix, nullptr, nullptr, d_off, &ctx->scratch[2], &total);
-  if (rc) { kd_thread.join(); return rc; }
+  if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
 
   // 3. restore the kd pre-order inside every neighbour list
-  kd_thread.join();
+  rc = kd_preorder_rank_dev(ctx, ctx->d_vxy.as<double>(), n, d_rank);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_rank, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   int32_t* d_ids = ctx->scratch[2].as<int32_t>();
   rc = segments_sort_by_key_dev(ctx, d_off, n, d_ids, d_rank, n);
   if (rc) return rc;
@@ -265,7 +333,19 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   t1 = now_ms(); ph[6] = t1 - t0;
   ph[7] = (double)total;
   if (out_phase_ms) memcpy(out_phase_ms, ph, sizeof(ph));
+  ctx->prm_n = n; ctx->prm_edges = n_edges; ctx->prm_row_ptr = d_row_ptr; ctx->prm_col = d_col;  // retained for porrt_prm_fetch
   return status;
+}
+
+PORRT_API int32_t porrt_prm_fetch(porrt_ctx* ctx, int64_t* out_row_ptr, int32_t* out_col, int64_t cap) {
+  CTX_CHECK(ctx);
+  if (ctx->prm_n <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "prm_fetch: no retained PRM result");
+  if (cap < ctx->prm_edges || !out_col) return porrt_fail(ctx, PORRT_ERR_CAPACITY, "prm_fetch: out_col too small");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (out_row_ptr) CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, ctx->prm_row_ptr, (size_t)(ctx->prm_n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->prm_edges) CUDA_TRY(ctx, cudaMemcpyAsync(out_col, ctx->prm_col, (size_t)ctx->prm_edges * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PORRT_OK;
 }
 
 // ================================================================================================ SSSP per world

@@ -468,13 +468,63 @@ __global__ void copy_u32_i32_kernel(const uint32_t* __restrict__ in, int64_t n, 
   if (i < n) out[i] = (int32_t)in[i];
 }
 
+// Fast path: one warp sorts one segment in shared memory (bitonic network on (key, id) pairs, <= SEG_SORT_CAP entries).
+// Keys are distinct inside a segment (ids are distinct and ranks are a permutation), so no stability concern arises.
+#define SEG_SORT_CAP 256
+#define SEG_SORT_WARPS 4
+__global__ void __launch_bounds__(SEG_SORT_WARPS * 32) seg_sort_small_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ ids,
+                                                                             const int32_t* __restrict__ key_of_id, int32_t* __restrict__ n_big) {
+  __shared__ uint64_t s_kv[SEG_SORT_WARPS][SEG_SORT_CAP];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t seg = (int64_t)blockIdx.x * SEG_SORT_WARPS + wib;
+  if (seg >= m) return;
+  const int64_t s = offsets[seg];
+  const int len = (int)min((int64_t)0x7fffffff, offsets[seg + 1] - s);
+  if (len <= 1) return;
+  if (len > SEG_SORT_CAP) { if (lane == 0) atomicAdd(n_big, 1); return; }
+  int np2 = 2;
+  while (np2 < len) np2 <<= 1;
+  uint64_t* kv = s_kv[wib];
+  for (int i = lane; i < np2; i += 32) {
+    uint64_t v = ~0ull;
+    if (i < len) {
+      const int32_t id = ids[s + i];
+      const uint32_t key = key_of_id ? (uint32_t)key_of_id[id] : (uint32_t)id;
+      v = ((uint64_t)key << 32) | (uint32_t)id;
+    }
+    kv[i] = v;
+  }
+  __syncwarp();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (np2 >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j cleared
+        const int p = i | j;
+        const uint64_t a = kv[i], b = kv[p];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { kv[i] = b; kv[p] = a; }
+      }
+      __syncwarp();
+    }
+  for (int i = lane; i < len; i += 32) ids[s + i] = (int32_t)(uint32_t)kv[i];
+}
+
 // key_limit: all keys (ids or key_of_id values) are < key_limit
 int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev, const int32_t* key_of_id_dev, int64_t key_limit) {
   cudaStream_t st = ctx->stream;
+  if (m <= 0) return PORRT_OK;
+  CUDA_TRY(ctx, ctx->scratch[4].ensure(16));
+  int32_t* d_big = ctx->scratch[4].as<int32_t>();
+  CUDA_TRY(ctx, cudaMemsetAsync(d_big, 0, 4, st));
+  seg_sort_small_kernel<<<div_up(m, SEG_SORT_WARPS), SEG_SORT_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_big);
+  LAUNCH_CHECK(ctx);
   int64_t total = 0;
+  int32_t n_big = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(&n_big, d_big, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  if (total <= 1) return PORRT_OK;
+  if (n_big == 0 || total <= 1) return PORRT_OK;
+  // some segment exceeds the shared-memory network: one global stable LSD radix sort on (segment, key) orders them all
   const int key_bits = bits_for((uint64_t)(key_limit > 1 ? key_limit - 1 : 1));
   const int seg_bits = bits_for((uint64_t)(m > 1 ? m - 1 : 1));
   CUDA_TRY(ctx, ctx->scratch[5].ensure((size_t)total * 8));
@@ -483,9 +533,6 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
   uint32_t* vals = ctx->scratch[6].as<uint32_t>();
   seg_key_kernel<<<div_up(m * 32, 256), 256, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, key_bits, keys, vals);
   LAUNCH_CHECK(ctx);
-  // segments are already contiguous and in order: only the low (key) bits need sorting, LSD passes over them suffice
-  // because a stable sort on the key bits followed by stable passes on the segment bits == full sort; since the
-  // input is segment-ordered we still need the segment passes to undo the mixing of the key passes.
   int32_t rc = radix_sort_pairs(ctx, keys, vals, total, key_bits + seg_bits);
   if (rc) return rc;
   copy_u32_i32_kernel<<<div_up(total, 256), 256, 0, st>>>(vals, total, ids_dev);
@@ -521,8 +568,10 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
   if (d_world) CUDA_TRY(ctx, cudaMemcpyAsync(d_world, world, (size_t)m * 4, cudaMemcpyHostToDevice, st));
   if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
   int64_t total = 0;
+  tstart(ctx);  // phases: [count+scan+fill, order restore, D2H]
   int32_t rc = nn_radius_count_fill_dev(ctx, d_q, d_r, m, d_prefix, d_reach, d_world, d_off, &ctx->scratch[2], &total);
   if (rc) return rc;
+  tmark(ctx);
   if (out_total) *out_total = total;
   CUDA_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (total > cap || (total > 0 && !out_ids)) {
@@ -531,8 +580,11 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
   }
   rc = segments_sort_by_key_dev(ctx, d_off, m, ctx->scratch[2].as<int32_t>(), nullptr, V);
   if (rc) return rc;
+  tmark(ctx);
   if (total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(out_ids, ctx->scratch[2].p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  tmark(ctx);
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  tfinish(ctx);
   return PORRT_OK;
 }
 
@@ -644,14 +696,18 @@ static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, co
   if (d_world) CUDA_TRY(ctx, cudaMemcpyAsync(d_world, world, (size_t)m * 4, cudaMemcpyHostToDevice, st));
   if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
   GridDev g = grid_dev(ctx);
+  tstart(ctx);  // phases: [kernel, D2H]
   if (k == 1) knn_kernel<1><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, 1, d_reach, d_world, d_ids, d_dist, d_ties);
   else if (k <= 8) knn_kernel<8><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, k, d_reach, d_world, d_ids, d_dist, nullptr);
   else knn_kernel<32><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, k, d_reach, d_world, d_ids, d_dist, nullptr);
   LAUNCH_CHECK(ctx);
+  tmark(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(out_ids, d_ids, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
   if (out_dist) CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_dist, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
   if (out_ties && k == 1) CUDA_TRY(ctx, cudaMemcpyAsync(out_ties, d_ties, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+  tmark(ctx);
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  tfinish(ctx);
   return PORRT_OK;
 }
 

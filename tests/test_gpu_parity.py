@@ -207,6 +207,39 @@ def test_radius_query_vs_oracle(ctx):
         np.testing.assert_array_equal(got[np.argsort(rank[got], kind="stable")], oids[ooffs[k]:ooffs[k + 1]])
 
 
+def test_radius_query_large_segments(ctx):
+    """> 256 hits per query: the shared-memory sorting network is bypassed for the global radix sort"""
+    pts = synth.points(20_000, seed=33)
+    q = synth.points(300, seed=34)
+    otree = _oracle_tree(pts)
+    tree = P.KdTree(ctx, pts, cell_size=0.05)
+    radius = np.where(np.arange(300) % 3 == 0, 0.3, 0.02)
+    offs, ids = tree.nearest_neighbors(q, radius)
+    rank = tree.preorder_rank()
+    assert (np.diff(offs) > 256).any() and (np.diff(offs) < 64).any()
+    for k in range(300):
+        got = ids[offs[k]:offs[k + 1]]
+        want = otree.nearest_neighbors(q[k], radius[k])
+        np.testing.assert_array_equal(got, np.sort(want))
+        np.testing.assert_array_equal(got[np.argsort(rank[got], kind="stable")], want)
+
+
+def test_kd_preorder_rank_device(ctx):
+    """level-synchronous device construction == sequential insertion (incl. duplicate points and collinear runs)"""
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(-1, 1, (30_000, 2))
+    pts[100:200] = pts[0:100]                      # exact duplicates go right, in insertion order
+    pts[300:400, 0] = 0.25                         # equal x
+    pts[500:600] = np.round(pts[500:600] * 4) / 4  # lattice points: many ties on both axes
+    tree = P.KdTree(ctx, pts)
+    rank = tree.preorder_rank()
+    otree = _oracle_tree(pts)
+    order = otree.nearest_neighbors([0.0, 0.0], 10.0)          # everything, in kd pre-order
+    np.testing.assert_array_equal(np.argsort(rank), order)
+    chain = np.arange(2000, dtype=np.float64)[:, None] * np.array([[1e-3, 1e-3]]) - 1.0   # sorted input: depth == n
+    np.testing.assert_array_equal(P.KdTree(ctx, chain).preorder_rank(), np.arange(2000))
+
+
 def test_radius_threshold_boundary(ctx):
     """inclusive `<=` on the sqrt-ed distance: hits at exactly r, misses one ulp below"""
     pts = np.array([[0.0, 0.0], [3.0, 4.0], [1.0, 1.0], [-0.3, 0.4]])
