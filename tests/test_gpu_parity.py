@@ -443,6 +443,23 @@ def test_belief_planning_shelf_config2(ctx):
     assert np.isfinite(want[0])
 
 
+def test_belief_planning_shelf_8_goals_config3(ctx):
+    """BASELINE config 3 shape (8 goal zones, B = 255 reachable beliefs) on a stand-in map, reduced iteration count"""
+    Z = 8
+    occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    zp = omap.zone_positions()
+    goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
+    pto = _grow_pto(omap, (0.0, -0.9), goals, 0.1, 2.0, 1500)
+    plan, want, typ = _belief_compare(ctx, omap, pmap, pto, [1.0 / Z] * Z)
+    assert len(plan.beliefs) == 255 and np.isfinite(want[0]) and plan.policy_leaf.sum() == Z
+    # QMDP on the same roadmap: 8 world-view dijkstras at once
+    xy, nvid, rp, col, ev = pto.graph.export(0)
+    finals = [pto.reach.get_final_nodes_for_world(w) for w in range(Z)]
+    got, _ = P.dijkstra_worlds(ctx, rp, col, xy, nvid, pmap.world_validities_words(), finals)
+    np.testing.assert_array_equal(got, pto.plan_qmdp())
+
+
 def test_build_belief_graph_mock(ctx):
     """pto.rs:548-590 'mock graph growth' on a stand-in map: node 2 sees the door, belief jump only there"""
     size = 200
