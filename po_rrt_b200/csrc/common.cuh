@@ -49,6 +49,13 @@ struct MapDev {
   const uint8_t* grid;  // fused code grid, tiled (see map.cu: tile_addr)
   const uint8_t* coarse[3]; // one class byte per 8x8 / 16x16 / 32x32 block, row-major (map.cu: C_* flags)
   int32_t cw[3];            // their row pitches
+  // edge3.cu: 2-bit class per 16 x 16 block (16 per word, row-major; staged in shared memory by the kernel) and the
+  // blocking-pixel bitmaps of the blocks, four orientations x 32 bytes per block
+  const uint32_t* plane;
+  const uint32_t* bits;
+  int32_t plane_cw;         // blocks per block row
+  int32_t plane_bytes;      // padded to a multiple of 16
+  int32_t bits_var_words;   // 32-bit words per orientation (= blocks * 8)
   int32_t H, W;         // logical size
   int32_t tiles_x;      // 128-byte tiles (16 x 8 px) per tile row
   int32_t kind;         // PORRT_DOMAIN_*
@@ -81,8 +88,9 @@ struct porrt_ctx {
   std::vector<uint64_t> validities;     // [n_validities * mask_words]
   std::vector<double> zone_pos;         // [2 * n_zones]
   std::vector<uint64_t> zone_world_masks;  // DOOR: zones_to_worlds [n_zones * mask_words]
-  DevBuf d_grid, d_coarse[3], d_validities, d_zone_pos;
-  int edge_variant = 3;  // 1: byte-grid warp walk; 2/3/4: class bytes + flattened strips with 8/16/32-px blocks
+  DevBuf d_grid, d_coarse[3], d_validities, d_zone_pos, d_plane, d_bits;
+  int edge_variant = 0;  // 0: edge3.cu (class plane in shared memory + block bitmaps); 1: byte-grid warp walk;
+                         // 2..7: class bytes + flattened strips (map.cu v2) with various block / group sizes
   // host copies of the raw images are NOT kept: the product never walks pixels on the CPU.
 
   // ---- vertices / cell grid (nn.cu)
@@ -161,6 +169,11 @@ int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const doub
                               int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st);
 int32_t map_edge_validity_indexed_dev(porrt_ctx* ctx, const double* xy_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev,
                                       int64_t n, int32_t* out_vid_dev, cudaStream_t st);
+// edge3.cu
+int32_t edge3_build(porrt_ctx* ctx, cudaStream_t st);
+bool edge3_usable(const porrt_ctx* ctx);
+int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
+                     uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st);
 // nn.cu helpers used by graph.cu
 int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi);
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,

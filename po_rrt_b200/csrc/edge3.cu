@@ -1,0 +1,486 @@
+// edge3.cu -- batched edge validity, third design (SURVEY.md 8(a) rows A3/A3'/A5): the headline kernel.
+//
+// Replaces Map::get_traversed_space + transition_validator (reference src/map_io.rs:216-241,495-513) and the
+// MapShelfDomain pair (src/map_shelves_io.rs:187-203,471-488) over line_drawing::Bresenham (crate 0.8).
+//
+// Why a third design: ncu on v2 (map.cu) showed the L1 data pipe at 57 % of its wavefront peak and 75 warp
+// instructions per edge: every class byte and every pixel was a scattered global load (32 distinct lines = 32 L1
+// wavefronts per warp instruction) and a resolved pixel cost ~15 instructions.  Here
+//   * the coarse level -- a 2-bit class per 16 x 16 block: free / mixed / all blocking / special -- is 64 KiB for an
+//     8192^2 map and is staged ONCE per CTA in shared memory (one bulk-async copy, mbarrier completion), so the
+//     two class lookups a 16-pixel strip needs are shared-memory reads (bank conflicts ~3 wavefronts instead of 32);
+//   * the fine level is a bitmap: 256 bits per block, stored as sixteen 16-bit vectors, one per position along the
+//     line's major axis, in the four orientations a line can cross a block (major axis i/j, minor step +/-).  One
+//     256-bit load (LDG.E.256) per block brings every pixel a strip can touch in that block; the strip is then
+//     tested in registers, 5 instructions per pixel, no further memory traffic;
+//   * pixel k of the line is a + k*U + floor(k*dy/dx)*V (closed form, A5) and floor(k*dy/dx) = hi32(k*S + 2^16) with
+//     S = min(floor(dy*2^32/dx), 2^32-1): ONE integer multiply-add, exact for dx < 2^15 (proof in DESIGN.md 3.1,
+//     exhaustive check in tests/test_oracle_golden.py).
+// Work is flattened as in v2: the strips of a warp's 32 edges form one sequence, lanes take consecutive groups of
+// four strips, undecided strips are queued in shared memory and resolved by full warps afterwards; strips of edges
+// already known to be blocked are dropped.  Blocks containing gray pixels (door zones: zone ids and the reference's
+// panics matter) go to a per-pixel pass over the fused byte grid; whenever the ORDER of events along the line could
+// matter the edge is re-walked sequentially (walk_sequential), which is what makes the panic codes bit-exact.
+#include "map_dev.cuh"
+
+#define E3_LOG_BS 4
+#define E3_BS 16
+#define E3_G 4              // consecutive strips of one edge per lane and round
+#define E3_QB 384           // bitmap-queue entries per warp
+#define E3_QG 256           // byte-queue entries per warp
+#define E3_BIAS 65536ull
+#define E3_MAX_WARPS 32
+
+#define K_FREE 0u
+#define K_MIXED 1u          // blocking and free pixels, nothing else: the bitmap decides
+#define K_BLOCKED 2u        // every pixel blocks
+#define K_SPECIAL 3u        // contains gray pixels (DOOR zones / gray without zone id): per-pixel pass on the byte grid
+
+struct Rec3 {               // 40 bytes per edge in shared memory
+  int32_t c0, n0;           // start pixel: major-axis / minor-axis coordinate
+  int32_t dxo;              // octant-space major delta = pixels on the line - 1
+  uint32_t S;               // fixed-point slope, see above
+  int32_t dirs;             // bit0 major axis is i (rows), bit1 major step is -1, bit2 minor step is -1
+  int32_t n_strips;         // 0: nothing to walk here (start or end outside the map)
+  int32_t lo_raw0;          // k of the first position (in k order) of strip 0's block column (<= 0)
+  int32_t idx0;             // block index of (major block of strip 0, minor block 0)
+  int32_t stride_major;     // block-index step per strip (signed)
+  int32_t stride_minor;     // block-index step per minor block
+};
+
+struct WarpMem {
+  Rec3 rec[32];
+  uint32_t obst[32];        // != 0: a blocking pixel is on the line
+  uint32_t zmin[32], zmax[32];
+  uint32_t qb[E3_QB];       // e | strip << 5 | look at block a << 30 | look at block b << 31
+  uint32_t qg[E3_QG];       // e | strip << 5
+};
+
+__device__ __forceinline__ uint32_t minor_of(uint32_t k, uint32_t S) {   // floor(k * dyo / dxo)
+  return (uint32_t)(((uint64_t)k * (uint64_t)S + E3_BIAS) >> 32);
+}
+
+__device__ __forceinline__ void ld256(uint32_t (&v)[8], const uint32_t* p) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------------------ the kernel
+// One persistent CTA per SM; blockDim.x / 32 warps, each with its own WarpMem.  dynamic shared memory:
+//   [ class plane (m.plane_bytes) | mbarrier (16) | WarpMem x warps ]
+template <int KIND, bool INDEXED>
+__global__ void __launch_bounds__(E3_MAX_WARPS * 32, 1)
+edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double2* __restrict__ to, int64_t n,
+                        int32_t* __restrict__ out_vid, uint64_t* __restrict__ out_mask,
+                        const uint64_t* __restrict__ validities, const int32_t* __restrict__ from_idx,
+                        const int32_t* __restrict__ to_idx) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t* s_plane = (const uint32_t*)smem;
+  uint64_t* s_mbar = (uint64_t*)(smem + m.plane_bytes);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpMem& wm = *(WarpMem*)(smem + m.plane_bytes + 16 + (size_t)wib * sizeof(WarpMem));
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // ---- stage the class plane: bulk-async copies global -> shared, completion counted in bytes on an mbarrier
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_mbar)), "r"((uint32_t)m.plane_bytes) : "memory");
+    for (int off = 0; off < m.plane_bytes; off += 32768) {
+      const int sz = min(32768, m.plane_bytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem + off)),
+                   "l"((const unsigned char*)m.plane + off), "r"((uint32_t)sz), "r"(smem_u32(s_mbar))
+                   : "memory");
+    }
+  }
+  bool plane_ready = false;
+
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int cw = m.plane_cw;
+  int qb_n = 0, qg_n = 0;   // queue fill, warp-uniform
+
+  // ---- resolution of the queued strips
+  auto drain = [&]() {
+    __syncwarp();
+    // (1) bitmap strips: drop those of edges already blocked, then one lane per strip
+    int live_n = 0;
+    for (int q0 = 0; q0 < qb_n; q0 += 32) {
+      const int q = q0 + lane;
+      uint32_t ent = 0;
+      bool live = false;
+      if (q < qb_n) { ent = wm.qb[q]; live = wm.obst[ent & 31] == 0; }
+      const unsigned lv = __ballot_sync(0xffffffffu, live);
+      __syncwarp();
+      if (live) wm.qb[live_n + __popc(lv & lt_mask)] = ent;
+      live_n += __popc(lv);
+      __syncwarp();
+    }
+    for (int q0 = 0; q0 < live_n; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < live_n) {
+        const uint32_t ent = wm.qb[q];
+        const int e = ent & 31, ts = (int)((ent >> 5) & 0x1ffffu);
+        if (wm.obst[e] == 0) {
+          const Rec3& r = wm.rec[e];
+          const int dxo = r.dxo, dirs = r.dirs, n0 = r.n0, stride_minor = r.stride_minor;
+          const uint32_t S = r.S;
+          const int lo_raw = r.lo_raw0 + ts * E3_BS;
+          const int k_lo = max(0, lo_raw), k_hi = min(dxo, lo_raw + E3_BS - 1);
+          const int sn = (dirs & 4) ? -1 : 1;
+          const bool neg_major = (dirs & 2) != 0;
+          const int na = n0 + sn * (int)minor_of((uint32_t)k_lo, S);
+          const int bn_a = na >> E3_LOG_BS;
+          const int blk_a = r.idx0 + ts * r.stride_major + bn_a * stride_minor;
+          const int blk_b = blk_a + sn * stride_minor;
+          const uint32_t* tiles = m.bits + (size_t)(((dirs & 1) << 1) | ((dirs >> 2) & 1)) * (size_t)m.bits_var_words;
+          uint32_t A[8], B[8];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { A[w] = 0; B[w] = 0; }
+          if (ent & (1u << 30)) ld256(A, tiles + (size_t)blk_a * 8);
+          if (ent & (1u << 31)) ld256(B, tiles + (size_t)blk_b * 8);
+          // u_t = minor offset of the pixel at major position t, counted from block a's first row in walking
+          // direction: 0..15 in block a, 16..31 in block b.  hi32(Y_t) = u_t - t, Y linear in t.
+          const int ref = sn > 0 ? (bn_a << E3_LOG_BS) : (bn_a << E3_LOG_BS) + E3_BS - 1;
+          const int u_base = sn * (n0 - ref);
+          const int k0 = neg_major ? lo_raw + E3_BS - 1 : lo_raw;          // k at t = 0
+          uint64_t Y = ((uint64_t)(uint32_t)u_base << 32) + (uint64_t)((int64_t)k0 * (int64_t)(uint64_t)S) + E3_BIAS;
+          const uint64_t D = (neg_major ? (uint64_t)0 - (uint64_t)S : (uint64_t)S) - (1ull << 32);
+          const int t_lo = neg_major ? lo_raw + E3_BS - 1 - k_hi : k_lo - lo_raw;
+          const int t_hi = neg_major ? lo_raw + E3_BS - 1 - k_lo : k_hi - lo_raw;
+          const uint32_t Vm = ((2u << t_hi) - 1u) & ~((1u << t_lo) - 1u);  // positions that are pixels of this edge
+          uint32_t acc = 0;
+#pragma unroll
+          for (int t = 0; t < E3_BS; ++t) {
+            const uint32_t V = (t & 1) ? __byte_perm(A[t >> 1], B[t >> 1], 0x7632) : __byte_perm(A[t >> 1], B[t >> 1], 0x5410);
+            const uint32_t x = Vm & (1u << t);
+            acc |= __funnelshift_l(x, x, (uint32_t)(Y >> 32)) & V;     // bit t rotated to bit u_t
+            Y += D;
+          }
+          if (acc) wm.obst[e] = 1;
+        }
+      }
+      __syncwarp();
+    }
+    // (2) strips through blocks with gray pixels: per pixel on the fused byte grid, one lane per strip
+    for (int q0 = 0; q0 < qg_n; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < qg_n) {
+        const uint32_t ent = wm.qg[q];
+        const int e = ent & 31, ts = (int)(ent >> 5);
+        const Rec3& r = wm.rec[e];
+        const int dxo = r.dxo, dirs = r.dirs;
+        const uint32_t S = r.S;
+        const int lo_raw = r.lo_raw0 + ts * E3_BS;
+        const int k_lo = max(0, lo_raw), k_hi = min(dxo, lo_raw + E3_BS - 1);
+        const int sm = (dirs & 2) ? -1 : 1, sn = (dirs & 4) ? -1 : 1;
+        uint32_t f = 0, zmin = 255, zmax = 0;
+        for (int k = k_lo; k <= k_hi; ++k) {
+          const int major = r.c0 + sm * k, minor = r.n0 + sn * (int)minor_of((uint32_t)k, S);
+          const int i = (dirs & 1) ? major : minor, j = (dirs & 1) ? minor : major;
+          const uint32_t code = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
+          if (code != 255) {
+            if (KIND == PORRT_DOMAIN_SHELF) f = 1;
+            else if (code == 0) f = 1;
+            else { zmin = min(zmin, code); zmax = max(zmax, code); }
+          }
+        }
+        if (f) wm.obst[e] = 1;
+        if (zmax) { atomicMin(&wm.zmin[e], zmin); atomicMax(&wm.zmax[e], zmax); }
+      }
+    }
+    __syncwarp();
+    qb_n = 0; qg_n = 0;
+  };
+
+  for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
+    const int64_t eidx = base + lane;
+    // ---- per-lane setup of one edge
+    Rec3 mine;
+    int my_flags = 0, my_dyo = 0;  // flags: bit0 start outside the map, bit1 end outside
+    mine.c0 = mine.n0 = mine.dxo = 0; mine.S = 0; mine.dirs = 0; mine.n_strips = 0;
+    mine.lo_raw0 = mine.idx0 = mine.stride_major = mine.stride_minor = 0;
+    if (eidx < n) {
+      const double2 a = INDEXED ? from[from_idx[eidx]] : from[eidx];
+      const double2 b = INDEXED ? to[to_idx[eidx]] : to[eidx];
+      const EdgeSetup s = make_setup(m, a.x, a.y, b.x, b.y);
+      const int ui = (s.steps & 3) - 1, uj = ((s.steps >> 2) & 3) - 1, vi = ((s.steps >> 4) & 3) - 1, vj = ((s.steps >> 6) & 3) - 1;
+      mine.c0 = ui ? s.ai : s.aj; mine.n0 = ui ? s.aj : s.ai;
+      mine.dxo = s.dxo; my_dyo = s.dyo;
+      mine.dirs = (ui ? 1 : 0) | ((ui + uj) < 0 ? 2 : 0) | ((vi + vj) < 0 ? 4 : 0);
+      my_flags = s.flags;
+      if (!my_flags) {
+        if (s.dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
+          if (s.dyo == s.dxo) mine.S = 0xFFFFFFFFu;
+          else {
+            const uint32_t d = (uint32_t)s.dxo, num = (uint32_t)s.dyo << 16;
+            const uint32_t q1 = num / d, r1 = num - q1 * d;
+            mine.S = (q1 << 16) + ((r1 << 16) / d);
+          }
+        }
+        const int sgn = (mine.dirs & 2) ? -1 : 1;
+        const int b0 = mine.c0 >> E3_LOG_BS, b1 = (mine.c0 + sgn * mine.dxo) >> E3_LOG_BS;
+        mine.n_strips = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;
+        mine.lo_raw0 = sgn * ((b0 << E3_LOG_BS) - mine.c0) - ((mine.dirs & 2) ? E3_BS - 1 : 0);
+        mine.stride_major = sgn * ((mine.dirs & 1) ? cw : 1);
+        mine.stride_minor = (mine.dirs & 1) ? 1 : cw;
+        mine.idx0 = b0 * ((mine.dirs & 1) ? cw : 1);
+      }
+    }
+    wm.rec[lane] = mine;
+    wm.obst[lane] = 0; wm.zmin[lane] = 255; wm.zmax[lane] = 0;
+    // items = groups of E3_G strips; every lane owns at least one (possibly empty) item so that the inclusive prefix
+    // sums are strictly increasing and the owner of a flattened position can be ranked with a bitmask
+    int incl = max(1, (mine.n_strips + E3_G - 1) / E3_G);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const bool may_overflow = total * E3_G > min(E3_QB, E3_QG);     // warp-uniform
+    __syncwarp();
+    if (!plane_ready) {
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
+      plane_ready = true;
+    }
+
+    // ---- pass 1: item w = w0 + lane of the flattened sequence; classes of the <= 2 blocks of each strip
+    for (int w0 = 0; w0 < total; w0 += 32) {
+      if (may_overflow && (qb_n > E3_QB - 32 * E3_G || qg_n > E3_QG - 32 * E3_G)) drain();
+      const int d = incl - w0;                                    // edge `lane` ends before window position d
+      const int e_base = __popc(__ballot_sync(0xffffffffu, d <= 0));
+      const unsigned marks = __reduce_or_sync(0xffffffffu, (d >= 1 && d <= 32) ? (1u << (d - 1)) : 0u);
+      const int e = min(31, e_base + __popc(marks & lt_mask));
+      const int p_prev = __shfl_sync(0xffffffffu, incl, (e + 31) & 31);
+      const int w = w0 + lane;
+      uint32_t look = 0;      // per strip g: bit g = queue for the bitmap pass, bit 8+g = block a, bit 16+g = block b,
+                              // bit 24+g = queue for the byte pass
+      int ts0 = 0;
+      if (w < total) {
+        const Rec3& r = wm.rec[e];
+        const int n_strips = r.n_strips, dxo = r.dxo, n0 = r.n0, stride_minor = r.stride_minor, stride_major = r.stride_major;
+        const uint32_t S = r.S;
+        const int sn = (r.dirs & 4) ? -1 : 1;
+        ts0 = (w - (e ? p_prev : 0)) * E3_G;
+        int lo_raw = r.lo_raw0 + ts0 * E3_BS;
+        int idx_m = r.idx0 + ts0 * stride_major;
+        uint32_t any_blocked = 0;
+#pragma unroll
+        for (int g = 0; g < E3_G; ++g) {
+          if (ts0 + g < n_strips) {
+            const int k_lo = max(0, lo_raw), k_hi = min(dxo, lo_raw + E3_BS - 1);
+            const int bn_a = (n0 + sn * (int)minor_of((uint32_t)k_lo, S)) >> E3_LOG_BS;
+            const int bn_b = (n0 + sn * (int)minor_of((uint32_t)k_hi, S)) >> E3_LOG_BS;
+            const int ia = idx_m + bn_a * stride_minor, ib = idx_m + bn_b * stride_minor;
+            const uint32_t ca = (s_plane[ia >> 4] >> ((ia & 15) << 1)) & 3u;
+            const uint32_t cb = (s_plane[ib >> 4] >> ((ib & 15) << 1)) & 3u;
+            const bool special = ca == K_SPECIAL || cb == K_SPECIAL;
+            any_blocked |= (ca == K_BLOCKED || cb == K_BLOCKED) ? 1u : 0u;
+            const bool la = ca == K_MIXED, lb = cb == K_MIXED && ib != ia;
+            if (special) look |= 1u << (24 + g);
+            else if (la || lb) look |= (1u << g) | (la ? (1u << (8 + g)) : 0u) | (lb ? (1u << (16 + g)) : 0u);
+          }
+          lo_raw += E3_BS; idx_m += stride_major;
+        }
+        if (any_blocked) { wm.obst[e] = 1; look &= 0xff000000u; }   // the bitmaps cannot change the outcome any more
+      }
+      // enqueue: exclusive scan over the lanes of (bitmap entries | byte entries << 16)
+      if (__any_sync(0xffffffffu, look != 0)) {
+        const int cnt = __popc(look & 0xffu) | (__popc(look >> 24) << 16);
+        int sc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, sc, o);
+          if (lane >= o) sc += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, sc, 31);
+        sc -= cnt;
+        int pb = qb_n + (sc & 0xffff), pg = qg_n + (sc >> 16);
+#pragma unroll
+        for (int g = 0; g < E3_G; ++g) {
+          if (look & (1u << g))
+            wm.qb[pb++] = (uint32_t)e | ((uint32_t)(ts0 + g) << 5) | (((look >> (8 + g)) & 1u) << 30) | (((look >> (16 + g)) & 1u) << 31);
+          if (look & (1u << (24 + g))) wm.qg[pg++] = (uint32_t)e | ((uint32_t)(ts0 + g) << 5);
+        }
+        qb_n += tot & 0xffff; qg_n += tot >> 16;
+      }
+      __syncwarp();
+    }
+    // ---- pass 2: bitmaps / pixels of the strips that are still undecided
+    if (qb_n | qg_n) drain();
+    __syncwarp();
+
+    // ---- results
+    if (eidx < n) {
+      int32_t r;
+      bool slow = false;
+      if (my_flags & 1) r = PORRT_PANIC_OOB;             // the first pixel read already panics
+      else if (my_flags & 2) slow = true;                // end pixel outside: order of events matters
+      else {
+        const bool blocked = wm.obst[lane] != 0;
+        if (KIND == PORRT_DOMAIN_SHELF) r = blocked ? R_BLOCKED : R_FREE;   // Low and High obstacle both invalidate the edge
+        else {
+          const uint32_t zmin = wm.zmin[lane], zmax = wm.zmax[lane];
+          if (zmax != 0 && (zmin != zmax || zmax == 254)) slow = true;      // order of events decides: re-walk
+          else r = blocked ? R_BLOCKED : (zmax ? (int32_t)zmin - 1 : R_FREE);
+        }
+      }
+      if (slow) {
+        Walker wk;
+        const int sm = (mine.dirs & 2) ? -1 : 1, sn = (mine.dirs & 4) ? -1 : 1;
+        wk.dxo = mine.dxo; wk.dyo = my_dyo;
+        wk.M = mine.dxo > 1 ? (0xFFFFFFFFFFFFFFFFull / (uint64_t)mine.dxo) + 1ull : 0ull;
+        if (mine.dirs & 1) { wk.ai = mine.c0; wk.aj = mine.n0; wk.ui = sm; wk.uj = 0; wk.vi = 0; wk.vj = sn; }
+        else { wk.ai = mine.n0; wk.aj = mine.c0; wk.ui = 0; wk.uj = sm; wk.vi = sn; wk.vj = 0; }
+        r = walk_sequential<KIND>(m, wk);
+        if (KIND == PORRT_DOMAIN_SHELF && r == R_LOW) r = R_BLOCKED;
+      }
+      const int32_t vid = walk_to_validity(m, r);
+      out_vid[eidx] = vid;
+      if (out_mask) {
+        if (m.mask_words == 1) out_mask[eidx] = vid >= 0 ? validities[vid] : 0ull;
+        else
+          for (int wd = 0; wd < m.mask_words; ++wd)
+            out_mask[eidx * m.mask_words + wd] = vid >= 0 ? validities[(int64_t)vid * m.mask_words + wd] : 0ull;
+      }
+    }
+    __syncwarp();
+  }
+  if (!plane_ready) {  // a warp without work must not leave while the copy is in flight
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ map build
+// One thread per (block, row): 16 fused codes -> 16-bit blocking mask of the row; the column vectors come from
+// ballots (a warp holds the 16 rows of two blocks).  Writes the four bitmap orientations and the class plane.
+//   orientation 0: major j, minor i ascending  : vec[t = column] bit r        1: the same with bit 15 - r
+//   orientation 2: major i, minor j ascending  : vec[t = row]    bit c        3: the same with bit 15 - c
+template <int KIND>
+__global__ void __launch_bounds__(256) edge3_build_kernel(const uint8_t* __restrict__ grid, int H, int W, int tiles_x, int cw, int ch,
+                                                          uint32_t* __restrict__ plane, uint16_t* __restrict__ bits, size_t var_halfwords) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, r = lane & 15;
+  const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_blocks = (int64_t)cw * ch;
+  const int64_t blk = pair * 2 + half;
+  const bool have = blk < n_blocks;
+  const int bi = have ? (int)(blk / cw) : 0, bj = have ? (int)(blk % cw) : 0;
+  const int i = bi * E3_BS + r;
+  uint32_t rowmask = 0, n_in = 0, n_block = 0, n_special = 0;
+  if (have && i < H) {
+#pragma unroll
+    for (int c = 0; c < E3_BS; ++c) {
+      const int j = bj * E3_BS + c;
+      if (j < W) {
+        const uint32_t code = grid[tile_addr(i, j, tiles_x)];
+        ++n_in;
+        const bool blocking = KIND == PORRT_DOMAIN_SHELF ? code != 255 : code == 0;
+        if (blocking) { rowmask |= 1u << c; ++n_block; }
+        else if (code != 255) ++n_special;
+      }
+    }
+  }
+  uint32_t colvec = 0;
+#pragma unroll
+  for (int c = 0; c < E3_BS; ++c) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, (rowmask >> c) & 1u);
+    if (r == c) colvec = (bal >> (16 * half)) & 0xffffu;
+  }
+  uint32_t cnt = n_in | (n_block << 10) | (n_special << 20);   // <= 256 each: three 10-bit counters
+#pragma unroll
+  for (int o = 8; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (have) {
+    uint16_t* t0 = bits + (size_t)blk * 16 + r;
+    t0[0] = (uint16_t)colvec;
+    t0[var_halfwords] = (uint16_t)(__brev(colvec) >> 16);
+    t0[2 * var_halfwords] = (uint16_t)rowmask;
+    t0[3 * var_halfwords] = (uint16_t)(__brev(rowmask) >> 16);
+    if (r == 0) {
+      const uint32_t t_in = cnt & 1023u, t_block = (cnt >> 10) & 1023u, t_special = cnt >> 20;
+      const uint32_t cls = t_special ? K_SPECIAL : (t_block == 0 ? K_FREE : (t_block == t_in ? K_BLOCKED : K_MIXED));
+      if (cls) atomicOr(&plane[blk >> 4], cls << ((blk & 15) << 1));
+    }
+  }
+}
+
+int32_t edge3_build(porrt_ctx* ctx, cudaStream_t st) {
+  MapDev& m = ctx->map;
+  const int cw = (m.W + E3_BS - 1) / E3_BS, ch = (m.H + E3_BS - 1) / E3_BS;
+  const size_t n_blocks = (size_t)cw * ch;
+  const size_t plane_bytes = ((((n_blocks + 15) / 16) * 4 + 15) / 16) * 16;
+  CUDA_TRY(ctx, ctx->d_plane.ensure(plane_bytes));
+  CUDA_TRY(ctx, ctx->d_bits.ensure(n_blocks * 32 * 4));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plane.p, 0, plane_bytes, st));
+  const int grid = div_up((int64_t)((n_blocks + 1) / 2) * 32, 256);
+  if (m.kind == PORRT_DOMAIN_SHELF)
+    edge3_build_kernel<PORRT_DOMAIN_SHELF><<<grid, 256, 0, st>>>(m.grid, m.H, m.W, m.tiles_x, cw, ch, ctx->d_plane.as<uint32_t>(), ctx->d_bits.as<uint16_t>(), n_blocks * 16);
+  else
+    edge3_build_kernel<PORRT_DOMAIN_DOOR><<<grid, 256, 0, st>>>(m.grid, m.H, m.W, m.tiles_x, cw, ch, ctx->d_plane.as<uint32_t>(), ctx->d_bits.as<uint16_t>(), n_blocks * 16);
+  LAUNCH_CHECK(ctx);
+  m.plane = ctx->d_plane.as<uint32_t>();
+  m.bits = ctx->d_bits.as<uint32_t>();
+  m.plane_cw = cw;
+  m.plane_bytes = (int32_t)plane_bytes;
+  m.bits_var_words = (int32_t)(n_blocks * 8);
+  return PORRT_OK;
+}
+
+static const int E3_SMEM_LIMIT = 227 * 1024;
+
+static int edge3_max_warps(const porrt_ctx* ctx) {
+  const int64_t room = (int64_t)E3_SMEM_LIMIT - ctx->map.plane_bytes - 16;
+  const int64_t w = room / (int64_t)sizeof(WarpMem);
+  return (int)(w > E3_MAX_WARPS ? E3_MAX_WARPS : w);
+}
+
+// the class plane has to fit in shared memory next to at least 8 warps' queues, and dx < 2^15 (exact slope)
+bool edge3_usable(const porrt_ctx* ctx) {
+  return ctx->map.plane != nullptr && edge3_max_warps(ctx) >= 8 && ctx->map.H <= 32768 && ctx->map.W <= 32768;
+}
+
+template <int KIND, bool INDEXED>
+static int32_t edge3_launch_t(porrt_ctx* ctx, const double2* from, const double2* to, int64_t n, int32_t* out_vid, uint64_t* out_mask,
+                              const int32_t* from_idx, const int32_t* to_idx, cudaStream_t st) {
+  auto kern = edge_validity_v3_kernel<KIND, INDEXED>;
+  static bool attr_set[16] = {};
+  if (!attr_set[ctx->device & 15]) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E3_SMEM_LIMIT));
+    attr_set[ctx->device & 15] = true;
+  }
+  const int max_warps = edge3_max_warps(ctx);
+  const int64_t warps_needed = (n + 31) / 32;
+  // one CTA per SM; small batches are spread over the SMs with fewer warps each
+  int warps = (int)((warps_needed + ctx->sm_count - 1) / ctx->sm_count);
+  warps = warps < 4 ? 4 : (warps > max_warps ? max_warps : warps);
+  int64_t ctas = (warps_needed + warps - 1) / warps;
+  if (ctas > ctx->sm_count) ctas = ctx->sm_count;
+  const size_t smem = (size_t)ctx->map.plane_bytes + 16 + (size_t)warps * sizeof(WarpMem);
+  kern<<<(int)ctas, warps * 32, smem, st>>>(ctx->map, from, to, n, out_vid, out_mask, ctx->d_validities.as<uint64_t>(), from_idx, to_idx);
+  LAUNCH_CHECK(ctx);
+  return PORRT_OK;
+}
+
+int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
+                     uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st) {
+  const double2* f = (const double2*)from_dev;
+  const double2* t = (const double2*)to_dev;
+  const bool shelf = ctx->map.kind == PORRT_DOMAIN_SHELF;
+  if (from_idx_dev)
+    return shelf ? edge3_launch_t<PORRT_DOMAIN_SHELF, true>(ctx, f, t, n, out_vid_dev, out_mask_dev, from_idx_dev, to_idx_dev, st)
+                 : edge3_launch_t<PORRT_DOMAIN_DOOR, true>(ctx, f, t, n, out_vid_dev, out_mask_dev, from_idx_dev, to_idx_dev, st);
+  return shelf ? edge3_launch_t<PORRT_DOMAIN_SHELF, false>(ctx, f, t, n, out_vid_dev, out_mask_dev, nullptr, nullptr, st)
+               : edge3_launch_t<PORRT_DOMAIN_DOOR, false>(ctx, f, t, n, out_vid_dev, out_mask_dev, nullptr, nullptr, st);
+}
