@@ -53,7 +53,7 @@ struct MapDev {
   // blocking-pixel bitmaps of the blocks, four orientations x 32 bytes per block
   const uint32_t* plane;
   const uint32_t* bits;
-  int32_t plane_cw;         // blocks per block row
+  int32_t plane_cw, plane_ch;  // blocks per block row / block rows
   int32_t plane_bytes;      // padded to a multiple of 16
   int32_t bits_var_words;   // 32-bit words per orientation (= blocks * 8)
   int32_t H, W;         // logical size

@@ -36,28 +36,38 @@
 #define K_BLOCKED 2u        // every pixel blocks
 #define K_SPECIAL 3u        // contains gray pixels (DOOR zones / gray without zone id): per-pixel pass on the byte grid
 
-struct Rec3 {               // 40 bytes per edge in shared memory
-  int32_t c0, n0;           // start pixel: major-axis / minor-axis coordinate
-  int32_t dxo;              // octant-space major delta = pixels on the line - 1
-  uint32_t S;               // fixed-point slope, see above
-  int32_t dirs;             // bit0 major axis is i (rows), bit1 major step is -1, bit2 minor step is -1
-  int32_t n_strips;         // 0: nothing to walk here (start or end outside the map)
+// Per-edge record in shared memory, three 16-byte chunks.  The minor axis is MIRRORED for edges whose minor step is
+// -1 (n' = 16 * blocks_along_minor - 1 - n), so that in (k, n') space every line has a non-negative slope: block row
+// bn' = n' >> 4 only ever grows with k, and the real block index is idx_m + bn' * stride_minor with the sign folded
+// into stride_minor / idx0.
+struct Rec3 {
+  // chunk 0
   int32_t lo_raw0;          // k of the first position (in k order) of strip 0's block column (<= 0)
-  int32_t idx0;             // block index of (major block of strip 0, minor block 0)
+  int32_t idx0;             // block index of (major block of strip 0, mirrored minor block 0)
   int32_t stride_major;     // block-index step per strip (signed)
-  int32_t stride_minor;     // block-index step per minor block
+  int32_t stride_minor;     // block-index step per mirrored minor block (signed)
+  // chunk 1
+  int32_t n0m;              // (mirrored) minor coordinate of the start pixel
+  int32_t dxo;              // octant-space major delta = pixels on the line - 1
+  uint32_t S;               // fixed-point slope: minor offset of pixel k = hi32(k * S + 2^16)
+  int32_t n_strips;         // 0: nothing to walk here (start or end outside the map)
+  // chunk 2
+  int32_t c0, n0;           // start pixel: major-axis / real minor-axis coordinate
+  int32_t dirs;             // bit0 major axis is i (rows), bit1 major step is -1, bit2 minor step is -1
+  int32_t pad;
 };
 
 struct WarpMem {
-  Rec3 rec[32];
+  uint4 rec[3][32];         // Rec3 chunks, chunk-major (conflict-free 16-byte accesses)
   uint32_t obst[32];        // != 0: a blocking pixel is on the line
   uint32_t zmin[32], zmax[32];
-  uint32_t qb[E3_QB];       // e | strip << 5 | look at block a << 30 | look at block b << 31
+  uint32_t qb[E3_QB];       // e | strip << 5
   uint32_t qg[E3_QG];       // e | strip << 5
 };
 
-__device__ __forceinline__ uint32_t minor_of(uint32_t k, uint32_t S) {   // floor(k * dyo / dxo)
-  return (uint32_t)(((uint64_t)k * (uint64_t)S + E3_BIAS) >> 32);
+// n' of pixel k = hi32(k * S + (n0m << 32 | 2^16))
+__device__ __forceinline__ int32_t minor_m(uint32_t k, uint32_t S, int32_t n0m) {
+  return (int32_t)(((uint64_t)k * (uint64_t)S + (((uint64_t)(uint32_t)n0m << 32) | E3_BIAS)) >> 32);
 }
 
 __device__ __forceinline__ void ld256(uint32_t (&v)[8], const uint32_t* p) {
@@ -67,6 +77,13 @@ __device__ __forceinline__ void ld256(uint32_t (&v)[8], const uint32_t* p) {
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait0(uint64_t* bar) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 // One persistent CTA per SM; blockDim.x / 32 warps, each with its own WarpMem.  dynamic shared memory:
@@ -78,7 +95,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
                         const uint64_t* __restrict__ validities, const int32_t* __restrict__ from_idx,
                         const int32_t* __restrict__ to_idx) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t* s_plane = (const uint32_t*)smem;
+  const uint8_t* s_plane = (const uint8_t*)smem;
   uint64_t* s_mbar = (uint64_t*)(smem + m.plane_bytes);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpMem& wm = *(WarpMem*)(smem + m.plane_bytes + 16 + (size_t)wib * sizeof(WarpMem));
@@ -103,7 +120,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
 
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  const int cw = m.plane_cw;
+  const int cw = m.plane_cw, ch = m.plane_ch;
   int qb_n = 0, qg_n = 0;   // queue fill, warp-uniform
 
   // ---- resolution of the queued strips
@@ -126,31 +143,28 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       const int q = q0 + lane;
       if (q < live_n) {
         const uint32_t ent = wm.qb[q];
-        const int e = ent & 31, ts = (int)((ent >> 5) & 0x1ffffu);
+        const int e = ent & 31, ts = (int)(ent >> 5);
         if (wm.obst[e] == 0) {
-          const Rec3& r = wm.rec[e];
-          const int dxo = r.dxo, dirs = r.dirs, n0 = r.n0, stride_minor = r.stride_minor;
-          const uint32_t S = r.S;
-          const int lo_raw = r.lo_raw0 + ts * E3_BS;
+          const uint4 r0 = wm.rec[0][e], r1 = wm.rec[1][e];
+          const int dirs = (int)wm.rec[2][e].z;
+          const int dxo = (int)r1.y, n0m = (int)r1.x;
+          const uint32_t S = r1.z;
+          const int lo_raw = (int)r0.x + ts * E3_BS;
           const int k_lo = max(0, lo_raw), k_hi = min(dxo, lo_raw + E3_BS - 1);
-          const int sn = (dirs & 4) ? -1 : 1;
           const bool neg_major = (dirs & 2) != 0;
-          const int na = n0 + sn * (int)minor_of((uint32_t)k_lo, S);
-          const int bn_a = na >> E3_LOG_BS;
-          const int blk_a = r.idx0 + ts * r.stride_major + bn_a * stride_minor;
-          const int blk_b = blk_a + sn * stride_minor;
+          const int bn_a = minor_m((uint32_t)k_lo, S, n0m) >> E3_LOG_BS;
+          const int bn_b = minor_m((uint32_t)k_hi, S, n0m) >> E3_LOG_BS;
+          const int blk_a = (int)r0.y + ts * (int)r0.z + bn_a * (int)r0.w;
           const uint32_t* tiles = m.bits + (size_t)(((dirs & 1) << 1) | ((dirs >> 2) & 1)) * (size_t)m.bits_var_words;
           uint32_t A[8], B[8];
 #pragma unroll
-          for (int w = 0; w < 8; ++w) { A[w] = 0; B[w] = 0; }
-          if (ent & (1u << 30)) ld256(A, tiles + (size_t)blk_a * 8);
-          if (ent & (1u << 31)) ld256(B, tiles + (size_t)blk_b * 8);
-          // u_t = minor offset of the pixel at major position t, counted from block a's first row in walking
-          // direction: 0..15 in block a, 16..31 in block b.  hi32(Y_t) = u_t - t, Y linear in t.
-          const int ref = sn > 0 ? (bn_a << E3_LOG_BS) : (bn_a << E3_LOG_BS) + E3_BS - 1;
-          const int u_base = sn * (n0 - ref);
+          for (int w = 0; w < 8; ++w) B[w] = 0;
+          ld256(A, tiles + (size_t)blk_a * 8);
+          if (bn_b != bn_a) ld256(B, tiles + (size_t)(blk_a + (int)r0.w) * 8);
+          // u_t = minor offset (walking direction) of the pixel at major position t, counted from block a's first
+          // row: 0..15 in block a, 16..31 in block b.  hi32(Y_t) = u_t - t, Y linear in t.
           const int k0 = neg_major ? lo_raw + E3_BS - 1 : lo_raw;          // k at t = 0
-          uint64_t Y = ((uint64_t)(uint32_t)u_base << 32) + (uint64_t)((int64_t)k0 * (int64_t)(uint64_t)S) + E3_BIAS;
+          uint64_t Y = ((uint64_t)(uint32_t)(n0m - (bn_a << E3_LOG_BS)) << 32) + (uint64_t)((int64_t)k0 * (int64_t)(uint64_t)S) + E3_BIAS;
           const uint64_t D = (neg_major ? (uint64_t)0 - (uint64_t)S : (uint64_t)S) - (1ull << 32);
           const int t_lo = neg_major ? lo_raw + E3_BS - 1 - k_hi : k_lo - lo_raw;
           const int t_hi = neg_major ? lo_raw + E3_BS - 1 - k_lo : k_hi - lo_raw;
@@ -168,32 +182,41 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       }
       __syncwarp();
     }
-    // (2) strips through blocks with gray pixels: per pixel on the fused byte grid, one lane per strip
-    for (int q0 = 0; q0 < qg_n; q0 += 32) {
-      const int q = q0 + lane;
+    // (2) strips through blocks with gray pixels: per pixel on the fused byte grid, 16 lanes per strip
+    for (int q0 = 0; q0 < qg_n; q0 += 2) {
+      const int q = q0 + (lane >> 4);
+      uint32_t code = 255;
+      int e = 0;
       if (q < qg_n) {
         const uint32_t ent = wm.qg[q];
-        const int e = ent & 31, ts = (int)(ent >> 5);
-        const Rec3& r = wm.rec[e];
-        const int dxo = r.dxo, dirs = r.dirs;
-        const uint32_t S = r.S;
-        const int lo_raw = r.lo_raw0 + ts * E3_BS;
-        const int k_lo = max(0, lo_raw), k_hi = min(dxo, lo_raw + E3_BS - 1);
-        const int sm = (dirs & 2) ? -1 : 1, sn = (dirs & 4) ? -1 : 1;
-        uint32_t f = 0, zmin = 255, zmax = 0;
-        for (int k = k_lo; k <= k_hi; ++k) {
-          const int major = r.c0 + sm * k, minor = r.n0 + sn * (int)minor_of((uint32_t)k, S);
+        e = ent & 31;
+        const int ts = (int)(ent >> 5);
+        const uint4 r0 = wm.rec[0][e], r1 = wm.rec[1][e], r2 = wm.rec[2][e];
+        const int dirs = (int)r2.z, dxo = (int)r1.y;
+        const int lo_raw = (int)r0.x + ts * E3_BS;
+        const int k = max(0, lo_raw) + (lane & 15);
+        if (k <= min(dxo, lo_raw + E3_BS - 1)) {
+          const int mk = minor_m((uint32_t)k, r1.z, 0);
+          const int major = (int)r2.x + ((dirs & 2) ? -k : k), minor = (int)r2.y + ((dirs & 4) ? -mk : mk);
           const int i = (dirs & 1) ? major : minor, j = (dirs & 1) ? minor : major;
-          const uint32_t code = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
-          if (code != 255) {
-            if (KIND == PORRT_DOMAIN_SHELF) f = 1;
-            else if (code == 0) f = 1;
-            else { zmin = min(zmin, code); zmax = max(zmax, code); }
-          }
+          code = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
         }
-        if (f) wm.obst[e] = 1;
-        if (zmax) { atomicMin(&wm.zmin[e], zmin); atomicMax(&wm.zmax[e], zmax); }
       }
+      const bool blocking = KIND == PORRT_DOMAIN_SHELF ? code != 255 : code == 0;
+      const bool gray = KIND != PORRT_DOMAIN_SHELF && code != 0 && code != 255;
+      const unsigned half_mask = 0xffffu << (lane & 16);
+      const unsigned bl = __ballot_sync(0xffffffffu, blocking) & half_mask;
+      const unsigned gr_all = __ballot_sync(0xffffffffu, gray);
+      if (gr_all) {   // warp-uniform
+        uint32_t zmin = gray ? code : 255u, zmax = gray ? code : 0u;
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {   // within each half warp
+          zmin = min(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+          zmax = max(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        }
+        if ((gr_all & half_mask) && (lane & 15) == 0) { atomicMin(&wm.zmin[e], zmin); atomicMax(&wm.zmax[e], zmax); }
+      }
+      if (bl && (lane & 15) == 0) wm.obst[e] = 1;
     }
     __syncwarp();
     qb_n = 0; qg_n = 0;
@@ -202,42 +225,57 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
   for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
     const int64_t eidx = base + lane;
     // ---- per-lane setup of one edge
-    Rec3 mine;
-    int my_flags = 0, my_dyo = 0;  // flags: bit0 start outside the map, bit1 end outside
-    mine.c0 = mine.n0 = mine.dxo = 0; mine.S = 0; mine.dirs = 0; mine.n_strips = 0;
-    mine.lo_raw0 = mine.idx0 = mine.stride_major = mine.stride_minor = 0;
+    int my_flags = 0;  // bit0 start outside the map, bit1 end outside
+    int c0 = 0, n0 = 0, dxo = 0, dyo = 0, dirs = 0, n_strips = 0;
+    uint4 r0 = make_uint4(0, 0, 0, 0);
+    uint32_t S = 0;
+    int n0m = 0;
     if (eidx < n) {
       const double2 a = INDEXED ? from[from_idx[eidx]] : from[eidx];
       const double2 b = INDEXED ? to[to_idx[eidx]] : to[eidx];
-      const EdgeSetup s = make_setup(m, a.x, a.y, b.x, b.y);
-      const int ui = (s.steps & 3) - 1, uj = ((s.steps >> 2) & 3) - 1, vi = ((s.steps >> 4) & 3) - 1, vj = ((s.steps >> 6) & 3) - 1;
-      mine.c0 = ui ? s.ai : s.aj; mine.n0 = ui ? s.aj : s.ai;
-      mine.dxo = s.dxo; my_dyo = s.dyo;
-      mine.dirs = (ui ? 1 : 0) | ((ui + uj) < 0 ? 2 : 0) | ((vi + vj) < 0 ? 4 : 0);
-      my_flags = s.flags;
+      uint32_t ai, aj, bi, bj;
+      to_pixel(m, a.x, a.y, ai, aj);
+      to_pixel(m, b.x, b.y, bi, bj);
+      my_flags = ((ai >= (uint32_t)m.H || aj >= (uint32_t)m.W) ? 1 : 0) | ((bi >= (uint32_t)m.H || bj >= (uint32_t)m.W) ? 2 : 0);
+      // line_drawing's octant (Octant::new) reduces to: major axis = the longer delta (ties give the same pixels),
+      // unit steps = the signs of the two deltas
+      const int di = (int)bi - (int)ai, dj = (int)bj - (int)aj;
+      const int adi = abs(di), adj = abs(dj);
+      const bool major_i = adi >= adj;
+      dxo = major_i ? adi : adj; dyo = major_i ? adj : adi;
+      const int d_major = major_i ? di : dj, d_minor = major_i ? dj : di;
+      c0 = major_i ? (int)ai : (int)aj; n0 = major_i ? (int)aj : (int)ai;
+      dirs = (major_i ? 1 : 0) | (d_major < 0 ? 2 : 0) | (d_minor < 0 ? 4 : 0);
       if (!my_flags) {
-        if (s.dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
-          if (s.dyo == s.dxo) mine.S = 0xFFFFFFFFu;
+        if (dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
+          if (dyo == dxo) S = 0xFFFFFFFFu;
           else {
-            const uint32_t d = (uint32_t)s.dxo, num = (uint32_t)s.dyo << 16;
+            const uint32_t d = (uint32_t)dxo, num = (uint32_t)dyo << 16;
             const uint32_t q1 = num / d, r1 = num - q1 * d;
-            mine.S = (q1 << 16) + ((r1 << 16) / d);
+            S = (q1 << 16) + ((r1 << 16) / d);
           }
         }
-        const int sgn = (mine.dirs & 2) ? -1 : 1;
-        const int b0 = mine.c0 >> E3_LOG_BS, b1 = (mine.c0 + sgn * mine.dxo) >> E3_LOG_BS;
-        mine.n_strips = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;
-        mine.lo_raw0 = sgn * ((b0 << E3_LOG_BS) - mine.c0) - ((mine.dirs & 2) ? E3_BS - 1 : 0);
-        mine.stride_major = sgn * ((mine.dirs & 1) ? cw : 1);
-        mine.stride_minor = (mine.dirs & 1) ? 1 : cw;
-        mine.idx0 = b0 * ((mine.dirs & 1) ? cw : 1);
+        const int sgn = (dirs & 2) ? -1 : 1;
+        const int b0 = c0 >> E3_LOG_BS, b1 = (c0 + sgn * dxo) >> E3_LOG_BS;
+        n_strips = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;
+        const int blocks_minor = major_i ? cw : ch;            // blocks along the minor axis
+        int stride_minor = major_i ? 1 : cw;
+        int idx0 = b0 * (major_i ? cw : 1);
+        n0m = n0;
+        if (dirs & 4) { n0m = blocks_minor * E3_BS - 1 - n0; idx0 += (blocks_minor - 1) * stride_minor; stride_minor = -stride_minor; }
+        r0.x = (uint32_t)(sgn * ((b0 << E3_LOG_BS) - c0) - ((dirs & 2) ? E3_BS - 1 : 0));
+        r0.y = (uint32_t)idx0;
+        r0.z = (uint32_t)(sgn * (major_i ? cw : 1));
+        r0.w = (uint32_t)stride_minor;
       }
     }
-    wm.rec[lane] = mine;
+    wm.rec[0][lane] = r0;
+    wm.rec[1][lane] = make_uint4((uint32_t)n0m, (uint32_t)dxo, S, (uint32_t)n_strips);
+    wm.rec[2][lane] = make_uint4((uint32_t)c0, (uint32_t)n0, (uint32_t)dirs, 0u);
     wm.obst[lane] = 0; wm.zmin[lane] = 255; wm.zmax[lane] = 0;
     // items = groups of E3_G strips; every lane owns at least one (possibly empty) item so that the inclusive prefix
     // sums are strictly increasing and the owner of a flattened position can be ranked with a bitmask
-    int incl = max(1, (mine.n_strips + E3_G - 1) / E3_G);
+    int incl = max(1, (n_strips + E3_G - 1) / E3_G);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -246,13 +284,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const bool may_overflow = total * E3_G > min(E3_QB, E3_QG);     // warp-uniform
     __syncwarp();
-    if (!plane_ready) {
-      uint32_t done = 0;
-      while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
-      plane_ready = true;
-    }
+    if (!plane_ready) { mbar_wait0(s_mbar); plane_ready = true; }
 
     // ---- pass 1: item w = w0 + lane of the flattened sequence; classes of the <= 2 blocks of each strip
     for (int w0 = 0; w0 < total; w0 += 32) {
@@ -263,56 +295,55 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       const int e = min(31, e_base + __popc(marks & lt_mask));
       const int p_prev = __shfl_sync(0xffffffffu, incl, (e + 31) & 31);
       const int w = w0 + lane;
-      uint32_t look = 0;      // per strip g: bit g = queue for the bitmap pass, bit 8+g = block a, bit 16+g = block b,
-                              // bit 24+g = queue for the byte pass
-      int ts0 = 0;
+      // per strip g a one-hot nibble pair OR-ed: bit 4g+1 mixed, 4g+2 blocked, 4g+3 special (bit 4g: free)
+      uint32_t cls = 0;
+      const int ts0 = (w - (e ? p_prev : 0)) * E3_G;
       if (w < total) {
-        const Rec3& r = wm.rec[e];
-        const int n_strips = r.n_strips, dxo = r.dxo, n0 = r.n0, stride_minor = r.stride_minor, stride_major = r.stride_major;
-        const uint32_t S = r.S;
-        const int sn = (r.dirs & 4) ? -1 : 1;
-        ts0 = (w - (e ? p_prev : 0)) * E3_G;
-        int lo_raw = r.lo_raw0 + ts0 * E3_BS;
-        int idx_m = r.idx0 + ts0 * stride_major;
-        uint32_t any_blocked = 0;
+        const uint4 q0 = wm.rec[0][e], q1 = wm.rec[1][e];
+        const int sm_ = (int)q0.z, sn_ = (int)q0.w, e_dxo = (int)q1.y, e_n0m = (int)q1.x;
+        const uint32_t e_S = q1.z;
+        const int left = (int)q1.w - ts0;        // strips of this edge from ts0 on
+        int lo_raw = (int)q0.x + ts0 * E3_BS;
+        int idx_m = (int)q0.y + ts0 * sm_;
 #pragma unroll
         for (int g = 0; g < E3_G; ++g) {
-          if (ts0 + g < n_strips) {
-            const int k_lo = max(0, lo_raw), k_hi = min(dxo, lo_raw + E3_BS - 1);
-            const int bn_a = (n0 + sn * (int)minor_of((uint32_t)k_lo, S)) >> E3_LOG_BS;
-            const int bn_b = (n0 + sn * (int)minor_of((uint32_t)k_hi, S)) >> E3_LOG_BS;
-            const int ia = idx_m + bn_a * stride_minor, ib = idx_m + bn_b * stride_minor;
-            const uint32_t ca = (s_plane[ia >> 4] >> ((ia & 15) << 1)) & 3u;
-            const uint32_t cb = (s_plane[ib >> 4] >> ((ib & 15) << 1)) & 3u;
-            const bool special = ca == K_SPECIAL || cb == K_SPECIAL;
-            any_blocked |= (ca == K_BLOCKED || cb == K_BLOCKED) ? 1u : 0u;
-            const bool la = ca == K_MIXED, lb = cb == K_MIXED && ib != ia;
-            if (special) look |= 1u << (24 + g);
-            else if (la || lb) look |= (1u << g) | (la ? (1u << (8 + g)) : 0u) | (lb ? (1u << (16 + g)) : 0u);
+          const int k_lo = max(0, lo_raw), k_hi = min(e_dxo, lo_raw + E3_BS - 1);
+          const int ia = idx_m + (minor_m((uint32_t)k_lo, e_S, e_n0m) >> E3_LOG_BS) * sn_;
+          const int ib = idx_m + (minor_m((uint32_t)k_hi, e_S, e_n0m) >> E3_LOG_BS) * sn_;
+          if (g < left) {
+            const uint32_t ca = ((uint32_t)s_plane[ia >> 2] >> ((ia & 3) << 1)) & 3u;
+            const uint32_t cb = ((uint32_t)s_plane[ib >> 2] >> ((ib & 3) << 1)) & 3u;
+            cls |= ((1u << ca) | (1u << cb)) << (4 * g);
           }
-          lo_raw += E3_BS; idx_m += stride_major;
+          lo_raw += E3_BS; idx_m += sm_;
         }
-        if (any_blocked) { wm.obst[e] = 1; look &= 0xff000000u; }   // the bitmaps cannot change the outcome any more
       }
-      // enqueue: exclusive scan over the lanes of (bitmap entries | byte entries << 16)
-      if (__any_sync(0xffffffffu, look != 0)) {
-        const int cnt = __popc(look & 0xffu) | (__popc(look >> 24) << 16);
+      const uint32_t blocked = cls & 0x4444u, special = (cls >> 3) & 0x1111u;
+      if (blocked) wm.obst[e] = 1;                                 // the bitmaps cannot change the outcome any more
+      const uint32_t want = blocked ? 0u : ((cls >> 1) & 0x1111u & ~special);
+      // enqueue the strips that need the bitmaps: exclusive scan of the per-lane counts
+      if (__any_sync(0xffffffffu, want != 0)) {
+        const int cnt = __popc(want);
         int sc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int t = __shfl_up_sync(0xffffffffu, sc, o);
           if (lane >= o) sc += t;
         }
-        const int tot = __shfl_sync(0xffffffffu, sc, 31);
-        sc -= cnt;
-        int pb = qb_n + (sc & 0xffff), pg = qg_n + (sc >> 16);
+        int pb = qb_n + sc - cnt;
+        qb_n += __shfl_sync(0xffffffffu, sc, 31);
+        const uint32_t ent0 = (uint32_t)e | ((uint32_t)ts0 << 5);
+#pragma unroll
+        for (int g = 0; g < E3_G; ++g)
+          if (want & (1u << (4 * g))) wm.qb[pb++] = ent0 + ((uint32_t)g << 5);
+      }
+      if (__any_sync(0xffffffffu, special != 0)) {                 // rare: strips through gray pixels
 #pragma unroll
         for (int g = 0; g < E3_G; ++g) {
-          if (look & (1u << g))
-            wm.qb[pb++] = (uint32_t)e | ((uint32_t)(ts0 + g) << 5) | (((look >> (8 + g)) & 1u) << 30) | (((look >> (16 + g)) & 1u) << 31);
-          if (look & (1u << (24 + g))) wm.qg[pg++] = (uint32_t)e | ((uint32_t)(ts0 + g) << 5);
+          const unsigned bal = __ballot_sync(0xffffffffu, (special >> (4 * g)) & 1u);
+          if ((special >> (4 * g)) & 1u) wm.qg[qg_n + __popc(bal & lt_mask)] = (uint32_t)e | ((uint32_t)(ts0 + g) << 5);
+          qg_n += __popc(bal);
         }
-        qb_n += tot & 0xffff; qg_n += tot >> 16;
       }
       __syncwarp();
     }
@@ -327,21 +358,21 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       if (my_flags & 1) r = PORRT_PANIC_OOB;             // the first pixel read already panics
       else if (my_flags & 2) slow = true;                // end pixel outside: order of events matters
       else {
-        const bool blocked = wm.obst[lane] != 0;
-        if (KIND == PORRT_DOMAIN_SHELF) r = blocked ? R_BLOCKED : R_FREE;   // Low and High obstacle both invalidate the edge
+        const bool is_blocked = wm.obst[lane] != 0;
+        if (KIND == PORRT_DOMAIN_SHELF) r = is_blocked ? R_BLOCKED : R_FREE;   // Low and High obstacle both invalidate the edge
         else {
           const uint32_t zmin = wm.zmin[lane], zmax = wm.zmax[lane];
-          if (zmax != 0 && (zmin != zmax || zmax == 254)) slow = true;      // order of events decides: re-walk
-          else r = blocked ? R_BLOCKED : (zmax ? (int32_t)zmin - 1 : R_FREE);
+          if (zmax != 0 && (zmin != zmax || zmax == 254)) slow = true;         // order of events decides: re-walk
+          else r = is_blocked ? R_BLOCKED : (zmax ? (int32_t)zmin - 1 : R_FREE);
         }
       }
       if (slow) {
         Walker wk;
-        const int sm = (mine.dirs & 2) ? -1 : 1, sn = (mine.dirs & 4) ? -1 : 1;
-        wk.dxo = mine.dxo; wk.dyo = my_dyo;
-        wk.M = mine.dxo > 1 ? (0xFFFFFFFFFFFFFFFFull / (uint64_t)mine.dxo) + 1ull : 0ull;
-        if (mine.dirs & 1) { wk.ai = mine.c0; wk.aj = mine.n0; wk.ui = sm; wk.uj = 0; wk.vi = 0; wk.vj = sn; }
-        else { wk.ai = mine.n0; wk.aj = mine.c0; wk.ui = 0; wk.uj = sm; wk.vi = sn; wk.vj = 0; }
+        const int sm = (dirs & 2) ? -1 : 1, sn = (dirs & 4) ? -1 : 1;
+        wk.dxo = dxo; wk.dyo = dyo;
+        wk.M = dxo > 1 ? (0xFFFFFFFFFFFFFFFFull / (uint64_t)dxo) + 1ull : 0ull;
+        if (dirs & 1) { wk.ai = c0; wk.aj = n0; wk.ui = sm; wk.uj = 0; wk.vi = 0; wk.vj = sn; }
+        else { wk.ai = n0; wk.aj = c0; wk.ui = 0; wk.uj = sm; wk.vi = sn; wk.vj = 0; }
         r = walk_sequential<KIND>(m, wk);
         if (KIND == PORRT_DOMAIN_SHELF && r == R_LOW) r = R_BLOCKED;
       }
@@ -356,12 +387,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     }
     __syncwarp();
   }
-  if (!plane_ready) {  // a warp without work must not leave while the copy is in flight
-    uint32_t done = 0;
-    while (!done)
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(done) : "r"(smem_u32(s_mbar)) : "memory");
-  }
+  if (!plane_ready) mbar_wait0(s_mbar);  // a warp without work must not leave while the copy is in flight
 }
 
 // ------------------------------------------------------------------------------------------------ map build
@@ -433,6 +459,7 @@ int32_t edge3_build(porrt_ctx* ctx, cudaStream_t st) {
   m.plane = ctx->d_plane.as<uint32_t>();
   m.bits = ctx->d_bits.as<uint32_t>();
   m.plane_cw = cw;
+  m.plane_ch = ch;
   m.plane_bytes = (int32_t)plane_bytes;
   m.bits_var_words = (int32_t)(n_blocks * 8);
   return PORRT_OK;
