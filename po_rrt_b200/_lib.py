@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libporrt_b200.so")
+LIB_PATH = os.environ.get("PORRT_B200_LIB") or os.path.join(_HERE, "libporrt_b200.so")  # override: A/B builds of the kernels
 
 vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 pp = C.POINTER

@@ -55,6 +55,7 @@ struct MapDev {
   const uint32_t* bits;
   int32_t plane_cw, plane_ch;  // blocks per block row / block rows
   int32_t plane_bytes;      // padded to a multiple of 16
+  int32_t plane_guard;      // free blocks in front of (and behind) block 0 in the plane
   int32_t bits_var_words;   // 32-bit words per orientation (= blocks * 8)
   int32_t H, W;         // logical size
   int32_t tiles_x;      // 128-byte tiles (16 x 8 px) per tile row

@@ -25,8 +25,10 @@
 
 #define E3_LOG_BS 4
 #define E3_BS 16
-#define E3_G 4              // consecutive strips of one edge per lane and round
-#define E3_QB 384           // bitmap-queue entries per warp
+#ifndef E3_G
+#define E3_G 8              // consecutive strips of one edge per lane and round (<= 8: one class nibble each)
+#endif
+#define E3_QB 512           // bitmap-queue entries per warp (a round adds at most 32 * E3_G)
 #define E3_QG 256           // byte-queue entries per warp
 #define E3_BIAS 65536ull
 #define E3_MAX_WARPS 32
@@ -154,7 +156,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
           const bool neg_major = (dirs & 2) != 0;
           const int bn_a = minor_m((uint32_t)k_lo, S, n0m) >> E3_LOG_BS;
           const int bn_b = minor_m((uint32_t)k_hi, S, n0m) >> E3_LOG_BS;
-          const int blk_a = (int)r0.y + ts * (int)r0.z + bn_a * (int)r0.w;
+          const int blk_a = (int)r0.y - m.plane_guard + ts * (int)r0.z + bn_a * (int)r0.w;
           const uint32_t* tiles = m.bits + (size_t)(((dirs & 1) << 1) | ((dirs >> 2) & 1)) * (size_t)m.bits_var_words;
           uint32_t A[8], B[8];
 #pragma unroll
@@ -224,8 +226,10 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
 
   for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
     const int64_t eidx = base + lane;
+    if (!plane_ready) { mbar_wait0(s_mbar); plane_ready = true; }
     // ---- per-lane setup of one edge
     int my_flags = 0;  // bit0 start outside the map, bit1 end outside
+    uint32_t pre_blocked = 0;
     int c0 = 0, n0 = 0, dxo = 0, dyo = 0, dirs = 0, n_strips = 0;
     uint4 r0 = make_uint4(0, 0, 0, 0);
     uint32_t S = 0;
@@ -246,7 +250,11 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       const int d_major = major_i ? di : dj, d_minor = major_i ? dj : di;
       c0 = major_i ? (int)ai : (int)aj; n0 = major_i ? (int)aj : (int)ai;
       dirs = (major_i ? 1 : 0) | (d_major < 0 ? 2 : 0) | (d_minor < 0 ? 4 : 0);
-      if (!my_flags) {
+      if (!my_flags) {  // the start pixel's block blocks entirely: Obstacle at k = 0, nothing to walk
+        const int sb = m.plane_guard + ((int)ai >> E3_LOG_BS) * cw + ((int)aj >> E3_LOG_BS);
+        pre_blocked = ((((uint32_t)s_plane[sb >> 2] >> ((sb & 3) << 1)) & 3u) == K_BLOCKED) ? 1u : 0u;
+      }
+      if (!my_flags && !pre_blocked) {
         if (dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
           if (dyo == dxo) S = 0xFFFFFFFFu;
           else {
@@ -260,7 +268,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         n_strips = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;
         const int blocks_minor = major_i ? cw : ch;            // blocks along the minor axis
         int stride_minor = major_i ? 1 : cw;
-        int idx0 = b0 * (major_i ? cw : 1);
+        int idx0 = m.plane_guard + b0 * (major_i ? cw : 1);
         n0m = n0;
         if (dirs & 4) { n0m = blocks_minor * E3_BS - 1 - n0; idx0 += (blocks_minor - 1) * stride_minor; stride_minor = -stride_minor; }
         r0.x = (uint32_t)(sgn * ((b0 << E3_LOG_BS) - c0) - ((dirs & 2) ? E3_BS - 1 : 0));
@@ -272,7 +280,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     wm.rec[0][lane] = r0;
     wm.rec[1][lane] = make_uint4((uint32_t)n0m, (uint32_t)dxo, S, (uint32_t)n_strips);
     wm.rec[2][lane] = make_uint4((uint32_t)c0, (uint32_t)n0, (uint32_t)dirs, 0u);
-    wm.obst[lane] = 0; wm.zmin[lane] = 255; wm.zmax[lane] = 0;
+    wm.obst[lane] = pre_blocked; wm.zmin[lane] = 255; wm.zmax[lane] = 0;
     // items = groups of E3_G strips; every lane owns at least one (possibly empty) item so that the inclusive prefix
     // sums are strictly increasing and the owner of a flattened position can be ranked with a bitmask
     int incl = max(1, (n_strips + E3_G - 1) / E3_G);
@@ -284,7 +292,6 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const bool may_overflow = total * E3_G > min(E3_QB, E3_QG);     // warp-uniform
     __syncwarp();
-    if (!plane_ready) { mbar_wait0(s_mbar); plane_ready = true; }
 
     // ---- pass 1: item w = w0 + lane of the flattened sequence; classes of the <= 2 blocks of each strip
     for (int w0 = 0; w0 < total; w0 += 32) {
@@ -295,32 +302,33 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       const int e = min(31, e_base + __popc(marks & lt_mask));
       const int p_prev = __shfl_sync(0xffffffffu, incl, (e + 31) & 31);
       const int w = w0 + lane;
-      // per strip g a one-hot nibble pair OR-ed: bit 4g+1 mixed, 4g+2 blocked, 4g+3 special (bit 4g: free)
+      // per strip g the one-hot classes of its blocks OR-ed: bit 4g+1 mixed, 4g+2 blocked, 4g+3 special (4g: free).
+      // Branch-free: strips past the end of the edge read the guard zone / neighbouring blocks and are masked out.
       uint32_t cls = 0;
-      const int ts0 = (w - (e ? p_prev : 0)) * E3_G;
-      if (w < total) {
+      const bool has_item = w < total;
+      const int ts0 = has_item ? (w - (e ? p_prev : 0)) * E3_G : 0;
+      {
         const uint4 q0 = wm.rec[0][e], q1 = wm.rec[1][e];
         const int sm_ = (int)q0.z, sn_ = (int)q0.w, e_dxo = (int)q1.y, e_n0m = (int)q1.x;
         const uint32_t e_S = q1.z;
-        const int left = (int)q1.w - ts0;        // strips of this edge from ts0 on
+        const int left = has_item ? (int)q1.w - ts0 : 0;        // strips of this edge from ts0 on
         int lo_raw = (int)q0.x + ts0 * E3_BS;
         int idx_m = (int)q0.y + ts0 * sm_;
 #pragma unroll
         for (int g = 0; g < E3_G; ++g) {
-          const int k_lo = max(0, lo_raw), k_hi = min(e_dxo, lo_raw + E3_BS - 1);
+          const int k_lo = min(max(0, lo_raw), e_dxo), k_hi = min(e_dxo, lo_raw + E3_BS - 1);
           const int ia = idx_m + (minor_m((uint32_t)k_lo, e_S, e_n0m) >> E3_LOG_BS) * sn_;
           const int ib = idx_m + (minor_m((uint32_t)k_hi, e_S, e_n0m) >> E3_LOG_BS) * sn_;
-          if (g < left) {
-            const uint32_t ca = ((uint32_t)s_plane[ia >> 2] >> ((ia & 3) << 1)) & 3u;
-            const uint32_t cb = ((uint32_t)s_plane[ib >> 2] >> ((ib & 3) << 1)) & 3u;
-            cls |= ((1u << ca) | (1u << cb)) << (4 * g);
-          }
+          const uint32_t ca = ((uint32_t)s_plane[ia >> 2] >> ((ia & 3) << 1)) & 3u;
+          const uint32_t cb = ((uint32_t)s_plane[ib >> 2] >> ((ib & 3) << 1)) & 3u;
+          cls |= ((1u << ca) | (1u << cb)) << (4 * g);
           lo_raw += E3_BS; idx_m += sm_;
         }
+        cls &= left >= E3_G ? 0xffffffffu : ((1u << (4 * max(left, 0))) - 1u);
       }
-      const uint32_t blocked = cls & 0x4444u, special = (cls >> 3) & 0x1111u;
+      const uint32_t blocked = cls & 0x44444444u, special = (cls >> 3) & 0x11111111u;
       if (blocked) wm.obst[e] = 1;                                 // the bitmaps cannot change the outcome any more
-      const uint32_t want = blocked ? 0u : ((cls >> 1) & 0x1111u & ~special);
+      const uint32_t want = blocked ? 0u : ((cls >> 1) & 0x11111111u & ~special);
       // enqueue the strips that need the bitmaps: exclusive scan of the per-lane counts
       if (__any_sync(0xffffffffu, want != 0)) {
         const int cnt = __popc(want);
@@ -397,7 +405,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
 //   orientation 2: major i, minor j ascending  : vec[t = row]    bit c        3: the same with bit 15 - c
 template <int KIND>
 __global__ void __launch_bounds__(256) edge3_build_kernel(const uint8_t* __restrict__ grid, int H, int W, int tiles_x, int cw, int ch,
-                                                          uint32_t* __restrict__ plane, uint16_t* __restrict__ bits, size_t var_halfwords) {
+                                                          uint32_t* __restrict__ plane, int guard, uint16_t* __restrict__ bits, size_t var_halfwords) {
   const int lane = threadIdx.x & 31, half = lane >> 4, r = lane & 15;
   const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_blocks = (int64_t)cw * ch;
@@ -437,7 +445,8 @@ __global__ void __launch_bounds__(256) edge3_build_kernel(const uint8_t* __restr
     if (r == 0) {
       const uint32_t t_in = cnt & 1023u, t_block = (cnt >> 10) & 1023u, t_special = cnt >> 20;
       const uint32_t cls = t_special ? K_SPECIAL : (t_block == 0 ? K_FREE : (t_block == t_in ? K_BLOCKED : K_MIXED));
-      if (cls) atomicOr(&plane[blk >> 4], cls << ((blk & 15) << 1));
+      const int64_t pb = blk + guard;
+      if (cls) atomicOr(&plane[pb >> 4], cls << ((pb & 15) << 1));
     }
   }
 }
@@ -446,20 +455,24 @@ int32_t edge3_build(porrt_ctx* ctx, cudaStream_t st) {
   MapDev& m = ctx->map;
   const int cw = (m.W + E3_BS - 1) / E3_BS, ch = (m.H + E3_BS - 1) / E3_BS;
   const size_t n_blocks = (size_t)cw * ch;
-  const size_t plane_bytes = ((((n_blocks + 15) / 16) * 4 + 15) / 16) * 16;
+  // guard zones of >= 4 block rows (class 0 = free) on both sides: the branch-free pass 1 reads up to E3_G - 1 strips
+  // past the end of an edge, i.e. at most E3_G block rows / columns outside the map
+  const int guard = (int)(((size_t)(E3_G + 1) * cw + 63) / 64 * 64);
+  const size_t plane_bytes = ((((n_blocks + 2 * (size_t)guard + 15) / 16) * 4 + 15) / 16) * 16;
   CUDA_TRY(ctx, ctx->d_plane.ensure(plane_bytes));
   CUDA_TRY(ctx, ctx->d_bits.ensure(n_blocks * 32 * 4));
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plane.p, 0, plane_bytes, st));
   const int grid = div_up((int64_t)((n_blocks + 1) / 2) * 32, 256);
   if (m.kind == PORRT_DOMAIN_SHELF)
-    edge3_build_kernel<PORRT_DOMAIN_SHELF><<<grid, 256, 0, st>>>(m.grid, m.H, m.W, m.tiles_x, cw, ch, ctx->d_plane.as<uint32_t>(), ctx->d_bits.as<uint16_t>(), n_blocks * 16);
+    edge3_build_kernel<PORRT_DOMAIN_SHELF><<<grid, 256, 0, st>>>(m.grid, m.H, m.W, m.tiles_x, cw, ch, ctx->d_plane.as<uint32_t>(), guard, ctx->d_bits.as<uint16_t>(), n_blocks * 16);
   else
-    edge3_build_kernel<PORRT_DOMAIN_DOOR><<<grid, 256, 0, st>>>(m.grid, m.H, m.W, m.tiles_x, cw, ch, ctx->d_plane.as<uint32_t>(), ctx->d_bits.as<uint16_t>(), n_blocks * 16);
+    edge3_build_kernel<PORRT_DOMAIN_DOOR><<<grid, 256, 0, st>>>(m.grid, m.H, m.W, m.tiles_x, cw, ch, ctx->d_plane.as<uint32_t>(), guard, ctx->d_bits.as<uint16_t>(), n_blocks * 16);
   LAUNCH_CHECK(ctx);
   m.plane = ctx->d_plane.as<uint32_t>();
   m.bits = ctx->d_bits.as<uint32_t>();
   m.plane_cw = cw;
   m.plane_ch = ch;
+  m.plane_guard = guard;
   m.plane_bytes = (int32_t)plane_bytes;
   m.bits_var_words = (int32_t)(n_blocks * 8);
   return PORRT_OK;
