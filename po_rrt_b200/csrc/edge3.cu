@@ -23,6 +23,15 @@
 // matter the edge is re-walked sequentially (walk_sequential), which is what makes the panic codes bit-exact.
 #include "map_dev.cuh"
 
+#ifndef E3_SHR_FMA
+#define E3_SHR_FMA 0       // measured: moving the shifts to IMAD.HI loses 2-4 % (the FMA-heavy pipe is as narrow as the ALU pipe)
+#endif
+#ifndef E3_ADDR_MODE
+#define E3_ADDR_MODE 0      // bit0 / bit1: first / second class lookup of a strip uses word loads + rotate
+#endif
+#ifndef E3_FINE_MODE
+#define E3_FINE_MODE 0       // 1: per-pixel IMAD.HI instead of the 64-bit running sum (slower, same reason)
+#endif
 #define E3_LOG_BS 4
 #define E3_BS 16
 #ifndef E3_G
@@ -72,6 +81,22 @@ __device__ __forceinline__ int32_t minor_m(uint32_t k, uint32_t S, int32_t n0m) 
   return (int32_t)(((uint64_t)k * (uint64_t)S + (((uint64_t)(uint32_t)n0m << 32) | E3_BIAS)) >> 32);
 }
 
+
+// x >> s for a compile-time s, on the ALU pipe (SHF) or the FMA pipe (IMAD.HI): the kernel is bound by integer issue on
+// these two pipes, so the split between them is tuned (E3_* switches, measured on B200)
+template <bool FMA>
+__device__ __forceinline__ uint32_t shr_c(uint32_t x, int s) { return FMA ? __umulhi(x, 1u << (32 - s)) : x >> s; }
+
+// 2-bit class of block idx from the plane in shared memory (16 per 32-bit word)
+template <bool WORD>
+__device__ __forceinline__ uint32_t plane_class(const unsigned char* plane, uint32_t idx) {
+  if (WORD) {
+    const uint32_t w = ((const uint32_t*)plane)[__umulhi(idx, 1u << 28)];
+    return __funnelshift_r(w, w, idx * 2u) & 3u;           // rotate by 2 * idx mod 32
+  }
+  return ((uint32_t)plane[idx >> 2] >> ((idx * 2u) & 6u)) & 3u;
+}
+
 __device__ __forceinline__ void ld256(uint32_t (&v)[8], const uint32_t* p) {
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -97,7 +122,6 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
                         const uint64_t* __restrict__ validities, const int32_t* __restrict__ from_idx,
                         const int32_t* __restrict__ to_idx) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint8_t* s_plane = (const uint8_t*)smem;
   uint64_t* s_mbar = (uint64_t*)(smem + m.plane_bytes);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpMem& wm = *(WarpMem*)(smem + m.plane_bytes + 16 + (size_t)wib * sizeof(WarpMem));
@@ -166,18 +190,28 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
           // u_t = minor offset (walking direction) of the pixel at major position t, counted from block a's first
           // row: 0..15 in block a, 16..31 in block b.  hi32(Y_t) = u_t - t, Y linear in t.
           const int k0 = neg_major ? lo_raw + E3_BS - 1 : lo_raw;          // k at t = 0
-          uint64_t Y = ((uint64_t)(uint32_t)(n0m - (bn_a << E3_LOG_BS)) << 32) + (uint64_t)((int64_t)k0 * (int64_t)(uint64_t)S) + E3_BIAS;
-          const uint64_t D = (neg_major ? (uint64_t)0 - (uint64_t)S : (uint64_t)S) - (1ull << 32);
+          const int c_hi = n0m - (bn_a << E3_LOG_BS), smaj = neg_major ? -1 : 1;
           const int t_lo = neg_major ? lo_raw + E3_BS - 1 - k_hi : k_lo - lo_raw;
           const int t_hi = neg_major ? lo_raw + E3_BS - 1 - k_lo : k_hi - lo_raw;
           const uint32_t Vm = ((2u << t_hi) - 1u) & ~((1u << t_lo) - 1u);  // positions that are pixels of this edge
           uint32_t acc = 0;
+#if !E3_FINE_MODE
+          uint64_t Y = ((uint64_t)(uint32_t)c_hi << 32) + (uint64_t)((int64_t)k0 * (int64_t)(uint64_t)S) + E3_BIAS;
+          const uint64_t D = (neg_major ? (uint64_t)0 - (uint64_t)S : (uint64_t)S) - (1ull << 32);
+#endif
 #pragma unroll
           for (int t = 0; t < E3_BS; ++t) {
             const uint32_t V = (t & 1) ? __byte_perm(A[t >> 1], B[t >> 1], 0x7632) : __byte_perm(A[t >> 1], B[t >> 1], 0x5410);
+#if E3_FINE_MODE
+            int kt;   // k at major position t; IMAD keeps the add off the ALU pipe
+            asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(kt) : "r"(smaj), "r"(t), "r"(k0));
+            const int u = minor_m((uint32_t)kt, S, c_hi);               // garbage where Vm is 0
+            if (Vm & (1u << t)) acc |= (1u << u) & V;
+#else
             const uint32_t x = Vm & (1u << t);
-            acc |= __funnelshift_l(x, x, (uint32_t)(Y >> 32)) & V;     // bit t rotated to bit u_t
+            acc |= __funnelshift_l(x, x, (uint32_t)(Y >> 32)) & V;     // bit t rotated to bit u_t; hi32(Y_t) = u_t - t
             Y += D;
+#endif
           }
           if (acc) wm.obst[e] = 1;
         }
@@ -252,7 +286,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       dirs = (major_i ? 1 : 0) | (d_major < 0 ? 2 : 0) | (d_minor < 0 ? 4 : 0);
       if (!my_flags) {  // the start pixel's block blocks entirely: Obstacle at k = 0, nothing to walk
         const int sb = m.plane_guard + ((int)ai >> E3_LOG_BS) * cw + ((int)aj >> E3_LOG_BS);
-        pre_blocked = ((((uint32_t)s_plane[sb >> 2] >> ((sb & 3) << 1)) & 3u) == K_BLOCKED) ? 1u : 0u;
+        pre_blocked = plane_class<false>(smem, (uint32_t)sb) == K_BLOCKED ? 1u : 0u;
       }
       if (!my_flags && !pre_blocked) {
         if (dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
@@ -316,12 +350,15 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         int idx_m = (int)q0.y + ts0 * sm_;
 #pragma unroll
         for (int g = 0; g < E3_G; ++g) {
-          const int k_lo = min(max(0, lo_raw), e_dxo), k_hi = min(e_dxo, lo_raw + E3_BS - 1);
-          const int ia = idx_m + (minor_m((uint32_t)k_lo, e_S, e_n0m) >> E3_LOG_BS) * sn_;
-          const int ib = idx_m + (minor_m((uint32_t)k_hi, e_S, e_n0m) >> E3_LOG_BS) * sn_;
-          const uint32_t ca = ((uint32_t)s_plane[ia >> 2] >> ((ia & 3) << 1)) & 3u;
-          const uint32_t cb = ((uint32_t)s_plane[ib >> 2] >> ((ib & 3) << 1)) & 3u;
-          cls |= ((1u << ca) | (1u << cb)) << (4 * g);
+          // only an edge's first strip starts before k = 0; k_lo past the end (masked strips) stays inside the guards.
+          // Shifts by constants are written as multiply-high so that they issue on the FMA pipe: the ALU pipe is the
+          // kernel's bound (ncu: math-pipe throttle).
+          const int k_lo = g == 0 ? max(0, lo_raw) : lo_raw, k_hi = min(e_dxo, lo_raw + E3_BS - 1);
+          const uint32_t na = (uint32_t)minor_m((uint32_t)k_lo, e_S, e_n0m), nb = (uint32_t)minor_m((uint32_t)k_hi, e_S, e_n0m);
+          const uint32_t ia = (uint32_t)idx_m + shr_c<E3_SHR_FMA != 0>(na, E3_LOG_BS) * (uint32_t)sn_;
+          const uint32_t ib = (uint32_t)idx_m + shr_c<E3_SHR_FMA != 0>(nb, E3_LOG_BS) * (uint32_t)sn_;
+          const uint32_t ca = plane_class<(E3_ADDR_MODE & 1) != 0>(smem, ia), cb = plane_class<(E3_ADDR_MODE & 2) != 0>(smem, ib);
+          cls += ((1u << ca) | (1u << cb)) * (1u << (4 * g));
           lo_raw += E3_BS; idx_m += sm_;
         }
         cls &= left >= E3_G ? 0xffffffffu : ((1u << (4 * max(left, 0))) - 1u);
