@@ -89,8 +89,9 @@ struct porrt_ctx {
   std::vector<uint64_t> validities;     // [n_validities * mask_words]
   std::vector<double> zone_pos;         // [2 * n_zones]
   std::vector<uint64_t> zone_world_masks;  // DOOR: zones_to_worlds [n_zones * mask_words]
-  DevBuf d_grid, d_coarse[3], d_validities, d_zone_pos, d_plane, d_bits;
-  int edge_variant = 0;  // 0: edge3.cu (class plane in shared memory + block bitmaps); 1: byte-grid warp walk;
+  DevBuf d_grid, d_coarse[3], d_validities, d_zone_pos, d_plane, d_bits, d_ticket;
+  int edge_variant = 0;  // 0: edge4.cu (lane per edge over length-sorted groups; class plane in shared memory + block bitmaps);
+                         // 8: edge3.cu (same data, flattened strips); 1: byte-grid warp walk;
                          // 2..7: class bytes + flattened strips (map.cu v2) with various block / group sizes
   // host copies of the raw images are NOT kept: the product never walks pixels on the CPU.
 
@@ -174,6 +175,10 @@ int32_t map_edge_validity_indexed_dev(porrt_ctx* ctx, const double* xy_dev, cons
 int32_t edge3_build(porrt_ctx* ctx, cudaStream_t st);
 bool edge3_usable(const porrt_ctx* ctx);
 int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
+                     uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st);
+// edge4.cu
+bool edge4_usable(const porrt_ctx* ctx);
+int32_t edge4_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
                      uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st);
 // nn.cu helpers used by graph.cu
 int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi);

@@ -1,0 +1,64 @@
+// edge_common.cuh -- constants and device helpers shared by the edge-validity kernels edge3.cu / edge4.cu
+#pragma once
+#include "map_dev.cuh"
+
+#ifndef E3_SHR_FMA
+#define E3_SHR_FMA 0       // measured: moving the shifts to IMAD.HI loses 2-4 % (the FMA-heavy pipe is as narrow as the ALU pipe)
+#endif
+#ifndef E3_ADDR_MODE
+#define E3_ADDR_MODE 0      // bit0 / bit1: first / second class lookup of a strip uses word loads + rotate
+#endif
+#ifndef E3_FINE_MODE
+#define E3_FINE_MODE 0       // 1: per-pixel IMAD.HI instead of the 64-bit running sum (slower, same reason)
+#endif
+#define E3_LOG_BS 4
+#define E3_BS 16
+#ifndef E3_G
+#define E3_G 8              // consecutive strips of one edge per lane and round (<= 8: one class nibble each)
+#endif
+#define E3_QB 512           // bitmap-queue entries per warp (a round adds at most 32 * E3_G)
+#define E3_QG 256           // byte-queue entries per warp
+#define E3_BIAS 65536ull
+#define E3_MAX_WARPS 32
+
+#define K_FREE 0u
+#define K_MIXED 1u          // blocking and free pixels, nothing else: the bitmap decides
+#define K_BLOCKED 2u        // every pixel blocks
+#define K_SPECIAL 3u        // contains gray pixels (DOOR zones / gray without zone id): per-pixel pass on the byte grid
+
+// n' of pixel k = hi32(k * S + (n0m << 32 | 2^16))
+__device__ __forceinline__ int32_t minor_m(uint32_t k, uint32_t S, int32_t n0m) {
+  return (int32_t)(((uint64_t)k * (uint64_t)S + (((uint64_t)(uint32_t)n0m << 32) | E3_BIAS)) >> 32);
+}
+
+
+// x >> s for a compile-time s, on the ALU pipe (SHF) or the FMA pipe (IMAD.HI): the kernel is bound by integer issue on
+// these two pipes, so the split between them is tuned (E3_* switches, measured on B200)
+template <bool FMA>
+__device__ __forceinline__ uint32_t shr_c(uint32_t x, int s) { return FMA ? __umulhi(x, 1u << (32 - s)) : x >> s; }
+
+// 2-bit class of block idx from the plane in shared memory (16 per 32-bit word)
+template <bool WORD>
+__device__ __forceinline__ uint32_t plane_class(const unsigned char* plane, uint32_t idx) {
+  if (WORD) {
+    const uint32_t w = ((const uint32_t*)plane)[__umulhi(idx, 1u << 28)];
+    return __funnelshift_r(w, w, idx * 2u) & 3u;           // rotate by 2 * idx mod 32
+  }
+  return ((uint32_t)plane[idx >> 2] >> ((idx * 2u) & 6u)) & 3u;
+}
+
+__device__ __forceinline__ void ld256(uint32_t (&v)[8], const uint32_t* p) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait0(uint64_t* bar) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+}
+
