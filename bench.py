@@ -314,7 +314,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_launch": alg_bytes, "mean_pixels_per_edge": n_px / E, "kernel": "edge_validity_v3_kernel<DOOR,false>" if os.environ.get("PORRT_EDGE_VARIANT", "0") == "0" else "edge_validity_v%s" % os.environ["PORRT_EDGE_VARIANT"],
+                "algorithmic_bytes_per_launch": alg_bytes, "mean_pixels_per_edge": n_px / E, "kernel": {"0": "edge_validity_v3_kernel<DOOR,false>", "9": "edge_validity_v4_kernel<DOOR,false>"}.get(os.environ.get("PORRT_EDGE_VARIANT", "0"), "edge_validity_v2_kernel<DOOR>"),
                 "bound_note": "algorithmic bytes / kernel time against the HBM peak (SURVEY 8(d)); the kernel itself is bound by integer issue (ALU pipe 74 %), DRAM traffic ~ the 44 B/edge streams",
                 "kernel_ms": ms / args.steps}
 

@@ -90,9 +90,10 @@ struct porrt_ctx {
   std::vector<double> zone_pos;         // [2 * n_zones]
   std::vector<uint64_t> zone_world_masks;  // DOOR: zones_to_worlds [n_zones * mask_words]
   DevBuf d_grid, d_coarse[3], d_validities, d_zone_pos, d_plane, d_bits, d_ticket;
-  int edge_variant = 0;  // 0: edge4.cu (lane per edge over length-sorted groups; class plane in shared memory + block bitmaps);
-                         // 8: edge3.cu (same data, flattened strips); 1: byte-grid warp walk;
-                         // 2..7: class bytes + flattened strips (map.cu v2) with various block / group sizes
+  int edge_variant = 0;  // 0: edge3.cu (class plane in shared memory + block bitmaps, flattened strips) -- the product path;
+                         // 9: edge4.cu (same data, lane per edge over length-sorted groups; measured equal, kept for A/B);
+                         // 1: byte-grid warp walk; 2..7: class bytes in global memory + flattened strips (map.cu v2, also the
+                         // fallback for maps whose class plane does not fit in shared memory)
   // host copies of the raw images are NOT kept: the product never walks pixels on the CPU.
 
   // ---- vertices / cell grid (nn.cu)

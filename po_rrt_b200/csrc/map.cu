@@ -640,10 +640,10 @@ template <bool INDEXED>
 static int32_t launch_edges(porrt_ctx* ctx, const double2* from, const double2* to, int64_t n, int32_t* out_vid, uint64_t* out_mask,
                             const int32_t* from_idx, const int32_t* to_idx, cudaStream_t st) {
   if (n == 0) return PORRT_OK;
-  if (ctx->edge_variant == 0 && edge4_usable(ctx))
-    return edge4_launch(ctx, (const double*)from, (const double*)to, n, out_vid, out_mask, from_idx, to_idx, st);
-  if ((ctx->edge_variant == 0 || ctx->edge_variant == 8) && edge3_usable(ctx))
+  if (ctx->edge_variant == 0 && edge3_usable(ctx))
     return edge3_launch(ctx, (const double*)from, (const double*)to, n, out_vid, out_mask, from_idx, to_idx, st);
+  if (ctx->edge_variant == 9 && edge4_usable(ctx))
+    return edge4_launch(ctx, (const double*)from, (const double*)to, n, out_vid, out_mask, from_idx, to_idx, st);
   const uint64_t* val = ctx->d_validities.as<uint64_t>();
   const int grid = edge_grid(ctx, n);
   const bool shelf = ctx->map.kind == PORRT_DOMAIN_SHELF;

@@ -92,6 +92,48 @@ def test_door_edges_panics(ctx):
     assert (sv == O.PANIC_OOB).any() and (sv == O.PANIC_ZONE_UNWRAP).any()
 
 
+@pytest.mark.parametrize("variant", ["9", "3", "1"])
+def test_edge_kernel_variants(ctx, variant, monkeypatch):
+    """the other edge kernels kept in the library (9: lane per edge over sorted groups, 3: class bytes in global
+    memory = the fallback for maps too large for the shared-memory plane, 1: byte-grid warp walk) give the same bits"""
+    monkeypatch.setenv("PORRT_EDGE_VARIANT", variant)       # read at map upload
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    a, b = synth.edges(120_000, seed=31, max_len=0.4)
+    _check_edges(omap, pmap, a, b)
+    a, b = synth.edges(20_000, seed=32, max_len=2.5)        # edges across the whole map (> 32 strips)
+    _check_edges(omap, pmap, a, b)
+    rng = np.random.default_rng(33)
+    a = rng.uniform(-1.1, 1.1, (40_000, 2)); b = a + rng.uniform(-0.3, 0.3, (40_000, 2))
+    _check_edges(omap, pmap, a, b)                          # some end points outside the map
+    occ, zones = synth.shelf_map(400, n_rects=20, n_zones=5, seed=6)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.6)
+    a, b = synth.edges(60_000, seed=34, max_len=0.5)
+    _check_edges(omap, pmap, a, b)
+    monkeypatch.delenv("PORRT_EDGE_VARIANT")
+    occ, zones = util.small_door_map(256, 2)
+    util.make_pair(ctx, occ, zones, P.DOOR, 0.3)            # leave the ctx on the default kernel
+
+
+def test_edges_odd_map_sizes(ctx):
+    """maps whose sides are not multiples of the 16-pixel blocks, and a non-square one"""
+    rng = np.random.default_rng(40)
+    for (H, W) in ((200, 200), (333, 517), (1000, 250)):
+        occ = np.full((H, W), 255, np.uint8)
+        for _ in range(60):
+            h, w = rng.integers(3, max(4, H // 6)), rng.integers(3, max(4, W // 6))
+            i, j = rng.integers(0, H - h), rng.integers(0, W - w)
+            occ[i:i + h, j:j + w] = 0
+        zones = np.full((H, W), 255, np.uint8)
+        occ[H // 2:H // 2 + 9, W // 3:W // 3 + 7] = 128; zones[H // 2:H // 2 + 9, W // 3:W // 3 + 7] = 0
+        occ[H - 12:H - 3, W - 11:W - 2] = 128; zones[H - 12:H - 3, W - 11:W - 2] = 1   # zone touching the last (partial) blocks
+        omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+        a, b = synth.edges(80_000, seed=41, max_len=0.6)
+        want = _check_edges(omap, pmap, a, b)
+        assert (want == -1).any() and (want >= 0).any()
+        _check_edges(omap, pmap, b, a)
+
+
 def test_door_without_zones(ctx):
     occ, _ = util.small_door_map(256, 1)
     occ[occ == 128] = 255
