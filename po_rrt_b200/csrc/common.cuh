@@ -101,6 +101,8 @@ struct porrt_ctx {
   double cell = 0, inv_cell = 0, org_x = 0, org_y = 0;
   int32_t cells_x = 0, cells_y = 0;
   DevBuf d_vxy_sorted, d_vid_sorted, d_cell_start, d_vxy, d_vcell;
+  DevBuf nn_tmp[3];      // nn_tile.cu: query bins
+  int32_t nn_fb_n = 0;   // queries of the last tile pass left to the thread-per-query kernels
 
   // ---- last belief VI result (graph.cu), kept for porrt_extract_policy
   struct BeliefState_ {
@@ -181,6 +183,15 @@ int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_de
 bool edge4_usable(const porrt_ctx* ctx);
 int32_t edge4_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
                      uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st);
+// nn_tile.cu (TMA-staged vertex tiles); GridDev is defined in nn_dev.cuh
+struct GridDev;
+bool nn_tile_usable(const porrt_ctx* ctx, int64_t m);
+int32_t nn_tile_radius(porrt_ctx* ctx, const GridDev& g, const double* q_dev, const double* radius_dev, int64_t m,
+                       const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev, bool fill, int32_t* counts_dev,
+                       const int64_t* offsets_dev, int32_t* ids_dev, const int32_t** fb_list_out, int32_t* fb_n_out);
+int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64_t m, int k, const uint64_t* reach_dev,
+                    const uint32_t* world_dev, int32_t* ids_dev, double* dist_dev, int32_t* ties_dev, const int32_t** fb_list_out,
+                    int32_t* fb_n_out);
 // nn.cu helpers used by graph.cu
 int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi);
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,

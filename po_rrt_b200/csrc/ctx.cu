@@ -40,6 +40,7 @@ PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
   ctx->d_plane.release(); ctx->d_bits.release(); ctx->d_ticket.release();
   ctx->d_vxy_sorted.release(); ctx->d_vid_sorted.release(); ctx->d_cell_start.release();
   ctx->d_vxy.release(); ctx->d_vcell.release();
+  for (DevBuf& b : ctx->nn_tmp) b.release();
   for (DevBuf& b : ctx->scratch) b.release();
   for (PinBuf& b : ctx->pin) b.release();
   for (int s = 0; s < MAX_SLOTS; ++s) {

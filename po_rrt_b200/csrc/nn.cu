@@ -12,6 +12,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "nn_dev.cuh"
 
 // ================================================================================================ scan
 // exclusive scan of u32 counts into i64 offsets; three-phase (block scan, scan of block sums, add).
@@ -212,22 +213,6 @@ int bits_for(uint64_t max_value) {
 }
 
 // ================================================================================================ cell grid
-struct GridDev {
-  const double2* vxy;       // cell-sorted vertex coordinates
-  const int32_t* vid;       // their ids
-  const int64_t* cell_start;  // [cells_x*cells_y + 1]
-  double org_x, org_y, inv_cell, cell;
-  int32_t cells_x, cells_y;
-  int64_t n;
-};
-
-__device__ __forceinline__ int cell_coord(double v, double org, double inv_cell, int n_cells) {
-  double c = floor(__dmul_rn(__dsub_rn(v, org), inv_cell));
-  if (!(c > 0.0)) return 0;
-  if (c >= (double)(n_cells - 1)) return n_cells - 1;
-  return (int)c;
-}
-
 __global__ void bbox_kernel(const double2* __restrict__ xy, int64_t n, double* __restrict__ out /* minx,miny,maxx,maxy as ordered u64 */) {
   double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -356,31 +341,15 @@ PORRT_API int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n) {
 }
 
 // ================================================================================================ radius query
-// T(r) = max{ t : sqrt_rn(t) <= r }  (SURVEY 8(g) note 3): the reference tests `norm2(..) <= radius` on the sqrt-ed value.
-__device__ __forceinline__ double radius_threshold(double r) {
-  if (!(r >= 0.0)) return -1.0;  // negative or NaN radius: nothing passes `d <= radius`
-  double t = __dmul_rn(r, r);
-  if (isinf(t)) return t;
-  while (t > 0.0 && __dsqrt_rn(t) > r) t = __longlong_as_double(__double_as_longlong(t) - 1);
-  for (;;) {
-    double u = __longlong_as_double(__double_as_longlong(t) + 1);
-    if (isfinite(u) && __dsqrt_rn(u) <= r) t = u; else break;
-  }
-  return t;
-}
-
-__device__ __forceinline__ double dist2(double2 v, double qx, double qy) {
-  double dx = __dsub_rn(qx, v.x), dy = __dsub_rn(qy, v.y);
-  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));  // 0.0 + dx*dx is exact, so this is the reference's sum
-}
-
 template <bool FILL>
 __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius, int64_t m,
                                                      const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
                                                      const uint32_t* __restrict__ world, int32_t* __restrict__ counts,
-                                                     const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids) {
+                                                     const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids,
+                                                     const int32_t* __restrict__ list) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
+  if (list) t = list[t];   // m = length of the list: the queries nn_tile.cu left to this kernel
   const double2 p = q[t];
   const double r = radius[t];
   const double T = radius_threshold(r);
@@ -432,8 +401,21 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   GridDev g = grid_dev(ctx);
   CUDA_TRY(ctx, ctx->scratch[4].ensure((size_t)m * 4 + 16));
   int32_t* counts = ctx->scratch[4].as<int32_t>();
-  radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr);
-  LAUNCH_CHECK(ctx);
+  const bool tiles = nn_tile_usable(ctx, m);
+  const int32_t* fb_list = nullptr;
+  int32_t fb_n = 0;
+  if (tiles) {   // TMA-staged tiles, warp per query; queries with a wider reach come back in fb_list
+    CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)m * 4, st));
+    int32_t rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, false, counts, nullptr, nullptr, &fb_list, &fb_n);
+    if (rc) return rc;
+    if (fb_n > 0) {
+      radius_kernel<false><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, fb_list);
+      LAUNCH_CHECK(ctx);
+    }
+  } else {
+    radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK(ctx);
+  }
   int32_t rc = scan_exclusive_i64(ctx, counts, m, offsets_dev);
   if (rc) return rc;
   int64_t total = 0;
@@ -442,8 +424,17 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   *total_out = total;
   CUDA_TRY(ctx, ids_buf->ensure((size_t)std::max<int64_t>(total, 1) * 4));
   if (total > 0) {
-    radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>());
-    LAUNCH_CHECK(ctx);
+    if (tiles) {
+      rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, true, nullptr, offsets_dev, ids_buf->as<int32_t>(), &fb_list, &fb_n);
+      if (rc) return rc;
+      if (fb_n > 0) {
+        radius_kernel<true><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), fb_list);
+        LAUNCH_CHECK(ctx);
+      }
+    } else {
+      radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), nullptr);
+      LAUNCH_CHECK(ctx);
+    }
   }
   return PORRT_OK;
 }
@@ -609,26 +600,14 @@ struct TopK {
   }
 };
 
-__device__ __forceinline__ double ring_lower_bound2(const GridDev& g, double qx, double qy, int cx, int cy, int R) {
-  // squared distance from q to the nearest point outside the square of cells [cx-R,cx+R] x [cy-R,cy+R];
-  // sides beyond the grid have nothing behind them.  Shrunk by 1e-9 relative to stay conservative.
-  double lb = INFINITY;
-  if (cx - R > 0) lb = fmin(lb, qx - (g.org_x + (double)(cx - R) * g.cell));
-  if (cx + R < g.cells_x - 1) lb = fmin(lb, (g.org_x + (double)(cx + R + 1) * g.cell) - qx);
-  if (cy - R > 0) lb = fmin(lb, qy - (g.org_y + (double)(cy - R) * g.cell));
-  if (cy + R < g.cells_y - 1) lb = fmin(lb, (g.org_y + (double)(cy + R + 1) * g.cell) - qy);
-  if (isinf(lb)) return INFINITY;
-  if (!(lb > 0.0)) return 0.0;
-  lb *= (1.0 - 1e-9);
-  return lb * lb;
-}
-
 template <int KMAX>
 __global__ void __launch_bounds__(128) knn_kernel(GridDev g, const double2* __restrict__ q, int64_t m, int k,
                                                   const uint64_t* __restrict__ reach, const uint32_t* __restrict__ world,
-                                                  int32_t* __restrict__ out_ids, double* __restrict__ out_dist, int32_t* __restrict__ out_ties) {
+                                                  int32_t* __restrict__ out_ids, double* __restrict__ out_dist, int32_t* __restrict__ out_ties,
+                                                  const int32_t* __restrict__ list) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
+  if (list) t = list[t];   // m = length of the list: the queries nn_tile.cu left to the exact ring search
   const double2 p = q[t];
   TopK<KMAX> top;
   top.init(k);
@@ -697,10 +676,20 @@ static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, co
   if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
   GridDev g = grid_dev(ctx);
   tstart(ctx);  // phases: [kernel, D2H]
-  if (k == 1) knn_kernel<1><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, 1, d_reach, d_world, d_ids, d_dist, d_ties);
-  else if (k <= 8) knn_kernel<8><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, k, d_reach, d_world, d_ids, d_dist, nullptr);
-  else knn_kernel<32><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)d_q, m, k, d_reach, d_world, d_ids, d_dist, nullptr);
-  LAUNCH_CHECK(ctx);
+  int64_t m_run = m;
+  const int32_t* list = nullptr;
+  if (nn_tile_usable(ctx, m)) {   // TMA-staged tiles, thread per query; whoever needs a wider ring comes back in the list
+    int32_t fb_n = 0;
+    int32_t rc = nn_tile_knn(ctx, g, d_q, m, k, d_reach, d_world, d_ids, d_dist, k == 1 ? d_ties : nullptr, &list, &fb_n);
+    if (rc) return rc;
+    m_run = fb_n;
+  }
+  if (m_run > 0) {
+    if (k == 1) knn_kernel<1><<<div_up(m_run, 128), 128, 0, st>>>(g, (const double2*)d_q, m_run, 1, d_reach, d_world, d_ids, d_dist, d_ties, list);
+    else if (k <= 8) knn_kernel<8><<<div_up(m_run, 128), 128, 0, st>>>(g, (const double2*)d_q, m_run, k, d_reach, d_world, d_ids, d_dist, nullptr, list);
+    else knn_kernel<32><<<div_up(m_run, 128), 128, 0, st>>>(g, (const double2*)d_q, m_run, k, d_reach, d_world, d_ids, d_dist, nullptr, list);
+    LAUNCH_CHECK(ctx);
+  }
   tmark(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(out_ids, d_ids, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
   if (out_dist) CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_dist, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));

@@ -369,6 +369,42 @@ def _prm_compare(ctx, occ, zones, kind, n_iter, max_step, search_radius, start=(
     return prm, oprm
 
 
+def test_nn_tiles_equal_thread_per_query(ctx, monkeypatch):
+    """nn_tile.cu (TMA-staged tiles) against nn.cu's thread-per-query kernels on the same batches: mixed radii (some wider
+    than a cell -> index-list fallback), prefix limits, reachability filters, NaN / far-away queries, clustered vertices
+    (tiles that exceed the staging buffer), k = 1 / 5 / 16 / 32"""
+    rng = np.random.default_rng(77)
+    pts = np.vstack([synth.points(60_000, seed=71), 0.02 * rng.standard_normal((30_000, 2)) + [0.3, -0.2]])   # dense cluster
+    tree = P.KdTree(ctx, pts, cell_size=0.02)
+    q = np.vstack([synth.points(12_000, seed=72), 0.02 * rng.standard_normal((4_000, 2)) + [0.3, -0.2],
+                   synth.points(500, seed=73, low=-1.6, up=1.6)])
+    q[7] = [np.nan, 0.1]
+    radius = rng.uniform(0.0, 0.03, len(q)); radius[::50] = 0.08; radius[3] = -1.0; radius[11] = np.nan
+    prefix = rng.integers(0, len(pts) + 1, len(q)).astype(np.uint32)
+    reach = rng.integers(0, 2 ** 63, len(pts), dtype=np.uint64)
+    world = rng.integers(0, 63, len(q)).astype(np.uint32)
+
+    def run():
+        out = {}
+        out["r"] = tree.nearest_neighbors(q, radius)
+        out["rp"] = tree.nearest_neighbors(q, radius, prefix_limit=prefix)
+        out["rf"] = tree.nearest_neighbors(q, radius, reach_mask=reach, world=world)
+        out["nn"] = tree.nearest_neighbor(q)
+        out["nnf"] = tree.nearest_neighbor(q, reach_mask=reach, world=world)
+        for k in (5, 16, 32):
+            out["k%d" % k] = tree.knn(q, k)
+        return out
+
+    got = run()
+    monkeypatch.setenv("PORRT_NN_NO_TILES", "1")
+    want = run()
+    monkeypatch.delenv("PORRT_NN_NO_TILES")
+    for key in want:
+        for a, b in zip(got[key], want[key]):
+            np.testing.assert_array_equal(a, b, err_msg=key)
+    assert len(got["r"][1]) > 100_000
+
+
 def test_prm_build_door(ctx):
     occ, zones = util.small_door_map(512, 3)
     prm, _ = _prm_compare(ctx, occ, zones, P.DOOR, 6000, 0.1, 2.0)
