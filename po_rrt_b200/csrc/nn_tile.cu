@@ -9,11 +9,9 @@
 //   * a CTA takes such a tile, and the vertices any of its queries can reach -- three cell rows x (NT_W + 2) cells,
 //     i.e. three CONTIGUOUS ranges of the cell-sorted arrays -- are staged in shared memory by bulk-async copies
 //     (cp.async.bulk, mbarrier byte-count completion): each vertex is fetched once per tile instead of once per query;
-//   * radius search: one WARP per query, lanes stride the staged candidates (conflict-free 16-byte shared loads), hits are
-//     counted / written with ballots, so the id lists come out coalesced;
-//   * 1-NN / k-NN: one THREAD per query with its k best in shared memory (column layout, conflict-free).  A warp-wide
-//     sorted list was measured on paper first: ~25 instructions per insertion x ~49 insertions per query would cost
-//     ~1000 warp instructions per query, the per-thread list ~100.
+//   * every query is owned by one THREAD of the tile's CTA, which walks its (<= 3) candidate runs in shared memory; k-NN
+//     keeps its k best in shared memory too (column layout, conflict-free).  Warp-per-query variants (ballot-compacted
+//     hit lists; a warp-wide sorted list) cost 2-10x the instructions per candidate -- see the notes at the kernels.
 // Distances are the reference's f64 arithmetic (common.rs:203-213) and `sqrt(d2) <= r` is evaluated as d2 <= T(r).
 // Queries whose radius reaches beyond the neighbouring cells, tiles whose candidates exceed the staging buffer and k-NN
 // queries that need a wider ring go to nn.cu's thread-per-query kernels (exact ring search) through an index list.
@@ -22,7 +20,7 @@
 #define NT_W 8               // cells per tile along x
 #define NT_THREADS 128
 #define NT_CAP 2048          // staged vertices per tile (radius): 32 KiB + 8 KiB ids
-#define NT_CAP_KNN 1024      // k-NN: leaves room for the per-thread lists
+#define NT_CAP_KNN 768       // k-NN: leaves room for the per-thread lists
 
 __device__ __forceinline__ uint32_t nt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void nt_mbar_init(uint64_t* bar) {
@@ -137,7 +135,11 @@ __device__ __forceinline__ void tile_stage(const GridDev& g, const Tile& T, doub
   }
 }
 
-// ------------------------------------------------------------------------------------------------ radius: warp per query
+// ------------------------------------------------------------------------------------------------ radius: thread per query
+// (A warp-per-query version -- lanes striding the candidates, ballot-compacted coalesced id lists -- was built first and
+// measured: 709 + 828 us for the count + fill passes of 1e6 queries, slower than nn.cu's 450 + 450 us.  The per-query set-up
+// (exact threshold, cell cover, six cell_start look-ups) was paid by 32 lanes for ONE query and the cross-lane bookkeeping
+// cost ~0.8 warp instructions per candidate against ~0.4 for a thread that owns its query.)
 template <bool FILL>
 __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius,
                                                                const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
@@ -151,9 +153,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
   const Tile T = tile_setup(g, qstart, tiles_per_row, NT_CAP);
   if (T.nq == 0) return;
   tile_stage(g, T, s_xy, s_id, &s_bar);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int qi = wib; qi < T.nq; qi += NT_THREADS / 32) {
+  for (int qi = threadIdx.x; qi < T.nq; qi += NT_THREADS) {
     const int32_t t = qorder[T.qa + qi];
     const double2 p = q[t];
     const double r = radius[t];
@@ -163,129 +163,168 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
     const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);
     const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
     const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
-    // the query's candidates: <= 3 runs, addressed as one index space
-    int n_run[3], s_run[3];            // length, start relative to the staged row
-    int64_t g_run[3];                  // start in the global arrays
-    int nt = 0;
+    int cnt = 0;
+    int32_t* out = FILL ? out_ids + offsets[t] : nullptr;
 #pragma unroll
     for (int rr3 = 0; rr3 < 3; ++rr3) {
       const int row = T.cy - 1 + rr3;
-      n_run[rr3] = 0; s_run[rr3] = 0; g_run[rr3] = 0;
-      if (row >= cy0 && row <= cy1) {
-        const int64_t s = g.cell_start[(int64_t)row * g.cells_x + cx0], e = g.cell_start[(int64_t)row * g.cells_x + cx1 + 1];
-        n_run[rr3] = (int)(e - s); s_run[rr3] = (int)(s - T.k0[rr3]); g_run[rr3] = s;
-      }
-      nt += n_run[rr3];
-    }
-    int cnt = 0;
-    int32_t* out = FILL ? out_ids + offsets[t] : nullptr;
-    for (int i0 = 0; i0 < nt; i0 += 32) {
-      const int idx = i0 + lane;
-      bool hit = false;
-      int32_t id = 0;
-      if (idx < nt) {
-        const int rsel = (idx >= n_run[0]) + (idx >= n_run[0] + n_run[1]);
-        const int j = idx - (rsel > 0 ? n_run[0] : 0) - (rsel > 1 ? n_run[1] : 0);
-        const int srow = rsel == 0 ? s_run[0] : (rsel == 1 ? s_run[1] : s_run[2]);
-        double2 v;
-        if (T.staged) {
-          const int xo = rsel == 0 ? T.xoff[0] : (rsel == 1 ? T.xoff[1] : T.xoff[2]);
-          const int io = rsel == 0 ? T.ioff[0] : (rsel == 1 ? T.ioff[1] : T.ioff[2]);
-          v = s_xy[xo + srow + j];
-          id = s_id[io + srow + j];
-        } else {
-          const int64_t gk = (rsel == 0 ? g_run[0] : (rsel == 1 ? g_run[1] : g_run[2])) + j;
-          v = g.vxy[gk];
-          id = g.vid[gk];
+      if (row < cy0 || row > cy1) continue;
+      const int64_t s = g.cell_start[(int64_t)row * g.cells_x + cx0], e = g.cell_start[(int64_t)row * g.cells_x + cx1 + 1];
+      const int n_run = (int)(e - s), s_run = (int)(s - T.k0[rr3]);
+      const double2* cx = T.staged ? s_xy + T.xoff[rr3] + s_run : g.vxy + s;
+      const int32_t* ci = T.staged ? s_id + T.ioff[rr3] + s_run : g.vid + s;
+      for (int j = 0; j < n_run; ++j) {
+        if (dist2(cx[j], p.x, p.y) <= Tr) {
+          const int32_t id = ci[j];
+          if ((uint32_t)id < limit && (!reach || ((reach[id] >> wbit) & 1ull))) {
+            if (FILL) out[cnt] = id;
+            ++cnt;
+          }
         }
-        hit = dist2(v, p.x, p.y) <= Tr && (uint32_t)id < limit;
-        if (hit && reach) hit = ((reach[id] >> wbit) & 1ull) != 0;
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (FILL && hit) out[cnt + __popc(bal & lt_mask)] = id;
-      cnt += __popc(bal);
     }
-    if (!FILL && lane == 0) counts[t] = cnt;
+    if (!FILL) counts[t] = cnt;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ 1-NN / k-NN: thread per query
-// dynamic shared memory: [ s_xy NT_CAP_KNN | s_id NT_CAP_KNN + 24 | best d2 k x NT_THREADS (f64) | best id k x NT_THREADS ]
+// k = 1: running minimum (+ the number of vertices at exactly the winning d2, nn.cu: knn_kernel<1>).
+// k > 1: a sorted list kept by insertion was measured first (1.75 ms for 1e6 queries, k = 16): lanes insert at different
+// candidates, so the warp pays the insertion loop at almost every candidate.  Now two uniform passes over the candidates:
+//   pass 1 bins d2 into NT_BINS equal-width bins (equal area: candidates are ~uniform in d2) in a per-thread byte
+//          histogram and finds the first bin where the cumulative count reaches k;
+//   pass 2 collects the candidates of the bins up to that one (k + a few) into the thread's list, which is then
+//          insertion-sorted by (d2, id) and cut at k.
+// Exact: both passes evaluate the same expression per candidate; a query is finished here only if its k-th best is
+// provably closer than anything outside the 3 x 3 cells (ring_lower_bound2, R = 1), otherwise -- or if its list overflows
+// (> k + NT_SLACK candidates in the bins, e.g. many exact duplicates) -- it goes to nn.cu's exact ring search.
+// dynamic shared memory: [ s_xy NT_CAP_KNN | list d2 cap x NT_THREADS (f64) | list id cap x NT_THREADS | s_id NT_CAP_KNN + 24
+//                          | histogram NT_BINS x NT_THREADS (u8) ],  cap = k + NT_SLACK
+#define NT_BINS 32
+#define NT_SLACK 8
 __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const double2* __restrict__ q, int k,
                                                             const uint64_t* __restrict__ reach, const uint32_t* __restrict__ world,
                                                             const int32_t* __restrict__ qorder, const int64_t* __restrict__ qstart,
                                                             int tiles_per_row, int32_t* __restrict__ out_ids, double* __restrict__ out_dist,
                                                             int32_t* __restrict__ out_ties, int32_t* __restrict__ fb_list, int32_t* __restrict__ fb_n) {
   extern __shared__ __align__(128) unsigned char nt_smem[];
+  const int cap = k + NT_SLACK;
   double2* s_xy = (double2*)nt_smem;
   double* s_bd = (double*)(nt_smem + (size_t)NT_CAP_KNN * 16);
-  int32_t* s_bi = (int32_t*)(nt_smem + (size_t)NT_CAP_KNN * 16 + (size_t)k * NT_THREADS * 8);
-  int32_t* s_id = s_bi + (size_t)k * NT_THREADS;
+  int32_t* s_bi = (int32_t*)(nt_smem + (size_t)NT_CAP_KNN * 16 + (size_t)cap * NT_THREADS * 8);
+  int32_t* s_id = s_bi + (size_t)cap * NT_THREADS;
+  uint8_t* s_hist = (uint8_t*)(s_id + NT_CAP_KNN + 24);
   __shared__ uint64_t s_bar;
   const Tile T = tile_setup(g, qstart, tiles_per_row, NT_CAP_KNN);
   if (T.nq == 0) return;
   tile_stage(g, T, s_xy, s_id, &s_bar);
   double* bd = s_bd + threadIdx.x;     // column layout: entry j of this thread at [j * NT_THREADS]
   int32_t* bi = s_bi + threadIdx.x;
+  uint8_t* hist = s_hist + threadIdx.x;
+  // bins cover d2 in [0, (1.5 cell)^2): whatever lies beyond cannot be certified by the R = 1 bound anyway (<= 2 cells)
+  const double bin_scale = (double)NT_BINS / (2.25 * g.cell * g.cell);
   for (int qi = threadIdx.x; qi < T.nq; qi += NT_THREADS) {
     const int32_t t = qorder[T.qa + qi];
     const double2 p = q[t];
     const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
     const int cx = cell_coord(p.x, g.org_x, g.inv_cell, g.cells_x);
     const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, g.cells_x - 1);
-    int cnt = 0, ties = 0;
-    double worst = INFINITY;           // d2 of entry k-1 once the list is full
-    int32_t worst_id = 0x7fffffff;
+    // the query's candidate runs (rows cy-1, cy, cy+1)
+    const double2* rx[3]; const int32_t* ri[3]; int rn[3];
 #pragma unroll
     for (int rr3 = 0; rr3 < 3; ++rr3) {
       const int row = T.cy - 1 + rr3;
-      if (row < 0 || row >= g.cells_y) continue;
-      const int64_t s = g.cell_start[(int64_t)row * g.cells_x + cx0], e = g.cell_start[(int64_t)row * g.cells_x + cx1 + 1];
-      const int n_run = (int)(e - s), s_run = (int)(s - T.k0[rr3]);
-      for (int j = 0; j < n_run; ++j) {
-        double2 v;
-        int32_t id;
-        if (T.staged) { v = s_xy[T.xoff[rr3] + s_run + j]; id = s_id[T.ioff[rr3] + s_run + j]; }
-        else { v = g.vxy[s + j]; id = g.vid[s + j]; }
-        const double d = dist2(v, p.x, p.y);
-        if (d != d) continue;
-        if (k == 1 ? (cnt != 0 && d > worst) : !(cnt < k || d < worst || (d == worst && id < worst_id))) continue;
-        if (reach && !((reach[id] >> wbit) & 1ull)) continue;
-        if (k == 1) {                  // ties = vertices at exactly the winning d2 (nn.cu: knn_kernel<1>)
-          if (cnt == 0 || d < worst) ties = 1; else if (d == worst) ++ties;
-          if (cnt == 0 || d < worst || id < worst_id) { worst = d; worst_id = id; }
-          cnt = 1;
-          continue;
-        }
-        int pos = cnt < k ? cnt : k - 1;   // insertion keeps the list ascending by (d2, id)
-        while (pos > 0) {
-          const double pd = bd[(pos - 1) * NT_THREADS];
-          const int32_t pi = bi[(pos - 1) * NT_THREADS];
-          if (!(d < pd || (d == pd && id < pi))) break;
-          bd[pos * NT_THREADS] = pd; bi[pos * NT_THREADS] = pi;
-          --pos;
-        }
-        bd[pos * NT_THREADS] = d; bi[pos * NT_THREADS] = id;
-        if (cnt < k) ++cnt;
-        if (cnt == k) { worst = bd[(k - 1) * NT_THREADS]; worst_id = bi[(k - 1) * NT_THREADS]; }
+      rn[rr3] = 0; rx[rr3] = s_xy; ri[rr3] = s_id;
+      if (row >= 0 && row < g.cells_y) {
+        const int64_t s = g.cell_start[(int64_t)row * g.cells_x + cx0], e = g.cell_start[(int64_t)row * g.cells_x + cx1 + 1];
+        const int s_run = (int)(s - T.k0[rr3]);
+        rn[rr3] = (int)(e - s);
+        rx[rr3] = T.staged ? s_xy + T.xoff[rr3] + s_run : g.vxy + s;
+        ri[rr3] = T.staged ? s_id + T.ioff[rr3] + s_run : g.vid + s;
       }
     }
-    // exact only if nothing outside the 3 x 3 cells can beat the k-th best (nn.cu: ring_lower_bound2 with R = 1)
-    const int cy = T.cy;
-    if (cnt == k && worst < ring_lower_bound2(g, p.x, p.y, cx, cy, 1)) {
-      if (k == 1) {
-        out_ids[t] = worst_id;
-        if (out_dist) out_dist[t] = __dsqrt_rn(worst);
-        if (out_ties) out_ties[t] = ties;
-      } else {
-        for (int j = 0; j < k; ++j) {
-          out_ids[(int64_t)t * k + j] = bi[j * NT_THREADS];
-          if (out_dist) out_dist[(int64_t)t * k + j] = __dsqrt_rn(bd[j * NT_THREADS]);
+    bool done = false;
+    if (k == 1) {
+      int cnt = 0, ties = 0;
+      double best = INFINITY;
+      int32_t best_id = 0x7fffffff;
+#pragma unroll
+      for (int rr3 = 0; rr3 < 3; ++rr3)
+        for (int j = 0; j < rn[rr3]; ++j) {
+          const double d = dist2(rx[rr3][j], p.x, p.y);
+          if (d != d || (cnt != 0 && d > best)) continue;
+          const int32_t id = ri[rr3][j];
+          if (reach && !((reach[id] >> wbit) & 1ull)) continue;
+          if (cnt == 0 || d < best) ties = 1; else ++ties;       // here d == best
+          if (cnt == 0 || d < best || id < best_id) { best = d; best_id = id; }
+          cnt = 1;
         }
+      if (cnt == 1 && best < ring_lower_bound2(g, p.x, p.y, cx, T.cy, 1)) {
+        out_ids[t] = best_id;
+        if (out_dist) out_dist[t] = __dsqrt_rn(best);
+        if (out_ties) out_ties[t] = ties;
+        done = true;
       }
     } else {
-      fb_list[atomicAdd(fb_n, 1)] = t;
+      // pass 1: histogram of d2
+#pragma unroll
+      for (int bsel = 0; bsel < NT_BINS; ++bsel) hist[bsel * NT_THREADS] = 0;
+      int n_far = 0;   // candidates beyond the last bin are only counted
+#pragma unroll
+      for (int rr3 = 0; rr3 < 3; ++rr3)
+        for (int j = 0; j < rn[rr3]; ++j) {
+          const double d = dist2(rx[rr3][j], p.x, p.y);
+          if (d != d) continue;
+          if (reach && !((reach[ri[rr3][j]] >> wbit) & 1ull)) continue;
+          const double fb = d * bin_scale;
+          if (fb < (double)NT_BINS) { uint8_t* h = hist + (int)fb * NT_THREADS; if (*h < 255) ++*h; }
+          else ++n_far;
+        }
+      int cum = 0, B = -1;
+      for (int bsel = 0; bsel < NT_BINS; ++bsel) {
+        const int h = hist[bsel * NT_THREADS];
+        if (h == 255) break;           // saturated counter: let the exact ring search handle it
+        cum += h;
+        if (cum >= k) { B = bsel; break; }
+      }
+      if (B >= 0 && cum <= cap) {
+        // pass 2: collect the candidates of bins 0..B (unsorted), then insertion sort by (d2, id)
+        const double lim = (double)(B + 1);
+        int cnt = 0;
+#pragma unroll
+        for (int rr3 = 0; rr3 < 3; ++rr3)
+          for (int j = 0; j < rn[rr3]; ++j) {
+            const double d = dist2(rx[rr3][j], p.x, p.y);
+            if (d != d || !(d * bin_scale < lim)) continue;
+            const int32_t id = ri[rr3][j];
+            if (reach && !((reach[id] >> wbit) & 1ull)) continue;
+            bd[cnt * NT_THREADS] = d; bi[cnt * NT_THREADS] = id;   // unsorted append: the warp stays together
+            ++cnt;
+          }
+        for (int i = 1; i < cnt; ++i) {                              // every lane sorts its k + few entries at the same time
+          const double d = bd[i * NT_THREADS];
+          const int32_t id = bi[i * NT_THREADS];
+          int pos = i;
+          while (pos > 0) {
+            const double pd = bd[(pos - 1) * NT_THREADS];
+            const int32_t pi = bi[(pos - 1) * NT_THREADS];
+            if (!(d < pd || (d == pd && id < pi))) break;
+            bd[pos * NT_THREADS] = pd; bi[pos * NT_THREADS] = pi;
+            --pos;
+          }
+          bd[pos * NT_THREADS] = d; bi[pos * NT_THREADS] = id;
+        }
+        if (cnt >= k && bd[(k - 1) * NT_THREADS] < ring_lower_bound2(g, p.x, p.y, cx, T.cy, 1)) {
+          for (int j = 0; j < k; ++j) {
+            out_ids[(int64_t)t * k + j] = bi[j * NT_THREADS];
+            if (out_dist) out_dist[(int64_t)t * k + j] = __dsqrt_rn(bd[j * NT_THREADS]);
+          }
+          done = true;
+        }
+      }
+      (void)n_far;
     }
+    if (!done) fb_list[atomicAdd(fb_n, 1)] = t;
   }
 }
 
@@ -352,6 +391,7 @@ int32_t nn_tile_radius(porrt_ctx* ctx, const GridDev& g, const double* q_dev, co
   }
   *fb_list_out = B.fb_list;
   *fb_n_out = ctx->nn_fb_n;
+  if (getenv("PORRT_DEBUG")) fprintf(stderr, "[porrt] nn tiles: %lld queries, %d left to the thread-per-query kernels\n", (long long)m, ctx->nn_fb_n);
   return PORRT_OK;
 }
 
@@ -362,7 +402,7 @@ int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64
   NtBins B;
   int32_t rc = nt_bin<true>(ctx, g, q_dev, nullptr, m, &B);
   if (rc) return rc;
-  const size_t smem = (size_t)NT_CAP_KNN * 16 + (size_t)k * NT_THREADS * 12 + (size_t)(NT_CAP_KNN + 24) * 4;
+  const size_t smem = (size_t)NT_CAP_KNN * 16 + (size_t)(k + NT_SLACK) * NT_THREADS * 12 + (size_t)(NT_CAP_KNN + 24) * 4 + (size_t)NT_BINS * NT_THREADS;
   static bool attr_set[16] = {};
   if (!attr_set[ctx->device & 15]) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(nt_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -375,5 +415,6 @@ int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   *fb_list_out = B.fb_list;
   *fb_n_out = ctx->nn_fb_n;
+  if (getenv("PORRT_DEBUG")) fprintf(stderr, "[porrt] nn tiles: %lld queries, %d left to the thread-per-query kernels\n", (long long)m, ctx->nn_fb_n);
   return PORRT_OK;
 }
