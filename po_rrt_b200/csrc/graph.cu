@@ -136,6 +136,11 @@ static double heuristic_radius(size_t n_nodes, double max_step, double search_ra
 }
 
 // ================================================================================================ PRM build
+__global__ void iota_u32_kernel(uint32_t* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+
 __global__ void seg_owner_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ owner) {
   const int lane = threadIdx.x & 31;
   const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -213,23 +218,21 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   double t0 = now_ms(), t1;
   double ph[8] = {0};
 
-  // radii: node k (k >= 1) queries with heuristic_radius(k + 1) -- n_nodes AFTER adding the new node (prm.rs:61-65)
-  std::vector<double> radius((size_t)n, 0.0);
-  std::vector<uint32_t> prefix((size_t)n);
+  // radii: node k (k >= 1) queries with heuristic_radius(k + 1) -- n_nodes AFTER adding the new node (prm.rs:61-65).
+  // libm on host threads, started now and joined after the device has binned the vertices and ranked the kd-tree
+  // (neither needs the radii): ~3.6 ms at n = 1e6 that used to sit in front of the device work.
+  CUDA_TRY(ctx, ctx->pin[1].ensure((size_t)n * 8));   // pinned: the upload after the join is one async DMA
+  double* radius = ctx->pin[1].as<double>();
+  std::vector<std::thread> th;
   {
-    int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    int nt = (int)std::min<int64_t>(std::max(2u, std::thread::hardware_concurrency()) / 2, 8);   // leave cores to the driver's copies
     if (n < 20000) nt = 1;
-    std::vector<std::thread> th;
     for (int t = 0; t < nt; ++t)
-      th.emplace_back([&, t]() {
-        for (int64_t k = t; k < n; k += nt) {
-          radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, max_step, search_radius, 2);
-          prefix[k] = (uint32_t)k;
-        }
+      th.emplace_back([=]() {
+        for (int64_t k = t; k < n; k += nt) radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, max_step, search_radius, 2);
       });
-    for (auto& x : th) x.join();
   }
-  t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;
+  struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); } } joiner{th};
 
   // device inputs
   CUDA_TRY(ctx, ctx->d_vxy.ensure((size_t)n * 16));
@@ -247,37 +250,44 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   int32_t* d_late_cnt = (int32_t*)b; b += (size_t)n * 4;
   int32_t* d_flag = (int32_t*)b; b += 16;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vxy.p, samples_xy, (size_t)n * 16, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_radius, radius.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_prefix, prefix.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemsetAsync(d_late_cnt, 0, (size_t)n * 4, st));
   CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
 
   // 1. bin vertices; cell = the smallest radius in use (the last one) so late queries touch 3x3 cells
-  double cell = radius[n - 1] > 0 ? radius[n - 1] : max_step;
+  const double r_last = n > 1 ? heuristic_radius((size_t)n, max_step, search_radius, 2) : -1.0;
+  double cell = r_last > 0 ? r_last : max_step;
   int32_t rc = nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell, nullptr, nullptr);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
 
-  // 2. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
+  // 2. the kd pre-order rank of every vertex (restores the reference's neighbour order in step 4)
+  rc = kd_preorder_rank_dev(ctx, ctx->d_vxy.as<double>(), n, d_rank);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
+
+  for (auto& x : th) x.join();
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_radius, radius, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  iota_u32_kernel<<<div_up(n, 256), 256, 0, st>>>(d_prefix, n);   // prefix limit of query k = k: the tree before node k arrived
+  LAUNCH_CHECK(ctx);
+  t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;   // what is left of the radii after the overlap
+
+  // 3. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
   int64_t total = 0;
   rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>(), d_radius, n, d_prefix, nullptr, nullptr, d_off, &ctx->scratch[2], &total);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
 
-  // 3. restore the kd pre-order inside every neighbour list
-  rc = kd_preorder_rank_dev(ctx, ctx->d_vxy.as<double>(), n, d_rank);
-  if (rc) return rc;
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
+  // 4. restore the kd pre-order inside every neighbour list
   int32_t* d_ids = ctx->scratch[2].as<int32_t>();
   rc = segments_sort_by_key_dev(ctx, d_off, n, d_ids, d_rank, n);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[4] = t1 - t0; t0 = t1;
 
-  // 4. edge checks neighbour -> new node (prm.rs:91-96)
+  // 5. edge checks neighbour -> new node (prm.rs:91-96)
   const int64_t tot1 = std::max<int64_t>(total, 1);
   CUDA_TRY(ctx, ctx->scratch[0].ensure((size_t)tot1 * 4));  // owner (= new node id)
   CUDA_TRY(ctx, ctx->scratch[1].ensure((size_t)tot1 * 4));  // validity ids
@@ -292,7 +302,7 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[5] = t1 - t0; t0 = t1;
 
-  // 5. CSR in insertion order: row k = valid earlier neighbours (kd order), then later nodes ascending (prm.rs:99-106)
+  // 6. CSR in insertion order: row k = valid earlier neighbours (kd order), then later nodes ascending (prm.rs:99-106)
   prm_compact_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_ids, d_vid, d_early_cnt, d_ids, d_flag);
   LAUNCH_CHECK(ctx);
   rc = scan_exclusive_i64(ctx, d_early_cnt, n, d_early_off);
