@@ -31,17 +31,32 @@ static double now_ms() {
 // with; all of them descend one level per round (so the split axis is the round parity), and the child slot (node, side)
 // goes to the smallest id that wants it (atomicMin) -- exactly the point that sequential insertion would have put there.
 // Subtree sizes are counted on the way down; ranks follow top-down, one depth per launch.
+template <bool AGGREGATE>
 __global__ void kd_descend_kernel(const double2* __restrict__ xy, int64_t n, int axis, const int32_t* __restrict__ cur,
                                   int32_t* __restrict__ child, int32_t* __restrict__ size, uint8_t* __restrict__ side) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t c = cur[i];
-  if (c < 0) return;
-  const double2 p = xy[i], q = xy[c];
-  const int s = (axis ? p.y < q.y : p.x < q.x) ? 0 : 1;   // strictly-less goes left (nearest_neighbor.rs:32)
-  atomicMin(&child[2 * (int64_t)c + s], (int32_t)i);
-  atomicAdd(&size[c], 1);
-  side[i] = (uint8_t)s;
+  const int32_t c = i < n ? cur[i] : -1;
+  int s = 0;
+  if (c >= 0) {
+    const double2 p = xy[i], q = xy[c];
+    s = (axis ? p.y < q.y : p.x < q.x) ? 0 : 1;   // strictly-less goes left (nearest_neighbor.rs:32)
+    side[i] = (uint8_t)s;
+  }
+  if (AGGREGATE) {
+    // near the root a million points compete for a handful of child slots: one atomic per (slot, warp) instead of per point
+    const int64_t slot = c >= 0 ? 2 * (int64_t)c + s : -1 - (int64_t)(threadIdx.x & 31);
+    const unsigned peers = __match_any_sync(0xffffffffu, slot);
+    if (c >= 0) {
+      const int leader = __ffs(peers) - 1;          // lanes are in id order: the lowest lane holds the smallest id
+      if ((int)(threadIdx.x & 31) == leader) {
+        atomicMin(&child[slot], (int32_t)i);
+        atomicAdd(&size[c], __popc(peers));
+      }
+    }
+  } else if (c >= 0) {
+    atomicMin(&child[2 * (int64_t)c + s], (int32_t)i);
+    atomicAdd(&size[c], 1);
+  }
 }
 __global__ void kd_place_kernel(int64_t n, int depth, int32_t* __restrict__ cur, const int32_t* __restrict__ child,
                                 const uint8_t* __restrict__ side, int32_t* __restrict__ parent, int32_t* __restrict__ node_depth,
@@ -52,7 +67,7 @@ __global__ void kd_place_kernel(int64_t n, int depth, int32_t* __restrict__ cur,
   if (c < 0) return;
   const int32_t w = child[2 * (int64_t)c + side[i]];
   if (w == (int32_t)i) { parent[i] = c; node_depth[i] = depth + 1; cur[i] = -1; }
-  else { cur[i] = w; atomicAdd(remaining, 1); }
+  else { cur[i] = w; if (remaining) atomicAdd(remaining, 1); }
 }
 __global__ void kd_rank_kernel(int64_t n, int depth, const int32_t* __restrict__ node_depth, const int32_t* __restrict__ parent,
                                const uint8_t* __restrict__ side, const int32_t* __restrict__ child, const int32_t* __restrict__ size,
@@ -94,16 +109,18 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
   LAUNCH_CHECK(ctx);
   int depth = 0;
   for (;; ++depth) {
-    CUDA_TRY(ctx, cudaMemsetAsync(remaining, 0, 4, st));
-    kd_descend_kernel<<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
+    if ((depth & 3) == 0) CUDA_TRY(ctx, cudaMemsetAsync(remaining, 0, 4, st));
+    if (depth < 14) kd_descend_kernel<true><<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
+    else kd_descend_kernel<false><<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
     LAUNCH_CHECK(ctx);
-    kd_place_kernel<<<blocks, 256, 0, st>>>(n, depth, cur, child, side, parent, node_depth, remaining);
+    kd_place_kernel<<<blocks, 256, 0, st>>>(n, depth, cur, child, side, parent, node_depth, (depth & 3) == 3 ? remaining : nullptr);
     LAUNCH_CHECK(ctx);
+    if ((depth & 3) != 3) continue;      // the host looks at the number of unplaced points every fourth level only
     int32_t rem = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&rem, remaining, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (rem == 0) break;
-    if (depth > n) return porrt_fail(ctx, PORRT_ERR_CUDA, "kd_preorder_rank: no convergence");
+    if (depth > n + 4) return porrt_fail(ctx, PORRT_ERR_CUDA, "kd_preorder_rank: no convergence");
   }
   for (int d = 1; d <= depth + 1; ++d) {
     kd_rank_kernel<<<blocks, 256, 0, st>>>(n, d, node_depth, parent, side, child, size, out_rank_dev);
