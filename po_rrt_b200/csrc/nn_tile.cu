@@ -198,10 +198,10 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
 // Exact: both passes evaluate the same expression per candidate; a query is finished here only if its k-th best is
 // provably closer than anything outside the 3 x 3 cells (ring_lower_bound2, R = 1), otherwise -- or if its list overflows
 // (> k + NT_SLACK candidates in the bins, e.g. many exact duplicates) -- it goes to nn.cu's exact ring search.
-// dynamic shared memory: [ s_xy NT_CAP_KNN | list d2 cap x NT_THREADS (f64) | list id cap x NT_THREADS | s_id NT_CAP_KNN + 24
+// dynamic shared memory: [ s_xy NT_CAP_KNN | s_id NT_CAP_KNN + 24 | list cap x NT_THREADS (u16 codes)
 //                          | histogram NT_BINS x NT_THREADS (u8) ],  cap = k + NT_SLACK
 #define NT_BINS 32
-#define NT_SLACK 8
+#define NT_SLACK 16
 __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const double2* __restrict__ q, int k,
                                                             const uint64_t* __restrict__ reach, const uint32_t* __restrict__ world,
                                                             const int32_t* __restrict__ qorder, const int64_t* __restrict__ qstart,
@@ -210,16 +210,14 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
   extern __shared__ __align__(128) unsigned char nt_smem[];
   const int cap = k + NT_SLACK;
   double2* s_xy = (double2*)nt_smem;
-  double* s_bd = (double*)(nt_smem + (size_t)NT_CAP_KNN * 16);
-  int32_t* s_bi = (int32_t*)(nt_smem + (size_t)NT_CAP_KNN * 16 + (size_t)cap * NT_THREADS * 8);
-  int32_t* s_id = s_bi + (size_t)cap * NT_THREADS;
-  uint8_t* s_hist = (uint8_t*)(s_id + NT_CAP_KNN + 24);
+  int32_t* s_id = (int32_t*)(nt_smem + (size_t)NT_CAP_KNN * 16);
+  uint16_t* s_lst = (uint16_t*)(s_id + NT_CAP_KNN + 24);
+  uint8_t* s_hist = (uint8_t*)(s_lst + (size_t)cap * NT_THREADS);
   __shared__ uint64_t s_bar;
   const Tile T = tile_setup(g, qstart, tiles_per_row, NT_CAP_KNN);
   if (T.nq == 0) return;
   tile_stage(g, T, s_xy, s_id, &s_bar);
-  double* bd = s_bd + threadIdx.x;     // column layout: entry j of this thread at [j * NT_THREADS]
-  int32_t* bi = s_bi + threadIdx.x;
+  uint16_t* lst = s_lst + threadIdx.x; // column layout: entry j of this thread at [j * NT_THREADS]
   uint8_t* hist = s_hist + threadIdx.x;
   // bins cover d2 in [0, (1.5 cell)^2): whatever lies beyond cannot be certified by the R = 1 bound anyway (<= 2 cells)
   const double bin_scale = (double)NT_BINS / (2.25 * g.cell * g.cell);
@@ -287,8 +285,10 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
         cum += h;
         if (cum >= k) { B = bsel; break; }
       }
-      if (B >= 0 && cum <= cap) {
-        // pass 2: collect the candidates of bins 0..B (unsorted), then insertion sort by (d2, id)
+      if (B >= 0 && cum <= cap && T.staged) {
+        // pass 2: collect the candidates of bins 0..B as 16-bit codes (row << 14 | position in the row's run), unsorted,
+        // then insertion sort by (d2, id) with d2 recomputed from the staged tile.  2 bytes per entry instead of 12: the
+        // shared-memory footprint of a CTA drops from 56 to 25 KiB and twice as many warps hide the latencies.
         const double lim = (double)(B + 1);
         int cnt = 0;
 #pragma unroll
@@ -296,30 +296,41 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
           for (int j = 0; j < rn[rr3]; ++j) {
             const double d = dist2(rx[rr3][j], p.x, p.y);
             if (d != d || !(d * bin_scale < lim)) continue;
-            const int32_t id = ri[rr3][j];
-            if (reach && !((reach[id] >> wbit) & 1ull)) continue;
-            bd[cnt * NT_THREADS] = d; bi[cnt * NT_THREADS] = id;   // unsorted append: the warp stays together
+            if (reach && !((reach[ri[rr3][j]] >> wbit) & 1ull)) continue;
+            lst[cnt * NT_THREADS] = (uint16_t)((rr3 << 14) | j);     // unsorted append: the warp stays together
             ++cnt;
           }
+        auto cand_xy = [&](uint32_t code) -> double2 {
+          const uint32_t r = code >> 14, j = code & 0x3fffu;
+          return (r == 0 ? rx[0] : (r == 1 ? rx[1] : rx[2]))[j];
+        };
+        auto cand_id = [&](uint32_t code) -> int32_t {
+          const uint32_t r = code >> 14, j = code & 0x3fffu;
+          return (r == 0 ? ri[0] : (r == 1 ? ri[1] : ri[2]))[j];
+        };
         for (int i = 1; i < cnt; ++i) {                              // every lane sorts its k + few entries at the same time
-          const double d = bd[i * NT_THREADS];
-          const int32_t id = bi[i * NT_THREADS];
+          const uint32_t code = lst[i * NT_THREADS];
+          const double d = dist2(cand_xy(code), p.x, p.y);
           int pos = i;
           while (pos > 0) {
-            const double pd = bd[(pos - 1) * NT_THREADS];
-            const int32_t pi = bi[(pos - 1) * NT_THREADS];
-            if (!(d < pd || (d == pd && id < pi))) break;
-            bd[pos * NT_THREADS] = pd; bi[pos * NT_THREADS] = pi;
+            const uint32_t pc = lst[(pos - 1) * NT_THREADS];
+            const double pd = dist2(cand_xy(pc), p.x, p.y);
+            if (!(d < pd || (d == pd && cand_id(code) < cand_id(pc)))) break;
+            lst[pos * NT_THREADS] = (uint16_t)pc;
             --pos;
           }
-          bd[pos * NT_THREADS] = d; bi[pos * NT_THREADS] = id;
+          lst[pos * NT_THREADS] = (uint16_t)code;
         }
-        if (cnt >= k && bd[(k - 1) * NT_THREADS] < ring_lower_bound2(g, p.x, p.y, cx, T.cy, 1)) {
-          for (int j = 0; j < k; ++j) {
-            out_ids[(int64_t)t * k + j] = bi[j * NT_THREADS];
-            if (out_dist) out_dist[(int64_t)t * k + j] = __dsqrt_rn(bd[j * NT_THREADS]);
+        if (cnt >= k) {
+          const double dk = dist2(cand_xy(lst[(k - 1) * NT_THREADS]), p.x, p.y);
+          if (dk < ring_lower_bound2(g, p.x, p.y, cx, T.cy, 1)) {
+            for (int j = 0; j < k; ++j) {
+              const uint32_t code = lst[j * NT_THREADS];
+              out_ids[(int64_t)t * k + j] = cand_id(code);
+              if (out_dist) out_dist[(int64_t)t * k + j] = __dsqrt_rn(dist2(cand_xy(code), p.x, p.y));
+            }
+            done = true;
           }
-          done = true;
         }
       }
       (void)n_far;
@@ -402,7 +413,7 @@ int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64
   NtBins B;
   int32_t rc = nt_bin<true>(ctx, g, q_dev, nullptr, m, &B);
   if (rc) return rc;
-  const size_t smem = (size_t)NT_CAP_KNN * 16 + (size_t)(k + NT_SLACK) * NT_THREADS * 12 + (size_t)(NT_CAP_KNN + 24) * 4 + (size_t)NT_BINS * NT_THREADS;
+  const size_t smem = (size_t)NT_CAP_KNN * 16 + (size_t)(NT_CAP_KNN + 24) * 4 + (size_t)(k + NT_SLACK) * NT_THREADS * 2 + (size_t)NT_BINS * NT_THREADS;
   static bool attr_set[16] = {};
   if (!attr_set[ctx->device & 15]) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(nt_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
