@@ -168,6 +168,28 @@ int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const
 int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_t* out_belief, int32_t* out_parent,
                              uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost);
 
+/* ------------------------------------------------------------------ policy refinement (pto_policy_refiner.rs)
+ * PTOPolicyRefiner::is_transition_valid (pto_policy_refiner.rs:395-423), batched: out_valid[i] = 1 iff both end states are
+ * valid, the transition from -> to is valid with validity id v, and compat_row[v] != 0, where compat_row[n_validities] is
+ * compatibilities[belief_state_id] (compute_compatibility, common.rs:266-276).  Where the reference would panic on element i,
+ * out_valid[i] = 0 and out_status[i] (nullable) carries the panic code; otherwise out_status[i] = 0. */
+int32_t porrt_transition_valid(porrt_ctx* ctx, const double* from_xy, const double* to_xy, int64_t n,
+                               const uint8_t* compat_row, uint8_t* out_valid, int32_t* out_status);
+/* PTOPolicyRefiner::partial_shortcut (pto_policy_refiner.rs:158-206) on one path piece: states_xy[2 * n_states] is updated in
+ * place.  The trial sequence is the one a DiscreteSampler seeded with sampler_seed draws (the reference uses
+ * DiscreteSampler::new(), seed 0); trials are evaluated in speculative waves on the device and replayed in order, so states
+ * and *out_commits equal the sequential result.  *out_waves (nullable) = device round trips used.
+ * PORRT_ERR_PANIC if a transition check hits a reference panic. */
+int32_t porrt_partial_shortcut(porrt_ctx* ctx, double* states_xy, int32_t n_states, const uint8_t* compat_row,
+                               int32_t n_iterations, uint64_t sampler_seed, int32_t* out_commits, int32_t* out_waves);
+/* The same for all path pieces of a policy at once (refine_solution's loop, pto_policy_refiner.rs:102-115): piece p owns the
+ * states piece_ptr[p] .. piece_ptr[p+1]-1 of states_xy and the compatibility row compat_rows[p * n_validities ..] of its belief
+ * state; every piece draws from its own fresh sampler (same seed), exactly like the reference.  The waves of all pieces share
+ * one device batch, so the number of device round trips is that of the slowest piece.  out_commits[n_pieces] (nullable). */
+int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy, const int32_t* piece_ptr, int32_t n_pieces,
+                                     const uint8_t* compat_rows, int32_t n_iterations, uint64_t sampler_seed,
+                                     int32_t* out_commits, int32_t* out_waves);
+
 /* reachable_belief_states (map_io.rs:515-546 / map_shelves_io.rs:490-520): host-side closure over the uploaded map's
  * zones; out[cap * n_worlds]; *out_B = count (PORRT_ERR_CAPACITY if > cap). */
 int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B);

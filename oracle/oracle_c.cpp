@@ -505,3 +505,22 @@ API int64_t orc_pto_react_qmdp(void* p, const double* start, const double* belie
   }
   return tot;
 }
+
+
+// ---------------------------------------------------------------- pto_policy_refiner.rs
+API void orc_refiner_transition_valid_batch(void* mp, const double* from, const double* to, int64_t n, const uint8_t* compat_row, uint64_t n_validities, int64_t* out) {
+  GridMap* m = (GridMap*)mp;
+  std::vector<bool> row(n_validities);
+  for (uint64_t v = 0; v < n_validities; ++v) row[v] = compat_row[v] != 0;
+  for (int64_t i = 0; i < n; ++i) out[i] = refiner_is_transition_valid(*m, {from[2 * i], from[2 * i + 1]}, {to[2 * i], to[2 * i + 1]}, row);
+}
+API int64_t orc_refiner_partial_shortcut(void* mp, double* states, uint64_t L, const uint8_t* compat_row, uint64_t n_validities, uint64_t n_iterations) {
+  GridMap* m = (GridMap*)mp;
+  std::vector<bool> row(n_validities);
+  for (uint64_t v = 0; v < n_validities; ++v) row[v] = compat_row[v] != 0;
+  std::vector<State> st(L);
+  for (uint64_t k = 0; k < L; ++k) st[k] = {states[2 * k], states[2 * k + 1]};
+  const int64_t rc = refiner_partial_shortcut(*m, st, row, (size_t)n_iterations);
+  for (uint64_t k = 0; k < L; ++k) { states[2 * k] = st[k][0]; states[2 * k + 1] = st[k][1]; }
+  return rc;
+}

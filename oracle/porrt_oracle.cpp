@@ -888,4 +888,55 @@ bool PTO::react_qmdp(State start, const BeliefState& belief, double horizon, std
   return true;
 }
 
+// ============================================================== pto_policy_refiner.rs (partial shortcut)
+int64_t refiner_is_transition_valid(const GridMap& m, const State& from, const State& to, const std::vector<bool>& compat_row) {
+  const int64_t fv = m.state_validity(from);       // :396
+  if (fv < -1) return fv;
+  const int64_t tv = m.state_validity(to);         // :397
+  if (tv < -1) return tv;
+  if (fv < 0 || tv < 0) return 0;                  // :399 `if let (Some, Some)` ... else false
+  const int64_t v = m.transition_validator(from, to);   // :414
+  if (v < -1) return v;
+  if (v < 0) return 0;                             // None => false (:418)
+  return compat_row[(size_t)v] ? 1 : 0;            // :417
+}
+
+int64_t refiner_partial_shortcut(const GridMap& m, std::vector<State>& states, const std::vector<bool>& compat_row, size_t n_iterations) {
+  auto interpolate = [](double a, double b, double lambda) { return a * (1.0 - lambda) + b * lambda; };   // :159-161
+  if (states.size() <= 2) return 0;                // :163-165
+  const size_t joint_dim = 2;                      // tree.nodes.first().state.len()
+  DiscreteSampler sampler;                         // :169 DiscreteSampler::new()
+  int64_t commits = 0;
+  for (size_t it = 0; it < n_iterations; ++it) {
+    const size_t joint = (size_t)sampler.sample(joint_dim);                                   // :172
+    const size_t a = (size_t)sampler.sample(states.size() - 2);                               // :173
+    const size_t b = a + 2 + (size_t)sampler.sample(states.size() - a - 2);                   // :174
+    const State sa = states[a], sb = states[b];
+    std::vector<State> sc;                                                                    // :182-190
+    for (size_t j = a; j < b; ++j) {
+      const double lambda = (double)(j - a) / (double)(b - a);
+      State s = states[j];
+      s[joint] = interpolate(sa[joint], sb[joint], lambda);
+      sc.push_back(s);
+    }
+    bool should_commit = true;                                                                // :193-197 (short-circuit `&&`)
+    for (size_t k = 0; k + 1 < sc.size(); ++k) {
+      if (!should_commit) break;
+      const int64_t r = refiner_is_transition_valid(m, sc[k], sc[k + 1], compat_row);
+      if (r < 0) return r;
+      should_commit = r == 1;
+    }
+    if (should_commit) {
+      const int64_t r = refiner_is_transition_valid(m, sc.back(), sb, compat_row);
+      if (r < 0) return r;
+      should_commit = r == 1;
+    }
+    if (should_commit) {                                                                      // :200-204
+      for (size_t j = a; j < b; ++j) states[j] = sc[j - a];
+      ++commits;
+    }
+  }
+  return commits;
+}
+
 }  // namespace orc

@@ -187,6 +187,14 @@ struct Policy { std::vector<PolicyNode> nodes; std::vector<size_t> leafs; double
 bool extract_policy(const BeliefGraph& g, const std::vector<double>& costs, Policy& out);  // :184-267
 
 // ---------------------------------------------------------------- planners
+// ---------------------------------------------------------------- pto_policy_refiner.rs (partial shortcut)
+// is_transition_valid (pto_policy_refiner.rs:395-423): both end states valid, transition valid, and the belief compatible
+// with the transition's validity.  Returns 1 / 0, or the (negative) panic code the reference would hit first.
+int64_t refiner_is_transition_valid(const GridMap& m, const State& from, const State& to, const std::vector<bool>& compat_row);
+// partial_shortcut (pto_policy_refiner.rs:158-206) on one path piece: `states` is modified in place; returns the number of
+// committed shortcuts, or a negative panic code.  The sampler is a fresh DiscreteSampler::new() (seed 0) like in the reference.
+int64_t refiner_partial_shortcut(const GridMap& m, std::vector<State>& states, const std::vector<bool>& compat_row, size_t n_iterations);
+
 struct PRM {  // prm.rs
   const GridMap* fns;
   ContinuousSampler sampler;

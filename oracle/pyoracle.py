@@ -71,6 +71,8 @@ _SIGS = {
     "orc_pto_compute_expected_costs": (C.c_int, [vp, vp]), "orc_pto_final_belief_nodes": (i64, [vp, vp, i64]),
     "orc_pto_extract_policy": (vp, [vp]), "orc_pto_plan_qmdp": (C.c_int, [vp, vp]),
     "orc_pto_react_qmdp": (i64, [vp, vp, vp, f64, vp, vp, i64]),
+    "orc_refiner_transition_valid_batch": (None, [vp, vp, vp, i64, vp, u64, vp]),
+    "orc_refiner_partial_shortcut": (i64, [vp, vp, u64, vp, u64, u64]),
 }
 
 
@@ -225,6 +227,21 @@ class GridMap:
         tot = i64()
         lib().orc_edge_pixel_counts(self.h, P(f64a(frm)), P(f64a(to)), len(frm), C.byref(tot))
         return tot.value
+
+    def refiner_transition_valid(self, frm, to, compat_row):
+        """pto_policy_refiner.rs:395-423 is_transition_valid, batched: 1 / 0 / negative panic code"""
+        frm, to = f64a(frm), f64a(to)
+        row = np.ascontiguousarray(np.asarray(compat_row, dtype=np.uint8))
+        out = np.empty(len(frm), np.int64)
+        lib().orc_refiner_transition_valid_batch(self.h, P(frm), P(to), len(frm), P(row), len(row), P(out))
+        return out
+
+    def refiner_partial_shortcut(self, states, compat_row, n_iterations):
+        """pto_policy_refiner.rs:158-206 partial_shortcut on one path piece -> (new states, commits or panic code)"""
+        st = f64a(states).copy()
+        row = np.ascontiguousarray(np.asarray(compat_row, dtype=np.uint8))
+        rc = lib().orc_refiner_partial_shortcut(self.h, P(st), len(st), P(row), len(row), int(n_iterations))
+        return st, int(rc)
 
     def visible_zones(self, xy):
         xy = f64a(xy).reshape(-1, 2)

@@ -32,6 +32,9 @@ SIGNATURES = {
     "porrt_state_validity_dev": (i32, [vp, vp, i64, vp]),
     "porrt_edge_validity_dev": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_visibility_dev": (i32, [vp, vp, i64, vp, vp]),
+    "porrt_transition_valid": (i32, [vp, vp, vp, i64, vp, vp, vp]),
+    "porrt_partial_shortcut": (i32, [vp, vp, i32, vp, i32, C.c_uint64, pp(i32), pp(i32)]),
+    "porrt_partial_shortcut_batch": (i32, [vp, vp, vp, i32, vp, i32, C.c_uint64, vp, pp(i32)]),
     "porrt_vertices_set": (i32, [vp, vp, i64, f64]),
     "porrt_vertices_set_dev": (i32, [vp, vp, i64, f64, vp, vp]),
     "porrt_vertices_count": (i32, [vp, pp(i64)]),

@@ -170,6 +170,42 @@ class _GridDomain:
         self.ctx.check(self.ctx.lib.porrt_edge_validity(self.ctx.h, _p(f), _p(t), len(f), _p(out), _p(masks)))
         return (out, masks) if want_masks else out
 
+    def is_transition_valid(self, from_xy, to_xy, compat_row):
+        """PTOPolicyRefiner::is_transition_valid (pto_policy_refiner.rs:395-423), batched -> (valid u8, status i32)"""
+        self._need()
+        f, t = _f64(from_xy, 2), _f64(to_xy, 2)
+        row = np.ascontiguousarray(np.asarray(compat_row, dtype=np.uint8))
+        assert len(f) == len(t) and len(row) == self.n_validities
+        valid = np.empty(len(f), np.uint8)
+        status = np.empty(len(f), np.int32)
+        self.ctx.check(self.ctx.lib.porrt_transition_valid(self.ctx.h, _p(f), _p(t), len(f), _p(row), _p(valid), _p(status)))
+        return valid, status
+
+    def partial_shortcut(self, states, compat_row, n_iterations, sampler_seed=0):
+        """PTOPolicyRefiner::partial_shortcut (pto_policy_refiner.rs:158-206) on one path piece
+        -> (refined states, committed shortcuts, device round trips)"""
+        self._need()
+        st = _f64(states, 2).copy()
+        row = np.ascontiguousarray(np.asarray(compat_row, dtype=np.uint8))
+        assert len(row) == self.n_validities
+        commits, waves = C.c_int32(), C.c_int32()
+        self.ctx.check(self.ctx.lib.porrt_partial_shortcut(self.ctx.h, _p(st), len(st), _p(row), int(n_iterations), int(sampler_seed),
+                                                           C.byref(commits), C.byref(waves)))
+        return st, commits.value, waves.value
+
+    def partial_shortcut_batch(self, pieces, compat_rows, n_iterations, sampler_seed=0):
+        """partial_shortcut for all path pieces of a policy in shared device waves -> (list of refined pieces, commits[], waves)"""
+        self._need()
+        ptr = np.zeros(len(pieces) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(p) for p in pieces])
+        st = np.ascontiguousarray(np.concatenate([_f64(p, 2) for p in pieces])) if len(pieces) else np.zeros((0, 2))
+        rows = np.ascontiguousarray(np.asarray(compat_rows, dtype=np.uint8).reshape(len(pieces), self.n_validities))
+        commits = np.zeros(len(pieces), np.int32)
+        waves = C.c_int32()
+        self.ctx.check(self.ctx.lib.porrt_partial_shortcut_batch(self.ctx.h, _p(st), _p(ptr), len(pieces), _p(rows), int(n_iterations),
+                                                                 int(sampler_seed), _p(commits), C.byref(waves)))
+        return [st[ptr[k]:ptr[k + 1]].copy() for k in range(len(pieces))], commits, waves.value
+
     def visible_zones(self, xy):
         """geometric part of observe(): (zone bitmask, status) per state"""
         self._need()

@@ -1,6 +1,6 @@
 """Differential fuzz of the edge / state / visibility kernels against the oracle: random map sizes (incl. sides that are not
 multiples of 16), both domains, dense / touching zones, gray pixels without zone ids, long and degenerate edges, end points
-outside the map.  usage: fuzz_edges.py [rounds] [seed]"""
+outside the map.  usage: fuzz_edges.py [rounds] [seed] [edges per round]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,6 +9,7 @@ from oracle import pyoracle as O
 
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+n_edges = int(sys.argv[3]) if len(sys.argv) > 3 else 150_000
 rng = np.random.default_rng(seed)
 ctx = P.Context(0)
 bad = 0
@@ -45,7 +46,7 @@ for it in range(rounds):
     omap = O.GridMap(occ, zones, low, up, kind, vis)
     pmap = (P.MapShelfDomain if kind == P.SHELF else P.Map)(ctx, occ, low, up)
     pmap.add_zones(zones, vis)
-    n = 150_000
+    n = n_edges
     a = rng.uniform(-1.05, 1.05, (n, 2))
     L = np.where(rng.random(n) < 0.1, rng.uniform(0, 2.5, n), rng.uniform(0, 0.3, n))
     t = rng.uniform(0, 2 * np.pi, n)
@@ -61,7 +62,7 @@ for it in range(rounds):
     wv = pmap.world_validities_words()
     ok_m = np.array_equal(masks, np.where((want >= 0)[:, None], wv[np.clip(want, 0, None)], 0))
     ok_s = np.array_equal(pmap.state_validity(a).astype(np.int64), omap.state_validity(a))
-    wm, wp = omap.visible_zones(a[:20000]); gm, gs = pmap.visible_zones(a[:20000])
+    nv = min(20000, n); wm, wp = omap.visible_zones(a[:nv]); gm, gs = pmap.visible_zones(a[:nv])
     ok_v = np.array_equal(gm, wm) and np.array_equal(gs.astype(np.int64), wp)
     codes = {int(c): int((want == c).sum()) for c in np.unique(want)}
     print("round %2d %s %4dx%-4d zones %d: edges %s masks %s states %s visibility %s  %s" % (it, "SHELF" if kind == P.SHELF else "DOOR ", H, W, nz, ok_e, ok_m, ok_s, ok_v, codes), flush=True)

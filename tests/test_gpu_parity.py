@@ -560,3 +560,78 @@ def test_build_belief_graph_mock(ctx):
     typ_o, bid, rp_b, col_b = pto.belief_graph.export()
     assert list(col_b[rp_b[6]:rp_b[7]]) == [7, 8]       # observation transitions (pto.rs:579)
     assert plan.type[2, 0] == P.NODE_OBSERVATION
+
+
+# ---------------------------------------------------------------------------------------------- policy refinement
+def _path_through_free_space(omap, rng, n_states, step):
+    """a jagged polyline of valid states (what a policy path piece looks like before refinement)"""
+    for _ in range(1000):
+        p = rng.uniform(-0.9, 0.9, 2)
+        if omap.state_validity(p[None])[0] >= 0:
+            break
+    pts = [p]
+    while len(pts) < n_states:
+        q = np.clip(pts[-1] + rng.uniform(-step, step, 2), -0.95, 0.95)
+        if omap.state_validity(q[None])[0] >= 0 and omap.edge_validity(pts[-1][None], q[None])[0] >= 0:
+            pts.append(q)
+    return np.array(pts)
+
+
+def test_refiner_is_transition_valid(ctx):
+    """pto_policy_refiner.rs:395-423, batched, incl. the order in which the reference's panics would fire"""
+    occ, zones = util.small_door_map(512, 3)
+    occ[40:44, 40:120] = 77                                    # gray without zone id: unwrap panic
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1.1, 1.1, (60_000, 2))
+    b = a + rng.uniform(-0.08, 0.08, (60_000, 2))
+    for compat in ([1, 1, 1, 1], [0, 1, 0, 1], [1, 0, 0, 0]):
+        want = omap.refiner_transition_valid(a, b, compat)
+        valid, status = pmap.is_transition_valid(a, b, compat)
+        np.testing.assert_array_equal(valid.astype(np.int64), (want == 1).astype(np.int64))
+        np.testing.assert_array_equal(status.astype(np.int64), np.where(want < 0, want, 0))
+    assert (want == 1).any() and (want == 0).any() and (want == O.PANIC_OOB).any() and (want == O.PANIC_ZONE_UNWRAP).any()
+
+
+@pytest.mark.parametrize("kind", ["door", "shelf"])
+def test_refiner_partial_shortcut(ctx, kind):
+    """pto_policy_refiner.rs:158-206 on stand-in maps: the speculative waves must reproduce the sequential trial-by-trial
+    result bit for bit (states and number of commits), with far fewer device round trips than trials"""
+    rng = np.random.default_rng(9)
+    if kind == "door":
+        occ, zones = util.planning_door_map(200)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.5)
+        compats = ([1, 1, 1], [0, 1, 1], [1, 0, 1])        # validities: zone 0, zone 1, free
+    else:
+        occ, zones = synth.shelf_map(200, n_rects=10, n_zones=4, seed=5)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+        compats = ([1],)
+    total_commits = waves_sum = trials_sum = 0
+    for n_states, n_it in ((3, 50), (12, 400), (40, 1500), (90, 600)):
+        path = _path_through_free_space(omap, rng, n_states, 0.08)
+        for compat in compats:
+            want_states, want_commits = omap.refiner_partial_shortcut(path, compat, n_it)
+            assert want_commits >= 0
+            got_states, commits, waves = pmap.partial_shortcut(path, compat, n_it)
+            np.testing.assert_array_equal(got_states, want_states)      # bit-exact f64
+            assert commits == want_commits
+            assert 1 <= waves <= n_it
+            total_commits += commits
+            waves_sum += waves; trials_sum += n_it
+    assert total_commits > 20
+    assert waves_sum * 3 < trials_sum, (waves_sum, trials_sum)            # speculation pays: > 3 trials per device round trip
+    # all pieces of a policy in shared waves (refine_solution's loop): same results, round trips of the slowest piece only
+    pieces = [_path_through_free_space(omap, rng, n, 0.08) for n in (25, 2, 60, 9, 33, 3, 48)]
+    rows = [compats[k % len(compats)] for k in range(len(pieces))]
+    got, commits, waves = pmap.partial_shortcut_batch(pieces, rows, 500)
+    single_waves = []
+    for k, piece in enumerate(pieces):
+        want_states, want_commits = omap.refiner_partial_shortcut(piece, rows[k], 500)
+        np.testing.assert_array_equal(got[k], want_states)
+        assert commits[k] == max(want_commits, 0)
+        single_waves.append(pmap.partial_shortcut(piece, rows[k], 500)[2])
+    assert waves == max(single_waves) and waves < sum(single_waves)
+    # fewer than 3 states: nothing to do (pto_policy_refiner.rs:163-165)
+    st, c, w = pmap.partial_shortcut(path[:2], compats[0], 100)
+    np.testing.assert_array_equal(st, path[:2])
+    assert (c, w) == (0, 0)
