@@ -208,11 +208,42 @@ def side_measurements(ctx, pmap, args):
         import traceback
         ex["error"] = repr(e) + " | " + traceback.format_exc()[-400:]
     try:
+        ex["refiner"] = refiner_measurement(ctx, pmap)
+    except Exception as e:
+        import traceback
+        ex["refiner"] = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
+    try:
         ex["belief_c3"] = belief_measurement(ctx)
     except Exception as e:
         import traceback
         ex["belief_c3"] = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
     return ex
+
+
+def refiner_measurement(ctx, pmap, n_pieces=64, n_states=30, n_iterations=1000):
+    """PTOPolicyRefiner::partial_shortcut (SURVEY 8(f) rank 1) on the c5 map: n_pieces jagged path pieces (random walks through
+    free space), n_iterations trials each; the device runs the trials of all pieces in shared speculative waves, the oracle runs
+    them one by one like the reference.  States and commit counts must be identical."""
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(12)
+    omap = O.GridMap(pmap.occ, pmap.zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
+    pieces = []
+    while len(pieces) < n_pieces:
+        starts = rng.uniform(-0.9, 0.9, (4000, 1, 2))
+        walks = np.clip(starts + np.cumsum(rng.uniform(-0.01, 0.01, (4000, n_states, 2)), 1), -0.99, 0.99)
+        a, b = walks[:, :-1].reshape(-1, 2), walks[:, 1:].reshape(-1, 2)
+        ok = (pmap.transition_validator(np.ascontiguousarray(a), np.ascontiguousarray(b)) >= 0).reshape(4000, n_states - 1).all(1)
+        ok &= (pmap.state_validity(np.ascontiguousarray(walks[:, 0])) >= 0)
+        pieces += [w for w in walks[ok]][: n_pieces - len(pieces)]
+    rows = np.ones((n_pieces, pmap.n_validities), np.uint8)
+    pmap.partial_shortcut_batch(pieces[:4], rows[:4], 50)   # warm-up
+    t0 = time.perf_counter(); got, commits, waves = pmap.partial_shortcut_batch(pieces, rows, n_iterations); t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want = [omap.refiner_partial_shortcut(p, rows[k], n_iterations) for k, p in enumerate(pieces)]
+    t_cpu = time.perf_counter() - t0
+    exact = all(np.array_equal(got[k], want[k][0]) and commits[k] == want[k][1] for k in range(n_pieces))
+    return {"pieces": n_pieces, "states_per_piece": n_states, "trials_per_piece": n_iterations, "device_round_trips": int(waves),
+            "commits": int(commits.sum()), "gpu_ms": 1e3 * t_gpu, "cpu_oracle_ms_1thread": 1e3 * t_cpu, "bit_exact": bool(exact)}
 
 
 def belief_measurement(ctx, Z=8, n_min=5000):
