@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
         if (cum >= k) { B = bsel; break; }
       }
       if (B >= 0 && cum <= cap && T.staged) {
-        // pass 2: collect the candidates of bins 0..B as 16-bit codes (row << 14 | position in the row's run), unsorted,
+        // pass 2: collect the candidates of bins 0..B as 16-bit codes (index into the staged tile), unsorted,
         // then insertion sort by (d2, id) with d2 recomputed from the staged tile.  2 bytes per entry instead of 12: the
         // shared-memory footprint of a CTA drops from 56 to 25 KiB and twice as many warps hide the latencies.
         const double lim = (double)(B + 1);
@@ -297,17 +297,13 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
             const double d = dist2(rx[rr3][j], p.x, p.y);
             if (d != d || !(d * bin_scale < lim)) continue;
             if (reach && !((reach[ri[rr3][j]] >> wbit) & 1ull)) continue;
-            lst[cnt * NT_THREADS] = (uint16_t)((rr3 << 14) | j);     // unsorted append: the warp stays together
+            lst[cnt * NT_THREADS] = (uint16_t)(rx[rr3] - s_xy + j);    // unsorted append: the warp stays together
             ++cnt;
           }
-        auto cand_xy = [&](uint32_t code) -> double2 {
-          const uint32_t r = code >> 14, j = code & 0x3fffu;
-          return (r == 0 ? rx[0] : (r == 1 ? rx[1] : rx[2]))[j];
-        };
-        auto cand_id = [&](uint32_t code) -> int32_t {
-          const uint32_t r = code >> 14, j = code & 0x3fffu;
-          return (r == 0 ? ri[0] : (r == 1 ? ri[1] : ri[2]))[j];
-        };
+        // code = index into the staged coordinates; the staged ids sit at a per-row offset from it (16-byte phase of the copy)
+        const int x1 = T.xoff[1], x2 = T.xoff[2], d0 = T.ioff[0] - T.xoff[0], d1 = T.ioff[1] - T.xoff[1], d2o = T.ioff[2] - T.xoff[2];
+        auto cand_xy = [&](uint32_t code) -> double2 { return s_xy[code]; };
+        auto cand_id = [&](uint32_t code) -> int32_t { return s_id[(int)code + ((int)code >= x2 ? d2o : ((int)code >= x1 ? d1 : d0))]; };
         for (int i = 1; i < cnt; ++i) {                              // every lane sorts its k + few entries at the same time
           const uint32_t code = lst[i * NT_THREADS];
           const double d = dist2(cand_xy(code), p.x, p.y);
