@@ -236,7 +236,7 @@ def refiner_measurement(ctx, pmap, n_pieces=64, n_states=30, n_iterations=1000):
         ok &= (pmap.state_validity(np.ascontiguousarray(walks[:, 0])) >= 0)
         pieces += [w for w in walks[ok]][: n_pieces - len(pieces)]
     rows = np.ones((n_pieces, pmap.n_validities), np.uint8)
-    pmap.partial_shortcut_batch(pieces[:4], rows[:4], 50)   # warm-up
+    pmap.partial_shortcut_batch(pieces, rows, n_iterations)   # warm-up at full size: pinned / device staging is allocated here
     t0 = time.perf_counter(); got, commits, waves = pmap.partial_shortcut_batch(pieces, rows, n_iterations); t_gpu = time.perf_counter() - t0
     t0 = time.perf_counter()
     want = [omap.refiner_partial_shortcut(p, rows[k], n_iterations) for k, p in enumerate(pieces)]

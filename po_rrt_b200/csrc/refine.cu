@@ -15,6 +15,7 @@
 // The sampler is rand_pcg 0.3 Pcg64 (Lcg128Xsl64) seeded by rand_core 0.6 seed_from_u64 and rand 0.8's
 // UniformInt<usize>::sample_single, restated from their published algorithms (the crates are not vendored in the reference).
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "common.cuh"
@@ -197,7 +198,10 @@ PORRT_API int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy
   CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, compat_rows, (size_t)n_pieces * nv, cudaMemcpyHostToDevice, st));
 
   int waves = 0;
+  double t_build = 0, t_dev = 0, t_replay = 0;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (;;) {
+    const double tb0 = now();
     // ---- build: the next <= SHORTCUT_WAVE trials of every unfinished piece, on a SPECULATIVE copy of its path: every trial
     // is assumed to end like most recent ones did (commit / reject), so later trials of the wave see the states they will
     // most likely see.  Shortcut states (:182-190) and transitions (:193-197) of all pieces form one device batch.
@@ -235,6 +239,8 @@ PORRT_API int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy
       pc.snap_at[(size_t)pc.K] = pc.snap.size();
     }
     if (m == 0) break;                 // every piece has run all its trials
+    const double tb1 = now();
+    t_build += tb1 - tb0;
     CUDA_TRY(ctx, cudaMemcpyAsync(d_from, h_from, m * 16, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_to, h_to, m * 16, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_row, h_row, m * 4, cudaMemcpyHostToDevice, st));
@@ -244,6 +250,8 @@ PORRT_API int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy
     CUDA_TRY(ctx, cudaMemcpyAsync(h_status, d_status, m * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     ++waves;
+    const double tb2 = now();
+    t_dev += tb2 - tb1;
     // ---- replay, piece by piece, in trial order on the REAL path.  A trial's device results are usable iff the states it
     // read while the wave was built are bit-identical to the real ones now; the first trial that fails this test starts
     // the piece's next wave.
@@ -276,7 +284,9 @@ PORRT_API int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy
       pc.i0 += w;                      // w >= 1 whenever K >= 1: the first trial of a wave is built from the real path
       if (out_commits) out_commits[piece_of[q]] = pc.commits;
     }
+    t_replay += now() - tb2;
   }
+  if (getenv("PORRT_DEBUG")) fprintf(stderr, "[porrt] partial_shortcut: %d waves, build %.2f ms, device %.2f ms, replay %.2f ms\n", waves, t_build, t_dev, t_replay);
   if (out_waves) *out_waves = waves;
   return PORRT_OK;
 }
