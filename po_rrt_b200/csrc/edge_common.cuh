@@ -11,10 +11,14 @@
 #ifndef E3_FINE_MODE
 #define E3_FINE_MODE 0       // 1: per-pixel IMAD.HI instead of the 64-bit running sum (slower, same reason)
 #endif
+#ifndef E3_TWO_PHASE
+#define E3_TWO_PHASE 1     // first item of every edge by its own lane, remaining items only for edges not yet blocked
+#endif
 #define E3_LOG_BS 4
 #define E3_BS 16
 #ifndef E3_G
-#define E3_G 8              // consecutive strips of one edge per lane and round (<= 8: one class nibble each)
+#define E3_G 7              // consecutive strips of one edge per lane and round (<= 8: one class nibble each); measured with the
+                            // two-phase pass 1 on c5: G = 4 / 5 / 6 / 7 / 8 -> 0.768 / 0.754 / 0.721 / 0.710 / 0.760 ms
 #endif
 #define E3_QB 512           // bitmap-queue entries per warp (a round adds at most 32 * E3_G)
 #define E3_QG 256           // byte-queue entries per warp
