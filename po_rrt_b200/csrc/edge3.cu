@@ -224,9 +224,16 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       const int d_major = major_i ? di : dj, d_minor = major_i ? dj : di;
       c0 = major_i ? (int)ai : (int)aj; n0 = major_i ? (int)aj : (int)ai;
       dirs = (major_i ? 1 : 0) | (d_major < 0 ? 2 : 0) | (d_minor < 0 ? 4 : 0);
-      if (!my_flags) {  // the start pixel's block blocks entirely: Obstacle at k = 0, nothing to walk
+      if (!my_flags) {  // the start pixel blocks: Obstacle at k = 0, nothing to walk (the reference returns at the first pixel)
         const int sb = m.plane_guard + ((int)ai >> E3_LOG_BS) * cw + ((int)aj >> E3_LOG_BS);
-        pre_blocked = plane_class<false>(smem, (uint32_t)sb) == K_BLOCKED ? 1u : 0u;
+        const uint32_t sc = plane_class<false>(smem, (uint32_t)sb);
+        pre_blocked = sc == K_BLOCKED ? 1u : 0u;
+#if E3_START_PIXEL
+        if (sc == K_MIXED || sc == K_SPECIAL) {   // one byte of the fused grid settles the edges that start inside an obstacle
+          const uint32_t code = __ldg(m.grid + tile_addr((int)ai, (int)aj, m.tiles_x));
+          pre_blocked = (KIND == PORRT_DOMAIN_SHELF ? code != 255 : code == 0) ? 1u : 0u;
+        }
+#endif
       }
       if (!my_flags && !pre_blocked) {
         if (dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
