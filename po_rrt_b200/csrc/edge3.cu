@@ -21,8 +21,6 @@
 // already known to be blocked are dropped.  Blocks containing gray pixels (door zones: zone ids and the reference's
 // panics matter) go to a per-pixel pass over the fused byte grid; whenever the ORDER of events along the line could
 // matter the edge is re-walked sequentially (walk_sequential), which is what makes the panic codes bit-exact.
-#include <type_traits>
-
 #include "edge_common.cuh"
 
 // Per-edge record in shared memory, three 16-byte chunks.  The minor axis is MIRRORED for edges whose minor step is
@@ -266,12 +264,12 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     wm.obst[lane] = pre_blocked; wm.zmin[lane] = 255; wm.zmax[lane] = 0;
     // items = groups of E3_G consecutive strips of one edge.  One lane looks at one item per round: classes of the <= 2
     // blocks of each strip from the plane in shared memory.
-    auto process_item = [&](auto ng_tag, const int e, const int ts_first, const bool has_item) {
-      constexpr int NG = decltype(ng_tag)::value;                    // strips in this item
+    const int my_items = (n_strips + E3_G - 1) / E3_G;
+    auto process_item = [&](const int e, const int item, const bool has_item) {
       // per strip g the one-hot classes of its blocks OR-ed: bit 4g+1 mixed, 4g+2 blocked, 4g+3 special (4g: free).
       // Branch-free: strips past the end of the edge read the guard zone / neighbouring blocks and are masked out.
       uint32_t cls = 0;
-      const int ts0 = has_item ? ts_first : 0;
+      const int ts0 = has_item ? item * E3_G : 0;
       {
         const uint4 q0 = wm.rec[0][e], q1 = wm.rec[1][e];
         const int sm_ = (int)q0.z, sn_ = (int)q0.w, e_dxo = (int)q1.y, e_n0m = (int)q1.x;
@@ -280,7 +278,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         int lo_raw = (int)q0.x + ts0 * E3_BS;
         int idx_m = (int)q0.y + ts0 * sm_;
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
+        for (int g = 0; g < E3_G; ++g) {
           // only an edge's first strip starts before k = 0; k_lo past the end (masked strips) stays inside the guards.
           // Shifts by constants are written as multiply-high so that they issue on the FMA pipe: the ALU pipe is the
           // kernel's bound (ncu: math-pipe throttle).
@@ -292,7 +290,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
           cls += ((1u << ca) | (1u << cb)) * (1u << (4 * g));
           lo_raw += E3_BS; idx_m += sm_;
         }
-        cls &= left >= NG ? 0xffffffffu : ((1u << (4 * max(left, 0))) - 1u);
+        cls &= left >= E3_G ? 0xffffffffu : ((1u << (4 * max(left, 0))) - 1u);
       }
       const uint32_t blocked = cls & 0x44444444u, special = (cls >> 3) & 0x11111111u;
       if (blocked) wm.obst[e] = 1;                                 // the bitmaps cannot change the outcome any more
@@ -310,12 +308,12 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         qb_n += __shfl_sync(0xffffffffu, sc, 31);
         const uint32_t ent0 = (uint32_t)e | ((uint32_t)ts0 << 5);
 #pragma unroll
-        for (int g = 0; g < NG; ++g)
+        for (int g = 0; g < E3_G; ++g)
           if (want & (1u << (4 * g))) wm.qb[pb++] = ent0 + ((uint32_t)g << 5);
       }
       if (__any_sync(0xffffffffu, special != 0)) {                 // rare: strips through gray pixels
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
+        for (int g = 0; g < E3_G; ++g) {
           const unsigned bal = __ballot_sync(0xffffffffu, (special >> (4 * g)) & 1u);
           if ((special >> (4 * g)) & 1u) wm.qg[qg_n + __popc(bal & lt_mask)] = (uint32_t)e | ((uint32_t)(ts0 + g) << 5);
           qg_n += __popc(bal);
@@ -328,15 +326,14 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     // change the result (the reference returns at it), so their remaining items are never looked at.
     const bool may_overflow = true;
     __syncwarp();
-    process_item(std::integral_constant<int, E3_G0>(), lane, 0, n_strips > 0);
+    process_item(lane, 0, my_items > 0);
     __syncwarp();
-    const int my_rem = n_strips > E3_G0 ? (n_strips - E3_G0 + E3_G - 1) / E3_G : 0;   // items behind the first one
 #if E3_TWO_PHASE == 2
     // resolving the first items' bitmaps now lets more edges finish early, but the extra, half-empty drain costs more than
     // it saves: measured 0.905 ms against 0.760 ms
-    if (__any_sync(0xffffffffu, my_rem > 0) && (qb_n | qg_n)) drain();
+    if (__any_sync(0xffffffffu, my_items > 1) && (qb_n | qg_n)) drain();
 #endif
-    int rem = wm.obst[lane] != 0 ? 0 : my_rem;
+    int rem = (my_items <= 1 || wm.obst[lane] != 0) ? 0 : my_items - 1;
     int incl = rem;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -345,7 +342,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     for (int w0 = 0; w0 < total; w0 += 32) {
-      if (may_overflow && (qb_n > E3_QB - 32 * 8 || qg_n > E3_QG - 32 * 8)) drain();
+      if (may_overflow && (qb_n > E3_QB - 32 * E3_G || qg_n > E3_QG - 32 * E3_G)) drain();
       const int w = w0 + lane;
       int e = 0;                                                    // owner: the first lane whose inclusive sum exceeds w
 #pragma unroll
@@ -354,13 +351,12 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         if (v <= w) e += sft;
       }
       const int excl = __shfl_sync(0xffffffffu, incl - rem, e);
-      process_item(std::integral_constant<int, E3_G>(), e, E3_G0 + (w - excl) * E3_G, w < total);
+      process_item(e, 1 + w - excl, w < total);
       __syncwarp();
     }
 #else
     // every lane owns at least one (possibly empty) item so that the inclusive prefix sums are strictly increasing and the
     // owner of a flattened position can be ranked with a bitmask
-    const int my_items = (n_strips + E3_G - 1) / E3_G;
     int incl = max(1, my_items);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -371,13 +367,13 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     const bool may_overflow = total * E3_G > min(E3_QB, E3_QG);     // warp-uniform
     __syncwarp();
     for (int w0 = 0; w0 < total; w0 += 32) {
-      if (may_overflow && (qb_n > E3_QB - 32 * 8 || qg_n > E3_QG - 32 * 8)) drain();
+      if (may_overflow && (qb_n > E3_QB - 32 * E3_G || qg_n > E3_QG - 32 * E3_G)) drain();
       const int d = incl - w0;                                    // edge `lane` ends before window position d
       const int e_base = __popc(__ballot_sync(0xffffffffu, d <= 0));
       const unsigned marks = __reduce_or_sync(0xffffffffu, (d >= 1 && d <= 32) ? (1u << (d - 1)) : 0u);
       const int e = min(31, e_base + __popc(marks & lt_mask));
       const int p_prev = __shfl_sync(0xffffffffu, incl, (e + 31) & 31);
-      process_item(std::integral_constant<int, E3_G>(), e, (w0 + lane - (e ? p_prev : 0)) * E3_G, w0 + lane < total);
+      process_item(e, w0 + lane - (e ? p_prev : 0), w0 + lane < total);
       __syncwarp();
     }
 #endif
@@ -481,9 +477,9 @@ int32_t edge3_build(porrt_ctx* ctx, cudaStream_t st) {
   MapDev& m = ctx->map;
   const int cw = (m.W + E3_BS - 1) / E3_BS, ch = (m.H + E3_BS - 1) / E3_BS;
   const size_t n_blocks = (size_t)cw * ch;
-  // guard zones of 9 block rows (class 0 = free) on both sides: the branch-free pass 1 reads up to 7 strips past the end
-  // of an edge, i.e. at most 8 block rows / columns outside the map
-  const int guard = (int)(((size_t)(8 + 1) * cw + 63) / 64 * 64);   // items have at most 8 strips
+  // guard zones of >= 4 block rows (class 0 = free) on both sides: the branch-free pass 1 reads up to E3_G - 1 strips
+  // past the end of an edge, i.e. at most E3_G block rows / columns outside the map
+  const int guard = (int)(((size_t)(E3_G + 1) * cw + 63) / 64 * 64);
   const size_t plane_bytes = ((((n_blocks + 2 * (size_t)guard + 15) / 16) * 4 + 15) / 16) * 16;
   CUDA_TRY(ctx, ctx->d_plane.ensure(plane_bytes));
   CUDA_TRY(ctx, ctx->d_bits.ensure(n_blocks * 32 * 4));

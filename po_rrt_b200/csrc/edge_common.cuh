@@ -23,9 +23,6 @@
 #define E3_G 7              // consecutive strips of one edge per lane and round (<= 8: one class nibble each); measured with the
                             // two-phase pass 1 on c5: G = 4 / 5 / 6 / 7 / 8 -> 0.768 / 0.754 / 0.721 / 0.710 / 0.760 ms
 #endif
-#ifndef E3_G0
-#define E3_G0 E3_G          // strips in the first item of an edge (round 0 of the two-phase pass 1)
-#endif
 #define E3_QB 512           // bitmap-queue entries per warp (a round adds at most 32 * E3_G)
 #define E3_QG 256           // byte-queue entries per warp
 #define E3_BIAS 65536ull
