@@ -26,7 +26,9 @@
 #define E3_QB 512           // bitmap-queue entries per warp (a round adds at most 32 * E3_G)
 #define E3_QG 256           // byte-queue entries per warp
 #define E3_BIAS 65536ull
+#ifndef E3_MAX_WARPS
 #define E3_MAX_WARPS 32
+#endif
 
 #define K_FREE 0u
 #define K_MIXED 1u          // blocking and free pixels, nothing else: the bitmap decides
