@@ -658,6 +658,91 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(GridDev g, const doubl
   if (KMAX == 1 && out_ties) out_ties[t] = ties;
 }
 
+// One WARP per query, for the few queries nn_tile.cu could not certify (sparse neighbourhoods: a wider ring is needed).  The
+// thread-per-query kernel above is latency bound there (one thread walks ~350 candidates through global memory: 0.3 ms for
+// 574 queries).  Lanes stride the candidates of every run of the ring, each lane keeps its own sorted list; after a ring the k
+// globally best are drawn from the 32 list heads (k warp-wide arg-min rounds) to test the stopping rule, and once more to write.
+template <int KMAX>
+__global__ void __launch_bounds__(KNN_THREADS) knn_warp_kernel(GridDev g, const double2* __restrict__ q, int64_t m, int k,
+                                                               const uint64_t* __restrict__ reach, const uint32_t* __restrict__ world,
+                                                               int32_t* __restrict__ out_ids, double* __restrict__ out_dist,
+                                                               int32_t* __restrict__ out_ties, const int32_t* __restrict__ list) {
+  __shared__ double s_d2[KMAX][KNN_THREADS];
+  __shared__ int32_t s_id[KMAX][KNN_THREADS];
+  const int lane = threadIdx.x & 31;
+  const int64_t wq = ((int64_t)blockIdx.x * KNN_THREADS + threadIdx.x) >> 5;
+  if (wq >= m) return;                       // whole warps leave together
+  const int64_t t = list ? list[wq] : wq;
+  const double2 p = q[t];
+  TopK<KMAX> top;
+  top.init(k, s_d2, s_id);
+  int32_t ties = 0;                          // k == 1: vertices at exactly this lane's best d2
+  const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+  // k rounds of "smallest (d2, id) among the lane heads"; returns the k-th best d2 (inf if fewer than k exist) and, when
+  // `write`, stores the sorted result
+  auto draw = [&](bool write) -> double {
+    int head = 0, found = 0;
+    double kth = INFINITY;
+    for (int j = 0; j < k; ++j) {
+      double d = head < top.cnt ? top.dist_at(head) : INFINITY;
+      int32_t id = head < top.cnt ? top.id_at(head) : 0x7fffffff;
+      int src = lane;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const int32_t oi = __shfl_xor_sync(0xffffffffu, id, o);
+        const int os = __shfl_xor_sync(0xffffffffu, src, o);
+        if (od < d || (od == d && oi < id)) { d = od; id = oi; src = os; }
+      }
+      const bool any = d < INFINITY || id != 0x7fffffff;
+      if (any) { ++found; kth = d; if (src == lane) ++head; }
+      if (write && lane == 0) {
+        out_ids[t * k + j] = any ? id : -1;
+        if (out_dist) out_dist[t * k + j] = any ? __dsqrt_rn(d) : INFINITY;
+      }
+    }
+    return found == k ? kth : INFINITY;
+  };
+  if (p.x == p.x && p.y == p.y) {
+    const int cx = cell_coord(p.x, g.org_x, g.inv_cell, g.cells_x), cy = cell_coord(p.y, g.org_y, g.inv_cell, g.cells_y);
+    const int maxR = max(max(cx, g.cells_x - 1 - cx), max(cy, g.cells_y - 1 - cy));
+    for (int R = 0; R <= maxR; ++R) {
+      for (int dy = -R; dy <= R; ++dy) {
+        const int yy = cy + dy;
+        if (yy < 0 || yy >= g.cells_y) continue;
+        const bool full_row = (dy == -R || dy == R);
+        for (int side = 0; side < (full_row || R == 0 ? 1 : 2); ++side) {
+          int x0, x1;
+          if (full_row || R == 0) { x0 = max(cx - R, 0); x1 = min(cx + R, g.cells_x - 1); }
+          else { x0 = x1 = side ? cx + R : cx - R; if (x0 < 0 || x0 >= g.cells_x) continue; }
+          const int64_t s = g.cell_start[(int64_t)yy * g.cells_x + x0], e = g.cell_start[(int64_t)yy * g.cells_x + x1 + 1];
+          for (int64_t kk = s + lane; kk < e; kk += 32) {
+            const double d = dist2(g.vxy[kk], p.x, p.y);
+            if (d <= top.worst() || top.cnt < k) {
+              const int32_t id = g.vid[kk];
+              if (!reach || ((reach[id] >> wbit) & 1ull)) {
+                if (KMAX == 1) {
+                  if (top.cnt == 0 || d < top.dist_at(0)) ties = 1;
+                  else if (d == top.dist_at(0)) ++ties;
+                }
+                if (d == d) top.push(d, id);
+              }
+            }
+          }
+        }
+      }
+      if (draw(false) < ring_lower_bound2(g, p.x, p.y, cx, cy, R)) break;   // warp-uniform
+    }
+  }
+  const double best = draw(true);
+  if (KMAX == 1 && out_ties) {               // ties of the lanes whose own best is the global best
+    int32_t tt = (top.cnt > 0 && top.dist_at(0) == best) ? ties : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
+    if (lane == 0) out_ties[t] = best < INFINITY ? tt : 0;
+  }
+}
+
 static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, const uint64_t* reach_mask, const uint32_t* world,
                         int32_t* out_ids, double* out_dist, int32_t* out_ties) {
   if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
@@ -690,7 +775,13 @@ static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, co
     if (rc) return rc;
     m_run = fb_n;
   }
-  if (m_run > 0) {
+  if (m_run > 0 && list && m_run <= 65536) {   // few hard queries left by the tiles: a warp each
+    const int blocks = div_up(m_run * 32, KNN_THREADS);
+    if (k == 1) knn_warp_kernel<1><<<blocks, KNN_THREADS, 0, st>>>(g, (const double2*)d_q, m_run, 1, d_reach, d_world, d_ids, d_dist, d_ties, list);
+    else if (k <= 8) knn_warp_kernel<8><<<blocks, KNN_THREADS, 0, st>>>(g, (const double2*)d_q, m_run, k, d_reach, d_world, d_ids, d_dist, nullptr, list);
+    else knn_warp_kernel<32><<<blocks, KNN_THREADS, 0, st>>>(g, (const double2*)d_q, m_run, k, d_reach, d_world, d_ids, d_dist, nullptr, list);
+    LAUNCH_CHECK(ctx);
+  } else if (m_run > 0) {
     if (k == 1) knn_kernel<1><<<div_up(m_run, KNN_THREADS), KNN_THREADS, 0, st>>>(g, (const double2*)d_q, m_run, 1, d_reach, d_world, d_ids, d_dist, d_ties, list);
     else if (k <= 8) knn_kernel<8><<<div_up(m_run, KNN_THREADS), KNN_THREADS, 0, st>>>(g, (const double2*)d_q, m_run, k, d_reach, d_world, d_ids, d_dist, nullptr, list);
     else knn_kernel<32><<<div_up(m_run, KNN_THREADS), KNN_THREADS, 0, st>>>(g, (const double2*)d_q, m_run, k, d_reach, d_world, d_ids, d_dist, nullptr, list);
