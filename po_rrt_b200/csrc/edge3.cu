@@ -236,14 +236,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
 #endif
       }
       if (!my_flags && !pre_blocked) {
-        if (dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
-          if (dyo == dxo) S = 0xFFFFFFFFu;
-          else {
-            const uint32_t d = (uint32_t)dxo, num = (uint32_t)dyo << 16;
-            const uint32_t q1 = num / d, r1 = num - q1 * d;
-            S = (q1 << 16) + ((r1 << 16) / d);
-          }
-        }
+        if (dxo > 0) S = slope_fixed_point(dyo, dxo);
         const int sgn = (dirs & 2) ? -1 : 1;
         const int b0 = c0 >> E3_LOG_BS, b1 = (c0 + sgn * dxo) >> E3_LOG_BS;
         n_strips = (b1 > b0 ? b1 - b0 : b0 - b1) + 1;

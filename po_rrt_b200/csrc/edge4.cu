@@ -240,14 +240,7 @@ edge_validity_v4_kernel(MapDev m, const double2* __restrict__ from, const double
           // the start pixel's block blocks entirely: Obstacle at k = 0, nothing to walk
           const int sb = guard + ((int)ai >> E3_LOG_BS) * cw + ((int)aj >> E3_LOG_BS);
           pre_blocked = plane_class<false>(smem, (uint32_t)sb) == K_BLOCKED ? 1u : 0u;
-          if (dxo > 0) {  // S = floor(dyo * 2^32 / dxo) by two 32-bit divisions (dyo <= dxo < 2^15)
-            if (dyo == dxo) S = 0xFFFFFFFFu;
-            else {
-              const uint32_t d = (uint32_t)dxo, num = (uint32_t)dyo << 16;
-              const uint32_t q1 = num / d, r1 = num - q1 * d;
-              S = (q1 << 16) + ((r1 << 16) / d);
-            }
-          }
+          if (dxo > 0) S = slope_fixed_point(dyo, dxo);
           const int n0m = (dirs & 4) ? (major_i ? cw : ch) * E3_BS - 1 - n0 : n0;
           N = (uint32_t)n0m | ((uint32_t)dxo << 16);
           C |= (uint32_t)c0 | ((uint32_t)dirs << 16);

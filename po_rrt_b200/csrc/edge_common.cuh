@@ -35,6 +35,25 @@
 #define K_BLOCKED 2u        // every pixel blocks
 #define K_SPECIAL 3u        // contains gray pixels (DOOR zones / gray without zone id): per-pixel pass on the byte grid
 
+// Fixed-point slope S ~ dy * 2^32 / dx for 0 <= dy <= dx < 2^15.  hi32(k * S + 2^16) == floor(k * dy / dx) for every
+// 0 <= k <= dx as long as |dy * 2^32 / dx - S| < 1.9, so S need not be the exact floor: one correctly
+// rounded reciprocal, one multiply and a saturating conversion (dy == dx -> 2^32 - 1) on the FP64 pipe replace two 32-bit
+// integer divisions (~40 ALU/FMA instructions, the pipes that bound the kernel).  E3_SLOPE_DIV = 1 keeps the divisions.
+// tests/test_oracle_golden.py::test_fixed_point_minor_offset_is_exact replays both variants in IEEE arithmetic.
+#ifndef E3_SLOPE_DIV
+#define E3_SLOPE_DIV 0
+#endif
+__device__ __forceinline__ uint32_t slope_fixed_point(int dy, int dx) {
+#if E3_SLOPE_DIV
+  if (dy == dx) return 0xFFFFFFFFu;
+  const uint32_t d = (uint32_t)dx, num = (uint32_t)dy << 16;
+  const uint32_t q1 = num / d, r1 = num - q1 * d;
+  return (q1 << 16) + ((r1 << 16) / d);
+#else
+  return __double2uint_rz(__dmul_rn(__dmul_rn((double)dy, 4294967296.0), __drcp_rn((double)dx)));
+#endif
+}
+
 // n' of pixel k = hi32(k * S + (n0m << 32 | 2^16))
 __device__ __forceinline__ int32_t minor_m(uint32_t k, uint32_t S, int32_t n0m) {
   return (int32_t)(((uint64_t)k * (uint64_t)S + (((uint64_t)(uint32_t)n0m << 32) | E3_BIAS)) >> 32);

@@ -364,15 +364,20 @@ def test_bresenham_doc_example_and_closed_form():
 
 
 def test_fixed_point_minor_offset_is_exact():
-    """edge3.cu / edge4.cu: floor(k*dy/dx) == hi32(k*S + 2^16) with S = min(floor(dy*2^32/dx), 2^32-1), for every
-    0 <= dy <= dx < 2^15 and 0 <= k <= dx.  Exhaustive for dx <= 160, all dy / sampled k for large dx."""
+    """edge3.cu / edge4.cu: floor(k*dy/dx) == hi32(k*S + 2^16) for every 0 <= dy <= dx < 2^15 and 0 <= k <= dx,
+    both for the exact S = min(floor(dy*2^32/dx), 2^32-1) and for the S the kernels compute on the FP64 pipe,
+    trunc_sat(dy * 2^32 * rn(1/dx)) -- replayed here in IEEE double arithmetic (numpy division and multiplication are correctly
+    rounded like __drcp_rn / __dmul_rn).  Exhaustive for dx <= 160, all dy / sampled k for large dx."""
     B = np.uint64(65536)
     for dx in list(range(1, 161)) + [255, 256, 257, 4095, 4096, 8191, 16383, 32767]:
         dy = np.arange(0, dx + 1, dtype=np.uint64)
         if dx > 160:
             dy = np.unique(np.concatenate([dy[:40], dy[-40:], dy[::max(1, dx // 97)]]))
-        S = np.minimum((dy << np.uint64(32)) // np.uint64(dx), np.uint64(0xFFFFFFFF))
         k = np.arange(0, dx + 1, dtype=np.uint64)
-        got = (k[None, :] * S[:, None] + B) >> np.uint64(32)
         want = (k[None, :] * dy[:, None]) // np.uint64(dx)
-        assert np.array_equal(got, want), dx
+        S_exact = np.minimum((dy << np.uint64(32)) // np.uint64(dx), np.uint64(0xFFFFFFFF))
+        S_fp = np.minimum(np.floor((dy.astype(np.float64) * 4294967296.0) * (1.0 / np.float64(dx))), 4294967295.0).astype(np.uint64)
+        assert (np.abs(S_fp.astype(np.int64) - S_exact.astype(np.int64)) <= 1).all()
+        for S in (S_exact, S_fp):
+            got = (k[None, :] * S[:, None] + B) >> np.uint64(32)
+            assert np.array_equal(got, want), dx
