@@ -606,6 +606,19 @@ __global__ void belief_type_kernel(BeliefDev g, uint8_t* __restrict__ type) {
   type[t] = ty;
 }
 
+__global__ void fill_inf_kernel(double* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = INFINITY;
+}
+__global__ void scatter_zero_kernel(double* __restrict__ d, const int64_t* __restrict__ idx, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[idx[i]] = 0.0;
+}
+// belief nodes that do not exist were typed 255 for the sweeps; the reference adds them anyway, typed Unknown (pto.rs:199)
+__global__ void type_finish_kernel(uint8_t* __restrict__ type, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (type[i] == 255) type[i] = PORRT_NODE_UNKNOWN;
+}
+
 // One pull sweep of conditional_dijkstra's backup (belief_graph.rs:117-146):
 //   Action     : alt = min_v  norm2(u,v) + dist[v]                      (:121-124)
 //   Observation: alt = sum_vv p(u->vv) * (0.0 + dist[vv]) in stored order (:125-135; obs edges keep the state => cost 0.0)
@@ -675,46 +688,77 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     if (it == set_index.end()) { it = set_index.emplace(visible_zone_mask[n], (int)sets.size()).first; sets.push_back(visible_zone_mask[n]); }
     node_set[n] = it->second;
   }
-  std::vector<int64_t> succ_ptr(sets.size() * (size_t)B + 1, 0);
+  // one table entry per (set, belief): independent of each other, so the index space is cut into chunks for host threads and the
+  // chunks' lists are concatenated in order (at B = 4095 this loop was 130 ms single-threaded)
+  const size_t n_sb = sets.size() * (size_t)B;
+  std::vector<int64_t> succ_ptr(n_sb + 1, 0);
   std::vector<int32_t> succ_belief;
   std::vector<double> succ_p;
-  std::vector<Belief> cur, nxt;
-  for (size_t s = 0; s < sets.size(); ++s)
-    for (int b = 0; b < B; ++b) {
-      cur.assign(1, Belief(beliefs + (size_t)b * nw, beliefs + (size_t)(b + 1) * nw));
-      for (int z = 0; z < ctx->n_zones; ++z)
-        if ((sets[s] >> z) & 1) {  // zones ascending, every current belief split in turn (map_io.rs:285-297)
-          nxt.clear();
-          for (const Belief& bel : cur) successor_beliefs(ctx, bel, z, nxt);
-          cur.swap(nxt);
+  {
+    const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::max(1u, std::thread::hardware_concurrency()), n_sb / 256 + 1}));
+    std::vector<std::vector<int32_t>> c_belief((size_t)n_chunks);
+    std::vector<std::vector<double>> c_p((size_t)n_chunks);
+    std::vector<int> c_err((size_t)n_chunks, 0);
+    auto work = [&](int c) {
+      const size_t lo = n_sb * (size_t)c / (size_t)n_chunks, hi = n_sb * (size_t)(c + 1) / (size_t)n_chunks;
+      std::vector<Belief> cur, nxt;
+      for (size_t sb = lo; sb < hi; ++sb) {
+        const size_t si = sb / (size_t)B;
+        const int b = (int)(sb % (size_t)B);
+        cur.assign(1, Belief(beliefs + (size_t)b * nw, beliefs + (size_t)(b + 1) * nw));
+        for (int z = 0; z < ctx->n_zones; ++z)
+          if ((sets[si] >> z) & 1) {  // zones ascending, every current belief split in turn (map_io.rs:285-297)
+            nxt.clear();
+            for (const Belief& bel : cur) successor_beliefs(ctx, bel, z, nxt);
+            cur.swap(nxt);
+          }
+        int64_t cnt = 0;
+        for (const Belief& child : cur) {
+          const uint64_t h = belief_hash(child.data(), nw);
+          if (h == bhash[b]) continue;  // pto.rs:216
+          auto it = hash_to_id.find(h);
+          if (it == hash_to_id.end()) { c_err[(size_t)c] = 1; return; }
+          c_belief[(size_t)c].push_back(it->second);
+          // transition_probability on the STORED reachable belief states (belief_graph.rs:128)
+          c_p[(size_t)c].push_back(transition_probability(beliefs + (size_t)b * nw, beliefs + (size_t)it->second * nw, nw));
+          ++cnt;
         }
-      for (const Belief& child : cur) {
-        const uint64_t h = belief_hash(child.data(), nw);
-        if (h == bhash[b]) continue;  // pto.rs:216
-        auto it = hash_to_id.find(h);
-        if (it == hash_to_id.end()) return porrt_fail(ctx, PORRT_ERR_PANIC, "no id corresponding to this belief state! (belief_graph.rs:69)");
-        succ_belief.push_back(it->second);
-        // transition_probability on the STORED reachable belief states (belief_graph.rs:128)
-        succ_p.push_back(transition_probability(beliefs + (size_t)b * nw, beliefs + (size_t)it->second * nw, nw));
+        succ_ptr[sb + 1] = cnt;       // counts first; prefix-summed below
       }
-      succ_ptr[s * (size_t)B + b + 1] = (int64_t)succ_belief.size();
+    };
+    if (n_chunks == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (int c = 0; c < n_chunks; ++c) th.emplace_back(work, c);
+      for (auto& t : th) t.join();
     }
+    for (int c = 0; c < n_chunks; ++c)
+      if (c_err[(size_t)c]) return porrt_fail(ctx, PORRT_ERR_PANIC, "no id corresponding to this belief state! (belief_graph.rs:69)");
+    for (size_t k = 0; k < n_sb; ++k) succ_ptr[k + 1] += succ_ptr[k];
+    succ_belief.reserve((size_t)succ_ptr[n_sb]); succ_p.reserve((size_t)succ_ptr[n_sb]);
+    for (int c = 0; c < n_chunks; ++c) {
+      succ_belief.insert(succ_belief.end(), c_belief[(size_t)c].begin(), c_belief[(size_t)c].end());
+      succ_p.insert(succ_p.end(), c_p[(size_t)c].begin(), c_p[(size_t)c].end());
+    }
+  }
   for (double p : succ_p)
     if (!(p > 0.0)) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p > 0.0) (belief_graph.rs:130)");
-  // initial distances: 0 at final belief nodes (pto.rs:261-271)
-  const double INF = std::numeric_limits<double>::infinity();
-  std::vector<double> dist0((size_t)V * B, INF);
+  // initial distances: 0 at final belief nodes (pto.rs:261-271), +inf elsewhere -- written on the device; only the list of final
+  // belief nodes is built here (a host-side V*B table cost 30 ms + a 150 MB upload at B = 4095)
+  std::vector<int64_t> zero_idx;
   for (int k = 0; k < n_finals; ++k) {
     const int32_t f = finals_ids[k];
     if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: final id out of range");
     for (int b = 0; b < B; ++b)
-      if (compat[(size_t)b * n_validities + node_vid[f]] && is_compatible(beliefs + (size_t)b * nw, finals_masks + (size_t)k * mask_words, nw)) dist0[(size_t)f * B + b] = 0.0;
+      if (compat[(size_t)b * n_validities + node_vid[f]] && is_compatible(beliefs + (size_t)b * nw, finals_masks + (size_t)k * mask_words, nw))
+        zero_idx.push_back((int64_t)f * B + b);
   }
   t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;
 
   DevBuf& g = ctx->scratch[3];
   const size_t n_succ = succ_belief.size();
-  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 16 + (size_t)V * 24 + succ_ptr.size() * 8 + n_succ * 12 + compat.size() + (size_t)V * B * 9 + 512;
+  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 16 + (size_t)V * 24 + succ_ptr.size() * 8 + n_succ * 12 + compat.size() + (size_t)V * B * 9 +
+                      zero_idx.size() * 8 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
@@ -732,6 +776,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   int32_t* d_changed = (int32_t*)take(16);
   uint8_t* d_compat = (uint8_t*)take(compat.size());
   uint8_t* d_type = (uint8_t*)take((size_t)V * B);
+  int64_t* d_zero = (int64_t*)take(zero_idx.size() * 8 + 8);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
   if (E) {
     CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
@@ -746,7 +791,13 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_p, succ_p.data(), n_succ * 8, cudaMemcpyHostToDevice, st));
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, compat.data(), compat.size(), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_dist, dist0.data(), (size_t)V * B * 8, cudaMemcpyHostToDevice, st));
+  fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_dist, V * (int64_t)B);
+  LAUNCH_CHECK(ctx);
+  if (!zero_idx.empty()) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_zero, zero_idx.data(), zero_idx.size() * 8, cudaMemcpyHostToDevice, st));
+    scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_dist, d_zero, (int64_t)zero_idx.size());
+    LAUNCH_CHECK(ctx);
+  }
   edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
   LAUNCH_CHECK(ctx);
   BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, d_succ_ptr, d_succ_b, d_succ_p, V, B, n_validities};
@@ -780,18 +831,24 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   R.beliefs.assign(beliefs, beliefs + (size_t)B * nw);
   R.dist.resize((size_t)V * B); R.type.resize((size_t)V * B);
   R.node_obs_set = node_set; R.succ_ptr = succ_ptr; R.succ_belief = succ_belief; R.compat = compat;
-  R.exists.assign((size_t)V * B, 0);
+  type_finish_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_type, V * (int64_t)B);
+  LAUNCH_CHECK(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(R.dist.data(), d_dist, (size_t)V * B * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(R.type.data(), d_type, (size_t)V * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   std::vector<int32_t> nvid(node_vid, node_vid + V);
-  for (int64_t n = 0; n < V; ++n)
-    for (int bb = 0; bb < B; ++bb) {
-      R.exists[(size_t)n * B + bb] = compat[(size_t)bb * n_validities + nvid[n]];
-      if (R.type[(size_t)n * B + bb] == 255) R.type[(size_t)n * B + bb] = PORRT_NODE_UNKNOWN;  // the reference adds the node anyway, typed Unknown (pto.rs:199)
-    }
-  memcpy(out_dist, R.dist.data(), (size_t)V * B * 8);
-  if (out_type) memcpy(out_type, R.type.data(), (size_t)V * B);
+  {  // the caller's copies, by a few host threads (150 MB at B = 4095)
+    const size_t nb = (size_t)V * B;
+    const int nt = nb > (1u << 20) ? 8 : 1;
+    std::vector<std::thread> th;
+    for (int k = 0; k < nt; ++k)
+      th.emplace_back([&, k]() {
+        const size_t lo = nb * (size_t)k / (size_t)nt, hi = nb * (size_t)(k + 1) / (size_t)nt;
+        memcpy(out_dist + lo, R.dist.data() + lo, (hi - lo) * 8);
+        if (out_type) memcpy(out_type + lo, R.type.data() + lo, hi - lo);
+      });
+    for (auto& t : th) t.join();
+  }
   if (out_sweeps) *out_sweeps = sweeps;
   t1 = now_ms(); ph[3] = t1 - t0;
   if (out_phase_ms) memcpy(out_phase_ms, ph, sizeof(ph));
