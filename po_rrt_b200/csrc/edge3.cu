@@ -48,7 +48,7 @@ struct WarpMem {
   uint4 rec[3][32];         // Rec3 chunks, chunk-major (conflict-free 16-byte accesses)
   uint32_t obst[32];        // != 0: a blocking pixel is on the line
   uint32_t zmin[32], zmax[32];
-  uint32_t qb[E3_QB];       // e | strip << 5
+  uint32_t qb[E3_QB];       // E3_ITEM_QUEUE: pairs (e | first strip << 5, want mask: bit 4g = strip g); else e | strip << 5
   uint32_t qg[E3_QG];       // e | strip << 5
 };
 
@@ -92,6 +92,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
   // ---- resolution of the queued strips
   auto drain = [&]() {
     __syncwarp();
+#if !E3_ITEM_QUEUE
     // (1) bitmap strips: drop those of edges already blocked, then one lane per strip
     int live_n = 0;
     for (int q0 = 0; q0 < qb_n; q0 += 32) {
@@ -110,6 +111,40 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       if (q < live_n) {
         const uint32_t ent = wm.qb[q];
         const int e = ent & 31, ts = (int)(ent >> 5);
+#else
+    // (1) bitmap strips.  The queue holds ITEMS (edge, first strip, mask of the strips that need their bitmaps); per group
+    // of 32 items the strips are flattened here -- prefix sums of the mask popcounts, 5-step owner search, r-th set bit --
+    // so that every lane of a round tests one strip.  Items of edges already blocked contribute nothing.
+    for (int i0 = 0; i0 < qb_n; i0 += 32) {
+      uint32_t i_ent = 0, i_want = 0;
+      if (i0 + lane < qb_n) {
+        i_ent = wm.qb[2 * (i0 + lane)]; i_want = wm.qb[2 * (i0 + lane) + 1];
+        if (wm.obst[i_ent & 31] != 0) i_want = 0;
+      }
+      const int i_cnt = __popc(i_want);
+      int i_incl = i_cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, i_incl, o);
+        if (lane >= o) i_incl += t;
+      }
+      const int live_n = __shfl_sync(0xffffffffu, i_incl, 31);
+    for (int q0 = 0; q0 < live_n; q0 += 32) {
+      const int q = q0 + lane;
+      int own = 0;                                                  // owner: the first item whose inclusive sum exceeds q
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, i_incl, own + sft - 1);
+        if (v <= q) own += sft;
+      }
+      own = min(own, 31);
+      const uint32_t o_ent = __shfl_sync(0xffffffffu, i_ent, own);
+      uint32_t o_want = __shfl_sync(0xffffffffu, i_want, own);
+      const int o_excl = __shfl_sync(0xffffffffu, i_incl - i_cnt, own);
+      if (q < live_n) {
+        for (int rnk = q - o_excl; rnk > 0; --rnk) o_want &= o_want - 1;   // drop the rnk lowest set bits
+        const int e = o_ent & 31, ts = (int)(o_ent >> 5) + ((__ffs(o_want) - 1) >> 2);
+#endif
         if (wm.obst[e] == 0) {
           const uint4 r0 = wm.rec[0][e], r1 = wm.rec[1][e];
           const int dirs = (int)wm.rec[2][e].z;
@@ -158,6 +193,9 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       }
       __syncwarp();
     }
+#if E3_ITEM_QUEUE
+    }
+#endif
     // (2) strips through blocks with gray pixels: per pixel on the fused byte grid, 16 lanes per strip
     for (int q0 = 0; q0 < qg_n; q0 += 2) {
       const int q = q0 + (lane >> 4);
@@ -288,6 +326,20 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
       const uint32_t blocked = cls & 0x44444444u, special = (cls >> 3) & 0x11111111u;
       if (blocked) wm.obst[e] = 1;                                 // the bitmaps cannot change the outcome any more
       const uint32_t want = blocked ? 0u : ((cls >> 1) & 0x11111111u & ~special);
+#if E3_ITEM_QUEUE
+      // enqueue the ITEM if any of its strips needs the bitmaps (one ballot; the strips are flattened when the queue is drained)
+      {
+        const unsigned bal = __ballot_sync(0xffffffffu, want != 0);
+        if (bal) {
+          if (want) {
+            const int pos = 2 * (qb_n + __popc(bal & lt_mask));
+            wm.qb[pos] = (uint32_t)e | ((uint32_t)ts0 << 5);
+            wm.qb[pos + 1] = want;
+          }
+          qb_n += __popc(bal);
+        }
+      }
+#else
       // enqueue the strips that need the bitmaps: exclusive scan of the per-lane counts
       if (__any_sync(0xffffffffu, want != 0)) {
         const int cnt = __popc(want);
@@ -304,6 +356,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         for (int g = 0; g < E3_G; ++g)
           if (want & (1u << (4 * g))) wm.qb[pb++] = ent0 + ((uint32_t)g << 5);
       }
+#endif
       if (__any_sync(0xffffffffu, special != 0)) {                 // rare: strips through gray pixels
 #pragma unroll
         for (int g = 0; g < E3_G; ++g) {
@@ -335,7 +388,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     for (int w0 = 0; w0 < total; w0 += 32) {
-      if (may_overflow && (qb_n > E3_QB - 32 * E3_G || qg_n > E3_QG - 32 * E3_G)) drain();
+      if (may_overflow && (qb_n > E3_QB_LIMIT || qg_n > E3_QG - 32 * E3_G)) drain();
       const int w = w0 + lane;
       int e = 0;                                                    // owner: the first lane whose inclusive sum exceeds w
 #pragma unroll
@@ -360,7 +413,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
     const bool may_overflow = total * E3_G > min(E3_QB, E3_QG);     // warp-uniform
     __syncwarp();
     for (int w0 = 0; w0 < total; w0 += 32) {
-      if (may_overflow && (qb_n > E3_QB - 32 * E3_G || qg_n > E3_QG - 32 * E3_G)) drain();
+      if (may_overflow && (qb_n > E3_QB_LIMIT || qg_n > E3_QG - 32 * E3_G)) drain();
       const int d = incl - w0;                                    // edge `lane` ends before window position d
       const int e_base = __popc(__ballot_sync(0xffffffffu, d <= 0));
       const unsigned marks = __reduce_or_sync(0xffffffffu, (d >= 1 && d <= 32) ? (1u << (d - 1)) : 0u);

@@ -25,6 +25,14 @@
 #endif
 #define E3_QB 512           // bitmap-queue entries per warp (a round adds at most 32 * E3_G)
 #define E3_QG 256           // byte-queue entries per warp
+#ifndef E3_ITEM_QUEUE
+#define E3_ITEM_QUEUE 1     // the bitmap queue holds items (edge, first strip, strip mask) and is flattened when drained
+#endif
+#if E3_ITEM_QUEUE
+#define E3_QB_LIMIT (E3_QB / 2 - 32)          // items; a round adds at most 32
+#else
+#define E3_QB_LIMIT (E3_QB - 32 * E3_G)       // strips; a round adds at most 32 * E3_G
+#endif
 #define E3_BIAS 65536ull
 #ifndef E3_MAX_WARPS
 #define E3_MAX_WARPS 32
