@@ -112,9 +112,10 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         const uint32_t ent = wm.qb[q];
         const int e = ent & 31, ts = (int)(ent >> 5);
 #else
-    // (1) bitmap strips.  The queue holds ITEMS (edge, first strip, mask of the strips that need their bitmaps); per group
-    // of 32 items the strips are flattened here -- prefix sums of the mask popcounts, 5-step owner search, r-th set bit --
-    // so that every lane of a round tests one strip.  Items of edges already blocked contribute nothing.
+    // (1) bitmap strips.  The queue holds ITEMS (edge, first strip, mask of the strips that need their bitmaps) in
+    // qb[0 .. 2 * E3_QI); per group of 32 items the strips are written out to qb[2 * E3_QI ..) -- prefix sums of the mask
+    // popcounts, every lane expands its own item -- so that every lane of a round tests one strip.  Items of edges already
+    // blocked contribute nothing.
     for (int i0 = 0; i0 < qb_n; i0 += 32) {
       uint32_t i_ent = 0, i_want = 0;
       if (i0 + lane < qb_n) {
@@ -129,21 +130,15 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         if (lane >= o) i_incl += t;
       }
       const int live_n = __shfl_sync(0xffffffffu, i_incl, 31);
+      uint32_t* qs = wm.qb + 2 * E3_QI;
+      for (int pos = i_incl - i_cnt; i_want; i_want &= i_want - 1)
+        qs[pos++] = i_ent + ((uint32_t)((__ffs(i_want) - 1) >> 2) << 5);
+      __syncwarp();
     for (int q0 = 0; q0 < live_n; q0 += 32) {
       const int q = q0 + lane;
-      int own = 0;                                                  // owner: the first item whose inclusive sum exceeds q
-#pragma unroll
-      for (int sft = 16; sft >= 1; sft >>= 1) {
-        const int v = __shfl_sync(0xffffffffu, i_incl, own + sft - 1);
-        if (v <= q) own += sft;
-      }
-      own = min(own, 31);
-      const uint32_t o_ent = __shfl_sync(0xffffffffu, i_ent, own);
-      uint32_t o_want = __shfl_sync(0xffffffffu, i_want, own);
-      const int o_excl = __shfl_sync(0xffffffffu, i_incl - i_cnt, own);
       if (q < live_n) {
-        for (int rnk = q - o_excl; rnk > 0; --rnk) o_want &= o_want - 1;   // drop the rnk lowest set bits
-        const int e = o_ent & 31, ts = (int)(o_ent >> 5) + ((__ffs(o_want) - 1) >> 2);
+        const uint32_t ent = qs[q];
+        const int e = ent & 31, ts = (int)(ent >> 5);
 #endif
         if (wm.obst[e] == 0) {
           const uint4 r0 = wm.rec[0][e], r1 = wm.rec[1][e];

@@ -28,8 +28,9 @@
 #ifndef E3_ITEM_QUEUE
 #define E3_ITEM_QUEUE 1     // the bitmap queue holds items (edge, first strip, strip mask) and is flattened when drained
 #endif
+#define E3_QI ((E3_QB - 32 * 8) / 2)          // item entries (2 words each) in front of the strip scratch (32 items x 8 strips)
 #if E3_ITEM_QUEUE
-#define E3_QB_LIMIT (E3_QB / 2 - 32)          // items; a round adds at most 32
+#define E3_QB_LIMIT (E3_QI - 32)              // items; a round adds at most 32
 #else
 #define E3_QB_LIMIT (E3_QB - 32 * E3_G)       // strips; a round adds at most 32 * E3_G
 #endif
