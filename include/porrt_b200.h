@@ -31,6 +31,7 @@ extern "C" {
 #define PORRT_ERR_PANIC 5       /* the reference would panic on this input as a whole (see porrt_last_error) */
 #define PORRT_ERR_UNSUPPORTED 6
 #define PORRT_ERR_NO_VERTICES 7 /* NN call before porrt_vertices_set */
+#define PORRT_ERR_COMM 8        /* NCCL not loadable / communicator error (multi-GPU paths only) */
 
 /* per-element validity codes (int32): >= 0 is a validity id into the world-validity table */
 #define PORRT_INVALID (-1)            /* Option::None: obstacle                          map_io.rs:491,511 */
@@ -193,6 +194,30 @@ int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy, const in
 /* reachable_belief_states (map_io.rs:515-546 / map_shelves_io.rs:490-520): host-side closure over the uploaded map's
  * zones; out[cap * n_worlds]; *out_B = count (PORRT_ERR_CAPACITY if > cap). */
 int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * The reference is single-threaded and has no distributed code; what shards are its independent units (edge checks,
+ * radius / NN queries, the worlds of plan_qmdp).  One process and one ctx per GPU; map and vertex set replicated.
+ * A ctx that was given a communicator runs porrt_prm_build and porrt_sssp_worlds SHARDED (same signatures, same
+ * results on every rank, bit-identical to the single-GPU result):
+ *   porrt_prm_build   : rank r runs the radius queries and edge checks of new nodes shard_range(n, r, world); the valid
+ *                       (neighbour, new node) pairs are all-gathered (NCCL over NVLink) and every rank assembles the CSR.
+ *   porrt_sssp_worlds : rank r relaxes worlds shard_range(n_worlds, r, world); the dist rows are all-gathered.
+ * Edge / state / NN batches have no exchange step: each rank calls the ordinary entry points on its slice; when a later
+ * device-resident stage needs all slices, porrt_comm_all_gather_dev assembles them.
+ * NCCL is bound at run time (dlopen "libnccl.so.2", override with PORRT_NCCL_LIB); there is no link-time dependency. */
+/* rank 0: create the 128-byte ncclUniqueId; the host carries it to the other ranks (any 128-byte broadcast) */
+int32_t porrt_comm_unique_id(uint8_t* out_id128);
+int32_t porrt_comm_init(porrt_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);   /* collective */
+int32_t porrt_comm_destroy(porrt_ctx* ctx);
+int32_t porrt_comm_info(porrt_ctx* ctx, int32_t* out_rank, int32_t* out_world, int32_t* out_nccl_version);
+/* contiguous shard [lo, hi) of n units: sizes differ by at most one, lower ranks take the extra unit */
+int32_t porrt_shard_range(int64_t n, int32_t rank, int32_t world, int64_t* out_lo, int64_t* out_hi);
+/* rank r owns rows shard_range(n_total, r, world), bytes_per_unit bytes each; recv_dev gets all n_total rows in rank order on
+ * every rank.  send_dev == NULL: the rank's rows already sit at their place in recv_dev (in-place).  Enqueued on the ctx stream. */
+int32_t porrt_comm_all_gather_dev(porrt_ctx* ctx, const void* send_dev, void* recv_dev, int64_t n_total, int64_t bytes_per_unit);
+/* ragged: rank r contributes byte_counts[r] bytes (host array [world], identical on every rank) */
+int32_t porrt_comm_all_gatherv_dev(porrt_ctx* ctx, const void* send_dev, void* recv_dev, const int64_t* byte_counts);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,13 @@ SIGNATURES = {
     "porrt_belief_vi": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, pp(i32), vp]),
     "porrt_extract_policy": (i32, [vp, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),
     "porrt_reachable_belief_states": (i32, [vp, vp, vp, i32, pp(i32)]),
+    "porrt_comm_unique_id": (i32, [vp]),
+    "porrt_comm_init": (i32, [vp, vp, i32, i32]),
+    "porrt_comm_destroy": (i32, [vp]),
+    "porrt_comm_info": (i32, [vp, pp(i32), pp(i32), pp(i32)]),
+    "porrt_shard_range": (i32, [i64, i32, i32, pp(i64), pp(i64)]),
+    "porrt_comm_all_gather_dev": (i32, [vp, vp, vp, i64, i64]),
+    "porrt_comm_all_gatherv_dev": (i32, [vp, vp, vp, vp]),
 }
 
 _lib = None

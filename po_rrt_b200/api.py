@@ -77,6 +77,32 @@ class Context:
     def launch_count(self):
         return self.lib.porrt_ctx_launch_count(self.h)
 
+    # -- multi-GPU: one process and one Context per GPU; see po_rrt_b200/shard.py:init_comm for the plumbing
+    def comm_unique_id(self):
+        """rank 0: the 128-byte ncclUniqueId every rank must pass to comm_init"""
+        out = np.zeros(128, dtype=np.uint8)
+        rc = self.lib.porrt_comm_unique_id(_p(out))
+        if rc:
+            raise PorrtError(rc, "porrt_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return out
+
+    def comm_init(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        self.check(self.lib.porrt_comm_init(self.h, _p(uid), int(rank), int(world)))
+
+    def comm_destroy(self):
+        self.check(self.lib.porrt_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self.check(self.lib.porrt_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def all_gather_dev(self, send_ptr, recv_ptr, n_total, bytes_per_unit):
+        """device pointers (ints); rank r owns rows shard_range(n_total, r, world); send_ptr None/0 = in place"""
+        self.check(self.lib.porrt_comm_all_gather_dev(self.h, send_ptr or None, recv_ptr, int(n_total), int(bytes_per_unit)))
+
     def last_phase_ms(self):
         out = np.zeros(16)
         n = C.c_int32()

@@ -122,6 +122,10 @@ struct porrt_ctx {
   const int64_t* prm_row_ptr = nullptr;
   const int32_t* prm_col = nullptr;
 
+  // ---- multi-GPU (comm.cu): NCCL communicator bound at run time; world 1 = no communicator
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+
   // ---- scratch
   DevBuf scratch[12];
   PinBuf pin[6];
@@ -169,6 +173,9 @@ static inline void tfinish(porrt_ctx* ctx) {  // call after the stream has been 
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// comm.cu
+void comm_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi);
+int32_t comm_all_gatherv_dev(porrt_ctx* ctx, const void* send_dev, void* recv_dev, const int64_t* offsets /* host [world+1] */, cudaStream_t st);
 // map.cu
 int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
                               int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st);

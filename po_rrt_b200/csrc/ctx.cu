@@ -36,6 +36,7 @@ PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
   CTX_CHECK(ctx);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  porrt_comm_destroy(ctx);
   ctx->d_grid.release(); for (DevBuf& b : ctx->d_coarse) b.release(); ctx->d_validities.release(); ctx->d_zone_pos.release();
   ctx->d_plane.release(); ctx->d_bits.release(); ctx->d_ticket.release();
   ctx->d_vxy_sorted.release(); ctx->d_vid_sorted.release(); ctx->d_cell_start.release();

@@ -158,12 +158,26 @@ __global__ void iota_u32_kernel(uint32_t* __restrict__ out, int64_t n) {
   if (i < n) out[i] = (uint32_t)i;
 }
 
-__global__ void seg_owner_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ owner) {
+__global__ void seg_owner_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t base, int32_t* __restrict__ owner) {
   const int lane = threadIdx.x & 31;
   const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (seg >= m) return;
   const int64_t s = offsets[seg], e = offsets[seg + 1];
-  for (int64_t k = s + lane; k < e; k += 32) owner[k] = (int32_t)seg;
+  for (int64_t k = s + lane; k < e; k += 32) owner[k] = base + (int32_t)seg;
+}
+
+// sharded build: the compacted neighbour lists of this rank's segments, packed densely for the exchange
+__global__ void prm_pack_kernel(const int64_t* __restrict__ offsets, const int64_t* __restrict__ dense_off, int64_t m,
+                                const int32_t* __restrict__ compact, const int32_t* __restrict__ early_cnt, int32_t* __restrict__ dense) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= m) return;
+  const int64_t s = offsets[seg], o = dense_off[seg];
+  const int32_t c = early_cnt[seg];
+  for (int32_t k = lane; k < c; k += 32) dense[o + k] = compact[s + k];
+}
+__global__ void prm_shard_summary_kernel(const int64_t* __restrict__ local_total, const int32_t* __restrict__ flag, int64_t* __restrict__ out2) {
+  out2[0] = *local_total; out2[1] = (int64_t)*flag;
 }
 
 // ordered compaction of the valid hits of every segment + counts; one warp per segment
@@ -290,16 +304,22 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   LAUNCH_CHECK(ctx);
   t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;   // what is left of the radii after the overlap
 
+  // multi-GPU (comm.cu): this rank answers the queries of new nodes [lo, hi) only; bins and kd ranks are replicated
+  const int world = ctx->comm_world;
+  int64_t lo = 0, hi = n;
+  if (world > 1) comm_shard_range(n, ctx->comm_rank, world, &lo, &hi);
+  const int64_t m = hi - lo;
+
   // 3. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
   int64_t total = 0;
-  rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>(), d_radius, n, d_prefix, nullptr, nullptr, d_off, &ctx->scratch[2], &total);
+  rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>() + 2 * lo, d_radius + lo, m, d_prefix + lo, nullptr, nullptr, d_off, &ctx->scratch[2], &total);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
 
   // 4. restore the kd pre-order inside every neighbour list
   int32_t* d_ids = ctx->scratch[2].as<int32_t>();
-  rc = segments_sort_by_key_dev(ctx, d_off, n, d_ids, d_rank, n);
+  if (m > 0) rc = segments_sort_by_key_dev(ctx, d_off, m, d_ids, d_rank, n);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[4] = t1 - t0; t0 = t1;
@@ -311,7 +331,7 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   int32_t* d_owner = ctx->scratch[0].as<int32_t>();
   int32_t* d_vid = ctx->scratch[1].as<int32_t>();
   if (total > 0) {
-    seg_owner_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_owner);
+    seg_owner_kernel<<<div_up(m * 32, 256), 256, 0, st>>>(d_off, m, (int32_t)lo, d_owner);
     LAUNCH_CHECK(ctx);
     rc = map_edge_validity_indexed_dev(ctx, ctx->d_vxy.as<double>(), d_ids, d_owner, total, d_vid, st);
     if (rc) return rc;
@@ -320,15 +340,64 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   t1 = now_ms(); ph[5] = t1 - t0; t0 = t1;
 
   // 6. CSR in insertion order: row k = valid earlier neighbours (kd order), then later nodes ascending (prm.rs:99-106)
-  prm_compact_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_ids, d_vid, d_early_cnt, d_ids, d_flag);
-  LAUNCH_CHECK(ctx);
-  rc = scan_exclusive_i64(ctx, d_early_cnt, n, d_early_off);
-  if (rc) return rc;
+  if (m > 0) {
+    prm_compact_kernel<<<div_up(m * 32, 256), 256, 0, st>>>(d_off, m, d_ids, d_vid, d_early_cnt + lo, d_ids, d_flag);
+    LAUNCH_CHECK(ctx);
+  }
   int64_t n_half = 0;
   int32_t flag = 0;
-  CUDA_TRY(ctx, cudaMemcpyAsync(&n_half, d_early_off + n, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  const int64_t* d_seg_off = d_off;      // where the compacted list of segment k starts ...
+  const int32_t* d_compact = d_ids;      // ... in this array
+  if (world == 1) {
+    rc = scan_exclusive_i64(ctx, d_early_cnt, n, d_early_off);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&n_half, d_early_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  } else {
+    // the exchange step: every rank gets all counts and all valid (neighbour, new node) lists, then
+    // assembles the whole CSR itself -- the graph stays device-resident on every GPU for the value backups that follow.
+    const double tx0 = now_ms();
+    int64_t* d_local_off = d_late_off;   // free until the transpose below
+    rc = scan_exclusive_i64(ctx, d_early_cnt + lo, m, d_local_off);
+    if (rc) return rc;
+    CUDA_TRY(ctx, ctx->scratch[10].ensure((size_t)world * 16 + 64));
+    int64_t* d_summary = ctx->scratch[10].as<int64_t>();
+    prm_shard_summary_kernel<<<1, 1, 0, st>>>(d_local_off + m, d_flag, d_summary + 2 * ctx->comm_rank);
+    LAUNCH_CHECK(ctx);
+    std::vector<int64_t> off16(world + 1);
+    for (int r = 0; r <= world; ++r) off16[r] = 16 * (int64_t)r;
+    rc = comm_all_gatherv_dev(ctx, nullptr, d_summary, off16.data(), st);
+    if (rc) return rc;
+    std::vector<int64_t> cnt_off(world + 1);
+    for (int r = 0; r < world; ++r) { int64_t a, b2; comm_shard_range(n, r, world, &a, &b2); cnt_off[r] = a * 4; cnt_off[r + 1] = b2 * 4; }
+    rc = comm_all_gatherv_dev(ctx, nullptr, d_early_cnt, cnt_off.data(), st);
+    if (rc) return rc;
+    std::vector<int64_t> summary(2 * world);
+    CUDA_TRY(ctx, cudaMemcpyAsync(summary.data(), d_summary, (size_t)world * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    std::vector<int64_t> ids_off(world + 1, 0);
+    for (int r = 0; r < world; ++r) {
+      ids_off[r + 1] = ids_off[r] + summary[2 * r] * 4;
+      if (summary[2 * r + 1] < -1) flag = (int32_t)summary[2 * r + 1];   // a panic on any rank fails the build on every rank
+    }
+    n_half = ids_off[world] / 4;
+    if (flag >= -1) {
+      CUDA_TRY(ctx, ctx->scratch[0].ensure((size_t)std::max<int64_t>(n_half, 1) * 4));   // the owner list is dead by now
+      int32_t* d_dense = ctx->scratch[0].as<int32_t>();
+      if (m > 0) {
+        prm_pack_kernel<<<div_up(m * 32, 256), 256, 0, st>>>(d_off, d_local_off, m, d_ids, d_early_cnt + lo, d_dense + ids_off[ctx->comm_rank] / 4);
+        LAUNCH_CHECK(ctx);
+      }
+      rc = comm_all_gatherv_dev(ctx, nullptr, d_dense, ids_off.data(), st);
+      if (rc) return rc;
+      rc = scan_exclusive_i64(ctx, d_early_cnt, n, d_early_off);
+      if (rc) return rc;
+      d_seg_off = d_early_off; d_compact = d_dense;
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    ctx->last_ms[0] = now_ms() - tx0; ctx->n_last = 1;   // porrt_ctx_last_phase_ms: wall time of the exchange
+  }
   if (flag < -1) return porrt_fail(ctx, PORRT_ERR_PANIC, "prm_build: an edge check hit a reference panic (code " + std::to_string(flag) + ")");
   const int64_t n_edges = 2 * n_half;
   *out_n_edges = n_edges;
@@ -339,7 +408,7 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   uint64_t* d_keys = ctx->scratch[5].as<uint64_t>();
   uint32_t* d_vals = ctx->scratch[6].as<uint32_t>();
   int32_t* d_col = ctx->scratch[7].as<int32_t>();
-  prm_pairs_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_ids, d_early_cnt, d_early_off, d_keys, d_vals, d_late_cnt);
+  prm_pairs_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_early_off, d_keys, d_vals, d_late_cnt);
   LAUNCH_CHECK(ctx);
   rc = scan_exclusive_i64(ctx, d_late_cnt, n, d_late_off);
   if (rc) return rc;
@@ -347,7 +416,7 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   if (rc) return rc;
   prm_rowptr_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(d_early_off, d_late_off, n, d_row_ptr);
   LAUNCH_CHECK(ctx);
-  prm_fill_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, n, d_ids, d_early_cnt, d_late_off, d_vals, d_row_ptr, d_col);
+  prm_fill_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_off, d_vals, d_row_ptr, d_col);
   LAUNCH_CHECK(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, d_row_ptr, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
   int32_t status = PORRT_OK;
@@ -427,7 +496,13 @@ PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* ro
   if (world_view && (!node_vid || !validities || n_validities <= 0 || mask_words <= 0)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: world view needs validities");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const int W = world_view ? n_worlds : 1;
+  const int Wall = world_view ? n_worlds : 1;
+  // multi-GPU (comm.cu): the worlds are independent problems on one graph -- rank r relaxes worlds [wlo, whi) and the dist
+  // rows are all-gathered; the plain-graph call (n_worlds == 0) is not sharded
+  int64_t wlo = 0, whi = Wall;
+  const bool sharded = world_view && ctx->comm_world > 1;
+  if (sharded) comm_shard_range(Wall, ctx->comm_rank, ctx->comm_world, &wlo, &whi);
+  const int W = (int)(whi - wlo);
   const int64_t E = row_ptr[V];
   if (E > 0 && !col) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: null col");
   // host prep: validity per (node, world) and the initial distances (inf, 0 at the finals)
@@ -438,16 +513,16 @@ PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* ro
     for (int64_t u = 0; u < V; ++u) {
       const int32_t vid = node_vid[u];
       if (vid < 0 || vid >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: node validity id out of range");
-      for (int w = 0; w < W; ++w) ok[(size_t)u * W + w] = (validities[(size_t)vid * mask_words + w / 64] >> (w % 64)) & 1;
+      for (int w = 0; w < W; ++w) { const int wg = (int)wlo + w; ok[(size_t)u * W + w] = (validities[(size_t)vid * mask_words + wg / 64] >> (wg % 64)) & 1; }
     }
-  for (int w = 0; w < W; ++w)
+  for (int w = 0; w < Wall; ++w)
     for (int64_t k = finals_ptr[w]; k < finals_ptr[w + 1]; ++k) {
       const int32_t f = finals_ids[k];
       if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: final id out of range");
-      dist0[(size_t)f * W + w] = 0.0;
+      if (w >= wlo && w < whi) dist0[(size_t)f * W + (w - wlo)] = 0.0;
     }
   DevBuf& g = ctx->scratch[3];
-  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 16 + (size_t)V * W * 17 + 512;
+  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 16 + (size_t)V * W * 9 + (size_t)V * Wall * 8 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };  // keeps double2 loads aligned
@@ -455,35 +530,43 @@ PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* ro
   double* d_cost = (double*)take((size_t)E * 8);
   double* d_xy = (double*)take((size_t)V * 16);
   double* d_dist = (double*)take((size_t)V * W * 8);
-  double* d_out = (double*)take((size_t)V * W * 8);
+  double* d_out = (double*)take((size_t)V * Wall * 8);   // [Wall][V]: this rank fills rows wlo..whi, the gather the rest
   int32_t* d_col = (int32_t*)take((size_t)E * 4);
   int32_t* d_changed = (int32_t*)take(16);
   uint8_t* d_ok = (uint8_t*)take((size_t)V * W);
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_dist, dist0.data(), (size_t)V * W * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_ok, ok.data(), (size_t)V * W, cudaMemcpyHostToDevice, st));
-  edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
-  LAUNCH_CHECK(ctx);
   int sweeps = 0;
-  const int BATCH = 8;  // sweeps between two convergence checks
-  for (;;) {
-    CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
-    for (int k = 0; k < BATCH; ++k) {
-      sssp_sweep_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_row, d_col, d_cost, d_ok, V, W, d_dist, d_changed);
-      LAUNCH_CHECK(ctx);
+  if (W > 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dist, dist0.data(), (size_t)V * W * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_ok, ok.data(), (size_t)V * W, cudaMemcpyHostToDevice, st));
+    edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
+    LAUNCH_CHECK(ctx);
+    const int BATCH = 8;  // sweeps between two convergence checks
+    for (;;) {
+      CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
+      for (int k = 0; k < BATCH; ++k) {
+        sssp_sweep_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_row, d_col, d_cost, d_ok, V, W, d_dist, d_changed);
+        LAUNCH_CHECK(ctx);
+      }
+      sweeps += BATCH;
+      int32_t changed = 0;
+      CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (!changed) break;
+      if (sweeps > 4 * V + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp_worlds: no convergence");
     }
-    sweeps += BATCH;
-    int32_t changed = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    if (!changed) break;
-    if (sweeps > 4 * V + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp_worlds: no convergence");
+    transpose_dist_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_dist, V, W, d_out + wlo * V);
+    LAUNCH_CHECK(ctx);
   }
-  transpose_dist_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_dist, V, W, d_out);
-  LAUNCH_CHECK(ctx);
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_out, (size_t)V * W * 8, cudaMemcpyDeviceToHost, st));
+  if (sharded) {
+    std::vector<int64_t> off(ctx->comm_world + 1);
+    for (int r = 0; r < ctx->comm_world; ++r) { int64_t a2, b2; comm_shard_range(Wall, r, ctx->comm_world, &a2, &b2); off[r] = a2 * V * 8; off[r + 1] = b2 * V * 8; }
+    int32_t rc = comm_all_gatherv_dev(ctx, nullptr, d_out, off.data(), st);
+    if (rc) return rc;
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_out, (size_t)V * Wall * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   if (out_sweeps) *out_sweeps = sweeps;
   return PORRT_OK;

@@ -398,6 +398,12 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
                                  int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out) {
   cudaStream_t st = ctx->stream;
+  if (m <= 0) {   // an empty shard of a sharded batch
+    CUDA_TRY(ctx, cudaMemsetAsync(offsets_dev, 0, 8, st));
+    CUDA_TRY(ctx, ids_buf->ensure(4));
+    *total_out = 0;
+    return PORRT_OK;
+  }
   GridDev g = grid_dev(ctx);
   CUDA_TRY(ctx, ctx->scratch[4].ensure((size_t)m * 4 + 16));
   int32_t* counts = ctx->scratch[4].as<int32_t>();

@@ -27,6 +27,27 @@ def all_gather_shards(local, n_total, group=None):
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0)
 
 
+def exchange_unique_id(make_id, group=None):
+    """rank 0 calls make_id() -> 128 uint8 (ncclUniqueId); every rank returns rank 0's bytes.  Any backend (gloo or nccl)."""
+    rank = dist.get_rank(group)
+    box = [bytes(bytearray(make_id())) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+def init_comm(ctx, group=None):
+    """Give the Context (one per process / GPU) an NCCL communicator spanning the torch.distributed group: porrt_prm_build and
+    porrt_sssp_worlds then run sharded with their exchange step inside the library (csrc/comm.cu)."""
+    import numpy as np
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return rank, world
+    uid = exchange_unique_id(lambda: ctx.comm_unique_id().tolist(), group)
+    ctx.comm_init(np.frombuffer(uid, dtype=np.uint8), rank, world)
+    return rank, world
+
+
 def max_over_ranks(value, device="cpu", group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

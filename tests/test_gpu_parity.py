@@ -635,3 +635,24 @@ def test_refiner_partial_shortcut(ctx, kind):
     st, c, w = pmap.partial_shortcut(path[:2], compats[0], 100)
     np.testing.assert_array_equal(st, path[:2])
     assert (c, w) == (0, 0)
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU
+def test_sharded_paths_multi_gpu():
+    """scripts/multi_gpu_check.py under torchrun on min(2, visible GPUs) ranks: sharded PRM build / plan_qmdp / gathered edge
+    masks are bit-identical to the single-GPU results and to the oracle (with one GPU only the world-1 plumbing runs)"""
+    import os
+    import socket
+    import subprocess
+    import sys
+    import torch
+    n = min(2, torch.cuda.device_count())
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "scripts", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "multi_gpu_check: ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
