@@ -220,6 +220,63 @@ def side_measurements(ctx, pmap, args):
     return ex
 
 
+def multi_gpu_measurements(ctx, pmap, rank, world, dev):
+    """N > 1 only, called by EVERY rank (collective): the other two BASELINE metrics at N GPUs.
+    NN queries: vertex set replicated, 1e6 queries per rank (weak scaling, no data-path collective), device ms = max over ranks.
+    PRM build: ONE roadmap of 1e6 samples built by all ranks together (strong scaling): sharded radius + edge batches, NCCL
+    all-gather of the valid pairs, CSR assembled on every rank (csrc/comm.cu, graph.cu)."""
+    import torch
+    import torch.distributed as dist
+    import po_rrt_b200 as P
+    from po_rrt_b200 import shard, synth
+    out = {}
+
+    def rmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    V = Q = 1_000_000
+    pts, qs = synth.points(V, seed=3), synth.points(Q, seed=4 + rank)
+    r = 2.0 * (np.log(V) / V) ** 0.5
+    tree = P.KdTree(ctx, pts, cell_size=r)
+    pin_ids = torch.empty(64 * Q, dtype=torch.int32).pin_memory().numpy()
+    pin_k = torch.empty((Q, 16), dtype=torch.int32).pin_memory().numpy()
+    pin_d = torch.empty((Q, 16), dtype=torch.float64).pin_memory().numpy()
+    tree.nearest_neighbors(qs[:1000], r)
+    res = {}
+    for name, call, n_ph in (("radius", lambda: tree.nearest_neighbors(qs, r, cap=64 * Q, ids_out=pin_ids), 2),
+                             ("nearest", lambda: tree.nearest_neighbor(qs), 1),
+                             ("knn16", lambda: tree.knn(qs, 16, ids_out=pin_k, dist_out=pin_d), 1)):
+        best = None
+        for _ in range(3):
+            dist.barrier()
+            t0 = time.perf_counter(); call(); t1 = time.perf_counter()
+            dms, wall = rmax(sum(ctx.last_phase_ms()[:n_ph])), rmax(t1 - t0)
+            if best is None or dms < best[0]:
+                best = (dms, wall)
+        res[name] = {"queries_per_rank": Q, "device_ms_max": best[0], "queries_per_s_device": Q * world / (best[0] * 1e-3),
+                     "queries_per_s_e2e": Q * world / best[1]}
+    out["nn"] = res
+
+    shard.init_comm(ctx)
+    pin_col = torch.empty(64 * V, dtype=torch.int32).pin_memory().numpy()
+    best = None
+    for _ in range(3):
+        dist.barrier()
+        prm = P.PRM(pmap)
+        t0 = time.perf_counter(); prm.grow_graph(pts, 0.1, 2.0, col_out=pin_col); t1 = time.perf_counter()
+        wall = rmax(t1 - t0)
+        if best is None or wall < best[0]:
+            best = (wall, [round(float(x), 3) for x in prm.phase_ms[:7]], ctx.last_phase_ms()[:1], int(len(prm.col)))
+    out["prm_build_sharded"] = {"V": V, "ms_max_over_ranks": 1e3 * best[0], "directed_edges": best[3], "exchange_ms": best[2],
+                                "phase_ms_rank0[radii,bin,radius,kd_rank,order,edges,csr]": best[1], "scaling": "strong",
+                                "note": "one roadmap built by all ranks; bins, kd ranks and the CSR assembly are replicated, "
+                                        "radius + order + edge batches are sharded"}
+    ctx.comm_destroy()
+    return out
+
+
 def refiner_measurement(ctx, pmap, n_pieces=64, n_states=30, n_iterations=1000):
     """PTOPolicyRefiner::partial_shortcut (SURVEY 8(f) rank 1) on the c5 map: n_pieces jagged path pieces (random walks through
     free space), n_iterations trials each; the device runs the trials of all pieces in shared speculative waves, the oracle runs
@@ -421,6 +478,14 @@ def main():
     # the e2e result must equal the device-resident one
     assert torch.equal(h_vid, d_vid.cpu()) and torch.equal(h_mask, d_mask.cpu())
 
+    multi = None
+    if world > 1 and not args.no_extras:
+        try:
+            multi = multi_gpu_measurements(ctx, pmap, rank, world, dev)
+        except Exception as e:  # side numbers must never take the headline down (a failed rank leaves the others to NCCL's timeout)
+            import traceback
+            multi = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
+
     line = None
     if rank == 0:
         base, oracle_vid, _ = cpu_baseline(args, occ, zones, a, b)
@@ -438,6 +503,8 @@ def main():
     # ---- side measurements of the other BASELINE metrics (kNN queries/s, PRM build ms); not part of `value`
     if rank == 0 and not args.no_extras:
         line["extras"] = side_measurements(ctx, pmap, args)
+        if multi is not None:
+            line["extras"]["multi_gpu"] = multi
     if rank == 0:
         emit(line)
     ctx.close()

@@ -169,6 +169,23 @@ int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const
 int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_t* out_belief, int32_t* out_parent,
                              uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost);
 
+/* conditional_dijkstra (belief_graph.rs:89-182) on an EXPLICIT BeliefGraph (belief_graph.rs:12-73): the reference's free function
+ * as called by its own tests (:276-567) and by the multi-modal PRM (map_shelves_tamp_prm.rs:476).  Belief node k has state
+ * xy[2k..], node_type[k] (PORRT_NODE_*), belief_id[k] into beliefs[B * n_worlds]; children adjacency as CSR in add_edge order
+ * (parents are implied: add_edge keeps both lists).  cost_evaluator = norm2.  out_dist[V] bit-identical to the reference;
+ * PORRT_ERR_PANIC where it would panic (:130 p <= 0 at an evaluated Observation node, :140 Unknown parent of a reached node). */
+int32_t porrt_conditional_dijkstra(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy,
+                                   const uint8_t* node_type, const int32_t* belief_id, const double* beliefs, int32_t B,
+                                   int32_t n_worlds, const int32_t* finals, int32_t n_finals, double* out_dist,
+                                   int32_t* out_sweeps /* nullable */);
+/* extract_policy (belief_graph.rs:184-267) on the same explicit graph and the dist of porrt_conditional_dijkstra: host walk from
+ * belief node 0.  Policy nodes in creation order: out_belief_node[k], out_parent[k] (-1 = root), out_is_leaf[k].
+ * PORRT_ERR_PANIC where the reference's asserts (:250, :261) fire; PORRT_ERR_CAPACITY (with *out_n) when cap is too small. */
+int32_t porrt_extract_policy_graph(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy,
+                                   const uint8_t* node_type, const int32_t* belief_id, const double* beliefs, int32_t B,
+                                   int32_t n_worlds, const double* dist, int32_t* out_belief_node, int32_t* out_parent,
+                                   uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost);
+
 /* ------------------------------------------------------------------ policy refinement (pto_policy_refiner.rs)
  * PTOPolicyRefiner::is_transition_valid (pto_policy_refiner.rs:395-423), batched: out_valid[i] = 1 iff both end states are
  * valid, the transition from -> to is valid with validity id v, and compat_row[v] != 0, where compat_row[n_validities] is

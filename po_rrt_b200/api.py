@@ -430,6 +430,54 @@ def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, f
     return plan
 
 
+class BeliefGraph:
+    """src/belief_graph.rs BeliefGraph as arrays: belief node k = (state xy[k], belief_id[k], node_type[k]); children adjacency
+    as CSR in add_edge order.  conditional_dijkstra / extract_policy are the reference's free functions (:89-267)."""
+
+    def __init__(self, ctx, row_ptr, col, xy, node_type, belief_id, beliefs):
+        self.ctx = ctx
+        self.row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        self.col = np.ascontiguousarray(col, np.int32)
+        self.xy = _f64(xy, 2)
+        self.node_type = np.ascontiguousarray(node_type, np.uint8)
+        self.belief_id = np.ascontiguousarray(belief_id, np.int32)
+        self.beliefs = np.ascontiguousarray(np.atleast_2d(np.asarray(beliefs, np.float64)))
+        self.V = len(self.xy)
+        assert len(self.row_ptr) == self.V + 1 and len(self.node_type) == self.V and len(self.belief_id) == self.V
+
+    def _graph_args(self):
+        B, nw = self.beliefs.shape
+        return (self.V, _p(self.row_ptr), _p(self.col), _p(self.xy), _p(self.node_type), _p(self.belief_id), _p(self.beliefs), B, nw)
+
+    def conditional_dijkstra(self, final_node_ids):
+        fin = np.ascontiguousarray(final_node_ids, np.int32)
+        out = np.empty(self.V)
+        sweeps = C.c_int32()
+        c = self.ctx
+        c.check(c.lib.porrt_conditional_dijkstra(c.h, *self._graph_args(), _p(fin), len(fin), _p(out), C.byref(sweeps)))
+        self.sweeps = sweeps.value
+        return out
+
+    def extract_policy(self, expected_costs_to_goals):
+        """-> (belief_node[k], parent[k], is_leaf[k], expected_cost) in the reference's creation order"""
+        dist = _f64(expected_costs_to_goals)
+        c = self.ctx
+        cap = 1024
+        n, cost = C.c_int64(), C.c_double()
+        while True:
+            node, parent = np.empty(cap, np.int32), np.empty(cap, np.int32)
+            leaf = np.empty(cap, np.uint8)
+            rc = c.lib.porrt_extract_policy_graph(c.h, *self._graph_args(), _p(dist), _p(node), _p(parent), _p(leaf), cap,
+                                                  C.byref(n), C.byref(cost))
+            if rc == ERR_CAPACITY:
+                cap = max(n.value, 2 * cap)
+                continue
+            c.check(rc)
+            break
+        k = n.value
+        return node[:k].copy(), parent[:k].copy(), leaf[:k].copy(), cost.value
+
+
 def words_from_bits(bits):
     """[n, n_worlds] 0/1 -> [n, ceil(n_worlds/64)] u64 (bit w of word w/64 = world w)"""
     bits = np.atleast_2d(np.asarray(bits, np.uint8))

@@ -656,3 +656,143 @@ def test_sharded_paths_multi_gpu():
            "--master-port", str(port), os.path.join(root, "scripts", "multi_gpu_check.py")]
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "multi_gpu_check: ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ---------------------------------------------------------------------------------------------- explicit belief graphs
+class _RecordingBeliefGraph:
+    """stands in for O.BeliefGraph while the reference's hand-built test graphs are constructed: keeps the oracle graph and
+    the (state, belief_id, type) / edge lists the product needs as arrays"""
+
+    def __init__(self, beliefs):
+        self.o = _ORACLE_BG(beliefs)
+        self.beliefs = np.asarray(beliefs, np.float64)
+        self.nodes, self.children = [], []
+
+    def add_node(self, s, belief_id, node_type):
+        self.nodes.append((tuple(s), belief_id, node_type))
+        self.children.append([])
+        return self.o.add_node(s, belief_id, node_type)
+
+    def add_edge(self, a, b):
+        self.children[a].append(b)
+        self.o.add_edge(a, b)
+
+    def product(self, ctx):
+        rp = np.zeros(len(self.nodes) + 1, np.int64)
+        for k, c in enumerate(self.children):
+            rp[k + 1] = rp[k] + len(c)
+        col = np.array([v for c in self.children for v in c], np.int32)
+        xy = np.array([n[0] for n in self.nodes], np.float64)
+        return P.BeliefGraph(ctx, rp, col, xy, [n[2] for n in self.nodes], [n[1] for n in self.nodes], self.beliefs)
+
+
+_ORACLE_BG = O.BeliefGraph
+
+
+def _check_policy(g, pg, d):
+    opol = g.o.extract_policy(d)
+    node, parent, leaf, cost = pg.extract_policy(d)
+    np.testing.assert_array_equal(node.astype(np.int64), opol.original)
+    np.testing.assert_array_equal(parent.astype(np.int64), opol.parent)
+    np.testing.assert_array_equal(np.nonzero(leaf)[0], opol.leafs)
+    assert cost == opol.expected_costs
+    return opol
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_conditional_dijkstra_golden_through_gpu(ctx, which, monkeypatch):  # belief_graph.rs:500-567
+    import test_oracle_golden as golden
+    monkeypatch.setattr(O, "BeliefGraph", _RecordingBeliefGraph)
+    bs = [[0.4, 0.6], [1.0, 0.0], [0.0, 1.0]]
+    g = golden.create_graph_1(bs) if which == 1 else golden.create_graph_2(bs)
+    finals = [3, 10, 16] if which == 1 else [8, 17, 27]
+    pg = g.product(ctx)
+    d = pg.conditional_dijkstra(finals)
+    np.testing.assert_array_equal(d, g.o.conditional_dijkstra(finals))        # bit-exact f64
+    if which == 1:
+        assert d[4] == bs[0][0] * d[5] + bs[0][1] * d[11]                      # belief_graph.rs:528
+        assert d[0] < d[1] and d[4] < d[0] and d[16] < d[15]
+    else:
+        assert int(np.argmax(d)) == 10 and d.max() == 8.0                      # :557-560
+    opol = _check_policy(g, pg, d)
+    assert len(opol.leafs) == 2
+
+
+def test_conditional_dijkstra_random_graphs(ctx):
+    """random Action / Observation graphs (zero-length observation edges, unreachable parts, several finals) against the
+    oracle's label-correcting heap version: identical bits, identical policy"""
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        nb, nw = 6, 4
+        beliefs = rng.uniform(0.05, 1.0, (nb, nw))
+        beliefs[1:, :] *= rng.integers(0, 2, (nb - 1, nw)) | np.eye(nw, dtype=np.int64)[rng.integers(0, nw, nb - 1)]
+        beliefs /= beliefs.sum(1, keepdims=True)
+        n_base = 300 + 50 * trial
+        pts = rng.uniform(-1, 1, (n_base, 2))
+        g = _RecordingBeliefGraph(beliefs)
+        ids = {}
+        for b in range(nb):
+            for k in range(n_base):
+                ids[(k, b)] = g.add_node(pts[k], b, O.ACTION)
+        # observation nodes: node (k, 0) observes into two other beliefs with overlapping support
+        obs = set(rng.choice(n_base, n_base // 10, replace=False).tolist()) - {0}
+        for k in obs:
+            kids = [b for b in rng.choice(np.arange(1, nb), 2, replace=False)
+                    if (np.where(beliefs[b] > 0, beliefs[0], 0.0)).sum() > 0]
+            if not kids:
+                continue
+            g.nodes[ids[(k, 0)]] = (g.nodes[ids[(k, 0)]][0], 0, O.OBSERVATION)
+            g.o = None
+            for b in kids:
+                g.children[ids[(k, 0)]].append(ids[(k, b)])
+        # action edges between near base nodes, inside every belief, skipping observation nodes as sources
+        d2 = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+        near = [np.nonzero((d2[k] < 0.03) & (np.arange(n_base) != k))[0] for k in range(n_base)]
+        for b in range(nb):
+            for k in range(n_base):
+                if g.nodes[ids[(k, b)]][2] == O.OBSERVATION:
+                    continue
+                for j in near[k]:
+                    g.children[ids[(k, b)]].append(ids[(int(j), b)])
+        # rebuild the oracle graph with the final types / edges (types were changed after add_node above)
+        og = _ORACLE_BG(beliefs)
+        for s, b, t in g.nodes:
+            og.add_node(s, b, t)
+        for a, ch in enumerate(g.children):
+            for c in ch:
+                og.add_edge(a, c)
+        g.o = og
+        finals = [ids[(int(k), b)] for b in range(1, nb) for k in rng.choice(n_base, 2, replace=False)]
+        pg = g.product(ctx)
+        d = pg.conditional_dijkstra(finals)
+        np.testing.assert_array_equal(d, og.conditional_dijkstra(finals))
+        assert np.isfinite(d).sum() > n_base
+        if np.isfinite(d[0]):
+            _check_policy(g, pg, d)
+
+
+def test_conditional_dijkstra_panics(ctx):
+    """belief_graph.rs:130 / :140: an evaluated Observation node with p == 0 towards a child, an Unknown-typed parent of a
+    reached node; neither fires when the offending node is never evaluated"""
+    beliefs = [[0.5, 0.5], [1.0, 0.0], [0.0, 1.0]]
+    xy = [[0, 0], [1, 0], [2, 0], [3, 0]]
+
+    def run(types, bids, edges, finals):
+        rp = np.zeros(5, np.int64)
+        for a, _ in edges:
+            rp[a + 1:] += 1
+        col = [b for a, b in sorted(edges, key=lambda e: e[0])]
+        return P.BeliefGraph(ctx, rp, col, xy, types, bids, beliefs).conditional_dijkstra(finals)
+
+    A_, O_, U_ = P.NODE_ACTION, P.NODE_OBSERVATION, P.NODE_UNKNOWN
+    # node 1 (belief 1) "observes" into belief 2: p = 0 -> panic once its child 2 is reached
+    with pytest.raises(P.PorrtError) as e:
+        run([A_, O_, A_, A_], [0, 1, 2, 2], [(0, 1), (1, 2), (2, 3)], [3])
+    assert e.value.code == 5
+    d = run([A_, O_, A_, A_], [0, 1, 2, 2], [(0, 1), (1, 2), (2, 3)], [])      # nothing reached: no evaluation, no panic
+    assert np.isinf(d).all()
+    with pytest.raises(P.PorrtError) as e:
+        run([A_, U_, A_, A_], [0, 0, 0, 0], [(0, 1), (1, 2), (2, 3)], [3])
+    assert e.value.code == 5
+    d = run([A_, A_, A_, U_], [0, 0, 0, 0], [(0, 1), (1, 2), (2, 3)], [2])      # the Unknown node has no reached child
+    np.testing.assert_array_equal(d, [2.0, 1.0, 0.0, np.inf])
