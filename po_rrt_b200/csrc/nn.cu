@@ -470,14 +470,15 @@ __global__ void copy_u32_i32_kernel(const uint32_t* __restrict__ in, int64_t n, 
 #define SEG_SORT_CAP 256
 #define SEG_SORT_WARPS 4
 __global__ void __launch_bounds__(SEG_SORT_WARPS * 32) seg_sort_small_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ ids,
-                                                                             const int32_t* __restrict__ key_of_id, int32_t* __restrict__ n_big) {
+                                                                             const int32_t* __restrict__ key_of_id, int32_t* __restrict__ n_big,
+                                                                             int min_len /* shorter segments are already sorted */) {
   __shared__ uint64_t s_kv[SEG_SORT_WARPS][SEG_SORT_CAP];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t seg = (int64_t)blockIdx.x * SEG_SORT_WARPS + wib;
   if (seg >= m) return;
   const int64_t s = offsets[seg];
   const int len = (int)min((int64_t)0x7fffffff, offsets[seg + 1] - s);
-  if (len <= 1) return;
+  if (len < min_len) return;
   if (len > SEG_SORT_CAP) { if (lane == 0) atomicAdd(n_big, 1); return; }
   int np2 = 2;
   while (np2 < len) np2 <<= 1;
@@ -506,19 +507,116 @@ __global__ void __launch_bounds__(SEG_SORT_WARPS * 32) seg_sort_small_kernel(con
   for (int i = lane; i < len; i += 32) ids[s + i] = (int32_t)(uint32_t)kv[i];
 }
 
-// key_limit: all keys (ids or key_of_id values) are < key_limit
+// Register path for the common case (<= 128 entries; a radius query at the c5 shape returns ~43): one warp per segment, R
+// 32-bit values per lane (element i = r * 32 + lane), bitonic network by __shfl_xor (partner in another lane) or a register
+// swap (partner in the same lane); no shared memory, no barriers.  Sorting values are the ids themselves, or -- BY_KEY --
+// the keys key_of_id[id], which must then be a permutation of 0..key_limit-1 (kd pre-order ranks are): the sorted keys are
+// mapped back through id_of_key.  Segments of 129..256 entries are counted in n_mid (shared-memory network above), longer
+// ones in n_big (global radix sort).
+template <int R>
+__device__ __forceinline__ void warp_bitonic_u32(uint32_t (&v)[R], int lane, int np2) {
+#pragma unroll
+  for (int k = 2; k <= 32 * R; k <<= 1) {
+    if (k > np2) break;
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if ((r & jr) == 0) {
+            const bool up = (((r << 5) & k) == 0);
+            const uint32_t a = v[r], b = v[r | jr];
+            const uint32_t lo = min(a, b), hi = max(a, b);
+            v[r] = up ? lo : hi; v[r | jr] = up ? hi : lo;
+          }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool up = ((((r << 5) | lane) & k) == 0);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, v[r], j);
+          v[r] = (lower == up) ? min(v[r], other) : max(v[r], other);
+        }
+      }
+    }
+  }
+}
+template <int R, bool BY_KEY>
+__device__ __forceinline__ void seg_sort_regs(int32_t* __restrict__ seg_ids, int len, int lane, const int32_t* __restrict__ key_of_id,
+                                              const int32_t* __restrict__ id_of_key) {
+  uint32_t v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = r * 32 + lane;
+    v[r] = 0xffffffffu;
+    if (i < len) { const int32_t id = seg_ids[i]; v[r] = BY_KEY ? (uint32_t)key_of_id[id] : (uint32_t)id; }
+  }
+  int np2 = 2;
+  while (np2 < len) np2 <<= 1;
+  warp_bitonic_u32<R>(v, lane, np2);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = r * 32 + lane;
+    if (i < len) seg_ids[i] = BY_KEY ? id_of_key[v[r]] : (int32_t)v[r];
+  }
+}
+#define SEG_REG_WARPS 8
+#define SEG_REG_CAP 128
+template <bool BY_KEY>
+__global__ void __launch_bounds__(SEG_REG_WARPS * 32) seg_sort_reg_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ ids,
+                                                                          const int32_t* __restrict__ key_of_id, const int32_t* __restrict__ id_of_key,
+                                                                          int32_t* __restrict__ n_mid_big) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * SEG_REG_WARPS + (threadIdx.x >> 5);
+  if (seg >= m) return;
+  const int64_t s = offsets[seg];
+  const int64_t len64 = offsets[seg + 1] - s;
+  if (len64 <= 1) return;
+  if (len64 > SEG_REG_CAP) { if (lane == 0) atomicAdd(&n_mid_big[len64 > SEG_SORT_CAP ? 1 : 0], 1); return; }
+  const int len = (int)len64;
+  if (len <= 32) seg_sort_regs<1, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
+  else if (len <= 64) seg_sort_regs<2, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
+  else seg_sort_regs<4, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
+}
+__global__ void invert_perm_kernel(const int32_t* __restrict__ key_of_id, int64_t n, int32_t* __restrict__ id_of_key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) id_of_key[key_of_id[i]] = (int32_t)i;
+}
+
+// key_limit: all keys (ids or key_of_id values) are < key_limit; key_of_id (if given) is a permutation of 0..key_limit-1
 int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev, const int32_t* key_of_id_dev, int64_t key_limit) {
   cudaStream_t st = ctx->stream;
   if (m <= 0) return PORRT_OK;
-  CUDA_TRY(ctx, ctx->scratch[4].ensure(16));
-  int32_t* d_big = ctx->scratch[4].as<int32_t>();
-  CUDA_TRY(ctx, cudaMemsetAsync(d_big, 0, 4, st));
-  seg_sort_small_kernel<<<div_up(m, SEG_SORT_WARPS), SEG_SORT_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_big);
-  LAUNCH_CHECK(ctx);
+  static const bool no_regs = getenv("PORRT_SEGSORT_NO_REGS") != nullptr;   // A/B switch: shared-memory network for everything
+  CUDA_TRY(ctx, ctx->scratch[4].ensure(16 + (key_of_id_dev ? (size_t)key_limit * 4 : 0)));
+  int32_t* d_big = ctx->scratch[4].as<int32_t>();   // [0] n_mid (129..256), [1] n_big (> 256)
+  int32_t* d_inv = d_big + 4;
+  CUDA_TRY(ctx, cudaMemsetAsync(d_big, 0, 8, st));
+  int32_t n_mid = 1, n_big = 0;
+  if (!no_regs) {
+    if (key_of_id_dev) {
+      invert_perm_kernel<<<div_up(key_limit, 256), 256, 0, st>>>(key_of_id_dev, key_limit, d_inv);
+      LAUNCH_CHECK(ctx);
+      seg_sort_reg_kernel<true><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_inv, d_big);
+    } else {
+      seg_sort_reg_kernel<false><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, nullptr, nullptr, d_big);
+    }
+    LAUNCH_CHECK(ctx);
+    int32_t cnt[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(cnt, d_big, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    n_mid = cnt[0]; n_big = cnt[1];
+    if (n_mid == 0 && n_big == 0) return PORRT_OK;
+  }
   int64_t total = 0;
-  int32_t n_big = 0;
+  if (n_mid > 0) {
+    CUDA_TRY(ctx, cudaMemsetAsync(d_big, 0, 4, st));
+    seg_sort_small_kernel<<<div_up(m, SEG_SORT_WARPS), SEG_SORT_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_big, no_regs ? 2 : SEG_REG_CAP + 1);
+    LAUNCH_CHECK(ctx);
+    if (no_regs) CUDA_TRY(ctx, cudaMemcpyAsync(&n_big, d_big, 4, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(&n_big, d_big, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   if (n_big == 0 || total <= 1) return PORRT_OK;
   // some segment exceeds the shared-memory network: one global stable LSD radix sort on (segment, key) orders them all

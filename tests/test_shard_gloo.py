@@ -34,6 +34,22 @@ def _worker(rank, world, port, n_edges, out_dir):
     lo, hi = shard.shard_range(n_edges, rank, world)
     local = torch.from_numpy(omap.edge_validity(a[lo:hi], b[lo:hi]))        # this rank's slice only
     full = shard.all_gather_shards(local, n_edges)
+    # the 128-byte ncclUniqueId travels from rank 0 to everybody (shard.init_comm's host-side step); rank 0 really asks the library
+    from po_rrt_b200 import _lib
+    import ctypes as C
+
+    def make_id():
+        buf = np.zeros(128, np.uint8)
+        assert _lib.load().porrt_comm_unique_id(buf.ctypes.data_as(C.c_void_p)) == 0
+        return buf.tolist()
+    uid = shard.exchange_unique_id(make_id)
+    assert len(uid) == 128
+    gathered = [None] * world
+    dist.all_gather_object(gathered, uid)
+    assert all(g == gathered[0] for g in gathered)
+    lo_c, hi_c = C.c_int64(), C.c_int64()
+    assert _lib.load().porrt_shard_range(n_edges, rank, world, C.byref(lo_c), C.byref(hi_c)) == 0
+    assert (lo_c.value, hi_c.value) == (lo, hi)          # the library shards exactly like shard.py
     t = shard.max_over_ranks(1.0 + rank)
     if rank == 0:
         np.save(os.path.join(out_dir, "gathered.npy"), full.numpy())
