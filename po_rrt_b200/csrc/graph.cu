@@ -662,6 +662,7 @@ struct BeliefDev {
   const int64_t* row_ptr; const int32_t* col; const int32_t* edge_vid; const double* cost;
   const int32_t* node_vid; const int32_t* node_set;
   const uint8_t* compat;      // [B][n_validities]
+  const uint8_t* compat_t;    // [n_validities][B]: the threads of a node (consecutive beliefs) read consecutive bytes
   const int64_t* succ_ptr;    // [n_sets * B + 1]
   const int32_t* succ_belief; const double* succ_p;
   int64_t V; int32_t B, n_validities;
@@ -705,13 +706,31 @@ __global__ void type_finish_kernel(uint8_t* __restrict__ type, int64_t n) {
 // One pull sweep of conditional_dijkstra's backup (belief_graph.rs:117-146):
 //   Action     : alt = min_v  norm2(u,v) + dist[v]                      (:121-124)
 //   Observation: alt = sum_vv p(u->vv) * (0.0 + dist[vv]) in stored order (:125-135; obs edges keep the state => cost 0.0)
+// Work skipping: a backup can only change if one of its inputs changed since it was last evaluated.  node_epoch[n] = last sweep
+// in which any belief of node n changed; before sweep s, belief_active_kernel marks the nodes with a child (action edges) or
+// themselves (observation edges stay on the node) changed in sweep s-1; all other nodes saw their inputs' final values when they
+// were evaluated in sweep s-1 (kernel boundary) and are skipped.  Sweep 1 evaluates everything.
+__global__ void belief_active_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int64_t V,
+                                     const int32_t* __restrict__ node_epoch, int32_t sweep, uint8_t* __restrict__ active) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= V) return;
+  bool a = sweep <= 1 || node_epoch[n] == sweep - 1;
+  if (!a)
+    for (int64_t e = row_ptr[n] + lane; e < row_ptr[n + 1]; e += 32) a |= node_epoch[col[e]] == sweep - 1;
+  a = __any_sync(0xffffffffu, a);
+  if (lane == 0) active[n] = a ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) belief_sweep_kernel(BeliefDev g, const uint8_t* __restrict__ type, double* __restrict__ dist,
-                                                           int32_t* __restrict__ changed) {
+                                                           int32_t* __restrict__ changed, const uint8_t* __restrict__ active,
+                                                           int32_t* __restrict__ node_epoch, int32_t sweep) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.V * g.B) return;
+  const int64_t n = t / g.B;
+  if (active && !active[n]) return;
   const uint8_t ty = type[t];
   if (ty != PORRT_NODE_ACTION && ty != PORRT_NODE_OBSERVATION) return;
-  const int64_t n = t / g.B;
   const int b = (int)(t - n * g.B);
   const double old = dist[t];
   double alt;
@@ -726,15 +745,15 @@ __global__ void __launch_bounds__(256) belief_sweep_kernel(BeliefDev g, const ui
     }
   } else {
     alt = INFINITY;
-    const uint8_t* cm = g.compat + (int64_t)b * g.n_validities;
+    const uint8_t* cm = g.compat_t + b;
     for (int64_t e = g.row_ptr[n]; e < g.row_ptr[n + 1]; ++e) {
       const int32_t c = g.col[e];
-      if (!cm[g.node_vid[c]] || !cm[g.edge_vid[e]]) continue;
+      if (!cm[(int64_t)g.node_vid[c] * g.B] || !cm[(int64_t)g.edge_vid[e] * g.B]) continue;
       const double a = __dadd_rn(g.cost[e], dist[(int64_t)c * g.B + b]);
       if (a < alt) alt = a;
     }
   }
-  if (alt < old) { dist[t] = alt; *changed = 1; }
+  if (alt < old) { dist[t] = alt; *changed = 1; if (node_epoch) node_epoch[n] = sweep; }
 }
 
 PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const int32_t* edge_vid,
@@ -840,7 +859,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
 
   DevBuf& g = ctx->scratch[3];
   const size_t n_succ = succ_belief.size();
-  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 16 + (size_t)V * 24 + succ_ptr.size() * 8 + n_succ * 12 + compat.size() + (size_t)V * B * 9 +
+  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 16 + (size_t)V * 24 + succ_ptr.size() * 8 + n_succ * 12 + 2 * compat.size() + (size_t)V * 5 + (size_t)V * B * 9 +
                       zero_idx.size() * 8 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
@@ -858,6 +877,9 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   int32_t* d_succ_b = (int32_t*)take(n_succ * 4);
   int32_t* d_changed = (int32_t*)take(16);
   uint8_t* d_compat = (uint8_t*)take(compat.size());
+  uint8_t* d_compat_t = (uint8_t*)take(compat.size());
+  uint8_t* d_active = (uint8_t*)take((size_t)V);
+  int32_t* d_epoch = (int32_t*)take((size_t)V * 4);
   uint8_t* d_type = (uint8_t*)take((size_t)V * B);
   int64_t* d_zero = (int64_t*)take(zero_idx.size() * 8 + 8);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -874,6 +896,11 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_p, succ_p.data(), n_succ * 8, cudaMemcpyHostToDevice, st));
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, compat.data(), compat.size(), cudaMemcpyHostToDevice, st));
+  std::vector<uint8_t> compat_t(compat.size());
+  for (int bb = 0; bb < B; ++bb)
+    for (int v = 0; v < n_validities; ++v) compat_t[(size_t)v * B + bb] = compat[(size_t)bb * n_validities + v];
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_compat_t, compat_t.data(), compat_t.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_epoch, 0, (size_t)V * 4, st));
   fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_dist, V * (int64_t)B);
   LAUNCH_CHECK(ctx);
   if (!zero_idx.empty()) {
@@ -883,7 +910,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   }
   edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
   LAUNCH_CHECK(ctx);
-  BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, d_succ_ptr, d_succ_b, d_succ_p, V, B, n_validities};
+  BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, d_compat_t, d_succ_ptr, d_succ_b, d_succ_p, V, B, n_validities};
   const int blocks = div_up(V * (int64_t)B, 256);
   belief_type_kernel<<<blocks, 256, 0, st>>>(gd, d_type);
   LAUNCH_CHECK(ctx);
@@ -891,13 +918,18 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
   int sweeps = 0;
   const int BATCH = 8;
+  static const bool skip = getenv("PORRT_BELIEF_NO_SKIP") == nullptr;   // A/B switch for the work skipping
   for (;;) {
     CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
     for (int k = 0; k < BATCH; ++k) {
-      belief_sweep_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_dist, d_changed);
+      ++sweeps;
+      if (skip) {
+        belief_active_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, V, d_epoch, sweeps, d_active);
+        LAUNCH_CHECK(ctx);
+      }
+      belief_sweep_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_dist, d_changed, skip ? d_active : nullptr, skip ? d_epoch : nullptr, sweeps);
       LAUNCH_CHECK(ctx);
     }
-    sweeps += BATCH;
     int32_t changed = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));

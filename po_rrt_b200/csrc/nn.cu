@@ -507,12 +507,12 @@ __global__ void __launch_bounds__(SEG_SORT_WARPS * 32) seg_sort_small_kernel(con
   for (int i = lane; i < len; i += 32) ids[s + i] = (int32_t)(uint32_t)kv[i];
 }
 
-// Register path for the common case (<= 128 entries; a radius query at the c5 shape returns ~43): one warp per segment, R
+// Register path for the common case (<= 256 entries; a radius query at the c5 shape returns ~43): one warp per segment, R
 // 32-bit values per lane (element i = r * 32 + lane), bitonic network by __shfl_xor (partner in another lane) or a register
 // swap (partner in the same lane); no shared memory, no barriers.  Sorting values are the ids themselves, or -- BY_KEY --
 // the keys key_of_id[id], which must then be a permutation of 0..key_limit-1 (kd pre-order ranks are): the sorted keys are
-// mapped back through id_of_key.  Segments of 129..256 entries are counted in n_mid (shared-memory network above), longer
-// ones in n_big (global radix sort).
+// mapped back through id_of_key.  Longer segments are counted in n_big (global radix sort); the shared-memory network above
+// remains as the A/B variant (PORRT_SEGSORT_NO_REGS).
 template <int R>
 __device__ __forceinline__ void warp_bitonic_u32(uint32_t (&v)[R], int lane, int np2) {
 #pragma unroll
@@ -562,7 +562,7 @@ __device__ __forceinline__ void seg_sort_regs(int32_t* __restrict__ seg_ids, int
   }
 }
 #define SEG_REG_WARPS 8
-#define SEG_REG_CAP 128
+#define SEG_REG_CAP 256
 template <bool BY_KEY>
 __global__ void __launch_bounds__(SEG_REG_WARPS * 32) seg_sort_reg_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ ids,
                                                                           const int32_t* __restrict__ key_of_id, const int32_t* __restrict__ id_of_key,
@@ -577,7 +577,8 @@ __global__ void __launch_bounds__(SEG_REG_WARPS * 32) seg_sort_reg_kernel(const 
   const int len = (int)len64;
   if (len <= 32) seg_sort_regs<1, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
   else if (len <= 64) seg_sort_regs<2, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
-  else seg_sort_regs<4, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
+  else if (len <= 128) seg_sort_regs<4, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
+  else seg_sort_regs<8, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
 }
 __global__ void invert_perm_kernel(const int32_t* __restrict__ key_of_id, int64_t n, int32_t* __restrict__ id_of_key) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -668,14 +669,15 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
   if (rc) return rc;
   tmark(ctx);
   if (out_total) *out_total = total;
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (total > cap || (total > 0 && !out_ids)) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return porrt_fail(ctx, PORRT_ERR_CAPACITY, "radius_query: out_ids too small");
   }
   rc = segments_sort_by_key_dev(ctx, d_off, m, ctx->scratch[2].as<int32_t>(), nullptr, V);
   if (rc) return rc;
   tmark(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(out_ids, ctx->scratch[2].p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
   tmark(ctx);
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
