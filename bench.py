@@ -259,20 +259,35 @@ def multi_gpu_measurements(ctx, pmap, rank, world, dev):
                      "queries_per_s_e2e": Q * world / best[1]}
     out["nn"] = res
 
-    shard.init_comm(ctx)
+    # replicas: every rank builds its own roadmap (its own sample stream) at the same time -- how independent planning problems
+    # / seeds scale (weak); ms = max over ranks for one roadmap each
     pin_col = torch.empty(64 * V, dtype=torch.int32).pin_memory().numpy()
+    my_pts = synth.points(V, seed=30 + rank)
     best = None
     for _ in range(3):
         dist.barrier()
         prm = P.PRM(pmap)
-        t0 = time.perf_counter(); prm.grow_graph(pts, 0.1, 2.0, col_out=pin_col); t1 = time.perf_counter()
+        t0 = time.perf_counter(); prm.grow_graph(my_pts, 0.1, 2.0, col_out=pin_col); t1 = time.perf_counter()
+        wall = rmax(t1 - t0)
+        if best is None or wall < best:
+            best = wall
+    out["prm_build_replicas"] = {"V": V, "roadmaps": world, "ms_max_over_ranks": 1e3 * best, "roadmaps_per_s": world / best,
+                                 "scaling": "weak"}
+
+    shard.init_comm(ctx)
+    best = None
+    for _ in range(3):
+        dist.barrier()
+        prm = P.PRM(pmap)
+        t0 = time.perf_counter(); prm.grow_graph(pts, 0.1, 2.0, col_out=pin_col, fetch_col=(rank == 0)); t1 = time.perf_counter()
         wall = rmax(t1 - t0)
         if best is None or wall < best[0]:
-            best = (wall, [round(float(x), 3) for x in prm.phase_ms[:7]], ctx.last_phase_ms()[:1], int(len(prm.col)))
+            best = (wall, [round(float(x), 3) for x in prm.phase_ms[:7]], ctx.last_phase_ms()[:1], int(prm.row_ptr[-1]))
     out["prm_build_sharded"] = {"V": V, "ms_max_over_ranks": 1e3 * best[0], "directed_edges": best[3], "exchange_ms": best[2],
                                 "phase_ms_rank0[radii,bin,radius,kd_rank,order,edges,csr]": best[1], "scaling": "strong",
                                 "note": "one roadmap built by all ranks; bins, kd ranks and the CSR assembly are replicated, "
-                                        "radius + order + edge batches are sharded"}
+                                        "radius + order + edge batches are sharded; the CSR ends device-resident on every rank, "
+                                        "rank 0 alone copies the column array to the host"}
     ctx.comm_destroy()
     return out
 
@@ -383,8 +398,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    occ, zones, a, b = make_inputs(args, rank)
     ctx = P.Context(local_rank)
+    # host locality: this process's pinned buffers and copy-issuing thread sit on the NUMA node next to its GPU
+    # (N ranks on a two-socket box otherwise push their H2D / D2H through the socket interconnect); undone before the CPU baseline
+    affinity0 = os.sched_getaffinity(0)
+    numa_node = ctx.bind_host_thread() if world > 1 else -1
+    occ, zones, a, b = make_inputs(args, rank)
     pmap = P.Map(ctx, occ, [-1.0, -1.0], [1.0, 1.0])
     pmap.add_zones(zones, 0.3)
     assert pmap.n_worlds() == N_WORLDS
@@ -487,6 +506,7 @@ def main():
             multi = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
 
     line = None
+    os.sched_setaffinity(0, affinity0)
     if rank == 0:
         base, oracle_vid, _ = cpu_baseline(args, occ, zones, a, b)
         n = len(oracle_vid)
@@ -499,6 +519,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * E, "d2h_bytes_per_step": 12 * E,
                         "steps": e2e_steps, "edges_per_s": e2e_value / N_WORLDS},
                 "gpu_launches": int(launches), "clocks": clocks, "parity_checked_edges": n}
+        line["config"]["host_numa_node_rank0"] = numa_node
 
     # ---- side measurements of the other BASELINE metrics (kNN queries/s, PRM build ms); not part of `value`
     if rank == 0 and not args.no_extras:

@@ -57,6 +57,9 @@ int32_t porrt_ctx_destroy(porrt_ctx* ctx);
  * stream.  Pass cudaStreamLegacy ((void*)1) to address the legacy default stream explicitly. */
 int32_t porrt_ctx_set_stream(porrt_ctx* ctx, void* cuda_stream);
 int32_t porrt_ctx_synchronize(porrt_ctx* ctx);
+/* bind the calling host thread to the CPUs of the NUMA node next to the ctx's GPU (pinned buffers touched afterwards land there);
+ * *out_node (nullable) = that node, -1 if unknown / nothing changed.  Call it once per process before allocating host buffers. */
+int32_t porrt_ctx_bind_host_thread(porrt_ctx* ctx, int32_t* out_node);
 const char* porrt_last_error(porrt_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t porrt_ctx_launch_count(porrt_ctx* ctx);

@@ -19,6 +19,7 @@ SIGNATURES = {
     "porrt_ctx_destroy": (i32, [vp]),
     "porrt_ctx_set_stream": (i32, [vp, vp]),
     "porrt_ctx_synchronize": (i32, [vp]),
+    "porrt_ctx_bind_host_thread": (i32, [vp, pp(i32)]),
     "porrt_last_error": (C.c_char_p, [vp]),
     "porrt_ctx_launch_count": (i64, [vp]),
     "porrt_ctx_last_phase_ms": (i32, [vp, vp, i32, pp(i32)]),

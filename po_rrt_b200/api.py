@@ -74,6 +74,12 @@ class Context:
     def synchronize(self):
         self.check(self.lib.porrt_ctx_synchronize(self.h))
 
+    def bind_host_thread(self):
+        """bind this thread to the NUMA node next to the GPU; returns the node (-1: unknown)"""
+        node = C.c_int32()
+        self.check(self.lib.porrt_ctx_bind_host_thread(self.h, C.byref(node)))
+        return node.value
+
     def launch_count(self):
         return self.lib.porrt_ctx_launch_count(self.h)
 
@@ -335,8 +341,9 @@ class PRM:
     def init(self, start):
         self.states = _f64(start, 2)
 
-    def grow_graph(self, samples, max_step, search_radius, col_out=None):
-        """samples: the ContinuousSampler stream (n_iter states); nodes = [init state] + samples"""
+    def grow_graph(self, samples, max_step, search_radius, col_out=None, fetch_col=True):
+        """samples: the ContinuousSampler stream (n_iter states); nodes = [init state] + samples.
+        fetch_col=False leaves the column array on the device (row_ptr still comes back)"""
         self.fns._need()
         xy = np.ascontiguousarray(np.vstack([self.states, _f64(samples, 2)]))
         n = len(xy)
@@ -346,6 +353,9 @@ class PRM:
                                           C.byref(n_edges), _p(self.phase_ms))
         if rc != ERR_CAPACITY:
             self.ctx.check(rc)
+        if not fetch_col:
+            self.states, self.row_ptr, self.col = xy, row_ptr, None
+            return self
         col = np.empty(n_edges.value, np.int32) if col_out is None else col_out
         self.ctx.check(self.ctx.lib.porrt_prm_fetch(self.ctx.h, None, _p(col), len(col)))
         self.states, self.row_ptr, self.col = xy, row_ptr, col[:n_edges.value]

@@ -1,4 +1,7 @@
 // ctx.cu -- context lifetime, stream plumbing (no compute kernels here).
+#include <ctype.h>
+#include <sched.h>
+
 #include "common.cuh"
 
 PORRT_API const char* porrt_version(void) { return "porrt_b200 0.1 (sm_100a)"; }
@@ -67,6 +70,54 @@ PORRT_API int32_t porrt_ctx_synchronize(porrt_ctx* ctx) {
   CTX_CHECK(ctx);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PORRT_OK;
+}
+
+// Host-side locality for the H2D / D2H pipelines: bind the CALLING thread to the CPUs of the NUMA node the ctx's GPU hangs off
+// (sysfs: /sys/bus/pci/devices/<bus id>/numa_node -> /sys/devices/system/node/node<N>/cpulist).  Pinned buffers touched after
+// this call land on that node (first touch), so N processes on a two-socket box do not push their copies through the socket
+// interconnect.  *out_node = the node (-1: unknown, nothing changed).  The reference is single-threaded; this is deployment glue.
+PORRT_API int32_t porrt_ctx_bind_host_thread(porrt_ctx* ctx, int32_t* out_node) {
+  CTX_CHECK(ctx);
+  if (out_node) *out_node = -1;
+  char bus[32] = {0};
+  CUDA_TRY(ctx, cudaDeviceGetPCIBusId(bus, sizeof(bus), ctx->device));
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[160];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return PORRT_OK;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  if (node < 0) return PORRT_OK;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return PORRT_OK;
+  char list[4096] = {0};
+  const bool got = fgets(list, sizeof(list), f) != nullptr;
+  fclose(f);
+  if (!got) return PORRT_OK;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n_cpus = 0;
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k < 1) continue;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); ++n_cpus; }
+  }
+  if (n_cpus == 0) return PORRT_OK;
+  // keep only CPUs this process is allowed to use (containers): an empty intersection leaves the affinity alone
+  cpu_set_t cur, both;
+  if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {
+    CPU_AND(&both, &set, &cur);
+    if (CPU_COUNT(&both) == 0) return PORRT_OK;
+    set = both;
+  }
+  if (sched_setaffinity(0, sizeof(set), &set) != 0) return PORRT_OK;
+  if (out_node) *out_node = node;
   return PORRT_OK;
 }
 

@@ -254,13 +254,19 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   // (neither needs the radii): ~3.6 ms at n = 1e6 that used to sit in front of the device work.
   CUDA_TRY(ctx, ctx->pin[1].ensure((size_t)n * 8));   // pinned: the upload after the join is one async DMA
   double* radius = ctx->pin[1].as<double>();
+  // multi-GPU (comm.cu): this rank answers the queries of new nodes [lo, hi) only -- and needs only their radii
+  const int world = ctx->comm_world;
+  int64_t lo = 0, hi = n;
+  if (world > 1) comm_shard_range(n, ctx->comm_rank, world, &lo, &hi);
+  const int64_t m = hi - lo;
   std::vector<std::thread> th;
   {
     int nt = (int)std::min<int64_t>(std::max(2u, std::thread::hardware_concurrency()) / 2, 8);   // leave cores to the driver's copies
-    if (n < 20000) nt = 1;
+    if (world > 1) nt = std::max(1, nt / world + 1);                                                // the box's cores are shared by all ranks
+    if (m < 20000) nt = 1;
     for (int t = 0; t < nt; ++t)
       th.emplace_back([=]() {
-        for (int64_t k = t; k < n; k += nt) radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, max_step, search_radius, 2);
+        for (int64_t k = lo + t; k < hi; k += nt) radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, max_step, search_radius, 2);
       });
   }
   struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); } } joiner{th};
@@ -299,17 +305,12 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
 
   for (auto& x : th) x.join();
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_radius, radius, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if (m > 0) CUDA_TRY(ctx, cudaMemcpyAsync(d_radius + lo, radius + lo, (size_t)m * 8, cudaMemcpyHostToDevice, st));
   iota_u32_kernel<<<div_up(n, 256), 256, 0, st>>>(d_prefix, n);   // prefix limit of query k = k: the tree before node k arrived
   LAUNCH_CHECK(ctx);
   t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;   // what is left of the radii after the overlap
 
-  // multi-GPU (comm.cu): this rank answers the queries of new nodes [lo, hi) only; bins and kd ranks are replicated
-  const int world = ctx->comm_world;
-  int64_t lo = 0, hi = n;
-  if (world > 1) comm_shard_range(n, ctx->comm_rank, world, &lo, &hi);
-  const int64_t m = hi - lo;
-
+  // (bins and kd ranks above are replicated on every rank; from here on the rank works on its shard [lo, hi))
   // 3. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
   int64_t total = 0;
   rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>() + 2 * lo, d_radius + lo, m, d_prefix + lo, nullptr, nullptr, d_off, &ctx->scratch[2], &total);
