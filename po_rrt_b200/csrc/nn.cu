@@ -563,22 +563,59 @@ __device__ __forceinline__ void seg_sort_regs(int32_t* __restrict__ seg_ids, int
 }
 #define SEG_REG_WARPS 8
 #define SEG_REG_CAP 256
+#define SEG_MID_CAP 4096
 template <bool BY_KEY>
 __global__ void __launch_bounds__(SEG_REG_WARPS * 32) seg_sort_reg_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ ids,
                                                                           const int32_t* __restrict__ key_of_id, const int32_t* __restrict__ id_of_key,
-                                                                          int32_t* __restrict__ n_mid_big) {
+                                                                          int32_t* __restrict__ n_mid_big, int32_t* __restrict__ mid_list) {
   const int lane = threadIdx.x & 31;
   const int64_t seg = (int64_t)blockIdx.x * SEG_REG_WARPS + (threadIdx.x >> 5);
   if (seg >= m) return;
   const int64_t s = offsets[seg];
   const int64_t len64 = offsets[seg + 1] - s;
   if (len64 <= 1) return;
-  if (len64 > SEG_REG_CAP) { if (lane == 0) atomicAdd(&n_mid_big[len64 > SEG_SORT_CAP ? 1 : 0], 1); return; }
+  if (len64 > SEG_REG_CAP) {   // 257..SEG_MID_CAP: listed for the block kernel below; longer: counted for the global radix sort
+    if (lane == 0) {
+      if (len64 > SEG_MID_CAP) atomicAdd(&n_mid_big[1], 1);
+      else mid_list[atomicAdd(&n_mid_big[0], 1)] = (int32_t)seg;
+    }
+    return;
+  }
   const int len = (int)len64;
   if (len <= 32) seg_sort_regs<1, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
   else if (len <= 64) seg_sort_regs<2, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
   else if (len <= 128) seg_sort_regs<4, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
   else seg_sort_regs<8, BY_KEY>(ids + s, len, lane, key_of_id, id_of_key);
+}
+// 257..4096 entries (the early rows of a PRM's late lists, wide radius queries): one block per listed segment, bitonic network
+// on 32-bit values in shared memory
+template <bool BY_KEY>
+__global__ void __launch_bounds__(256) seg_sort_mid_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ mid_list,
+                                                           int32_t* __restrict__ ids, const int32_t* __restrict__ key_of_id,
+                                                           const int32_t* __restrict__ id_of_key) {
+  __shared__ uint32_t s_v[SEG_MID_CAP];
+  const int64_t seg = mid_list[blockIdx.x];
+  const int64_t s = offsets[seg];
+  const int len = (int)(offsets[seg + 1] - s);
+  int np2 = 512;
+  while (np2 < len) np2 <<= 1;
+  for (int i = threadIdx.x; i < np2; i += 256) {
+    uint32_t v = 0xffffffffu;
+    if (i < len) { const int32_t id = ids[s + i]; v = BY_KEY ? (uint32_t)key_of_id[id] : (uint32_t)id; }
+    s_v[i] = v;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += 256) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const uint32_t a = s_v[i], b = s_v[p];
+        if ((a > b) == ((i & k) == 0)) { s_v[i] = b; s_v[p] = a; }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < len; i += 256) ids[s + i] = BY_KEY ? id_of_key[s_v[i]] : (int32_t)s_v[i];
 }
 __global__ void invert_perm_kernel(const int32_t* __restrict__ key_of_id, int64_t n, int32_t* __restrict__ id_of_key) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -590,32 +627,36 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
   cudaStream_t st = ctx->stream;
   if (m <= 0) return PORRT_OK;
   static const bool no_regs = getenv("PORRT_SEGSORT_NO_REGS") != nullptr;   // A/B switch: shared-memory network for everything
-  CUDA_TRY(ctx, ctx->scratch[4].ensure(16 + (key_of_id_dev ? (size_t)key_limit * 4 : 0)));
-  int32_t* d_big = ctx->scratch[4].as<int32_t>();   // [0] n_mid (129..256), [1] n_big (> 256)
-  int32_t* d_inv = d_big + 4;
+  CUDA_TRY(ctx, ctx->scratch[4].ensure(16 + (size_t)m * 4 + (key_of_id_dev ? (size_t)key_limit * 4 : 0)));
+  int32_t* d_big = ctx->scratch[4].as<int32_t>();   // [0] n_mid (257..4096, listed), [1] n_big (longer)
+  int32_t* d_mid_list = d_big + 4;
+  int32_t* d_inv = d_mid_list + m;
   CUDA_TRY(ctx, cudaMemsetAsync(d_big, 0, 8, st));
-  int32_t n_mid = 1, n_big = 0;
+  int32_t n_mid = 0, n_big = 0;
+  int64_t total = 0;
   if (!no_regs) {
     if (key_of_id_dev) {
       invert_perm_kernel<<<div_up(key_limit, 256), 256, 0, st>>>(key_of_id_dev, key_limit, d_inv);
       LAUNCH_CHECK(ctx);
-      seg_sort_reg_kernel<true><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_inv, d_big);
+      seg_sort_reg_kernel<true><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_inv, d_big, d_mid_list);
     } else {
-      seg_sort_reg_kernel<false><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, nullptr, nullptr, d_big);
+      seg_sort_reg_kernel<false><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, nullptr, nullptr, d_big, d_mid_list);
     }
     LAUNCH_CHECK(ctx);
     int32_t cnt[2] = {0, 0};
     CUDA_TRY(ctx, cudaMemcpyAsync(cnt, d_big, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     n_mid = cnt[0]; n_big = cnt[1];
-    if (n_mid == 0 && n_big == 0) return PORRT_OK;
-  }
-  int64_t total = 0;
-  if (n_mid > 0) {
-    CUDA_TRY(ctx, cudaMemsetAsync(d_big, 0, 4, st));
-    seg_sort_small_kernel<<<div_up(m, SEG_SORT_WARPS), SEG_SORT_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_big, no_regs ? 2 : SEG_REG_CAP + 1);
+    if (n_mid > 0 && n_big == 0) {
+      if (key_of_id_dev) seg_sort_mid_kernel<true><<<n_mid, 256, 0, st>>>(offsets_dev, d_mid_list, ids_dev, key_of_id_dev, d_inv);
+      else seg_sort_mid_kernel<false><<<n_mid, 256, 0, st>>>(offsets_dev, d_mid_list, ids_dev, nullptr, nullptr);
+      LAUNCH_CHECK(ctx);
+    }
+    if (n_big == 0) return PORRT_OK;
+  } else {
+    seg_sort_small_kernel<<<div_up(m, SEG_SORT_WARPS), SEG_SORT_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_big + 1, 2);
     LAUNCH_CHECK(ctx);
-    if (no_regs) CUDA_TRY(ctx, cudaMemcpyAsync(&n_big, d_big, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&n_big, d_big + 1, 4, cudaMemcpyDeviceToHost, st));
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -623,6 +664,7 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
   // some segment exceeds the shared-memory network: one global stable LSD radix sort on (segment, key) orders them all
   const int key_bits = bits_for((uint64_t)(key_limit > 1 ? key_limit - 1 : 1));
   const int seg_bits = bits_for((uint64_t)(m > 1 ? m - 1 : 1));
+  // (scratch 5 / 6 here, 8..10 inside radix_sort_pairs: callers keep their segment data elsewhere)
   CUDA_TRY(ctx, ctx->scratch[5].ensure((size_t)total * 8));
   CUDA_TRY(ctx, ctx->scratch[6].ensure((size_t)total * 4));
   uint64_t* keys = ctx->scratch[5].as<uint64_t>();

@@ -249,16 +249,20 @@ def test_radius_query_vs_oracle(ctx):
         np.testing.assert_array_equal(got[np.argsort(rank[got], kind="stable")], oids[ooffs[k]:ooffs[k + 1]])
 
 
-def test_radius_query_large_segments(ctx):
-    """> 256 hits per query: the shared-memory sorting network is bypassed for the global radix sort"""
+@pytest.mark.parametrize("huge", [False, True])
+def test_radius_query_large_segments(ctx, huge):
+    """> 256 hits per query: block-level sorting network (257..4096 entries); with `huge`, one query beyond that sends the call
+    to the global radix sort instead"""
     pts = synth.points(20_000, seed=33)
     q = synth.points(300, seed=34)
     otree = _oracle_tree(pts)
     tree = P.KdTree(ctx, pts, cell_size=0.05)
     radius = np.where(np.arange(300) % 3 == 0, 0.3, 0.02)
+    if huge:
+        radius[7] = 0.9
     offs, ids = tree.nearest_neighbors(q, radius)
     rank = tree.preorder_rank()
-    assert (np.diff(offs) > 256).any() and (np.diff(offs) < 64).any()
+    assert (np.diff(offs) > 256).any() and (np.diff(offs) < 64).any() and (np.diff(offs).max() > 4096) == huge
     for k in range(300):
         got = ids[offs[k]:offs[k + 1]]
         want = otree.nearest_neighbors(q[k], radius[k])
@@ -414,6 +418,13 @@ def test_prm_build_door(ctx):
 def test_prm_build_shelf_reference_params(ctx):  # prm.rs:136-155: grow_graph(0.1, 5.0, 1500)
     occ, zones = synth.shelf_map(200, n_zones=2)
     _prm_compare(ctx, occ, zones, P.SHELF, 1500, 0.1, 5.0)
+
+
+def test_prm_build_wide_rows(ctx):
+    """a wide connection radius: neighbour lists of ~170 and late lists beyond 256 entries (block-level segment sort)"""
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    prm, _ = _prm_compare(ctx, occ, zones, P.SHELF, 6000, 0.3, 5.0)
+    assert np.diff(prm.row_ptr).max() > 400
 
 
 def test_prm_plan_path(ctx):
