@@ -189,12 +189,14 @@ def side_measurements(ctx, pmap, args):
         ex["cpu_note"] = "oracle kd-tree (incremental insert %.2f s for 1e6 vertices), %d threads, %d-query sample" % (t_build, threads, qn)
         # PRM build (prm.rs grow_graph): total host call incl. H2D of the samples and D2H of the CSR into pinned memory
         ex["prm_build"] = {}
+        pin_pts = torch.from_numpy(pts).pin_memory().numpy()      # e2e from pinned host memory, like the edge arm
         for n_nodes in (10_000, 100_000, 1_000_000):
             pin_col = torch.empty(64 * n_nodes, dtype=torch.int32).pin_memory().numpy()
+            pin_row = torch.empty(n_nodes + 1, dtype=torch.int64).pin_memory().numpy()
             best = None
-            for _ in range(2):
+            for _ in range(3):
                 prm = P.PRM(pmap)
-                t0 = time.perf_counter(); prm.grow_graph(pts[:n_nodes], 0.1, 2.0, col_out=pin_col); t1 = time.perf_counter()
+                t0 = time.perf_counter(); prm.grow_graph(pin_pts[:n_nodes], 0.1, 2.0, col_out=pin_col, row_ptr_out=pin_row); t1 = time.perf_counter()
                 if best is None or t1 - t0 < best[0]:
                     best = (t1 - t0, [round(float(x), 3) for x in prm.phase_ms], int(len(prm.col)))
             ex["prm_build"]["V%d" % n_nodes] = {"ms": 1e3 * best[0], "directed_edges": best[2], "candidate_edge_checks": int(best[1][7]),
@@ -262,12 +264,14 @@ def multi_gpu_measurements(ctx, pmap, rank, world, dev):
     # replicas: every rank builds its own roadmap (its own sample stream) at the same time -- how independent planning problems
     # / seeds scale (weak); ms = max over ranks for one roadmap each
     pin_col = torch.empty(64 * V, dtype=torch.int32).pin_memory().numpy()
-    my_pts = synth.points(V, seed=30 + rank)
+    pin_row = torch.empty(V + 1, dtype=torch.int64).pin_memory().numpy()
+    my_pts = torch.from_numpy(synth.points(V, seed=30 + rank)).pin_memory().numpy()
+    pts = torch.from_numpy(pts).pin_memory().numpy()
     best = None
     for _ in range(3):
         dist.barrier()
         prm = P.PRM(pmap)
-        t0 = time.perf_counter(); prm.grow_graph(my_pts, 0.1, 2.0, col_out=pin_col); t1 = time.perf_counter()
+        t0 = time.perf_counter(); prm.grow_graph(my_pts, 0.1, 2.0, col_out=pin_col, row_ptr_out=pin_row); t1 = time.perf_counter()
         wall = rmax(t1 - t0)
         if best is None or wall < best:
             best = wall
@@ -279,7 +283,7 @@ def multi_gpu_measurements(ctx, pmap, rank, world, dev):
     for _ in range(3):
         dist.barrier()
         prm = P.PRM(pmap)
-        t0 = time.perf_counter(); prm.grow_graph(pts, 0.1, 2.0, col_out=pin_col, fetch_col=(rank == 0)); t1 = time.perf_counter()
+        t0 = time.perf_counter(); prm.grow_graph(pts, 0.1, 2.0, col_out=pin_col, fetch_col=(rank == 0), row_ptr_out=pin_row); t1 = time.perf_counter()
         wall = rmax(t1 - t0)
         if best is None or wall < best[0]:
             best = (wall, [round(float(x), 3) for x in prm.phase_ms[:7]], ctx.last_phase_ms()[:1], int(prm.row_ptr[-1]))

@@ -341,13 +341,15 @@ class PRM:
     def init(self, start):
         self.states = _f64(start, 2)
 
-    def grow_graph(self, samples, max_step, search_radius, col_out=None, fetch_col=True):
+    def grow_graph(self, samples, max_step, search_radius, col_out=None, fetch_col=True, row_ptr_out=None):
         """samples: the ContinuousSampler stream (n_iter states); nodes = [init state] + samples.
-        fetch_col=False leaves the column array on the device (row_ptr still comes back)"""
+        fetch_col=False leaves the column array on the device (row_ptr still comes back); col_out / row_ptr_out: caller-owned
+        (e.g. pinned) result buffers; samples are used in place (no host copy) when no init state precedes them"""
         self.fns._need()
-        xy = np.ascontiguousarray(np.vstack([self.states, _f64(samples, 2)]))
+        samples = _f64(samples, 2)
+        xy = samples if len(self.states) == 0 else np.ascontiguousarray(np.vstack([self.states, samples]))
         n = len(xy)
-        row_ptr = np.empty(n + 1, np.int64)
+        row_ptr = np.empty(n + 1, np.int64) if row_ptr_out is None else row_ptr_out[:n + 1]
         n_edges = C.c_int64()
         rc = self.ctx.lib.porrt_prm_build(self.ctx.h, _p(xy), n, max_step, search_radius, _p(row_ptr), None, 0,
                                           C.byref(n_edges), _p(self.phase_ms))
