@@ -189,6 +189,29 @@ int32_t porrt_extract_policy_graph(porrt_ctx* ctx, int64_t V, const int64_t* row
                                    int32_t n_worlds, const double* dist, int32_t* out_belief_node, int32_t* out_parent,
                                    uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost);
 
+/* ------------------------------------------------------------------ multi-modal PRM (map_shelves_tamp_prm.rs)
+ * MapShelfDomainTampPRM::plan (:308-326) for a given SCHEDULE.  The growth (grow_mm_prm, :328-397) never looks at validity
+ * results -- modes, observed zones and samples are decided by the RNG streams -- so the caller, who owns the samplers and the
+ * mode tree, passes what they decided and this call does the computing:
+ *   mode m owns the add_sample calls mode_node_ptr[m] .. mode_node_ptr[m+1]-1 of samples_xy / max_step / search_radius (in call
+ *   order: PRM node k of the mode is its k-th call; goal seeds are calls with (0.0, 0.0)), belief mode_belief_id[m] of
+ *   beliefs[B * n_worlds] (the mode's own belief vector, :419) and final nodes mode_final_nodes[mode_final_ptr[m] ..];
+ *   transition t goes from mode tr_from_mode[t] to tr_to_mode[t] with the (observation node, destination node) pairs
+ *   tr_pairs[2 * tr_pair_ptr[t] ..] (PRM node ids inside the two modes, :386-390).
+ * Builds every mode's PRM (prm.rs add_sample semantics), the belief graph of build_belief_graph (:399-473; belief node id =
+ * mode_node_ptr[mode] + PRM node id) and runs conditional_dijkstra: out_dist[total nodes], bit-identical to the reference's
+ * expected_costs_to_goals.  out_phase_ms (nullable [4]): PRM builds, graph assembly, value backups. */
+int32_t porrt_mmprm_plan(porrt_ctx* ctx, int32_t n_modes, const int64_t* mode_node_ptr, const double* samples_xy,
+                         const double* max_step, const double* search_radius, const int32_t* mode_belief_id,
+                         const double* beliefs, int32_t B, int32_t n_worlds, int32_t n_transitions,
+                         const int32_t* tr_from_mode, const int32_t* tr_to_mode, const int64_t* tr_pair_ptr,
+                         const int32_t* tr_pairs, const int64_t* mode_final_ptr, const int32_t* mode_final_nodes,
+                         double* out_dist, int64_t* out_n_edges, int32_t* out_sweeps, double* out_phase_ms);
+/* the belief graph assembled by the last porrt_mmprm_plan (children CSR, node types, belief ids), e.g. for
+ * porrt_extract_policy_graph; all outputs nullable except that cap must hold *out_n_edges columns */
+int32_t porrt_mmprm_fetch_graph(porrt_ctx* ctx, int64_t* out_row_ptr, int32_t* out_col, int64_t cap, uint8_t* out_node_type,
+                                int32_t* out_belief_id);
+
 /* ------------------------------------------------------------------ policy refinement (pto_policy_refiner.rs)
  * PTOPolicyRefiner::is_transition_valid (pto_policy_refiner.rs:395-423), batched: out_valid[i] = 1 iff both end states are
  * valid, the transition from -> to is valid with validity id v, and compat_row[v] != 0, where compat_row[n_validities] is

@@ -524,3 +524,74 @@ API int64_t orc_refiner_partial_shortcut(void* mp, double* states, uint64_t L, c
   for (uint64_t k = 0; k < L; ++k) { states[2 * k] = st[k][0]; states[2 * k + 1] = st[k][1]; }
   return rc;
 }
+
+// ---------------------------------------------------------------- multi-modal PRM (map_shelves_tamp_prm.rs)
+struct TampHandle { TampPRM t; Policy policy; bool ok = false; TampHandle(GridMap* m, State lo, State up, uint64_t seed) : t(m, lo, up, seed) {} };
+API void* orc_tamp_new(void* map, const double* low, const double* up, uint64_t seed) {
+  return new TampHandle((GridMap*)map, {low[0], low[1]}, {up[0], up[1]}, seed);
+}
+API void orc_tamp_free(void* p) { delete (TampHandle*)p; }
+// MapShelfDomainTampPRM::plan; returns 1 ok / 0 reference panic; *seconds = [grow_mm_prm, build_belief_graph, conditional_dijkstra, extract_policy]
+API int orc_tamp_plan(void* p, const double* start, const double* b0, uint64_t n_worlds, double max_step, double search_radius,
+                      uint64_t n_iter_per_belief, double* seconds) {
+  TampHandle* h = (TampHandle*)p;
+  BeliefState b(b0, b0 + n_worlds);
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double>(c - a).count(); };
+  auto t0 = now();
+  h->t.grow_mm_prm({start[0], start[1]}, b, max_step, search_radius, n_iter_per_belief);
+  auto t1 = now();
+  if (!h->t.build_belief_graph()) return 0;
+  auto t2 = now();
+  if (!conditional_dijkstra(h->t.belief_graph, h->t.final_belief_node_ids, h->t.expected_costs)) return 0;
+  auto t3 = now();
+  h->ok = extract_policy(h->t.belief_graph, h->t.expected_costs, h->policy);
+  auto t4 = now();
+  if (seconds) { seconds[0] = secs(t0, t1); seconds[1] = secs(t1, t2); seconds[2] = secs(t2, t3); seconds[3] = secs(t3, t4); }
+  return h->ok ? 1 : 0;
+}
+API void* orc_tamp_belief_graph(void* p) { return &((TampHandle*)p)->t.belief_graph; }
+API void* orc_tamp_policy(void* p) {   // a copy the caller frees with orc_policy_free
+  PolicyHandle* ph = new PolicyHandle();
+  ph->p = ((TampHandle*)p)->policy;
+  return ph;
+}
+// sizes: [n_modes, total_nodes, n_transitions, total_pairs, n_finals, B, n_worlds]
+API void orc_tamp_sizes(void* p, int64_t* out7) {
+  TampPRM& t = ((TampHandle*)p)->t;
+  int64_t nodes = 0, pairs = 0, finals = 0;
+  for (auto& m : t.modes) { nodes += (int64_t)m->samples.size(); finals += (int64_t)m->final_node_ids.size(); }
+  for (auto& tr : t.transitions) pairs += (int64_t)tr.observation_transitions.size();
+  out7[0] = (int64_t)t.modes.size(); out7[1] = nodes; out7[2] = (int64_t)t.transitions.size(); out7[3] = pairs; out7[4] = finals;
+  out7[5] = (int64_t)t.belief_states.size(); out7[6] = (int64_t)t.domain->n_worlds;
+}
+// the recorded schedule (inputs of the product's porrt_mmprm_plan) and the expected costs (its expected output)
+API void orc_tamp_export(void* p, int64_t* mode_node_ptr, double* samples_xy, double* max_steps, double* search_radii,
+                         int32_t* mode_belief_id, double* beliefs /* [B * n_worlds], mode vectors substituted */,
+                         int32_t* tr_from_mode, int32_t* tr_to_mode, int64_t* tr_pair_ptr, int32_t* tr_pairs,
+                         int64_t* mode_final_ptr, int32_t* mode_final_nodes, double* expected_costs) {
+  TampPRM& t = ((TampHandle*)p)->t;
+  const size_t nw = t.domain->n_worlds;
+  int64_t k = 0, f = 0;
+  for (size_t m = 0; m < t.modes.size(); ++m) {
+    auto& mode = *t.modes[m];
+    mode_node_ptr[m] = k; mode_final_ptr[m] = f;
+    for (size_t i = 0; i < mode.samples.size(); ++i, ++k) {
+      samples_xy[2 * k] = mode.samples[i][0]; samples_xy[2 * k + 1] = mode.samples[i][1];
+      max_steps[k] = mode.max_steps[i]; search_radii[k] = mode.search_radii[i];
+    }
+    for (size_t id : mode.final_node_ids) mode_final_nodes[f++] = (int32_t)id;
+    mode_belief_id[m] = (int32_t)t.belief_graph.belief_states_to_id.at(belief_hash(mode.belief_state));
+  }
+  mode_node_ptr[t.modes.size()] = k; mode_final_ptr[t.modes.size()] = f;
+  for (size_t b = 0; b < t.belief_states.size(); ++b)
+    for (size_t w = 0; w < nw; ++w) beliefs[b * nw + w] = t.belief_graph.reachable_belief_states[b][w];
+  int64_t q = 0;
+  for (size_t i = 0; i < t.transitions.size(); ++i) {
+    tr_from_mode[i] = (int32_t)t.transitions[i].from_mode_id; tr_to_mode[i] = (int32_t)t.transitions[i].to_mode_id;
+    tr_pair_ptr[i] = q;
+    for (auto& e : t.transitions[i].observation_transitions) { tr_pairs[2 * q] = (int32_t)e[0]; tr_pairs[2 * q + 1] = (int32_t)e[1]; ++q; }
+  }
+  tr_pair_ptr[t.transitions.size()] = q;
+  if (expected_costs) std::memcpy(expected_costs, t.expected_costs.data(), 8 * t.expected_costs.size());
+}

@@ -939,4 +939,177 @@ int64_t refiner_partial_shortcut(const GridMap& m, std::vector<State>& states, c
   return commits;
 }
 
+// ============================================================== map_shelves_tamp_prm.rs
+static bool tamp_is_final(const BeliefState& b) {  // :19-21
+  double m = b[0];
+  for (double p : b) if (p > m) m = p;
+  return m >= 0.999;
+}
+static BeliefState tamp_normalize(const BeliefState& b) {  // :23-26 (map_shelves_tamp_rrt.rs:15-18)
+  double sum = 0.0;
+  for (double p : b) sum = sum + p;
+  BeliefState out;
+  for (double p : b) out.push_back(p / sum);
+  return out;
+}
+size_t TampPRM::Mode::add_sample(State s, double max_step, double search_radius) {
+  samples.push_back(s); max_steps.push_back(max_step); search_radii.push_back(search_radius);
+  return prm.add_sample(s, max_step, search_radius);
+}
+TampPRM::TampPRM(const GridMap* m, State low, State up, uint64_t seed)
+    : domain(m), continuous(low, up, seed), zone_sampler({0.0, 0.0}, {m->visibility_distance, 2.0 * M_PI}, seed), discrete(seed) {}
+size_t TampPRM::add_mode(const std::vector<size_t>& remaining, double reaching_p, const BeliefState& b) {
+  size_t id = modes.size();
+  modes.emplace_back(new Mode(domain, continuous));   // PRM::new(continuous_sampler.clone(), ..): every mode starts the same stream
+  Mode& v = *modes.back();
+  v.id = id; v.remaining_zones = remaining; v.reaching_probability = reaching_p; v.belief_state = b;
+  mode_hash_map[belief_hash(b)] = id;
+  return id;
+}
+std::vector<size_t> TampPRM::get_transitions(size_t mode_id, size_t target_zone_id) {
+  std::vector<size_t> successor;
+  if (tamp_is_final(modes[mode_id]->belief_state)) return successor;
+  auto remaining_without = [&](const Mode& m) {
+    std::vector<size_t> r;
+    for (size_t z : m.remaining_zones) if (z != target_zone_id) r.push_back(z);
+    return r;
+  };
+  {  // object there (:187-226)
+    Mode& mode = *modes[mode_id];
+    auto it = mode.there.find(target_zone_id);
+    if (it != mode.there.end()) successor.push_back(it->second);
+    else {
+      BeliefState succ(mode.belief_state.size(), 0.0);
+      succ[target_zone_id] = 1.0;
+      succ = tamp_normalize(succ);
+      double p = mode.reaching_probability * transition_probability(mode.belief_state, succ);
+      size_t succ_mode;
+      auto hm = mode_hash_map.find(belief_hash(succ));
+      if (hm != mode_hash_map.end()) succ_mode = hm->second;
+      else {
+        succ_mode = add_mode(remaining_without(mode), p, succ);
+        Mode& nm = *modes[succ_mode];
+        size_t goal_id = nm.add_sample(domain->zone_positions[target_zone_id], 0.0, 0.0);
+        nm.final_node_ids.push_back(goal_id);
+      }
+      size_t t = transitions.size();
+      transitions.push_back({target_zone_id, mode_id, succ_mode, {}});
+      modes[mode_id]->there[target_zone_id] = t;
+      successor.push_back(t);
+    }
+  }
+  {  // object not there (:230-267)
+    Mode& mode = *modes[mode_id];
+    auto it = mode.not_there.find(target_zone_id);
+    if (it != mode.not_there.end()) successor.push_back(it->second);
+    else {
+      BeliefState succ = mode.belief_state;
+      succ[target_zone_id] = 0.0;
+      double p = mode.reaching_probability * transition_probability(mode.belief_state, succ);
+      succ = tamp_normalize(succ);
+      size_t succ_mode;
+      auto hm = mode_hash_map.find(belief_hash(succ));
+      if (hm != mode_hash_map.end()) succ_mode = hm->second;
+      else {
+        succ_mode = add_mode(remaining_without(mode), p, succ);
+        for (size_t z = 0; z < succ.size(); ++z)
+          if (succ[z] == 1.0) {
+            Mode& nm = *modes[succ_mode];
+            size_t goal_id = nm.add_sample(domain->zone_positions[z], 0.0, 0.0);
+            nm.final_node_ids.push_back(goal_id);
+            break;
+          }
+      }
+      size_t t = transitions.size();
+      transitions.push_back({target_zone_id, mode_id, succ_mode, {}});
+      modes[mode_id]->not_there[target_zone_id] = t;
+      successor.push_back(t);
+    }
+  }
+  return successor;
+}
+State TampPRM::sample_observation_of_zone(size_t target_zone_id) {
+  State zp = domain->zone_positions[target_zone_id];
+  State ra = zone_sampler.sample();
+  double radius = domain->visibility_distance, angle = ra[1];
+  auto clamp = [](double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  return {clamp(zp[0] + radius * std::cos(angle), continuous.low[0], continuous.up[0] - 0.0001),
+          clamp(zp[1] + radius * std::sin(angle), continuous.low[1], continuous.up[1] - 0.0001)};
+}
+void TampPRM::grow_mm_prm(State start, const BeliefState& b0, double max_step, double search_radius, size_t n_iter_per_belief) {
+  belief_states = domain->reachable_belief_states(b0);
+  std::vector<size_t> all(domain->n_zones);
+  for (size_t z = 0; z < all.size(); ++z) all[z] = z;
+  add_mode(all, 1.0, b0);
+  modes[0]->add_sample(start, 0.0, 0.0);
+  size_t total = n_iter_per_belief * belief_states.size();
+  const size_t batch = 200, per_batch_transitions = 10;
+  size_t n_outer = (size_t)((double)total / (double)batch);
+  size_t n_within = batch - per_batch_transitions;
+  for (size_t i = 0; i < n_outer; ++i) {
+    size_t mode_id = discrete.sample(modes.size());
+    {
+      Mode& mode = *modes[mode_id];
+      for (size_t k = 0; k < n_within; ++k) {   // PRM::grow_graph (prm.rs:38-50)
+        State s = mode.prm.sampler.sample();
+        mode.add_sample(s, max_step, search_radius);
+        mode.prm.n_it += 1;
+      }
+    }
+    for (size_t j = 0; j < per_batch_transitions; ++j) {
+      if (modes[mode_id]->remaining_zones.empty()) continue;
+      size_t zi = discrete.sample(modes[mode_id]->remaining_zones.size());
+      size_t target = modes[mode_id]->remaining_zones[zi];
+      std::vector<size_t> tids = get_transitions(mode_id, target);
+      State ts = sample_observation_of_zone(target);
+      size_t obs_node = modes[mode_id]->add_sample(ts, max_step, search_radius);
+      for (size_t tid : tids) {
+        size_t to_mode = transitions[tid].to_mode_id;
+        size_t dst = modes[to_mode]->add_sample(ts, max_step, search_radius);
+        transitions[tid].observation_transitions.push_back({obs_node, dst});
+      }
+    }
+  }
+}
+bool TampPRM::build_belief_graph() {
+  belief_graph = BeliefGraph();
+  belief_graph.reachable_belief_states = belief_states;
+  for (size_t b = 0; b < belief_states.size(); ++b) belief_graph.belief_states_to_id[belief_hash(belief_states[b])] = b;
+  final_belief_node_ids.clear();
+  std::vector<size_t> base(modes.size());
+  for (auto& mp : modes) {
+    Mode& mode = *mp;
+    auto it = belief_graph.belief_states_to_id.find(belief_hash(mode.belief_state));
+    if (it == belief_graph.belief_states_to_id.end()) return false;   // HashMap index panic (:413)
+    size_t belief_id = it->second;
+    // the reference stores the MODE's belief vector in every belief node (:419); our BeliefGraph resolves beliefs through
+    // belief_id, so the table entry of this belief is replaced by the mode's vector (one mode per belief hash)
+    belief_graph.reachable_belief_states[belief_id] = mode.belief_state;
+    base[mode.id] = belief_graph.nodes.size();
+    for (const PTONode& n : mode.prm.graph.nodes) belief_graph.add_node(n.state, belief_id, ACTION);
+    for (size_t f : mode.final_node_ids) final_belief_node_ids.push_back(base[mode.id] + f);
+  }
+  for (const Transition& t : transitions)
+    for (const auto& e : t.observation_transitions) {
+      size_t from = base[t.from_mode_id] + e[0], to = base[t.to_mode_id] + e[1];
+      belief_graph.add_edge(from, to);
+      belief_graph.nodes[from].node_type = OBSERVATION;
+    }
+  for (auto& mp : modes) {
+    Mode& mode = *mp;
+    for (size_t id = 0; id < mode.prm.graph.nodes.size(); ++id) {
+      size_t bn = base[mode.id] + id;
+      if (belief_graph.nodes[bn].node_type == OBSERVATION) continue;
+      for (const PTOEdge& c : mode.prm.graph.nodes[id].children) belief_graph.add_edge(bn, base[mode.id] + c.id);
+    }
+  }
+  return true;
+}
+bool TampPRM::plan(State start, const BeliefState& b0, double max_step, double search_radius, size_t n_iter_per_belief, Policy& out) {
+  grow_mm_prm(start, b0, max_step, search_radius, n_iter_per_belief);
+  if (!build_belief_graph()) return false;
+  if (!conditional_dijkstra(belief_graph, final_belief_node_ids, expected_costs)) return false;
+  return extract_policy(belief_graph, expected_costs, out);
+}
+
 }  // namespace orc

@@ -23,6 +23,8 @@
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
+#include <memory>
+#include <array>
 #include <vector>
 
 namespace orc {
@@ -232,6 +234,39 @@ struct PTO {  // pto.rs
   std::vector<std::vector<double>> cost_to_goals;
   int plan_qmdp();
   bool react_qmdp(State start, const BeliefState& b, double horizon, std::vector<std::vector<State>>& paths);
+};
+
+// ---------------------------------------------------------------- map_shelves_tamp_prm.rs (multi-modal PRM baseline)
+// MapShelfDomainTampPRM: one PRM per belief "mode", observation transitions between modes, conditional_dijkstra on the
+// resulting explicit belief graph.  Every add_sample call is recorded per mode (state, max_step, search_radius): the whole
+// growth is driven by the RNG streams only (no validity feedback), so the recorded schedule is a complete description of it.
+struct TampPRM {
+  struct Mode {   // :61-99
+    size_t id; std::vector<size_t> remaining_zones; double reaching_probability; BeliefState belief_state;
+    PRM prm; std::vector<size_t> final_node_ids;
+    std::unordered_map<size_t, size_t> there, not_there;   // zone -> transition index
+    std::vector<State> samples; std::vector<double> max_steps, search_radii;   // the recorded add_sample calls
+    Mode(const GridMap* m, const ContinuousSampler& s) : prm(m, s.low, s.up, 0) { prm.sampler = s; }
+    size_t add_sample(State s, double max_step, double search_radius);
+  };
+  struct Transition { size_t observed_zone_id, from_mode_id, to_mode_id; std::vector<std::array<size_t, 2>> observation_transitions; };
+  const GridMap* domain;
+  ContinuousSampler continuous, zone_sampler;
+  DiscreteSampler discrete;
+  std::vector<std::unique_ptr<Mode>> modes;
+  std::vector<Transition> transitions;
+  std::vector<BeliefState> belief_states;
+  std::unordered_map<uint64_t, size_t> mode_hash_map;
+  BeliefGraph belief_graph;
+  std::vector<size_t> final_belief_node_ids;
+  std::vector<double> expected_costs;
+  TampPRM(const GridMap* m, State low, State up, uint64_t seed = 0);
+  size_t add_mode(const std::vector<size_t>& remaining, double reaching_p, const BeliefState& b);      // :122-147
+  std::vector<size_t> get_transitions(size_t mode_id, size_t target_zone_id);                           // :166-270
+  State sample_observation_of_zone(size_t target_zone_id);                                               // :487-498
+  void grow_mm_prm(State start, const BeliefState& b0, double max_step, double search_radius, size_t n_iter_per_belief);  // :328-397
+  bool build_belief_graph();                                                                             // :399-473
+  bool plan(State start, const BeliefState& b0, double max_step, double search_radius, size_t n_iter_per_belief, Policy& out);  // :308-326
 };
 
 }  // namespace orc

@@ -73,6 +73,10 @@ _SIGS = {
     "orc_pto_react_qmdp": (i64, [vp, vp, vp, f64, vp, vp, i64]),
     "orc_refiner_transition_valid_batch": (None, [vp, vp, vp, i64, vp, u64, vp]),
     "orc_refiner_partial_shortcut": (i64, [vp, vp, u64, vp, u64, u64]),
+    "orc_tamp_new": (vp, [vp, vp, vp, u64]), "orc_tamp_free": (None, [vp]),
+    "orc_tamp_plan": (C.c_int, [vp, vp, vp, u64, f64, f64, u64, vp]), "orc_tamp_belief_graph": (vp, [vp]),
+    "orc_tamp_policy": (vp, [vp]), "orc_tamp_sizes": (None, [vp, vp]),
+    "orc_tamp_export": (None, [vp] * 14),
 }
 
 
@@ -631,3 +635,39 @@ class PTO:
             out.append(xy[o:o + n].copy())
             o += n
         return out
+
+
+class TampPRM:
+    """MapShelfDomainTampPRM (map_shelves_tamp_prm.rs): plan() runs the reference algorithm; schedule() returns the recorded
+    add_sample calls per mode + mode transitions (everything the RNG streams decided) and the expected costs."""
+
+    def __init__(self, gridmap, low, up, seed=0):
+        self.map = gridmap
+        self.h = lib().orc_tamp_new(gridmap.h, P(f64a(low)), P(f64a(up)), seed)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_tamp_free(self.h)
+            self.h = None
+
+    def plan(self, start, b0, max_step, search_radius, n_iter_per_belief):
+        b0 = f64a(b0)
+        self.seconds = np.zeros(4)
+        if not lib().orc_tamp_plan(self.h, P(f64a(start)), P(b0), len(b0), max_step, search_radius, n_iter_per_belief, P(self.seconds)):
+            raise RuntimeError("reference panic in MapShelfDomainTampPRM::plan")
+        self.belief_graph = BeliefGraph(handle=lib().orc_tamp_belief_graph(self.h), owner=self)
+        return Policy(lib().orc_tamp_policy(self.h))
+
+    def schedule(self):
+        sz = np.zeros(7, np.int64)
+        lib().orc_tamp_sizes(self.h, P(sz))
+        n_modes, nodes, n_tr, pairs, finals, B, nw = (int(x) for x in sz)
+        d = dict(mode_node_ptr=np.zeros(n_modes + 1, np.int64), samples=np.zeros((nodes, 2)), max_step=np.zeros(nodes),
+                 search_radius=np.zeros(nodes), mode_belief_id=np.zeros(n_modes, np.int32), beliefs=np.zeros((B, nw)),
+                 tr_from_mode=np.zeros(n_tr, np.int32), tr_to_mode=np.zeros(n_tr, np.int32), tr_pair_ptr=np.zeros(n_tr + 1, np.int64),
+                 tr_pairs=np.zeros((pairs, 2), np.int32), mode_final_ptr=np.zeros(n_modes + 1, np.int64),
+                 mode_final_nodes=np.zeros(finals, np.int32), expected_costs=np.zeros(nodes))
+        lib().orc_tamp_export(self.h, *(P(d[k]) for k in ("mode_node_ptr", "samples", "max_step", "search_radius", "mode_belief_id",
+                                                          "beliefs", "tr_from_mode", "tr_to_mode", "tr_pair_ptr", "tr_pairs",
+                                                          "mode_final_ptr", "mode_final_nodes", "expected_costs")))
+        return d

@@ -50,6 +50,8 @@ SIGNATURES = {
     "porrt_extract_policy": (i32, [vp, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),
     "porrt_conditional_dijkstra": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, pp(i32)]),
     "porrt_extract_policy_graph": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),
+    "porrt_mmprm_plan": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, pp(i64), pp(i32), vp]),
+    "porrt_mmprm_fetch_graph": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_reachable_belief_states": (i32, [vp, vp, vp, i32, pp(i32)]),
     "porrt_comm_unique_id": (i32, [vp]),
     "porrt_comm_init": (i32, [vp, vp, i32, i32]),

@@ -490,6 +490,39 @@ class BeliefGraph:
         return node[:k].copy(), parent[:k].copy(), leaf[:k].copy(), cost.value
 
 
+def mmprm_plan(fns, schedule):
+    """MapShelfDomainTampPRM::plan (src/map_shelves_tamp_prm.rs:308-326) for a recorded schedule (dict with the arrays of
+    porrt_mmprm_plan: mode_node_ptr, samples, max_step, search_radius, mode_belief_id, beliefs, tr_from_mode, tr_to_mode,
+    tr_pair_ptr, tr_pairs, mode_final_ptr, mode_final_nodes).  Returns (expected costs, BeliefGraph, policy tuple, phase ms)."""
+    ctx = fns.ctx
+    fns._need()
+    s = schedule
+    ptr = np.ascontiguousarray(s["mode_node_ptr"], np.int64)
+    xy = _f64(s["samples"], 2)
+    ms, sr = _f64(s["max_step"]), _f64(s["search_radius"])
+    mb = np.ascontiguousarray(s["mode_belief_id"], np.int32)
+    beliefs = np.ascontiguousarray(np.atleast_2d(np.asarray(s["beliefs"], np.float64)))
+    trf, trt = np.ascontiguousarray(s["tr_from_mode"], np.int32), np.ascontiguousarray(s["tr_to_mode"], np.int32)
+    trp = np.ascontiguousarray(s["tr_pair_ptr"], np.int64)
+    pairs = np.ascontiguousarray(s["tr_pairs"], np.int32)
+    fptr = np.ascontiguousarray(s["mode_final_ptr"], np.int64)
+    fin = np.ascontiguousarray(s["mode_final_nodes"], np.int32)
+    T = int(ptr[-1])
+    dist = np.empty(T)
+    n_edges, sweeps = C.c_int64(), C.c_int32()
+    phase = np.zeros(4)
+    ctx.check(ctx.lib.porrt_mmprm_plan(ctx.h, len(mb), _p(ptr), _p(xy), _p(ms), _p(sr), _p(mb), _p(beliefs), beliefs.shape[0],
+                                       beliefs.shape[1], len(trf), _p(trf), _p(trt), _p(trp), _p(pairs), _p(fptr), _p(fin),
+                                       _p(dist), C.byref(n_edges), C.byref(sweeps), _p(phase)))
+    rp, col = np.empty(T + 1, np.int64), np.empty(n_edges.value, np.int32)
+    typ, bid = np.empty(T, np.uint8), np.empty(T, np.int32)
+    ctx.check(ctx.lib.porrt_mmprm_fetch_graph(ctx.h, _p(rp), _p(col), len(col), _p(typ), _p(bid)))
+    graph = BeliefGraph(ctx, rp, col, xy, typ, bid, beliefs)
+    graph.sweeps = sweeps.value
+    policy = graph.extract_policy(dist)
+    return dist, graph, policy, phase
+
+
 def words_from_bits(bits):
     """[n, n_worlds] 0/1 -> [n, ceil(n_worlds/64)] u64 (bit w of word w/64 = world w)"""
     bits = np.atleast_2d(np.asarray(bits, np.uint8))

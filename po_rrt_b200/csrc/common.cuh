@@ -122,6 +122,11 @@ struct porrt_ctx {
   const int64_t* prm_row_ptr = nullptr;
   const int32_t* prm_col = nullptr;
 
+  // ---- last multi-modal PRM result (mmprm.cu): the explicit belief graph, kept for porrt_mmprm_fetch_graph
+  struct MmPrm_ {
+    std::vector<int64_t> row_ptr; std::vector<int32_t> col, belief_id; std::vector<uint8_t> type;
+  } mm;
+
   // ---- multi-GPU (comm.cu): NCCL communicator bound at run time; world 1 = no communicator
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;
@@ -209,4 +214,7 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
                                  const int32_t* key_of_id_dev, int64_t key_limit);
 int32_t radix_sort_pairs(porrt_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);
 int bits_for(uint64_t max_value);
+int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
+                       const double* ms_arr, const double* sr_arr, int64_t* out_row_ptr, int32_t* out_col, int64_t cap,
+                       int64_t* out_n_edges, double* out_phase_ms);
 int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev);

@@ -249,8 +249,11 @@ __global__ void prm_fill_kernel(const int64_t* __restrict__ offsets, int64_t m, 
   for (int64_t k = ls + lane; k < le; k += 32) col[r + c + (k - ls)] = late_vals[k];
 }
 
-PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
-                                  int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms) {
+// ms_arr / sr_arr (nullable): per-sample (max_step, search_radius) of the add_sample call that created node k -- the multi-modal
+// PRM seeds goal nodes with add_sample(goal, 0.0, 0.0) (map_shelves_tamp_prm.rs:211,256), i.e. radius 0 = exact duplicates only
+int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
+                       const double* ms_arr, const double* sr_arr,
+                       int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms) {
   CTX_CHECK(ctx);
   ctx->prm_n = 0;
   if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
@@ -277,7 +280,8 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
     if (m < 20000) nt = 1;
     for (int t = 0; t < nt; ++t)
       th.emplace_back([=]() {
-        for (int64_t k = lo + t; k < hi; k += nt) radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, max_step, search_radius, 2);
+        for (int64_t k = lo + t; k < hi; k += nt)
+          radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, ms_arr ? ms_arr[k] : max_step, sr_arr ? sr_arr[k] : search_radius, 2);
       });
   }
   struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); } } joiner{th};
@@ -302,8 +306,15 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
 
   // 1. bin vertices; cell = the smallest radius in use (the last one) so late queries touch 3x3 cells
-  const double r_last = n > 1 ? heuristic_radius((size_t)n, max_step, search_radius, 2) : -1.0;
-  double cell = r_last > 0 ? r_last : max_step;
+  double r_last = n > 1 ? heuristic_radius((size_t)n, max_step, search_radius, 2) : -1.0;
+  if (ms_arr || sr_arr) {   // per-sample parameters: the smallest positive radius in use (needs the radii: no overlap here)
+    for (auto& x : th) if (x.joinable()) x.join();
+    r_last = -1.0;
+    for (int64_t k = lo; k < hi; ++k)
+      if (radius[k] > 0.0 && (r_last < 0.0 || radius[k] < r_last)) r_last = radius[k];
+    if (world > 1) r_last = -1.0;   // (shards would disagree on the cell size; per-sample parameters are a small-n path)
+  }
+  double cell = r_last > 0 ? r_last : (max_step > 0 ? max_step : 0.05);
   int32_t rc = nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell, nullptr, nullptr);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -315,7 +326,7 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
 
-  for (auto& x : th) x.join();
+  for (auto& x : th) if (x.joinable()) x.join();
   if (m > 0) CUDA_TRY(ctx, cudaMemcpyAsync(d_radius + lo, radius + lo, (size_t)m * 8, cudaMemcpyHostToDevice, st));
   iota_u32_kernel<<<div_up(n, 256), 256, 0, st>>>(d_prefix, n);   // prefix limit of query k = k: the tree before node k arrived
   LAUNCH_CHECK(ctx);
@@ -447,6 +458,11 @@ PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int6
   if (out_phase_ms) memcpy(out_phase_ms, ph, sizeof(ph));
   ctx->prm_n = n; ctx->prm_edges = n_edges; ctx->prm_row_ptr = d_row_ptr; ctx->prm_col = d_col;  // retained for porrt_prm_fetch
   return status;
+}
+
+PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
+                                  int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms) {
+  return prm_build_impl(ctx, samples_xy, n, max_step, search_radius, nullptr, nullptr, out_row_ptr, out_col, cap, out_n_edges, out_phase_ms);
 }
 
 PORRT_API int32_t porrt_prm_fetch(porrt_ctx* ctx, int64_t* out_row_ptr, int32_t* out_col, int64_t cap) {

@@ -807,3 +807,29 @@ def test_conditional_dijkstra_panics(ctx):
     assert e.value.code == 5
     d = run([A_, A_, A_, U_], [0, 0, 0, 0], [(0, 1), (1, 2), (2, 3)], [2])      # the Unknown node has no reached child
     np.testing.assert_array_equal(d, [2.0, 1.0, 0.0, np.inf])
+
+
+# ---------------------------------------------------------------------------------------------- multi-modal PRM
+@pytest.mark.parametrize("n_zones,start,n_iter", [(2, (-0.9, 0.0), 2500), (4, (0.0, -0.9), 1200)])
+def test_mmprm_plan_vs_oracle(ctx, n_zones, start, n_iter):
+    """MapShelfDomainTampPRM::plan (map_shelves_tamp_prm.rs:308-326; its tests :506-552 use plan(start, uniform belief, 0.1, 2.0,
+    2500)): the oracle runs the reference algorithm and records the RNG-decided schedule; the product rebuilds every mode's PRM,
+    the belief graph and the expected costs from that schedule on the GPU -- identical graph, bit-identical costs, same policy"""
+    occ, zones = synth.shelf_map(200, n_zones=n_zones)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    tamp = O.TampPRM(omap, util.LOW, util.UP)
+    opol = tamp.plan(start, [1.0 / n_zones] * n_zones, 0.1, 2.0, n_iter)
+    sch = tamp.schedule()
+    assert len(sch["mode_belief_id"]) >= n_zones + 1 and len(sch["tr_pairs"]) > 0
+    dist, graph, (node, parent, leaf, cost), phase = P.mmprm_plan(pmap, sch)
+    typ, bid, rp, col = tamp.belief_graph.export()
+    np.testing.assert_array_equal(graph.row_ptr, rp)                       # every mode's PRM adjacency + observation edges
+    np.testing.assert_array_equal(graph.col.astype(np.int64), col)
+    np.testing.assert_array_equal(graph.node_type.astype(np.int32), typ)
+    np.testing.assert_array_equal(graph.belief_id, bid)
+    np.testing.assert_array_equal(dist, sch["expected_costs"])             # bit-exact f64
+    assert np.isfinite(dist[0])
+    np.testing.assert_array_equal(node.astype(np.int64), opol.original)
+    np.testing.assert_array_equal(parent.astype(np.int64), opol.parent)
+    np.testing.assert_array_equal(np.nonzero(leaf)[0], opol.leafs)
+    assert cost == opol.expected_costs and len(opol.leafs) == n_zones
