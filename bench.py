@@ -215,6 +215,11 @@ def side_measurements(ctx, pmap, args):
         import traceback
         ex["refiner"] = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
     try:
+        ex["mmprm_z6"] = mmprm_measurement(ctx)
+    except Exception as e:
+        import traceback
+        ex["mmprm_z6"] = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
+    try:
         ex["belief_c3"] = belief_measurement(ctx)
     except Exception as e:
         import traceback
@@ -366,6 +371,36 @@ def belief_measurement(ctx, Z=8, n_min=5000):
             "note": "dist table (V*B f64) is L2-resident: the sweep rate is an L2 gather rate, not HBM"}
 
 _REAL_STDOUT = None
+
+
+def mmprm_measurement(ctx, Z=6, n_iter=2500):
+    """multi-modal PRM (map_shelves_tamp_prm.rs test shape :539-552: 6 shelves, plan(.., 0.1, 2.0, 2500)): the oracle
+    runs the reference algorithm (and so decides the RNG schedule), the product rebuilds all mode PRMs + belief graph + expected
+    costs on the GPU from the schedule"""
+    import po_rrt_b200 as P
+    from po_rrt_b200 import synth
+    from oracle import pyoracle as O
+    occ, zones = synth.shelf_map(200, n_zones=Z)
+    low, up = [-1.0, -1.0], [1.0, 1.0]
+    omap = O.GridMap(occ, zones, low, up, O.SHELF, 0.5)
+    smap = P.MapShelfDomain(ctx, occ, low, up)
+    smap.add_zones(zones, 0.5)
+    tamp = O.TampPRM(omap, low, up)
+    opol = tamp.plan((0.0, -0.9), [1.0 / Z] * Z, 0.1, 2.0, n_iter)
+    sch = tamp.schedule()
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        dist, graph, pol, phase = P.mmprm_plan(smap, sch)
+        t = time.perf_counter() - t0
+        if best is None or t < best[0]:
+            best = (t, [round(float(x), 3) for x in phase[:3]])
+    exact = bool(np.array_equal(dist, sch["expected_costs"]) and np.array_equal(pol[0].astype(np.int64), opol.original))
+    return {"zones": Z, "modes": int(len(sch["mode_belief_id"])), "prm_nodes_total": int(len(sch["samples"])),
+            "belief_graph_edges": int(len(graph.col)), "sweeps": int(graph.sweeps), "gpu_ms_total": 1e3 * best[0],
+            "gpu_phase_ms[prm builds,graph assembly,value backups]": best[1],
+            "cpu_oracle_ms[grow_mm_prm,build_belief_graph,conditional_dijkstra,extract_policy]": [round(1e3 * float(x), 1) for x in tamp.seconds],
+            "bit_exact": exact}
 
 
 def emit(line):

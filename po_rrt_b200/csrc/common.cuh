@@ -200,7 +200,8 @@ struct GridDev;
 bool nn_tile_usable(const porrt_ctx* ctx, int64_t m);
 int32_t nn_tile_radius(porrt_ctx* ctx, const GridDev& g, const double* q_dev, const double* radius_dev, int64_t m,
                        const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev, bool fill, int32_t* counts_dev,
-                       const int64_t* offsets_dev, int32_t* ids_dev, const int32_t** fb_list_out, int32_t* fb_n_out);
+                       const int64_t* offsets_dev, int32_t* ids_dev, const int32_t** fb_list_out, int32_t* fb_n_out,
+                       const uint32_t* prefix_lo_dev = nullptr);
 int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64_t m, int k, const uint64_t* reach_dev,
                     const uint32_t* world_dev, int32_t* ids_dev, double* dist_dev, int32_t* ties_dev, const int32_t** fb_list_out,
                     int32_t* fb_n_out);
@@ -208,7 +209,8 @@ int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64
 int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi);
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
-                                 int64_t* offsets_dev /* [m+1] */, DevBuf* ids_buf, int64_t* total_out);
+                                 int64_t* offsets_dev /* [m+1] */, DevBuf* ids_buf, int64_t* total_out,
+                                 const uint32_t* prefix_lo_dev = nullptr);
 int32_t scan_exclusive_i64(porrt_ctx* ctx, const int32_t* counts_dev, int64_t n, int64_t* out_dev /* [n+1] */);
 int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev,
                                  const int32_t* key_of_id_dev, int64_t key_limit);
@@ -216,5 +218,5 @@ int32_t radix_sort_pairs(porrt_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t
 int bits_for(uint64_t max_value);
 int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
                        const double* ms_arr, const double* sr_arr, int64_t* out_row_ptr, int32_t* out_col, int64_t cap,
-                       int64_t* out_n_edges, double* out_phase_ms);
-int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev);
+                       int64_t* out_n_edges, double* out_phase_ms, const int64_t* group_ptr = nullptr, int32_t n_groups = 0);
+int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev, const uint32_t* root_of_dev = nullptr);

@@ -82,17 +82,21 @@ __global__ void kd_rank_kernel(int64_t n, int depth, const int32_t* __restrict__
   }
   rank[i] = r;
 }
+// root_of (nullable): several independent trees in one id space (the modes of a multi-modal PRM): point i belongs to the tree
+// rooted at root_of[i] (= the first id of its group); ranks then start at the root's id, so that the ranks of all trees
+// together are still a permutation of 0..n-1 (tree g occupies the id range of group g)
 __global__ void kd_init_kernel(int64_t n, int32_t* __restrict__ cur, int32_t* __restrict__ child, int32_t* __restrict__ size,
-                               int32_t* __restrict__ node_depth, int32_t* __restrict__ rank) {
+                               int32_t* __restrict__ node_depth, int32_t* __restrict__ rank, const uint32_t* __restrict__ root_of) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  cur[i] = i == 0 ? -1 : 0;
+  const int64_t root = root_of ? (int64_t)root_of[i] : 0;
+  cur[i] = i == root ? -1 : (int32_t)root;
   child[2 * i] = 0x7fffffff; child[2 * i + 1] = 0x7fffffff;
-  size[i] = 0; node_depth[i] = i == 0 ? 0 : -1; rank[i] = 0;
+  size[i] = 0; node_depth[i] = i == root ? 0 : -1; rank[i] = i == root ? (int32_t)root : 0;
 }
 
 // xy_dev: n vertices (device); out_rank_dev[n]; uses ctx->scratch[8..10]
-int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev) {
+int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev, const uint32_t* root_of_dev) {
   cudaStream_t st = ctx->stream;
   if (n <= 0) return PORRT_OK;
   CUDA_TRY(ctx, ctx->scratch[8].ensure((size_t)n * 4 * 6 + (size_t)n + 64));
@@ -105,7 +109,7 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
   int32_t* remaining = (int32_t*)b; b += 16;
   uint8_t* side = (uint8_t*)b;
   const int blocks = div_up(n, 256);
-  kd_init_kernel<<<blocks, 256, 0, st>>>(n, cur, child, size, node_depth, out_rank_dev);
+  kd_init_kernel<<<blocks, 256, 0, st>>>(n, cur, child, size, node_depth, out_rank_dev, root_of_dev);
   LAUNCH_CHECK(ctx);
   int depth = 0;
   for (;; ++depth) {
@@ -138,7 +142,7 @@ PORRT_API int32_t porrt_kd_preorder_rank(porrt_ctx* ctx, const double* xy, int64
   double* d_xy = ctx->scratch[9].as<double>();
   int32_t* d_rank = (int32_t*)(ctx->scratch[9].as<char>() + (size_t)n * 16);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
-  int32_t rc = kd_preorder_rank_dev(ctx, d_xy, n, d_rank);
+  int32_t rc = kd_preorder_rank_dev(ctx, d_xy, n, d_rank, nullptr);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(out_rank, d_rank, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -253,11 +257,27 @@ __global__ void prm_fill_kernel(const int64_t* __restrict__ offsets, int64_t m, 
 // PRM seeds goal nodes with add_sample(goal, 0.0, 0.0) (map_shelves_tamp_prm.rs:211,256), i.e. radius 0 = exact duplicates only
 int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
                        const double* ms_arr, const double* sr_arr,
-                       int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms) {
+                       int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms,
+                       const int64_t* group_ptr, int32_t n_groups) {
+  // group_ptr (nullable, [n_groups + 1]): several independent roadmaps in one call -- the samples group_ptr[g] .. group_ptr[g+1]-1
+  // form roadmap g (the PRM of mode g of a multi-modal PRM).  Node ids stay global; a node only ever sees earlier nodes of its
+  // own group (id range test in the radius kernels), its radius uses its index inside the group, and every group has its own kd
+  // order.  One binning, one radius batch, one edge batch and one CSR serve all roadmaps.
   CTX_CHECK(ctx);
   ctx->prm_n = 0;
   if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
   if (n <= 0 || !samples_xy || !out_row_ptr || !out_n_edges) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "prm_build: bad arguments");
+  std::vector<uint32_t> group_base;   // [n]: first id of the node's group
+  if (group_ptr) {
+    if (ctx->comm_world > 1) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "prm_build: grouped builds are not sharded");
+    if (n_groups <= 0 || group_ptr[0] != 0 || group_ptr[n_groups] != n) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "prm_build: bad group table");
+    group_base.resize((size_t)n);
+    for (int g = 0; g < n_groups; ++g) {
+      if (group_ptr[g + 1] < group_ptr[g]) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "prm_build: bad group table");
+      for (int64_t k = group_ptr[g]; k < group_ptr[g + 1]; ++k) group_base[(size_t)k] = (uint32_t)group_ptr[g];
+    }
+  }
+  const uint32_t* gb = group_ptr ? group_base.data() : nullptr;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   double t0 = now_ms(), t1;
@@ -280,8 +300,10 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
     if (m < 20000) nt = 1;
     for (int t = 0; t < nt; ++t)
       th.emplace_back([=]() {
-        for (int64_t k = lo + t; k < hi; k += nt)
-          radius[k] = k == 0 ? -1.0 : heuristic_radius((size_t)k + 1, ms_arr ? ms_arr[k] : max_step, sr_arr ? sr_arr[k] : search_radius, 2);
+        for (int64_t k = lo + t; k < hi; k += nt) {
+          const int64_t kl = gb ? k - (int64_t)gb[k] : k;   // index inside the node's own roadmap
+          radius[k] = kl == 0 ? -1.0 : heuristic_radius((size_t)kl + 1, ms_arr ? ms_arr[k] : max_step, sr_arr ? sr_arr[k] : search_radius, 2);
+        }
       });
   }
   struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); } } joiner{th};
@@ -289,7 +311,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   // device inputs
   CUDA_TRY(ctx, ctx->d_vxy.ensure((size_t)n * 16));
   DevBuf& aux = ctx->scratch[3];
-  CUDA_TRY(ctx, aux.ensure((size_t)n * (8 + 4 + 8 + 4 + 4 + 8 + 8 + 8) + 256));
+  CUDA_TRY(ctx, aux.ensure((size_t)n * (8 + 4 + 8 + 4 + 4 + 8 + 8 + 8 + 4) + 256));
   char* b = aux.as<char>();
   double* d_radius = (double*)b; b += (size_t)n * 8;
   int64_t* d_off = (int64_t*)b; b += (size_t)(n + 1) * 8;
@@ -301,6 +323,11 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   int32_t* d_early_cnt = (int32_t*)b; b += (size_t)n * 4;
   int32_t* d_late_cnt = (int32_t*)b; b += (size_t)n * 4;
   int32_t* d_flag = (int32_t*)b; b += 16;
+  uint32_t* d_group_base = nullptr;
+  if (gb) {
+    d_group_base = (uint32_t*)b; b += (size_t)n * 4;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_group_base, gb, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vxy.p, samples_xy, (size_t)n * 16, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemsetAsync(d_late_cnt, 0, (size_t)n * 4, st));
   CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
@@ -321,7 +348,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
 
   // 2. the kd pre-order rank of every vertex (restores the reference's neighbour order in step 4)
-  rc = kd_preorder_rank_dev(ctx, ctx->d_vxy.as<double>(), n, d_rank);
+  rc = kd_preorder_rank_dev(ctx, ctx->d_vxy.as<double>(), n, d_rank, d_group_base);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
@@ -335,7 +362,8 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   // (bins and kd ranks above are replicated on every rank; from here on the rank works on its shard [lo, hi))
   // 3. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
   int64_t total = 0;
-  rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>() + 2 * lo, d_radius + lo, m, d_prefix + lo, nullptr, nullptr, d_off, &ctx->scratch[2], &total);
+  rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>() + 2 * lo, d_radius + lo, m, d_prefix + lo, nullptr, nullptr, d_off, &ctx->scratch[2], &total,
+                                d_group_base ? d_group_base + lo : nullptr);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
@@ -462,7 +490,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
 
 PORRT_API int32_t porrt_prm_build(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
                                   int64_t* out_row_ptr, int32_t* out_col, int64_t cap, int64_t* out_n_edges, double* out_phase_ms) {
-  return prm_build_impl(ctx, samples_xy, n, max_step, search_radius, nullptr, nullptr, out_row_ptr, out_col, cap, out_n_edges, out_phase_ms);
+  return prm_build_impl(ctx, samples_xy, n, max_step, search_radius, nullptr, nullptr, out_row_ptr, out_col, cap, out_n_edges, out_phase_ms, nullptr, 0);
 }
 
 PORRT_API int32_t porrt_prm_fetch(porrt_ctx* ctx, int64_t* out_row_ptr, int32_t* out_col, int64_t cap) {

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
                                                      const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
                                                      const uint32_t* __restrict__ world, int32_t* __restrict__ counts,
                                                      const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids,
-                                                     const int32_t* __restrict__ list) {
+                                                     const int32_t* __restrict__ list, const uint32_t* __restrict__ prefix_lo) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
   if (list) t = list[t];   // m = length of the list: the queries nn_tile.cu left to this kernel
@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
   int32_t cnt = 0;
   if (T >= 0.0 && p.x == p.x && p.y == p.y) {
     const uint32_t limit = prefix ? prefix[t] : 0xffffffffu;
+    const uint32_t lo_limit = prefix_lo ? prefix_lo[t] : 0u;   // ids below belong to other roadmaps sharing the vertex set
     const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
     const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);  // conservative cell cover
     const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
           for (int64_t k = g.cell_start[c]; k < e; ++k) {
             const uint32_t id = (uint32_t)g.vid[k];
             if (id >= limit) break;
+            if (id < lo_limit) continue;
             if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || ((reach[id] >> wbit) & 1ull))) {
               if (FILL) out[cnt] = (int32_t)id;
               ++cnt;
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
 // offsets_dev[m+1] filled; ids_buf grown to the total; *total_out = total hits (host value; synchronises once)
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
-                                 int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out) {
+                                 int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out, const uint32_t* prefix_lo_dev) {
   cudaStream_t st = ctx->stream;
   if (m <= 0) {   // an empty shard of a sharded batch
     CUDA_TRY(ctx, cudaMemsetAsync(offsets_dev, 0, 8, st));
@@ -412,14 +414,14 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   int32_t fb_n = 0;
   if (tiles) {   // TMA-staged tiles, warp per query; queries with a wider reach come back in fb_list
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)m * 4, st));
-    int32_t rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, false, counts, nullptr, nullptr, &fb_list, &fb_n);
+    int32_t rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, false, counts, nullptr, nullptr, &fb_list, &fb_n, prefix_lo_dev);
     if (rc) return rc;
     if (fb_n > 0) {
-      radius_kernel<false><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, fb_list);
+      radius_kernel<false><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, fb_list, prefix_lo_dev);
       LAUNCH_CHECK(ctx);
     }
   } else {
-    radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, nullptr);
+    radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, nullptr, prefix_lo_dev);
     LAUNCH_CHECK(ctx);
   }
   int32_t rc = scan_exclusive_i64(ctx, counts, m, offsets_dev);
@@ -431,14 +433,14 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   CUDA_TRY(ctx, ids_buf->ensure((size_t)std::max<int64_t>(total, 1) * 4));
   if (total > 0) {
     if (tiles) {
-      rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, true, nullptr, offsets_dev, ids_buf->as<int32_t>(), &fb_list, &fb_n);
+      rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, true, nullptr, offsets_dev, ids_buf->as<int32_t>(), &fb_list, &fb_n, prefix_lo_dev);
       if (rc) return rc;
       if (fb_n > 0) {
-        radius_kernel<true><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), fb_list);
+        radius_kernel<true><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), fb_list, prefix_lo_dev);
         LAUNCH_CHECK(ctx);
       }
     } else {
-      radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), nullptr);
+      radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), nullptr, prefix_lo_dev);
       LAUNCH_CHECK(ctx);
     }
   }
@@ -707,7 +709,7 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
   if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
   int64_t total = 0;
   tstart(ctx);  // phases: [count+scan+fill, order restore, D2H]
-  int32_t rc = nn_radius_count_fill_dev(ctx, d_q, d_r, m, d_prefix, d_reach, d_world, d_off, &ctx->scratch[2], &total);
+  int32_t rc = nn_radius_count_fill_dev(ctx, d_q, d_r, m, d_prefix, d_reach, d_world, d_off, &ctx->scratch[2], &total, nullptr);
   if (rc) return rc;
   tmark(ctx);
   if (out_total) *out_total = total;

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
                                                                const uint32_t* __restrict__ world, const int32_t* __restrict__ qorder,
                                                                const int64_t* __restrict__ qstart, int tiles_per_row,
                                                                int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
-                                                               int32_t* __restrict__ out_ids) {
+                                                               int32_t* __restrict__ out_ids, const uint32_t* __restrict__ prefix_lo) {
   __shared__ __align__(128) double2 s_xy[NT_CAP];
   __shared__ __align__(16) int32_t s_id[NT_CAP + 24];
   __shared__ uint64_t s_bar;
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
     const double r = radius[t];
     const double Tr = radius_threshold(r);
     const uint32_t limit = prefix ? prefix[t] : 0xffffffffu;
+    const uint32_t lo_limit = prefix_lo ? prefix_lo[t] : 0u;
     const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
     const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);
     const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
       for (int j = 0; j < n_run; ++j) {
         if (dist2(cx[j], p.x, p.y) <= Tr) {
           const int32_t id = ci[j];
-          if ((uint32_t)id < limit && (!reach || ((reach[id] >> wbit) & 1ull))) {
+          if ((uint32_t)id < limit && (uint32_t)id >= lo_limit && (!reach || ((reach[id] >> wbit) & 1ull))) {
             if (FILL) out[cnt] = id;
             ++cnt;
           }
@@ -379,7 +380,8 @@ bool nn_tile_usable(const porrt_ctx* ctx, int64_t m) {
 // counts (zero-initialised by the caller) / fill for the queries the tiles can serve; *fb_list_out / *fb_n_out: the rest
 int32_t nn_tile_radius(porrt_ctx* ctx, const GridDev& g, const double* q_dev, const double* radius_dev, int64_t m,
                        const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev, bool fill, int32_t* counts_dev,
-                       const int64_t* offsets_dev, int32_t* ids_dev, const int32_t** fb_list_out, int32_t* fb_n_out) {
+                       const int64_t* offsets_dev, int32_t* ids_dev, const int32_t** fb_list_out, int32_t* fb_n_out,
+                       const uint32_t* prefix_lo_dev) {
   cudaStream_t st = ctx->stream;
   NtBins B;          // the fill pass reuses the bins of the count pass of the same call (same buffers, same layout)
   if (fill) { int32_t rc = nt_layout(ctx, g, m, &B); if (rc) return rc; }
@@ -387,13 +389,13 @@ int32_t nn_tile_radius(porrt_ctx* ctx, const GridDev& g, const double* q_dev, co
     int32_t rc = nt_bin<false>(ctx, g, q_dev, radius_dev, m, &B);
     if (rc) return rc;
     nt_radius_kernel<false><<<B.n_tiles, NT_THREADS, 0, st>>>(g, (const double2*)q_dev, radius_dev, prefix_dev, reach_dev, world_dev, B.qorder,
-                                                              B.qstart, B.tiles_per_row, counts_dev, nullptr, nullptr);
+                                                              B.qstart, B.tiles_per_row, counts_dev, nullptr, nullptr, prefix_lo_dev);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->nn_fb_n, B.fb_n, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
   } else {
     nt_radius_kernel<true><<<B.n_tiles, NT_THREADS, 0, st>>>(g, (const double2*)q_dev, radius_dev, prefix_dev, reach_dev, world_dev, B.qorder,
-                                                             B.qstart, B.tiles_per_row, nullptr, offsets_dev, ids_dev);
+                                                             B.qstart, B.tiles_per_row, nullptr, offsets_dev, ids_dev, prefix_lo_dev);
     LAUNCH_CHECK(ctx);
   }
   *fb_list_out = B.fb_list;
