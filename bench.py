@@ -394,11 +394,12 @@ def mmprm_measurement(ctx, Z=6, n_iter=2500):
         dist, graph, pol, phase = P.mmprm_plan(smap, sch)
         t = time.perf_counter() - t0
         if best is None or t < best[0]:
-            best = (t, [round(float(x), 3) for x in phase[:3]])
+            best = (t, [round(float(x), 3) for x in phase[:3]], [round(float(x), 3) for x in ctx.last_phase_ms()[:7]])
     exact = bool(np.array_equal(dist, sch["expected_costs"]) and np.array_equal(pol[0].astype(np.int64), opol.original))
     return {"zones": Z, "modes": int(len(sch["mode_belief_id"])), "prm_nodes_total": int(len(sch["samples"])),
             "belief_graph_edges": int(len(graph.col)), "sweeps": int(graph.sweeps), "gpu_ms_total": 1e3 * best[0],
             "gpu_phase_ms[prm builds,graph assembly,value backups]": best[1],
+            "prm_phase_ms[radii,bin,radius,kd_rank,order,edges,csr]": best[2],
             "cpu_oracle_ms[grow_mm_prm,build_belief_graph,conditional_dijkstra,extract_policy]": [round(1e3 * float(x), 1) for x in tamp.seconds],
             "bit_exact": exact}
 

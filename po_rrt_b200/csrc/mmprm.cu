@@ -41,17 +41,22 @@ PORRT_API int32_t porrt_mmprm_plan(porrt_ctx* ctx, int32_t n_modes, const int64_
   // 1. the PRMs of all modes in ONE grouped build (prm_build_impl, graph.cu): one binning, one radius batch, one edge batch, one
   //    CSR over global node ids; a node only sees earlier nodes of its own mode.  (Per-mode calls cost ~1 ms of launch latency
   //    each: 66 ms for 63 modes against ~4 ms for the grouped build.)
-  std::vector<int64_t> rp((size_t)T + 1, 0);
-  std::vector<int32_t> cl;
+  CUDA_TRY(ctx, ctx->pin[4].ensure((size_t)(T + 1) * 8));   // pinned staging: the CSR comes back by DMA, not through pageable copies
+  int64_t* rp = ctx->pin[4].as<int64_t>();
+  const int32_t* cl = nullptr;
+  int64_t ne = 0;
   {
-    int64_t ne = 0;
-    int32_t rc = prm_build_impl(ctx, samples_xy, T, 0.0, 0.0, max_step, search_radius, rp.data(), nullptr, 0, &ne, nullptr, mode_node_ptr, n_modes);
+    double prm_ph[8] = {0};
+    int32_t rc = prm_build_impl(ctx, samples_xy, T, 0.0, 0.0, max_step, search_radius, rp, nullptr, 0, &ne, prm_ph, mode_node_ptr, n_modes);
     if (rc != PORRT_OK && rc != PORRT_ERR_CAPACITY) return rc;
-    cl.resize((size_t)ne);
+    for (int k = 0; k < 7; ++k) ctx->last_ms[k] = prm_ph[k];   // porrt_ctx_last_phase_ms: [radii, bin, radius, kd_rank, order, edges, csr]
+    ctx->n_last = 7;
+    CUDA_TRY(ctx, ctx->pin[5].ensure((size_t)std::max<int64_t>(ne, 1) * 4));
     if (ne > 0) {
-      rc = porrt_prm_fetch(ctx, nullptr, cl.data(), ne);
+      rc = porrt_prm_fetch(ctx, nullptr, ctx->pin[5].as<int32_t>(), ne);
       if (rc) return rc;
     }
+    cl = ctx->pin[5].as<int32_t>();
   }
   t1 = mm_now_ms(); ph[0] = t1 - t0; t0 = t1;
 
@@ -68,7 +73,7 @@ PORRT_API int32_t porrt_mmprm_plan(porrt_ctx* ctx, int32_t n_modes, const int64_
     }
   }
   auto& G = ctx->mm;
-  G.row_ptr.assign((size_t)T + 1, 0); G.type.assign((size_t)T, PORRT_NODE_ACTION); G.belief_id.resize((size_t)T); G.col.clear(); G.col.reserve(cl.size());
+  G.row_ptr.assign((size_t)T + 1, 0); G.type.assign((size_t)T, PORRT_NODE_ACTION); G.belief_id.resize((size_t)T); G.col.clear(); G.col.reserve((size_t)ne);
   for (int m = 0; m < n_modes; ++m) {
     const int64_t a = mode_node_ptr[m], n = mode_node_ptr[m + 1] - a;
     for (int64_t k = 0; k < n; ++k) {
@@ -78,7 +83,7 @@ PORRT_API int32_t porrt_mmprm_plan(porrt_ctx* ctx, int32_t n_modes, const int64_
         G.type[(size_t)u] = PORRT_NODE_OBSERVATION;
         G.col.insert(G.col.end(), obs[(size_t)u].begin(), obs[(size_t)u].end());
       } else {
-        G.col.insert(G.col.end(), cl.begin() + rp[(size_t)u], cl.begin() + rp[(size_t)u + 1]);   // PRM children, already global ids
+        G.col.insert(G.col.end(), cl + rp[u], cl + rp[u + 1]);   // PRM children, already global ids
       }
       G.row_ptr[(size_t)u + 1] = (int64_t)G.col.size();
     }

@@ -368,10 +368,14 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
         for (int cx = cx0; cx <= cx1; ++cx) {
           const int64_t c = (int64_t)cy * g.cells_x + cx;
           const int64_t e = g.cell_start[c + 1];
-          for (int64_t k = g.cell_start[c]; k < e; ++k) {
+          int64_t k = g.cell_start[c];
+          if (lo_limit) {   // grouped vertex sets: jump to the first id of the query's own group (the list is id-ascending)
+            int64_t hi = e;
+            while (k < hi) { const int64_t mid = (k + hi) >> 1; if ((uint32_t)g.vid[mid] < lo_limit) k = mid + 1; else hi = mid; }
+          }
+          for (; k < e; ++k) {
             const uint32_t id = (uint32_t)g.vid[k];
             if (id >= limit) break;
-            if (id < lo_limit) continue;
             if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || ((reach[id] >> wbit) & 1ull))) {
               if (FILL) out[cnt] = (int32_t)id;
               ++cnt;
@@ -409,7 +413,9 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   GridDev g = grid_dev(ctx);
   CUDA_TRY(ctx, ctx->scratch[4].ensure((size_t)m * 4 + 16));
   int32_t* counts = ctx->scratch[4].as<int32_t>();
-  const bool tiles = nn_tile_usable(ctx, m);
+  // grouped vertex sets (prefix_lo): the other groups' vertices share the cells, staging them all would only cost; the
+  // thread-per-query kernel skips to its own group inside each cell list
+  const bool tiles = nn_tile_usable(ctx, m) && !prefix_lo_dev;
   const int32_t* fb_list = nullptr;
   int32_t fb_n = 0;
   if (tiles) {   // TMA-staged tiles, warp per query; queries with a wider reach come back in fb_list
