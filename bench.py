@@ -365,10 +365,12 @@ def belief_measurement(ctx, Z=8, n_min=5000):
     gather = float(E) * B * 8 + float(V) * B * 16          # dist of every child per (node, belief) + own read/write, per sweep
     return {"zones": Z, "nodes": V, "directed_edges": E, "beliefs": B, "belief_nodes": V * B, "sweeps": int(plan.sweeps),
             "gpu_ms_total": 1e3 * best[0], "gpu_phase_ms[host tables,upload+types,sweeps,download]": [round(x, 3) for x in best[1]],
-            "sweep_bytes_each": gather, "sweep_gather_gbs": gather * plan.sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
+            "sweep_bytes_each": gather, "sweep_equiv_gbs": gather * plan.sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
             "cpu_oracle_ms[build_belief_graph,conditional_dijkstra,extract_policy]": [round(1e3 * t_build, 1), round(1e3 * t_dp, 1), round(1e3 * t_pol, 2)],
             "roadmap_growth_cpu_ms": round(1e3 * t_grow, 1), "bit_exact": exact,
-            "note": "dist table (V*B f64) is L2-resident: the sweep rate is an L2 gather rate, not HBM"}
+            "note": "sweep_equiv_gbs = bytes of FULL sweeps / time: with work skipping (nodes whose inputs did not change are not "
+                    "re-evaluated) part of those bytes is never read, so it is an equivalent rate, not a measured bandwidth; the dist "
+                    "table (V*B f64) is L2-resident"}
 
 _REAL_STDOUT = None
 
