@@ -545,6 +545,8 @@ API int orc_tamp_plan(void* p, const double* start, const double* b0, uint64_t n
   auto t2 = now();
   if (!conditional_dijkstra(h->t.belief_graph, h->t.final_belief_node_ids, h->t.expected_costs)) return 0;
   auto t3 = now();
+  // no finite cost at the root: the reference's extract_policy would walk an infinite-cost cycle forever; report failure instead
+  if (h->t.expected_costs.empty() || !std::isfinite(h->t.expected_costs[0])) return 0;
   h->ok = extract_policy(h->t.belief_graph, h->t.expected_costs, h->policy);
   auto t4 = now();
   if (seconds) { seconds[0] = secs(t0, t1); seconds[1] = secs(t1, t2); seconds[2] = secs(t2, t3); seconds[3] = secs(t3, t4); }

@@ -1109,6 +1109,7 @@ bool TampPRM::plan(State start, const BeliefState& b0, double max_step, double s
   grow_mm_prm(start, b0, max_step, search_radius, n_iter_per_belief);
   if (!build_belief_graph()) return false;
   if (!conditional_dijkstra(belief_graph, final_belief_node_ids, expected_costs)) return false;
+  if (expected_costs.empty() || !std::isfinite(expected_costs[0])) return false;   // (the reference would not terminate)
   return extract_policy(belief_graph, expected_costs, out);
 }
 

@@ -60,3 +60,12 @@ out.update(ref_path=path, ref_states=st, ref_commits=np.int64(commits))
 os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "standin_v1.npz"), **out)
 print("wrote tests/golden/standin_v1.npz:", {k: np.asarray(v).shape for k, v in out.items()})
+
+# ---- v2: multi-modal PRM (map_shelves_tamp_prm.rs): the RNG-decided schedule + expected costs + policy on the 3-shelf map
+tamp = O.TampPRM(smap, low, up)
+tpol = tamp.plan((0.0, -0.9), [1.0 / 3] * 3, 0.15, 3.0, 800)
+sch = tamp.schedule()
+out2 = {"mm_" + k: v for k, v in sch.items()}
+out2.update(mm_policy=np.asarray(tpol.original), mm_policy_parent=np.asarray(tpol.parent), mm_policy_cost=np.float64(tpol.expected_costs))
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "standin_v2.npz"), **out2)
+print("wrote tests/golden/standin_v2.npz:", {k: np.asarray(v).shape for k, v in out2.items()})

@@ -87,3 +87,36 @@ def test_cuda_reproduces_golden():
         np.testing.assert_array_equal(st, G["ref_states"]); assert commits == int(G["ref_commits"])
     finally:
         ctx.close()
+
+
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "standin_v2.npz"))
+_MM_KEYS = ("mode_node_ptr", "samples", "max_step", "search_radius", "mode_belief_id", "beliefs", "tr_from_mode", "tr_to_mode",
+            "tr_pair_ptr", "tr_pairs", "mode_final_ptr", "mode_final_nodes", "expected_costs")
+
+
+def test_oracle_reproduces_golden_mmprm():
+    """multi-modal PRM: the schedule is decided by the restated RNG streams (Pcg64 seed_from_u64 / gen_range, the mode tree),
+    so this pins them together with the PRMs, the belief graph and the value backups"""
+    smap = O.GridMap(G["shelf_occ"], G["shelf_zones"], LOW, UP, O.SHELF, 0.7)
+    tamp = O.TampPRM(smap, LOW, UP)
+    pol = tamp.plan((0.0, -0.9), [1.0 / 3] * 3, 0.15, 3.0, 800)
+    sch = tamp.schedule()
+    for k in _MM_KEYS:
+        np.testing.assert_array_equal(sch[k], G2["mm_" + k], err_msg=k)
+    np.testing.assert_array_equal(pol.original, G2["mm_policy"])
+    assert pol.expected_costs == float(G2["mm_policy_cost"]) and len(pol.leafs) == 3
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_mmprm():
+    import po_rrt_b200 as P
+    ctx = P.Context(0)
+    try:
+        smap = P.MapShelfDomain(ctx, G["shelf_occ"], LOW, UP); smap.add_zones(G["shelf_zones"], 0.7)
+        dist, graph, (node, parent, leaf, cost), _ = P.mmprm_plan(smap, {k: G2["mm_" + k] for k in _MM_KEYS})
+        np.testing.assert_array_equal(dist, G2["mm_expected_costs"])
+        np.testing.assert_array_equal(node.astype(np.int64), G2["mm_policy"])
+        np.testing.assert_array_equal(parent.astype(np.int64), G2["mm_policy_parent"])
+        assert cost == float(G2["mm_policy_cost"])
+    finally:
+        ctx.close()
