@@ -108,7 +108,8 @@ struct porrt_ctx {
   struct BeliefState_ {
     int64_t V = 0; int32_t B = 0, n_worlds = 0;
     std::vector<int64_t> row_ptr; std::vector<int32_t> col, edge_vid; std::vector<double> xy;
-    std::vector<double> beliefs, dist; std::vector<uint8_t> type;
+    std::vector<double> beliefs;
+    const double* dist = nullptr; const uint8_t* type = nullptr;   // live in ctx->pin[3] (pinned: the V*B table comes back by DMA)
     std::vector<uint8_t> exists;                  // [V*B]
     std::vector<int32_t> node_obs_set;            // [V] index into obs tables
     std::vector<int64_t> succ_ptr;                // [(n_sets*B)+1]
