@@ -1,0 +1,50 @@
+"""PTOGraph JSON (pto_graph.rs:22-118, its test :566-572 only saves and loads): round trip through the reference's on-disk layout,
+field names and nesting as serde writes them, and CSR conversion that keeps the stored edge order."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from po_rrt_b200 import graph_io, synth
+
+
+def _oracle_prm_graph():
+    occ, zones = synth.shelf_map(120, n_rects=8, n_zones=3, seed=9)
+    smap = O.GridMap(occ, zones, [-1.0, -1.0], [1.0, 1.0], O.SHELF, 0.7)
+    prm = O.PRM(smap, [-1.0, -1.0], [1.0, 1.0], seed=0)
+    prm.init([0.0, 0.0])
+    prm.grow_graph(0.15, 3.0, 300)
+    xy, nvid, rp, col, ev = prm.graph.export(0)
+    _, _, prp, pcol, pev = prm.graph.export(1)
+    return graph_io.PTOGraphArrays(xy, nvid, rp, col, ev, prp, pcol, pev, smap.world_validities())
+
+
+def test_round_trip_and_layout(tmp_path):
+    g = _oracle_prm_graph()
+    p = tmp_path / "graph.json"
+    graph_io.save_pto_graph(str(p), g)
+    doc = json.loads(p.read_text())
+    assert set(doc) == {"nodes", "validities"}
+    assert set(doc["nodes"][0]) == {"state", "validity_id", "parents", "children"}     # SerializablePTONode, pto_graph.rs:22-28
+    assert set(doc["nodes"][5]["children"][0]) == {"id", "validity_id"}                # SerializablePTOEdge, :30-34
+    assert all(isinstance(b, bool) for b in doc["validities"][0])                      # Vec<Vec<bool>>, :76-80
+    h = graph_io.load_pto_graph(str(p))
+    for a in ("xy", "node_vid", "row_ptr", "col", "edge_vid", "p_row_ptr", "p_col", "p_edge_vid", "validities"):
+        np.testing.assert_array_equal(getattr(h, a), getattr(g, a), err_msg=a)          # f64 states survive bit for bit
+
+
+def test_parents_are_the_transpose_in_insertion_order():
+    g = _oracle_prm_graph()
+    prp, pcol, pev = graph_io.transpose_csr(g.row_ptr, g.col, g.edge_vid, g.n_nodes)
+    np.testing.assert_array_equal(prp, g.p_row_ptr)
+    np.testing.assert_array_equal(np.sort(pcol[prp[7]:prp[8]]), np.sort(g.p_col[g.p_row_ptr[7]:g.p_row_ptr[8]]))
+    for k in range(g.n_nodes):                                                          # prm.rs:99-106: same sequences
+        np.testing.assert_array_equal(g.p_col[g.p_row_ptr[k]:g.p_row_ptr[k + 1]], g.col[g.row_ptr[k]:g.row_ptr[k + 1]])
+
+
+def test_rejects_wrong_state_dimension(tmp_path):
+    p = tmp_path / "bad.json"
+    p.write_text(json.dumps({"nodes": [{"state": [0.0, 1.0, 2.0], "validity_id": 0, "parents": [], "children": []}], "validities": [[True]]}))
+    with pytest.raises(ValueError):
+        graph_io.load_pto_graph(str(p))
