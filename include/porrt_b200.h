@@ -90,6 +90,11 @@ int32_t porrt_edge_validity(porrt_ctx* ctx, const double* from_xy, const double*
 /* geometric part of PTOFuncs::observe (map_io.rs:281-300, map_shelves_io.rs:242-265): bit z of out_zone_mask[i]
  * = norm2(state_i, zone_pos[z]) < visibility && line of sight.  out_status[i] = 0 or the panic code (< -1). */
 int32_t porrt_visibility(porrt_ctx* ctx, const double* xy, int64_t n, uint64_t* out_zone_mask, int32_t* out_status);
+/* transition_validator(&PTONode from, &PTONode to) as the planners call it (pto.rs:105, prm.rs:93): both ends are nodes of the
+ * vertex set uploaded with porrt_vertices_set (ids in upload order).  Same results as porrt_edge_validity on the nodes' states;
+ * 8 instead of 32 bytes per edge cross the bus.  out_world_mask nullable. */
+int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* from_idx, const int32_t* to_idx, int64_t n,
+                                    int32_t* out_validity_id, uint64_t* out_world_mask);
 
 int32_t porrt_state_validity_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_validity_id_dev);
 int32_t porrt_edge_validity_dev(porrt_ctx* ctx, const double* from_xy_dev, const double* to_xy_dev, int64_t n,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "porrt_state_validity": (i32, [vp, vp, i64, vp]),
     "porrt_edge_validity": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_visibility": (i32, [vp, vp, i64, vp, vp]),
+    "porrt_edge_validity_indexed": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_state_validity_dev": (i32, [vp, vp, i64, vp]),
     "porrt_edge_validity_dev": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_visibility_dev": (i32, [vp, vp, i64, vp, vp]),

@@ -202,6 +202,17 @@ class _GridDomain:
         self.ctx.check(self.ctx.lib.porrt_edge_validity(self.ctx.h, _p(f), _p(t), len(f), _p(out), _p(masks)))
         return (out, masks) if want_masks else out
 
+    def transition_validator_nodes(self, from_idx, to_idx, want_masks=False, vid_out=None, mask_out=None):
+        """transition_validator between nodes of the uploaded vertex set (KdTree.set / porrt_vertices_set), by id"""
+        self._need()
+        fi, ti = np.ascontiguousarray(from_idx, np.int32), np.ascontiguousarray(to_idx, np.int32)
+        n = len(fi)
+        vid = np.empty(n, np.int32) if vid_out is None else vid_out
+        masks = (np.empty((n, self.mask_words), np.uint64) if mask_out is None else mask_out) if want_masks else None
+        c = self.ctx
+        c.check(c.lib.porrt_edge_validity_indexed(c.h, _p(fi), _p(ti), n, _p(vid), _p(masks)))
+        return (vid, masks) if want_masks else vid
+
     def is_transition_valid(self, from_xy, to_xy, compat_row):
         """PTOPolicyRefiner::is_transition_valid (pto_policy_refiner.rs:395-423), batched -> (valid u8, status i32)"""
         self._need()

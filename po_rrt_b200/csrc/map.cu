@@ -769,6 +769,90 @@ PORRT_API int32_t porrt_edge_validity(porrt_ctx* ctx, const double* from_xy, con
   return PORRT_OK;
 }
 
+// transition_validator(&PTONode, &PTONode) as the planners call it (pto.rs:105, prm.rs:93): both ends are NODES.  With the node
+// states resident on the device (porrt_vertices_set / porrt_prm_build), an edge is two 4-byte ids instead of four doubles: the
+// host->device stream shrinks from 32 to 8 bytes per edge, which is what bounds the end-to-end rate of porrt_edge_validity
+// (PCIe).  Same chunked three-stream pipeline; results identical to porrt_edge_validity on the same coordinates.
+PORRT_API int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* from_idx, const int32_t* to_idx, int64_t n,
+                                              int32_t* out_vid, uint64_t* out_mask) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
+  if (n < 0 || (n > 0 && (!from_idx || !to_idx || !out_vid))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_indexed: bad arguments");
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int words = ctx->mask_words;
+  int64_t CH = n / 8;
+  CH = CH < (1 << 19) ? (1 << 19) : (CH > (1 << 22) ? (1 << 22) : CH);
+  const int64_t ch = n < CH ? n : CH;
+  const bool pinned = is_pinned_host(from_idx) && is_pinned_host(to_idx) && is_pinned_host(out_vid) && (!out_mask || is_pinned_host(out_mask));
+  const int slots = MAX_SLOTS;
+  // device slots: mask | from idx | to idx | vid
+  const size_t slot_bytes = (size_t)ch * (8 * (size_t)words + 4 + 4 + 4);
+  CUDA_TRY(ctx, ctx->scratch[3].ensure(slot_bytes * slots));
+  if (!pinned) CUDA_TRY(ctx, ctx->pin[0].ensure(slot_bytes * slots));
+  cudaStream_t st = ctx->stream;
+  const int64_t n_chunks = (n + ch - 1) / ch;
+  const double* d_xy = ctx->d_vxy.as<double>();
+  const int64_t V = ctx->n_vertices;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[0], st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
+  auto unstage = [&](int64_t c) {   // pageable outputs: copy chunk c out of its pinned slot
+    const int s = (int)(c % slots);
+    const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
+    char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+    memcpy(out_vid + off, hb + (size_t)ch * (8 * (size_t)words + 8), (size_t)cnt * 4);
+    if (out_mask) memcpy(out_mask + off * words, hb, (size_t)cnt * 8 * words);
+  };
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int s = (int)(c % slots);
+    const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
+    char* dbase = ctx->scratch[3].as<char>() + slot_bytes * s;
+    uint64_t* d_mask = (uint64_t*)dbase;
+    int32_t* d_from = (int32_t*)(dbase + (size_t)ch * 8 * (size_t)words);
+    int32_t* d_to = d_from + ch;
+    int32_t* d_vid = d_to + ch;
+    if (c >= slots) {
+      CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_out[s]));
+      if (!pinned) unstage(c - slots);
+    }
+    const int32_t *h_from = from_idx + off, *h_to = to_idx + off;
+    if (!pinned) {
+      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+      int32_t* hf = (int32_t*)(hb + (size_t)ch * 8 * (size_t)words);
+      memcpy(hf, h_from, (size_t)cnt * 4);
+      memcpy(hf + ch, h_to, (size_t)cnt * 4);
+      h_from = hf; h_to = hf + ch;
+    }
+    for (int64_t k = 0; k < cnt; k += (cnt > 4096 ? cnt / 64 : 1)) {   // cheap sanity probe; the kernel itself does not bounds-check ids
+      if (h_from[k] < 0 || h_from[k] >= V || h_to[k] < 0 || h_to[k] >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_indexed: vertex id out of range");
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_from, h_from, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_to, h_to, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_in[s], 0));
+    int32_t rc = launch_edges<true>(ctx, (const double2*)d_xy, (const double2*)d_xy, cnt, d_vid, out_mask ? d_mask : nullptr, d_from, d_to, st);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[s], st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[s], 0));
+    int32_t* h_vid = out_vid + off;
+    uint64_t* h_mask = out_mask ? out_mask + off * words : nullptr;
+    if (!pinned) {
+      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+      h_vid = (int32_t*)(hb + (size_t)ch * (8 * (size_t)words + 8));
+      h_mask = (uint64_t*)hb;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_vid, d_vid, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(h_mask, d_mask, (size_t)cnt * 8 * words, cudaMemcpyDeviceToHost, ctx->copy_out));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (!pinned)
+    for (int64_t c = n_chunks > slots ? n_chunks - slots : 0; c < n_chunks; ++c) unstage(c);
+  return PORRT_OK;
+}
+
 PORRT_API int32_t porrt_state_validity_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_dev) {
   CTX_CHECK(ctx);
   if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");

@@ -322,6 +322,10 @@ PORRT_API int32_t porrt_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, i
   CTX_CHECK(ctx);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (!xy_dev) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_set_dev: null");
+  if (n > 0 && xy_dev != ctx->d_vxy.as<double>()) {   // the library keeps its own copy in upload order (porrt_edge_validity_indexed reads it)
+    CUDA_TRY(ctx, ctx->d_vxy.ensure((size_t)n * 16));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vxy.p, xy_dev, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   return nn_vertices_set_dev(ctx, xy_dev, n, cell_size, lo, hi);
 }
 

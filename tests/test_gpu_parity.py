@@ -833,3 +833,31 @@ def test_mmprm_plan_vs_oracle(ctx, n_zones, start, n_iter):
     np.testing.assert_array_equal(parent.astype(np.int64), opol.parent)
     np.testing.assert_array_equal(np.nonzero(leaf)[0], opol.leafs)
     assert cost == opol.expected_costs and len(opol.leafs) == n_zones
+
+
+def test_edges_between_nodes_by_id(ctx):
+    """porrt_edge_validity_indexed == porrt_edge_validity on the nodes' states (ids, masks, panic codes), pageable and pinned
+    buffers, several pipeline chunks"""
+    import torch
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    pts = synth.points(50_000, seed=21)
+    pts[:200] = np.random.default_rng(1).uniform(-1.2, 1.2, (200, 2))        # some nodes outside the map: panic codes
+    tree = P.KdTree(ctx, pts)
+    rng = np.random.default_rng(5)
+    n = 1_300_000
+    fi = rng.integers(0, len(pts), n).astype(np.int32)
+    ti = (fi + rng.integers(1, 40, n)).astype(np.int32) % len(pts)            # short and long edges
+    ti[:100_000] = np.argsort(pts[:, 0])[rng.integers(0, len(pts) - 1, 100_000)].astype(np.int32)
+    want_vid, want_mask = pmap.transition_validator(pts[fi], pts[ti], want_masks=True)
+    got_vid, got_mask = pmap.transition_validator_nodes(fi, ti, want_masks=True)
+    np.testing.assert_array_equal(got_vid, want_vid)
+    np.testing.assert_array_equal(got_mask, want_mask)
+    np.testing.assert_array_equal(got_vid[:20000].astype(np.int64), omap.edge_validity(pts[fi[:20000]], pts[ti[:20000]]))
+    pf, pt = torch.from_numpy(fi).pin_memory().numpy(), torch.from_numpy(ti).pin_memory().numpy()
+    pv = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+    got2 = pmap.transition_validator_nodes(pf, pt, vid_out=pv)
+    np.testing.assert_array_equal(got2, want_vid)
+    assert (want_vid >= 0).any() and (want_vid == -1).any() and (want_vid < -1).any()
+    with pytest.raises(P.PorrtError):
+        pmap.transition_validator_nodes(np.array([0, len(pts)], np.int32), np.array([1, 2], np.int32))
