@@ -547,6 +547,37 @@ def main():
             import traceback
             multi = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
 
+    # ---- the same edges as NODE PAIRS (transition_validator(&node, &node), pto.rs:105 / prm.rs:93): node states resident on the
+    # device (uploaded once, outside the timed region, like a roadmap's vertices), per step 8 B of ids in and 12 B out per edge
+    nodes_e2e = None
+    if not args.no_extras:
+        try:
+            tree = P.KdTree(ctx, np.concatenate([a, b]), cell_size=0.01)
+            h_fi = torch.arange(0, E, dtype=torch.int32).pin_memory()
+            h_ti = torch.arange(E, 2 * E, dtype=torch.int32).pin_memory()
+            h_vid2 = torch.empty(E, dtype=torch.int32).pin_memory()
+            h_mask2 = torch.empty(E, dtype=torch.int64).pin_memory()
+
+            def step_nodes():
+                ctx.check(lib.porrt_edge_validity_indexed(h, h_fi.data_ptr(), h_ti.data_ptr(), E, h_vid2.data_ptr(), h_mask2.data_ptr()))
+            step_nodes()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                step_nodes()
+            barrier()
+            t_n = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_n, op=dist.ReduceOp.MAX)
+            assert torch.equal(h_vid2, h_vid) and torch.equal(h_mask2, h_mask)
+            v = E * world * N_WORLDS * e2e_steps / float(t_n.item())
+            nodes_e2e = {"value": v, "unit": UNIT, "edges_per_s": v / N_WORLDS, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 12 * E,
+                         "resident_vertices": 2 * E, "identical_to_e2e": True,
+                         "note": "porrt_edge_validity_indexed: the step's edges given as pairs of node ids into a device-resident vertex set"}
+            del tree
+        except Exception as e:
+            nodes_e2e = {"error": repr(e)}
+
     line = None
     os.sched_setaffinity(0, affinity0)
     if rank == 0:
@@ -566,6 +597,7 @@ def main():
     # ---- side measurements of the other BASELINE metrics (kNN queries/s, PRM build ms); not part of `value`
     if rank == 0 and not args.no_extras:
         line["extras"] = side_measurements(ctx, pmap, args)
+        line["extras"]["edges_by_node_id_e2e"] = nodes_e2e
         if multi is not None:
             line["extras"]["multi_gpu"] = multi
     if rank == 0:
