@@ -133,6 +133,8 @@ struct porrt_ctx {
   int comm_rank = 0, comm_world = 1;
 
   // ---- scratch
+  DevBuf kd_buf;                       // kd pre-order rank work space (its own: the rank runs concurrently with the binning sort)
+  cudaStream_t aux_stream = nullptr;   // second compute stream (created on first use): kd rank next to radius / edge batches
   DevBuf scratch[12];
   PinBuf pin[6];
 };
@@ -220,4 +222,7 @@ int bits_for(uint64_t max_value);
 int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,
                        const double* ms_arr, const double* sr_arr, int64_t* out_row_ptr, int32_t* out_col, int64_t cap,
                        int64_t* out_n_edges, double* out_phase_ms, const int64_t* group_ptr = nullptr, int32_t n_groups = 0);
-int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev, const uint32_t* root_of_dev = nullptr);
+// st / err / n_launch: when the rank is computed by a helper thread on its own stream, errors and launch counts come back through
+// these instead of touching ctx (st == nullptr: ctx->stream, ctx->err, ctx->launches as usual)
+int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev, const uint32_t* root_of_dev = nullptr,
+                             cudaStream_t st = nullptr, std::string* err = nullptr, int64_t* n_launch = nullptr);

@@ -46,6 +46,8 @@ PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
   ctx->d_vxy.release(); ctx->d_vcell.release();
   for (DevBuf& b : ctx->nn_tmp) b.release();
   for (DevBuf& b : ctx->scratch) b.release();
+  ctx->kd_buf.release();
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   for (PinBuf& b : ctx->pin) b.release();
   for (int s = 0; s < MAX_SLOTS; ++s) {
     if (ctx->ev_in[s]) cudaEventDestroy(ctx->ev_in[s]);

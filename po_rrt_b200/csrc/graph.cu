@@ -95,12 +95,21 @@ __global__ void kd_init_kernel(int64_t n, int32_t* __restrict__ cur, int32_t* __
   size[i] = 0; node_depth[i] = i == root ? 0 : -1; rank[i] = i == root ? (int32_t)root : 0;
 }
 
-// xy_dev: n vertices (device); out_rank_dev[n]; uses ctx->scratch[8..10]
-int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev, const uint32_t* root_of_dev) {
-  cudaStream_t st = ctx->stream;
+// xy_dev: n vertices (device); out_rank_dev[n]; work space ctx->kd_buf
+int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_rank_dev, const uint32_t* root_of_dev,
+                             cudaStream_t st_in, std::string* err, int64_t* n_launch) {
+  cudaStream_t st = st_in ? st_in : ctx->stream;
+  int64_t launches = 0;
+  auto fail = [&](const char* what, cudaError_t e) {
+    const std::string msg = std::string("kd_preorder_rank: ") + what + " -> " + cudaGetErrorString(e);
+    if (err) *err = msg; else ctx->err = msg;
+    return PORRT_ERR_CUDA;
+  };
+#define KD_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(#expr, _e); } while (0)
+#define KD_LAUNCHED() do { ++launches; KD_TRY(cudaGetLastError()); } while (0)
   if (n <= 0) return PORRT_OK;
-  CUDA_TRY(ctx, ctx->scratch[8].ensure((size_t)n * 4 * 6 + (size_t)n + 64));
-  char* b = ctx->scratch[8].as<char>();
+  KD_TRY(ctx->kd_buf.ensure((size_t)n * 4 * 6 + (size_t)n + 64));
+  char* b = ctx->kd_buf.as<char>();
   int32_t* cur = (int32_t*)b; b += (size_t)n * 4;
   int32_t* child = (int32_t*)b; b += (size_t)n * 8;
   int32_t* size = (int32_t*)b; b += (size_t)n * 4;
@@ -110,26 +119,29 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
   uint8_t* side = (uint8_t*)b;
   const int blocks = div_up(n, 256);
   kd_init_kernel<<<blocks, 256, 0, st>>>(n, cur, child, size, node_depth, out_rank_dev, root_of_dev);
-  LAUNCH_CHECK(ctx);
+  KD_LAUNCHED();
   int depth = 0;
   for (;; ++depth) {
-    if ((depth & 3) == 0) CUDA_TRY(ctx, cudaMemsetAsync(remaining, 0, 4, st));
+    if ((depth & 3) == 0) KD_TRY(cudaMemsetAsync(remaining, 0, 4, st));
     if (depth < 14) kd_descend_kernel<true><<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
     else kd_descend_kernel<false><<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
-    LAUNCH_CHECK(ctx);
+    KD_LAUNCHED();
     kd_place_kernel<<<blocks, 256, 0, st>>>(n, depth, cur, child, side, parent, node_depth, (depth & 3) == 3 ? remaining : nullptr);
-    LAUNCH_CHECK(ctx);
+    KD_LAUNCHED();
     if ((depth & 3) != 3) continue;      // the host looks at the number of unplaced points every fourth level only
     int32_t rem = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&rem, remaining, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    KD_TRY(cudaMemcpyAsync(&rem, remaining, 4, cudaMemcpyDeviceToHost, st));
+    KD_TRY(cudaStreamSynchronize(st));
     if (rem == 0) break;
-    if (depth > n + 4) return porrt_fail(ctx, PORRT_ERR_CUDA, "kd_preorder_rank: no convergence");
+    if (depth > n + 4) return fail("no convergence", cudaErrorUnknown);
   }
   for (int d = 1; d <= depth + 1; ++d) {
     kd_rank_kernel<<<blocks, 256, 0, st>>>(n, d, node_depth, parent, side, child, size, out_rank_dev);
-    LAUNCH_CHECK(ctx);
+    KD_LAUNCHED();
   }
+#undef KD_TRY
+#undef KD_LAUNCHED
+  if (n_launch) *n_launch = launches; else ctx->launches += launches;
   return PORRT_OK;
 }
 
@@ -332,6 +344,24 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   CUDA_TRY(ctx, cudaMemsetAsync(d_late_cnt, 0, (size_t)n * 4, st));
   CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
 
+  // the kd pre-order rank of every vertex (restores the reference's neighbour order in step 5) needs only the coordinates: ~150
+  // small launches with a host check every fourth tree level, latency-bound.  A helper thread runs it on a second stream while
+  // this thread bins, searches and checks edges (throughput-bound kernels); the two meet before the neighbour lists are sorted.
+  if (!ctx->aux_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[1], st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_k[1], 0));
+  struct KdJob { int32_t rc = PORRT_OK; std::string err; int64_t launches = 0; std::thread th; bool joined = true; } kd;
+  {
+    porrt_ctx* c = ctx; int32_t* rank_out = d_rank; const uint32_t* roots = d_group_base; KdJob* job = &kd;
+    kd.joined = false;
+    kd.th = std::thread([c, n, rank_out, roots, job]() {
+      if (cudaSetDevice(c->device) != cudaSuccess) { job->rc = PORRT_ERR_CUDA; job->err = "kd thread: cudaSetDevice failed"; return; }
+      job->rc = kd_preorder_rank_dev(c, c->d_vxy.as<double>(), n, rank_out, roots, c->aux_stream, &job->err, &job->launches);
+      if (job->rc == PORRT_OK && cudaStreamSynchronize(c->aux_stream) != cudaSuccess) { job->rc = PORRT_ERR_CUDA; job->err = "kd thread: stream sync failed"; }
+    });
+  }
+  struct KdJoiner { KdJob& j; ~KdJoiner() { if (!j.joined && j.th.joinable()) j.th.join(); } } kd_joiner{kd};   // early returns
+
   // 1. bin vertices; cell = the smallest radius in use (the last one) so late queries touch 3x3 cells
   double r_last = n > 1 ? heuristic_radius((size_t)n, max_step, search_radius, 2) : -1.0;
   if (ms_arr || sr_arr) {   // per-sample parameters: the smallest positive radius in use (needs the radii: no overlap here)
@@ -346,12 +376,6 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
-
-  // 2. the kd pre-order rank of every vertex (restores the reference's neighbour order in step 4)
-  rc = kd_preorder_rank_dev(ctx, ctx->d_vxy.as<double>(), n, d_rank, d_group_base);
-  if (rc) return rc;
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  t1 = now_ms(); ph[3] = t1 - t0; t0 = t1;
 
   for (auto& x : th) if (x.joinable()) x.join();
   if (m > 0) CUDA_TRY(ctx, cudaMemcpyAsync(d_radius + lo, radius + lo, (size_t)m * 8, cudaMemcpyHostToDevice, st));
@@ -368,14 +392,9 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
 
-  // 4. restore the kd pre-order inside every neighbour list
   int32_t* d_ids = ctx->scratch[2].as<int32_t>();
-  if (m > 0) rc = segments_sort_by_key_dev(ctx, d_off, m, d_ids, d_rank, n);
-  if (rc) return rc;
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  t1 = now_ms(); ph[4] = t1 - t0; t0 = t1;
 
-  // 5. edge checks neighbour -> new node (prm.rs:91-96)
+  // 4. edge checks neighbour -> new node (prm.rs:91-96); the order inside a list does not matter to them
   const int64_t tot1 = std::max<int64_t>(total, 1);
   CUDA_TRY(ctx, ctx->scratch[0].ensure((size_t)tot1 * 4));  // owner (= new node id)
   CUDA_TRY(ctx, ctx->scratch[1].ensure((size_t)tot1 * 4));  // validity ids
@@ -390,7 +409,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[5] = t1 - t0; t0 = t1;
 
-  // 6. CSR in insertion order: row k = valid earlier neighbours (kd order), then later nodes ascending (prm.rs:99-106)
+  // 5. + 6. valid neighbours in kd pre-order, then the CSR in insertion order: row k = valid earlier neighbours (kd order), then later nodes ascending (prm.rs:99-106)
   if (m > 0) {
     prm_compact_kernel<<<div_up(m * 32, 256), 256, 0, st>>>(d_off, m, d_ids, d_vid, d_early_cnt + lo, d_ids, d_flag);
     LAUNCH_CHECK(ctx);
@@ -405,6 +424,28 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
     CUDA_TRY(ctx, cudaMemcpyAsync(&n_half, d_early_off + n, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (flag >= -1) {
+      // valid neighbours packed densely, then every list put into kd pre-order (2/3 of the candidates are left to sort)
+      CUDA_TRY(ctx, ctx->scratch[0].ensure((size_t)std::max<int64_t>(n_half, 1) * 4));   // the owner list is dead by now
+      int32_t* d_dense = ctx->scratch[0].as<int32_t>();
+      prm_pack_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_off, d_early_off, n, d_ids, d_early_cnt, d_dense);
+      LAUNCH_CHECK(ctx);
+      const double tw = now_ms();
+      rc = [&]() -> int32_t {   // meet the kd-rank thread
+    if (!kd.joined) { kd.th.join(); kd.joined = true; ctx->launches += kd.launches; }
+    if (kd.rc) return porrt_fail(ctx, kd.rc, kd.err);
+    return PORRT_OK;
+  }();
+      if (rc) return rc;
+      ph[3] = now_ms() - tw;   // what is left of the kd rank after the overlap
+      const double ts = now_ms();
+      rc = segments_sort_by_key_dev(ctx, d_early_off, n, d_dense, d_rank, n);
+      if (rc) return rc;
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      ph[4] = now_ms() - ts;
+      t0 += ph[3] + ph[4];     // keep them out of the csr phase below
+      d_seg_off = d_early_off; d_compact = d_dense;
+    }
   } else {
     // the exchange step: every rank gets all counts and all valid (neighbour, new node) lists, then
     // assembles the whole CSR itself -- the graph stays device-resident on every GPU for the value backups that follow.
@@ -440,6 +481,14 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
         prm_pack_kernel<<<div_up(m * 32, 256), 256, 0, st>>>(d_off, d_local_off, m, d_ids, d_early_cnt + lo, d_dense + ids_off[ctx->comm_rank] / 4);
         LAUNCH_CHECK(ctx);
       }
+      rc = [&]() -> int32_t {   // meet the kd-rank thread
+    if (!kd.joined) { kd.th.join(); kd.joined = true; ctx->launches += kd.launches; }
+    if (kd.rc) return porrt_fail(ctx, kd.rc, kd.err);
+    return PORRT_OK;
+  }();
+      if (rc) return rc;
+      if (m > 0) rc = segments_sort_by_key_dev(ctx, d_local_off, m, d_dense + ids_off[ctx->comm_rank] / 4, d_rank, n);   // kd pre-order, this rank's lists
+      if (rc) return rc;
       rc = comm_all_gatherv_dev(ctx, nullptr, d_dense, ids_off.data(), st);
       if (rc) return rc;
       rc = scan_exclusive_i64(ctx, d_early_cnt, n, d_early_off);
