@@ -21,7 +21,11 @@ PORRT_API int32_t porrt_ctx_create(int32_t device, porrt_ctx** out_ctx) {
   porrt_ctx* ctx = new porrt_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  // the main compute stream outranks the helper stream (graph.cu: kd rank next to the radius / edge batches)
+  bool ok = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_least) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
   for (int s = 0; ok && s < MAX_SLOTS; ++s)
