@@ -861,3 +861,48 @@ def test_edges_between_nodes_by_id(ctx):
     assert (want_vid >= 0).any() and (want_vid == -1).any() and (want_vid < -1).any()
     with pytest.raises(P.PorrtError):
         pmap.transition_validator_nodes(np.array([0, len(pts)], np.int32), np.array([1, 2], np.int32))
+
+
+# ---------------------------------------------------------------------------------------------- empty / degenerate inputs
+def test_empty_and_degenerate_inputs(ctx):
+    """batches of zero, single vertices, k larger than the vertex set, graphs without edges or goals: every entry point answers
+    (or refuses with an error code) instead of faulting"""
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    e0 = np.zeros((0, 2))
+    assert len(pmap.transition_validator(e0, e0)) == 0
+    assert len(pmap.state_validity(e0)) == 0
+    vz, st = pmap.visible_zones(e0)
+    assert len(vz) == 0 and len(st) == 0
+    # one vertex
+    tree = P.KdTree(ctx, np.array([[0.25, -0.5]]))
+    offs, ids = tree.nearest_neighbors(e0, 0.1)
+    assert list(offs) == [0] and len(ids) == 0
+    offs, ids = tree.nearest_neighbors([[0.25, -0.5], [0.9, 0.9]], [0.0, 0.05])
+    assert list(offs) == [0, 1, 1] and list(ids) == [0]                       # radius 0 finds the exact duplicate only
+    nid, nd, ties = tree.nearest_neighbor([[0.0, 0.0], [5.0, 5.0]])
+    assert list(nid) == [0, 0]
+    kid, kd = tree.knn([[0.0, 0.0]], 4)                                        # k > V: the missing entries are marked
+    assert kid[0, 0] == 0 and (kid[0, 1:] < 0).all() and np.isinf(kd[0, 1:]).all()
+    assert len(pmap.transition_validator_nodes(np.zeros(0, np.int32), np.zeros(0, np.int32))) == 0
+    # PRM with one and two samples
+    for n in (1, 2):
+        prm = P.PRM(pmap)
+        prm.grow_graph(np.array([[0.0, 0.0], [0.01, 0.0]])[:n], 0.1, 2.0)
+        oprm = O.PRM(omap, util.LOW, util.UP, seed=0)
+        oprm.add_samples(np.array([[0.0, 0.0], [0.01, 0.0]])[:n], 0.1, 2.0)
+        _, _, rp, col, _ = oprm.graph.export(0)
+        np.testing.assert_array_equal(prm.row_ptr, rp)
+        np.testing.assert_array_equal(prm.col, col)
+    # value backups: a graph without edges, no goals, a goal only
+    xy = np.array([[0.0, 0.0], [0.1, 0.0], [0.2, 0.0]])
+    rp, col = np.zeros(4, np.int64), np.zeros(0, np.int32)
+    d, _ = P.dijkstra_worlds(ctx, rp, col, xy, None, None, [1])
+    np.testing.assert_array_equal(d, [np.inf, 0.0, np.inf])
+    d, _ = P.dijkstra_worlds(ctx, rp, col, xy, None, None, [])
+    assert np.isinf(d).all()
+    g = P.BeliefGraph(ctx, rp, col, xy, [P.NODE_ACTION] * 3, [0, 0, 0], [[1.0, 0.0]])
+    np.testing.assert_array_equal(g.conditional_dijkstra([2]), [np.inf, np.inf, 0.0])
+    assert np.isinf(g.conditional_dijkstra([])).all()
+    node, parent, leaf, cost = g.extract_policy(g.conditional_dijkstra([0]))   # the root is a goal: a policy of one node
+    assert list(node) == [0] and list(parent) == [-1] and cost == 0.0
