@@ -906,3 +906,23 @@ def test_empty_and_degenerate_inputs(ctx):
     assert np.isinf(g.conditional_dijkstra([])).all()
     node, parent, leaf, cost = g.extract_policy(g.conditional_dijkstra([0]))   # the root is a goal: a policy of one node
     assert list(node) == [0] and list(parent) == [-1] and cost == 0.0
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE config 1: RRT* (sequential caller)
+def test_rrt_star_through_per_query_wrappers(ctx):
+    """rrt.rs:269-304 shape (RRT* on a MapShelfDomain, plan(start, goal, 0.1, 2.0, 2500, 10000)): the planner is sequential and
+    stays on the host; run over the oracle and over the product's per-query calls it must grow the same tree"""
+    import rrt_mirror as R
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    start = [0.0, -0.8]
+    zp = omap.zone_positions()
+    gx = next(float(zp[0][0]) - dx for dx in (0.06, 0.1, 0.15, 0.2, 0.3) if omap.state_validity([[float(zp[0][0]) - dx, float(zp[0][1])]])[0] >= 0)
+    goal = O.SquareGoal([((gx, float(zp[0][1])), [1])], 0.05)
+    samples = O.Pcg64(0).sample_states(util.LOW, util.UP, 2500)
+    want = R.grow_tree(R.OracleBackend(omap, start), samples, start, goal, 0.1, 2.0, 900, 2500)
+    got = R.grow_tree(R.ProductBackend(pmap, start), samples, start, goal, 0.1, 2.0, 900, 2500)
+    np.testing.assert_array_equal(got[0], want[0])      # states (steered samples)
+    np.testing.assert_array_equal(got[1], want[1])      # parents after choose-parent and rewiring
+    np.testing.assert_array_equal(got[2], want[2])      # dist_from_root, bit-exact
+    assert got[3] == want[3] and len(want[3]) > 0 and len(want[0]) > 600
