@@ -79,8 +79,15 @@ class ProductBackend:
     def nearest(self, q):
         self._sync()
         nid, _, ties = self.tree.nearest_neighbor([q])
-        if ties[0] != 1:      # equidistant vertices: the kd visit order decides (nearest_neighbor.rs:52-92); not expected with random samples
-            raise AssertionError("tie in 1-NN: resolve with the kd order on the host")
+        if ties[0] != 1:
+            # several vertices at exactly the winning distance.  Exact duplicates of one point (the goal-biased samples repeat the
+            # goal, rrt.rs:176-181) chain to the right in insertion order, so the reference's strict `d < dmin` keeps the lowest id
+            # -- which is what the library returns.  Distinct equidistant points would need the kd visit order: not expected here.
+            st = np.asarray(self.states)
+            dx, dy = q[0] - st[:, 0], q[1] - st[:, 1]
+            d2 = dx * dx + dy * dy
+            tied = np.nonzero(d2 == d2[nid[0]])[0]
+            assert len(tied) == ties[0] and (st[tied] == st[tied[0]]).all() and tied[0] == nid[0], "tie among distinct points"
         return int(nid[0])
 
     def neighbors(self, q, radius):
