@@ -549,6 +549,41 @@ def test_belief_planning_shelf_8_goals_config3(ctx):
     np.testing.assert_array_equal(got, pto.plan_qmdp())
 
 
+def test_belief_planning_12_goals_config4_full_size(ctx):
+    """BASELINE config 4 shape at FULL size (12 goal zones, B = 4095 beliefs, grow_graph(.., 0.05, 5.0, 5000, ..), main.rs:386-411) on a
+    stand-in map.  The reference's materialised belief graph is 'typically intractable' here (main.rs:385) and so is the oracle's, so
+    the 1.9e7-entry result is checked through what can be verified independently:
+      * the 12 fully informed beliefs have no observation edges, their columns are plain shortest paths: bit-equal to the oracle's
+        `dijkstra` towards that world's final nodes;
+      * the table is a fixed point (a second run gives the same bits) and informing never hurts: the root's expected cost under the
+        uniform belief is at least the probability-weighted cost of the informed columns;
+      * the policy ends in 12 leaves, one per world."""
+    Z = 12
+    occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.2)
+    zp = omap.zone_positions()
+    goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
+    pto = _grow_pto(omap, (0.0, -0.9), goals, 0.05, 5.0, 5000)
+    xy, nvid, rp, col, ev = pto.graph.export(0)
+    fin_ids, fin_bits = pto.reach.finals()
+    b0 = [1.0 / Z] * Z
+    plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
+    assert plan.beliefs.shape == (4095, Z) and plan.dist.shape == (len(xy), 4095)
+    informed = {int(np.argmax(b)): k for k, b in enumerate(plan.beliefs) if b.max() == 1.0}
+    assert sorted(informed) == list(range(Z))
+    for z, b in informed.items():
+        want = pto.graph.dijkstra(pto.reach.get_final_nodes_for_world(z))
+        np.testing.assert_array_equal(plan.dist[:, b], want, err_msg="world %d" % z)
+        assert (plan.type[:, b] != P.NODE_OBSERVATION).all()
+    again = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
+    np.testing.assert_array_equal(again.dist, plan.dist)
+    root = plan.dist[0, 0]
+    assert np.isfinite(root) and root >= sum(plan.dist[0, informed[z]] for z in range(Z)) / Z - 1e-12
+    assert plan.expected_cost == root and int(plan.policy_leaf.sum()) == Z
+    leaf_worlds = sorted(int(np.argmax(plan.beliefs[b])) for b in plan.policy_belief[plan.policy_leaf != 0])
+    assert leaf_worlds == list(range(Z))
+
+
 def test_build_belief_graph_mock(ctx):
     """pto.rs:548-590 'mock graph growth' on a stand-in map: node 2 sees the door, belief jump only there"""
     size = 200
