@@ -447,6 +447,15 @@ API void orc_pto_free(void* p) { delete (PTO*)p; }
 API int orc_pto_grow_graph(void* p, const double* start, void* goal, double max_step, double search_radius, uint64_t n_min, uint64_t n_max) {
   return ((PTO*)p)->grow_graph({start[0], start[1]}, *(SquareGoal*)goal, max_step, search_radius, n_min, n_max);
 }
+// per-query hooks (PTOHooks): the growth then runs as the caller of whoever implements them; null pointers keep the oracle's own
+API void orc_pto_set_hooks(void* p, void* nearest_filtered, void* radius, void* state_validity, void* edges, void* add_vertex) {
+  PTOHooks& h = ((PTO*)p)->hooks;
+  h.nearest_filtered = (decltype(h.nearest_filtered))nearest_filtered;
+  h.radius = (decltype(h.radius))radius;
+  h.state_validity = (decltype(h.state_validity))state_validity;
+  h.edges = (decltype(h.edges))edges;
+  h.add_vertex = (decltype(h.add_vertex))add_vertex;
+}
 API void* orc_pto_graph(void* p) { return &((PTO*)p)->graph; }
 API void* orc_pto_kdtree(void* p) { return &((PTO*)p)->kdtree; }
 API void* orc_pto_reach(void* p) { return &((PTO*)p)->reach; }

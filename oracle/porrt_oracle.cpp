@@ -734,30 +734,63 @@ int PTO::grow_graph(State start, const SquareGoal& goal, double max_step, double
   graph.add_node(start, (size_t)root_vid);
   reach.set_root(graph.validities[(size_t)root_vid]);
   kdtree.reset(start);
+  if (hooks.add_vertex) hooks.add_vertex(hooks.user, start.data(), 0);
   size_t i = 0;
+  std::vector<uint64_t> reach_words;
+  std::vector<int64_t> hook_ids;
   while (i < n_iter_min || (!reach.is_final_set_complete() && i < n_iter_max)) {
     i += 1;
     // sample(), pto.rs:141-149
     size_t world = discrete.sample(n_worlds);
     State new_state = (i % 100 == 0) ? goal.goal_example(world) : continuous.sample();
-    const KdTree::Node& kd_from = nn_filtered(kdtree, new_state, [&](size_t id) { return reach.reachabilities[id][world] != 0; });
-    State from_state = kd_from.state;
-    size_t from_id = kd_from.id;
+    State from_state;
+    size_t from_id;
+    if (hooks.nearest_filtered) {
+      const size_t V = graph.nodes.size(), words = (n_worlds + 63) / 64;
+      reach_words.assign(V * words, 0);
+      for (size_t id = 0; id < V; ++id)
+        for (size_t w = 0; w < n_worlds; ++w)
+          if (reach.reachabilities[id][w]) reach_words[id * words + w / 64] |= 1ull << (w % 64);
+      int64_t id = hooks.nearest_filtered(hooks.user, new_state.data(), world, reach_words.data(), V, words);
+      if (id < 0 || (size_t)id >= V) return -101;
+      from_id = (size_t)id; from_state = graph.nodes[from_id].state;
+    } else {
+      const KdTree::Node& kd_from = nn_filtered(kdtree, new_state, [&](size_t id) { return reach.reachabilities[id][world] != 0; });
+      from_state = kd_from.state; from_id = kd_from.id;
+    }
     steer(from_state, new_state, max_step);
-    int64_t svid = fns->state_validity(new_state);
+    int64_t svid = hooks.state_validity ? hooks.state_validity(hooks.user, new_state.data()) : fns->state_validity(new_state);
     if (svid < NONE) return (int)svid;
     if (svid >= 0) {
       size_t new_id = graph.add_node(new_state, (size_t)svid);
       reach.add_node(graph.validities[(size_t)svid]);
       double radius = heuristic_radius(graph.nodes.size(), max_step, search_radius, 2);
       std::vector<size_t> neighbours;
-      for (const KdTree::Node* n : kdtree.nearest_neighbors(new_state, radius)) neighbours.push_back(n->id);
+      if (hooks.radius) {
+        hook_ids.resize(graph.nodes.size());
+        int64_t cnt = hooks.radius(hooks.user, new_state.data(), radius, hook_ids.data(), (int64_t)hook_ids.size());
+        if (cnt < 0 || cnt > (int64_t)hook_ids.size()) return -102;
+        for (int64_t k = 0; k < cnt; ++k) neighbours.push_back((size_t)hook_ids[k]);
+      } else {
+        for (const KdTree::Node* n : kdtree.nearest_neighbors(new_state, radius)) neighbours.push_back(n->id);
+      }
       if (neighbours.empty()) neighbours.push_back(from_id);
       std::vector<std::pair<size_t, size_t>> edges;
-      for (size_t id : neighbours) {
-        int64_t v = fns->transition_validator(graph.nodes[id].state, graph.nodes[new_id].state);
-        if (v < NONE) return (int)v;
-        if (v >= 0) edges.push_back({id, (size_t)v});
+      std::vector<int64_t> vids(neighbours.size());
+      if (hooks.edges) {
+        std::vector<double> fr(2 * neighbours.size()), to(2 * neighbours.size());
+        for (size_t k = 0; k < neighbours.size(); ++k) {
+          fr[2 * k] = graph.nodes[neighbours[k]].state[0]; fr[2 * k + 1] = graph.nodes[neighbours[k]].state[1];
+          to[2 * k] = new_state[0]; to[2 * k + 1] = new_state[1];
+        }
+        hooks.edges(hooks.user, fr.data(), to.data(), (int64_t)neighbours.size(), vids.data());
+      } else {
+        for (size_t k = 0; k < neighbours.size(); ++k) vids[k] = fns->transition_validator(graph.nodes[neighbours[k]].state, graph.nodes[new_id].state);
+      }
+      for (size_t k = 0; k < neighbours.size(); ++k) {
+        int64_t v = vids[k];
+        if (v < NONE) return (int)v;     // (the reference panics at the first offending edge; any of them fails the call here)
+        if (v >= 0) edges.push_back({neighbours[k], (size_t)v});
       }
       for (auto& e : edges) {
         reach.add_edge(e.first, new_id, graph.validities[e.second]);
@@ -770,6 +803,7 @@ int PTO::grow_graph(State start, const SquareGoal& goal, double max_step, double
       WorldMask finality;
       if (goal.goal(new_state, &finality)) reach.add_final_node(new_id, finality);
       kdtree.add(new_state, new_id);
+      if (hooks.add_vertex) hooks.add_vertex(hooks.user, new_state.data(), new_id);
     }
   }
   n_it = i;

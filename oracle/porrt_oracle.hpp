@@ -210,7 +210,20 @@ struct PRM {  // prm.rs
   std::vector<State> plan_path(State start, State goal);
 };
 
+// Per-query answers supplied from outside (tests: the product's per-query wrappers, so that the sequential PTO growth of
+// pto.rs:55-139 runs as the CALLER of the drop-in boundary).  Any null entry falls back to the oracle's own function.
+struct PTOHooks {
+  // 1-NN among the vertices whose reachability bit `world` is set (pto.rs:74-77); the root if none passes (nearest_neighbor.rs:89)
+  int64_t (*nearest_filtered)(void* user, const double* q, uint64_t world, const uint64_t* reach_words, uint64_t n_nodes, uint64_t words) = nullptr;
+  int64_t (*radius)(void* user, const double* q, double r, int64_t* out_ids, int64_t cap) = nullptr;   // kd pre-order
+  int64_t (*state_validity)(void* user, const double* q) = nullptr;
+  void (*edges)(void* user, const double* from_xy, const double* to_xy, int64_t n, int64_t* out_vid) = nullptr;
+  void (*add_vertex)(void* user, const double* q, uint64_t id) = nullptr;
+  void* user = nullptr;
+};
+
 struct PTO {  // pto.rs
+  PTOHooks hooks;
   const GridMap* fns;
   ContinuousSampler continuous;
   DiscreteSampler discrete;

@@ -64,6 +64,7 @@ _SIGS = {
     "orc_prm_add_samples": (f64, [vp, vp, u64, f64, f64]), "orc_prm_graph": (vp, [vp]), "orc_prm_kdtree": (vp, [vp]), "orc_prm_plan_path": (i64, [vp, vp, vp, vp, i64]),
     "orc_pto_new": (vp, [vp, vp, vp, u64]), "orc_pto_free": (None, [vp]),
     "orc_pto_grow_graph": (C.c_int, [vp, vp, vp, f64, f64, u64, u64]),
+    "orc_pto_set_hooks": (None, [vp, vp, vp, vp, vp, vp]),
     "orc_pto_graph": (vp, [vp]), "orc_pto_kdtree": (vp, [vp]), "orc_pto_reach": (vp, [vp]),
     "orc_pto_belief_graph": (vp, [vp]), "orc_pto_n_it": (u64, [vp]), "orc_pto_set_n_worlds": (None, [vp, u64]),
     "orc_pto_set_validities": (None, [vp, vp, u64, u64]), "orc_pto_build_belief_graph": (C.c_int, [vp, vp, u64]),
@@ -576,6 +577,41 @@ class PTO:
 
     def grow_graph(self, start, goal, max_step, search_radius, n_iter_min, n_iter_max):
         return lib().orc_pto_grow_graph(self.h, P(f64a(start)), goal.h, max_step, search_radius, n_iter_min, n_iter_max)
+
+    # per-query hooks (PTOHooks in porrt_oracle.hpp): the growth runs as the caller of `backend`, an object with
+    # nearest_filtered(q, world, reach_words[V, words]) -> id, radius(q, r) -> ids in kd pre-order, state_validity(q) -> id,
+    # edges(from[n,2], to[n,2]) -> ids[n], add_vertex(q, id)
+    HOOK_TYPES = (C.CFUNCTYPE(i64, vp, C.POINTER(f64), u64, C.POINTER(u64), u64, u64),
+                  C.CFUNCTYPE(i64, vp, C.POINTER(f64), f64, C.POINTER(i64), i64),
+                  C.CFUNCTYPE(i64, vp, C.POINTER(f64)),
+                  C.CFUNCTYPE(None, vp, C.POINTER(f64), C.POINTER(f64), i64, C.POINTER(i64)),
+                  C.CFUNCTYPE(None, vp, C.POINTER(f64), u64))
+
+    def set_hooks(self, backend):
+        def nearest(_u, q, world, reach, n_nodes, words):
+            rw = np.ctypeslib.as_array(reach, shape=(n_nodes, words)).copy()
+            return int(backend.nearest_filtered([q[0], q[1]], int(world), rw))
+
+        def radius(_u, q, r, out, cap):
+            ids = backend.radius([q[0], q[1]], float(r))
+            assert len(ids) <= cap
+            for k, v in enumerate(ids):
+                out[k] = int(v)
+            return len(ids)
+
+        def state(_u, q):
+            return int(backend.state_validity([q[0], q[1]]))
+
+        def edges(_u, fr, to, n, out):
+            f = np.ctypeslib.as_array(fr, shape=(n, 2)).copy()
+            t = np.ctypeslib.as_array(to, shape=(n, 2)).copy()
+            for k, v in enumerate(backend.edges(f, t)):
+                out[k] = int(v)
+
+        def add_vertex(_u, q, node_id):
+            backend.add_vertex([q[0], q[1]], int(node_id))
+        self._hooks = [T(f) for T, f in zip(self.HOOK_TYPES, (nearest, radius, state, edges, add_vertex))]   # keep them alive
+        lib().orc_pto_set_hooks(self.h, *(C.cast(h, vp) for h in self._hooks))
 
     def n_it(self):
         return lib().orc_pto_n_it(self.h)

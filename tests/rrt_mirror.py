@@ -152,3 +152,45 @@ def grow_tree(backend, samples, start, goal, max_step, search_radius, n_iter_min
         if goal.goal(new_state) is not None:
             finals.append(new_id)
     return np.asarray(states), np.asarray(parent), np.asarray(dist), finals
+
+
+class ProductPTOBackend:
+    """the five per-query answers PTO::grow_graph needs (oracle/pyoracle.py: PTO.set_hooks), from libporrt_b200"""
+
+    def __init__(self, pmap):
+        import po_rrt_b200 as P
+        self.P, self.map, self.ctx = P, pmap, pmap.ctx
+        self.states, self.tree, self.rank = [], None, None
+
+    def _sync(self):
+        if self.tree is None:
+            self.tree = self.P.KdTree(self.ctx, np.asarray(self.states, np.float64))
+            self.rank = None
+
+    def add_vertex(self, q, node_id):
+        assert node_id == len(self.states)
+        self.states.append(list(q))
+        self.tree = None
+
+    def nearest_filtered(self, q, world, reach_words):      # pto.rs:74-77: 1-NN among nodes reachable in `world`
+        self._sync()
+        nid, _, ties = self.tree.nearest_neighbor([q], reach_mask=reach_words[:, 0].copy(), world=[world])
+        if nid[0] < 0:
+            return 0                                         # nothing passes the filter: the root (nearest_neighbor.rs:89)
+        assert ties[0] == 1, "tie in filtered 1-NN"
+        return int(nid[0])
+
+    def radius(self, q, r):
+        self._sync()
+        _, ids = self.tree.nearest_neighbors([q], r)
+        if len(ids) > 1:
+            if self.rank is None:
+                self.rank = self.tree.preorder_rank()
+            ids = ids[np.argsort(self.rank[ids], kind="stable")]
+        return [int(i) for i in ids]
+
+    def state_validity(self, q):
+        return int(self.map.state_validity([q])[0])
+
+    def edges(self, frm, to):
+        return [int(v) for v in self.map.transition_validator(frm, to)]

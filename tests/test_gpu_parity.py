@@ -961,3 +961,26 @@ def test_rrt_star_through_per_query_wrappers(ctx):
     np.testing.assert_array_equal(got[1], want[1])      # parents after choose-parent and rewiring
     np.testing.assert_array_equal(got[2], want[2])      # dist_from_root, bit-exact
     assert got[3] == want[3] and len(want[3]) > 0 and len(want[0]) > 600
+
+
+def test_pto_growth_through_per_query_wrappers(ctx):
+    """PTO::grow_graph (pto.rs:55-139; configs 2-4 grow their roadmap with it) is sequential and stays on the host.  The oracle's
+    restatement runs twice: on its own functions, and with every per-query answer -- 1-NN filtered by the reachability bit of the
+    sampled world, radius search in kd order, state validity ids, the candidate edges' validity ids -- coming from the C ABI.
+    Door map: validity ids differ per zone, so reachability (and with it the filter) really depends on them."""
+    import rrt_mirror as R
+    occ, zones = util.planning_door_map(200)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    goal = O.SquareGoal([((0.8, 0.8), [1, 1, 1, 1])], 0.05)
+    ref = O.PTO(omap, util.LOW, util.UP, seed=0)
+    assert ref.grow_graph((-0.8, -0.8), goal, 0.05, 5.0, 700, 100000) == 0
+    pto = O.PTO(omap, util.LOW, util.UP, seed=0)
+    pto.set_hooks(R.ProductPTOBackend(pmap))
+    assert pto.grow_graph((-0.8, -0.8), goal, 0.05, 5.0, 700, 100000) == 0
+    assert pto.n_it() == ref.n_it()
+    for which in (0, 1):
+        for a, b in zip(pto.graph.export(which), ref.graph.export(which)):
+            np.testing.assert_array_equal(a, b)              # states, node validity ids, adjacency in insertion order, edge ids
+    fa, fb = pto.reach.finals(), ref.reach.finals()
+    assert list(fa[0]) == list(fb[0]) and np.array_equal(np.asarray(fa[1]), np.asarray(fb[1]))
+    assert len(np.unique(ref.graph.export(0)[1])) > 1        # several validity ids occur among the nodes

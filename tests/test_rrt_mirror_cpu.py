@@ -30,3 +30,49 @@ def test_rrt_star_tree_invariants():
     # determinism: same stream, same tree
     st2, par2, dist2, fin2 = R.grow_tree(R.OracleBackend(omap, start), samples, start, goal, 0.1, 2.0, 500, 1500)
     assert np.array_equal(st, st2) and np.array_equal(par, par2) and np.array_equal(dist, dist2) and fin == fin2
+
+
+def test_pto_growth_hooks_plumbing():
+    """PTO.set_hooks (the per-query hook points of the oracle's PTO::grow_graph restatement): with the hooks answered by the
+    oracle's own primitives the growth must reproduce itself -- the GPU test plugs the product in at the same five points"""
+    import porrt_testutil as util
+    occ, zones = util.planning_door_map(200)
+    omap = O.GridMap(occ, zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
+    goal = O.SquareGoal([((0.8, 0.8), [1, 1, 1, 1])], 0.05)
+    ref = O.PTO(omap, [-1.0, -1.0], [1.0, 1.0], seed=0)
+    assert ref.grow_graph((-0.8, -0.8), goal, 0.05, 5.0, 400, 100000) == 0
+
+    class OwnAnswers:
+        def __init__(self):
+            self.tree, self.states = None, []
+
+        def add_vertex(self, q, node_id):
+            if self.tree is None:
+                self.tree = O.KdTree(q, 0)
+            else:
+                self.tree.add(q, node_id)
+            self.states.append(q)
+
+        def nearest_filtered(self, q, world, reach_words):
+            ok = [i for i in range(len(self.states)) if (int(reach_words[i, 0]) >> world) & 1]
+            if not ok:
+                return 0
+            st = np.asarray(self.states)
+            dx, dy = st[ok, 0] - q[0], st[ok, 1] - q[1]
+            return ok[int(np.argmin(np.sqrt(dx * dx + dy * dy)))]
+
+        def radius(self, q, r):
+            return [int(i) for i in self.tree.nearest_neighbors(q, r)]
+
+        def state_validity(self, q):
+            return int(omap.state_validity([q])[0])
+
+        def edges(self, frm, to):
+            return [int(v) for v in omap.edge_validity(frm, to)]
+
+    pto = O.PTO(omap, [-1.0, -1.0], [1.0, 1.0], seed=0)
+    pto.set_hooks(OwnAnswers())
+    assert pto.grow_graph((-0.8, -0.8), goal, 0.05, 5.0, 400, 100000) == 0
+    assert pto.n_it() == ref.n_it()
+    for a, b in zip(pto.graph.export(0), ref.graph.export(0)):
+        np.testing.assert_array_equal(a, b)
