@@ -177,7 +177,13 @@ class ProductPTOBackend:
         nid, _, ties = self.tree.nearest_neighbor([q], reach_mask=reach_words[:, 0].copy(), world=[world])
         if nid[0] < 0:
             return 0                                         # nothing passes the filter: the root (nearest_neighbor.rs:89)
-        assert ties[0] == 1, "tie in filtered 1-NN"
+        if ties[0] != 1:      # exact duplicates (repeated goal samples): the lowest id wins in the reference too, see ProductBackend.nearest
+            st = np.asarray(self.states)
+            ok = np.nonzero((reach_words[:, 0] >> np.uint64(world)) & np.uint64(1))[0]
+            dx, dy = q[0] - st[ok, 0], q[1] - st[ok, 1]
+            d2 = dx * dx + dy * dy
+            tied = ok[d2 == d2.min()]
+            assert (st[tied] == st[tied[0]]).all() and tied[0] == nid[0], "tie among distinct points"
         return int(nid[0])
 
     def radius(self, q, r):
