@@ -307,12 +307,13 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   const int64_t m = hi - lo;
   std::vector<std::thread> th;
   {
-    int nt = (int)std::min<int64_t>(std::max(2u, std::thread::hardware_concurrency()) / 2, 8);   // leave cores to the driver's copies
+    int nt = (int)std::min<int64_t>(std::max(2, (int)std::thread::hardware_concurrency() - 4), 16);   // leave cores to the driver's copies
     if (world > 1) nt = std::max(1, nt / world + 1);                                                // the box's cores are shared by all ranks
     if (m < 20000) nt = 1;
     for (int t = 0; t < nt; ++t)
       th.emplace_back([=]() {
-        for (int64_t k = lo + t; k < hi; k += nt) {
+        const int64_t per = (m + nt - 1) / nt, k0 = lo + t * per, k1 = std::min<int64_t>(hi, k0 + per);   // contiguous: no shared cache lines
+        for (int64_t k = k0; k < k1; ++k) {
           const int64_t kl = gb ? k - (int64_t)gb[k] : k;   // index inside the node's own roadmap
           radius[k] = kl == 0 ? -1.0 : heuristic_radius((size_t)kl + 1, ms_arr ? ms_arr[k] : max_step, sr_arr ? sr_arr[k] : search_radius, 2);
         }
@@ -351,7 +352,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[1], st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_k[1], 0));
   struct KdJob { int32_t rc = PORRT_OK; std::string err; int64_t launches = 0; std::thread th; bool joined = true; } kd;
-  {
+  auto start_kd = [&]() {
     porrt_ctx* c = ctx; int32_t* rank_out = d_rank; const uint32_t* roots = d_group_base; KdJob* job = &kd;
     kd.joined = false;
     kd.th = std::thread([c, n, rank_out, roots, job]() {
@@ -359,8 +360,13 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
       job->rc = kd_preorder_rank_dev(c, c->d_vxy.as<double>(), n, rank_out, roots, c->aux_stream, &job->err, &job->launches);
       if (job->rc == PORRT_OK && cudaStreamSynchronize(c->aux_stream) != cudaSuccess) { job->rc = PORRT_ERR_CUDA; job->err = "kd thread: stream sync failed"; }
     });
-  }
+  };
   struct KdJoiner { KdJob& j; ~KdJoiner() { if (!j.joined && j.th.joinable()) j.th.join(); } } kd_joiner{kd};   // early returns
+  // PORRT_PRM_KD_AFTER_BIN=1 starts the rank after the binning sort instead of next to it (bin 2.4 -> 0.7 ms at 1e6 nodes, but the
+  // waits move elsewhere: interleaved A/B runs gave 13.6 / 14.0 ms against 14.1 / 13.6 ms -- no difference beyond run-to-run noise)
+  const char* kd_env = getenv("PORRT_PRM_KD_AFTER_BIN");
+  const bool kd_after_bin = kd_env && atoi(kd_env) != 0;
+  if (!kd_after_bin) start_kd();
 
   // 1. bin vertices; cell = the smallest radius in use (the last one) so late queries touch 3x3 cells
   double r_last = n > 1 ? heuristic_radius((size_t)n, max_step, search_radius, 2) : -1.0;
@@ -375,6 +381,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   int32_t rc = nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell, nullptr, nullptr);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (kd_after_bin) start_kd();
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
 
   for (auto& x : th) if (x.joinable()) x.join();
