@@ -66,3 +66,12 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in text and "liboracle" not in text and "porrt_oracle" not in text, f
+
+
+def test_integration_doc_lists_every_symbol():
+    """INTEGRATION.md's Rust `extern "C"` block binds exactly what include/porrt_b200.h declares"""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    hdr = open(os.path.join(ROOT, "include", "porrt_b200.h")).read()
+    syms = sorted(set(re.findall(r"\b(porrt_[a-z0-9_]+)\s*\(", hdr)))
+    missing = [s for s in syms if ("pub fn %s(" % s) not in doc]
+    assert not missing, missing
