@@ -769,6 +769,18 @@ PORRT_API int32_t porrt_edge_validity(porrt_ctx* ctx, const double* from_xy, con
   return PORRT_OK;
 }
 
+// ids outside [0, V) must never reach the edge kernels (they index the vertex array): clamp them and remember that it happened
+__global__ void idx_check_kernel(int32_t* __restrict__ a, int32_t* __restrict__ b, int64_t n, int32_t V, int32_t* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t x = a[i], y = b[i];
+  if ((uint32_t)x >= (uint32_t)V || (uint32_t)y >= (uint32_t)V) {
+    *bad = 1;
+    if ((uint32_t)x >= (uint32_t)V) a[i] = 0;
+    if ((uint32_t)y >= (uint32_t)V) b[i] = 0;
+  }
+}
+
 // transition_validator(&PTONode, &PTONode) as the planners call it (pto.rs:105, prm.rs:93): both ends are NODES.  With the node
 // states resident on the device (porrt_vertices_set / porrt_prm_build), an edge is two 4-byte ids instead of four doubles: the
 // host->device stream shrinks from 32 to 8 bytes per edge, which is what bounds the end-to-end rate of porrt_edge_validity
@@ -795,6 +807,9 @@ PORRT_API int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* fro
   const int64_t n_chunks = (n + ch - 1) / ch;
   const double* d_xy = ctx->d_vxy.as<double>();
   const int64_t V = ctx->n_vertices;
+  CUDA_TRY(ctx, ctx->scratch[4].ensure(16));
+  int32_t* d_bad = ctx->scratch[4].as<int32_t>();
+  CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, 4, st));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[0], st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
   auto unstage = [&](int64_t c) {   // pageable outputs: copy chunk c out of its pinned slot
@@ -824,13 +839,12 @@ PORRT_API int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* fro
       memcpy(hf + ch, h_to, (size_t)cnt * 4);
       h_from = hf; h_to = hf + ch;
     }
-    for (int64_t k = 0; k < cnt; k += (cnt > 4096 ? cnt / 64 : 1)) {   // cheap sanity probe; the kernel itself does not bounds-check ids
-      if (h_from[k] < 0 || h_from[k] >= V || h_to[k] < 0 || h_to[k] >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_indexed: vertex id out of range");
-    }
     CUDA_TRY(ctx, cudaMemcpyAsync(d_from, h_from, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_to, h_to, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_in[s], 0));
+    idx_check_kernel<<<div_up(cnt, 256), 256, 0, st>>>(d_from, d_to, cnt, (int32_t)V, d_bad);
+    LAUNCH_CHECK(ctx);
     int32_t rc = launch_edges<true>(ctx, (const double2*)d_xy, (const double2*)d_xy, cnt, d_vid, out_mask ? d_mask : nullptr, d_from, d_to, st);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[s], st));
@@ -846,10 +860,13 @@ PORRT_API int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* fro
     if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(h_mask, d_mask, (size_t)cnt * 8 * words, cudaMemcpyDeviceToHost, ctx->copy_out));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
   }
+  int32_t bad = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   if (!pinned)
     for (int64_t c = n_chunks > slots ? n_chunks - slots : 0; c < n_chunks; ++c) unstage(c);
+  if (bad) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_indexed: vertex id out of range");
   return PORRT_OK;
 }
 
