@@ -561,6 +561,16 @@ PORRT_API int32_t porrt_prm_fetch(porrt_ctx* ctx, int64_t* out_row_ptr, int32_t*
   return PORRT_OK;
 }
 
+// the device kernels index by col[e] without checks: a malformed graph must be refused on the host
+static bool csr_ok(int64_t V, const int64_t* row_ptr, const int32_t* col) {
+  if (row_ptr[0] != 0) return false;
+  for (int64_t u = 0; u < V; ++u)
+    if (row_ptr[u + 1] < row_ptr[u]) return false;
+  for (int64_t e = 0; e < row_ptr[V]; ++e)
+    if (col[e] < 0 || col[e] >= V) return false;
+  return true;
+}
+
 // ================================================================================================ SSSP per world
 __global__ void edge_cost_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy,
                                  int64_t V, double* __restrict__ cost) {
@@ -622,6 +632,7 @@ PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* ro
   const int W = (int)(whi - wlo);
   const int64_t E = row_ptr[V];
   if (E > 0 && !col) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: null col");
+  if (!csr_ok(V, row_ptr, col)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: malformed CSR (row_ptr not monotone or edge target out of range)");
   // host prep: validity per (node, world) and the initial distances (inf, 0 at the finals)
   const double INF = std::numeric_limits<double>::infinity();
   std::vector<uint8_t> ok((size_t)V * W, 1);
@@ -1012,6 +1023,11 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   double t0 = now_ms(), t1, ph[4] = {0};
   const int64_t E = row_ptr[V];
   if (E > 0 && (!col || !edge_vid)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: null col/edge_vid");
+  if (!csr_ok(V, row_ptr, col)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: malformed CSR (row_ptr not monotone or edge target out of range)");
+  for (int64_t e = 0; e < E; ++e)
+    if (edge_vid[e] < 0 || edge_vid[e] >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: edge validity id out of range");
+  for (int64_t u = 0; u < V; ++u)
+    if (node_vid[u] < 0 || node_vid[u] >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: node validity id out of range");
   const int nw = n_worlds;
   // compute_compatibility (common.rs:266-276)
   std::vector<uint8_t> compat((size_t)B * n_validities);

@@ -984,3 +984,25 @@ def test_pto_growth_through_per_query_wrappers(ctx):
     fa, fb = pto.reach.finals(), ref.reach.finals()
     assert list(fa[0]) == list(fb[0]) and np.array_equal(np.asarray(fa[1]), np.asarray(fb[1]))
     assert len(np.unique(ref.graph.export(0)[1])) > 1        # several validity ids occur among the nodes
+
+
+def test_malformed_graphs_are_refused(ctx):
+    """edge targets / validity ids outside their range must come back as PORRT_ERR_INVALID_ARG, not reach a kernel"""
+    occ, zones = synth.shelf_map(200, n_zones=2)
+    _, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    xy = np.array([[0.0, 0.0], [0.1, 0.0], [0.2, 0.0]])
+    rp = np.array([0, 1, 2, 2], np.int64)
+    for bad_col in ([1, 3], [-1, 2]):
+        with pytest.raises(P.PorrtError) as e:
+            P.dijkstra_worlds(ctx, rp, np.array(bad_col, np.int32), xy, None, None, [2])
+        assert e.value.code == 1
+        with pytest.raises(P.PorrtError) as e:
+            P.BeliefGraph(ctx, rp, bad_col, xy, [P.NODE_ACTION] * 3, [0, 0, 0], [[1.0, 0.0]]).conditional_dijkstra([2])
+        assert e.value.code == 1
+    with pytest.raises(P.PorrtError) as e:      # row_ptr not monotone
+        P.dijkstra_worlds(ctx, np.array([0, 2, 1, 2], np.int64), np.array([1, 2], np.int32), xy, None, None, [2])
+    assert e.value.code == 1
+    with pytest.raises(P.PorrtError) as e:      # edge validity id beyond the table
+        P.plan_belief_space(pmap, rp, np.array([1, 2], np.int32), np.array([0, 7], np.int32), xy, np.zeros(3, np.int32), [0.5, 0.5], [2],
+                            P.words_from_bits([[1, 1]]))
+    assert e.value.code == 1
