@@ -61,6 +61,10 @@ int32_t porrt_ctx_synchronize(porrt_ctx* ctx);
  * *out_node (nullable) = that node, -1 if unknown / nothing changed.  Call it once per process before allocating host buffers. */
 int32_t porrt_ctx_bind_host_thread(porrt_ctx* ctx, int32_t* out_node);
 const char* porrt_last_error(porrt_ctx* ctx);
+/* options (tests / tuning); unknown options are refused */
+#define PORRT_OPT_FORCE_LARGE_MAP_PATH 1  /* value != 0: edge batches take the large-map kernel (class bytes in global memory, used
+                                             by itself for maps > ~14000^2 px) although the map would fit the shared-memory path */
+int32_t porrt_ctx_set_option(porrt_ctx* ctx, int32_t option, int64_t value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t porrt_ctx_launch_count(porrt_ctx* ctx);
 const char* porrt_version(void);
@@ -96,6 +100,20 @@ int32_t porrt_visibility(porrt_ctx* ctx, const double* xy, int64_t n, uint64_t* 
 int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* from_idx, const int32_t* to_idx, int64_t n,
                                     int32_t* out_validity_id, uint64_t* out_world_mask);
 
+/* Compact results: the validity id as ONE signed byte per edge (ids are < 128 -- n_validities <= 17 for the door domain, 1 for
+ * shelves -- and the negative codes are the same as in the int32 form); the per-world bitvec of an edge is
+ * world_validities[id] (porrt_map_world_validities), exactly what the reference's callers look up (pto.rs:111-118).
+ * Per edge 32 B in / 1 B out (coordinates), 8 B in / 1 B out (node ids), 4 B in / 1 B out (adjacency rows). */
+int32_t porrt_edge_validity_i8(porrt_ctx* ctx, const double* from_xy, const double* to_xy, int64_t n, int8_t* out_validity_id);
+int32_t porrt_edge_validity_indexed_i8(porrt_ctx* ctx, const int32_t* from_idx, const int32_t* to_idx, int64_t n,
+                                       int8_t* out_validity_id);
+/* The candidate edges of a roadmap as the planners hold them: an adjacency over the resident vertex set.  Row r of the CSR
+ * (row_ptr[n_rows + 1], col[row_ptr[n_rows]]) lists the nodes transition_validator is asked about for node r:
+ * row_is_to != 0: edge e of row r runs col[e] -> r  (prm.rs:91-96 / pto.rs:103-108: neighbour -> new node);
+ * row_is_to == 0: r -> col[e].  out_validity_id[e] in the order of col. */
+int32_t porrt_edge_validity_csr_i8(porrt_ctx* ctx, const int64_t* row_ptr, const int32_t* col, int64_t n_rows, int32_t row_is_to,
+                                   int8_t* out_validity_id);
+
 int32_t porrt_state_validity_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_validity_id_dev);
 int32_t porrt_edge_validity_dev(porrt_ctx* ctx, const double* from_xy_dev, const double* to_xy_dev, int64_t n,
                                 int32_t* out_validity_id_dev, uint64_t* out_world_mask_dev);
@@ -113,17 +131,18 @@ int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n);
 /* KdTree::nearest_neighbors[_filtered] (nearest_neighbor.rs:94-126), batched: all ids j with
  *   norm2(vertex_j, q_i) <= radius[i]   (inclusive, on the sqrt-ed f64 value)
  *   and j < prefix_limit[i]             (if prefix_limit != NULL: the tree as it was before vertex prefix_limit[i] was added)
- *   and bit world[i] of reach_mask[j]   (if reach_mask != NULL: the validator closure of pto.rs:74-77)
+ *   and bit world[i] of vertex j's reachability mask reach_mask[j * reach_words ..]   (if reach_mask != NULL: the validator
+ *       closure of pto.rs:74-77; BitVec Lsb0 layout, reach_words = ceil(n_worlds / 64); a world >= 64 * reach_words passes nothing)
  * Result: CSR -- out_offsets[m+1], out_ids ascending per query (the SET contract; kd pre-order is restored by
  * porrt_kd_preorder_rank + porrt_segments_sort_by_key).  If the hits exceed cap: PORRT_ERR_CAPACITY, *out_total = needed. */
 int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const double* radius, int64_t m,
-                           const uint32_t* prefix_limit, const uint64_t* reach_mask, const uint32_t* world,
+                           const uint32_t* prefix_limit, const uint64_t* reach_mask, int32_t reach_words, const uint32_t* world,
                            int64_t* out_offsets, int32_t* out_ids, int64_t cap, int64_t* out_total);
 /* KdTree::nearest_neighbor[_filtered] (nearest_neighbor.rs:48-92), batched: argmin over (d2, id); out_id = -1 when
  * nothing passes the filter (the reference then returns the root).  out_dist = norm2 of the winner.
  * out_ties (nullable): number of vertices at exactly the winning squared distance (>1 = tie the kd order decides). */
-int32_t porrt_nearest(porrt_ctx* ctx, const double* q_xy, int64_t m, const uint64_t* reach_mask, const uint32_t* world,
-                      int32_t* out_id, double* out_dist, int32_t* out_ties);
+int32_t porrt_nearest(porrt_ctx* ctx, const double* q_xy, int64_t m, const uint64_t* reach_mask, int32_t reach_words,
+                      const uint32_t* world, int32_t* out_id, double* out_dist, int32_t* out_ties);
 /* k nearest (no reference counterpart; BASELINE metric "kNN queries/sec"): ids/dists ascending by (d2, id), -1/inf padded */
 int32_t porrt_knn(porrt_ctx* ctx, const double* q_xy, int64_t m, int32_t k, int32_t* out_ids, double* out_dist);
 
@@ -242,6 +261,57 @@ int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy, const in
 /* reachable_belief_states (map_io.rs:515-546 / map_shelves_io.rs:490-520): host-side closure over the uploaded map's
  * zones; out[cap * n_worlds]; *out_B = count (PORRT_ERR_CAPACITY if > cap). */
 int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B);
+
+/* ------------------------------------------------------------------ QMDP policy (qmdp_policy_extractor.rs)
+ * QMdpPolicyExtractor::react_qmdp (:38-49) with get_common_path (:65-87), get_best_expected_child (:90-108), get_path (:51-62) and
+ * get_best_child (:110-123), walking the cost table of porrt_sssp_worlds (cost_to_goals[w * V + v], plan_qmdp's result) over the
+ * children CSR.  start_node = kdtree.nearest_neighbor(start).id (porrt_nearest).  Host walk; ctx may be NULL.
+ * out_path_ptr[n_worlds + 1], out_path_nodes: paths[w] as node ids = the common path (its length in *out_n_common) followed by
+ * world w's own path.  PORRT_ERR_PANIC: belief_len != n_worlds (the reference's Err(..).unwrap(), :42), or a walk that would
+ * never end in the reference (no finite child); PORRT_ERR_CAPACITY with *out_total when cap is too small. */
+int32_t porrt_qmdp_react(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy, int32_t n_worlds,
+                         const double* cost_to_goals, int64_t start_node, const double* belief, int32_t belief_len,
+                         double common_horizon, int64_t* out_path_ptr, int32_t* out_path_nodes, int64_t cap, int64_t* out_total,
+                         int64_t* out_n_common);
+
+/* ------------------------------------------------------------------ host-side rows (sequential by nature; no device work)
+ * What the reference's sequential callers (PTO::grow_graph pto.rs:55-149, RRT::grow_tree rrt.rs:102-181) need around the batched
+ * calls above, bit-faithful to the crate, so that the whole path sits behind one ABI. */
+/* heuristic_radius (common.rs:357-369): min(search_radius * (ln n / n)^(1/dim), max_step), libm on the host */
+int32_t porrt_heuristic_radius(int64_t n_nodes, double max_step, double search_radius, int32_t dim, double* out_radius);
+/* steer (common.rs:215-225), batched: to_xy[k] is pulled towards from_xy[k] when norm1(from, to) > max_step (in place) */
+int32_t porrt_steer(const double* from_xy, double* to_xy, int64_t n, double max_step);
+
+/* ContinuousSampler / DiscreteSampler (sample_space.rs:6-60): one Pcg64::seed_from_u64(seed) stream per handle (the reference
+ * seeds with 0; PTO keeps one continuous and one discrete sampler, two independent streams with the same seed, pto.rs:141-149) */
+typedef struct porrt_sampler porrt_sampler;
+int32_t porrt_sampler_create(uint64_t seed, porrt_sampler** out_sampler);
+int32_t porrt_sampler_destroy(porrt_sampler* s);
+/* n x ContinuousSampler::sample(): out[n * dim], one gen_range(low[d]..up[d]) per dimension in dimension order */
+int32_t porrt_sampler_continuous(porrt_sampler* s, const double* low, const double* up, int32_t dim, int64_t n, double* out);
+/* n x DiscreteSampler::sample(n_choices) */
+int32_t porrt_sampler_discrete(porrt_sampler* s, uint64_t n_choices, int64_t n, uint64_t* out);
+
+/* SquareGoal (common.rs:304-350).  goal(): out_goal[k] = index of the first goal with norm1(state_k, goal) < max_dist, -1 = None
+ * (the caller owns the goals' world masks).  goal_example(): out_xy[2 * w] = the goal valid in world w ((0, 0) if none);
+ * goal_masks[n_goals * ceil(n_worlds / 64)]; PORRT_ERR_PANIC when masks overlap (assert, :320). */
+int32_t porrt_square_goal(const double* goals_xy, int32_t n_goals, double max_dist, const double* xy, int64_t n, int32_t* out_goal);
+int32_t porrt_square_goal_examples(const double* goals_xy, const uint64_t* goal_masks, int32_t n_goals, int32_t n_worlds, double* out_xy);
+
+/* Reachability (pto_reachability.rs:6-102): per-node world masks propagated at edge insertion; masks are ceil(n_worlds / 64) u64
+ * words (BitVec Lsb0).  porrt_reach_create = new() + set_root(root_validity): node 0. */
+typedef struct porrt_reach porrt_reach;
+int32_t porrt_reach_create(int32_t n_worlds, const uint64_t* root_validity, porrt_reach** out_reach);
+int32_t porrt_reach_destroy(porrt_reach* r);
+int32_t porrt_reach_add_node(porrt_reach* r, const uint64_t* validity);                              /* :35-38 */
+int32_t porrt_reach_add_final_node(porrt_reach* r, int64_t id, const uint64_t* finality);            /* :40-45 */
+int32_t porrt_reach_add_edge(porrt_reach* r, int64_t from, int64_t to, const uint64_t* edge_validity); /* :47-57 */
+int32_t porrt_reach_count(porrt_reach* r, int64_t* out_nodes, int32_t* out_words);
+/* reachability(id) (:59-61) of nodes first .. first + n - 1: out[n * words], the reach_mask of porrt_nearest / porrt_radius_query */
+int32_t porrt_reach_masks(porrt_reach* r, int64_t first, int64_t n, uint64_t* out);
+int32_t porrt_reach_final_nodes_for_world(porrt_reach* r, int32_t world, int64_t* out_ids, int64_t cap, int64_t* out_n); /* :63-68 */
+int32_t porrt_reach_finals(porrt_reach* r, int64_t* out_ids, uint64_t* out_masks, int64_t cap, int64_t* out_n);          /* :82-84 */
+int32_t porrt_reach_is_final_set_complete(porrt_reach* r, int32_t* out_complete);                                       /* :86-95 */
 
 /* ------------------------------------------------------------------ multi-GPU
  * The reference is single-threaded and has no distributed code; what shards are its independent units (edge checks,

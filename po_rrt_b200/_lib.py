@@ -31,6 +31,10 @@ SIGNATURES = {
     "porrt_edge_validity": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_visibility": (i32, [vp, vp, i64, vp, vp]),
     "porrt_edge_validity_indexed": (i32, [vp, vp, vp, i64, vp, vp]),
+    "porrt_edge_validity_i8": (i32, [vp, vp, vp, i64, vp]),
+    "porrt_edge_validity_indexed_i8": (i32, [vp, vp, vp, i64, vp]),
+    "porrt_edge_validity_csr_i8": (i32, [vp, vp, vp, i64, i32, vp]),
+    "porrt_ctx_set_option": (i32, [vp, i32, i64]),
     "porrt_state_validity_dev": (i32, [vp, vp, i64, vp]),
     "porrt_edge_validity_dev": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_visibility_dev": (i32, [vp, vp, i64, vp, vp]),
@@ -40,8 +44,8 @@ SIGNATURES = {
     "porrt_vertices_set": (i32, [vp, vp, i64, f64]),
     "porrt_vertices_set_dev": (i32, [vp, vp, i64, f64, vp, vp]),
     "porrt_vertices_count": (i32, [vp, pp(i64)]),
-    "porrt_radius_query": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, pp(i64)]),
-    "porrt_nearest": (i32, [vp, vp, i64, vp, vp, vp, vp, vp]),
+    "porrt_radius_query": (i32, [vp, vp, vp, i64, vp, vp, i32, vp, vp, vp, i64, pp(i64)]),
+    "porrt_nearest": (i32, [vp, vp, i64, vp, i32, vp, vp, vp, vp]),
     "porrt_knn": (i32, [vp, vp, i64, i32, vp, vp]),
     "porrt_kd_preorder_rank": (i32, [vp, vp, i64, vp]),
     "porrt_prm_build": (i32, [vp, vp, i64, f64, f64, vp, vp, i64, pp(i64), vp]),
@@ -53,6 +57,25 @@ SIGNATURES = {
     "porrt_extract_policy_graph": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),
     "porrt_mmprm_plan": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, pp(i64), pp(i32), vp]),
     "porrt_mmprm_fetch_graph": (i32, [vp, vp, vp, i64, vp, vp]),
+    "porrt_qmdp_react": (i32, [vp, i64, vp, vp, vp, i32, vp, i64, vp, i32, f64, vp, vp, i64, pp(i64), pp(i64)]),
+    "porrt_heuristic_radius": (i32, [i64, f64, f64, i32, pp(f64)]),
+    "porrt_steer": (i32, [vp, vp, i64, f64]),
+    "porrt_sampler_create": (i32, [C.c_uint64, pp(vp)]),
+    "porrt_sampler_destroy": (i32, [vp]),
+    "porrt_sampler_continuous": (i32, [vp, vp, vp, i32, i64, vp]),
+    "porrt_sampler_discrete": (i32, [vp, C.c_uint64, i64, vp]),
+    "porrt_square_goal": (i32, [vp, i32, f64, vp, i64, vp]),
+    "porrt_square_goal_examples": (i32, [vp, vp, i32, i32, vp]),
+    "porrt_reach_create": (i32, [i32, vp, pp(vp)]),
+    "porrt_reach_destroy": (i32, [vp]),
+    "porrt_reach_add_node": (i32, [vp, vp]),
+    "porrt_reach_add_final_node": (i32, [vp, i64, vp]),
+    "porrt_reach_add_edge": (i32, [vp, i64, i64, vp]),
+    "porrt_reach_count": (i32, [vp, pp(i64), pp(i32)]),
+    "porrt_reach_masks": (i32, [vp, i64, i64, vp]),
+    "porrt_reach_final_nodes_for_world": (i32, [vp, i32, vp, i64, pp(i64)]),
+    "porrt_reach_finals": (i32, [vp, vp, vp, i64, pp(i64)]),
+    "porrt_reach_is_final_set_complete": (i32, [vp, pp(i32)]),
     "porrt_reachable_belief_states": (i32, [vp, vp, vp, i32, pp(i32)]),
     "porrt_comm_unique_id": (i32, [vp]),
     "porrt_comm_init": (i32, [vp, vp, i32, i32]),

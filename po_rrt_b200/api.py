@@ -20,6 +20,7 @@ INVALID, PANIC_OOB, PANIC_ZONE_UNWRAP, PANIC_MULTI_ZONE = -1, -2, -3, -4
 DOOR, SHELF = 0, 1
 NODE_UNKNOWN, NODE_ACTION, NODE_OBSERVATION = 0, 1, 2
 ERR_CAPACITY = 4
+OPT_FORCE_LARGE_MAP_PATH = 1
 
 
 class PorrtError(RuntimeError):
@@ -82,6 +83,9 @@ class Context:
 
     def launch_count(self):
         return self.lib.porrt_ctx_launch_count(self.h)
+
+    def set_option(self, option, value):
+        self.check(self.lib.porrt_ctx_set_option(self.h, int(option), int(value)))
 
     # -- multi-GPU: one process and one Context per GPU; see po_rrt_b200/shard.py:init_comm for the plumbing
     def comm_unique_id(self):
@@ -193,25 +197,43 @@ class _GridDomain:
         self.ctx.check(self.ctx.lib.porrt_state_validity(self.ctx.h, _p(xy), len(xy), _p(out)))
         return out
 
-    def transition_validator(self, from_xy, to_xy, want_masks=False):
+    def transition_validator(self, from_xy, to_xy, want_masks=False, compact=False, vid_out=None):
+        """compact=True: one signed byte per edge (porrt_edge_validity_i8), no masks"""
         self._need()
         f, t = _f64(from_xy, 2), _f64(to_xy, 2)
         assert len(f) == len(t)
-        out = np.empty(len(f), np.int32)
+        if compact:
+            out = np.empty(len(f), np.int8) if vid_out is None else vid_out
+            self.ctx.check(self.ctx.lib.porrt_edge_validity_i8(self.ctx.h, _p(f), _p(t), len(f), _p(out)))
+            return out
+        out = np.empty(len(f), np.int32) if vid_out is None else vid_out
         masks = np.empty((len(f), self.mask_words), np.uint64) if want_masks else None
         self.ctx.check(self.ctx.lib.porrt_edge_validity(self.ctx.h, _p(f), _p(t), len(f), _p(out), _p(masks)))
         return (out, masks) if want_masks else out
 
-    def transition_validator_nodes(self, from_idx, to_idx, want_masks=False, vid_out=None, mask_out=None):
+    def transition_validator_nodes(self, from_idx, to_idx, want_masks=False, vid_out=None, mask_out=None, compact=False):
         """transition_validator between nodes of the uploaded vertex set (KdTree.set / porrt_vertices_set), by id"""
         self._need()
         fi, ti = np.ascontiguousarray(from_idx, np.int32), np.ascontiguousarray(to_idx, np.int32)
         n = len(fi)
+        if compact:
+            vid = np.empty(n, np.int8) if vid_out is None else vid_out
+            self.ctx.check(self.ctx.lib.porrt_edge_validity_indexed_i8(self.ctx.h, _p(fi), _p(ti), n, _p(vid)))
+            return vid
         vid = np.empty(n, np.int32) if vid_out is None else vid_out
         masks = (np.empty((n, self.mask_words), np.uint64) if mask_out is None else mask_out) if want_masks else None
         c = self.ctx
         c.check(c.lib.porrt_edge_validity_indexed(c.h, _p(fi), _p(ti), n, _p(vid), _p(masks)))
         return (vid, masks) if want_masks else vid
+
+    def transition_validator_adjacency(self, row_ptr, col, row_is_to=True, vid_out=None):
+        """transition_validator for every entry of an adjacency over the uploaded vertex set: entry e of row r is the edge
+        col[e] -> r (row_is_to, the planners' neighbour -> new node) or r -> col[e]; one signed byte per entry"""
+        self._need()
+        rp, cl = np.ascontiguousarray(row_ptr, np.int64), np.ascontiguousarray(col, np.int32)
+        vid = np.empty(len(cl), np.int8) if vid_out is None else vid_out
+        self.ctx.check(self.ctx.lib.porrt_edge_validity_csr_i8(self.ctx.h, _p(rp), _p(cl), len(rp) - 1, 1 if row_is_to else 0, _p(vid)))
+        return vid
 
     def is_transition_valid(self, from_xy, to_xy, compat_row):
         """PTOPolicyRefiner::is_transition_valid (pto_policy_refiner.rs:395-423), batched -> (valid u8, status i32)"""
@@ -299,14 +321,15 @@ class KdTree:
         m = len(q)
         r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float64), (m,)))
         pl = None if prefix_limit is None else np.ascontiguousarray(prefix_limit, np.uint32)
-        rm = None if reach_mask is None else np.ascontiguousarray(reach_mask, np.uint64)
+        rm = None if reach_mask is None else np.ascontiguousarray(reach_mask, np.uint64).reshape(self.n, -1)
+        rw = 1 if rm is None else rm.shape[1]
         w = None if world is None else np.ascontiguousarray(world, np.uint32)
         offs = np.empty(m + 1, np.int64)
         cap = cap if cap is not None else max(1024, 64 * m)
         total = C.c_int64()
         while True:
             ids = ids_out if (ids_out is not None and len(ids_out) >= cap) else np.empty(cap, np.int32)
-            rc = self.ctx.lib.porrt_radius_query(self.ctx.h, _p(q), _p(r), m, _p(pl), _p(rm), _p(w), _p(offs), _p(ids), cap,
+            rc = self.ctx.lib.porrt_radius_query(self.ctx.h, _p(q), _p(r), m, _p(pl), _p(rm), rw, _p(w), _p(offs), _p(ids), cap,
                                                  C.byref(total))
             if rc == ERR_CAPACITY:
                 cap = total.value
@@ -318,10 +341,11 @@ class KdTree:
         """-> (id, dist, ties); id = -1 when the filter rejects everything (the reference returns the root)"""
         q = _f64(q, 2)
         m = len(q)
-        rm = None if reach_mask is None else np.ascontiguousarray(reach_mask, np.uint64)
+        rm = None if reach_mask is None else np.ascontiguousarray(reach_mask, np.uint64).reshape(self.n, -1)
+        rw = 1 if rm is None else rm.shape[1]
         w = None if world is None else np.ascontiguousarray(world, np.uint32)
         ids, dist, ties = np.empty(m, np.int32), np.empty(m), np.empty(m, np.int32)
-        self.ctx.check(self.ctx.lib.porrt_nearest(self.ctx.h, _p(q), m, _p(rm), _p(w), _p(ids), _p(dist), _p(ties)))
+        self.ctx.check(self.ctx.lib.porrt_nearest(self.ctx.h, _p(q), m, _p(rm), rw, _p(w), _p(ids), _p(dist), _p(ties)))
         return ids, dist, ties
 
     def knn(self, q, k, ids_out=None, dist_out=None):
@@ -542,3 +566,188 @@ def words_from_bits(bits):
     for w in range(nw):
         out[:, w // 64] |= bits[:, w].astype(np.uint64) << np.uint64(w % 64)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- host-side rows (no device work)
+def heuristic_radius(n_nodes, max_step, search_radius, dim=2):
+    """common.rs:357-369"""
+    out = C.c_double()
+    rc = _lib.load().porrt_heuristic_radius(int(n_nodes), float(max_step), float(search_radius), int(dim), C.byref(out))
+    if rc:
+        raise PorrtError(rc, "porrt_heuristic_radius")
+    return out.value
+
+
+def steer(from_xy, to_xy, max_step):
+    """common.rs:215-225, batched; returns the steered copies of to_xy"""
+    f, t = _f64(from_xy, 2), _f64(to_xy, 2).copy()
+    rc = _lib.load().porrt_steer(_p(f), _p(t), len(f), float(max_step))
+    if rc:
+        raise PorrtError(rc, "porrt_steer")
+    return t
+
+
+class Sampler:
+    """one Pcg64::seed_from_u64(seed) stream: ContinuousSampler::sample / DiscreteSampler::sample (sample_space.rs)"""
+
+    def __init__(self, seed=0):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        rc = self.lib.porrt_sampler_create(int(seed), C.byref(self.h))
+        if rc:
+            raise PorrtError(rc, "porrt_sampler_create")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.porrt_sampler_destroy(self.h)
+            self.h = None
+
+    def sample_states(self, low, up, n):
+        low, up = _f64(low), _f64(up)
+        out = np.empty((n, len(low)))
+        rc = self.lib.porrt_sampler_continuous(self.h, _p(low), _p(up), len(low), n, _p(out))
+        if rc:
+            raise PorrtError(rc, "porrt_sampler_continuous")
+        return out
+
+    def sample_discrete(self, n_choices, n):
+        out = np.empty(n, np.uint64)
+        rc = self.lib.porrt_sampler_discrete(self.h, int(n_choices), n, _p(out))
+        if rc:
+            raise PorrtError(rc, "porrt_sampler_discrete")
+        return out
+
+
+class SquareGoal:
+    """common.rs:304-350: goals [(state, world mask bits)], max_dist"""
+
+    def __init__(self, goal_to_validity, max_dist):
+        self.lib = _lib.load()
+        self.goals = _f64([g for g, _ in goal_to_validity], 2)
+        self.bits = np.asarray([m for _, m in goal_to_validity], np.uint8)
+        self.masks = words_from_bits(self.bits)
+        self.max_dist = float(max_dist)
+        self.n_worlds = self.bits.shape[1]
+        self.world_to_goal = np.empty((self.n_worlds, 2))
+        rc = self.lib.porrt_square_goal_examples(_p(self.goals), _p(self.masks), len(self.goals), self.n_worlds, _p(self.world_to_goal))
+        if rc:
+            raise PorrtError(rc, "validities shouldn't overlap (common.rs:320)")
+
+    def goal_index(self, xy):
+        xy = _f64(xy, 2)
+        out = np.empty(len(xy), np.int32)
+        rc = self.lib.porrt_square_goal(_p(self.goals), len(self.goals), self.max_dist, _p(xy), len(xy), _p(out))
+        if rc:
+            raise PorrtError(rc, "porrt_square_goal")
+        return out
+
+    def goal(self, state):
+        """Option<WorldMask> as a bit list / None"""
+        g = int(self.goal_index([state])[0])
+        return None if g < 0 else [int(b) for b in self.bits[g]]
+
+    def goal_example(self, world):
+        return self.world_to_goal[world].copy()
+
+
+class Reachability:
+    """pto_reachability.rs; masks as 0/1 lists of length n_worlds"""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.h = None
+        self.n_worlds = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.porrt_reach_destroy(self.h)
+            self.h = None
+
+    def _w(self, bits):
+        assert len(bits) == self.n_worlds
+        return words_from_bits([bits])[0].copy()
+
+    def _ck(self, rc, what):
+        if rc:
+            raise PorrtError(rc, what)
+
+    def set_root(self, validity):
+        self.n_worlds = len(validity)
+        self.h = C.c_void_p()
+        self._ck(self.lib.porrt_reach_create(self.n_worlds, _p(self._w(validity)), C.byref(self.h)), "porrt_reach_create")
+
+    def add_node(self, validity):
+        self._ck(self.lib.porrt_reach_add_node(self.h, _p(self._w(validity))), "porrt_reach_add_node")
+
+    def add_final_node(self, id, finality):
+        self._ck(self.lib.porrt_reach_add_final_node(self.h, int(id), _p(self._w(finality))), "porrt_reach_add_final_node")
+
+    def add_edge(self, a, b, edge_validity):
+        self._ck(self.lib.porrt_reach_add_edge(self.h, int(a), int(b), _p(self._w(edge_validity))), "porrt_reach_add_edge")
+
+    def n_nodes(self):
+        n = C.c_int64()
+        self._ck(self.lib.porrt_reach_count(self.h, C.byref(n), None), "porrt_reach_count")
+        return n.value
+
+    def masks_words(self, first=0, n=None):
+        n = self.n_nodes() - first if n is None else n
+        out = np.empty((n, (self.n_worlds + 63) // 64), np.uint64)
+        self._ck(self.lib.porrt_reach_masks(self.h, first, n, _p(out)), "porrt_reach_masks")
+        return out
+
+    def reachability(self, id):
+        w = self.masks_words(id, 1)[0]
+        return [int((w[k // 64] >> np.uint64(k % 64)) & np.uint64(1)) for k in range(self.n_worlds)]
+
+    def get_final_nodes_for_world(self, world):
+        cap = 16
+        while True:
+            out, n = np.empty(cap, np.int64), C.c_int64()
+            rc = self.lib.porrt_reach_final_nodes_for_world(self.h, int(world), _p(out), cap, C.byref(n))
+            if rc == ERR_CAPACITY:
+                cap = n.value
+                continue
+            self._ck(rc, "porrt_reach_final_nodes_for_world")
+            return [int(x) for x in out[:n.value]]
+
+    def finals(self):
+        n = C.c_int64()
+        self.lib.porrt_reach_finals(self.h, None, None, 0, C.byref(n))
+        ids = np.empty(n.value, np.int64)
+        masks = np.empty((n.value, (self.n_worlds + 63) // 64), np.uint64)
+        self._ck(self.lib.porrt_reach_finals(self.h, _p(ids), _p(masks), n.value, C.byref(n)), "porrt_reach_finals")
+        return ids, masks
+
+    def is_final_set_complete(self):
+        if self.h is None:
+            return False
+        out = C.c_int32()
+        self._ck(self.lib.porrt_reach_is_final_set_complete(self.h, C.byref(out)), "porrt_reach_is_final_set_complete")
+        return bool(out.value)
+
+
+def react_qmdp(ctx, row_ptr, col, xy, cost_to_goals, start_node, belief, common_horizon):
+    """QMdpPolicyExtractor::react_qmdp (qmdp_policy_extractor.rs:38-123) over plan_qmdp's cost table -> (paths as lists of
+    node ids, one per world; length of the common prefix).  ctx may be None (host walk)."""
+    lib = _lib.load()
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    col = np.ascontiguousarray(col, np.int32)
+    xy = _f64(xy, 2)
+    cost = np.ascontiguousarray(cost_to_goals, np.float64)
+    W, V = cost.shape
+    b = _f64(belief)
+    ptr = np.empty(W + 1, np.int64)
+    total, n_common = C.c_int64(), C.c_int64()
+    cap = 1024
+    h = ctx.h if ctx is not None else None
+    while True:
+        nodes = np.empty(cap, np.int32)
+        rc = lib.porrt_qmdp_react(h, V, _p(row_ptr), _p(col), _p(xy), W, _p(cost), int(start_node), _p(b), len(b), float(common_horizon),
+                                  _p(ptr), _p(nodes), cap, C.byref(total), C.byref(n_common))
+        if rc == ERR_CAPACITY:
+            cap = total.value
+            continue
+        if rc:
+            raise PorrtError(rc, (lib.porrt_last_error(h) or b"").decode() if h else "porrt_qmdp_react")
+        return [nodes[ptr[w]:ptr[w + 1]].copy() for w in range(W)], n_common.value

@@ -47,8 +47,8 @@ struct PinBuf {  // grow-only pinned host staging
 // Device-side description of an uploaded map (passed by value to kernels).
 struct MapDev {
   const uint8_t* grid;  // fused code grid, tiled (see map.cu: tile_addr)
-  const uint8_t* coarse[3]; // one class byte per 8x8 / 16x16 / 32x32 block, row-major (map.cu: C_* flags)
-  int32_t cw[3];            // their row pitches
+  const uint8_t* coarse;    // large-map path (map.cu): one class byte per 16 x 16 block, row-major (C_* flags)
+  int32_t coarse_cw;        // its row pitch
   // edge3.cu: 2-bit class per 16 x 16 block (16 per word, row-major; staged in shared memory by the kernel) and the
   // blocking-pixel bitmaps of the blocks, four orientations x 32 bytes per block
   const uint32_t* plane;
@@ -89,11 +89,8 @@ struct porrt_ctx {
   std::vector<uint64_t> validities;     // [n_validities * mask_words]
   std::vector<double> zone_pos;         // [2 * n_zones]
   std::vector<uint64_t> zone_world_masks;  // DOOR: zones_to_worlds [n_zones * mask_words]
-  DevBuf d_grid, d_coarse[3], d_validities, d_zone_pos, d_plane, d_bits, d_ticket;
-  int edge_variant = 0;  // 0: edge3.cu (class plane in shared memory + block bitmaps, flattened strips) -- the product path;
-                         // 9: edge4.cu (same data, lane per edge over length-sorted groups; measured equal, kept for A/B);
-                         // 1: byte-grid warp walk; 2..7: class bytes in global memory + flattened strips (map.cu v2, also the
-                         // fallback for maps whose class plane does not fit in shared memory)
+  DevBuf d_grid, d_coarse, d_validities, d_zone_pos, d_plane, d_bits;
+  bool force_large_map_path = false;   // PORRT_OPT_FORCE_LARGE_MAP_PATH (tests): run map.cu's kernel although edge3.cu's would fit
   // host copies of the raw images are NOT kept: the product never walks pixels on the CPU.
 
   // ---- vertices / cell grid (nn.cu)
@@ -103,6 +100,7 @@ struct porrt_ctx {
   DevBuf d_vxy_sorted, d_vid_sorted, d_cell_start, d_vxy, d_vcell;
   DevBuf nn_tmp[3];      // nn_tile.cu: query bins
   int32_t nn_fb_n = 0;   // queries of the last tile pass left to the thread-per-query kernels
+  int32_t reach_words = 1;  // u64 words per vertex of the reachability filter of the running NN call
 
   // ---- last belief VI result (graph.cu), kept for porrt_extract_policy
   struct BeliefState_ {
@@ -122,6 +120,7 @@ struct porrt_ctx {
   int64_t prm_n = 0, prm_edges = 0;
   const int64_t* prm_row_ptr = nullptr;
   const int32_t* prm_col = nullptr;
+  DevBuf d_prm_row, d_prm_col;         // dedicated: the retained CSR must survive later calls that reuse the shared scratch
 
   // ---- last multi-modal PRM result (mmprm.cu): the explicit belief graph, kept for porrt_mmprm_fetch_graph
   struct MmPrm_ {
@@ -185,19 +184,22 @@ static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
 void comm_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi);
 int32_t comm_all_gatherv_dev(porrt_ctx* ctx, const void* send_dev, void* recv_dev, const int64_t* offsets /* host [world+1] */, cudaStream_t st);
 // map.cu
+struct EdgeOut {   // where an edge batch's results go (device pointers): vid XOR vid8, mask optional
+  int32_t* vid = nullptr;
+  int8_t* vid8 = nullptr;
+  uint64_t* mask = nullptr;
+};
 int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
                               int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st);
+int32_t map_edge_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, const int32_t* from_idx_dev,
+                        const int32_t* to_idx_dev, int64_t n, const EdgeOut& out, cudaStream_t st);
 int32_t map_edge_validity_indexed_dev(porrt_ctx* ctx, const double* xy_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev,
                                       int64_t n, int32_t* out_vid_dev, cudaStream_t st);
 // edge3.cu
 int32_t edge3_build(porrt_ctx* ctx, cudaStream_t st);
 bool edge3_usable(const porrt_ctx* ctx);
-int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
-                     uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st);
-// edge4.cu
-bool edge4_usable(const porrt_ctx* ctx);
-int32_t edge4_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
-                     uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st);
+int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, const EdgeOut& out,
+                     const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st);
 // nn_tile.cu (TMA-staged vertex tiles); GridDev is defined in nn_dev.cuh
 struct GridDev;
 bool nn_tile_usable(const porrt_ctx* ctx, int64_t m);

@@ -33,7 +33,7 @@ PORRT_API int32_t porrt_ctx_create(int32_t device, porrt_ctx** out_ctx) {
          cudaEventCreateWithFlags(&ctx->ev_k[s], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
   for (int s = 0; ok && s < 16; ++s) ok = cudaEventCreate(&ctx->ev_t[s]) == cudaSuccess;
-  if (!ok) { delete ctx; return PORRT_ERR_CUDA; }
+  if (!ok) { cudaGetLastError(); porrt_ctx_destroy(ctx); return PORRT_ERR_CUDA; }  // releases whatever was created so far
   ctx->stream = ctx->own_stream;
   *out_ctx = ctx;
   return PORRT_OK;
@@ -44,13 +44,13 @@ PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   porrt_comm_destroy(ctx);
-  ctx->d_grid.release(); for (DevBuf& b : ctx->d_coarse) b.release(); ctx->d_validities.release(); ctx->d_zone_pos.release();
-  ctx->d_plane.release(); ctx->d_bits.release(); ctx->d_ticket.release();
+  ctx->d_grid.release(); ctx->d_coarse.release(); ctx->d_validities.release(); ctx->d_zone_pos.release();
+  ctx->d_plane.release(); ctx->d_bits.release();
   ctx->d_vxy_sorted.release(); ctx->d_vid_sorted.release(); ctx->d_cell_start.release();
   ctx->d_vxy.release(); ctx->d_vcell.release();
   for (DevBuf& b : ctx->nn_tmp) b.release();
   for (DevBuf& b : ctx->scratch) b.release();
-  ctx->kd_buf.release();
+  ctx->kd_buf.release(); ctx->d_prm_row.release(); ctx->d_prm_col.release();
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   for (PinBuf& b : ctx->pin) b.release();
   for (int s = 0; s < MAX_SLOTS; ++s) {

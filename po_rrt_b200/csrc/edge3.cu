@@ -58,7 +58,7 @@ struct WarpMem {
 template <int KIND, bool INDEXED>
 __global__ void __launch_bounds__(E3_MAX_WARPS * 32, 1)
 edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double2* __restrict__ to, int64_t n,
-                        int32_t* __restrict__ out_vid, uint64_t* __restrict__ out_mask,
+                        int32_t* __restrict__ out_vid, int8_t* __restrict__ out_vid8, uint64_t* __restrict__ out_mask,
                         const uint64_t* __restrict__ validities, const int32_t* __restrict__ from_idx,
                         const int32_t* __restrict__ to_idx) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -447,14 +447,7 @@ edge_validity_v3_kernel(MapDev m, const double2* __restrict__ from, const double
         r = walk_sequential<KIND>(m, wk);
         if (KIND == PORRT_DOMAIN_SHELF && r == R_LOW) r = R_BLOCKED;
       }
-      const int32_t vid = walk_to_validity(m, r);
-      out_vid[eidx] = vid;
-      if (out_mask) {
-        if (m.mask_words == 1) out_mask[eidx] = vid >= 0 ? validities[vid] : 0ull;
-        else
-          for (int wd = 0; wd < m.mask_words; ++wd)
-            out_mask[eidx * m.mask_words + wd] = vid >= 0 ? validities[(int64_t)vid * m.mask_words + wd] : 0ull;
-      }
+      store_edge_result(m, eidx, walk_to_validity(m, r), out_vid, out_vid8, out_mask, validities);
     }
     __syncwarp();
   }
@@ -555,7 +548,7 @@ bool edge3_usable(const porrt_ctx* ctx) {
 }
 
 template <int KIND, bool INDEXED>
-static int32_t edge3_launch_t(porrt_ctx* ctx, const double2* from, const double2* to, int64_t n, int32_t* out_vid, uint64_t* out_mask,
+static int32_t edge3_launch_t(porrt_ctx* ctx, const double2* from, const double2* to, int64_t n, const EdgeOut& out,
                               const int32_t* from_idx, const int32_t* to_idx, cudaStream_t st) {
   auto kern = edge_validity_v3_kernel<KIND, INDEXED>;
   static bool attr_set[16] = {};
@@ -571,19 +564,19 @@ static int32_t edge3_launch_t(porrt_ctx* ctx, const double2* from, const double2
   int64_t ctas = (warps_needed + warps - 1) / warps;
   if (ctas > ctx->sm_count) ctas = ctx->sm_count;
   const size_t smem = (size_t)ctx->map.plane_bytes + 16 + (size_t)warps * sizeof(WarpMem);
-  kern<<<(int)ctas, warps * 32, smem, st>>>(ctx->map, from, to, n, out_vid, out_mask, ctx->d_validities.as<uint64_t>(), from_idx, to_idx);
+  kern<<<(int)ctas, warps * 32, smem, st>>>(ctx->map, from, to, n, out.vid, out.vid8, out.mask, ctx->d_validities.as<uint64_t>(), from_idx, to_idx);
   LAUNCH_CHECK(ctx);
   return PORRT_OK;
 }
 
-int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, int32_t* out_vid_dev,
-                     uint64_t* out_mask_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st) {
+int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n, const EdgeOut& out,
+                     const int32_t* from_idx_dev, const int32_t* to_idx_dev, cudaStream_t st) {
   const double2* f = (const double2*)from_dev;
   const double2* t = (const double2*)to_dev;
   const bool shelf = ctx->map.kind == PORRT_DOMAIN_SHELF;
   if (from_idx_dev)
-    return shelf ? edge3_launch_t<PORRT_DOMAIN_SHELF, true>(ctx, f, t, n, out_vid_dev, out_mask_dev, from_idx_dev, to_idx_dev, st)
-                 : edge3_launch_t<PORRT_DOMAIN_DOOR, true>(ctx, f, t, n, out_vid_dev, out_mask_dev, from_idx_dev, to_idx_dev, st);
-  return shelf ? edge3_launch_t<PORRT_DOMAIN_SHELF, false>(ctx, f, t, n, out_vid_dev, out_mask_dev, nullptr, nullptr, st)
-               : edge3_launch_t<PORRT_DOMAIN_DOOR, false>(ctx, f, t, n, out_vid_dev, out_mask_dev, nullptr, nullptr, st);
+    return shelf ? edge3_launch_t<PORRT_DOMAIN_SHELF, true>(ctx, f, t, n, out, from_idx_dev, to_idx_dev, st)
+                 : edge3_launch_t<PORRT_DOMAIN_DOOR, true>(ctx, f, t, n, out, from_idx_dev, to_idx_dev, st);
+  return shelf ? edge3_launch_t<PORRT_DOMAIN_SHELF, false>(ctx, f, t, n, out, nullptr, nullptr, st)
+               : edge3_launch_t<PORRT_DOMAIN_DOOR, false>(ctx, f, t, n, out, nullptr, nullptr, st);
 }

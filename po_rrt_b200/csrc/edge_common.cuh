@@ -1,4 +1,4 @@
-// edge_common.cuh -- constants and device helpers shared by the edge-validity kernels edge3.cu / edge4.cu
+// edge_common.cuh -- constants and device helpers of the edge-validity kernel (edge3.cu)
 #pragma once
 #include "map_dev.cuh"
 

@@ -325,13 +325,15 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   // device inputs
   CUDA_TRY(ctx, ctx->d_vxy.ensure((size_t)n * 16));
   DevBuf& aux = ctx->scratch[3];
-  CUDA_TRY(ctx, aux.ensure((size_t)n * (8 + 4 + 8 + 4 + 4 + 8 + 8 + 8 + 4) + 256));
-  char* b = aux.as<char>();
+  // carved below: 1 + 3 arrays of 8 bytes, 4 (+ 1 for grouped builds) of 4 bytes per node, + the "+1" entries and the flag
+  CUDA_TRY(ctx, aux.ensure((size_t)n * (8 + 3 * 8 + 4 * 4 + (gb ? 4 : 0)) + 3 * 8 + 16 + 256));
+  CUDA_TRY(ctx, ctx->d_prm_row.ensure((size_t)(n + 1) * 8));   // the result lives in its own buffers: it is retained (porrt_prm_fetch,
+  char* b = aux.as<char>();                                     // porrt_graph_from_prm) while later calls reuse the shared scratch
   double* d_radius = (double*)b; b += (size_t)n * 8;
   int64_t* d_off = (int64_t*)b; b += (size_t)(n + 1) * 8;
   int64_t* d_early_off = (int64_t*)b; b += (size_t)(n + 1) * 8;
   int64_t* d_late_off = (int64_t*)b; b += (size_t)(n + 1) * 8;
-  int64_t* d_row_ptr = (int64_t*)b; b += (size_t)(n + 1) * 8;
+  int64_t* d_row_ptr = ctx->d_prm_row.as<int64_t>();
   uint32_t* d_prefix = (uint32_t*)b; b += (size_t)n * 4;
   int32_t* d_rank = (int32_t*)b; b += (size_t)n * 4;
   int32_t* d_early_cnt = (int32_t*)b; b += (size_t)n * 4;
@@ -513,10 +515,10 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   // the validity ids (scratch 1) are dead after the compaction: late lists + cursors go there (the segment sort's radix
   // fallback owns scratch 5 / 6 and 8..10)
   CUDA_TRY(ctx, ctx->scratch[1].ensure((size_t)half1 * 4 + (size_t)n * 4));
-  CUDA_TRY(ctx, ctx->scratch[7].ensure((size_t)std::max<int64_t>(n_edges, 1) * 4));
+  CUDA_TRY(ctx, ctx->d_prm_col.ensure((size_t)std::max<int64_t>(n_edges, 1) * 4));
   int32_t* d_vals = ctx->scratch[1].as<int32_t>();
   int32_t* d_cursor = d_vals + half1;
-  int32_t* d_col = ctx->scratch[7].as<int32_t>();
+  int32_t* d_col = ctx->d_prm_col.as<int32_t>();
   CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, (size_t)n * 4, st));
   prm_late_count_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_cnt);
   LAUNCH_CHECK(ctx);

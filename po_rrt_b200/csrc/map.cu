@@ -81,53 +81,12 @@ __device__ __forceinline__ int32_t walk_warp(const MapDev& m, const EdgeSetup& s
 // ------------------------------------------------------------------------------------------------ kernels
 #define EDGE_BLOCK 256
 
-// INDEXED: endpoints are gathered from a vertex buffer, from[e] = xy[from_idx[e]], to[e] = xy[to_idx[e]] (PRM build).
-template <int KIND, bool INDEXED>
-__global__ void __launch_bounds__(EDGE_BLOCK) edge_validity_kernel(MapDev m, const double2* __restrict__ from,
-                                                                   const double2* __restrict__ to, int64_t n,
-                                                                   int32_t* __restrict__ out_vid,
-                                                                   uint64_t* __restrict__ out_mask,
-                                                                   const uint64_t* __restrict__ validities,
-                                                                   const int32_t* __restrict__ from_idx,
-                                                                   const int32_t* __restrict__ to_idx) {
-  __shared__ EdgeSetup s_setup[EDGE_BLOCK / 32][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t warp = ((int64_t)blockIdx.x * EDGE_BLOCK + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * EDGE_BLOCK) >> 5;
-  for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
-    const int64_t e = base + lane;
-    const int n_here = (int)min((int64_t)32, n - base);
-    if (e < n) {
-      double2 a = INDEXED ? from[from_idx[e]] : from[e];
-      double2 b = INDEXED ? to[to_idx[e]] : to[e];
-      s_setup[wib][lane] = make_setup(m, a.x, a.y, b.x, b.y);
-    }
-    __syncwarp();
-    int32_t mine = PORRT_INVALID;
-    for (int q = 0; q < n_here; ++q) {
-      EdgeSetup s = s_setup[wib][q];
-      int32_t r = walk_warp<KIND>(m, s, lane);
-      if (q == lane) mine = r;
-    }
-    __syncwarp();
-    if (e < n) {
-      int32_t vid = walk_to_validity(m, mine);
-      out_vid[e] = vid;
-      if (out_mask) {
-        if (m.mask_words == 1) out_mask[e] = vid >= 0 ? validities[vid] : 0ull;
-        else
-          for (int wd = 0; wd < m.mask_words; ++wd)
-            out_mask[e * m.mask_words + wd] = vid >= 0 ? validities[(int64_t)vid * m.mask_words + wd] : 0ull;
-      }
-    }
-  }
-}
-
-
-// ================================================================================================ edge validity, v2
-// Hierarchical, work-flattened variant.  v1 above is instruction-issue bound (ncu r1: 322 warp instructions per edge,
-// IPC 3.0 of 4): every pixel costs address arithmetic + a byte load + ballots.  v2 adds one CLASS byte per BS x BS
-// block (all free / all obstacle / all low / needs-per-pixel [+ contains gray]) and cuts the line into strips of <= BS
+// ================================================================================================ edge validity, large maps
+// The product's edge kernel is edge3.cu (class plane staged in shared memory).  Maps whose class plane does not fit in shared
+// memory (> ~14000^2 px) take this kernel instead: the same strip decomposition with the class bytes read from global memory
+// and per-pixel resolution of mixed strips on the fused byte grid.  INDEXED: endpoints are gathered from a vertex buffer,
+// from[e] = xy[from_idx[e]], to[e] = xy[to_idx[e]].
+// One CLASS byte per BS x BS block (all free / all obstacle / all low / needs-per-pixel [+ contains gray]) and cuts the line into strips of <= BS
 // pixels aligned to the block grid along the major axis; a strip touches at most two blocks (slope <= 1 in octant
 // space), so two class bytes settle it unless a block is mixed.  Only mixed strips are queued (shared memory) and
 // resolved per pixel afterwards, 32/BS strips per warp round, and strips of edges already known to be blocked are
@@ -195,15 +154,14 @@ __device__ __forceinline__ int32_t rec_minor(const EdgeRec& r, int32_t k) {
 }
 
 #define V2_QCAP 512  // queue entries per warp
-#ifndef V2_MINB
 #define V2_MINB 4
-#endif
 
 // V2_G: consecutive strips of one edge handled by a lane per round (amortises the owner search)
 template <int KIND, int LOG_BS, int V2_G, bool INDEXED>
 __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(MapDev m, const double2* __restrict__ from,
                                                                       const double2* __restrict__ to, int64_t n,
                                                                       int32_t* __restrict__ out_vid,
+                                                                      int8_t* __restrict__ out_vid8,
                                                                       uint64_t* __restrict__ out_mask,
                                                                       const uint64_t* __restrict__ validities,
                                                                       const int32_t* __restrict__ from_idx,
@@ -216,8 +174,9 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
   __shared__ uint32_t s_queue[WARPS][V2_QCAP];
   __shared__ int32_t s_qcount[WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint8_t* __restrict__ coarse = m.coarse[LOG_BS - 3];
-  const int cw = m.cw[LOG_BS - 3];
+  static_assert(LOG_BS == 4, "the class bytes are built for 16 x 16 blocks");
+  const uint8_t* __restrict__ coarse = m.coarse;
+  const int cw = m.coarse_cw;
   const int64_t warp = ((int64_t)blockIdx.x * EDGE_BLOCK + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * EDGE_BLOCK) >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -405,14 +364,7 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
         else { wk.ai = mine.n0; wk.aj = mine.c0; wk.ui = 0; wk.uj = sm; wk.vi = sn; wk.vj = 0; }
         r = walk_sequential<KIND>(m, wk);
       }
-      const int32_t vid = walk_to_validity(m, r);
-      out_vid[eidx] = vid;
-      if (out_mask) {
-        if (m.mask_words == 1) out_mask[eidx] = vid >= 0 ? validities[vid] : 0ull;
-        else
-          for (int wd = 0; wd < m.mask_words; ++wd)
-            out_mask[eidx * m.mask_words + wd] = vid >= 0 ? validities[(int64_t)vid * m.mask_words + wd] : 0ull;
-      }
+      store_edge_result(m, eidx, walk_to_validity(m, r), out_vid, out_vid8, out_mask, validities);
     }
     __syncwarp();
   }
@@ -577,16 +529,16 @@ PORRT_API int32_t porrt_map_upload(porrt_ctx* ctx, const uint8_t* occ, const uin
   fuse_tile_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->scratch[0].as<uint8_t>(), d_zone, H, W, tiles_x, tiles_y, kind,
                                                       ctx->d_grid.as<uint8_t>());
   LAUNCH_CHECK(ctx);
-  for (int lvl = 0; lvl < 3; ++lvl) {  // class bytes for 8x8, 16x16, 32x32 blocks
-    const int lg = 3 + lvl, bs = 1 << lg, cwl = (W + bs - 1) / bs, chl = (H + bs - 1) / bs;
-    CUDA_TRY(ctx, ctx->d_coarse[lvl].ensure((size_t)cwl * chl));
+  {  // class bytes of the 16 x 16 blocks (large-map path)
+    const int lg = 4, bs = 1 << lg, cwl = (W + bs - 1) / bs, chl = (H + bs - 1) / bs;
+    CUDA_TRY(ctx, ctx->d_coarse.ensure((size_t)cwl * chl));
     if (kind == PORRT_DOMAIN_SHELF)
-      coarse_build_kernel<PORRT_DOMAIN_SHELF><<<div_up((int64_t)cwl * chl * 32, 256), 256, 0, st>>>(ctx->d_grid.as<uint8_t>(), H, W, tiles_x, lg, cwl, chl, ctx->d_coarse[lvl].as<uint8_t>());
+      coarse_build_kernel<PORRT_DOMAIN_SHELF><<<div_up((int64_t)cwl * chl * 32, 256), 256, 0, st>>>(ctx->d_grid.as<uint8_t>(), H, W, tiles_x, lg, cwl, chl, ctx->d_coarse.as<uint8_t>());
     else
-      coarse_build_kernel<PORRT_DOMAIN_DOOR><<<div_up((int64_t)cwl * chl * 32, 256), 256, 0, st>>>(ctx->d_grid.as<uint8_t>(), H, W, tiles_x, lg, cwl, chl, ctx->d_coarse[lvl].as<uint8_t>());
+      coarse_build_kernel<PORRT_DOMAIN_DOOR><<<div_up((int64_t)cwl * chl * 32, 256), 256, 0, st>>>(ctx->d_grid.as<uint8_t>(), H, W, tiles_x, lg, cwl, chl, ctx->d_coarse.as<uint8_t>());
     LAUNCH_CHECK(ctx);
-    ctx->map.coarse[lvl] = ctx->d_coarse[lvl].as<uint8_t>();
-    ctx->map.cw[lvl] = cwl;
+    ctx->map.coarse = ctx->d_coarse.as<uint8_t>();
+    ctx->map.coarse_cw = cwl;
   }
   CUDA_TRY(ctx, ctx->d_validities.ensure(validities.size() * 8));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_validities.p, validities.data(), validities.size() * 8, cudaMemcpyHostToDevice, st));
@@ -595,7 +547,6 @@ PORRT_API int32_t porrt_map_upload(porrt_ctx* ctx, const uint8_t* occ, const uin
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zone_pos.p, zone_pos.data(), zone_pos.size() * 8, cudaMemcpyHostToDevice, st));
   MapDev& m = ctx->map;
   m.grid = ctx->d_grid.as<uint8_t>();
-  if (const char* v = getenv("PORRT_EDGE_VARIANT")) ctx->edge_variant = atoi(v);
   m.H = H; m.W = W; m.tiles_x = tiles_x; m.kind = kind; m.free_vid = n_validities - 1; m.mask_words = words;
   m.low0 = low[0]; m.low1 = low[1]; m.ppm = ppm; m.hm1 = (double)(H - 1);
   { int32_t rc = edge3_build(ctx, st); if (rc) return rc; }   // class plane + block bitmaps (edge3.cu)
@@ -636,42 +587,42 @@ static int edge_grid(porrt_ctx* ctx, int64_t n) {
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
-template <bool INDEXED>
-static int32_t launch_edges(porrt_ctx* ctx, const double2* from, const double2* to, int64_t n, int32_t* out_vid, uint64_t* out_mask,
-                            const int32_t* from_idx, const int32_t* to_idx, cudaStream_t st) {
+// One edge batch on the device: edge3.cu's kernel, or the large-map kernel above when the class plane does not fit in shared
+// memory.  from_idx / to_idx != NULL: endpoints are gathered from the vertex buffer from_dev == to_dev.
+int32_t map_edge_launch(porrt_ctx* ctx, const double* from_dev, const double* to_dev, const int32_t* from_idx, const int32_t* to_idx,
+                        int64_t n, const EdgeOut& out, cudaStream_t st) {
   if (n == 0) return PORRT_OK;
-  if (ctx->edge_variant == 0 && edge3_usable(ctx))
-    return edge3_launch(ctx, (const double*)from, (const double*)to, n, out_vid, out_mask, from_idx, to_idx, st);
-  if (ctx->edge_variant == 9 && edge4_usable(ctx))
-    return edge4_launch(ctx, (const double*)from, (const double*)to, n, out_vid, out_mask, from_idx, to_idx, st);
+  if (!ctx->force_large_map_path && edge3_usable(ctx)) return edge3_launch(ctx, from_dev, to_dev, n, out, from_idx, to_idx, st);
+  const double2 *from = (const double2*)from_dev, *to = (const double2*)to_dev;
   const uint64_t* val = ctx->d_validities.as<uint64_t>();
   const int grid = edge_grid(ctx, n);
   const bool shelf = ctx->map.kind == PORRT_DOMAIN_SHELF;
-#define LAUNCH_V2(K, L, G) edge_validity_v2_kernel<K, L, G, INDEXED><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out_vid, out_mask, val, from_idx, to_idx)
-#define LAUNCH_V1(K) edge_validity_kernel<K, INDEXED><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out_vid, out_mask, val, from_idx, to_idx)
-  switch (ctx->edge_variant) {
-    case 1: if (shelf) LAUNCH_V1(PORRT_DOMAIN_SHELF); else LAUNCH_V1(PORRT_DOMAIN_DOOR); break;
-    case 2: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 3, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 3, 4); break;
-    case 4: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 5, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 5, 4); break;
-    case 5: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4, 2); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4, 2); break;
-    case 6: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4, 8); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4, 8); break;
-    case 7: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 3, 8); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 3, 8); break;
-    default: if (shelf) LAUNCH_V2(PORRT_DOMAIN_SHELF, 4, 4); else LAUNCH_V2(PORRT_DOMAIN_DOOR, 4, 4); break;
-  }
-#undef LAUNCH_V1
-#undef LAUNCH_V2
+#define LAUNCH_LARGE(K, I) edge_validity_v2_kernel<K, 4, 4, I><<<grid, EDGE_BLOCK, 0, st>>>(ctx->map, from, to, n, out.vid, out.vid8, out.mask, val, from_idx, to_idx)
+  if (from_idx) { if (shelf) LAUNCH_LARGE(PORRT_DOMAIN_SHELF, true); else LAUNCH_LARGE(PORRT_DOMAIN_DOOR, true); }
+  else { if (shelf) LAUNCH_LARGE(PORRT_DOMAIN_SHELF, false); else LAUNCH_LARGE(PORRT_DOMAIN_DOOR, false); }
+#undef LAUNCH_LARGE
   LAUNCH_CHECK(ctx);
   return PORRT_OK;
 }
 
 int32_t map_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
                               int32_t* out_vid_dev, uint64_t* out_mask_dev, cudaStream_t st) {
-  return launch_edges<false>(ctx, (const double2*)from_dev, (const double2*)to_dev, n, out_vid_dev, out_mask_dev, nullptr, nullptr, st);
+  EdgeOut o; o.vid = out_vid_dev; o.mask = out_mask_dev;
+  return map_edge_launch(ctx, from_dev, to_dev, nullptr, nullptr, n, o, st);
 }
 
 int32_t map_edge_validity_indexed_dev(porrt_ctx* ctx, const double* xy_dev, const int32_t* from_idx_dev, const int32_t* to_idx_dev,
                                       int64_t n, int32_t* out_vid_dev, cudaStream_t st) {
-  return launch_edges<true>(ctx, (const double2*)xy_dev, (const double2*)xy_dev, n, out_vid_dev, nullptr, from_idx_dev, to_idx_dev, st);
+  EdgeOut o; o.vid = out_vid_dev;
+  return map_edge_launch(ctx, xy_dev, xy_dev, from_idx_dev, to_idx_dev, n, o, st);
+}
+
+PORRT_API int32_t porrt_ctx_set_option(porrt_ctx* ctx, int32_t option, int64_t value) {
+  CTX_CHECK(ctx);
+  switch (option) {
+    case PORRT_OPT_FORCE_LARGE_MAP_PATH: ctx->force_large_map_path = value != 0; return PORRT_OK;
+    default: return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_ctx_set_option: unknown option");
+  }
 }
 
 PORRT_API int32_t porrt_edge_validity_dev(porrt_ctx* ctx, const double* from_dev, const double* to_dev, int64_t n,
@@ -683,191 +634,231 @@ PORRT_API int32_t porrt_edge_validity_dev(porrt_ctx* ctx, const double* from_dev
   return map_edge_validity_dev(ctx, from_dev, to_dev, n, out_vid_dev, out_mask_dev, ctx->stream);
 }
 
-// Host-buffer entry point: chunks the batch and overlaps H2D(c+1) | kernel(c) | D2H(c-1) on three streams.
-// Caller buffers that are pinned (cudaHostAlloc / torch pin_memory) are DMA'd directly, pageable ones are staged.
-PORRT_API int32_t porrt_edge_validity(porrt_ctx* ctx, const double* from_xy, const double* to_xy, int64_t n,
-                                      int32_t* out_vid, uint64_t* out_mask) {
-  CTX_CHECK(ctx);
-  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
-  if (n < 0 || (n > 0 && (!from_xy || !to_xy || !out_vid))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity: bad arguments");
-  if (n == 0) return PORRT_OK;
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const int words = ctx->mask_words;
-  // edges per chunk: ~1/8 of the call, between 256 Ki and 2 Mi (measured on B200/PCIe 5: 2 Mi-edge chunks reach 50 GB/s
-  // host->device, 64 Ki-edge chunks 39 GB/s; at least ~8 chunks keep upload, kernel and download overlapped)
-  int64_t CH = n / 8;
-  CH = CH < (1 << 18) ? (1 << 18) : (CH > (1 << 21) ? (1 << 21) : CH);
-  if (const char* v = getenv("PORRT_EDGE_CHUNK_LOG2")) { const int l = atoi(v); if (l >= 10 && l <= 26) CH = (int64_t)1 << l; }
-  const int64_t ch = n < CH ? n : CH;
-  const bool pinned = is_pinned_host(from_xy) && is_pinned_host(to_xy) && is_pinned_host(out_vid) && (!out_mask || is_pinned_host(out_mask));
-  const int slots = MAX_SLOTS;
-  // device slots: from | to | vid | mask
-  const size_t slot_bytes = (size_t)ch * (16 + 16 + 4 + 8 * (size_t)words);
-  CUDA_TRY(ctx, ctx->scratch[3].ensure(slot_bytes * slots));
-  if (!pinned) CUDA_TRY(ctx, ctx->pin[0].ensure(slot_bytes * slots));
-  cudaStream_t st = ctx->stream;
-  const int64_t n_chunks = (n + ch - 1) / ch;
-  // the copy streams must not run ahead of work already queued on the compute stream
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[0], st));
-  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
-  for (int64_t c = 0; c < n_chunks; ++c) {
-    const int s = (int)(c % slots);
-    const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
-    char* dbase = ctx->scratch[3].as<char>() + slot_bytes * s;
-    double* d_from = (double*)dbase;
-    double* d_to = (double*)(dbase + (size_t)ch * 16);
-    uint64_t* d_mask = (uint64_t*)(dbase + (size_t)ch * 32);
-    int32_t* d_vid = (int32_t*)(dbase + (size_t)ch * (32 + 8 * (size_t)words));
-    if (c >= slots) {
-      // slot reuse: its previous D2H must be complete (also frees the pinned staging of that slot)
-      CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_out[s]));
-      if (!pinned) {
-        const int64_t poff = (c - slots) * ch, pcnt = (n - poff) < ch ? (n - poff) : ch;
-        char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
-        memcpy(out_vid + poff, hb + (size_t)ch * (32 + 8 * (size_t)words), (size_t)pcnt * 4);
-        if (out_mask) memcpy(out_mask + poff * words, hb + (size_t)ch * 32, (size_t)pcnt * 8 * words);
-      }
-    }
-    const double *h_from = from_xy + 2 * off, *h_to = to_xy + 2 * off;
-    if (!pinned) {
-      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
-      memcpy(hb, h_from, (size_t)cnt * 16);
-      memcpy(hb + (size_t)ch * 16, h_to, (size_t)cnt * 16);
-      h_from = (const double*)hb; h_to = (const double*)(hb + (size_t)ch * 16);
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_from, h_from, (size_t)cnt * 16, cudaMemcpyHostToDevice, ctx->copy_in));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_to, h_to, (size_t)cnt * 16, cudaMemcpyHostToDevice, ctx->copy_in));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_in[s], 0));
-    int32_t rc = map_edge_validity_dev(ctx, d_from, d_to, cnt, d_vid, out_mask ? d_mask : nullptr, st);
-    if (rc) return rc;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[s], st));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[s], 0));
-    int32_t* h_vid = out_vid + off;
-    uint64_t* h_mask = out_mask ? out_mask + off * words : nullptr;
-    if (!pinned) {
-      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
-      h_vid = (int32_t*)(hb + (size_t)ch * (32 + 8 * (size_t)words));
-      h_mask = (uint64_t*)(hb + (size_t)ch * 32);
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_vid, d_vid, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(h_mask, d_mask, (size_t)cnt * 8 * words, cudaMemcpyDeviceToHost, ctx->copy_out));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
-  }
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  if (!pinned) {
-    int64_t first = n_chunks > slots ? n_chunks - slots : 0;
-    for (int64_t c = first; c < n_chunks; ++c) {
-      const int s = (int)(c % slots);
-      const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
-      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
-      memcpy(out_vid + off, hb + (size_t)ch * (32 + 8 * (size_t)words), (size_t)cnt * 4);
-      if (out_mask) memcpy(out_mask + off * words, hb + (size_t)ch * 32, (size_t)cnt * 8 * words);
-    }
-  }
-  return PORRT_OK;
-}
-
 // ids outside [0, V) must never reach the edge kernels (they index the vertex array): clamp them and remember that it happened
 __global__ void idx_check_kernel(int32_t* __restrict__ a, int32_t* __restrict__ b, int64_t n, int32_t V, int32_t* __restrict__ bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int32_t x = a[i], y = b[i];
+  const int32_t x = a[i], y = b ? b[i] : 0;
   if ((uint32_t)x >= (uint32_t)V || (uint32_t)y >= (uint32_t)V) {
     *bad = 1;
     if ((uint32_t)x >= (uint32_t)V) a[i] = 0;
-    if ((uint32_t)y >= (uint32_t)V) b[i] = 0;
+    if (b && (uint32_t)y >= (uint32_t)V) b[i] = 0;
   }
 }
 
-// transition_validator(&PTONode, &PTONode) as the planners call it (pto.rs:105, prm.rs:93): both ends are NODES.  With the node
-// states resident on the device (porrt_vertices_set / porrt_prm_build), an edge is two 4-byte ids instead of four doubles: the
-// host->device stream shrinks from 32 to 8 bytes per edge, which is what bounds the end-to-end rate of porrt_edge_validity
-// (PCIe).  Same chunked three-stream pipeline; results identical to porrt_edge_validity on the same coordinates.
-PORRT_API int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* from_idx, const int32_t* to_idx, int64_t n,
-                                              int32_t* out_vid, uint64_t* out_mask) {
-  CTX_CHECK(ctx);
-  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
-  if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
-  if (n < 0 || (n > 0 && (!from_idx || !to_idx || !out_vid))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_indexed: bad arguments");
-  if (n == 0) return PORRT_OK;
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+// adjacency form: edge e of the CSR lies in row r = the last row with row_ptr[r] <= e; rows[e - e0] = r for e in [e0, e0 + n)
+__global__ void csr_rows_kernel(const int64_t* __restrict__ row_ptr, int64_t V, int64_t e0, int64_t n, int32_t* __restrict__ rows) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int64_t e = e0 + t;
+  int64_t lo = 0, hi = V;          // row_ptr[lo] <= e < row_ptr[hi]
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(row_ptr + mid) <= e) lo = mid; else hi = mid;
+  }
+  rows[t] = (int32_t)lo;
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer pipeline
+// Every host-buffer edge entry point is one chunked pipeline: H2D(c+1) | kernel(c) | D2H(c-1) on three streams over MAX_SLOTS
+// device slots.  Caller buffers that are pinned (cudaHostAlloc / torch pin_memory) are DMA'd directly, pageable ones are
+// staged through the ctx's pinned buffer.  A slot is carved with a 256-byte-aligned bump allocator (the kernels read endpoints
+// as 16-byte vectors and write 8-byte masks; chunk sizes are arbitrary).
+struct EdgeJob {
+  enum Mode { COORDS, INDEXED, CSR } mode = COORDS;
+  const void* in[2] = {nullptr, nullptr};   // per-edge host input arrays: COORDS from/to xy (16 B), INDEXED from/to ids (4 B), CSR col (4 B)
+  int in_elem[2] = {0, 0};
+  int n_in = 0;
+  int32_t* out_vid = nullptr;               // exactly one of out_vid / out_vid8
+  int8_t* out_vid8 = nullptr;
+  uint64_t* out_mask = nullptr;             // nullable, [n * mask_words]
+  const int64_t* row_ptr_dev = nullptr;     // CSR: device copy of row_ptr[V + 1]
+  int64_t csr_rows = 0;
+  int csr_row_is_to = 1;                    // CSR: 1 = edge col[e] -> row (prm.rs:93, neighbour -> new node), 0 = row -> col[e]
+  const char* name = "porrt_edge_validity";
+};
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int32_t edge_pipeline(porrt_ctx* ctx, const EdgeJob& job, int64_t n) {
   const int words = ctx->mask_words;
+  const int vid_elem = job.out_vid8 ? 1 : 4;
+  const size_t in_bytes = (size_t)job.in_elem[0] + (job.n_in > 1 ? (size_t)job.in_elem[1] : 0);
+  const size_t out_bytes = (size_t)vid_elem + (job.out_mask ? 8 * (size_t)words : 0);
+  // edges per chunk: ~1/8 of the call, between 2^18 and 2^21 edges for 48 B/edge (measured on B200/PCIe 5: 2 Mi-edge chunks of
+  // coordinates reach 50 GB/s host->device, 64 Ki-edge chunks 39 GB/s); lighter edges get proportionally longer chunks
+  const int64_t scale = (int64_t)(48 / (in_bytes + out_bytes)) < 1 ? 1 : (int64_t)(48 / (in_bytes + out_bytes));
   int64_t CH = n / 8;
-  CH = CH < (1 << 19) ? (1 << 19) : (CH > (1 << 22) ? (1 << 22) : CH);
+  const int64_t ch_lo = ((int64_t)1 << 18) * scale, ch_hi = ((int64_t)1 << 21) * scale;
+  CH = CH < ch_lo ? ch_lo : (CH > ch_hi ? ch_hi : CH);
+  if (const char* v = getenv("PORRT_EDGE_CHUNK_LOG2")) { const int l = atoi(v); if (l >= 10 && l <= 26) CH = (int64_t)1 << l; }
   const int64_t ch = n < CH ? n : CH;
-  const bool pinned = is_pinned_host(from_idx) && is_pinned_host(to_idx) && is_pinned_host(out_vid) && (!out_mask || is_pinned_host(out_mask));
+  bool pinned = is_pinned_host(job.in[0]) && (job.n_in < 2 || is_pinned_host(job.in[1])) &&
+                is_pinned_host(job.out_vid8 ? (const void*)job.out_vid8 : (const void*)job.out_vid) &&
+                (!job.out_mask || is_pinned_host(job.out_mask));
   const int slots = MAX_SLOTS;
-  // device slots: mask | from idx | to idx | vid
-  const size_t slot_bytes = (size_t)ch * (8 * (size_t)words + 4 + 4 + 4);
+  // slot layout (offsets valid for the device slot and, for pageable callers, its pinned twin)
+  size_t off_in[2] = {0, 0}, off_rows = 0, off_vid = 0, off_mask = 0, slot_bytes = 0;
+  for (int k = 0; k < job.n_in; ++k) { off_in[k] = slot_bytes; slot_bytes = align256(slot_bytes + (size_t)ch * job.in_elem[k]); }
+  if (job.mode == EdgeJob::CSR) { off_rows = slot_bytes; slot_bytes = align256(slot_bytes + (size_t)ch * 4); }
+  off_vid = slot_bytes; slot_bytes = align256(slot_bytes + (size_t)ch * vid_elem);
+  if (job.out_mask) { off_mask = slot_bytes; slot_bytes = align256(slot_bytes + (size_t)ch * 8 * words); }
   CUDA_TRY(ctx, ctx->scratch[3].ensure(slot_bytes * slots));
   if (!pinned) CUDA_TRY(ctx, ctx->pin[0].ensure(slot_bytes * slots));
   cudaStream_t st = ctx->stream;
   const int64_t n_chunks = (n + ch - 1) / ch;
   const double* d_xy = ctx->d_vxy.as<double>();
   const int64_t V = ctx->n_vertices;
-  CUDA_TRY(ctx, ctx->scratch[4].ensure(16));
-  int32_t* d_bad = ctx->scratch[4].as<int32_t>();
-  CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, 4, st));
+  int32_t* d_bad = nullptr;
+  if (job.mode != EdgeJob::COORDS) {
+    CUDA_TRY(ctx, ctx->scratch[4].ensure(16));
+    d_bad = ctx->scratch[4].as<int32_t>();
+    CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, 4, st));
+  }
+  // the copy streams must not run ahead of work already queued on the compute stream
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[0], st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
+  char* const h_vid_base = job.out_vid8 ? (char*)job.out_vid8 : (char*)job.out_vid;
   auto unstage = [&](int64_t c) {   // pageable outputs: copy chunk c out of its pinned slot
     const int s = (int)(c % slots);
     const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
-    char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
-    memcpy(out_vid + off, hb + (size_t)ch * (8 * (size_t)words + 8), (size_t)cnt * 4);
-    if (out_mask) memcpy(out_mask + off * words, hb, (size_t)cnt * 8 * words);
+    const char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
+    memcpy(h_vid_base + (size_t)off * vid_elem, hb + off_vid, (size_t)cnt * vid_elem);
+    if (job.out_mask) memcpy(job.out_mask + off * words, hb + off_mask, (size_t)cnt * 8 * words);
   };
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int s = (int)(c % slots);
     const int64_t off = c * ch, cnt = (n - off) < ch ? (n - off) : ch;
     char* dbase = ctx->scratch[3].as<char>() + slot_bytes * s;
-    uint64_t* d_mask = (uint64_t*)dbase;
-    int32_t* d_from = (int32_t*)(dbase + (size_t)ch * 8 * (size_t)words);
-    int32_t* d_to = d_from + ch;
-    int32_t* d_vid = d_to + ch;
+    char* hb = pinned ? nullptr : ctx->pin[0].as<char>() + slot_bytes * s;
     if (c >= slots) {
+      // slot reuse: its previous D2H must be complete (also frees the pinned staging of that slot)
       CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_out[s]));
       if (!pinned) unstage(c - slots);
     }
-    const int32_t *h_from = from_idx + off, *h_to = to_idx + off;
-    if (!pinned) {
-      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
-      int32_t* hf = (int32_t*)(hb + (size_t)ch * 8 * (size_t)words);
-      memcpy(hf, h_from, (size_t)cnt * 4);
-      memcpy(hf + ch, h_to, (size_t)cnt * 4);
-      h_from = hf; h_to = hf + ch;
+    for (int k = 0; k < job.n_in; ++k) {
+      const char* src = (const char*)job.in[k] + (size_t)off * job.in_elem[k];
+      if (!pinned) { memcpy(hb + off_in[k], src, (size_t)cnt * job.in_elem[k]); src = hb + off_in[k]; }
+      CUDA_TRY(ctx, cudaMemcpyAsync(dbase + off_in[k], src, (size_t)cnt * job.in_elem[k], cudaMemcpyHostToDevice, ctx->copy_in));
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_from, h_from, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_to, h_to, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_in[s], 0));
-    idx_check_kernel<<<div_up(cnt, 256), 256, 0, st>>>(d_from, d_to, cnt, (int32_t)V, d_bad);
-    LAUNCH_CHECK(ctx);
-    int32_t rc = launch_edges<true>(ctx, (const double2*)d_xy, (const double2*)d_xy, cnt, d_vid, out_mask ? d_mask : nullptr, d_from, d_to, st);
+    EdgeOut o;
+    if (job.out_vid8) o.vid8 = (int8_t*)(dbase + off_vid); else o.vid = (int32_t*)(dbase + off_vid);
+    if (job.out_mask) o.mask = (uint64_t*)(dbase + off_mask);
+    int32_t rc;
+    if (job.mode == EdgeJob::COORDS) {
+      rc = map_edge_launch(ctx, (const double*)(dbase + off_in[0]), (const double*)(dbase + off_in[1]), nullptr, nullptr, cnt, o, st);
+    } else {
+      int32_t* d_a = (int32_t*)(dbase + off_in[0]);
+      int32_t* d_b = job.mode == EdgeJob::INDEXED ? (int32_t*)(dbase + off_in[1]) : nullptr;
+      idx_check_kernel<<<div_up(cnt, 256), 256, 0, st>>>(d_a, d_b, cnt, (int32_t)V, d_bad);
+      LAUNCH_CHECK(ctx);
+      if (job.mode == EdgeJob::CSR) {
+        int32_t* d_rows = (int32_t*)(dbase + off_rows);
+        csr_rows_kernel<<<div_up(cnt, 256), 256, 0, st>>>(job.row_ptr_dev, job.csr_rows, off, cnt, d_rows);
+        LAUNCH_CHECK(ctx);
+        rc = job.csr_row_is_to ? map_edge_launch(ctx, d_xy, d_xy, d_a, d_rows, cnt, o, st)
+                               : map_edge_launch(ctx, d_xy, d_xy, d_rows, d_a, cnt, o, st);
+      } else {
+        rc = map_edge_launch(ctx, d_xy, d_xy, d_a, d_b, cnt, o, st);
+      }
+    }
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[s], st));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[s], 0));
-    int32_t* h_vid = out_vid + off;
-    uint64_t* h_mask = out_mask ? out_mask + off * words : nullptr;
-    if (!pinned) {
-      char* hb = ctx->pin[0].as<char>() + slot_bytes * s;
-      h_vid = (int32_t*)(hb + (size_t)ch * (8 * (size_t)words + 8));
-      h_mask = (uint64_t*)hb;
+    char* h_vid = pinned ? h_vid_base + (size_t)off * vid_elem : hb + off_vid;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_vid, dbase + off_vid, (size_t)cnt * vid_elem, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (job.out_mask) {
+      char* h_mask = pinned ? (char*)(job.out_mask + off * words) : hb + off_mask;
+      CUDA_TRY(ctx, cudaMemcpyAsync(h_mask, dbase + off_mask, (size_t)cnt * 8 * words, cudaMemcpyDeviceToHost, ctx->copy_out));
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_vid, d_vid, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(h_mask, d_mask, (size_t)cnt * 8 * words, cudaMemcpyDeviceToHost, ctx->copy_out));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
   }
   int32_t bad = 0;
-  CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+  if (d_bad) CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   if (!pinned)
     for (int64_t c = n_chunks > slots ? n_chunks - slots : 0; c < n_chunks; ++c) unstage(c);
-  if (bad) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_indexed: vertex id out of range");
+  if (bad) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, std::string(job.name) + ": vertex id out of range");
   return PORRT_OK;
+}
+
+static int32_t edge_entry_checks(porrt_ctx* ctx, const char* name, int64_t n, bool ok_args, bool need_vertices) {
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (need_vertices && ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
+  if (n < 0 || (n > 0 && !ok_args)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, std::string(name) + ": bad arguments");
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_edge_validity(porrt_ctx* ctx, const double* from_xy, const double* to_xy, int64_t n,
+                                      int32_t* out_vid, uint64_t* out_mask) {
+  CTX_CHECK(ctx);
+  if (int32_t rc = edge_entry_checks(ctx, "porrt_edge_validity", n, from_xy && to_xy && out_vid, false)) return rc;
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  EdgeJob j; j.mode = EdgeJob::COORDS; j.in[0] = from_xy; j.in[1] = to_xy; j.in_elem[0] = j.in_elem[1] = 16; j.n_in = 2;
+  j.out_vid = out_vid; j.out_mask = out_mask; j.name = "porrt_edge_validity";
+  return edge_pipeline(ctx, j, n);
+}
+
+PORRT_API int32_t porrt_edge_validity_i8(porrt_ctx* ctx, const double* from_xy, const double* to_xy, int64_t n, int8_t* out_vid8) {
+  CTX_CHECK(ctx);
+  if (int32_t rc = edge_entry_checks(ctx, "porrt_edge_validity_i8", n, from_xy && to_xy && out_vid8, false)) return rc;
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  EdgeJob j; j.mode = EdgeJob::COORDS; j.in[0] = from_xy; j.in[1] = to_xy; j.in_elem[0] = j.in_elem[1] = 16; j.n_in = 2;
+  j.out_vid8 = out_vid8; j.name = "porrt_edge_validity_i8";
+  return edge_pipeline(ctx, j, n);
+}
+
+// transition_validator(&PTONode, &PTONode) as the planners call it (pto.rs:105, prm.rs:93): both ends are NODES.  With the node
+// states resident on the device (porrt_vertices_set / porrt_prm_build), an edge is two 4-byte ids instead of four doubles: the
+// host->device stream shrinks from 32 to 8 bytes per edge, which is what bounds the end-to-end rate of porrt_edge_validity
+// (PCIe).  Same pipeline; results identical to porrt_edge_validity on the same coordinates.
+PORRT_API int32_t porrt_edge_validity_indexed(porrt_ctx* ctx, const int32_t* from_idx, const int32_t* to_idx, int64_t n,
+                                              int32_t* out_vid, uint64_t* out_mask) {
+  CTX_CHECK(ctx);
+  if (int32_t rc = edge_entry_checks(ctx, "porrt_edge_validity_indexed", n, from_idx && to_idx && out_vid, true)) return rc;
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  EdgeJob j; j.mode = EdgeJob::INDEXED; j.in[0] = from_idx; j.in[1] = to_idx; j.in_elem[0] = j.in_elem[1] = 4; j.n_in = 2;
+  j.out_vid = out_vid; j.out_mask = out_mask; j.name = "porrt_edge_validity_indexed";
+  return edge_pipeline(ctx, j, n);
+}
+
+PORRT_API int32_t porrt_edge_validity_indexed_i8(porrt_ctx* ctx, const int32_t* from_idx, const int32_t* to_idx, int64_t n,
+                                                 int8_t* out_vid8) {
+  CTX_CHECK(ctx);
+  if (int32_t rc = edge_entry_checks(ctx, "porrt_edge_validity_indexed_i8", n, from_idx && to_idx && out_vid8, true)) return rc;
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  EdgeJob j; j.mode = EdgeJob::INDEXED; j.in[0] = from_idx; j.in[1] = to_idx; j.in_elem[0] = j.in_elem[1] = 4; j.n_in = 2;
+  j.out_vid8 = out_vid8; j.name = "porrt_edge_validity_indexed_i8";
+  return edge_pipeline(ctx, j, n);
+}
+
+// The candidate edges of a roadmap as the planners hold them: an adjacency (CSR) over the resident vertex set -- row r lists the
+// neighbours transition_validator is asked about for node r (prm.rs:91-96, pto.rs:103-108).  4 bytes in, 1 byte out per edge.
+PORRT_API int32_t porrt_edge_validity_csr_i8(porrt_ctx* ctx, const int64_t* row_ptr, const int32_t* col, int64_t n_rows,
+                                             int32_t row_is_to, int8_t* out_vid8) {
+  CTX_CHECK(ctx);
+  if (n_rows < 0 || (n_rows > 0 && !row_ptr)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_csr_i8: bad arguments");
+  if (n_rows == 0) return PORRT_OK;
+  const int64_t n = row_ptr[n_rows];
+  if (int32_t rc = edge_entry_checks(ctx, "porrt_edge_validity_csr_i8", n, col && out_vid8, true)) return rc;
+  if (n_rows > ctx->n_vertices || row_ptr[0] != 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_csr_i8: rows exceed the vertex set / row_ptr[0] != 0");
+  for (int64_t r = 0; r < n_rows; ++r)
+    if (row_ptr[r + 1] < row_ptr[r]) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_edge_validity_csr_i8: row_ptr not monotone");
+  if (n == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, ctx->scratch[5].ensure((size_t)(n_rows + 1) * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scratch[5].p, row_ptr, (size_t)(n_rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  EdgeJob j; j.mode = EdgeJob::CSR; j.in[0] = col; j.in_elem[0] = 4; j.n_in = 1; j.out_vid8 = out_vid8;
+  j.row_ptr_dev = ctx->scratch[5].as<int64_t>(); j.csr_rows = n_rows; j.csr_row_is_to = row_is_to ? 1 : 0;
+  j.name = "porrt_edge_validity_csr_i8";
+  return edge_pipeline(ctx, j, n);
 }
 
 PORRT_API int32_t porrt_state_validity_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, int32_t* out_dev) {

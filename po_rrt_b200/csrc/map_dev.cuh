@@ -113,3 +113,18 @@ __device__ __forceinline__ int32_t walk_to_validity(const MapDev& m, int32_t r) 
   return r;                                // blocked (-1) or panic code
 }
 
+
+// One edge's outputs: the validity id as int32 or as a signed byte (ids are < 128: n_validities <= 65; the negative codes
+// are the same), and optionally its per-world bitvec = world_validities[id] (map_io.rs:548-550), all zero when invalid.
+__device__ __forceinline__ void store_edge_result(const MapDev& m, int64_t e, int32_t vid, int32_t* __restrict__ out_vid,
+                                                  int8_t* __restrict__ out_vid8, uint64_t* __restrict__ out_mask,
+                                                  const uint64_t* __restrict__ validities) {
+  if (out_vid8) out_vid8[e] = (int8_t)vid;
+  else out_vid[e] = vid;
+  if (out_mask) {
+    if (m.mask_words == 1) out_mask[e] = vid >= 0 ? validities[vid] : 0ull;
+    else
+      for (int wd = 0; wd < m.mask_words; ++wd)
+        out_mask[e * m.mask_words + wd] = vid >= 0 ? validities[(int64_t)vid * m.mask_words + wd] : 0ull;
+  }
+}

@@ -258,6 +258,7 @@ static GridDev grid_dev(porrt_ctx* ctx) {
   g.vxy = ctx->d_vxy_sorted.as<double2>(); g.vid = ctx->d_vid_sorted.as<int32_t>(); g.cell_start = ctx->d_cell_start.as<int64_t>();
   g.org_x = ctx->org_x; g.org_y = ctx->org_y; g.inv_cell = ctx->inv_cell; g.cell = ctx->cell;
   g.cells_x = ctx->cells_x; g.cells_y = ctx->cells_y; g.n = ctx->n_vertices;
+  g.reach_words = ctx->reach_words;
   return g;
 }
 
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
   if (T >= 0.0 && p.x == p.x && p.y == p.y) {
     const uint32_t limit = prefix ? prefix[t] : 0xffffffffu;
     const uint32_t lo_limit = prefix_lo ? prefix_lo[t] : 0u;   // ids below belong to other roadmaps sharing the vertex set
-    const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+    const uint32_t wq = (reach && world) ? world[t] : 0u;
     const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);  // conservative cell cover
     const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
     const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
           for (; k < e; ++k) {
             const uint32_t id = (uint32_t)g.vid[k];
             if (id >= limit) break;
-            if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || ((reach[id] >> wbit) & 1ull))) {
+            if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || reach_bit(reach, g.reach_words, id, wq))) {
               if (FILL) out[cnt] = (int32_t)id;
               ++cnt;
             }
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
         for (int64_t k = s; k < e; ++k) {
           if (dist2(g.vxy[k], p.x, p.y) <= T) {
             const uint32_t id = (uint32_t)g.vid[k];
-            if (!reach || ((reach[id] >> wbit) & 1ull)) {
+            if (!reach || reach_bit(reach, g.reach_words, id, wq)) {
               if (FILL) out[cnt] = (int32_t)id;
               ++cnt;
             }
@@ -691,24 +692,27 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
 }
 
 PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const double* radius, int64_t m,
-                                     const uint32_t* prefix_limit, const uint64_t* reach_mask, const uint32_t* world,
+                                     const uint32_t* prefix_limit, const uint64_t* reach_mask, int32_t reach_words, const uint32_t* world,
                                      int64_t* out_offsets, int32_t* out_ids, int64_t cap, int64_t* out_total) {
   CTX_CHECK(ctx);
   if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
-  if (m < 0 || (m > 0 && (!q_xy || !radius || !out_offsets)) || (reach_mask && !world)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "radius_query: bad arguments");
+  if (m < 0 || (m > 0 && (!q_xy || !radius || !out_offsets)) || (reach_mask && (!world || reach_words < 1)))
+    return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "radius_query: bad arguments");
+  ctx->reach_words = reach_mask ? reach_words : 1;
+  const size_t reach_bytes = reach_mask ? (size_t)ctx->n_vertices * 8 * (size_t)reach_words : 0;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   if (m == 0) { if (out_offsets) out_offsets[0] = 0; if (out_total) *out_total = 0; return PORRT_OK; }
   const int64_t V = ctx->n_vertices;
   // device inputs: q | radius | prefix | world | reach | offsets
-  size_t need = (size_t)m * (16 + 8 + 4 + 4 + 8) + 64 + (reach_mask ? (size_t)V * 8 : 0);
+  size_t need = (size_t)m * (16 + 8 + 4 + 4 + 8) + 64 + reach_bytes;
   CUDA_TRY(ctx, ctx->scratch[3].ensure(need));
   char* b = ctx->scratch[3].as<char>();
   double* d_q = (double*)b; b += (size_t)m * 16;
   double* d_r = (double*)b; b += (size_t)m * 8;
   int64_t* d_off = (int64_t*)b; b += (size_t)(m + 1) * 8;
   uint64_t* d_reach = nullptr;
-  if (reach_mask) { d_reach = (uint64_t*)b; b += (size_t)V * 8; }
+  if (reach_mask) { d_reach = (uint64_t*)b; b += reach_bytes; }
   uint32_t* d_prefix = nullptr; uint32_t* d_world = nullptr;
   if (prefix_limit) { d_prefix = (uint32_t*)b; b += (size_t)m * 4; }
   if (world) { d_world = (uint32_t*)b; b += (size_t)m * 4; }
@@ -716,7 +720,7 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
   CUDA_TRY(ctx, cudaMemcpyAsync(d_r, radius, (size_t)m * 8, cudaMemcpyHostToDevice, st));
   if (d_prefix) CUDA_TRY(ctx, cudaMemcpyAsync(d_prefix, prefix_limit, (size_t)m * 4, cudaMemcpyHostToDevice, st));
   if (d_world) CUDA_TRY(ctx, cudaMemcpyAsync(d_world, world, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-  if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
+  if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, reach_bytes, cudaMemcpyHostToDevice, st));
   int64_t total = 0;
   tstart(ctx);  // phases: [count+scan+fill, order restore, D2H]
   int32_t rc = nn_radius_count_fill_dev(ctx, d_q, d_r, m, d_prefix, d_reach, d_world, d_off, &ctx->scratch[2], &total, nullptr);
@@ -778,7 +782,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(GridDev g, const doubl
   TopK<KMAX> top;
   top.init(k, s_d2, s_id);
   int32_t ties = 0;  // KMAX == 1 only: vertices at exactly the winning d2
-  const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+  const uint32_t wq = (reach && world) ? world[t] : 0u;
   if (p.x == p.x && p.y == p.y) {
     const int cx = cell_coord(p.x, g.org_x, g.inv_cell, g.cells_x), cy = cell_coord(p.y, g.org_y, g.inv_cell, g.cells_y);
     const int maxR = max(max(cx, g.cells_x - 1 - cx), max(cy, g.cells_y - 1 - cy));
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(GridDev g, const doubl
             const double d = dist2(g.vxy[kk], p.x, p.y);
             if (d <= top.worst() || top.cnt < k) {
               const int32_t id = g.vid[kk];
-              if (!reach || ((reach[id] >> wbit) & 1ull)) {
+              if (!reach || reach_bit(reach, g.reach_words, id, wq)) {
                 if (KMAX == 1) {
                   if (top.cnt == 0 || d < top.dist_at(0)) ties = 1;
                   else if (d == top.dist_at(0)) ++ties;
@@ -830,14 +834,14 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_warp_kernel(GridDev g, const 
   __shared__ double s_d2[KMAX][KNN_THREADS];
   __shared__ int32_t s_id[KMAX][KNN_THREADS];
   const int lane = threadIdx.x & 31;
-  const int64_t wq = ((int64_t)blockIdx.x * KNN_THREADS + threadIdx.x) >> 5;
-  if (wq >= m) return;                       // whole warps leave together
-  const int64_t t = list ? list[wq] : wq;
+  const int64_t wslot = ((int64_t)blockIdx.x * KNN_THREADS + threadIdx.x) >> 5;
+  if (wslot >= m) return;                    // whole warps leave together
+  const int64_t t = list ? list[wslot] : wslot;
   const double2 p = q[t];
   TopK<KMAX> top;
   top.init(k, s_d2, s_id);
   int32_t ties = 0;                          // k == 1: vertices at exactly this lane's best d2
-  const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+  const uint32_t wq = (reach && world) ? world[t] : 0u;
   // k rounds of "smallest (d2, id) among the lane heads"; returns the k-th best d2 (inf if fewer than k exist) and, when
   // `write`, stores the sorted result
   auto draw = [&](bool write) -> double {
@@ -880,7 +884,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_warp_kernel(GridDev g, const 
             const double d = dist2(g.vxy[kk], p.x, p.y);
             if (d <= top.worst() || top.cnt < k) {
               const int32_t id = g.vid[kk];
-              if (!reach || ((reach[id] >> wbit) & 1ull)) {
+              if (!reach || reach_bit(reach, g.reach_words, id, wq)) {
                 if (KMAX == 1) {
                   if (top.cnt == 0 || d < top.dist_at(0)) ties = 1;
                   else if (d == top.dist_at(0)) ++ties;
@@ -903,28 +907,31 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_warp_kernel(GridDev g, const 
   }
 }
 
-static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, const uint64_t* reach_mask, const uint32_t* world,
-                        int32_t* out_ids, double* out_dist, int32_t* out_ties) {
+static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, const uint64_t* reach_mask, int32_t reach_words,
+                        const uint32_t* world, int32_t* out_ids, double* out_dist, int32_t* out_ties) {
   if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
-  if (m < 0 || (m > 0 && (!q_xy || !out_ids)) || k < 1 || k > 32 || (reach_mask && !world)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "nearest/knn: bad arguments (1 <= k <= 32)");
+  if (m < 0 || (m > 0 && (!q_xy || !out_ids)) || k < 1 || k > 32 || (reach_mask && (!world || reach_words < 1)))
+    return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "nearest/knn: bad arguments (1 <= k <= 32)");
   if (m == 0) return PORRT_OK;
+  ctx->reach_words = reach_mask ? reach_words : 1;
+  const size_t reach_bytes = reach_mask ? (size_t)ctx->n_vertices * 8 * (size_t)reach_words : 0;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int64_t V = ctx->n_vertices;
-  size_t need = (size_t)m * (16 + 4 + 4) + (size_t)m * k * 12 + (reach_mask ? (size_t)V * 8 : 0) + 64;
+  size_t need = (size_t)m * (16 + 4 + 4) + (size_t)m * k * 12 + reach_bytes + 64;
   CUDA_TRY(ctx, ctx->scratch[3].ensure(need));
   char* b = ctx->scratch[3].as<char>();
   double* d_q = (double*)b; b += (size_t)m * 16;
   double* d_dist = (double*)b; b += (size_t)m * k * 8;
   uint64_t* d_reach = nullptr;
-  if (reach_mask) { d_reach = (uint64_t*)b; b += (size_t)V * 8; }
+  if (reach_mask) { d_reach = (uint64_t*)b; b += reach_bytes; }
   int32_t* d_ids = (int32_t*)b; b += (size_t)m * k * 4;
   int32_t* d_ties = (int32_t*)b; b += (size_t)m * 4;
   uint32_t* d_world = nullptr;
   if (world) { d_world = (uint32_t*)b; b += (size_t)m * 4; }
   CUDA_TRY(ctx, cudaMemcpyAsync(d_q, q_xy, (size_t)m * 16, cudaMemcpyHostToDevice, st));
   if (d_world) CUDA_TRY(ctx, cudaMemcpyAsync(d_world, world, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-  if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, (size_t)V * 8, cudaMemcpyHostToDevice, st));
+  if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, reach_bytes, cudaMemcpyHostToDevice, st));
   GridDev g = grid_dev(ctx);
   tstart(ctx);  // phases: [kernel, D2H]
   int64_t m_run = m;
@@ -957,12 +964,12 @@ static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, co
   return PORRT_OK;
 }
 
-PORRT_API int32_t porrt_nearest(porrt_ctx* ctx, const double* q_xy, int64_t m, const uint64_t* reach_mask, const uint32_t* world,
-                                int32_t* out_id, double* out_dist, int32_t* out_ties) {
+PORRT_API int32_t porrt_nearest(porrt_ctx* ctx, const double* q_xy, int64_t m, const uint64_t* reach_mask, int32_t reach_words,
+                                const uint32_t* world, int32_t* out_id, double* out_dist, int32_t* out_ties) {
   CTX_CHECK(ctx);
-  return knn_host(ctx, q_xy, m, 1, reach_mask, world, out_id, out_dist, out_ties);
+  return knn_host(ctx, q_xy, m, 1, reach_mask, reach_words, world, out_id, out_dist, out_ties);
 }
 PORRT_API int32_t porrt_knn(porrt_ctx* ctx, const double* q_xy, int64_t m, int32_t k, int32_t* out_ids, double* out_dist) {
   CTX_CHECK(ctx);
-  return knn_host(ctx, q_xy, m, k, nullptr, nullptr, out_ids, out_dist, nullptr);
+  return knn_host(ctx, q_xy, m, k, nullptr, 1, nullptr, out_ids, out_dist, nullptr);
 }

@@ -10,7 +10,15 @@ struct GridDev {
   double org_x, org_y, inv_cell, cell;
   int32_t cells_x, cells_y;
   int64_t n;
+  int32_t reach_words;      // u64 words per vertex of the reachability filter of the running call (pto_reachability.rs: one bit per world)
 };
+
+// the validator closure of pto.rs:74-77: bit `w` of vertex id's reachability mask (BitVec Lsb0: bit w of word w / 64).
+// A world beyond the mask passes nothing (the reference's BitVec index would panic).
+__device__ __forceinline__ bool reach_bit(const uint64_t* __restrict__ reach, int words, int32_t id, uint32_t w) {
+  if ((w >> 6) >= (uint32_t)words) return false;
+  return (reach[(int64_t)id * words + (w >> 6)] >> (w & 63u)) & 1ull;
+}
 
 __device__ __forceinline__ int cell_coord(double v, double org, double inv_cell, int n_cells) {
   double c = floor(__dmul_rn(__dsub_rn(v, org), inv_cell));

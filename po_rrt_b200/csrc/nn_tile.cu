@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
     const double Tr = radius_threshold(r);
     const uint32_t limit = prefix ? prefix[t] : 0xffffffffu;
     const uint32_t lo_limit = prefix_lo ? prefix_lo[t] : 0u;
-    const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+    const uint32_t wq = (reach && world) ? world[t] : 0u;
     const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);
     const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
     const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_radius_kernel(GridDev g, const 
       for (int j = 0; j < n_run; ++j) {
         if (dist2(cx[j], p.x, p.y) <= Tr) {
           const int32_t id = ci[j];
-          if ((uint32_t)id < limit && (uint32_t)id >= lo_limit && (!reach || ((reach[id] >> wbit) & 1ull))) {
+          if ((uint32_t)id < limit && (uint32_t)id >= lo_limit && (!reach || reach_bit(reach, g.reach_words, id, wq))) {
             if (FILL) out[cnt] = id;
             ++cnt;
           }
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
   for (int qi = threadIdx.x; qi < T.nq; qi += NT_THREADS) {
     const int32_t t = qorder[T.qa + qi];
     const double2 p = q[t];
-    const int wbit = (reach && world) ? (int)(world[t] & 63u) : 0;
+    const uint32_t wq = (reach && world) ? world[t] : 0u;
     const int cx = cell_coord(p.x, g.org_x, g.inv_cell, g.cells_x);
     const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, g.cells_x - 1);
     // the query's candidate runs (rows cy-1, cy, cy+1)
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
           const double d = dist2(rx[rr3][j], p.x, p.y);
           if (d != d || (cnt != 0 && d > best)) continue;
           const int32_t id = ri[rr3][j];
-          if (reach && !((reach[id] >> wbit) & 1ull)) continue;
+          if (reach && !reach_bit(reach, g.reach_words, id, wq)) continue;
           if (cnt == 0 || d < best) ties = 1; else ++ties;       // here d == best
           if (cnt == 0 || d < best || id < best_id) { best = d; best_id = id; }
           cnt = 1;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
         for (int j = 0; j < rn[rr3]; ++j) {
           const double d = dist2(rx[rr3][j], p.x, p.y);
           if (d != d) continue;
-          if (reach && !((reach[ri[rr3][j]] >> wbit) & 1ull)) continue;
+          if (reach && !reach_bit(reach, g.reach_words, ri[rr3][j], wq)) continue;
           const double fb = d * bin_scale;
           if (fb < (double)NT_BINS) { uint8_t* h = hist + (int)fb * NT_THREADS; if (*h < 255) ++*h; }
           else ++n_far;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(NT_THREADS) nt_knn_kernel(GridDev g, const dou
           for (int j = 0; j < rn[rr3]; ++j) {
             const double d = dist2(rx[rr3][j], p.x, p.y);
             if (d != d || !(d * bin_scale < lim)) continue;
-            if (reach && !((reach[ri[rr3][j]] >> wbit) & 1ull)) continue;
+            if (reach && !reach_bit(reach, g.reach_words, ri[rr3][j], wq)) continue;
             lst[cnt * NT_THREADS] = (uint16_t)(rx[rr3] - s_xy + j);    // unsorted append: the warp stays together
             ++cnt;
           }

@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstring>
 
+#include "pcg64.h"
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------ device
@@ -87,39 +88,6 @@ PORRT_API int32_t porrt_transition_valid(porrt_ctx* ctx, const double* from_xy, 
 
 // ------------------------------------------------------------------------------------------------ sampler (host)
 namespace {
-struct Pcg64 {   // rand_pcg::Lcg128Xsl64 (pcg64): 128-bit LCG, XSL-RR output
-  unsigned __int128 state, inc;
-  static unsigned __int128 mul() { return ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull; }
-  static Pcg64 seed_from_u64(uint64_t s) {   // rand_core::SeedableRng::seed_from_u64: a PCG32 stream fills the 32-byte seed
-    const uint64_t M = 6364136223846793005ull, I = 11634580027462260723ull;
-    uint32_t w[8];
-    for (int c = 0; c < 8; ++c) {
-      s = s * M + I;
-      const uint32_t x = (uint32_t)(((s >> 18) ^ s) >> 27), rot = (uint32_t)(s >> 59);
-      w[c] = (x >> rot) | (x << ((32 - rot) & 31));
-    }
-    Pcg64 p;
-    p.state = (unsigned __int128)((uint64_t)w[0] | ((uint64_t)w[1] << 32)) | ((unsigned __int128)((uint64_t)w[2] | ((uint64_t)w[3] << 32)) << 64);
-    p.inc = ((unsigned __int128)((uint64_t)w[4] | ((uint64_t)w[5] << 32)) | ((unsigned __int128)((uint64_t)w[6] | ((uint64_t)w[7] << 32)) << 64)) | 1;
-    p.state = p.state + p.inc;               // Lcg128Xsl64::from_state_incr
-    p.state = p.state * mul() + p.inc;
-    return p;
-  }
-  uint64_t next_u64() {
-    state = state * mul() + inc;
-    const uint32_t rot = (uint32_t)(state >> 122);
-    const uint64_t x = (uint64_t)(state >> 64) ^ (uint64_t)state;
-    return (x >> rot) | (x << ((64 - rot) & 63));
-  }
-  uint64_t below(uint64_t range) {           // rand 0.8 gen_range(0..range): widening multiply, rejection zone
-    if (range == 0) return next_u64();
-    const uint64_t zone = (range << __builtin_clzll(range)) - 1;
-    for (;;) {
-      const unsigned __int128 m = (unsigned __int128)next_u64() * range;
-      if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
-    }
-  }
-};
 struct Trial { int joint, a, b; };
 }  // namespace
 

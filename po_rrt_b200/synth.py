@@ -17,8 +17,10 @@ def door_map(size=8192, n_rects=4096, side_lo=16, side_hi=112, n_zones=6, seed=1
     zones = np.full((size, size), 255, np.uint8)
     zw, zh = max(2, int(zone_w * s)), max(4, int(zone_h * s))
     cols = 3
+    rows = (n_zones + cols - 1) // cols
     for z in range(n_zones):
-        ci = int((0.25 + 0.5 * (z // cols)) * size)
+        # two rows of three (the c5 layout); more zones: as many rows as needed, still >= size/8 apart
+        ci = int((0.25 + 0.5 * (z // cols)) * size) if rows <= 2 else int((z // cols + 0.25) / rows * size)
         cj = int((0.2 + 0.3 * (z % cols)) * size)
         occ[ci:ci + zh, cj:cj + zw] = 128
         zones[ci:ci + zh, cj:cj + zw] = z

@@ -68,10 +68,25 @@ def test_product_does_not_touch_oracle():
                 assert "pyoracle" not in text and "liboracle" not in text and "porrt_oracle" not in text, f
 
 
-def test_integration_doc_lists_every_symbol():
-    """INTEGRATION.md's Rust `extern "C"` block binds exactly what include/porrt_b200.h declares"""
-    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
-    hdr = open(os.path.join(ROOT, "include", "porrt_b200.h")).read()
-    syms = sorted(set(re.findall(r"\b(porrt_[a-z0-9_]+)\s*\(", hdr)))
-    missing = [s for s in syms if ("pub fn %s(" % s) not in doc]
+def test_rust_ffi_is_generated_from_header():
+    """integration/rust/src/b200_ffi.rs (the crate-side `extern "C"` block) binds exactly what
+    include/porrt_b200.h declares and is what scripts/gen_rust_ffi.py produces from the header today"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gen_rust_ffi
+    text = open(gen_rust_ffi.OUT).read()
+    assert text == gen_rust_ffi.render(), "stale: run python scripts/gen_rust_ffi.py"
+    missing = [s for s in _declared_symbols() if ("pub fn %s(" % s) not in text]
     assert not missing, missing
+
+
+def test_rust_integration_files_use_only_declared_symbols():
+    """the hand-written Rust half (feature-gated impls, planner-level swaps) calls nothing the header does not declare"""
+    rust_dir = os.path.join(ROOT, "integration", "rust")
+    declared = set(_declared_symbols())
+    used = set()
+    for dirpath, _, files in os.walk(rust_dir):
+        for f in files:
+            if f.endswith(".rs") and f != "b200_ffi.rs":
+                used |= set(re.findall(r"\b(porrt_[a-z0-9_]+)\s*\(", open(os.path.join(dirpath, f)).read()))
+    assert used <= declared, sorted(used - declared)

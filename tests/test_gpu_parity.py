@@ -30,6 +30,9 @@ def _check_edges(omap, pmap, a, b):
     wv = pmap.world_validities_words()
     exp_masks = np.where((want >= 0)[:, None], wv[np.clip(want, 0, None)], 0)
     np.testing.assert_array_equal(masks, exp_masks)
+    got8 = pmap.transition_validator(a, b, compact=True)          # one signed byte per edge, same codes
+    assert got8.dtype == np.int8
+    np.testing.assert_array_equal(got8.astype(np.int64), want)
     return want
 
 
@@ -92,27 +95,38 @@ def test_door_edges_panics(ctx):
     assert (sv == O.PANIC_OOB).any() and (sv == O.PANIC_ZONE_UNWRAP).any()
 
 
-@pytest.mark.parametrize("variant", ["9", "3", "1"])
-def test_edge_kernel_variants(ctx, variant, monkeypatch):
-    """the other edge kernels kept in the library (9: lane per edge over sorted groups, 3: class bytes in global
-    memory = the fallback for maps too large for the shared-memory plane, 1: byte-grid warp walk) give the same bits"""
-    monkeypatch.setenv("PORRT_EDGE_VARIANT", variant)       # read at map upload
-    occ, zones = util.small_door_map(512, 3)
+def test_edge_large_map_path(ctx):
+    """maps whose class plane does not fit in shared memory (> ~14000^2 px) take map.cu's kernel (class bytes in global
+    memory); forced here on small maps, it must give the same bits"""
+    ctx.set_option(P.OPT_FORCE_LARGE_MAP_PATH, 1)
+    try:
+        occ, zones = util.small_door_map(512, 3)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+        a, b = synth.edges(120_000, seed=31, max_len=0.4)
+        _check_edges(omap, pmap, a, b)
+        a, b = synth.edges(20_000, seed=32, max_len=2.5)        # edges across the whole map (> 32 strips)
+        _check_edges(omap, pmap, a, b)
+        rng = np.random.default_rng(33)
+        a = rng.uniform(-1.1, 1.1, (40_000, 2)); b = a + rng.uniform(-0.3, 0.3, (40_000, 2))
+        _check_edges(omap, pmap, a, b)                          # some end points outside the map
+        occ, zones = synth.shelf_map(400, n_rects=20, n_zones=5, seed=6)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.6)
+        a, b = synth.edges(60_000, seed=34, max_len=0.5)
+        _check_edges(omap, pmap, a, b)
+    finally:
+        ctx.set_option(P.OPT_FORCE_LARGE_MAP_PATH, 0)
+
+
+def test_edge_large_map_path_real(ctx):
+    """a 15008^2 map: the class plane (220 KiB + guards) no longer leaves room for the warps' queues -> large-map kernel"""
+    size = 15008
+    occ, zones = synth.door_map(size=size, n_rects=2048, n_zones=3, seed=17)
     omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
-    a, b = synth.edges(120_000, seed=31, max_len=0.4)
-    _check_edges(omap, pmap, a, b)
-    a, b = synth.edges(20_000, seed=32, max_len=2.5)        # edges across the whole map (> 32 strips)
-    _check_edges(omap, pmap, a, b)
-    rng = np.random.default_rng(33)
-    a = rng.uniform(-1.1, 1.1, (40_000, 2)); b = a + rng.uniform(-0.3, 0.3, (40_000, 2))
-    _check_edges(omap, pmap, a, b)                          # some end points outside the map
-    occ, zones = synth.shelf_map(400, n_rects=20, n_zones=5, seed=6)
-    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.6)
-    a, b = synth.edges(60_000, seed=34, max_len=0.5)
-    _check_edges(omap, pmap, a, b)
-    monkeypatch.delenv("PORRT_EDGE_VARIANT")
+    a, b = synth.edges(300_000, seed=35, max_len=0.05)
+    want = _check_edges(omap, pmap, a, b)
+    assert (want == -1).any() and (want >= 0).any()
     occ, zones = util.small_door_map(256, 2)
-    util.make_pair(ctx, occ, zones, P.DOOR, 0.3)            # leave the ctx on the default kernel
+    util.make_pair(ctx, occ, zones, P.DOOR, 0.3)                # release the big grids' successor state
 
 
 def test_edges_odd_map_sizes(ctx):
@@ -178,6 +192,44 @@ def test_edges_host_pipeline_multi_chunk(ctx):
     omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
     a, b = synth.edges(3_500_000, seed=21, max_len=0.05)
     _check_edges(omap, pmap, a, b)
+
+
+@pytest.mark.parametrize("n", [2_150_001, 4_194_312 + 8, 2_150_000])
+def test_edges_host_pipeline_odd_chunk_sizes(ctx, n):
+    """chunk sizes that are not multiples of 4 edges: every array of a device slot must still be 16-byte aligned (the kernels
+    read endpoints as 16-byte vectors); pageable and pinned buffers, with and without masks, coordinates and node ids"""
+    import torch
+    occ, zones = util.small_door_map(512, 3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    a, b = synth.edges(n, seed=22, max_len=0.03)
+    want = omap.edge_validity(a, b)
+    wv = pmap.world_validities_words()
+    exp_masks = np.where((want >= 0)[:, None], wv[np.clip(want, 0, None)], 0)
+    got, masks = pmap.transition_validator(a, b, want_masks=True)                      # pageable, masks
+    np.testing.assert_array_equal(got.astype(np.int64), want)
+    np.testing.assert_array_equal(masks, exp_masks)
+    np.testing.assert_array_equal(pmap.transition_validator(a, b).astype(np.int64), want)   # pageable, no masks
+    pa, pb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    pv = torch.empty(n, dtype=torch.int32).pin_memory()
+    pm = torch.empty((n, 1), dtype=torch.int64).pin_memory()
+    c = ctx
+    c.check(c.lib.porrt_edge_validity(c.h, pa.data_ptr(), pb.data_ptr(), n, pv.data_ptr(), pm.data_ptr()))      # pinned, masks
+    np.testing.assert_array_equal(pv.numpy().astype(np.int64), want)
+    np.testing.assert_array_equal(pm.numpy().view(np.uint64), exp_masks)
+    pv.zero_()
+    c.check(c.lib.porrt_edge_validity(c.h, pa.data_ptr(), pb.data_ptr(), n, pv.data_ptr(), None))               # pinned, no masks
+    np.testing.assert_array_equal(pv.numpy().astype(np.int64), want)
+    p8 = torch.empty(n, dtype=torch.int8).pin_memory()
+    c.check(c.lib.porrt_edge_validity_i8(c.h, pa.data_ptr(), pb.data_ptr(), n, p8.data_ptr()))                  # pinned, bytes
+    np.testing.assert_array_equal(p8.numpy().astype(np.int64), want)
+    # the same edges as node pairs and as an adjacency over the resident vertex set
+    tree = P.KdTree(ctx, np.concatenate([a, b]), cell_size=0.02)
+    fi, ti = np.arange(n, dtype=np.int32), np.arange(n, 2 * n, dtype=np.int32)
+    got, masks = pmap.transition_validator_nodes(fi, ti, want_masks=True)
+    np.testing.assert_array_equal(got.astype(np.int64), want)
+    np.testing.assert_array_equal(masks, exp_masks)
+    np.testing.assert_array_equal(pmap.transition_validator_nodes(fi, ti, compact=True).astype(np.int64), want)
+    del tree
 
 
 def test_reachable_belief_states(ctx):
@@ -479,6 +531,17 @@ def test_qmdp_costs_shelf_config2(ctx):
     got, sweeps = P.dijkstra_worlds(ctx, rp, col, xy, nvid, pmap.world_validities_words(), finals)
     np.testing.assert_array_equal(got, want)   # bit-exact f64
     assert np.isfinite(want).any()
+    # the extracted QMDP policy (qmdp_policy_extractor.rs:176-199: react_qmdp(&[-0.8, -0.8], &vec![0.5, 0.5], 0.2)): start node by
+    # the device 1-NN, walk over the device-computed cost table; common path and per-world paths as in the reference
+    tree = P.KdTree(ctx, xy)
+    for start, belief, horizon in (((-0.8, -0.8), [0.5, 0.5], 0.2), ((-0.8, -0.8), [0.9, 0.1], 1.0), ((0.2, 0.1), [0.3, 0.7], 0.5)):
+        ids, _, ties = tree.nearest_neighbor([start])
+        assert ties[0] == 1 and ids[0] == pto.kdtree.nearest_neighbor(start)
+        paths, n_common = P.react_qmdp(ctx, rp, col, xy, got, int(ids[0]), belief, horizon)
+        want_paths = pto.react_qmdp(start, belief, horizon)
+        for w in range(2):
+            np.testing.assert_array_equal(xy[paths[w]], want_paths[w])
+        assert n_common >= 1 and len(paths[0]) > n_common
 
 
 def test_qmdp_costs_door(ctx):
@@ -533,13 +596,15 @@ def test_belief_planning_shelf_config2(ctx):
 
 
 def test_belief_planning_shelf_8_goals_config3(ctx):
-    """BASELINE config 3 shape (8 goal zones, B = 255 reachable beliefs) on a stand-in map, reduced iteration count"""
+    """BASELINE config 3 shape (8 goal zones, B = 255 reachable beliefs) on a stand-in map, at the reference's literal
+    n_iter_min = 5000 (main.rs:104, grow_graph(start (0,-1)-like, 0.1, 2.0, 5000, 100000), main.rs:757-799)"""
     Z = 8
     occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
     omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
     zp = omap.zone_positions()
     goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
-    pto = _grow_pto(omap, (0.0, -0.9), goals, 0.1, 2.0, 1500)
+    pto = _grow_pto(omap, (0.0, -0.9), goals, 0.1, 2.0, 5000)
+    assert pto.n_it() >= 5000
     plan, want, typ = _belief_compare(ctx, omap, pmap, pto, [1.0 / Z] * Z)
     assert len(plan.beliefs) == 255 and np.isfinite(want[0]) and plan.policy_leaf.sum() == Z
     # QMDP on the same roadmap: 8 world-view dijkstras at once
@@ -582,6 +647,167 @@ def test_belief_planning_12_goals_config4_full_size(ctx):
     assert plan.expected_cost == root and int(plan.policy_leaf.sum()) == Z
     leaf_worlds = sorted(int(np.argmax(plan.beliefs[b])) for b in plan.policy_belief[plan.policy_leaf != 0])
     assert leaf_worlds == list(range(Z))
+
+
+def _hand_built_roadmap(omap, n_nodes, radius, goal_states, goal_masks, seed):
+    """a small roadmap over `omap` assembled by hand in the oracle's PTO (graph + reachability): random valid states + the goal
+    states, bi-edges between all pairs within `radius` whose transition the oracle validates; finals = the goal nodes"""
+    rng = np.random.default_rng(seed)
+    pts = []
+    while len(pts) < n_nodes:
+        c = rng.uniform(-0.95, 0.95, (4 * n_nodes, 2))
+        pts += [p for p, v in zip(c, omap.state_validity(c)) if v >= 0][: n_nodes - len(pts)]
+    for g in goal_states:                                  # the nearest valid state left of / around the goal position
+        cand = np.array([[g[0] - dx, g[1] + dy] for dx in (0.0, 0.03, 0.06, 0.09, -0.03) for dy in (0.0, 0.03, -0.03)])
+        ok = np.nonzero(omap.state_validity(cand) >= 0)[0]
+        assert len(ok), g
+        pts.append(cand[ok[0]])
+    pts = np.array(pts)
+    vids = omap.state_validity(pts)
+    assert (vids >= 0).all()
+    pto = O.PTO(omap, util.LOW, util.UP)
+    ones = [1] * omap.n_worlds
+    for p, v in zip(pts, vids):
+        pto.graph.add_node([float(p[0]), float(p[1])], int(v))
+    pto.reach.set_root(ones)
+    for _ in range(len(pts) - 1):
+        pto.reach.add_node(ones)
+    d = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=2)
+    ii, jj = np.nonzero(np.triu(d <= radius, 1))
+    ev = omap.edge_validity(pts[ii], pts[jj])
+    for a, b, v in zip(ii, jj, ev):
+        if v >= 0:
+            pto.graph.add_bi_edge(int(a), int(b), int(v))
+    for k, m in enumerate(goal_masks):
+        pto.reach.add_final_node(n_nodes + k, list(m))
+    return pto
+
+
+def test_belief_planning_12_goals_full_table_vs_oracle(ctx):
+    """BASELINE config 4's belief space (12 goal zones, B = 4095 reachable beliefs) on a roadmap small enough for the oracle's
+    MATERIALISED belief graph (pto.rs:185-259): every one of the V x 4095 expected costs, every node type and the whole policy
+    must equal the reference algorithm's"""
+    Z = 12
+    occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.3)
+    zp = omap.zone_positions()
+    goal_states = [(float(zp[z][0]) - 0.08, float(zp[z][1])) for z in range(Z)]
+    goal_masks = [[1 if k == z else 0 for k in range(Z)] for z in range(Z)]
+    pto = _hand_built_roadmap(omap, 280, 0.3, goal_states, goal_masks, seed=77)
+    plan, want, typ = _belief_compare(ctx, omap, pmap, pto, [1.0 / Z] * Z)
+    assert plan.beliefs.shape == (4095, Z) and plan.dist.shape == (292, 4095)
+    assert np.isfinite(want[0]) and int(plan.policy_leaf.sum()) == Z
+    assert (typ == O.OBSERVATION).sum() > 1000
+
+
+def test_seven_door_zones_two_mask_words(ctx):
+    """7 door zones = 128 worlds: world masks are two u64 words wide (mask_words = 2) in the edge kernel's outputs, the world
+    validity table, the per-world SSSP (plan_qmdp) and the reachability filter of the nearest-neighbour search"""
+    occ, zones = synth.door_map(size=1024, n_rects=1500, n_zones=7, seed=23)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    assert (pmap.n_zones, pmap.n_worlds(), pmap.n_validities, pmap.mask_words) == (7, 128, 8, 2)
+    np.testing.assert_array_equal(pmap.world_validities(), omap.world_validities())
+    a, b = synth.edges(400_000, seed=24, max_len=0.15)
+    want = _check_edges(omap, pmap, a, b)                      # ids + [n, 2]-word masks
+    assert all((want == z).any() for z in range(7)) and (want == 7).any() and (want == -1).any()
+    ctx.set_option(P.OPT_FORCE_LARGE_MAP_PATH, 1)
+    try:
+        _check_edges(omap, pmap, a[:100_000], b[:100_000])
+    finally:
+        ctx.set_option(P.OPT_FORCE_LARGE_MAP_PATH, 0)
+    # node ids + masks through the indexed entry point
+    tree = P.KdTree(ctx, np.concatenate([a[:50_000], b[:50_000]]), cell_size=0.02)
+    fi, ti = np.arange(50_000, dtype=np.int32), np.arange(50_000, 100_000, dtype=np.int32)
+    got, masks = pmap.transition_validator_nodes(fi, ti, want_masks=True)
+    wv = pmap.world_validities_words()
+    np.testing.assert_array_equal(got.astype(np.int64), want[:50_000])
+    np.testing.assert_array_equal(masks, np.where((want[:50_000] >= 0)[:, None], wv[np.clip(want[:50_000], 0, None)], 0))
+    # plan_qmdp over 128 world views of a PTO roadmap (goal valid in every world)
+    pto = _grow_pto(omap, (-0.8, -0.8), [((0.8, 0.8), [1] * 128)], 0.05, 5.0, 2500)
+    want_costs = pto.plan_qmdp()
+    xy, nvid, rp, col, ev = pto.graph.export(0)
+    finals = [pto.reach.get_final_nodes_for_world(w) for w in range(128)]
+    got_costs, _ = P.dijkstra_worlds(ctx, rp, col, xy, nvid, wv, finals)
+    np.testing.assert_array_equal(got_costs, want_costs)
+    assert len({want_costs[w].tobytes() for w in range(128)}) > 1      # the worlds really differ
+    # filtered 1-NN / radius search with 128-bit reachability masks (pto.rs:74-77), worlds on both sides of bit 64
+    reach = pto.reach.all(len(xy))                                     # [V, 128] bits
+    rw = P.words_from_bits(reach)
+    assert rw.shape == (len(xy), 2)
+    rng = np.random.default_rng(25)
+    q = rng.uniform(-1, 1, (4000, 2))
+    world = rng.integers(0, 128, 4000).astype(np.uint32)
+    tree = P.KdTree(ctx, xy, cell_size=0.05)
+    ids, dist, ties = tree.nearest_neighbor(q, reach_mask=rw, world=world)
+    d = np.linalg.norm(xy[None, :, :] - q[:, None, :], axis=2)
+    d_f = np.where(reach[:, world].T != 0, d, np.inf)
+    best = d_f.min(1)
+    for k in range(len(q)):
+        if np.isfinite(best[k]):
+            assert ids[k] >= 0 and reach[ids[k], world[k]] and abs(dist[k] - best[k]) <= 1e-12, k
+        else:
+            assert ids[k] == -1
+    offs, rid = tree.nearest_neighbors(q, 0.12, reach_mask=rw, world=world)
+    for k in range(0, len(q), 7):
+        exp = np.nonzero((d[k] <= 0.12 - 1e-12) & (reach[:, world[k]] != 0))[0]
+        got_k = rid[offs[k]:offs[k + 1]]
+        assert set(exp) <= set(got_k) and all(reach[j, world[k]] for j in got_k) and (d[k, got_k] <= 0.12 + 1e-12).all()
+    # the belief space of 7 doors: hash() (common.rs:352-355) wraps from 20 worlds on, reachable_belief_states silently merges
+    # colliding beliefs (map_io.rs:515-546) and conditional_dijkstra then panics on the mangled successor table; the product
+    # must follow the reference into the same panic, not compute something else
+    small = _grow_pto(omap, (0.6, 0.6), [((0.8, 0.8), [1] * 128)], 0.05, 5.0, 200)        # 184 nodes
+    small.build_belief_graph([1.0 / 128] * 128)
+    assert len(small.beliefs()) == 1441                                # 3^7 = 2187 without the collisions
+    with pytest.raises(RuntimeError):
+        small.compute_expected_costs_to_goals()
+    xy, nvid, rp, col, ev = small.graph.export(0)
+    fin_ids, fin_bits = small.reach.finals()
+    np.testing.assert_array_equal(pmap.reachable_belief_states([1.0 / 128] * 128), small.beliefs())
+    with pytest.raises(P.PorrtError) as ei:
+        P.plan_belief_space(pmap, rp, col, ev, xy, nvid, [1.0 / 128] * 128, fin_ids, P.words_from_bits(fin_bits))
+    assert ei.value.code == 5
+
+
+def test_c5_full_shape_every_edge(ctx):
+    """BASELINE config 5 at full shape: the synthetic 8192^2 map, 6 door zones = 64 worlds, 2^24 edges from each of two seeds,
+    EVERY edge against the oracle (OpenMP over edges), through coordinates, node ids (int32 and byte results) and the adjacency
+    entry point; states and visibility on the same map"""
+    import os
+    occ, zones = synth.door_map(size=8192, n_zones=6, seed=1)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    assert pmap.n_worlds() == 64 and pmap.mask_words == 1
+    threads = max(1, len(os.sched_getaffinity(0)))
+    wv = pmap.world_validities_words()
+    E = 1 << 24
+    for seed in (2, 3):
+        a, b = synth.edges(E, seed=seed)
+        want, _ = omap.edge_validity_timed(a, b, threads)
+        got, masks = pmap.transition_validator(a, b, want_masks=True)
+        np.testing.assert_array_equal(got, want.astype(np.int32))
+        np.testing.assert_array_equal(masks[:, 0], np.where(want >= 0, wv[np.clip(want, 0, None), 0], 0))
+        del masks
+        if seed == 2:
+            assert all((want == z).any() for z in range(6)) and (want == 6).any() and (want == -1).any()
+            tree = P.KdTree(ctx, np.concatenate([a, b]), cell_size=0.01)
+            fi, ti = np.arange(E, dtype=np.int32), np.arange(E, 2 * E, dtype=np.int32)
+            np.testing.assert_array_equal(pmap.transition_validator_nodes(fi, ti), want.astype(np.int32))
+            np.testing.assert_array_equal(pmap.transition_validator_nodes(fi, ti, compact=True), want.astype(np.int8))
+            # the same batch as an adjacency: row r (a "new node" b_r = vertex E + r) lists its one neighbour a_r
+            rows = 1 << 20
+            rp = np.zeros(2 * E + 1, np.int64)
+            rp[E + 1:E + rows + 1] = np.arange(1, rows + 1)
+            rp[E + rows + 1:] = rows
+            np.testing.assert_array_equal(pmap.transition_validator_adjacency(rp, fi[:rows]), want[:rows].astype(np.int8))
+            del tree
+            pts = a[:2_000_000]
+            np.testing.assert_array_equal(pmap.state_validity(pts).astype(np.int64), omap.state_validity(pts))
+            wm, wp = omap.visible_zones(pts[:300_000])
+            gm, gs = pmap.visible_zones(pts[:300_000])
+            np.testing.assert_array_equal(gm, wm)
+            np.testing.assert_array_equal(gs.astype(np.int64), wp)
+            assert (wm != 0).any()
+    occ, zones = util.small_door_map(256, 2)
+    util.make_pair(ctx, occ, zones, P.DOOR, 0.3)                # drop the big map
 
 
 def test_build_belief_graph_mock(ctx):
