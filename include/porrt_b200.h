@@ -71,6 +71,10 @@ const char* porrt_version(void);
 /* device time (ms, CUDA events) of the phases of the last host-buffer NN call on this ctx; see the call's docs */
 int32_t porrt_ctx_last_phase_ms(porrt_ctx* ctx, double* out_ms, int32_t cap, int32_t* out_n);
 
+/* measurement aid (bench.py's L2 roofline denominator): GB/s of random independent 32-byte sector reads over a
+ * buffer of buffer_bytes (<= 0: 64 MiB) that stays in the 126 MB L2 */
+int32_t porrt_measure_l2_gather(porrt_ctx* ctx, int64_t buffer_bytes, double* out_gbs);
+
 /* ------------------------------------------------------------------ maps
  * Replaces Map::open + add_zones / init_without_zones (map_io.rs:82-145) and MapShelfDomain::open + add_zones
  * (map_shelves_io.rs:80-148) for already-decoded 8-bit gray images (row-major, row 0 = top).

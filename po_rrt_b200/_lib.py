@@ -23,6 +23,7 @@ SIGNATURES = {
     "porrt_last_error": (C.c_char_p, [vp]),
     "porrt_ctx_launch_count": (i64, [vp]),
     "porrt_ctx_last_phase_ms": (i32, [vp, vp, i32, pp(i32)]),
+    "porrt_measure_l2_gather": (i32, [vp, i64, pp(f64)]),
     "porrt_map_upload": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, f64]),
     "porrt_map_info": (i32, [vp, pp(i32), pp(i32), pp(i32), pp(i32)]),
     "porrt_map_zone_positions": (i32, [vp, vp]),
