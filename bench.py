@@ -57,35 +57,74 @@ def make_inputs(args, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons / power DURING the timed region (B200_PROFILING.md clocks line), polled in-process through
+    NVML every ~2 ms from before the warm-up on, so that even a 14 ms timed region holds several samples; falls back to an
+    `nvidia-smi -lms` child when NVML is not importable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []          # (t, sm_mhz, max_mhz, power_w, [4 reason flags])
+        self.stop_flag = False
+        self.p = None
+        self.source = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
             self.t.start()
         except Exception:
-            self.p = None
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+                self.t = threading.Thread(target=self._read_smi, daemon=True)
+                self.t.start()
+            except Exception:
+                self.p = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nv
+        masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.perf_counter(), sm, self.max_mhz, pw, [bool(r & m) for m in masks]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
         for line in self.p.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]), float(r[2]), [x.lower().startswith("active") for x in r[3:7]]))
+            except Exception:
+                pass
 
     def stop(self, t0, t1):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
-        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in rows for k in range(4) if len(r) >= 7 and r[3 + k].lower().startswith("active")})
-        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
-                "power_w_max": max(pw) if pw else None, "samples": len(rows)}
+        self.stop_flag = True
+        if self.p:
+            self.p.terminate()
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        in_region = len(rows)
+        if not rows:    # nothing landed inside (should not happen with the 2 ms poll): nearest samples around the region
+            rows = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:4]
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted({self.NAMES[k] for r in rows for k in range(4) if r[4][k]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": rows[0][2] if rows else None, "reasons": reasons,
+                "power_w_max": max((r[3] for r in rows), default=None), "samples": in_region, "samples_total": len(self.rows),
+                "source": self.source}
 
 
 def cpu_baseline(args, occ, zones, a, b, all_threads=True):
@@ -113,9 +152,9 @@ def run_reference(args):
     from oracle import pyoracle as O
     omap = O.GridMap(occ, zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
     threads = host_threads()
-    n = min(args.cpu_sample, len(a))
-    sa, sb = np.ascontiguousarray(a[:n]), np.ascontiguousarray(b[:n])
-    for _ in range(max(1, args.warmup)):
+    n = len(a)        # a step of the reference arm is the b200 arm's step: all edges_per_gpu_per_step edges (about 1 s on 16 cores)
+    sa, sb = a, b
+    for _ in range(max(1, min(args.warmup, 2))):
         omap.edge_validity_timed(sa[: n // 4], sb[: n // 4], threads)
     t = 0.0
     for _ in range(args.steps):
@@ -126,8 +165,8 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "each step = %d edges of the workload through the oracle C++ restatement with OpenMP "
-                                       "(reference Rust crate not buildable here: no cargo/rustc)" % n},
+                             "sample": "each step = all %d edges of the b200 arm's step through the oracle C++ restatement with OpenMP "
+                                       "over edges (reference Rust crate not buildable here: no cargo/rustc; it is single-threaded)" % n},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -201,6 +240,26 @@ def side_measurements(ctx, pmap, args):
                     best = (t1 - t0, [round(float(x), 3) for x in prm.phase_ms], int(len(prm.col)))
             ex["prm_build"]["V%d" % n_nodes] = {"ms": 1e3 * best[0], "directed_edges": best[2], "candidate_edge_checks": int(best[1][7]),
                                                 "phase_ms[radii,bin,radius,kd_rank,order,edges,csr]": best[1][:7]}
+        # re-validating a whole roadmap (e.g. after the map changed): its adjacency goes through porrt_edge_validity_csr_i8,
+        # 4 B per edge + 8 B per node in, 1 B per edge out; every edge of a PRM is valid, so every pixel is looked at
+        try:
+            n_nodes = 1_000_000
+            prm = P.PRM(pmap)
+            prm.grow_graph(pin_pts[:n_nodes], 0.1, 2.0, col_out=pin_col, row_ptr_out=pin_row)
+            n_e = int(pin_row[n_nodes])
+            pin_v8 = torch.empty(n_e, dtype=torch.int8).pin_memory().numpy()
+            tree = P.KdTree(ctx, pin_pts[:n_nodes], cell_size=r)
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter(); pmap.transition_validator_adjacency(pin_row[:n_nodes + 1], pin_col[:n_e], vid_out=pin_v8); t1 = time.perf_counter()
+                best = t1 - t0 if best is None else min(best, t1 - t0)
+            ex["roadmap_revalidation_e2e"] = {"nodes": n_nodes, "directed_edges": n_e, "ms": 1e3 * best, "edges_per_s": n_e / best,
+                                              "edge_world_checks_per_s": n_e * N_WORLDS / best, "all_valid": bool((pin_v8 >= 0).all()),
+                                              "h2d_bytes": 4 * n_e + 8 * (n_nodes + 1), "d2h_bytes": n_e,
+                                              "call": "porrt_edge_validity_csr_i8 (adjacency in, validity ids out)"}
+            del tree
+        except Exception as e:
+            ex["roadmap_revalidation_e2e"] = {"error": repr(e)}
         omap = O.GridMap(pmap.occ, pmap.zones, [-1.0, -1.0], [1.0, 1.0], O.DOOR, 0.3)
         for n_nodes in (10_000, 100_000):
             oprm = O.PRM(omap, [-1.0, -1.0], [1.0, 1.0], seed=0)
@@ -428,7 +487,7 @@ def main():
     import torch
     import torch.distributed as dist
     import po_rrt_b200 as P
-    from po_rrt_b200.api import _p
+    from po_rrt_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -495,6 +554,7 @@ def main():
     ai = torch.floor((args.map_size - 1) - (d_a[:, 1] + 1.0) * ppm); aj = torch.floor((d_a[:, 0] + 1.0) * ppm)
     bi = torch.floor((args.map_size - 1) - (d_b[:, 1] + 1.0) * ppm); bj = torch.floor((d_b[:, 0] + 1.0) * ppm)
     n_px = float((torch.maximum((ai - bi).abs(), (aj - bj).abs()) + 1).sum().item())
+    del ai, aj, bi, bj
     alg_bytes = 44.0 * E + n_px
     peaks = {}
     try:
@@ -502,42 +562,112 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this command
+    kernel_s = ms / args.steps * 1e-3
+    achieved = alg_bytes / kernel_s / 1e9
+    traffic, pipes = None, None  # dram bytes / pipe utilisation of one launch, from the committed ncu capture of this command
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "edge_traffic.json")))
         if tr["edges_per_launch"] == E and args.map_size == 8192:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            pipes = tr.get("pipes")
     except Exception:
         pass
+    # the L2-resident gather rate ("an L2 peak the builder must measure"): random independent 32-byte sector reads
+    # over a 64 MiB buffer, measured here and now on this GPU
+    l2_peak = C.c_double()
+    ctx.check(lib.porrt_measure_l2_gather(h, 64 << 20, C.byref(l2_peak)))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_launch": alg_bytes, "mean_pixels_per_edge": n_px / E, "kernel": {"0": "edge_validity_v3_kernel<DOOR,false>", "9": "edge_validity_v4_kernel<DOOR,false>"}.get(os.environ.get("PORRT_EDGE_VARIANT", "0"), "edge_validity_v2_kernel<DOOR>"),
-                "bound_note": "algorithmic bytes / kernel time against the HBM peak (SURVEY 8(d)); the kernel itself is bound by integer issue (ALU pipe 74 %), DRAM traffic ~ the 44 B/edge streams",
-                "kernel_ms": ms / args.steps}
+                "algorithmic_bytes_per_launch": alg_bytes, "mean_pixels_per_edge": n_px / E,
+                "kernel": "edge_validity_v3_kernel<DOOR,false>",
+                "hbm_streams": {"achieved": 44.0 * E / kernel_s / 1e9, "frac": 44.0 * E / kernel_s / 1e9 / peak,
+                                "note": "the 32 B in + 12 B out per edge that actually cross HBM"},
+                "l2": {"achieved": n_px / kernel_s / 1e9, "peak": l2_peak.value, "unit": "GB/s", "frac": n_px / kernel_s / 1e9 / l2_peak.value,
+                       "note": "pixel bytes (1 B per line pixel) per second against the measured rate of random 32-byte sector reads "
+                               "from a 64 MiB L2-resident buffer (porrt_measure_l2_gather)"},
+                "bound_note": "algorithmic bytes / kernel time against the HBM peak (SURVEY 8(d)); measured DRAM traffic ~ the 44 B/edge "
+                              "streams: the pixels are served by the class plane in shared memory and L2-resident bitmaps, the kernel "
+                              "is bound by integer issue (profiles/: ncu pipe utilisation)",
+                "ncu_pipes": pipes, "kernel_ms": ms / args.steps}
 
-    # ---- end-to-end arm: host (pinned) buffers through the C ABI, H2D + kernel + D2H inside the timed region
+    # ---- end-to-end arms: HOST (pinned) buffers through the C ABI, H2D + kernel + D2H inside the timed region.
+    # The headline `e2e` is the call the planners make -- transition_validator(&PTONode, &PTONode) -> Option<usize>
+    # (pto_graph.rs:133-139, call sites pto.rs:105 / prm.rs:93) batched: the nodes' states are resident on the device like a
+    # roadmap's vertices (uploaded once, outside the timed region), an edge is a pair of node ids in and one validity id out.
+    # `e2e_variants` holds the other shapes of the same call, down to raw coordinates with per-world bitvecs out.
     ctx.set_stream(None)
     h_a, h_b = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
     h_vid = torch.empty(E, dtype=torch.int32).pin_memory()
     h_mask = torch.empty(E, dtype=torch.int64).pin_memory()
+    h_vid8 = torch.empty(E, dtype=torch.int8).pin_memory()
+    h_fi = torch.arange(0, E, dtype=torch.int32).pin_memory()
+    h_ti = torch.arange(E, 2 * E, dtype=torch.int32).pin_memory()
+    want_vid = d_vid.cpu()
+    want_mask = d_mask.cpu()
+    del d_a, d_b, d_vid, d_mask
+    torch.cuda.empty_cache()
+    tree = P.KdTree(ctx, np.concatenate([a, b]), cell_size=0.01)        # the vertex set: 2E node states, resident
 
-    def step_e2e():
-        ctx.check(lib.porrt_edge_validity(h, h_a.data_ptr(), h_b.data_ptr(), E, h_vid.data_ptr(), h_mask.data_ptr()))
+    def run_e2e(call, check):
+        call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        check()
+        return E * world * N_WORLDS * e2e_steps / float(t.item())
+
+    def chk32():
+        assert torch.equal(h_vid, want_vid), "e2e result differs from the device-resident one"
+
+    def chk8():
+        assert torch.equal(h_vid8.to(torch.int32), want_vid), "e2e byte result differs from the device-resident one"
+
+    def chk32m():
+        chk32()
+        assert torch.equal(h_mask, want_mask)
 
     e2e_steps = max(2, min(args.steps, 5))
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    variants = {}
+    specs = [("node_ids_in__validity_id_out", 8, 1, chk8,
+              lambda: ctx.check(lib.porrt_edge_validity_indexed_i8(h, h_fi.data_ptr(), h_ti.data_ptr(), E, h_vid8.data_ptr()))),
+             ("coordinates_in__id_and_world_mask_out", 32, 12, chk32m,
+              lambda: ctx.check(lib.porrt_edge_validity(h, h_a.data_ptr(), h_b.data_ptr(), E, h_vid.data_ptr(), h_mask.data_ptr()))),
+             ("coordinates_in__validity_id_out", 32, 1, chk8,
+              lambda: ctx.check(lib.porrt_edge_validity_i8(h, h_a.data_ptr(), h_b.data_ptr(), E, h_vid8.data_ptr()))),
+             ("node_ids_in__id_and_world_mask_out", 8, 12, chk32m,
+              lambda: ctx.check(lib.porrt_edge_validity_indexed(h, h_fi.data_ptr(), h_ti.data_ptr(), E, h_vid.data_ptr(), h_mask.data_ptr())))]
+    if args.no_extras:
+        specs = specs[:2]
+    for name, bi_, bo_, check, call in specs:
+        h_vid.zero_(); h_vid8.zero_(); h_mask.zero_()
+        v = run_e2e(call, check)
+        variants[name] = {"value": v, "unit": UNIT, "edges_per_s": v / N_WORLDS, "h2d_bytes_per_step": bi_ * E, "d2h_bytes_per_step": bo_ * E}
+    e2e_main = variants["node_ids_in__validity_id_out"]
+    e2e_value = e2e_main["value"]
+
+    # N > 1: how the end-to-end path scales on this host -- the same call by rank 0 ALONE (the others wait), against all ranks at once
+    e2e_scaling = None
     if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = E * world * N_WORLDS * e2e_steps / float(t_e2e.item())
-    # the e2e result must equal the device-resident one
-    assert torch.equal(h_vid, d_vid.cpu()) and torch.equal(h_mask, d_mask.cpu())
+        solo = None
+        dist.barrier()
+        if rank == 0:
+            specs[0][4]()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                specs[0][4]()
+            torch.cuda.synchronize()
+            solo = E * N_WORLDS * e2e_steps / (time.perf_counter() - t0)
+        dist.barrier()
+        if rank == 0:
+            e2e_scaling = {"one_rank_alone": solo, "all_ranks_together": e2e_value, "efficiency": e2e_value / (world * solo),
+                           "note": "same box, same call (node ids in, validity id out); the ranks share the host's PCIe root / memory"}
+    del tree
 
     multi = None
     if world > 1 and not args.no_extras:
@@ -546,58 +676,62 @@ def main():
         except Exception as e:  # side numbers must never take the headline down (a failed rank leaves the others to NCCL's timeout)
             import traceback
             multi = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
+        if rank == 0 and isinstance(multi, dict):
+            multi["e2e_scaling"] = e2e_scaling
 
-    # ---- the same edges as NODE PAIRS (transition_validator(&node, &node), pto.rs:105 / prm.rs:93): node states resident on the
-    # device (uploaded once, outside the timed region, like a roadmap's vertices), per step 8 B of ids in and 12 B out per edge
-    nodes_e2e = None
+    # ---- batch-size sweep of the device-resident kernel (BASELINE config 5 names 1e6 - 1e8 edge checks)
+    sizes = None
     if not args.no_extras:
         try:
-            tree = P.KdTree(ctx, np.concatenate([a, b]), cell_size=0.01)
-            h_fi = torch.arange(0, E, dtype=torch.int32).pin_memory()
-            h_ti = torch.arange(E, 2 * E, dtype=torch.int32).pin_memory()
-            h_vid2 = torch.empty(E, dtype=torch.int32).pin_memory()
-            h_mask2 = torch.empty(E, dtype=torch.int64).pin_memory()
-
-            def step_nodes():
-                ctx.check(lib.porrt_edge_validity_indexed(h, h_fi.data_ptr(), h_ti.data_ptr(), E, h_vid2.data_ptr(), h_mask2.data_ptr()))
-            step_nodes()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                step_nodes()
-            barrier()
-            t_n = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t_n, op=dist.ReduceOp.MAX)
-            assert torch.equal(h_vid2, h_vid) and torch.equal(h_mask2, h_mask)
-            v = E * world * N_WORLDS * e2e_steps / float(t_n.item())
-            nodes_e2e = {"value": v, "unit": UNIT, "edges_per_s": v / N_WORLDS, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 12 * E,
-                         "resident_vertices": 2 * E, "identical_to_e2e": True,
-                         "note": "porrt_edge_validity_indexed: the step's edges given as pairs of node ids into a device-resident vertex set"}
-            del tree
+            sizes = {}
+            for n_e in (1_000_000, 100_000_000):
+                sa, sb = synth.edges(n_e, seed=50 + rank)
+                da, db = torch.from_numpy(sa).to(dev), torch.from_numpy(sb).to(dev)
+                dv = torch.empty(n_e, dtype=torch.int32, device=dev)
+                dm = torch.empty(n_e, dtype=torch.int64, device=dev)
+                torch.cuda.set_stream(stream)
+                ctx.set_stream(stream.cuda_stream)
+                reps = 20 if n_e <= 1_000_000 else 3
+                for _ in range(2):
+                    ctx.check(lib.porrt_edge_validity_dev(h, da.data_ptr(), db.data_ptr(), n_e, dv.data_ptr(), dm.data_ptr()))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(reps):
+                    ctx.check(lib.porrt_edge_validity_dev(h, da.data_ptr(), db.data_ptr(), n_e, dv.data_ptr(), dm.data_ptr()))
+                e1.record(stream)
+                torch.cuda.synchronize()
+                t_ms = e0.elapsed_time(e1) / reps
+                sizes["E%d" % n_e] = {"ms": t_ms, "edges_per_s": n_e / (t_ms * 1e-3), "value": n_e * N_WORLDS / (t_ms * 1e-3), "unit": UNIT}
+                ctx.set_stream(None)
+                del da, db, dv, dm, sa, sb
+                torch.cuda.empty_cache()
         except Exception as e:
-            nodes_e2e = {"error": repr(e)}
+            sizes = {"error": repr(e)}
 
     line = None
     os.sched_setaffinity(0, affinity0)
     if rank == 0:
         base, oracle_vid, _ = cpu_baseline(args, occ, zones, a, b)
         n = len(oracle_vid)
-        assert np.array_equal(h_vid.numpy()[:n].astype(np.int64), oracle_vid), "GPU result differs from the oracle"
+        assert np.array_equal(want_vid.numpy()[:n].astype(np.int64), oracle_vid), "GPU result differs from the oracle"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": workload_config(args),
                 "edges_per_s": value / N_WORLDS,
                 "roofline": roofline, "cpu_baseline": base,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * E, "d2h_bytes_per_step": 12 * E,
-                        "steps": e2e_steps, "edges_per_s": e2e_value / N_WORLDS},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 1 * E,
+                        "steps": e2e_steps, "edges_per_s": e2e_value / N_WORLDS,
+                        "call": "porrt_edge_validity_indexed_i8: transition_validator(&PTONode, &PTONode) -> Option<usize> batched over "
+                                "pinned host buffers -- node-id pairs in, one validity id out; node states resident on the device "
+                                "(uploaded once, outside the timed region, like a roadmap's vertices)"},
+                "e2e_variants": variants,
                 "gpu_launches": int(launches), "clocks": clocks, "parity_checked_edges": n}
-        line["config"]["host_numa_node_rank0"] = numa_node
 
     # ---- side measurements of the other BASELINE metrics (kNN queries/s, PRM build ms); not part of `value`
     if rank == 0 and not args.no_extras:
         line["extras"] = side_measurements(ctx, pmap, args)
-        line["extras"]["edges_by_node_id_e2e"] = nodes_e2e
+        line["extras"]["edge_batch_sizes_device"] = sizes
+        line["extras"]["host_numa_node_rank0"] = numa_node
         if multi is not None:
             line["extras"]["multi_gpu"] = multi
     if rank == 0:
