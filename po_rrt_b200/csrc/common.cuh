@@ -99,6 +99,9 @@ struct porrt_ctx {
   int32_t cells_x = 0, cells_y = 0;
   DevBuf d_vxy_sorted, d_vid_sorted, d_cell_start, d_vxy, d_vcell;
   DevBuf nn_tmp[3];      // nn_tile.cu: query bins
+  DevBuf d_nbr_start, d_nbr_script;   // nn_tile.cu: per-cell merge scripts of the 3 x 3 neighbourhood (built lazily per vertex set)
+  bool nbr_ready = false;
+  DevBuf nn_stage;       // nn_tile.cu: tile-ordered staging of the radius lists + per-query staging offsets
   int32_t nn_fb_n = 0;   // queries of the last tile pass left to the thread-per-query kernels
   int32_t reach_words = 1;  // u64 words per vertex of the reachability filter of the running NN call
 
@@ -203,10 +206,11 @@ int32_t edge3_launch(porrt_ctx* ctx, const double* from_dev, const double* to_de
 // nn_tile.cu (TMA-staged vertex tiles); GridDev is defined in nn_dev.cuh
 struct GridDev;
 bool nn_tile_usable(const porrt_ctx* ctx, int64_t m);
-int32_t nn_tile_radius(porrt_ctx* ctx, const GridDev& g, const double* q_dev, const double* radius_dev, int64_t m,
-                       const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev, bool fill, int32_t* counts_dev,
-                       const int64_t* offsets_dev, int32_t* ids_dev, const int32_t** fb_list_out, int32_t* fb_n_out,
-                       const uint32_t* prefix_lo_dev = nullptr);
+int32_t nn_tile_radius_collect(porrt_ctx* ctx, const GridDev& g, const double* q_dev, const double* radius_dev, int64_t m,
+                               const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev, int32_t* counts_dev,
+                               int64_t* stg_off_dev, const int32_t** staging_out, const int32_t** fb_list_out, int32_t* fb_n_out);
+int32_t nn_tile_radius_place(porrt_ctx* ctx, const int32_t* staging, const int64_t* stg_off_dev, const int64_t* offsets_dev, int64_t m,
+                             int32_t* ids_dev);
 int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64_t m, int k, const uint64_t* reach_dev,
                     const uint32_t* world_dev, int32_t* ids_dev, double* dist_dev, int32_t* ties_dev, const int32_t** fb_list_out,
                     int32_t* fb_n_out);
@@ -215,10 +219,10 @@ int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, dou
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
                                  int64_t* offsets_dev /* [m+1] */, DevBuf* ids_buf, int64_t* total_out,
-                                 const uint32_t* prefix_lo_dev = nullptr);
+                                 const uint32_t* prefix_lo_dev = nullptr, bool sort_ids = false);
 int32_t scan_exclusive_i64(porrt_ctx* ctx, const int32_t* counts_dev, int64_t n, int64_t* out_dev /* [n+1] */);
 int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev,
-                                 const int32_t* key_of_id_dev, int64_t key_limit);
+                                 const int32_t* key_of_id_dev, int64_t key_limit, const int32_t* seg_list_dev = nullptr, int64_t n_listed = 0);
 int32_t radix_sort_pairs(porrt_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);
 int bits_for(uint64_t max_value);
 int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, double max_step, double search_radius,

@@ -265,6 +265,7 @@ static GridDev grid_dev(porrt_ctx* ctx) {
 int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi) {
   cudaStream_t st = ctx->stream;
   ctx->n_vertices = 0;
+  ctx->nbr_ready = false;     // the merge scripts of nn_tile.cu belong to the previous vertex set
   if (n <= 0 || n > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_set: n out of range");
   double blo[2], bhi[2];
   if (lo && hi) { blo[0] = lo[0]; blo[1] = lo[1]; bhi[0] = hi[0]; bhi[1] = hi[1]; }
@@ -404,10 +405,12 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
   if (!FILL) counts[t] = cnt;
 }
 
-// offsets_dev[m+1] filled; ids_buf grown to the total; *total_out = total hits (host value; synchronises once)
+// offsets_dev[m+1] filled; ids_buf grown to the total; *total_out = total hits (host value).  Large batches go through the
+// one-pass tile kernel (nn_tile.cu), which delivers its lists id-ascending; the queries it leaves over, small batches and grouped
+// vertex sets (prefix_lo) are answered by the thread-per-query kernel above in cell order -- sort_ids puts those in id order too.
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
-                                 int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out, const uint32_t* prefix_lo_dev) {
+                                 int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out, const uint32_t* prefix_lo_dev, bool sort_ids) {
   cudaStream_t st = ctx->stream;
   if (m <= 0) {   // an empty shard of a sharded batch
     CUDA_TRY(ctx, cudaMemsetAsync(offsets_dev, 0, 8, st));
@@ -416,16 +419,18 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
     return PORRT_OK;
   }
   GridDev g = grid_dev(ctx);
-  CUDA_TRY(ctx, ctx->scratch[4].ensure((size_t)m * 4 + 16));
-  int32_t* counts = ctx->scratch[4].as<int32_t>();
+  CUDA_TRY(ctx, ctx->scratch[4].ensure((size_t)m * 12 + 64));
+  int64_t* stg_off = ctx->scratch[4].as<int64_t>();
+  int32_t* counts = (int32_t*)(stg_off + m);
   // grouped vertex sets (prefix_lo): the other groups' vertices share the cells, staging them all would only cost; the
   // thread-per-query kernel skips to its own group inside each cell list
   const bool tiles = nn_tile_usable(ctx, m) && !prefix_lo_dev;
   const int32_t* fb_list = nullptr;
+  const int32_t* staging = nullptr;
   int32_t fb_n = 0;
-  if (tiles) {   // TMA-staged tiles, warp per query; queries with a wider reach come back in fb_list
+  if (tiles) {
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)m * 4, st));
-    int32_t rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, false, counts, nullptr, nullptr, &fb_list, &fb_n, prefix_lo_dev);
+    int32_t rc = nn_tile_radius_collect(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, stg_off, &staging, &fb_list, &fb_n);
     if (rc) return rc;
     if (fb_n > 0) {
       radius_kernel<false><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, fb_list, prefix_lo_dev);
@@ -444,15 +449,23 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   CUDA_TRY(ctx, ids_buf->ensure((size_t)std::max<int64_t>(total, 1) * 4));
   if (total > 0) {
     if (tiles) {
-      rc = nn_tile_radius(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, true, nullptr, offsets_dev, ids_buf->as<int32_t>(), &fb_list, &fb_n, prefix_lo_dev);
+      rc = nn_tile_radius_place(ctx, staging, stg_off, offsets_dev, m, ids_buf->as<int32_t>());
       if (rc) return rc;
       if (fb_n > 0) {
         radius_kernel<true><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), fb_list, prefix_lo_dev);
         LAUNCH_CHECK(ctx);
+        if (sort_ids) {
+          rc = segments_sort_by_key_dev(ctx, offsets_dev, m, ids_buf->as<int32_t>(), nullptr, g.n, fb_list, fb_n);
+          if (rc) return rc;
+        }
       }
     } else {
       radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), nullptr, prefix_lo_dev);
       LAUNCH_CHECK(ctx);
+      if (sort_ids) {
+        rc = segments_sort_by_key_dev(ctx, offsets_dev, m, ids_buf->as<int32_t>(), nullptr, g.n);
+        if (rc) return rc;
+      }
     }
   }
   return PORRT_OK;
@@ -580,10 +593,12 @@ __device__ __forceinline__ void seg_sort_regs(int32_t* __restrict__ seg_ids, int
 template <bool BY_KEY>
 __global__ void __launch_bounds__(SEG_REG_WARPS * 32) seg_sort_reg_kernel(const int64_t* __restrict__ offsets, int64_t m, int32_t* __restrict__ ids,
                                                                           const int32_t* __restrict__ key_of_id, const int32_t* __restrict__ id_of_key,
-                                                                          int32_t* __restrict__ n_mid_big, int32_t* __restrict__ mid_list) {
+                                                                          int32_t* __restrict__ n_mid_big, int32_t* __restrict__ mid_list,
+                                                                          const int32_t* __restrict__ seg_list /* nullable: m listed segments */) {
   const int lane = threadIdx.x & 31;
-  const int64_t seg = (int64_t)blockIdx.x * SEG_REG_WARPS + (threadIdx.x >> 5);
-  if (seg >= m) return;
+  const int64_t slot = (int64_t)blockIdx.x * SEG_REG_WARPS + (threadIdx.x >> 5);
+  if (slot >= m) return;
+  const int64_t seg = seg_list ? seg_list[slot] : slot;
   const int64_t s = offsets[seg];
   const int64_t len64 = offsets[seg + 1] - s;
   if (len64 <= 1) return;
@@ -636,9 +651,13 @@ __global__ void invert_perm_kernel(const int32_t* __restrict__ key_of_id, int64_
 }
 
 // key_limit: all keys (ids or key_of_id values) are < key_limit; key_of_id (if given) is a permutation of 0..key_limit-1
-int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev, const int32_t* key_of_id_dev, int64_t key_limit) {
+int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev, const int32_t* key_of_id_dev, int64_t key_limit,
+                                 const int32_t* seg_list_dev, int64_t n_listed) {
+  // seg_list_dev (nullable): only the n_listed segments named there need sorting (of m segments in all); the rare global radix
+  // path ignores the list and sorts everything, which is harmless
   cudaStream_t st = ctx->stream;
-  if (m <= 0) return PORRT_OK;
+  if (m <= 0 || (seg_list_dev && n_listed <= 0)) return PORRT_OK;
+  const int64_t m_run = seg_list_dev ? n_listed : m;
   static const bool no_regs = getenv("PORRT_SEGSORT_NO_REGS") != nullptr;   // A/B switch: shared-memory network for everything
   CUDA_TRY(ctx, ctx->scratch[4].ensure(16 + (size_t)m * 4 + (key_of_id_dev ? (size_t)key_limit * 4 : 0)));
   int32_t* d_big = ctx->scratch[4].as<int32_t>();   // [0] n_mid (257..4096, listed), [1] n_big (longer)
@@ -651,9 +670,9 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
     if (key_of_id_dev) {
       invert_perm_kernel<<<div_up(key_limit, 256), 256, 0, st>>>(key_of_id_dev, key_limit, d_inv);
       LAUNCH_CHECK(ctx);
-      seg_sort_reg_kernel<true><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, key_of_id_dev, d_inv, d_big, d_mid_list);
+      seg_sort_reg_kernel<true><<<div_up(m_run, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m_run, ids_dev, key_of_id_dev, d_inv, d_big, d_mid_list, seg_list_dev);
     } else {
-      seg_sort_reg_kernel<false><<<div_up(m, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m, ids_dev, nullptr, nullptr, d_big, d_mid_list);
+      seg_sort_reg_kernel<false><<<div_up(m_run, SEG_REG_WARPS), SEG_REG_WARPS * 32, 0, st>>>(offsets_dev, m_run, ids_dev, nullptr, nullptr, d_big, d_mid_list, seg_list_dev);
     }
     LAUNCH_CHECK(ctx);
     int32_t cnt[2] = {0, 0};
@@ -723,7 +742,7 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
   if (d_reach) CUDA_TRY(ctx, cudaMemcpyAsync(d_reach, reach_mask, reach_bytes, cudaMemcpyHostToDevice, st));
   int64_t total = 0;
   tstart(ctx);  // phases: [count+scan+fill, order restore, D2H]
-  int32_t rc = nn_radius_count_fill_dev(ctx, d_q, d_r, m, d_prefix, d_reach, d_world, d_off, &ctx->scratch[2], &total, nullptr);
+  int32_t rc = nn_radius_count_fill_dev(ctx, d_q, d_r, m, d_prefix, d_reach, d_world, d_off, &ctx->scratch[2], &total, nullptr, true);
   if (rc) return rc;
   tmark(ctx);
   if (out_total) *out_total = total;
@@ -732,9 +751,7 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return porrt_fail(ctx, PORRT_ERR_CAPACITY, "radius_query: out_ids too small");
   }
-  rc = segments_sort_by_key_dev(ctx, d_off, m, ctx->scratch[2].as<int32_t>(), nullptr, V);
-  if (rc) return rc;
-  tmark(ctx);
+  tmark(ctx);   // (the id order comes out of the search itself now; the phase is kept so that the list keeps its three entries)
   CUDA_TRY(ctx, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(out_ids, ctx->scratch[2].p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
   tmark(ctx);
