@@ -64,6 +64,9 @@ const char* porrt_last_error(porrt_ctx* ctx);
 /* options (tests / tuning); unknown options are refused */
 #define PORRT_OPT_FORCE_LARGE_MAP_PATH 1  /* value != 0: edge batches take the large-map kernel (class bytes in global memory, used
                                              by itself for maps > ~14000^2 px) although the map would fit the shared-memory path */
+#define PORRT_OPT_FORCE_GLOBAL_SWEEPS 2   /* value != 0: porrt_sssp_worlds / porrt_belief_vi run the thread-per-(node, column) sweeps over
+                                             the table in global memory (used by itself for roadmaps whose column of V doubles does not
+                                             fit in shared memory, V > ~29000) although the on-chip column solver would fit */
 int32_t porrt_ctx_set_option(porrt_ctx* ctx, int32_t option, int64_t value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 int64_t porrt_ctx_launch_count(porrt_ctx* ctx);
@@ -193,6 +196,11 @@ int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const
                         const uint64_t* visible_zone_mask, const int32_t* finals_ids, const uint64_t* finals_masks,
                         int32_t n_finals, double* out_dist, uint8_t* out_type, int32_t* out_sweeps,
                         double* out_phase_ms /* nullable [4] */);
+/* The table of the last porrt_belief_vi without a second copy: *out_dist ([V*B], node-major) and *out_type point into pinned
+ * host memory owned by the ctx, valid until the next porrt_belief_vi on it (the convention of the reference's own FFI: results stay
+ * owned by the handle and are read through pointer getters, pto_c.rs:255-270).  porrt_belief_vi accepts out_dist = out_type = NULL
+ * for callers that read the result this way (at B = 4095 the copy into a fresh 172 MB caller buffer costs as much as the backups). */
+int32_t porrt_belief_result(porrt_ctx* ctx, const double** out_dist, const uint8_t** out_type, int64_t* out_V, int32_t* out_B);
 
 /* belief_graph.rs:184-267 extract_policy on the implicit graph, walking out_dist/out_type of porrt_belief_vi.
  * Policy nodes in creation order: out_node[k] = graph node, out_belief[k], out_parent[k] (-1 root), out_is_leaf[k].

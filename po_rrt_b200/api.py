@@ -21,6 +21,7 @@ DOOR, SHELF = 0, 1
 NODE_UNKNOWN, NODE_ACTION, NODE_OBSERVATION = 0, 1, 2
 ERR_CAPACITY = 4
 OPT_FORCE_LARGE_MAP_PATH = 1
+OPT_FORCE_GLOBAL_SWEEPS = 2
 
 
 class PorrtError(RuntimeError):
@@ -431,9 +432,10 @@ class BeliefPlan:
     pass
 
 
-def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, final_ids, final_masks_words, beliefs=None):
+def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, final_ids, final_masks_words, beliefs=None, copy=True):
     """PTO::plan_belief_space (src/pto.rs:152-182) for a grown roadmap given as CSR (children adjacency).
-    Returns a BeliefPlan with beliefs, visible (zone masks), dist[V,B], type[V,B], policy arrays, expected_cost."""
+    Returns a BeliefPlan with beliefs, visible (zone masks), dist[V,B], type[V,B], policy arrays, expected_cost.
+    copy=False: dist / type are views of the ctx-owned pinned result (porrt_belief_result), valid until the next call on the ctx."""
     ctx = fns.ctx
     fns._need()
     row_ptr = np.ascontiguousarray(row_ptr, np.int64)
@@ -451,14 +453,21 @@ def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, f
     vw = fns.world_validities_words()
     fin = np.ascontiguousarray(final_ids, np.int32)
     fmask = np.ascontiguousarray(final_masks_words, np.uint64).reshape(len(fin), fns.mask_words)
-    plan.dist = np.empty((V, B))
-    plan.type = np.empty((V, B), np.uint8)
+    if copy:
+        plan.dist = np.empty((V, B))
+        plan.type = np.empty((V, B), np.uint8)
     sweeps = C.c_int32()
     plan.phase_ms = np.zeros(4)
     ctx.check(ctx.lib.porrt_belief_vi(ctx.h, V, _p(row_ptr), _p(col), _p(edge_vid), _p(xy), _p(node_vid), _p(vw), vw.shape[0],
                                       vw.shape[1], fns.n_worlds(), _p(plan.beliefs), B, _p(plan.visible), _p(fin), _p(fmask),
-                                      len(fin), _p(plan.dist), _p(plan.type), C.byref(sweeps), _p(plan.phase_ms)))
+                                      len(fin), _p(plan.dist) if copy else None, _p(plan.type) if copy else None, C.byref(sweeps),
+                                      _p(plan.phase_ms)))
     plan.sweeps = sweeps.value
+    if not copy:
+        pd, pt = C.POINTER(C.c_double)(), C.POINTER(C.c_uint8)()
+        ctx.check(ctx.lib.porrt_belief_result(ctx.h, C.byref(pd), C.byref(pt), None, None))
+        plan.dist = np.ctypeslib.as_array(pd, shape=(V, B))
+        plan.type = np.ctypeslib.as_array(pt, shape=(V, B))
     cap = 4096
     n, cost = C.c_int64(), C.c_double()
     while True:

@@ -18,6 +18,8 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "colsolve.cuh"
+#include "belief_tables.cuh"
 
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -590,6 +592,7 @@ __global__ void edge_cost_kernel(const int64_t* __restrict__ row_ptr, const int3
 
 // One pull sweep: dist[u][w] = min(dist[u][w], min_{v in children(u)} dist[v][w] + cost(u,v)) for u valid in world w.
 // Layout dist[u * W + w]: the W threads of a node read its CSR row once (broadcast) and the children's rows coalesced.
+// Roadmaps too large for the shared-memory column solver (colsolve.cu) only.
 __global__ void __launch_bounds__(256) sssp_sweep_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                          const double* __restrict__ cost, const uint8_t* __restrict__ node_ok /* [V*W] */,
                                                          int64_t V, int W, double* __restrict__ dist, int32_t* __restrict__ changed) {
@@ -607,12 +610,31 @@ __global__ void __launch_bounds__(256) sssp_sweep_kernel(const int64_t* __restri
   if (best < old) { dist[t] = best; *changed = 1; }
 }
 
+// node_ok[u * W + w] = bit (wlo + w) of validities[node_vid[u]] (all ones without a world view); dist = +inf
+__global__ void sssp_init_kernel(const int32_t* __restrict__ node_vid, const uint64_t* __restrict__ validities, int mask_words,
+                                 int64_t V, int W, int wlo, uint8_t* __restrict__ node_ok, double* __restrict__ dist) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V * W) return;
+  const int64_t u = t / W;
+  const int wg = wlo + (int)(t - u * W);
+  node_ok[t] = node_vid ? (uint8_t)((validities[(int64_t)node_vid[u] * mask_words + (wg >> 6)] >> (wg & 63)) & 1) : 1;
+  dist[t] = INFINITY;
+}
+
 __global__ void transpose_dist_kernel(const double* __restrict__ in /* [V][W] */, int64_t V, int W, double* __restrict__ out /* [W][V] */) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V * W) return;
   const int64_t u = t / W;
   const int w = (int)(t - u * W);
   out[(int64_t)w * V + u] = in[t];
+}
+
+__global__ void fill_inf_kernel(double* __restrict__ d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = INFINITY;
+}
+__global__ void scatter_zero_kernel(double* __restrict__ d, const int64_t* __restrict__ idx, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[idx[i]] = 0.0;
 }
 
 PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy,
@@ -635,60 +657,100 @@ PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* ro
   const int64_t E = row_ptr[V];
   if (E > 0 && !col) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: null col");
   if (!csr_ok(V, row_ptr, col)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: malformed CSR (row_ptr not monotone or edge target out of range)");
-  // host prep: validity per (node, world) and the initial distances (inf, 0 at the finals)
-  const double INF = std::numeric_limits<double>::infinity();
-  std::vector<uint8_t> ok((size_t)V * W, 1);
-  std::vector<double> dist0((size_t)V * W, INF);
   if (world_view)
-    for (int64_t u = 0; u < V; ++u) {
-      const int32_t vid = node_vid[u];
-      if (vid < 0 || vid >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: node validity id out of range");
-      for (int w = 0; w < W; ++w) { const int wg = (int)wlo + w; ok[(size_t)u * W + w] = (validities[(size_t)vid * mask_words + wg / 64] >> (wg % 64)) & 1; }
-    }
+    for (int64_t u = 0; u < V; ++u)
+      if (node_vid[u] < 0 || node_vid[u] >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: node validity id out of range");
+  // the finals of this rank's worlds as indices into the value table (column solver: [world][node]; sweeps: [node][world])
+  const bool cols = colsolve_fits(V, E, world_view ? n_validities : 1) && !ctx->force_global_sweeps;
+  std::vector<int64_t> zero_idx;
   for (int w = 0; w < Wall; ++w)
     for (int64_t k = finals_ptr[w]; k < finals_ptr[w + 1]; ++k) {
       const int32_t f = finals_ids[k];
       if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: final id out of range");
-      if (w >= wlo && w < whi) dist0[(size_t)f * W + (w - wlo)] = 0.0;
+      if (w >= wlo && w < whi) zero_idx.push_back(cols ? (int64_t)w * V + f : (int64_t)f * W + (w - wlo));
     }
   DevBuf& g = ctx->scratch[3];
-  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 16 + (size_t)V * W * 9 + (size_t)V * Wall * 8 + 512;
+  const size_t nvw = world_view ? (size_t)n_validities * mask_words : 0;
+  const size_t need = (size_t)(V + 1) * 16 + (size_t)E * 24 + (size_t)V * 24 + (size_t)V * W * 9 + (size_t)V * Wall * 8 + nvw * 8 +
+                      (size_t)Wall * 32 + zero_idx.size() * 8 + 16 * 16 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };  // keeps double2 loads aligned
   int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
   double* d_cost = (double*)take((size_t)E * 8);
   double* d_xy = (double*)take((size_t)V * 16);
-  double* d_dist = (double*)take((size_t)V * W * 8);
   double* d_out = (double*)take((size_t)V * Wall * 8);   // [Wall][V]: this rank fills rows wlo..whi, the gather the rest
   int32_t* d_col = (int32_t*)take((size_t)E * 4);
-  int32_t* d_changed = (int32_t*)take(16);
-  uint8_t* d_ok = (uint8_t*)take((size_t)V * W);
+  int32_t* d_nvid = (int32_t*)take((size_t)V * 4);
+  uint64_t* d_val = (uint64_t*)take(nvw * 8);
+  int64_t* d_zero = (int64_t*)take(zero_idx.size() * 8 + 8);
+  int32_t* d_flag = (int32_t*)take(16);
   int sweeps = 0;
   if (W > 0) {
     CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
     if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_dist, dist0.data(), (size_t)V * W * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_ok, ok.data(), (size_t)V * W, cudaMemcpyHostToDevice, st));
+    if (world_view) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(d_nvid, node_vid, (size_t)V * 4, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(ctx, cudaMemcpyAsync(d_val, validities, nvw * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (!zero_idx.empty()) CUDA_TRY(ctx, cudaMemcpyAsync(d_zero, zero_idx.data(), zero_idx.size() * 8, cudaMemcpyHostToDevice, st));
     edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
     LAUNCH_CHECK(ctx);
-    const int BATCH = 8;  // sweeps between two convergence checks
-    for (;;) {
-      CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
-      for (int k = 0; k < BATCH; ++k) {
-        sssp_sweep_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_row, d_col, d_cost, d_ok, V, W, d_dist, d_changed);
+    if (cols) {
+      // one column per world, solved on chip (colsolve.cu); d_out is the column-major table itself
+      uint32_t* d_rs = (uint32_t*)take((size_t)(V + 1) * 4);
+      uint32_t* d_ce = (uint32_t*)take((size_t)E * 4);
+      uint64_t* d_cmask = (uint64_t*)take((size_t)Wall * 32);
+      std::vector<uint64_t> cmask((size_t)Wall * 4, world_view ? 0 : ~(uint64_t)0);
+      if (world_view)
+        for (int w = 0; w < Wall; ++w)
+          for (int v = 0; v < n_validities; ++v)
+            if ((validities[(size_t)v * mask_words + w / 64] >> (w % 64)) & 1) cmask[(size_t)w * 4 + v / 64] |= (uint64_t)1 << (v % 64);
+      CUDA_TRY(ctx, cudaMemcpyAsync(d_cmask, cmask.data(), cmask.size() * 8, cudaMemcpyHostToDevice, st));
+      double* d_cost_t = (double*)take((size_t)E * 8);
+      uint32_t* d_cursor = (uint32_t*)take((size_t)(V + 1) * 4);
+      int32_t rc = colsolve_pack(ctx, d_row, d_col, nullptr, d_cost, V, E, d_rs, d_ce, d_cost_t, d_cursor, st);
+      if (rc) return rc;
+      fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_out + wlo * V, V * (int64_t)W);
+      LAUNCH_CHECK(ctx);
+      if (!zero_idx.empty()) {
+        scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_out, d_zero, (int64_t)zero_idx.size());
         LAUNCH_CHECK(ctx);
       }
-      sweeps += BATCH;
-      int32_t changed = 0;
-      CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(ctx, cudaStreamSynchronize(st));
-      if (!changed) break;
-      if (sweeps > 4 * V + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp_worlds: no convergence");
+      CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
+      ColSolveArgs ca = {};
+      ca.row_start = d_rs; ca.cost = d_cost_t; ca.ce = d_ce; ca.V = (int32_t)V; ca.ld = V; ca.dist_cm = d_out; ca.cmask = d_cmask;
+      ca.nvid = world_view ? d_nvid : nullptr; ca.sweeps_out = d_flag;
+      rc = colsolve_level(ctx, ca, COLSOLVE_WORLD, (int)wlo, (int)whi, st);
+      if (rc) return rc;
+      CUDA_TRY(ctx, cudaMemcpyAsync(&sweeps, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      double* d_dist = (double*)take((size_t)V * W * 8);
+      uint8_t* d_ok = (uint8_t*)take((size_t)V * W);
+      sssp_init_kernel<<<div_up(V * W, 256), 256, 0, st>>>(world_view ? d_nvid : nullptr, d_val, mask_words, V, W, (int)wlo, d_ok, d_dist);
+      LAUNCH_CHECK(ctx);
+      if (!zero_idx.empty()) {
+        scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_dist, d_zero, (int64_t)zero_idx.size());
+        LAUNCH_CHECK(ctx);
+      }
+      const int BATCH = 8;  // sweeps between two convergence checks
+      for (;;) {
+        CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
+        for (int k = 0; k < BATCH; ++k) {
+          sssp_sweep_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_row, d_col, d_cost, d_ok, V, W, d_dist, d_flag);
+          LAUNCH_CHECK(ctx);
+        }
+        sweeps += BATCH;
+        int32_t changed = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_flag, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (!changed) break;
+        if (sweeps > 4 * V + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp_worlds: no convergence");
+      }
+      transpose_dist_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_dist, V, W, d_out + wlo * V);
+      LAUNCH_CHECK(ctx);
     }
-    transpose_dist_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_dist, V, W, d_out + wlo * V);
-    LAUNCH_CHECK(ctx);
   }
   if (sharded) {
     std::vector<int64_t> off(ctx->comm_world + 1);
@@ -709,11 +771,6 @@ static double transition_probability(const double* parent, const double* child, 
   double s = 0.0;
   for (int i = 0; i < n; ++i) s = s + (child[i] > 0.0 ? parent[i] : 0.0);
   return s;
-}
-static bool is_compatible(const double* b, const uint64_t* mask, int n) {
-  for (int i = 0; i < n; ++i)
-    if (b[i] > 0.0 && !((mask[i / 64] >> (i % 64)) & 1)) return false;
-  return true;
 }
 static uint64_t belief_hash(const double* bs, int n) {
   uint64_t h = 0, p10 = 1;
@@ -804,7 +861,7 @@ struct BeliefDev {
 
 // node typing (pto.rs:209-255): Observation iff an observation edge to an EXISTING successor belief node exists,
 // else Action iff some admissible geometric child exists, else Unknown.
-__global__ void belief_type_kernel(BeliefDev g, uint8_t* __restrict__ type) {
+__global__ void belief_type_kernel(BeliefDev g, uint8_t* __restrict__ type, const int32_t* __restrict__ colpos, uint8_t* __restrict__ type_cm) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.V * g.B) return;
   const int64_t n = t / g.B;
@@ -822,15 +879,9 @@ __global__ void belief_type_kernel(BeliefDev g, uint8_t* __restrict__ type) {
     ty = 255;  // belief node does not exist (node_to_belief_nodes[id][belief] == None)
   }
   type[t] = ty;
+  if (type_cm) type_cm[(int64_t)colpos[b] * g.V + n] = ty;   // colsolve.cu reads a belief's column along the nodes
 }
 
-__global__ void fill_inf_kernel(double* __restrict__ d, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = INFINITY;
-}
-__global__ void scatter_zero_kernel(double* __restrict__ d, const int64_t* __restrict__ idx, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) d[idx[i]] = 0.0;
-}
 // belief nodes that do not exist were typed 255 for the sweeps; the reference adds them anyway, typed Unknown (pto.rs:199)
 __global__ void type_finish_kernel(uint8_t* __restrict__ type, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -890,124 +941,22 @@ __global__ void __launch_bounds__(256) belief_sweep_kernel(BeliefDev g, const ui
   if (alt < old) { dist[t] = alt; *changed = 1; if (node_epoch) node_epoch[n] = sweep; }
 }
 
-// Chunked work skipping (opt-in experiment, see porrt_belief_vi): one warp = one (node, chunk of 32 beliefs).  A backup of belief b at node n reads the
-// same belief at the children (action edges) or other beliefs at n itself (observation edges), so a warp has to run only if
-// one of the children's chunks with the same index changed since the previous sweep, or -- when the chunk holds Observation nodes
-// -- anything at n did.  chunk_epoch[n * wpn + chunk] / node_epoch[n] = last sweep with a change; the test `>= sweep - 1` also
-// sees changes made earlier in the same sweep.  Per-node flags alone (belief_active_kernel) re-evaluate all 4095 beliefs of a
-// node's parents whenever one belief moved; per chunk the wavefronts of the individual beliefs are followed separately.
-__global__ void belief_chunk_obs_kernel(const uint8_t* __restrict__ type, int64_t V, int B, int wpn, uint8_t* __restrict__ has_obs) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= V * wpn) return;
-  const int64_t n = w / wpn;
-  const int b = (int)(w - n * wpn) * 32 + lane;
-  const bool o = b < B && type[n * B + b] == PORRT_NODE_OBSERVATION;
-  const unsigned any = __ballot_sync(0xffffffffu, o);
-  if (lane == 0) has_obs[w] = any ? 1 : 0;
-}
-__global__ void __launch_bounds__(256) belief_sweep_chunk_kernel(BeliefDev g, const uint8_t* __restrict__ type, double* __restrict__ dist,
-                                                                 int32_t* __restrict__ changed, int wpn, const uint8_t* __restrict__ has_obs,
-                                                                 int32_t* __restrict__ chunk_epoch, int32_t* __restrict__ node_epoch, int32_t sweep) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= g.V * wpn) return;
-  const int64_t n = w / wpn;
-  const int chunk = (int)(w - n * wpn);
-  const int64_t e0 = g.row_ptr[n], e1 = g.row_ptr[n + 1];
-  if (sweep > 1) {
-    bool a = has_obs[w] && node_epoch[n] >= sweep - 1;
-    for (int64_t e = e0 + lane; !a && e < e1; e += 32) a = chunk_epoch[(int64_t)g.col[e] * wpn + chunk] >= sweep - 1;
-    if (!__any_sync(0xffffffffu, a)) return;
-  }
-  const int b = chunk * 32 + lane;
-  bool upd = false;
-  if (b < g.B) {
-    const int64_t t = n * g.B + b;
-    const uint8_t ty = type[t];
-    if (ty == PORRT_NODE_ACTION || ty == PORRT_NODE_OBSERVATION) {
-      const double old = dist[t];
-      double alt;
-      if (ty == PORRT_NODE_OBSERVATION) {
-        const int32_t nv = g.node_vid[n];
-        const int64_t sp = (int64_t)g.node_set[n] * g.B + b;
-        alt = 0.0;
-        for (int64_t k = g.succ_ptr[sp]; k < g.succ_ptr[sp + 1]; ++k) {
-          const int32_t cb = g.succ_belief[k];
-          if (!g.compat[(int64_t)cb * g.n_validities + nv]) continue;
-          alt = __dadd_rn(alt, __dmul_rn(g.succ_p[k], __dadd_rn(0.0, dist[n * g.B + cb])));
-        }
-      } else {
-        alt = INFINITY;
-        const uint8_t* cm = g.compat_t + b;
-        for (int64_t e = e0; e < e1; ++e) {
-          const int32_t c = g.col[e];
-          if (!cm[(int64_t)g.node_vid[c] * g.B] || !cm[(int64_t)g.edge_vid[e] * g.B]) continue;
-          const double a2 = __dadd_rn(g.cost[e], dist[(int64_t)c * g.B + b]);
-          if (a2 < alt) alt = a2;
-        }
-      }
-      if (alt < old) { dist[t] = alt; upd = true; }
-    }
-  }
-  if (__any_sync(0xffffffffu, upd) && lane == 0) { chunk_epoch[w] = sweep; node_epoch[n] = sweep; *changed = 1; }
-}
-
-// Ordered variant (opt-in experiment, see porrt_belief_vi): the same backup, but
-//  * threads are laid out over a node ORDER (position p -> node order[p]): four orders, nodes sorted by +x, -x, +y, -y, are cycled
-//    sweep by sweep like the directions of a fast-sweeping scheme.  Blocks are scheduled roughly in index order and updates are in
-//    place, so within one sweep values travel many hops along the sweep direction instead of one hop per sweep;
-//  * activity is decided inside the sweep, per block, and also sees changes made EARLIER IN THE SAME SWEEP (epoch >= sweep - 1):
-//    a precomputed mask would cut the in-sweep propagation back to one hop.
-// The fixed point, hence every bit of the result, does not depend on the schedule.
-#define BSO_MAXN 260
-__global__ void __launch_bounds__(256) belief_sweep_ordered_kernel(BeliefDev g, const uint8_t* __restrict__ type, double* __restrict__ dist,
-                                                                   int32_t* __restrict__ changed, const int32_t* __restrict__ order,
-                                                                   int32_t* __restrict__ node_epoch, int32_t sweep) {
-  __shared__ uint8_t s_act[BSO_MAXN];
-  const int64_t t0 = (int64_t)blockIdx.x * 256;
-  const int64_t total = g.V * (int64_t)g.B;
-  const int64_t p_first = t0 / g.B;
-  const int64_t t_last = min(t0 + 255, total - 1);
-  const int count = (int)(t_last / g.B - p_first) + 1;
-  for (int i = threadIdx.x; i < count; i += 256) {
-    const int32_t n = order[p_first + i];
-    bool a = sweep <= 1 || node_epoch[n] >= sweep - 1;
-    for (int64_t e = g.row_ptr[n]; !a && e < g.row_ptr[n + 1]; ++e) a = node_epoch[g.col[e]] >= sweep - 1;
-    s_act[i] = a ? 1 : 0;
+// dist_cm[colpos[b]][n] -> dist[n][b] through a 32 x 32 tile (both sides coalesced)
+__global__ void __launch_bounds__(256) belief_untranspose_kernel(const double* __restrict__ dist_cm, int64_t ld, const int32_t* __restrict__ colpos,
+                                                                 int64_t V, int B, double* __restrict__ dist) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t n0 = (int64_t)blockIdx.x * 32;
+  const int b0 = blockIdx.y * 32;
+  for (int k = ty; k < 32; k += 8) {
+    const int b = b0 + k;
+    if (b < B && n0 + tx < V) tile[k][tx] = dist_cm[(int64_t)colpos[b] * ld + n0 + tx];
   }
   __syncthreads();
-  const int64_t t = t0 + threadIdx.x;
-  if (t >= total) return;
-  const int64_t p = t / g.B;
-  if (!s_act[p - p_first]) return;
-  const int b = (int)(t - p * g.B);
-  const int64_t n = order[p];
-  const int64_t idx = n * g.B + b;
-  const uint8_t ty = type[idx];
-  if (ty != PORRT_NODE_ACTION && ty != PORRT_NODE_OBSERVATION) return;
-  const double old = dist[idx];
-  double alt;
-  if (ty == PORRT_NODE_OBSERVATION) {
-    const int32_t nv = g.node_vid[n];
-    const int64_t sp = (int64_t)g.node_set[n] * g.B + b;
-    alt = 0.0;
-    for (int64_t k = g.succ_ptr[sp]; k < g.succ_ptr[sp + 1]; ++k) {
-      const int32_t cb = g.succ_belief[k];
-      if (!g.compat[(int64_t)cb * g.n_validities + nv]) continue;
-      alt = __dadd_rn(alt, __dmul_rn(g.succ_p[k], __dadd_rn(0.0, dist[n * g.B + cb])));
-    }
-  } else {
-    alt = INFINITY;
-    const uint8_t* cm = g.compat_t + b;
-    for (int64_t e = g.row_ptr[n]; e < g.row_ptr[n + 1]; ++e) {
-      const int32_t c = g.col[e];
-      if (!cm[(int64_t)g.node_vid[c] * g.B] || !cm[(int64_t)g.edge_vid[e] * g.B]) continue;
-      const double a = __dadd_rn(g.cost[e], dist[(int64_t)c * g.B + b]);
-      if (a < alt) alt = a;
-    }
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t n = n0 + k;
+    if (n < V && b0 + tx < B) dist[n * B + b0 + tx] = tile[tx][k];
   }
-  if (alt < old) { dist[idx] = alt; *changed = 1; node_epoch[n] = sweep; }
 }
 
 PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const int32_t* edge_vid,
@@ -1017,7 +966,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
                                   int32_t n_finals, double* out_dist, uint8_t* out_type, int32_t* out_sweeps, double* out_phase_ms) {
   CTX_CHECK(ctx);
   if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
-  if (V <= 0 || B <= 0 || !row_ptr || !xy || !node_vid || !validities || !beliefs || !visible_zone_mask || !out_dist || n_worlds != ctx->n_worlds ||
+  if (V <= 0 || B <= 0 || !row_ptr || !xy || !node_vid || !validities || !beliefs || !visible_zone_mask || n_worlds != ctx->n_worlds ||
       mask_words != ctx->mask_words || n_validities <= 0 || (n_finals > 0 && (!finals_ids || !finals_masks)))
     return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: bad arguments");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1032,9 +981,20 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     if (node_vid[u] < 0 || node_vid[u] >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: node validity id out of range");
   const int nw = n_worlds;
   // compute_compatibility (common.rs:266-276)
+  // is_compatible(belief, mask) (common.rs:256-264) = "no world with positive probability outside the mask": one AND-NOT per
+  // word on the belief's support bits
+  std::vector<uint64_t> support((size_t)B * mask_words, 0);
+  for (int b = 0; b < B; ++b)
+    for (int w = 0; w < nw; ++w)
+      if (beliefs[(size_t)b * nw + w] > 0.0) support[(size_t)b * mask_words + w / 64] |= (uint64_t)1 << (w % 64);
+  auto compatible = [&](int b, const uint64_t* mask) {
+    for (int k = 0; k < mask_words; ++k)
+      if (support[(size_t)b * mask_words + k] & ~mask[k]) return false;
+    return true;
+  };
   std::vector<uint8_t> compat((size_t)B * n_validities);
   for (int b = 0; b < B; ++b)
-    for (int v = 0; v < n_validities; ++v) compat[(size_t)b * n_validities + v] = is_compatible(beliefs + (size_t)b * nw, validities + (size_t)v * mask_words, nw);
+    for (int v = 0; v < n_validities; ++v) compat[(size_t)b * n_validities + v] = compatible(b, validities + (size_t)v * mask_words);
   // belief ids by hash (belief_graph.rs:75-87); collisions are a reference panic
   std::unordered_map<uint64_t, int> hash_to_id;
   std::vector<uint64_t> bhash(B);
@@ -1044,66 +1004,31 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   std::map<uint64_t, int> set_index;
   std::vector<int32_t> node_set((size_t)V);
   std::vector<uint64_t> sets;
+  const uint64_t zone_bits = ctx->n_zones >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << ctx->n_zones) - 1);
   for (int64_t n = 0; n < V; ++n) {
-    auto it = set_index.find(visible_zone_mask[n]);
-    if (it == set_index.end()) { it = set_index.emplace(visible_zone_mask[n], (int)sets.size()).first; sets.push_back(visible_zone_mask[n]); }
+    const uint64_t vis = visible_zone_mask[n] & zone_bits;
+    auto it = set_index.find(vis);
+    if (it == set_index.end()) { it = set_index.emplace(vis, (int)sets.size()).first; sets.push_back(vis); }
     node_set[n] = it->second;
   }
-  // one table entry per (set, belief): independent of each other, so the index space is cut into chunks for host threads and the
-  // chunks' lists are concatenated in order (at B = 4095 this loop was 130 ms single-threaded)
-  const size_t n_sb = sets.size() * (size_t)B;
-  std::vector<int64_t> succ_ptr(n_sb + 1, 0);
-  std::vector<int32_t> succ_belief;
-  std::vector<double> succ_p;
+  // column order for colsolve.cu: beliefs sorted by the size of their support (observations only ever split it, so a column
+  // reads Observation values from columns that come earlier), level by level
+  std::vector<int32_t> level((size_t)B, 0), colpos((size_t)B), col_belief((size_t)B);
+  for (int b2 = 0; b2 < B; ++b2)
+    for (int k = 0; k < mask_words; ++k) level[(size_t)b2] += __builtin_popcountll(support[(size_t)b2 * mask_words + k]);
+  for (int b2 = 0; b2 < B; ++b2) col_belief[(size_t)b2] = b2;
+  std::stable_sort(col_belief.begin(), col_belief.end(), [&](int32_t x, int32_t y) { return level[(size_t)x] < level[(size_t)y]; });
+  for (int c = 0; c < B; ++c) colpos[(size_t)col_belief[(size_t)c]] = c;
+  std::vector<int32_t> level_start;   // columns [level_start[k], level_start[k+1]) share a level
+  for (int c = 0; c < B; ++c)
+    if (c == 0 || level[(size_t)col_belief[(size_t)c]] != level[(size_t)col_belief[(size_t)c - 1]]) level_start.push_back(c);
+  level_start.push_back(B);
+  // observation successor tables, one entry per (set, belief), built on the device (belief_tables.cu)
+  BeliefSuccDev succ = {};
   {
-    const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::max(1u, std::thread::hardware_concurrency()), n_sb / 256 + 1}));
-    std::vector<std::vector<int32_t>> c_belief((size_t)n_chunks);
-    std::vector<std::vector<double>> c_p((size_t)n_chunks);
-    std::vector<int> c_err((size_t)n_chunks, 0);
-    auto work = [&](int c) {
-      const size_t lo = n_sb * (size_t)c / (size_t)n_chunks, hi = n_sb * (size_t)(c + 1) / (size_t)n_chunks;
-      std::vector<Belief> cur, nxt;
-      for (size_t sb = lo; sb < hi; ++sb) {
-        const size_t si = sb / (size_t)B;
-        const int b = (int)(sb % (size_t)B);
-        cur.assign(1, Belief(beliefs + (size_t)b * nw, beliefs + (size_t)(b + 1) * nw));
-        for (int z = 0; z < ctx->n_zones; ++z)
-          if ((sets[si] >> z) & 1) {  // zones ascending, every current belief split in turn (map_io.rs:285-297)
-            nxt.clear();
-            for (const Belief& bel : cur) successor_beliefs(ctx, bel, z, nxt);
-            cur.swap(nxt);
-          }
-        int64_t cnt = 0;
-        for (const Belief& child : cur) {
-          const uint64_t h = belief_hash(child.data(), nw);
-          if (h == bhash[b]) continue;  // pto.rs:216
-          auto it = hash_to_id.find(h);
-          if (it == hash_to_id.end()) { c_err[(size_t)c] = 1; return; }
-          c_belief[(size_t)c].push_back(it->second);
-          // transition_probability on the STORED reachable belief states (belief_graph.rs:128)
-          c_p[(size_t)c].push_back(transition_probability(beliefs + (size_t)b * nw, beliefs + (size_t)it->second * nw, nw));
-          ++cnt;
-        }
-        succ_ptr[sb + 1] = cnt;       // counts first; prefix-summed below
-      }
-    };
-    if (n_chunks == 1) work(0);
-    else {
-      std::vector<std::thread> th;
-      for (int c = 0; c < n_chunks; ++c) th.emplace_back(work, c);
-      for (auto& t : th) t.join();
-    }
-    for (int c = 0; c < n_chunks; ++c)
-      if (c_err[(size_t)c]) return porrt_fail(ctx, PORRT_ERR_PANIC, "no id corresponding to this belief state! (belief_graph.rs:69)");
-    for (size_t k = 0; k < n_sb; ++k) succ_ptr[k + 1] += succ_ptr[k];
-    succ_belief.reserve((size_t)succ_ptr[n_sb]); succ_p.reserve((size_t)succ_ptr[n_sb]);
-    for (int c = 0; c < n_chunks; ++c) {
-      succ_belief.insert(succ_belief.end(), c_belief[(size_t)c].begin(), c_belief[(size_t)c].end());
-      succ_p.insert(succ_p.end(), c_p[(size_t)c].begin(), c_p[(size_t)c].end());
-    }
+    int32_t rc = belief_succ_tables(ctx, beliefs, B, nw, sets, bhash, level, colpos, &succ, st);
+    if (rc) return rc;
   }
-  for (double p : succ_p)
-    if (!(p > 0.0)) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p > 0.0) (belief_graph.rs:130)");
   // initial distances: 0 at final belief nodes (pto.rs:261-271), +inf elsewhere -- written on the device; only the list of final
   // belief nodes is built here (a host-side V*B table cost 30 ms + a 150 MB upload at B = 4095)
   std::vector<int64_t> zero_idx;
@@ -1111,39 +1036,51 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     const int32_t f = finals_ids[k];
     if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_vi: final id out of range");
     for (int b = 0; b < B; ++b)
-      if (compat[(size_t)b * n_validities + node_vid[f]] && is_compatible(beliefs + (size_t)b * nw, finals_masks + (size_t)k * mask_words, nw))
+      if (compat[(size_t)b * n_validities + node_vid[f]] && compatible(b, finals_masks + (size_t)k * mask_words))
         zero_idx.push_back((int64_t)f * B + b);
   }
   t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;
 
+  const bool cols = colsolve_fits(V, E, n_validities) && !ctx->force_global_sweeps && succ.levels_ok;
+  const bool sharded = cols && ctx->comm_world > 1;   // the global sweeps are not sharded: every rank then computes the whole table
+  std::vector<uint64_t> cmask((size_t)B * 4, 0);
+  if (cols)
+    for (int c = 0; c < B; ++c)
+      for (int v = 0; v < n_validities; ++v)
+        if (compat[(size_t)col_belief[(size_t)c] * n_validities + v]) cmask[(size_t)c * 4 + v / 64] |= (uint64_t)1 << (v % 64);
+  // final belief nodes as indices into the table the backups run on ([column][node] for the column solver, else [node][belief])
+  if (cols)
+    for (int64_t& z : zero_idx) { const int64_t f = z / B; const int b2 = (int)(z % B); z = (int64_t)colpos[(size_t)b2] * V + f; }
+
   DevBuf& g = ctx->scratch[3];
-  const size_t n_succ = succ_belief.size();
-  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 16 + (size_t)V * 24 + succ_ptr.size() * 8 + n_succ * 12 + 2 * compat.size() + (size_t)V * 21 + 64 + (size_t)V * ((B + 31) / 32) * 5 + 64 + (size_t)V * B * 9 +
-                      zero_idx.size() * 8 + 512;
+  const size_t need = (size_t)(V + 1) * 16 + (size_t)E * 28 + (size_t)V * 16 + 2 * compat.size() + (size_t)V * 17 +
+                      (size_t)B * 40 + (size_t)V * B * 18 + zero_idx.size() * 8 + 24 * 16 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
   int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
   double* d_cost = (double*)take((size_t)E * 8);
   double* d_xy = (double*)take((size_t)V * 16);
-  int64_t* d_succ_ptr = (int64_t*)take(succ_ptr.size() * 8);
-  double* d_succ_p = (double*)take(n_succ * 8);
-  double* d_dist = (double*)take((size_t)V * B * 8);
+  double* d_dist = (double*)take((size_t)V * B * 8);       // [node][belief]: the caller's layout
+  double* d_dist_cm = (double*)take((size_t)V * B * 8);    // [column][node]: the column solver's table
+  uint64_t* d_cmask = (uint64_t*)take((size_t)B * 32);
   int32_t* d_col = (int32_t*)take((size_t)E * 4);
   int32_t* d_evid = (int32_t*)take((size_t)E * 4);
+  uint32_t* d_ce = (uint32_t*)take((size_t)E * 4);
+  uint32_t* d_rs = (uint32_t*)take((size_t)(V + 1) * 4);
+  uint32_t* d_cursor = (uint32_t*)take((size_t)(V + 1) * 4);
+  double* d_cost_t = (double*)take((size_t)E * 8);
   int32_t* d_nvid = (int32_t*)take((size_t)V * 4);
   int32_t* d_nset = (int32_t*)take((size_t)V * 4);
-  int32_t* d_succ_b = (int32_t*)take(n_succ * 4);
+  int32_t* d_colpos = (int32_t*)take((size_t)B * 4);
+  int32_t* d_col_belief = (int32_t*)take((size_t)B * 4);
   int32_t* d_changed = (int32_t*)take(16);
   uint8_t* d_compat = (uint8_t*)take(compat.size());
   uint8_t* d_compat_t = (uint8_t*)take(compat.size());
   uint8_t* d_active = (uint8_t*)take((size_t)V);
-  int32_t* d_order = (int32_t*)take((size_t)V * 16);
-  const int wpn = (B + 31) / 32;                                   // warps (belief chunks) per node
-  int32_t* d_chunk_epoch = (int32_t*)take((size_t)V * wpn * 4);
-  uint8_t* d_has_obs = (uint8_t*)take((size_t)V * wpn);
   int32_t* d_epoch = (int32_t*)take((size_t)V * 4);
   uint8_t* d_type = (uint8_t*)take((size_t)V * B);
+  uint8_t* d_type_cm = (uint8_t*)take((size_t)V * B);
   int64_t* d_zero = (int64_t*)take(zero_idx.size() * 8 + 8);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
   if (E) {
@@ -1153,90 +1090,84 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_nvid, node_vid, (size_t)V * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_nset, node_set.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_ptr, succ_ptr.data(), succ_ptr.size() * 8, cudaMemcpyHostToDevice, st));
-  if (n_succ) {
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_b, succ_belief.data(), n_succ * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_succ_p, succ_p.data(), n_succ * 8, cudaMemcpyHostToDevice, st));
-  }
   CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, compat.data(), compat.size(), cudaMemcpyHostToDevice, st));
-  std::vector<uint8_t> compat_t(compat.size());
-  for (int bb = 0; bb < B; ++bb)
-    for (int v = 0; v < n_validities; ++v) compat_t[(size_t)v * B + bb] = compat[(size_t)bb * n_validities + v];
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_compat_t, compat_t.data(), compat_t.size(), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemsetAsync(d_epoch, 0, (size_t)V * 4, st));
-  // sweep orders: nodes sorted by +x, -x, +y, -y (ties by id), cycled sweep by sweep
-  // Measured and left OFF (PORRT_BELIEF_ORDERED=1 turns it on): c4 shape 72-80 sweeps / 44 ms either way, c3 5.5 vs 4.5 ms.  A CPU
-  // replay explains it: ~300 k threads are in flight, i.e. ~74 nodes x 4095 beliefs are evaluated "simultaneously"; at that
-  // granularity a 4-direction order saves 12 % of the sweeps of a plain SSSP on this roadmap (40 -> 35), while a truly sequential
-  // sweep would need 9 -- roadmap paths wiggle more than the 0.03-wide x-slab such a wave covers.
-  static const bool ordered = getenv("PORRT_BELIEF_ORDERED") != nullptr;
-  std::vector<int32_t> order((size_t)V * 4);
-  if (ordered) {
-    for (int d = 0; d < 4; ++d) {
-      int32_t* o = order.data() + (size_t)d * V;
-      for (int64_t i = 0; i < V; ++i) o[i] = (int32_t)i;
-      const int ax = d >> 1;
-      const bool desc = d & 1;
-      std::sort(o, o + V, [&](int32_t a, int32_t c) {
-        const double va = xy[2 * (int64_t)a + ax], vc = xy[2 * (int64_t)c + ax];
-        if (va != vc) return desc ? va > vc : va < vc;
-        return a < c;
-      });
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_order, order.data(), (size_t)V * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_colpos, colpos.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_col_belief, col_belief.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_cmask, cmask.data(), cmask.size() * 8, cudaMemcpyHostToDevice, st));
+  std::vector<uint8_t> compat_t;
+  if (!cols) {   // the sweeps read the table transposed: the threads of a node (consecutive beliefs) read consecutive bytes
+    compat_t.resize(compat.size());
+    for (int bb = 0; bb < B; ++bb)
+      for (int v = 0; v < n_validities; ++v) compat_t[(size_t)v * B + bb] = compat[(size_t)bb * n_validities + v];
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_compat_t, compat_t.data(), compat_t.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_epoch, 0, (size_t)V * 4, st));
   }
-  fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_dist, V * (int64_t)B);
+  double* d_table = cols ? d_dist_cm : d_dist;
+  fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_table, V * (int64_t)B);
   LAUNCH_CHECK(ctx);
   if (!zero_idx.empty()) {
     CUDA_TRY(ctx, cudaMemcpyAsync(d_zero, zero_idx.data(), zero_idx.size() * 8, cudaMemcpyHostToDevice, st));
-    scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_dist, d_zero, (int64_t)zero_idx.size());
+    scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_table, d_zero, (int64_t)zero_idx.size());
     LAUNCH_CHECK(ctx);
   }
   edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
   LAUNCH_CHECK(ctx);
-  BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, d_compat_t, d_succ_ptr, d_succ_b, d_succ_p, V, B, n_validities};
+  BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, d_compat_t, succ.succ_ptr, succ.succ_b, succ.succ_p, V, B, n_validities};
   const int blocks = div_up(V * (int64_t)B, 256);
-  belief_type_kernel<<<blocks, 256, 0, st>>>(gd, d_type);
+  belief_type_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_colpos, cols ? d_type_cm : nullptr);
   LAUNCH_CHECK(ctx);
-  // measured and left OFF (PORRT_BELIEF_CHUNK_SKIP=1): c4 shape 53-55 ms of sweeps against 43 ms with the per-node flags, c3 5.0
-  // against 4.5 ms -- reading one epoch per child and chunk costs more than the evaluations it saves
-  static const bool chunked = getenv("PORRT_BELIEF_CHUNK_SKIP") != nullptr && !ordered;
-  if (chunked) {
-    CUDA_TRY(ctx, cudaMemsetAsync(d_chunk_epoch, 0, (size_t)V * wpn * 4, st));
-    belief_chunk_obs_kernel<<<div_up(V * wpn * 32, 256), 256, 0, st>>>(d_type, V, B, wpn, d_has_obs);
-    LAUNCH_CHECK(ctx);
+  if (cols) {
+    int32_t rc = colsolve_pack(ctx, d_row, d_col, d_evid, d_cost, V, E, d_rs, d_ce, d_cost_t, d_cursor, st);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
   int sweeps = 0;
-  const int BATCH = ordered ? 4 : 8;   // sweeps between two convergence checks
-  static const bool skip = getenv("PORRT_BELIEF_NO_SKIP") == nullptr;   // A/B switch for the work skipping
-  for (;;) {
-    CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
-    for (int k = 0; k < BATCH; ++k) {
-      ++sweeps;
-      if (chunked) {
-        belief_sweep_chunk_kernel<<<div_up(V * wpn * 32, 256), 256, 0, st>>>(gd, d_type, d_dist, d_changed, wpn, d_has_obs, d_chunk_epoch, d_epoch, sweeps);
-        LAUNCH_CHECK(ctx);
-        continue;
+  if (cols) {
+    // One launch per level; the CTAs of a level solve their columns on chip to the fixed point (colsolve.cu).  With a communicator
+    //  the columns of a level are sharded over the ranks and all-gathered before the next level reads them.
+    ColSolveArgs ca = {};
+    ca.row_start = d_rs; ca.cost = d_cost_t; ca.ce = d_ce; ca.V = (int32_t)V; ca.ld = V; ca.dist_cm = d_dist_cm; ca.cmask = d_cmask;
+    ca.nvid = d_nvid; ca.type_cm = d_type_cm; ca.node_set = d_nset; ca.col_belief = d_col_belief; ca.succ_ptr = succ.succ_ptr;
+    ca.succ_col = succ.succ_col; ca.succ_p = succ.succ_p; ca.B = B; ca.sweeps_out = d_changed;
+    for (size_t lv = 0; lv + 1 < level_start.size(); ++lv) {
+      const int lo = level_start[lv], hi = level_start[lv + 1];
+      int64_t mlo = 0, mhi = hi - lo;
+      if (sharded) comm_shard_range(hi - lo, ctx->comm_rank, ctx->comm_world, &mlo, &mhi);
+      int32_t rc = colsolve_level(ctx, ca, COLSOLVE_BELIEF, lo + (int)mlo, lo + (int)mhi, st);
+      if (rc) return rc;
+      if (sharded) {
+        std::vector<int64_t> off(ctx->comm_world + 1);
+        for (int r = 0; r < ctx->comm_world; ++r) {
+          int64_t a2, b2; comm_shard_range(hi - lo, r, ctx->comm_world, &a2, &b2);
+          off[r] = (lo + a2) * V * 8; off[r + 1] = (lo + b2) * V * 8;
+        }
+        rc = comm_all_gatherv_dev(ctx, nullptr, d_dist_cm, off.data(), st);
+        if (rc) return rc;
       }
-      if (ordered) {
-        belief_sweep_ordered_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_dist, d_changed, d_order + (size_t)((sweeps - 1) & 3) * V, d_epoch, sweeps);
-        LAUNCH_CHECK(ctx);
-        continue;
-      }
-      if (skip) {
+    }
+    belief_untranspose_kernel<<<dim3(div_up(V, 32), div_up(B, 32)), 256, 0, st>>>(d_dist_cm, V, d_colpos, V, B, d_dist);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(&sweeps, d_changed, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  } else {
+    const int BATCH = 8;   // sweeps between two convergence checks
+    for (;;) {
+      CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
+      for (int k = 0; k < BATCH; ++k) {
+        ++sweeps;
         belief_active_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, V, d_epoch, sweeps, d_active);
         LAUNCH_CHECK(ctx);
+        belief_sweep_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_dist, d_changed, d_active, d_epoch, sweeps);
+        LAUNCH_CHECK(ctx);
       }
-      belief_sweep_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_dist, d_changed, skip ? d_active : nullptr, skip ? d_epoch : nullptr, sweeps);
-      LAUNCH_CHECK(ctx);
+      int32_t changed = 0;
+      CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (!changed) break;
+      if (sweeps > 4 * V * (int64_t)B + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "belief_vi: no convergence");
     }
-    int32_t changed = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    if (!changed) break;
-    if (sweeps > 4 * V * (int64_t)B + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "belief_vi: no convergence");
   }
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
   // results: to the caller and retained for porrt_extract_policy
@@ -1250,24 +1181,42 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   double* h_dist = ctx->pin[3].as<double>();
   uint8_t* h_type = (uint8_t*)(h_dist + (size_t)V * B);
   R.dist = h_dist; R.type = h_type;
-  R.node_obs_set = node_set; R.succ_ptr = succ_ptr; R.succ_belief = succ_belief; R.compat = compat;
+  R.node_obs_set = node_set; R.compat = compat;
+  R.succ_ptr.resize(sets.size() * (size_t)B + 1); R.succ_belief.resize((size_t)succ.n_succ);   // the policy walk reads them on the host
+  CUDA_TRY(ctx, cudaMemcpyAsync(R.succ_ptr.data(), succ.succ_ptr, R.succ_ptr.size() * 8, cudaMemcpyDeviceToHost, st));
+  if (succ.n_succ) CUDA_TRY(ctx, cudaMemcpyAsync(R.succ_belief.data(), succ.succ_b, (size_t)succ.n_succ * 4, cudaMemcpyDeviceToHost, st));
   type_finish_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_type, V * (int64_t)B);
   LAUNCH_CHECK(ctx);
-  CUDA_TRY(ctx, cudaMemcpyAsync(h_dist, d_dist, (size_t)V * B * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(h_type, d_type, (size_t)V * B, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
   std::vector<int32_t> nvid(node_vid, node_vid + V);
-  {  // the caller's copies, by a few host threads (150 MB at B = 4095)
+  {
+    // The table comes back by DMA into the pinned retained copy in pieces; host threads hand each piece on to the caller's
+    // buffer as soon as its event has fired, so the second copy (172 MB at B = 4095) hides behind the first.
     const size_t nb = (size_t)V * B;
-    const int nt = nb > (1u << 20) ? 8 : 1;
-    std::vector<std::thread> th;
-    for (int k = 0; k < nt; ++k)
-      th.emplace_back([&, k]() {
-        const size_t lo = nb * (size_t)k / (size_t)nt, hi = nb * (size_t)(k + 1) / (size_t)nt;
-        memcpy(out_dist + lo, h_dist + lo, (hi - lo) * 8);
+    const int n_pieces = nb > (1u << 20) ? 8 : 1;
+    for (int k = 0; k < n_pieces; ++k) {
+      const size_t lo = nb * (size_t)k / (size_t)n_pieces, hi = nb * (size_t)(k + 1) / (size_t)n_pieces;
+      CUDA_TRY(ctx, cudaMemcpyAsync(h_dist + lo, d_dist + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaMemcpyAsync(h_type + lo, d_type + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t[k], st));
+    }
+    const int nt = n_pieces > 1 ? 4 : 1;
+    std::vector<int> bad((size_t)nt, 0);
+    auto hand_on = [&](int t) {
+      for (int k = t; k < n_pieces; k += nt) {
+        if (cudaEventSynchronize(ctx->ev_t[k]) != cudaSuccess) { bad[(size_t)t] = 1; return; }
+        const size_t lo = nb * (size_t)k / (size_t)n_pieces, hi = nb * (size_t)(k + 1) / (size_t)n_pieces;
+        if (out_dist) memcpy(out_dist + lo, h_dist + lo, (hi - lo) * 8);
         if (out_type) memcpy(out_type + lo, h_type + lo, hi - lo);
-      });
-    for (auto& t : th) t.join();
+      }
+    };
+    if (nt == 1) hand_on(0);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back(hand_on, t);
+      for (auto& t : th) t.join();
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    for (int x : bad) if (x) return porrt_fail(ctx, PORRT_ERR_CUDA, "belief_vi: result copy failed");
   }
   if (out_sweeps) *out_sweeps = sweeps;
   t1 = now_ms(); ph[3] = t1 - t0;
@@ -1275,6 +1224,18 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   // keep node/edge validity ids for the policy walk
   R.edge_vid.assign(edge_vid, edge_vid + E);
   ctx->bel_node_vid = nvid;
+  return PORRT_OK;
+}
+
+// The retained table of the last porrt_belief_vi (pinned host memory owned by the ctx, valid until the next call): the
+// reference's own FFI hands results out the same way (pointer getters over handle-owned vectors, pto_c.rs:255-270).
+PORRT_API int32_t porrt_belief_result(porrt_ctx* ctx, const double** out_dist, const uint8_t** out_type, int64_t* out_V, int32_t* out_B) {
+  CTX_CHECK(ctx);
+  if (ctx->bel.V <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_result: run porrt_belief_vi first");
+  if (out_dist) *out_dist = ctx->bel.dist;
+  if (out_type) *out_type = ctx->bel.type;
+  if (out_V) *out_V = ctx->bel.V;
+  if (out_B) *out_B = ctx->bel.B;
   return PORRT_OK;
 }
 

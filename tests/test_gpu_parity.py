@@ -612,6 +612,16 @@ def test_belief_planning_shelf_8_goals_config3(ctx):
     finals = [pto.reach.get_final_nodes_for_world(w) for w in range(Z)]
     got, _ = P.dijkstra_worlds(ctx, rp, col, xy, nvid, pmap.world_validities_words(), finals)
     np.testing.assert_array_equal(got, pto.plan_qmdp())
+    # the same two problems through the sweeps over global memory (the path of roadmaps too large for colsolve.cu)
+    ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 1)
+    try:
+        fin_ids, fin_bits = pto.reach.finals()
+        plan2 = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, [1.0 / Z] * Z, fin_ids, P.words_from_bits(fin_bits))
+        got2, _ = P.dijkstra_worlds(ctx, rp, col, xy, nvid, pmap.world_validities_words(), finals)
+    finally:
+        ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 0)
+    np.testing.assert_array_equal(plan2.dist, plan.dist)
+    np.testing.assert_array_equal(got2, got)
 
 
 def test_belief_planning_12_goals_config4_full_size(ctx):
@@ -642,6 +652,15 @@ def test_belief_planning_12_goals_config4_full_size(ctx):
         assert (plan.type[:, b] != P.NODE_OBSERVATION).all()
     again = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
     np.testing.assert_array_equal(again.dist, plan.dist)
+    # the two independent schedules -- on-chip column solver level by level (colsolve.cu) and order-free sweeps over the table in
+    # global memory (graph.cu) -- must give every one of the 1.9e7 entries bit for bit
+    ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 1)
+    try:
+        sweeps = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
+    finally:
+        ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 0)
+    np.testing.assert_array_equal(sweeps.dist, plan.dist)
+    np.testing.assert_array_equal(sweeps.type, plan.type)
     root = plan.dist[0, 0]
     assert np.isfinite(root) and root >= sum(plan.dist[0, informed[z]] for z in range(Z)) / Z - 1e-12
     assert plan.expected_cost == root and int(plan.policy_leaf.sum()) == Z
