@@ -287,6 +287,11 @@ def side_measurements(ctx, pmap, args):
     except Exception as e:
         import traceback
         ex["belief_c3"] = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
+    try:
+        ex["belief_c4"] = belief_measurement(ctx, Z=12, visibility=0.2, max_step=0.05, search_radius=5.0, check="sweeps")
+    except Exception as e:
+        import traceback
+        ex["belief_c4"] = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
     return ex
 
 
@@ -360,6 +365,29 @@ def multi_gpu_measurements(ctx, pmap, rank, world, dev):
                                 "note": "one roadmap built by all ranks; bins, kd ranks and the CSR assembly are replicated, "
                                         "radius + order + edge batches are sharded; the CSR ends device-resident on every rank, "
                                         "rank 0 alone copies the column array to the host"}
+    # belief-space planning at the config-4 shape: the columns of every belief level are sharded over the ranks and all-gathered
+    # before the next level reads them (graph.cu / colsolve.cu); every rank ends with the whole table
+    try:
+        prob = belief_problem(12, 0.2, 0.05, 5.0)
+        dist.barrier()
+        plan, best, _ = belief_run(ctx, prob)
+        wall, dev_ms = rmax(best[0]), rmax(best[2][0])
+        solo = P.Context(dev.index)
+        try:
+            ref_plan, ref_best, _ = belief_run(solo, prob, reps=2)
+            same = bool(np.array_equal(ref_plan.dist, plan.dist))
+        finally:
+            solo.close()
+        tsame = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tsame, op=dist.ReduceOp.MIN)
+        out["belief_c4_sharded"] = {"nodes": int(plan.dist.shape[0]), "beliefs": int(plan.dist.shape[1]), "ms_max_over_ranks": 1e3 * wall,
+                                    "backups_device_ms_max": dev_ms, "single_gpu_ms_rank0": 1e3 * ref_best[0],
+                                    "single_gpu_backups_device_ms": ref_best[2][0],
+                                    "phase_ms_rank0[tables,upload+types,backups,result]": [round(x, 3) for x in best[1]],
+                                    "bit_exact_vs_single_gpu_all_ranks": bool(tsame.item() == 1.0), "scaling": "strong"}
+    except Exception as e:
+        import traceback
+        out["belief_c4_sharded"] = {"error": repr(e) + " | " + traceback.format_exc()[-400:]}
     ctx.comm_destroy()
     return out
 
@@ -390,50 +418,88 @@ def refiner_measurement(ctx, pmap, n_pieces=64, n_states=30, n_iterations=1000):
             "commits": int(commits.sum()), "gpu_ms": 1e3 * t_gpu, "cpu_oracle_ms_1thread": 1e3 * t_cpu, "bit_exact": bool(exact)}
 
 
-def belief_measurement(ctx, Z=8, n_min=5000):
-    """BASELINE config 3 shape (8 goal zones, B = 255 beliefs) on a stand-in shelf map: the PTO roadmap is grown by the oracle
-    (sequential growth is out of scope), then belief-space planning = implicit belief graph + value sweeps on the
-    device (rows C2-C4) against the oracle's materialised belief graph + conditional_dijkstra, with a bit-exact comparison."""
-    import po_rrt_b200 as P
+def belief_problem(Z, visibility, max_step, search_radius, n_min=5000):
+    """the PTO roadmap of a BASELINE config-3 / config-4 shaped problem on a stand-in shelf map, grown by the oracle (sequential
+    growth is out of scope)"""
     from po_rrt_b200 import synth
     from oracle import pyoracle as O
     occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
     low, up = [-1.0, -1.0], [1.0, 1.0]
-    omap = O.GridMap(occ, zones, low, up, O.SHELF, 0.5)
-    pmap = P.MapShelfDomain(ctx, occ, low, up)
-    pmap.add_zones(zones, 0.5)
+    omap = O.GridMap(occ, zones, low, up, O.SHELF, visibility)
     zp = omap.zone_positions()
     goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
     pto = O.PTO(omap, low, up, seed=0)
-    t0 = time.perf_counter(); rc = pto.grow_graph((0.0, -0.9), O.SquareGoal(goals, 0.05), 0.1, 2.0, n_min, 100000); t_grow = time.perf_counter() - t0
+    t0 = time.perf_counter(); rc = pto.grow_graph((0.0, -0.9), O.SquareGoal(goals, 0.05), max_step, search_radius, n_min, 100000); t_grow = time.perf_counter() - t0
     if rc != 0:
-        return {"error": "roadmap growth failed (rc %d)" % rc}
-    b0 = [1.0 / Z] * Z
+        raise RuntimeError("roadmap growth failed (rc %d)" % rc)
+    return {"occ": occ, "zones": zones, "low": low, "up": up, "visibility": visibility, "pto": pto, "Z": Z, "grow_ms": 1e3 * t_grow}
+
+
+def belief_run(ctx, prob, reps=3, copy=False):
+    """plan_belief_space on the device: reachable beliefs + visibility + implicit belief graph + value backups + policy;
+    best of `reps` wall times, the phases of the best run and the column solver's device counters"""
+    import po_rrt_b200 as P
+    pmap = P.MapShelfDomain(ctx, prob["occ"], prob["low"], prob["up"])
+    pmap.add_zones(prob["zones"], prob["visibility"])
+    pto, Z = prob["pto"], prob["Z"]
     xy, nvid, rp, col, ev = pto.graph.export(0)
     fin_ids, fin_bits = pto.reach.finals()
+    fm = P.words_from_bits(fin_bits)
     best = None
-    for _ in range(3):
+    for _ in range(reps):
         t0 = time.perf_counter()
-        plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
+        plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, [1.0 / Z] * Z, fin_ids, fm, copy=copy)
         t = time.perf_counter() - t0
         if best is None or t < best[0]:
-            best = (t, [float(x) for x in plan.phase_ms])
+            best = (t, [float(x) for x in plan.phase_ms], list(ctx.last_phase_ms()[:2]))
+    return plan, best, (xy, nvid, rp, col, ev, fin_ids, fm, pmap)
+
+
+def belief_measurement(ctx, Z=8, n_min=5000, visibility=0.5, max_step=0.1, search_radius=2.0, check="oracle"):
+    """BASELINE config 3 (8 goal zones, B = 255 beliefs; main.rs:757-799) / config 4 (12 zones, B = 4095; main.rs:386-411) shapes on a
+    stand-in shelf map: belief-space planning = implicit belief graph + value backups on the device (rows C2-C4).  check = "oracle":
+    against the oracle's materialised belief graph + conditional_dijkstra, bit for bit (config 4 is intractable there, main.rs:385);
+    check = "sweeps": against the library's second, independent schedule (order-free sweeps over the table in global memory)."""
+    import po_rrt_b200 as P
+    prob = belief_problem(Z, visibility, max_step, search_radius, n_min)
+    plan, best, (xy, nvid, rp, col, ev, fin_ids, fm, pmap) = belief_run(ctx, prob)
     V, E, B = len(nvid), len(col), len(plan.beliefs)
-    t0 = time.perf_counter(); pto.build_belief_graph(b0); t_build = time.perf_counter() - t0
-    t0 = time.perf_counter(); want = pto.compute_expected_costs_to_goals(); t_dp = time.perf_counter() - t0
-    t0 = time.perf_counter(); opol = pto.extract_policy(); t_pol = time.perf_counter() - t0
-    exact = bool(np.array_equal(plan.dist.reshape(-1), want) and
-                 np.array_equal(plan.policy_node.astype(np.int64) * B + plan.policy_belief, opol.original))
-    sweep_ms = best[1][2]
-    gather = float(E) * B * 8 + float(V) * B * 16          # dist of every child per (node, belief) + own read/write, per sweep
-    return {"zones": Z, "nodes": V, "directed_edges": E, "beliefs": B, "belief_nodes": V * B, "sweeps": int(plan.sweeps),
-            "gpu_ms_total": 1e3 * best[0], "gpu_phase_ms[host tables,upload+types,sweeps,download]": [round(x, 3) for x in best[1]],
-            "sweep_bytes_each": gather, "sweep_equiv_gbs": gather * plan.sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
-            "cpu_oracle_ms[build_belief_graph,conditional_dijkstra,extract_policy]": [round(1e3 * t_build, 1), round(1e3 * t_dp, 1), round(1e3 * t_pol, 2)],
-            "roadmap_growth_cpu_ms": round(1e3 * t_grow, 1), "bit_exact": exact,
-            "note": "sweep_equiv_gbs = bytes of FULL sweeps / time: with work skipping (nodes whose inputs did not change are not "
-                    "re-evaluated) part of those bytes is never read, so it is an equivalent rate, not a measured bandwidth; the dist "
-                    "table (V*B f64) is L2-resident"}
+    out = {"zones": Z, "nodes": V, "directed_edges": E, "beliefs": B, "belief_nodes": V * B, "rounds_max": int(plan.sweeps),
+           "gpu_ms_total": 1e3 * best[0],
+           "gpu_phase_ms[tables,upload+types,backups,result]": [round(x, 3) for x in best[1]],
+           "call": "plan_belief_space: porrt_reachable_belief_states + porrt_visibility + porrt_belief_vi + porrt_extract_policy; "
+                   "the V*B table is read through porrt_belief_result (ctx-owned pinned memory)",
+           "roadmap_growth_cpu_ms": round(prob["grow_ms"], 1)}
+    dev_ms, offers = best[2]
+    if dev_ms and dev_ms > 0:
+        out["backups_device"] = {"ms": dev_ms, "edge_records": int(offers), "l2_bytes": int(offers) * 12,
+                                 "l2_gbs": offers * 12 / (dev_ms * 1e-3) / 1e9,
+                                 "full_sweep_records": E * B, "equivalent_full_sweeps": offers / float(E * B),
+                                 "note": "on-chip column solver (colsolve.cu): a record = one 12-byte (parent, validity id, cost) entry of "
+                                         "the transposed adjacency read from L2 when a node's value improved; the value table never "
+                                         "leaves shared memory between the first and the last round of a column"}
+    if check == "oracle":
+        pto = prob["pto"]
+        b0 = [1.0 / Z] * Z
+        t0 = time.perf_counter(); pto.build_belief_graph(b0); t_build = time.perf_counter() - t0
+        t0 = time.perf_counter(); want = pto.compute_expected_costs_to_goals(); t_dp = time.perf_counter() - t0
+        t0 = time.perf_counter(); opol = pto.extract_policy(); t_pol = time.perf_counter() - t0
+        out["cpu_oracle_ms[build_belief_graph,conditional_dijkstra,extract_policy]"] = [round(1e3 * t_build, 1), round(1e3 * t_dp, 1), round(1e3 * t_pol, 2)]
+        out["bit_exact"] = bool(np.array_equal(plan.dist.reshape(-1), want) and
+                                np.array_equal(plan.policy_node.astype(np.int64) * B + plan.policy_belief, opol.original))
+    else:
+        keep = plan.dist.copy()
+        ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 1)
+        try:
+            t0 = time.perf_counter()
+            other = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, [1.0 / Z] * Z, fin_ids, fm, copy=False)
+            out["global_sweeps_ms_total"] = 1e3 * (time.perf_counter() - t0)
+            out["global_sweeps_phase_ms"] = [round(float(x), 3) for x in other.phase_ms]
+            out["global_sweeps"] = int(other.sweeps)
+        finally:
+            ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 0)
+        out["bit_exact_vs_global_sweeps"] = bool(np.array_equal(other.dist, keep))
+    return out
 
 _REAL_STDOUT = None
 

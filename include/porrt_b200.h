@@ -190,6 +190,8 @@ int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, con
  *   visible_zone_mask[V]                 from porrt_visibility
  *   finals: node ids + their finality masks [n_finals * mask_words]   (pto_reachability.rs:77-79)
  * out_dist[V * B] = expected_costs_to_goals (inf where unreachable / non-existent), out_type[V * B] node types. */
+/* porrt_ctx_last_phase_ms after the call: [0] device ms of the value backups (all levels of the on-chip column solver, CUDA
+ * events), [1] edge records the solver worked through (12 bytes each, read from L2) -- the bytes actually moved. */
 int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const int32_t* edge_vid,
                         const double* xy, const int32_t* node_vid, const uint64_t* validities, int32_t n_validities,
                         int32_t mask_words, int32_t n_worlds, const double* beliefs, int32_t B,

@@ -116,15 +116,17 @@ __global__ void __launch_bounds__(COLSOLVE_THREADS, 1) colsolve_push_kernel(ColS
   const uint8_t* dirty8 = reinterpret_cast<const uint8_t*>(s_dirty);
   const int nblk = (V + 31) / 32;
   int rounds = 0;
+  unsigned n_offers = 0;   // edge records this thread worked through (measurement: bytes actually read from L2)
   for (;;) {
     // ---- collect: the dirty nodes go to a queue so that the groups of the whole CTA share them evenly (a warp that worked off
     // its own 32-node blocks one after the other paid the L2 latency chain of every block in turn).  Nodes that do not fit stay
     // dirty for the next round; the scan start rotates so that no node waits forever.
     unsigned* qn_ptr = s_qn + (rounds & 1);   // two counters: the other one is reset while this one is in use
     bool found = false;
+    const int rot = (rounds * 7) % nblk;
     for (int bi = warp; bi < nblk; bi += nwarp) {
-      int blk = bi + rounds * 7;
-      blk -= (blk / nblk) * nblk;
+      int blk = bi + rot;
+      if (blk >= nblk) blk -= nblk;
       const int n = blk * 32 + lane;
       const bool d = n < V && dirty8[n] != 0;
       const unsigned todo = __ballot_sync(0xffffffffu, d);
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(COLSOLVE_THREADS, 1) colsolve_push_kernel(ColS
           for (int q = 0; q < COLSOLVE_UNROLL; ++q) {
             const uint32_t ce = ce_r[q];
             if (ce == 0xffffffffu) break;
+            ++n_offers;
             const double cost = cost_r[q];
             const unsigned adm = (MODE == COLSOLVE_WORLD ? 0xffu : s_adm[ce >> 16]) & m;
             if (!adm) continue;
@@ -193,6 +196,10 @@ __global__ void __launch_bounds__(COLSOLVE_THREADS, 1) colsolve_push_kernel(ColS
     for (int n = tid; n < V; n += nthr) gcol[n] = fabs(sd[(size_t)n * C + j]);
   }
   if (tid == 0 && a.sweeps_out) atomicMax(a.sweeps_out, rounds);
+  if (a.offers_out) {
+    for (int sft = 16; sft > 0; sft >>= 1) n_offers += __shfl_xor_sync(0xffffffffu, n_offers, sft);
+    if (lane == 0) atomicAdd(a.offers_out, (unsigned long long)n_offers);
+  }
 }
 
 __global__ void colsolve_count_kernel(const int32_t* __restrict__ col, int64_t E, uint32_t* __restrict__ cnt) {

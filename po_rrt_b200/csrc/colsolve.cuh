@@ -31,6 +31,7 @@ struct ColSolveArgs {
   const double* succ_p;
   int32_t B;
   int32_t* sweeps_out;         // max over CTAs (atomicMax), may be null
+  unsigned long long* offers_out;   // += edge records worked through (12 bytes each from L2), may be null
 };
 
 bool colsolve_fits(int64_t V, int64_t E, int32_t n_validities);

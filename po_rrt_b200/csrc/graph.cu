@@ -782,70 +782,104 @@ static uint64_t belief_hash(const double* bs, int n) {
   }
   return h;
 }
-static void successor_beliefs(const porrt_ctx* ctx, const Belief& b, int zone, std::vector<Belief>& out) {
-  const int n = (int)b.size();
-  Belief first = b, second = b;
+// observe_impl's split of one belief by one zone (map_io.rs:257-275, map_shelves_io.rs:217-236): [closed, open] resp.
+// [there, not there], each normalised; a zero-mass branch (NaN after the division) is dropped.  Appends to `out` (n doubles per
+// belief) and returns how many were kept.
+static int successor_beliefs(const porrt_ctx* ctx, const double* b, int n, int zone, std::vector<double>& out) {
+  const size_t base = out.size();
+  out.resize(base + 2 * (size_t)n);
+  double* first = out.data() + base;
+  double* second = first + n;
+  const bool door = ctx->map.kind == PORRT_DOMAIN_DOOR;
   for (int w = 0; w < n; ++w) {
-    bool in_zone_world;
-    if (ctx->map.kind == PORRT_DOMAIN_DOOR) in_zone_world = (ctx->zone_world_masks[(size_t)zone * ctx->mask_words + w / 64] >> (w % 64)) & 1;
-    else in_zone_world = (w == zone);
-    if (ctx->map.kind == PORRT_DOMAIN_DOOR) {  // [closed, open]
-      first[w] = in_zone_world ? 0.0 : b[w];
-      second[w] = in_zone_world ? b[w] : 0.0;
-    } else {                                   // [there, not there]
-      first[w] = in_zone_world ? b[w] : 0.0;
-      second[w] = in_zone_world ? 0.0 : b[w];
-    }
+    const bool in_zone_world = door ? ((ctx->zone_world_masks[(size_t)zone * ctx->mask_words + w / 64] >> (w % 64)) & 1) != 0 : (w == zone);
+    const bool to_first = door ? !in_zone_world : in_zone_world;
+    first[w] = to_first ? b[w] : 0.0;
+    second[w] = to_first ? 0.0 : b[w];
   }
-  for (Belief* c : {&first, &second}) {
+  int kept = 0;
+  for (int c = 0; c < 2; ++c) {
+    const double* src = out.data() + base + (size_t)c * n;
     double sum = 0.0;
-    for (double p : *c) sum = sum + p;
+    for (int w = 0; w < n; ++w) sum = sum + src[w];
     bool nan = false;
-    for (double& p : *c) { p /= sum; nan |= std::isnan(p); }
-    if (!nan) out.push_back(*c);
+    double* dst = out.data() + base + (size_t)kept * n;
+    for (int w = 0; w < n; ++w) { const double p = src[w] / sum; nan |= std::isnan(p); dst[w] = p; }
+    if (!nan) ++kept;
   }
+  out.resize(base + (size_t)kept * n);
+  return kept;
 }
 
+// MapShelfDomain / Map::reachable_belief_states (map_shelves_io.rs:490-520, map_io.rs:515-546): LIFO over (belief, zones not yet
+// observed); a successor that is not yet in the list (exact f64 equality) is explored, and appended unless its hash is taken.
 PORRT_API int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B) {
   CTX_CHECK(ctx);
   if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
   if (!start_belief || !out_B) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "reachable_belief_states: bad arguments");
   const int nw = ctx->n_worlds, nz = ctx->n_zones;
-  std::vector<Belief> reachable;
-  // `reachable_beliefs.contains(successor)` is a linear scan with exact f64 equality in the reference (71 ms at 12 zones /
-  // 4095 beliefs); an ordered map over the same vectors answers the same question (no NaNs reach this point: zero-mass
-  // branches are dropped by successor_beliefs; -0.0 == 0.0 under both orderings) and keeps the enumeration order untouched
-  std::map<Belief, int> known_set;
+  if (nz > 64) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "reachable_belief_states: more than 64 zones");
+  // `reachable_beliefs.contains(successor)` is a linear scan with exact f64 equality in the reference (71 ms at 12 zones / 4095
+  // beliefs); an open-addressing table over the raw bits answers the same question (no NaNs reach this point: zero-mass branches
+  // are dropped; the zeros written by the split and 0.0 / sum are +0.0, so equal values have equal bits) and leaves the
+  // enumeration order untouched.  Beliefs live back to back in one arena; a LIFO entry is (arena offset, zones left as bits).
+  std::vector<double> reachable(start_belief, start_belief + nw);    // the result list, nw doubles per belief
+  std::vector<double> arena(start_belief, start_belief + nw);        // every belief ever pushed on the LIFO
+  std::vector<int64_t> table(1024, -1);                               // offsets into `reachable`, open addressing
+  size_t n_known = 1;
+  auto bits_hash = [&](const double* b) {
+    uint64_t h = 1469598103934665603ull;
+    for (int w = 0; w < nw; ++w) { uint64_t u; memcpy(&u, b + w, 8); h = (h ^ u) * 1099511628211ull; h ^= h >> 29; }
+    return h;
+  };
+  auto same = [&](const double* x, const double* y) {
+    for (int w = 0; w < nw; ++w) if (!(x[w] == y[w])) return false;
+    return true;
+  };
+  auto find_slot = [&](const double* b) {   // slot holding b, or the empty slot where it belongs
+    size_t k = (size_t)bits_hash(b) & (table.size() - 1);
+    while (table[k] >= 0 && !same(reachable.data() + table[k], b)) k = (k + 1) & (table.size() - 1);
+    return k;
+  };
+  table[find_slot(start_belief)] = 0;
   std::unordered_map<uint64_t, int> hashes;
-  std::vector<std::pair<Belief, std::vector<int>>> lifo;
-  Belief b0(start_belief, start_belief + nw);
-  reachable.push_back(b0);
-  known_set.emplace(b0, 0);
-  std::vector<int> all(nz);
-  for (int z = 0; z < nz; ++z) all[z] = z;
-  lifo.push_back({b0, all});
-  std::vector<Belief> succ;
+  std::vector<std::pair<int64_t, uint64_t>> lifo;
+  lifo.push_back({0, nz >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << nz) - 1)});
+  std::vector<double> succ;
   while (!lifo.empty()) {
-    auto top = lifo.back();
+    const std::pair<int64_t, uint64_t> top = lifo.back();
     lifo.pop_back();
-    for (int zone : top.second) {
-      std::vector<int> remaining;
-      for (int z : top.second) if (z != zone) remaining.push_back(z);
+    for (int zone = 0; zone < nz; ++zone) {
+      if (!((top.second >> zone) & 1)) continue;
+      const uint64_t remaining = top.second & ~((uint64_t)1 << zone);
       succ.clear();
-      successor_beliefs(ctx, top.first, zone, succ);
-      for (const Belief& s : succ) {
-        const bool known = known_set.count(s) != 0;
-        if (!known) {
-          uint64_t h = belief_hash(s.data(), nw);
-          if (!hashes.count(h)) { hashes[h] = 1; reachable.push_back(s); known_set.emplace(s, 1); }
-          lifo.push_back({s, remaining});
+      const int kept = successor_beliefs(ctx, arena.data() + top.first, nw, zone, succ);
+      for (int c = 0; c < kept; ++c) {
+        const double* sb = succ.data() + (size_t)c * nw;
+        size_t slot = find_slot(sb);
+        if (table[slot] >= 0) continue;   // known
+        const uint64_t h = belief_hash(sb, nw);
+        if (!hashes.count(h)) {
+          hashes[h] = 1;
+          table[slot] = (int64_t)reachable.size();
+          reachable.insert(reachable.end(), sb, sb + nw);
+          if (++n_known * 2 > table.size()) {   // grow + rehash
+            std::vector<int64_t> old;
+            old.swap(table);
+            table.assign(old.size() * 4, -1);
+            for (int64_t off : old) if (off >= 0) table[find_slot(reachable.data() + off)] = off;
+          }
         }
+        const int64_t at = (int64_t)arena.size();
+        arena.insert(arena.end(), sb, sb + nw);
+        lifo.push_back({at, remaining});
       }
     }
   }
-  *out_B = (int32_t)reachable.size();
-  if ((int)reachable.size() > cap || !out) return porrt_fail(ctx, PORRT_ERR_CAPACITY, "reachable_belief_states: cap too small");
-  for (size_t k = 0; k < reachable.size(); ++k) memcpy(out + k * nw, reachable[k].data(), (size_t)nw * 8);
+  const size_t n_b = reachable.size() / (size_t)nw;
+  *out_B = (int32_t)n_b;
+  if ((int64_t)n_b > cap || !out) return porrt_fail(ctx, PORRT_ERR_CAPACITY, "reachable_belief_states: cap too small");
+  memcpy(out, reachable.data(), reachable.size() * 8);
   return PORRT_OK;
 }
 
@@ -1119,7 +1153,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   if (cols) {
     int32_t rc = colsolve_pack(ctx, d_row, d_col, d_evid, d_cost, V, E, d_rs, d_ce, d_cost_t, d_cursor, st);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 16, st));
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
@@ -1131,6 +1165,8 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     ca.row_start = d_rs; ca.cost = d_cost_t; ca.ce = d_ce; ca.V = (int32_t)V; ca.ld = V; ca.dist_cm = d_dist_cm; ca.cmask = d_cmask;
     ca.nvid = d_nvid; ca.type_cm = d_type_cm; ca.node_set = d_nset; ca.col_belief = d_col_belief; ca.succ_ptr = succ.succ_ptr;
     ca.succ_col = succ.succ_col; ca.succ_p = succ.succ_p; ca.B = B; ca.sweeps_out = d_changed;
+    ca.offers_out = (unsigned long long*)(d_changed + 2);
+    tstart(ctx);
     for (size_t lv = 0; lv + 1 < level_start.size(); ++lv) {
       const int lo = level_start[lv], hi = level_start[lv + 1];
       int64_t mlo = 0, mhi = hi - lo;
@@ -1147,10 +1183,15 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
         if (rc) return rc;
       }
     }
+    tmark(ctx);
     belief_untranspose_kernel<<<dim3(div_up(V, 32), div_up(B, 32)), 256, 0, st>>>(d_dist_cm, V, d_colpos, V, B, d_dist);
     LAUNCH_CHECK(ctx);
+    unsigned long long offers = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&sweeps, d_changed, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&offers, d_changed + 2, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    tfinish(ctx);   // porrt_ctx_last_phase_ms: [0] device ms of the column solver (all levels), [1] edge records it worked through
+    ctx->last_ms[1] = (double)offers; ctx->n_last = 2;
   } else {
     const int BATCH = 8;   // sweeps between two convergence checks
     for (;;) {

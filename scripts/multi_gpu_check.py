@@ -8,6 +8,7 @@ porrt_comm_all_gather_dev) and `solo` without one (the single-GPU result).  Chec
   1. sharded PRM build == single-GPU PRM build == the oracle's PRM (CSR in the reference's insertion order), on every rank
   2. sharded plan_qmdp dist rows == single-GPU == oracle
   3. all-gathered per-shard edge validity ids / world masks == the whole batch evaluated on one GPU
+  4. belief-space value backups with the columns of every level sharded over the ranks == single GPU == oracle
 --big adds timings at the c5 shape (8192^2 map, V = 1e6 PRM build) and prints them as JSON on rank 0.
 The oracle is used here as the checker only.
 """
@@ -113,6 +114,30 @@ def main():
     np.testing.assert_array_equal(mask_all.cpu().numpy().view(np.uint64), want_mask.reshape(-1))
     np.testing.assert_array_equal(want_vid, omap.edge_validity(fa, fb))
     report["gathered_edges"] = E
+
+    # ---- 4. belief-space value backups: the columns of every belief level sharded over the ranks, all-gathered per level
+    for Z, nmin in ((5, 1500), (3, 700)):          # 31 / 7 beliefs: levels with fewer columns than ranks included
+        socc, szones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
+        somap = O.GridMap(socc, szones, [-1.0, -1.0], [1.0, 1.0], O.SHELF, 0.5)
+        zp = somap.zone_positions()
+        goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
+        pto = O.PTO(somap, [-1.0, -1.0], [1.0, 1.0], seed=0)
+        assert pto.grow_graph((0.0, -0.9), O.SquareGoal(goals, 0.05), 0.1, 2.0, nmin, 100000) == 0
+        bxy, bnvid, brp, bcol, bev = pto.graph.export(0)
+        fin_ids, fin_bits = pto.reach.finals()
+        plans = []
+        for c in (ctx, solo):
+            bm = P.MapShelfDomain(c, socc, [-1.0, -1.0], [1.0, 1.0])
+            bm.add_zones(szones, 0.5)
+            plans.append(P.plan_belief_space(bm, brp, bcol, bev, bxy, bnvid, [1.0 / Z] * Z, fin_ids, P.words_from_bits(fin_bits)))
+        np.testing.assert_array_equal(plans[0].dist, plans[1].dist)
+        np.testing.assert_array_equal(plans[0].type, plans[1].type)
+        np.testing.assert_array_equal(plans[0].policy_node, plans[1].policy_node)
+        pto.build_belief_graph([1.0 / Z] * Z)
+        np.testing.assert_array_equal(plans[0].dist.reshape(-1), pto.compute_expected_costs_to_goals())
+    report["belief_vi_sharded_levels"] = True
+    for m in (pmap, smap):      # the belief problems replaced the ctx maps
+        m.add_zones(zones, 0.3)
 
     if args.big:
         occ, zones = synth.door_map(size=8192, n_rects=4096, n_zones=6, seed=1)
