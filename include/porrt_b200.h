@@ -133,6 +133,10 @@ int32_t porrt_visibility_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, ui
 int32_t porrt_vertices_set(porrt_ctx* ctx, const double* xy, int64_t n, double cell_size);
 int32_t porrt_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size,
                                const double bbox_lo[2], const double bbox_hi[2]);
+/* KdTree::add (nearest_neighbor.rs:29-46), batched: the m new vertices get the ids n .. n+m-1.  Only the new coordinates cross
+ * the bus; the cell grid is rebuilt on the device (from the resident set, with the cell-size rule of the last porrt_vertices_set)
+ * before the next query.  This is what the sequential planners (RRT, PTO growth) call once per accepted sample. */
+int32_t porrt_vertices_append(porrt_ctx* ctx, const double* xy, int64_t m);
 int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n);
 
 /* KdTree::nearest_neighbors[_filtered] (nearest_neighbor.rs:94-126), batched: all ids j with
@@ -140,8 +144,8 @@ int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n);
  *   and j < prefix_limit[i]             (if prefix_limit != NULL: the tree as it was before vertex prefix_limit[i] was added)
  *   and bit world[i] of vertex j's reachability mask reach_mask[j * reach_words ..]   (if reach_mask != NULL: the validator
  *       closure of pto.rs:74-77; BitVec Lsb0 layout, reach_words = ceil(n_worlds / 64); a world >= 64 * reach_words passes nothing)
- * Result: CSR -- out_offsets[m+1], out_ids ascending per query (the SET contract; kd pre-order is restored by
- * porrt_kd_preorder_rank + porrt_segments_sort_by_key).  If the hits exceed cap: PORRT_ERR_CAPACITY, *out_total = needed. */
+ * Result: CSR -- out_offsets[m+1], out_ids ascending per query (the SET contract; the caller restores the reference's kd pre-order by
+ * sorting each list by porrt_kd_preorder_rank, as porrt_prm_build does internally).  If the hits exceed cap: PORRT_ERR_CAPACITY, *out_total = needed. */
 int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const double* radius, int64_t m,
                            const uint32_t* prefix_limit, const uint64_t* reach_mask, int32_t reach_words, const uint32_t* world,
                            int64_t* out_offsets, int32_t* out_ids, int64_t cap, int64_t* out_total);
@@ -154,7 +158,8 @@ int32_t porrt_nearest(porrt_ctx* ctx, const double* q_xy, int64_t m, const uint6
 int32_t porrt_knn(porrt_ctx* ctx, const double* q_xy, int64_t m, int32_t k, int32_t* out_ids, double* out_dist);
 
 /* The kd-tree's pre-order rank of every vertex (the order KdTree::nearest_neighbors returns hits in):
- * rank[i] = position of vertex i in a node-left-right walk of the tree obtained by inserting 0,1,..,n-1 in order. */
+ * rank[i] = position of vertex i in a node-left-right walk of the tree obtained by inserting 0,1,..,n-1 in order.
+ * xy == NULL ranks the ctx's own vertex set (porrt_vertices_set / porrt_vertices_append) in place, nothing is uploaded. */
 int32_t porrt_kd_preorder_rank(porrt_ctx* ctx, const double* xy, int64_t n, int32_t* out_rank);
 
 /* ------------------------------------------------------------------ PRM (prm.rs)

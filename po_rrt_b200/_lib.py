@@ -43,6 +43,7 @@ SIGNATURES = {
     "porrt_partial_shortcut": (i32, [vp, vp, i32, vp, i32, C.c_uint64, pp(i32), pp(i32)]),
     "porrt_partial_shortcut_batch": (i32, [vp, vp, vp, i32, vp, i32, C.c_uint64, vp, pp(i32)]),
     "porrt_vertices_set": (i32, [vp, vp, i64, f64]),
+    "porrt_vertices_append": (i32, [vp, vp, i64]),
     "porrt_vertices_set_dev": (i32, [vp, vp, i64, f64, vp, vp]),
     "porrt_vertices_count": (i32, [vp, pp(i64)]),
     "porrt_radius_query": (i32, [vp, vp, vp, i64, vp, vp, i32, vp, vp, vp, i64, pp(i64)]),

@@ -315,6 +315,16 @@ class KdTree:
         self.n = len(xy)
         self.ctx.check(self.ctx.lib.porrt_vertices_set(self.ctx.h, _p(xy), len(xy), float(cell_size)))
 
+    def add(self, xy):
+        """KdTree::add (nearest_neighbor.rs:29-46) for one or more states: ids continue after the current set; only the new
+        coordinates are uploaded (porrt_vertices_append)"""
+        xy = _f64(xy, 2)
+        if self.n == 0:
+            return self.set(xy)
+        self.ctx.check(self.ctx.lib.porrt_vertices_append(self.ctx.h, _p(xy), len(xy)))
+        self.xy = None          # the device copy is the set now; preorder_rank() ranks it in place
+        self.n += len(xy)
+
     def nearest_neighbors(self, q, radius, prefix_limit=None, reach_mask=None, world=None, cap=None, ids_out=None):
         """radius search -> (offsets[m+1], ids) with ids ascending per query.  ids_out: optional preallocated int32 buffer
         (e.g. pinned host memory) of at least `cap` entries"""
@@ -359,7 +369,7 @@ class KdTree:
 
     def preorder_rank(self):
         out = np.empty(self.n, np.int32)
-        self.ctx.check(self.ctx.lib.porrt_kd_preorder_rank(self.ctx.h, _p(self.xy), self.n, _p(out)))
+        self.ctx.check(self.ctx.lib.porrt_kd_preorder_rank(self.ctx.h, _p(self.xy) if self.xy is not None else None, self.n, _p(out)))
         return out
 
 

@@ -24,6 +24,22 @@ struct DevBuf {  // grow-only device scratch
     if (e == cudaSuccess) cap = want;
     return e;
   }
+  // grows like ensure() but carries the first keep_bytes over (device-to-device on `st`); the old block is freed after the copy
+  cudaError_t grow_keep(size_t bytes, size_t keep_bytes, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    void* q = nullptr;
+    const size_t want = bytes + bytes / 2 + 256;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) return e;
+    if (p && keep_bytes) {
+      e = cudaMemcpyAsync(q, p, keep_bytes, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { cudaFree(q); return e; }
+    }
+    if (p) cudaFree(p);
+    p = q; cap = want;
+    return cudaSuccess;
+  }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return (T*)p; }
 };
@@ -95,7 +111,9 @@ struct porrt_ctx {
   // host copies of the raw images are NOT kept: the product never walks pixels on the CPU.
 
   // ---- vertices / cell grid (nn.cu)
-  int64_t n_vertices = 0;
+  int64_t n_vertices = 0;          // vertices in d_vxy (upload order), including appended ones
+  bool grid_stale = false;         // porrt_vertices_append: the cell grid below is rebuilt on the device before the next query
+  double cell_request = 0.0;       // cell size asked for by the last porrt_vertices_set (<= 0: from the density)
   double cell = 0, inv_cell = 0, org_x = 0, org_y = 0;
   int32_t cells_x = 0, cells_y = 0;
   DevBuf d_vxy_sorted, d_vid_sorted, d_cell_start, d_vxy, d_vcell;
@@ -217,6 +235,7 @@ int32_t nn_tile_knn(porrt_ctx* ctx, const GridDev& g, const double* q_dev, int64
                     int32_t* fb_n_out);
 // nn.cu helpers used by graph.cu
 int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, double cell_size, const double* lo, const double* hi);
+int32_t nn_flush_appended(porrt_ctx* ctx);   // re-bins the vertex set if porrt_vertices_append left it stale
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
                                  int64_t* offsets_dev /* [m+1] */, DevBuf* ids_buf, int64_t* total_out,

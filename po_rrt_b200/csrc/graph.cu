@@ -149,13 +149,15 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
 
 PORRT_API int32_t porrt_kd_preorder_rank(porrt_ctx* ctx, const double* xy, int64_t n, int32_t* out_rank) {
   CTX_CHECK(ctx);
-  if (n < 0 || (n > 0 && (!xy || !out_rank))) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "kd_preorder_rank: bad arguments");
+  if (!xy) n = ctx->n_vertices;   // xy == NULL: the rank of the ctx's own vertex set (porrt_vertices_set / _append), nothing is uploaded
+  if (n < 0 || (n > 0 && !out_rank)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "kd_preorder_rank: bad arguments");
   if (n == 0) return PORRT_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, ctx->scratch[9].ensure((size_t)n * 20));
   double* d_xy = ctx->scratch[9].as<double>();
   int32_t* d_rank = (int32_t*)(ctx->scratch[9].as<char>() + (size_t)n * 16);
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  if (xy) CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  else d_xy = ctx->d_vxy.as<double>();
   int32_t rc = kd_preorder_rank_dev(ctx, d_xy, n, d_rank, nullptr);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(out_rank, d_rank, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -317,6 +317,7 @@ int32_t nn_vertices_set_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, dou
                                                          ctx->d_vxy_sorted.as<double2>(), ctx->d_vid_sorted.as<int32_t>());
   LAUNCH_CHECK(ctx);
   ctx->n_vertices = n;
+  ctx->grid_stale = false;
   return PORRT_OK;
 }
 
@@ -337,7 +338,31 @@ PORRT_API int32_t porrt_vertices_set(porrt_ctx* ctx, const double* xy, int64_t n
   if (!xy || n <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_set: bad arguments");
   CUDA_TRY(ctx, ctx->d_vxy.ensure((size_t)n * 16));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vxy.p, xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->cell_request = cell_size;
   return nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell_size, nullptr, nullptr);
+}
+
+// KdTree::add (nearest_neighbor.rs:29-46), batched: the m new vertices get the ids n .. n+m-1.  Only the new coordinates cross the
+// bus (a sequential caller that re-sent the whole set before every query moved O(V^2) bytes); the cell grid is rebuilt from the
+// device-resident set -- bounding box, cell size rule of the last porrt_vertices_set, sort by cell -- before the next query.
+PORRT_API int32_t porrt_vertices_append(porrt_ctx* ctx, const double* xy, int64_t m) {
+  CTX_CHECK(ctx);
+  if (m < 0 || (m > 0 && !xy)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_append: bad arguments");
+  if (m == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = ctx->n_vertices;
+  if (n + m > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "vertices_append: too many vertices");
+  CUDA_TRY(ctx, ctx->d_vxy.grow_keep((size_t)(n + m) * 16, (size_t)n * 16, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vxy.as<char>() + (size_t)n * 16, xy, (size_t)m * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // xy is the caller's (possibly pageable) memory
+  ctx->n_vertices = n + m;
+  ctx->grid_stale = true;
+  return PORRT_OK;
+}
+
+int32_t nn_flush_appended(porrt_ctx* ctx) {
+  if (!ctx->grid_stale) return PORRT_OK;
+  return nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), ctx->n_vertices, ctx->cell_request, nullptr, nullptr);
 }
 
 PORRT_API int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n) {
@@ -717,6 +742,8 @@ PORRT_API int32_t porrt_radius_query(porrt_ctx* ctx, const double* q_xy, const d
   if (ctx->n_vertices <= 0) return porrt_fail(ctx, PORRT_ERR_NO_VERTICES, "no vertex set");
   if (m < 0 || (m > 0 && (!q_xy || !radius || !out_offsets)) || (reach_mask && (!world || reach_words < 1)))
     return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "radius_query: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  { const int32_t rcf = nn_flush_appended(ctx); if (rcf) return rcf; }
   ctx->reach_words = reach_mask ? reach_words : 1;
   const size_t reach_bytes = reach_mask ? (size_t)ctx->n_vertices * 8 * (size_t)reach_words : 0;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -930,6 +957,8 @@ static int32_t knn_host(porrt_ctx* ctx, const double* q_xy, int64_t m, int k, co
   if (m < 0 || (m > 0 && (!q_xy || !out_ids)) || k < 1 || k > 32 || (reach_mask && (!world || reach_words < 1)))
     return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "nearest/knn: bad arguments (1 <= k <= 32)");
   if (m == 0) return PORRT_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  { const int32_t rcf = nn_flush_appended(ctx); if (rcf) return rcf; }
   ctx->reach_words = reach_mask ? reach_words : 1;
   const size_t reach_bytes = reach_mask ? (size_t)ctx->n_vertices * 8 * (size_t)reach_words : 0;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));

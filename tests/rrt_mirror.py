@@ -58,23 +58,24 @@ class OracleBackend:
 
 
 class ProductBackend:
-    """the same five questions through libporrt_b200 (po_rrt_b200.api): the vertex set is re-uploaded when it changed"""
+    """the same five questions through libporrt_b200 (po_rrt_b200.api); a new node is appended to the device-resident vertex set
+    (KdTree.add -> porrt_vertices_append: 16 bytes cross the bus, not the whole set)"""
 
     def __init__(self, pmap, start):
         import po_rrt_b200 as P
         self.P, self.map, self.ctx = P, pmap, pmap.ctx
         self.states = [list(start)]
-        self.tree, self.rank = None, None
+        self.tree = P.KdTree(self.ctx, np.asarray(self.states, np.float64))
+        self.rank = None
 
     def _sync(self):
-        if self.tree is None:
-            self.tree = self.P.KdTree(self.ctx, np.asarray(self.states, np.float64))
-            self.rank = None
+        pass
 
     def add(self, state, node_id):
         assert node_id == len(self.states)
         self.states.append(list(state))
-        self.tree = None
+        self.tree.add([state])
+        self.rank = None
 
     def nearest(self, q):
         self._sync()
@@ -160,17 +161,16 @@ class ProductPTOBackend:
     def __init__(self, pmap):
         import po_rrt_b200 as P
         self.P, self.map, self.ctx = P, pmap, pmap.ctx
-        self.states, self.tree, self.rank = [], None, None
+        self.states, self.tree, self.rank = [], P.KdTree(self.ctx), None
 
     def _sync(self):
-        if self.tree is None:
-            self.tree = self.P.KdTree(self.ctx, np.asarray(self.states, np.float64))
-            self.rank = None
+        pass
 
     def add_vertex(self, q, node_id):
         assert node_id == len(self.states)
         self.states.append(list(q))
-        self.tree = None
+        self.tree.add([q])             # porrt_vertices_append: only the new state is uploaded
+        self.rank = None
 
     def nearest_filtered(self, q, world, reach_words):      # pto.rs:74-77: 1-NN among nodes reachable in `world`
         self._sync()

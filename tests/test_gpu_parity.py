@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
 Integer / index results must be bit-exact; f64 values are compared for exact equality unless stated."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -1251,3 +1252,75 @@ def test_malformed_graphs_are_refused(ctx):
         P.plan_belief_space(pmap, rp, np.array([1, 2], np.int32), np.array([0, 7], np.int32), xy, np.zeros(3, np.int32), [0.5, 0.5], [2],
                             P.words_from_bits([[1, 1]]))
     assert e.value.code == 1
+
+
+def test_vertices_append_equals_full_set(ctx):
+    """KdTree::add (nearest_neighbor.rs:29-46): a vertex set grown by porrt_vertices_append -- one by one and in ragged batches --
+    answers radius / 1-NN / k-NN queries and ranks its kd pre-order exactly like the same set uploaded at once, and like the
+    oracle's incrementally built kd-tree."""
+    rng = np.random.default_rng(21)
+    pts = rng.uniform(-1, 1, (3000, 2))
+    pts[100] = pts[7]                                     # an exact duplicate
+    q = rng.uniform(-1, 1, (500, 2))
+    whole = P.KdTree(ctx, pts, cell_size=0.05)
+    want_offs, want_ids = whole.nearest_neighbors(q, 0.08)
+    want_nn = whole.nearest_neighbor(q)
+    want_knn = whole.knn(q, 5)
+    want_rank = whole.preorder_rank()
+    otree = O.KdTree(pts[0], 0)
+    otree.add_batch(pts[1:], 1)
+    grown = P.KdTree(ctx, pts[:1], cell_size=0.05)
+    k = 1
+    for step in (1, 1, 1, 5, 64, 1, 700, 1, 2225):       # sums to 2999
+        grown.add(pts[k:k + step])
+        k += step
+        if step == 1:                                     # query between appends: the grid is rebuilt for the grown set each time
+            offs, ids = grown.nearest_neighbors(q[:20], 0.3)
+            ooffs, oids, _ = otree_prefix_radius(pts[:k], q[:20], 0.3)
+            np.testing.assert_array_equal(offs, ooffs)
+            np.testing.assert_array_equal(ids, oids)
+    assert k == len(pts) and grown.n == len(pts)
+    offs, ids = grown.nearest_neighbors(q, 0.08)
+    np.testing.assert_array_equal(offs, want_offs)
+    np.testing.assert_array_equal(ids, want_ids)
+    for a, b in zip(grown.nearest_neighbor(q), want_nn):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(grown.knn(q, 5), want_knn):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(grown.preorder_rank(), want_rank)
+    # the oracle's kd-tree gives the same sets (ids ascending after sorting its kd-ordered lists)
+    ooffs, oids, _ = otree.radius_batch(q, 0.08, cap=len(ids) + 8)
+    np.testing.assert_array_equal(offs, ooffs)
+    for j in range(len(q)):
+        np.testing.assert_array_equal(ids[offs[j]:offs[j + 1]], np.sort(oids[ooffs[j]:ooffs[j + 1]]))
+    # node ids of appended vertices are usable by the indexed edge checks
+    occ, zones = synth.door_map(size=256, n_zones=2, seed=3)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    t2 = P.KdTree(ctx, pts[:10])
+    t2.add(pts[10:50])
+    a, b = rng.integers(0, 50, 400).astype(np.int32), rng.integers(0, 50, 400).astype(np.int32)
+    np.testing.assert_array_equal(pmap.transition_validator_nodes(a, b).astype(np.int64), omap.edge_validity(pts[a], pts[b]))
+
+
+def otree_prefix_radius(pts, q, r):
+    """brute-force radius sets (ids ascending) over the first len(pts) vertices, with the reference's predicate sqrt(d2) <= r"""
+    offs, ids = [0], []
+    for p in q:
+        d = np.sqrt((pts[:, 0] - p[0]) * (pts[:, 0] - p[0]) + (pts[:, 1] - p[1]) * (pts[:, 1] - p[1]))
+        hit = np.nonzero(d <= r)[0]
+        ids += list(hit)
+        offs.append(len(ids))
+    return np.asarray(offs, np.int64), np.asarray(ids, np.int32), None
+
+
+def test_c_abi_harness():
+    """the C ABI called from plain C (tests/c_abi_harness.c, gcc -std=c99), not through ctypes"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "_c_abi_harness")
+    libdir = os.path.join(root, "po_rrt_b200")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c_abi_harness.c"), "-o", exe, "-L", libdir, "-lporrt_b200", "-lm",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "c_abi_harness: ok" in r.stdout, r.stdout + r.stderr
