@@ -188,6 +188,13 @@ int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, con
                           const int32_t* node_vid, const uint64_t* validities, int32_t n_validities, int32_t mask_words,
                           int32_t n_worlds, const int64_t* finals_ptr, const int32_t* finals_ids,
                           double* out_dist, int32_t* out_sweeps);
+/* plan_qmdp straight on the roadmap porrt_prm_build left on the device (CSR + vertex coordinates) under the uploaded map's worlds:
+ * only the final-node lists cross the bus on the way in.  Node validity ids = the map's state validity of the vertices, evaluated
+ * on the device (a vertex inside an obstacle is invalid in every world).  finals_ptr[n_worlds + 1]; out_dist[n_worlds * V] may be
+ * NULL (the table then stays on the device: timing, device-resident pipelines).
+ * Both calls: porrt_ctx_last_phase_ms = [device ms of the backups, edge records / (parent, world) pairs worked through]. */
+int32_t porrt_sssp_worlds_prm(porrt_ctx* ctx, const int64_t* finals_ptr, const int32_t* finals_ids, double* out_dist,
+                              int32_t* out_sweeps);
 
 /* PTO::build_belief_graph + compute_expected_costs_to_goals (pto.rs:185-275, belief_graph.rs:89-182) on the IMPLICIT
  * belief graph (belief node id = node * B + belief):

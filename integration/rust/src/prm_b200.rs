@@ -18,7 +18,7 @@
 use super::PRM;
 use crate::b200::B200Domain;
 use crate::b200_ffi::*;
-use crate::pto_graph::{PTOEdge, PTOFuncs};
+use crate::pto_graph::PTOEdge;
 
 impl<'a> PRM<'a, B200Domain<'a>, 2> {
     /// drop-in for `grow_graph(max_step, search_radius, n_iter)` after `init(start)`
@@ -64,6 +64,5 @@ impl<'a> PRM<'a, B200Domain<'a>, 2> {
             self.kdtree.add(states[k], k);
         }
         self.n_it += n_iter;
-        debug_assert_eq!(self.fns.n_worlds(), self.fns.n_worlds());
     }
 }

@@ -52,6 +52,7 @@ SIGNATURES = {
     "porrt_kd_preorder_rank": (i32, [vp, vp, i64, vp]),
     "porrt_prm_build": (i32, [vp, vp, i64, f64, f64, vp, vp, i64, pp(i64), vp]),
     "porrt_prm_fetch": (i32, [vp, vp, vp, i64]),
+    "porrt_sssp_worlds_prm": (i32, [vp, vp, vp, vp, pp(i32)]),
     "porrt_sssp_worlds": (i32, [vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, pp(i32)]),
     "porrt_belief_result": (i32, [vp, vp, vp, vp, vp]),
     "porrt_belief_vi": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, pp(i32), vp]),

@@ -438,6 +438,21 @@ def dijkstra_worlds(ctx, row_ptr, col, xy, node_vid, validities_words, finals_pe
     return out, sweeps.value
 
 
+def dijkstra_worlds_resident_prm(fns, V, finals_per_world, want_dist=True):
+    """plan_qmdp on the roadmap the last PRM build left on the device (porrt_sssp_worlds_prm): node validity ids are the map's state
+    validity of the vertices, evaluated on the device.  -> (cost_to_goals[W][V] or None, rounds)"""
+    ctx = fns.ctx
+    W = len(finals_per_world)
+    fptr = np.zeros(W + 1, np.int64)
+    for w, f in enumerate(finals_per_world):
+        fptr[w + 1] = fptr[w] + len(f)
+    fin = np.ascontiguousarray(np.concatenate([np.asarray(f, np.int32) for f in finals_per_world]) if fptr[-1] else np.zeros(0, np.int32))
+    out = np.empty((W, V)) if want_dist else None
+    sweeps = C.c_int32()
+    ctx.check(ctx.lib.porrt_sssp_worlds_prm(ctx.h, _p(fptr), _p(fin), _p(out) if want_dist else None, C.byref(sweeps)))
+    return out, sweeps.value
+
+
 class BeliefPlan:
     pass
 

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "colsolve.cuh"
 #include "belief_tables.cuh"
+#include "sssp_frontier.cuh"
 
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -578,6 +579,11 @@ static bool csr_ok(int64_t V, const int64_t* row_ptr, const int32_t* col) {
 }
 
 // ================================================================================================ SSSP per world
+// validity ids < 0 (obstacle / panic codes) -> the appended all-zero row `none`
+__global__ void clamp_vid_kernel(int32_t* __restrict__ vid, int64_t n, int32_t none) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && vid[i] < 0) vid[i] = none;
+}
 __global__ void edge_cost_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy,
                                  int64_t V, double* __restrict__ cost) {
   // norm2(u, v) (common.rs:203-213) for every CSR edge u -> v; one warp per row
@@ -592,51 +598,118 @@ __global__ void edge_cost_kernel(const int64_t* __restrict__ row_ptr, const int3
   }
 }
 
-// One pull sweep: dist[u][w] = min(dist[u][w], min_{v in children(u)} dist[v][w] + cost(u,v)) for u valid in world w.
-// Layout dist[u * W + w]: the W threads of a node read its CSR row once (broadcast) and the children's rows coalesced.
-// Roadmaps too large for the shared-memory column solver (colsolve.cu) only.
-__global__ void __launch_bounds__(256) sssp_sweep_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                                                         const double* __restrict__ cost, const uint8_t* __restrict__ node_ok /* [V*W] */,
-                                                         int64_t V, int W, double* __restrict__ dist, int32_t* __restrict__ changed) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= V * W) return;
-  const int64_t u = t / W;
-  const int w = (int)(t - u * W);
-  if (!node_ok[t]) return;  // PTOGraphWorldView::parents filters by the PARENT node's validity (pto_graph.rs:264-270)
-  double best = dist[t];
-  const double old = best;
-  for (int64_t e = row_ptr[u]; e < row_ptr[u + 1]; ++e) {
-    const double alt = __dadd_rn(dist[(int64_t)col[e] * W + w], cost[e]);  // dist[v] + cost(u, v), pto_graph.rs:293
-    if (alt < best) best = alt;
-  }
-  if (best < old) { dist[t] = best; *changed = 1; }
-}
-
-// node_ok[u * W + w] = bit (wlo + w) of validities[node_vid[u]] (all ones without a world view); dist = +inf
-__global__ void sssp_init_kernel(const int32_t* __restrict__ node_vid, const uint64_t* __restrict__ validities, int mask_words,
-                                 int64_t V, int W, int wlo, uint8_t* __restrict__ node_ok, double* __restrict__ dist) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= V * W) return;
-  const int64_t u = t / W;
-  const int wg = wlo + (int)(t - u * W);
-  node_ok[t] = node_vid ? (uint8_t)((validities[(int64_t)node_vid[u] * mask_words + (wg >> 6)] >> (wg & 63)) & 1) : 1;
-  dist[t] = INFINITY;
-}
-
-__global__ void transpose_dist_kernel(const double* __restrict__ in /* [V][W] */, int64_t V, int W, double* __restrict__ out /* [W][V] */) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= V * W) return;
-  const int64_t u = t / W;
-  const int w = (int)(t - u * W);
-  out[(int64_t)w * V + u] = in[t];
-}
-
 __global__ void fill_inf_kernel(double* __restrict__ d, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = INFINITY;
 }
 __global__ void scatter_zero_kernel(double* __restrict__ d, const int64_t* __restrict__ idx, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[idx[i]] = 0.0;
+}
+
+// plan_qmdp on a graph that already lives on the device (all d_* are device pointers; h_val = host copy of the validity table).
+// Roadmaps whose value column fits in shared memory go to the on-chip column solver (colsolve.cu, one column per world), larger
+// ones to the frontier relaxation over global memory (sssp_frontier.cu).  out_dist (host, [Wall][V]) may be null: the table then
+// stays on the device only (timing, device-resident pipelines).  Work space: scratch[8]; porrt_ctx_last_phase_ms afterwards:
+// [0] device ms of the backups, [1] edge records / (parent, world) pairs worked through.
+static int32_t sssp_core(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d_col, const double* d_xy, int64_t V, int64_t E,
+                         const int32_t* d_nvid, const uint64_t* d_val, const uint64_t* h_val, int32_t n_validities, int32_t mask_words,
+                         bool world_view, int Wall, const int64_t* finals_ptr, const int32_t* finals_ids, double* out_dist,
+                         int32_t* out_sweeps) {
+  cudaStream_t st = ctx->stream;
+  // multi-GPU (comm.cu): the worlds are independent problems on one graph -- rank r relaxes worlds [wlo, whi) and the dist
+  // rows are all-gathered (SURVEY 8(e)); the plain-graph call (n_worlds == 0) is not sharded
+  int64_t wlo = 0, whi = Wall;
+  const bool sharded = world_view && ctx->comm_world > 1;
+  if (sharded) comm_shard_range(Wall, ctx->comm_rank, ctx->comm_world, &wlo, &whi);
+  const int W = (int)(whi - wlo);
+  const bool cols = colsolve_fits(V, E, world_view ? n_validities : 1) && !ctx->force_global_sweeps;
+  // the finals of this rank's worlds: indices into the [world][node] table (column solver) or (node, local world) pairs (frontier)
+  std::vector<int64_t> zero_idx;
+  std::vector<int32_t> fin_nw;
+  for (int w = 0; w < Wall; ++w)
+    for (int64_t k = finals_ptr[w]; k < finals_ptr[w + 1]; ++k) {
+      const int32_t f = finals_ids[k];
+      if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: final id out of range");
+      if (w >= wlo && w < whi) {
+        if (cols) zero_idx.push_back((int64_t)w * V + f);
+        else { fin_nw.push_back(f); fin_nw.push_back((int32_t)(w - wlo)); }
+      }
+    }
+  const int64_t n_fin = cols ? (int64_t)zero_idx.size() : (int64_t)fin_nw.size() / 2;
+  DevBuf& g = ctx->scratch[8];
+  const size_t need = (size_t)V * Wall * 8 + (size_t)n_fin * 8 + 64 +
+                      (cols ? (size_t)(V + 1) * 8 + (size_t)E * 20 + (size_t)Wall * 32 : 0) + 12 * 16 + 256;
+  CUDA_TRY(ctx, g.ensure(need));
+  char* b = g.as<char>();
+  auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
+  double* d_out = (double*)take((size_t)V * Wall * 8);   // [Wall][V]: this rank fills rows wlo..whi, the gather the rest
+  int32_t* d_flag = (int32_t*)take(16);
+  int sweeps = 0;
+  double offers = 0.0;
+  tstart(ctx);
+  if (W > 0 && cols) {
+    // one column per world, solved on chip; d_out is the column-major table itself
+    int64_t* d_zero = (int64_t*)take((size_t)n_fin * 8 + 8);
+    double* d_cost = (double*)take((size_t)E * 8);
+    double* d_cost_t = (double*)take((size_t)E * 8);
+    uint32_t* d_ce = (uint32_t*)take((size_t)E * 4);
+    uint32_t* d_rs = (uint32_t*)take((size_t)(V + 1) * 4);
+    uint32_t* d_cursor = (uint32_t*)take((size_t)(V + 1) * 4);
+    uint64_t* d_cmask = (uint64_t*)take((size_t)Wall * 32);
+    std::vector<uint64_t> cmask((size_t)Wall * 4, world_view ? 0 : ~(uint64_t)0);
+    if (world_view)
+      for (int w = 0; w < Wall; ++w)
+        for (int v = 0; v < n_validities; ++v)
+          if ((h_val[(size_t)v * mask_words + w / 64] >> (w % 64)) & 1) cmask[(size_t)w * 4 + v / 64] |= (uint64_t)1 << (v % 64);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_cmask, cmask.data(), cmask.size() * 8, cudaMemcpyHostToDevice, st));
+    if (n_fin) CUDA_TRY(ctx, cudaMemcpyAsync(d_zero, zero_idx.data(), (size_t)n_fin * 8, cudaMemcpyHostToDevice, st));
+    edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
+    LAUNCH_CHECK(ctx);
+    int32_t rc = colsolve_pack(ctx, d_row, d_col, nullptr, d_cost, V, E, d_rs, d_ce, d_cost_t, d_cursor, st);
+    if (rc) return rc;
+    fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_out + wlo * V, V * (int64_t)W);
+    LAUNCH_CHECK(ctx);
+    if (n_fin) {
+      scatter_zero_kernel<<<div_up(n_fin, 256), 256, 0, st>>>(d_out, d_zero, n_fin);
+      LAUNCH_CHECK(ctx);
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 16, st));
+    ColSolveArgs ca = {};
+    ca.row_start = d_rs; ca.cost = d_cost_t; ca.ce = d_ce; ca.V = (int32_t)V; ca.ld = V; ca.dist_cm = d_out; ca.cmask = d_cmask;
+    ca.nvid = world_view ? d_nvid : nullptr; ca.sweeps_out = d_flag; ca.offers_out = (unsigned long long*)(d_flag + 2);
+    rc = colsolve_level(ctx, ca, COLSOLVE_WORLD, (int)wlo, (int)whi, st);
+    if (rc) return rc;
+    tmark(ctx);
+    unsigned long long off = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&sweeps, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&off, d_flag + 2, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    offers = (double)off;
+  } else if (W > 0) {
+    int32_t* d_fin = (int32_t*)take((size_t)n_fin * 8 + 8);
+    // (node, world) pairs interleaved on the host -> two arrays on the device
+    std::vector<int32_t> split((size_t)n_fin * 2);
+    for (int64_t k = 0; k < n_fin; ++k) { split[(size_t)k] = fin_nw[(size_t)2 * k]; split[(size_t)(n_fin + k)] = fin_nw[(size_t)2 * k + 1]; }
+    if (n_fin) CUDA_TRY(ctx, cudaMemcpyAsync(d_fin, split.data(), (size_t)n_fin * 8, cudaMemcpyHostToDevice, st));
+    int32_t rc = sssp_frontier_run(ctx, d_row, d_col, d_xy, V, E, world_view ? d_nvid : nullptr, d_val, mask_words, (int32_t)wlo, W, d_fin,
+                                   d_fin + n_fin, n_fin, d_out + wlo * V, &sweeps, &offers, st);
+    if (rc) return rc;
+    tmark(ctx);
+  } else {
+    tmark(ctx);
+  }
+  if (sharded) {
+    std::vector<int64_t> off(ctx->comm_world + 1);
+    for (int r = 0; r < ctx->comm_world; ++r) { int64_t a2, b2; comm_shard_range(Wall, r, ctx->comm_world, &a2, &b2); off[r] = a2 * V * 8; off[r + 1] = b2 * V * 8; }
+    int32_t rc = comm_all_gatherv_dev(ctx, nullptr, d_out, off.data(), st);
+    if (rc) return rc;
+  }
+  if (out_dist) CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_out, (size_t)V * Wall * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  tfinish(ctx);
+  ctx->last_ms[1] = offers; ctx->n_last = 2;
+  if (out_sweeps) *out_sweeps = sweeps;
+  return PORRT_OK;
 }
 
 PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy,
@@ -649,121 +722,60 @@ PORRT_API int32_t porrt_sssp_worlds(porrt_ctx* ctx, int64_t V, const int64_t* ro
   if (world_view && (!node_vid || !validities || n_validities <= 0 || mask_words <= 0)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: world view needs validities");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const int Wall = world_view ? n_worlds : 1;
-  // multi-GPU (comm.cu): the worlds are independent problems on one graph -- rank r relaxes worlds [wlo, whi) and the dist
-  // rows are all-gathered (SURVEY 8(e)); the plain-graph call (n_worlds == 0) is not sharded
-  int64_t wlo = 0, whi = Wall;
-  const bool sharded = world_view && ctx->comm_world > 1;
-  if (sharded) comm_shard_range(Wall, ctx->comm_rank, ctx->comm_world, &wlo, &whi);
-  const int W = (int)(whi - wlo);
   const int64_t E = row_ptr[V];
   if (E > 0 && !col) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: null col");
   if (!csr_ok(V, row_ptr, col)) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: malformed CSR (row_ptr not monotone or edge target out of range)");
   if (world_view)
     for (int64_t u = 0; u < V; ++u)
       if (node_vid[u] < 0 || node_vid[u] >= n_validities) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: node validity id out of range");
-  // the finals of this rank's worlds as indices into the value table (column solver: [world][node]; sweeps: [node][world])
-  const bool cols = colsolve_fits(V, E, world_view ? n_validities : 1) && !ctx->force_global_sweeps;
-  std::vector<int64_t> zero_idx;
-  for (int w = 0; w < Wall; ++w)
-    for (int64_t k = finals_ptr[w]; k < finals_ptr[w + 1]; ++k) {
-      const int32_t f = finals_ids[k];
-      if (f < 0 || f >= V) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds: final id out of range");
-      if (w >= wlo && w < whi) zero_idx.push_back(cols ? (int64_t)w * V + f : (int64_t)f * W + (w - wlo));
-    }
   DevBuf& g = ctx->scratch[3];
   const size_t nvw = world_view ? (size_t)n_validities * mask_words : 0;
-  const size_t need = (size_t)(V + 1) * 16 + (size_t)E * 24 + (size_t)V * 24 + (size_t)V * W * 9 + (size_t)V * Wall * 8 + nvw * 8 +
-                      (size_t)Wall * 32 + zero_idx.size() * 8 + 16 * 16 + 512;
-  CUDA_TRY(ctx, g.ensure(need));
+  CUDA_TRY(ctx, g.ensure((size_t)(V + 1) * 8 + (size_t)E * 4 + (size_t)V * 20 + nvw * 8 + 8 * 16));
   char* b = g.as<char>();
-  auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };  // keeps double2 loads aligned
+  auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
   int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
-  double* d_cost = (double*)take((size_t)E * 8);
   double* d_xy = (double*)take((size_t)V * 16);
-  double* d_out = (double*)take((size_t)V * Wall * 8);   // [Wall][V]: this rank fills rows wlo..whi, the gather the rest
   int32_t* d_col = (int32_t*)take((size_t)E * 4);
   int32_t* d_nvid = (int32_t*)take((size_t)V * 4);
   uint64_t* d_val = (uint64_t*)take(nvw * 8);
-  int64_t* d_zero = (int64_t*)take(zero_idx.size() * 8 + 8);
-  int32_t* d_flag = (int32_t*)take(16);
-  int sweeps = 0;
-  if (W > 0) {
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
-    if (world_view) {
-      CUDA_TRY(ctx, cudaMemcpyAsync(d_nvid, node_vid, (size_t)V * 4, cudaMemcpyHostToDevice, st));
-      CUDA_TRY(ctx, cudaMemcpyAsync(d_val, validities, nvw * 8, cudaMemcpyHostToDevice, st));
-    }
-    if (!zero_idx.empty()) CUDA_TRY(ctx, cudaMemcpyAsync(d_zero, zero_idx.data(), zero_idx.size() * 8, cudaMemcpyHostToDevice, st));
-    edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
-    LAUNCH_CHECK(ctx);
-    if (cols) {
-      // one column per world, solved on chip (colsolve.cu); d_out is the column-major table itself
-      uint32_t* d_rs = (uint32_t*)take((size_t)(V + 1) * 4);
-      uint32_t* d_ce = (uint32_t*)take((size_t)E * 4);
-      uint64_t* d_cmask = (uint64_t*)take((size_t)Wall * 32);
-      std::vector<uint64_t> cmask((size_t)Wall * 4, world_view ? 0 : ~(uint64_t)0);
-      if (world_view)
-        for (int w = 0; w < Wall; ++w)
-          for (int v = 0; v < n_validities; ++v)
-            if ((validities[(size_t)v * mask_words + w / 64] >> (w % 64)) & 1) cmask[(size_t)w * 4 + v / 64] |= (uint64_t)1 << (v % 64);
-      CUDA_TRY(ctx, cudaMemcpyAsync(d_cmask, cmask.data(), cmask.size() * 8, cudaMemcpyHostToDevice, st));
-      double* d_cost_t = (double*)take((size_t)E * 8);
-      uint32_t* d_cursor = (uint32_t*)take((size_t)(V + 1) * 4);
-      int32_t rc = colsolve_pack(ctx, d_row, d_col, nullptr, d_cost, V, E, d_rs, d_ce, d_cost_t, d_cursor, st);
-      if (rc) return rc;
-      fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_out + wlo * V, V * (int64_t)W);
-      LAUNCH_CHECK(ctx);
-      if (!zero_idx.empty()) {
-        scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_out, d_zero, (int64_t)zero_idx.size());
-        LAUNCH_CHECK(ctx);
-      }
-      CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
-      ColSolveArgs ca = {};
-      ca.row_start = d_rs; ca.cost = d_cost_t; ca.ce = d_ce; ca.V = (int32_t)V; ca.ld = V; ca.dist_cm = d_out; ca.cmask = d_cmask;
-      ca.nvid = world_view ? d_nvid : nullptr; ca.sweeps_out = d_flag;
-      rc = colsolve_level(ctx, ca, COLSOLVE_WORLD, (int)wlo, (int)whi, st);
-      if (rc) return rc;
-      CUDA_TRY(ctx, cudaMemcpyAsync(&sweeps, d_flag, 4, cudaMemcpyDeviceToHost, st));
-    } else {
-      double* d_dist = (double*)take((size_t)V * W * 8);
-      uint8_t* d_ok = (uint8_t*)take((size_t)V * W);
-      sssp_init_kernel<<<div_up(V * W, 256), 256, 0, st>>>(world_view ? d_nvid : nullptr, d_val, mask_words, V, W, (int)wlo, d_ok, d_dist);
-      LAUNCH_CHECK(ctx);
-      if (!zero_idx.empty()) {
-        scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_dist, d_zero, (int64_t)zero_idx.size());
-        LAUNCH_CHECK(ctx);
-      }
-      const int BATCH = 8;  // sweeps between two convergence checks
-      for (;;) {
-        CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
-        for (int k = 0; k < BATCH; ++k) {
-          sssp_sweep_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_row, d_col, d_cost, d_ok, V, W, d_dist, d_flag);
-          LAUNCH_CHECK(ctx);
-        }
-        sweeps += BATCH;
-        int32_t changed = 0;
-        CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_flag, 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        if (!changed) break;
-        if (sweeps > 4 * V + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp_worlds: no convergence");
-      }
-      transpose_dist_kernel<<<div_up(V * W, 256), 256, 0, st>>>(d_dist, V, W, d_out + wlo * V);
-      LAUNCH_CHECK(ctx);
-    }
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
+  if (world_view) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_nvid, node_vid, (size_t)V * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_val, validities, nvw * 8, cudaMemcpyHostToDevice, st));
   }
-  if (sharded) {
-    std::vector<int64_t> off(ctx->comm_world + 1);
-    for (int r = 0; r < ctx->comm_world; ++r) { int64_t a2, b2; comm_shard_range(Wall, r, ctx->comm_world, &a2, &b2); off[r] = a2 * V * 8; off[r + 1] = b2 * V * 8; }
-    int32_t rc = comm_all_gatherv_dev(ctx, nullptr, d_out, off.data(), st);
-    if (rc) return rc;
-  }
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_dist, d_out, (size_t)V * Wall * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  if (out_sweeps) *out_sweeps = sweeps;
-  return PORRT_OK;
+  return sssp_core(ctx, d_row, d_col, d_xy, V, E, d_nvid, d_val, validities, n_validities, mask_words, world_view, world_view ? n_worlds : 1,
+                   finals_ptr, finals_ids, out_dist, out_sweeps);
+}
+
+// plan_qmdp straight on the roadmap porrt_prm_build left on the device (graph, vertex coordinates) under the uploaded map's worlds:
+// nothing but the final-node lists crosses the bus on the way in.  Node validity ids are the map's state validity of the vertices
+// (evaluated on the device); a vertex inside an obstacle is invalid in every world.  out_dist (host, [n_worlds][V]) may be null.
+PORRT_API int32_t porrt_sssp_worlds_prm(porrt_ctx* ctx, const int64_t* finals_ptr, const int32_t* finals_ids, double* out_dist,
+                                        int32_t* out_sweeps) {
+  CTX_CHECK(ctx);
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (ctx->prm_n <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds_prm: no retained PRM result (porrt_prm_build first)");
+  if (!finals_ptr) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "sssp_worlds_prm: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t V = ctx->prm_n, E = ctx->prm_edges;
+  const int nv = ctx->n_validities;
+  // node validity ids on the device; obstacles (-1) get an extra all-zero validity row appended to the table
+  DevBuf& g = ctx->scratch[3];
+  const size_t nvw = (size_t)(nv + 1) * ctx->mask_words;
+  CUDA_TRY(ctx, g.ensure((size_t)V * 4 + nvw * 8 + 64));
+  int32_t* d_nvid = g.as<int32_t>();
+  uint64_t* d_val = (uint64_t*)(g.as<char>() + (((size_t)V * 4 + 15) & ~(size_t)15));
+  std::vector<uint64_t> val(ctx->validities);
+  val.resize(nvw, 0);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_val, val.data(), nvw * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc = porrt_state_validity_dev(ctx, ctx->d_vxy.as<double>(), V, d_nvid);
+  if (rc) return rc;
+  clamp_vid_kernel<<<div_up(V, 256), 256, 0, ctx->stream>>>(d_nvid, V, nv);
+  LAUNCH_CHECK(ctx);
+  return sssp_core(ctx, ctx->prm_row_ptr, ctx->prm_col, ctx->d_vxy.as<double>(), V, E, d_nvid, d_val, val.data(), nv + 1, ctx->mask_words, true,
+                   ctx->n_worlds, finals_ptr, finals_ids, out_dist, out_sweeps);
 }
 
 // ================================================================================================ belief-space VI

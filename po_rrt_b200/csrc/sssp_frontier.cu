@@ -1,0 +1,290 @@
+// sssp_frontier.cu -- world-view shortest paths on roadmaps that do not fit the on-chip column solver (colsolve.cu): a
+// label-correcting FRONTIER relaxation over the value table in global memory.
+//
+// Reference: dijkstra over PTOGraphWorldView, one problem per world (pto_graph.rs:245-303, qmdp_policy_extractor.rs:23-35).
+//
+// At PRM scale (1e6 nodes, 5.3e7 directed edges, 64 worlds) a Bellman-Ford sweep touches E * W = 3.4e9 (edge, world) pairs and the
+// roadmap's diameter is several hundred hops: the order-free Jacobi sweeps of round 1 were never run at that size.  Here only
+// values that moved do work:
+//   * dist[v][w] (world fastest) holds the value; entries of nodes that are invalid in world w carry the sign bit (fixed, read
+//     through |.|, compare below every offer) -- the same encoding as colsolve.cu;
+//   * dirty[v] = worlds whose value at v improved since v last pushed; a round's worklist holds the nodes with a non-empty mask;
+//   * one warp takes a worklist node v, clears its mask and, for every dirty world w, offers  norm2(u, v) + dist[v][w]  to every
+//     parent u (transposed adjacency; norm2 is symmetric bit for bit) with a 64-bit atomicMin (non-negative doubles order like
+//     their bit patterns); an improvement marks (u, w) dirty for the next round and appends u to the next worklist once.
+// Rounds are launched back to back without host round trips (three rotating counters: read / append / reset); the host looks at
+// the worklist length every few rounds only.  The fixed point is the reference's: every stored value is the left-to-right sum
+// along an admissible path and the last improvement of every value is always pushed (SURVEY 8(g) note 5).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "sssp_frontier.cuh"
+
+namespace {
+
+__global__ void sf_count_kernel(const int32_t* __restrict__ col, int64_t E, int32_t* __restrict__ cnt) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) atomicAdd(&cnt[col[e]], 1);
+}
+// transposed records: row v lists (parent u, norm2(u, v)); one warp per row u of the forward CSR
+__global__ void sf_fill_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy, int64_t V,
+                               const int64_t* __restrict__ row_t, int32_t* __restrict__ cursor, int32_t* __restrict__ col_t,
+                               double* __restrict__ cost_t) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= V) return;
+  const double2 a = xy[u];
+  for (int64_t e = row_ptr[u] + lane; e < row_ptr[u + 1]; e += 32) {
+    const int32_t v = col[e];
+    const double2 c = xy[v];
+    const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
+    const int64_t pos = row_t[v] + atomicAdd(&cursor[v], 1);
+    col_t[pos] = (int32_t)u;
+    cost_t[pos] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // norm2(u, v), common.rs:203-213
+  }
+}
+
+// dist[v][w] = +inf, or -inf where node v is invalid in world wlo + w (PTOGraphWorldView::parents filters by the parent node)
+__global__ void sf_init_kernel(const int32_t* __restrict__ node_vid, const uint64_t* __restrict__ validities, int mask_words, int64_t V,
+                               int W, int wlo, double* __restrict__ dist) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V * W) return;
+  const int64_t u = t / W;
+  const int wg = wlo + (int)(t - u * W);
+  const bool ok = node_vid ? ((validities[(int64_t)node_vid[u] * mask_words + (wg >> 6)] >> (wg & 63)) & 1) != 0 : true;
+  dist[t] = ok ? INFINITY : -INFINITY;
+}
+// finals: value 0 (keeping the sign), dirty in that world, on the first worklist
+__global__ void sf_seed_kernel(const int32_t* __restrict__ fin_node, const int32_t* __restrict__ fin_world, int64_t n, int W, int words,
+                               double* __restrict__ dist, unsigned long long* __restrict__ dirty, int32_t* __restrict__ inq,
+                               int32_t* __restrict__ list, int32_t* __restrict__ counter) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t v = fin_node[i], w = fin_world[i];
+  double* d = dist + (int64_t)v * W + w;
+  *d = (__double_as_longlong(*d) < 0) ? -0.0 : 0.0;
+  atomicOr(&dirty[(int64_t)v * words + (w >> 6)], 1ull << (w & 63));
+  if (atomicExch(&inq[v], 1) == 0) list[atomicAdd(counter, 1)] = v;
+}
+
+struct SfArgs {
+  const int64_t* row_t; const int32_t* col_t; const double* cost_t;
+  double* dist; int32_t W, words;
+  unsigned long long* dirty[2];   // [V * words] each
+  int32_t* inq[2];                // [V] each: node already on that round's worklist
+  int32_t* list[2];               // [V] each
+  int32_t* counter;               // [3] rotating: read / append / reset
+  unsigned long long* offers;     // (parent, world) pairs looked at
+  // near / far ordering: a dirty value pushes only once it is <= the round's threshold, which advances by `delta` per round (or
+  // jumps to the smallest deferred value); without it a value is corrected ~19 times at PRM scale (long early edges let the
+  // fronts run far ahead with values that are much too large), with it a handful of times
+  double* thr;                    // [3] rotating thresholds
+  unsigned long long* min_far;    // [3] rotating: smallest deferred value of a round (bits)
+  double delta;
+  int2* pairs;                    // the round's push list: (node, world) pairs within the threshold
+  int32_t* pair_count;            // [2]
+  int32_t pair_cap;
+};
+
+// Round r, step 1 (one THREAD per worklist node): take the node's dirty mask; a dirty value within the round's threshold becomes a
+// (node, world) pair of the push list, the others stay dirty and come back next round.  Deferred values are looked at once per round
+// until their turn comes -- by one thread, not by a warp (at PRM scale the long edges of the early samples keep ~10x more values
+// waiting than moving).
+__global__ void __launch_bounds__(256) sf_classify_kernel(SfArgs a, int round) {
+  const int cur = round & 1, nxt = cur ^ 1;
+  const int n_cur = a.counter[round % 3];
+  const double far_prev = __longlong_as_double((long long)a.min_far[round % 3]);
+  const double thr = fmax(__dadd_rn(a.thr[round % 3], a.delta), far_prev < INFINITY ? far_prev : 0.0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.counter[(round + 2) % 3] = 0;
+    a.min_far[(round + 2) % 3] = 0x7ff0000000000000ull;   // +inf
+    a.thr[(round + 1) % 3] = thr;
+  }
+  unsigned long long my_far = 0x7ff0000000000000ull;
+  for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_cur; qi += gridDim.x * blockDim.x) {
+    const int32_t v = a.list[cur][qi];
+    a.inq[cur][v] = 0;
+    bool again = false;
+    for (int k = 0; k < a.words; ++k) {
+      unsigned long long m = atomicExch(&a.dirty[cur][(int64_t)v * a.words + k], 0ull);
+      if (!m) continue;
+      __threadfence();   // the values are read after the mask was taken: a later improvement marks v again
+      unsigned long long keep = 0;
+      for (; m; m &= m - 1) {
+        const int w = k * 64 + __ffsll((long long)m) - 1;
+        const double dv = fabs(*(volatile double*)(a.dist + (int64_t)v * a.W + w));
+        bool near = dv <= thr;
+        if (near) {
+          const int at = atomicAdd(&a.pair_count[round & 1], 1);
+          if (at < a.pair_cap) a.pairs[at] = make_int2(v, w);
+          else near = false;   // push list full: wait a round
+        }
+        if (!near) {
+          keep |= 1ull << (w & 63);
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(dv);
+          if (bits < my_far) my_far = bits;
+        }
+      }
+      if (keep) { atomicOr(&a.dirty[nxt][(int64_t)v * a.words + k], keep); again = true; }
+    }
+    if (again && atomicExch(&a.inq[nxt][v], 1) == 0) a.list[nxt][atomicAdd(&a.counter[(round + 1) % 3], 1)] = v;
+  }
+  for (int s2 = 16; s2 > 0; s2 >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, my_far, s2); if (o < my_far) my_far = o; }
+  if ((threadIdx.x & 31) == 0 && my_far < *(volatile unsigned long long*)&a.min_far[(round + 1) % 3]) atomicMin(&a.min_far[(round + 1) % 3], my_far);
+}
+
+// Round r, step 2 (one WARP per (node, world) pair of the push list): offer  norm2(u, v) + dist[v][w]  to every parent u.
+__global__ void __launch_bounds__(256) sf_push_kernel(SfArgs a, int round) {
+  const int nxt = (round & 1) ^ 1;
+  const int n_pairs = min(a.pair_count[round & 1], a.pair_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.pair_count[nxt] = 0;   // the next round's classify step appends there
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long n_off = 0;
+  for (int qi = warp; qi < n_pairs; qi += n_warps) {
+    const int2 vw = a.pairs[qi];
+    const int32_t v = vw.x;
+    const int w = vw.y, k = w >> 6;
+    const double dv = fabs(*(volatile double*)(a.dist + (int64_t)v * a.W + w));
+    const int64_t e1 = a.row_t[v + 1];
+    for (int64_t e = a.row_t[v] + lane; e < e1; e += 32) {
+      const int32_t u = __ldg(a.col_t + e);
+      const double alt = __dadd_rn(__ldg(a.cost_t + e), dv);   // norm2(u, v) + dist[v], pto_graph.rs:293
+      double* du = a.dist + (int64_t)u * a.W + w;
+      ++n_off;
+      if (alt < *du) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(alt);
+        const unsigned long long old = atomicMin(reinterpret_cast<unsigned long long*>(du), bits);
+        if (bits < old) {
+          atomicOr(&a.dirty[nxt][(int64_t)u * a.words + k], 1ull << (w & 63));
+          if (atomicExch(&a.inq[nxt][u], 1) == 0) a.list[nxt][atomicAdd(&a.counter[(round + 1) % 3], 1)] = u;
+        }
+      }
+    }
+  }
+  if (a.offers) {
+    for (int s = 16; s > 0; s >>= 1) n_off += __shfl_xor_sync(0xffffffffu, n_off, s);
+    if (lane == 0 && n_off) atomicAdd(a.offers, n_off);
+  }
+}
+
+__global__ void sf_sum_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);   // only the order of magnitude matters (a schedule parameter, not a result)
+}
+
+__global__ void sf_out_kernel(const double* __restrict__ dist /* [V][W] */, int64_t V, int W, double* __restrict__ out /* [W][V] */) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V * W) return;
+  const int64_t u = t / W;
+  const int w = (int)(t - u * W);
+  out[(int64_t)w * V + u] = fabs(dist[t]);
+}
+}  // namespace
+
+// All pointers are device pointers.  fin_node / fin_world: the finals of the worlds [wlo, wlo + W) as (node, local world) pairs.
+// out_wv receives rows [0, W) of the [world][node] table.  Uses ctx->scratch[6..8] as work space.
+int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d_col, const double* d_xy, int64_t V, int64_t E,
+                          const int32_t* d_node_vid, const uint64_t* d_validities, int32_t mask_words, int32_t wlo, int32_t W,
+                          const int32_t* d_fin_node, const int32_t* d_fin_world, int64_t n_fin, double* d_out_wv, int32_t* out_rounds,
+                          double* out_offers, cudaStream_t st) {
+  if (V > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "sssp: more than 2^31 nodes");
+  const int words = (W + 63) / 64;
+  // ---- transposed adjacency (scratch[6])
+  DevBuf& tb = ctx->scratch[6];
+  CUDA_TRY(ctx, tb.ensure((size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 4 + 4 * 16 + 64));
+  char* p = tb.as<char>();
+  auto take = [&](size_t bytes) { char* q = p; p += (bytes + 15) & ~(size_t)15; return q; };
+  int64_t* d_row_t = (int64_t*)take((size_t)(V + 1) * 8);
+  double* d_cost_t = (double*)take((size_t)E * 8);
+  int32_t* d_col_t = (int32_t*)take((size_t)E * 4 + 4);
+  int32_t* d_cnt = (int32_t*)take((size_t)V * 4);
+  CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)V * 4, st));
+  if (E > 0) {
+    sf_count_kernel<<<div_up(E, 256), 256, 0, st>>>(d_col, E, d_cnt);
+    LAUNCH_CHECK(ctx);
+  }
+  int32_t rc = scan_exclusive_i64(ctx, d_cnt, V, d_row_t);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)V * 4, st));
+  if (E > 0) {
+    sf_fill_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_row_t, d_cnt, d_col_t, d_cost_t);
+    LAUNCH_CHECK(ctx);
+  }
+  // ---- value table + frontier state (scratch[7])
+  DevBuf& sb = ctx->scratch[7];
+  CUDA_TRY(ctx, sb.ensure((size_t)V * W * 8 + 2 * (size_t)V * words * 8 + 4 * (size_t)V * 4 + 192 + 14 * 16 +
+                          (size_t)std::min<int64_t>(V * (int64_t)W, std::max<int64_t>(4 << 20, 4 * V)) * 8));
+  p = sb.as<char>();
+  SfArgs a = {};
+  a.row_t = d_row_t; a.col_t = d_col_t; a.cost_t = d_cost_t; a.W = W; a.words = words;
+  a.dist = (double*)take((size_t)V * W * 8);
+  a.dirty[0] = (unsigned long long*)take((size_t)V * words * 8);
+  a.dirty[1] = (unsigned long long*)take((size_t)V * words * 8);
+  a.inq[0] = (int32_t*)take((size_t)V * 4); a.inq[1] = (int32_t*)take((size_t)V * 4);
+  a.list[0] = (int32_t*)take((size_t)V * 4); a.list[1] = (int32_t*)take((size_t)V * 4);
+  a.counter = (int32_t*)take(16);
+  a.offers = (unsigned long long*)take(16);
+  a.thr = (double*)take(32);
+  a.min_far = (unsigned long long*)take(32);
+  a.pair_count = (int32_t*)take(16);
+  a.pair_cap = (int32_t)std::min<int64_t>(V * (int64_t)W, std::max<int64_t>(4 << 20, 4 * V));
+  a.pairs = (int2*)take((size_t)a.pair_cap * 8);
+  CUDA_TRY(ctx, cudaMemsetAsync(a.dirty[0], 0, 2 * (((size_t)V * words * 8 + 15) & ~(size_t)15), st));
+  CUDA_TRY(ctx, cudaMemsetAsync(a.inq[0], 0, 2 * (((size_t)V * 4 + 15) & ~(size_t)15), st));
+  CUDA_TRY(ctx, cudaMemsetAsync(a.counter, 0, 32 + 32, st));   // counters, offers, thresholds (0.0)
+  CUDA_TRY(ctx, cudaMemsetAsync(a.pair_count, 0, 16, st));
+  {
+    // delta = the mean edge length of the roadmap (one hop of a front); min_far starts at +inf
+    const unsigned long long inf3[4] = {0x7ff0000000000000ull, 0x7ff0000000000000ull, 0x7ff0000000000000ull, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(a.min_far, inf3, 32, cudaMemcpyHostToDevice, st));
+    double* d_sum = (double*)take(16);
+    CUDA_TRY(ctx, cudaMemsetAsync(d_sum, 0, 8, st));
+    if (E > 0) {
+      sf_sum_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_cost_t, E, d_sum);
+      LAUNCH_CHECK(ctx);
+    }
+    double sum = 0.0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&sum, d_sum, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    // measured at PRM scale (1e6 nodes, 64 worlds): delta = 0.5 / 0.75 / 1 / 1.5 / 2 / 4 mean edge lengths -> 1.05 / 1.12 / 1.27 / 2.6 / 5.5 /
+    // 13.9 full sweeps' worth of pairs in 592 / 400 / 304 / 240 / 224 / 240 rounds; no ordering at all: 19.1
+    a.delta = E > 0 && sum > 0.0 && std::isfinite(sum) ? sum / (double)E : 1.0;
+  }
+  sf_init_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(d_node_vid, d_validities, mask_words, V, W, wlo, a.dist);
+  LAUNCH_CHECK(ctx);
+  if (n_fin > 0) {
+    sf_seed_kernel<<<div_up(n_fin, 256), 256, 0, st>>>(d_fin_node, d_fin_world, n_fin, W, words, a.dist, a.dirty[0], a.inq[0], a.list[0], a.counter);
+    LAUNCH_CHECK(ctx);
+  }
+  // ---- rounds: a fixed grid strides over the worklist, whose length lives on the device; the host checks every CHECK rounds
+  const int grid = ctx->sm_count * 8;
+  const int CHECK = 16;
+  int round = 0;
+  int32_t counters[4] = {0, 0, 0, 0};
+  for (;;) {
+    for (int k = 0; k < CHECK; ++k, ++round) {
+      sf_classify_kernel<<<grid, 256, 0, st>>>(a, round);
+      LAUNCH_CHECK(ctx);
+      sf_push_kernel<<<grid, 256, 0, st>>>(a, round);
+      LAUNCH_CHECK(ctx);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(counters, a.counter, 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (counters[round % 3] == 0) break;   // the worklist of the next round is empty: nothing is dirty any more
+    if (round > 64 * V + 1024) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp: no convergence");
+  }
+  sf_out_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(a.dist, V, W, d_out_wv);
+  LAUNCH_CHECK(ctx);
+  if (out_rounds) *out_rounds = round;
+  if (out_offers) {
+    unsigned long long off = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&off, a.offers, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    *out_offers = (double)off;
+  }
+  return PORRT_OK;
+}

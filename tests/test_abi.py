@@ -90,3 +90,19 @@ def test_rust_integration_files_use_only_declared_symbols():
             if f.endswith(".rs") and f != "b200_ffi.rs":
                 used |= set(re.findall(r"\b(porrt_[a-z0-9_]+)\s*\(", open(os.path.join(dirpath, f)).read()))
     assert used <= declared, sorted(used - declared)
+
+
+def test_rust_build_script_lists_the_makefile_sources():
+    """integration/rust/build.rs compiles exactly the translation units of po_rrt_b200/csrc/Makefile (and watches its headers)"""
+    mk = open(os.path.join(ROOT, "po_rrt_b200", "csrc", "Makefile")).read()
+    srcs = re.search(r"^SRCS := (.*)$", mk, flags=re.M).group(1).split()
+    hdrs = re.search(r"^%\.o: %\.cu (.*)$", mk, flags=re.M).group(1).split()
+    rs = open(os.path.join(ROOT, "integration", "rust", "build.rs")).read()
+    listed = re.findall(r'"([a-z0-9_]+\.cu)"', rs)
+    assert sorted(listed) == sorted(srcs)
+    for h in hdrs:
+        if h.startswith(".."):
+            continue
+        assert '"%s"' % h in rs, h
+    for f in ("b200_ffi.rs", "b200.rs", "prm_b200.rs", "qmdp_b200.rs", "pto_b200.rs"):
+        assert os.path.exists(os.path.join(ROOT, "integration", "rust", "src", f))

@@ -1324,3 +1324,41 @@ def test_c_abi_harness():
                     "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "c_abi_harness: ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_qmdp_on_resident_prm(ctx):
+    """porrt_sssp_worlds_prm: world-view shortest paths on the roadmap porrt_prm_build left on the device, through both value-backup
+    paths (on-chip column solver; frontier relaxation over global memory), against the oracle's dijkstra over PTOGraphWorldView on
+    the same graph (pto_graph.rs:245-303)."""
+    occ, zones = synth.door_map(size=512, n_rects=600, n_zones=3, seed=11)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    xy = synth.points(2500, seed=8)
+    prm = P.PRM(pmap)
+    prm.init(xy[:1])
+    prm.grow_graph(xy[1:], 0.1, 2.0)
+    V, W = len(xy), 8
+    rng = np.random.default_rng(4)
+    finals = [sorted(rng.choice(V, 3, replace=False).tolist()) for _ in range(W)]
+    finals[5] = []                                                   # a world without final node: its row stays +inf
+    got, rounds = P.dijkstra_worlds_resident_prm(pmap, V, finals)
+    ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 1)
+    try:
+        got2, rounds2 = P.dijkstra_worlds_resident_prm(pmap, V, finals)
+    finally:
+        ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 0)
+    np.testing.assert_array_equal(got2, got)
+    assert rounds > 0 and rounds2 > 0
+    # the oracle: same graph, node validity id = state validity (obstacle -> an extra validity that holds in no world)
+    nvid = omap.state_validity(xy).astype(np.int64)
+    wv = omap.world_validities()
+    none = len(wv)
+    og = O.PTOGraph(validities=[list(map(int, m)) for m in wv] + [[0] * W])
+    for k in range(V):
+        og.add_node(xy[k], int(nvid[k]) if nvid[k] >= 0 else none)
+    for u in range(V):
+        for e in range(prm.row_ptr[u], prm.row_ptr[u + 1]):
+            og.add_edge(u, int(prm.col[e]), 0)
+    for w in range(W):
+        want = og.dijkstra(finals[w], world=w) if finals[w] else np.full(V, np.inf)
+        np.testing.assert_array_equal(got[w], want, err_msg="world %d" % w)
+    assert np.isfinite(got).any() and np.isinf(got[5]).all()
