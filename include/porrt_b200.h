@@ -363,6 +363,31 @@ int32_t porrt_comm_all_gather_dev(porrt_ctx* ctx, const void* send_dev, void* re
 /* ragged: rank r contributes byte_counts[r] bytes (host array [world], identical on every rank) */
 int32_t porrt_comm_all_gatherv_dev(porrt_ctx* ctx, const void* send_dev, void* recv_dev, const int64_t* byte_counts);
 
+/* ------------------------------------------------------------------ on-disk formats (host code, no GPU work)
+ * PNM gray maps, the decode step of Map::open_image (map_io.rs:98-105): P2 (ASCII) and P5 (binary), 8 bit; anything else is the
+ * reference's panic "Wrong image format!" (PORRT_ERR_PANIC).  Size query: out == NULL / cap too small -> PORRT_ERR_CAPACITY with
+ * *out_h, *out_w set.  ctx is used for error text only and may be NULL. */
+int32_t porrt_pgm_read(porrt_ctx* ctx, const char* path, uint8_t* out, int64_t cap, int32_t* out_h, int32_t* out_w);
+int32_t porrt_pgm_write(porrt_ctx* ctx, const char* path, const uint8_t* img, int32_t h, int32_t w, int32_t binary);
+/* PTOGraph JSON (pto_graph.rs:22-118, serde_json of SerializablePTOGraph) <-> the CSR arrays of the value-backup entry points.
+ * Stored (insertion) order of `children` / `parents` is kept.  load -> handle; porrt_graph_info gives the sizes, porrt_graph_arrays
+ * copies out whichever arrays are asked for (every pointer nullable): xy[2V], node_vid[V], children as row_ptr[V+1] / col / edge_vid,
+ * parents as p_row_ptr / p_col / p_edge_vid, validities[n_validities * n_worlds] (1 = holds in that world). */
+typedef struct porrt_graph porrt_graph;
+int32_t porrt_graph_load_json(porrt_ctx* ctx, const char* path, porrt_graph** out_graph);
+int32_t porrt_graph_info(const porrt_graph* g, int64_t* out_n_nodes, int64_t* out_n_children, int64_t* out_n_parents,
+                         int32_t* out_n_validities, int32_t* out_n_worlds);
+int32_t porrt_graph_arrays(const porrt_graph* g, double* out_xy, int32_t* out_node_vid, int64_t* out_row_ptr, int32_t* out_col,
+                           int32_t* out_edge_vid, int64_t* out_p_row_ptr, int32_t* out_p_col, int32_t* out_p_edge_vid,
+                           uint8_t* out_validities);
+int32_t porrt_graph_destroy(porrt_graph* g);
+/* pto_graph::save: serde_json::to_writer_pretty layout.  p_* == NULL: parents are derived from the children (exact for graphs whose
+ * edges were added row by row, e.g. a PRM). */
+int32_t porrt_graph_save_json(porrt_ctx* ctx, const char* path, int64_t V, const double* xy, const int32_t* node_vid,
+                              const int64_t* row_ptr, const int32_t* col, const int32_t* edge_vid, const int64_t* p_row_ptr,
+                              const int32_t* p_col, const int32_t* p_edge_vid, const uint8_t* validities, int32_t n_validities,
+                              int32_t n_worlds);
+
 #ifdef __cplusplus
 }
 #endif

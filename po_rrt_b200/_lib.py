@@ -15,6 +15,13 @@ pp = C.POINTER
 # name -> (restype, argtypes); mirrors include/porrt_b200.h one to one
 SIGNATURES = {
     "porrt_version": (C.c_char_p, []),
+    "porrt_pgm_read": (i32, [vp, C.c_char_p, vp, i64, vp, vp]),
+    "porrt_pgm_write": (i32, [vp, C.c_char_p, vp, i32, i32, i32]),
+    "porrt_graph_load_json": (i32, [vp, C.c_char_p, vp]),
+    "porrt_graph_info": (i32, [vp, vp, vp, vp, vp, vp]),
+    "porrt_graph_arrays": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "porrt_graph_destroy": (i32, [vp]),
+    "porrt_graph_save_json": (i32, [vp, C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]),
     "porrt_ctx_create": (i32, [i32, pp(vp)]),
     "porrt_ctx_destroy": (i32, [vp]),
     "porrt_ctx_set_stream": (i32, [vp, vp]),

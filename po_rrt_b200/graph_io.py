@@ -6,9 +6,11 @@ Format: {"nodes": [{"state": [x, y], "validity_id": n, "parents": [{"id": i, "va
          "validities": [[bool, ...], ...]}          (validities[v][w]: validity v holds in world w, pto_graph.rs:95-101)
 f64 values are written with Python's shortest round-trip repr (serde_json/ryu also writes shortest round-trip digits; the two may
 differ in exponent spelling, which every JSON reader accepts)."""
-import json
+import ctypes as C
 
 import numpy as np
+
+from . import _lib
 
 
 class PTOGraphArrays:
@@ -28,31 +30,27 @@ class PTOGraphArrays:
         return len(self.xy)
 
 
-def _csr(lists, key):
-    rp = np.zeros(len(lists) + 1, np.int64)
-    for k, l in enumerate(lists):
-        rp[k + 1] = rp[k] + len(l)
-    flat = [e[key] for l in lists for e in l]
-    return rp, np.asarray(flat, np.int32)
-
-
 def load_pto_graph(path):
-    """pto_graph::load (pto_graph.rs:110-118) -> PTOGraphArrays; edge order is the stored (insertion) order"""
-    with open(path) as f:
-        g = json.load(f)
-    nodes = g["nodes"]
-    for n in nodes:
-        if len(n["state"]) != 2:
-            raise ValueError("state is not [f64; 2] (to_pto_node's try_into().unwrap() would panic)")
-    xy = np.array([n["state"] for n in nodes], np.float64).reshape(-1, 2)
-    nvid = np.array([n["validity_id"] for n in nodes], np.int32)
-    rp, col = _csr([n["children"] for n in nodes], "id")
-    _, ev = _csr([n["children"] for n in nodes], "validity_id")
-    prp, pcol = _csr([n["parents"] for n in nodes], "id")
-    _, pev = _csr([n["parents"] for n in nodes], "validity_id")
-    if len(col) and (col.min() < 0 or col.max() >= len(nodes)) or len(pcol) and (pcol.min() < 0 or pcol.max() >= len(nodes)):
-        raise ValueError("edge id out of range")
-    val = np.array([[1 if b else 0 for b in v] for v in g["validities"]], np.uint8)
+    """pto_graph::load (pto_graph.rs:110-118) -> PTOGraphArrays; edge order is the stored (insertion) order.  The reader is the
+    library's (csrc/formats.cu: porrt_graph_load_json)."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.porrt_graph_load_json(None, str(path).encode(), C.byref(h))
+    if rc != 0:
+        raise ValueError("porrt_graph_load_json failed [status %d] (malformed file: the reference's serde / try_into unwrap would panic)" % rc)
+    try:
+        nn, nc, npar = C.c_int64(), C.c_int64(), C.c_int64()
+        nv, nw = C.c_int32(), C.c_int32()
+        lib.porrt_graph_info(h, C.byref(nn), C.byref(nc), C.byref(npar), C.byref(nv), C.byref(nw))
+        V = nn.value
+        xy, nvid = np.empty((V, 2)), np.empty(V, np.int32)
+        rp, col, ev = np.empty(V + 1, np.int64), np.empty(nc.value, np.int32), np.empty(nc.value, np.int32)
+        prp, pcol, pev = np.empty(V + 1, np.int64), np.empty(npar.value, np.int32), np.empty(npar.value, np.int32)
+        val = np.empty((nv.value, nw.value), np.uint8)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        lib.porrt_graph_arrays(h, p(xy), p(nvid), p(rp), p(col), p(ev), p(prp), p(pcol), p(pev), p(val))
+    finally:
+        lib.porrt_graph_destroy(h)
     return PTOGraphArrays(xy, nvid, rp, col, ev, prp, pcol, pev, val)
 
 
@@ -69,12 +67,11 @@ def transpose_csr(row_ptr, col, edge_vid, n):
 
 
 def save_pto_graph(path, g, indent=2):
-    """pto_graph::save (pto_graph.rs:105-108); `g` is a PTOGraphArrays"""
-    def edges(rp, col, ev, k):
-        return [{"id": int(col[e]), "validity_id": int(ev[e])} for e in range(rp[k], rp[k + 1])]
-    nodes = [{"state": [float(g.xy[k, 0]), float(g.xy[k, 1])], "validity_id": int(g.node_vid[k]),
-              "parents": edges(g.p_row_ptr, g.p_col, g.p_edge_vid, k), "children": edges(g.row_ptr, g.col, g.edge_vid, k)}
-             for k in range(g.n_nodes)]
-    doc = {"nodes": nodes, "validities": [[bool(b) for b in v] for v in g.validities]}
-    with open(path, "w") as f:
-        json.dump(doc, f, indent=indent)
+    """pto_graph::save (pto_graph.rs:105-108); `g` is a PTOGraphArrays.  The writer is the library's (porrt_graph_save_json):
+    serde_json::to_writer_pretty layout, floats as shortest round-trip digits in ryu's spelling."""
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    val = np.ascontiguousarray(g.validities, np.uint8).reshape(len(g.validities), -1)
+    rc = _lib.load().porrt_graph_save_json(None, str(path).encode(), g.n_nodes, p(g.xy), p(g.node_vid), p(g.row_ptr), p(g.col), p(g.edge_vid),
+                                           p(g.p_row_ptr), p(g.p_col), p(g.p_edge_vid), p(val), val.shape[0], val.shape[1])
+    if rc != 0:
+        raise OSError("porrt_graph_save_json failed [status %d]" % rc)

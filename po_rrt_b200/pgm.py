@@ -1,48 +1,29 @@
 """PNM gray-map reader/writer (P2 ASCII and P5 binary, 8 bit), the decode step of Map::open_image
-(reference src/map_io.rs:98-105: image::open -> ImageLuma8, anything else panics)."""
+(reference src/map_io.rs:98-105: image::open -> ImageLuma8, anything else panics).  Thin wrappers: the decoder is the library's
+(csrc/formats.cu: porrt_pgm_read / porrt_pgm_write), the same code a Rust or C caller gets."""
+import ctypes as C
+
 import numpy as np
 
-
-def _tokens(data, pos, n):
-    out = []
-    while len(out) < n:
-        while pos < len(data) and data[pos:pos + 1].isspace():
-            pos += 1
-        if data[pos:pos + 1] == b"#":
-            while pos < len(data) and data[pos:pos + 1] != b"\n":
-                pos += 1
-            continue
-        start = pos
-        while pos < len(data) and not data[pos:pos + 1].isspace():
-            pos += 1
-        out.append(data[start:pos])
-    return out, pos
+from . import _lib
 
 
 def read_pgm(path):
-    with open(path, "rb") as f:
-        data = f.read()
-    (magic, w, h, maxval), pos = _tokens(data, 0, 4)
-    w, h, maxval = int(w), int(h), int(maxval)
-    if magic not in (b"P2", b"P5") or not 0 < maxval < 256:
-        raise ValueError("Wrong image format! (only 8-bit P2/P5 gray maps decode to ImageLuma8)")
-    if magic == b"P5":
-        pos += 1  # exactly one whitespace byte after maxval
-        img = np.frombuffer(data, np.uint8, w * h, pos).reshape(h, w).copy()
-    else:
-        vals, _ = _tokens(data, pos, w * h)
-        img = np.array([int(v) for v in vals], np.uint8).reshape(h, w)
+    lib = _lib.load()
+    h, w = C.c_int32(), C.c_int32()
+    rc = lib.porrt_pgm_read(None, str(path).encode(), None, 0, C.byref(h), C.byref(w))
+    if rc != 4:   # PORRT_ERR_CAPACITY = the size query answered; anything else is the reference's panic
+        raise ValueError("Wrong image format! (only 8-bit P2/P5 gray maps decode to ImageLuma8) [status %d]" % rc)
+    img = np.empty((h.value, w.value), np.uint8)
+    rc = lib.porrt_pgm_read(None, str(path).encode(), img.ctypes.data_as(C.c_void_p), img.size, C.byref(h), C.byref(w))
+    if rc != 0:
+        raise ValueError("Impossible to open image: %s [status %d]" % (path, rc))
     return img
 
 
 def write_pgm(path, img, binary=True):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape
-    with open(path, "wb") as f:
-        if binary:
-            f.write(b"P5\n%d %d\n255\n" % (w, h))
-            f.write(img.tobytes())
-        else:
-            f.write(b"P2\n%d %d\n255\n" % (w, h))
-            for row in img:
-                f.write(b" ".join(b"%d" % v for v in row) + b"\n")
+    rc = _lib.load().porrt_pgm_write(None, str(path).encode(), img.ctypes.data_as(C.c_void_p), h, w, 1 if binary else 0)
+    if rc != 0:
+        raise OSError("porrt_pgm_write failed [status %d]" % rc)
