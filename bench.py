@@ -462,9 +462,10 @@ def belief_problem(Z, visibility, max_step, search_radius, n_min=5000):
     return {"occ": occ, "zones": zones, "low": low, "up": up, "visibility": visibility, "pto": pto, "Z": Z, "grow_ms": 1e3 * t_grow}
 
 
-def belief_run(ctx, prob, reps=3, copy=False):
+def belief_run(ctx, prob, reps=3, copy=None):
     """plan_belief_space on the device: reachable beliefs + visibility + implicit belief graph + value backups + policy;
-    best of `reps` wall times, the phases of the best run and the column solver's device counters"""
+    best of `reps` wall times, the phases of the best run and the column solver's device counters.  copy=None: what the planner
+    needs -- the policy and its expected cost; the V x B table stays on the device and is fetched afterwards for the checks."""
     import po_rrt_b200 as P
     pmap = P.MapShelfDomain(ctx, prob["occ"], prob["low"], prob["up"])
     pmap.add_zones(prob["zones"], prob["visibility"])
@@ -479,6 +480,8 @@ def belief_run(ctx, prob, reps=3, copy=False):
         t = time.perf_counter() - t0
         if best is None or t < best[0]:
             best = (t, [float(x) for x in plan.phase_ms], list(ctx.last_phase_ms()[:2]))
+    if plan.dist is None:
+        t0 = time.perf_counter(); plan.fetch_table(); best = best + (1e3 * (time.perf_counter() - t0),)
     return plan, best, (xy, nvid, rp, col, ev, fin_ids, fm, pmap)
 
 
@@ -494,8 +497,10 @@ def belief_measurement(ctx, Z=8, n_min=5000, visibility=0.5, max_step=0.1, searc
     out = {"zones": Z, "nodes": V, "directed_edges": E, "beliefs": B, "belief_nodes": V * B, "rounds_max": int(plan.sweeps),
            "gpu_ms_total": 1e3 * best[0],
            "gpu_phase_ms[tables,upload+types,backups,result]": [round(x, 3) for x in best[1]],
-           "call": "plan_belief_space: porrt_reachable_belief_states + porrt_visibility + porrt_belief_vi + porrt_extract_policy; "
-                   "the V*B table is read through porrt_belief_result (ctx-owned pinned memory)",
+           "call": "plan_belief_space: porrt_reachable_belief_states + porrt_visibility + porrt_belief_vi + porrt_extract_policy -> "
+                   "the policy and its expected cost; the V*B table stays on the device (the policy walk fetches the value columns it "
+                   "visits) and comes over on demand through porrt_belief_result",
+           "table_fetch_ms": round(best[3], 3) if len(best) > 3 else None,
            "roadmap_growth_cpu_ms": round(prob["grow_ms"], 1)}
     dev_ms, offers = best[2]
     if dev_ms and dev_ms > 0:
@@ -520,12 +525,14 @@ def belief_measurement(ctx, Z=8, n_min=5000, visibility=0.5, max_step=0.1, searc
         try:
             t0 = time.perf_counter()
             other = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, [1.0 / Z] * Z, fin_ids, fm, copy=False)
+            same_policy = bool(np.array_equal(other.policy_node, plan.policy_node) and np.array_equal(other.policy_belief, plan.policy_belief) and
+                               other.expected_cost == plan.expected_cost)
             out["global_sweeps_ms_total"] = 1e3 * (time.perf_counter() - t0)
             out["global_sweeps_phase_ms"] = [round(float(x), 3) for x in other.phase_ms]
             out["global_sweeps"] = int(other.sweeps)
         finally:
             ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 0)
-        out["bit_exact_vs_global_sweeps"] = bool(np.array_equal(other.dist, keep))
+        out["bit_exact_vs_global_sweeps"] = bool(np.array_equal(other.dist, keep)) and same_policy
     return out
 
 _REAL_STDOUT = None

@@ -454,13 +454,25 @@ def dijkstra_worlds_resident_prm(fns, V, finals_per_world, want_dist=True):
 
 
 class BeliefPlan:
-    pass
+    """result of plan_belief_space; `dist` / `type` are None when the call was made with copy=None -- fetch_table() then brings
+    the ctx-owned table over on demand (porrt_belief_result; valid until the next belief call on the ctx)"""
+    dist = None
+    type = None
+
+    def fetch_table(self):
+        pd, pt = C.POINTER(C.c_double)(), C.POINTER(C.c_uint8)()
+        self._ctx.check(self._ctx.lib.porrt_belief_result(self._ctx.h, C.byref(pd), C.byref(pt), None, None))
+        self.dist = np.ctypeslib.as_array(pd, shape=self._shape)
+        self.type = np.ctypeslib.as_array(pt, shape=self._shape)
+        return self.dist, self.type
 
 
 def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, final_ids, final_masks_words, beliefs=None, copy=True):
     """PTO::plan_belief_space (src/pto.rs:152-182) for a grown roadmap given as CSR (children adjacency).
     Returns a BeliefPlan with beliefs, visible (zone masks), dist[V,B], type[V,B], policy arrays, expected_cost.
-    copy=False: dist / type are views of the ctx-owned pinned result (porrt_belief_result), valid until the next call on the ctx."""
+    copy=False: dist / type are views of the ctx-owned pinned result (porrt_belief_result), valid until the next call on the ctx.
+    copy=None: policy only -- the V x B table stays on the device (the policy walk fetches the few value columns it visits);
+    plan.fetch_table() brings it over later if wanted."""
     ctx = fns.ctx
     fns._need()
     row_ptr = np.ascontiguousarray(row_ptr, np.int64)
@@ -488,11 +500,9 @@ def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, f
                                       len(fin), _p(plan.dist) if copy else None, _p(plan.type) if copy else None, C.byref(sweeps),
                                       _p(plan.phase_ms)))
     plan.sweeps = sweeps.value
-    if not copy:
-        pd, pt = C.POINTER(C.c_double)(), C.POINTER(C.c_uint8)()
-        ctx.check(ctx.lib.porrt_belief_result(ctx.h, C.byref(pd), C.byref(pt), None, None))
-        plan.dist = np.ctypeslib.as_array(pd, shape=(V, B))
-        plan.type = np.ctypeslib.as_array(pt, shape=(V, B))
+    plan._ctx, plan._shape = ctx, (V, B)
+    if copy is False:
+        plan.fetch_table()
     cap = 4096
     n, cost = C.c_int64(), C.c_double()
     while True:

@@ -136,6 +136,14 @@ struct porrt_ctx {
     std::vector<int32_t> succ_belief;             // successor belief ids
     std::vector<uint8_t> compat;                  // [B * n_validities]
     int32_t n_validities = 0;
+    // column-solver results stay on the device ([column][node], dedicated buffer); the host copy of the whole table is made only
+    // when somebody asks for it (out_dist / porrt_belief_result), the policy walk fetches the few columns it visits
+    bool on_host = false;
+    DevBuf dev;
+    const double* d_dist_cm = nullptr; const uint8_t* d_type_cm = nullptr; const uint8_t* d_type = nullptr; const int32_t* d_colpos = nullptr;
+    std::vector<int32_t> colpos;
+    std::vector<std::vector<double>> col_dist;    // [B] lazily fetched columns (empty = not fetched)
+    std::vector<std::vector<uint8_t>> col_type;
   } bel;
   std::vector<int32_t> bel_node_vid;
   // last PRM result, kept on the device (valid until the next call on this ctx)

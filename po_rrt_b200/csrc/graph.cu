@@ -1007,6 +1007,54 @@ __global__ void __launch_bounds__(256) belief_untranspose_kernel(const double* _
   }
 }
 
+// The whole V x B table of the last porrt_belief_vi on the host: into the ctx's pinned copy (R.dist / R.type) and, if given, the
+// caller's buffers.  d_dist_nb: the [node][belief] table on the device (global sweeps), or null = bring the column solver's
+// [column][node] table into that layout first.  The DMA runs in 8 pieces whose hand-over to the caller's buffer overlaps it.
+static int32_t belief_download_full(porrt_ctx* ctx, const double* d_dist_nb, double* out_dist, uint8_t* out_type) {
+  auto& R = ctx->bel;
+  cudaStream_t st = ctx->stream;
+  const int64_t V = R.V;
+  const int B = R.B;
+  const size_t nb = (size_t)V * B;
+  if (!d_dist_nb) {
+    CUDA_TRY(ctx, ctx->scratch[3].ensure(nb * 8));
+    double* d = ctx->scratch[3].as<double>();
+    belief_untranspose_kernel<<<dim3(div_up(V, 32), div_up(B, 32)), 256, 0, st>>>(R.d_dist_cm, V, R.d_colpos, V, B, d);
+    LAUNCH_CHECK(ctx);
+    d_dist_nb = d;
+  }
+  CUDA_TRY(ctx, ctx->pin[3].ensure(nb * 9 + 64));
+  double* h_dist = ctx->pin[3].as<double>();
+  uint8_t* h_type = (uint8_t*)(h_dist + nb);
+  const int n_pieces = nb > (1u << 20) ? 8 : 1;
+  for (int k = 0; k < n_pieces; ++k) {
+    const size_t lo = nb * (size_t)k / (size_t)n_pieces, hi = nb * (size_t)(k + 1) / (size_t)n_pieces;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_dist + lo, d_dist_nb + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_type + lo, R.d_type + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t[k], st));
+  }
+  const int nt = n_pieces > 1 && (out_dist || out_type) ? 4 : 1;
+  std::vector<int> bad((size_t)nt, 0);
+  auto hand_on = [&](int t) {
+    for (int k = t; k < n_pieces; k += nt) {
+      if (cudaEventSynchronize(ctx->ev_t[k]) != cudaSuccess) { bad[(size_t)t] = 1; return; }
+      const size_t lo = nb * (size_t)k / (size_t)n_pieces, hi = nb * (size_t)(k + 1) / (size_t)n_pieces;
+      if (out_dist) memcpy(out_dist + lo, h_dist + lo, (hi - lo) * 8);
+      if (out_type) memcpy(out_type + lo, h_type + lo, hi - lo);
+    }
+  };
+  if (nt == 1) hand_on(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(hand_on, t);
+    for (auto& t : th) t.join();
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  for (int x : bad) if (x) return porrt_fail(ctx, PORRT_ERR_CUDA, "belief_vi: result copy failed");
+  R.dist = h_dist; R.type = h_type; R.on_host = true;
+  return PORRT_OK;
+}
+
 PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, const int32_t* col, const int32_t* edge_vid,
                                   const double* xy, const int32_t* node_vid, const uint64_t* validities, int32_t n_validities,
                                   int32_t mask_words, int32_t n_worlds, const double* beliefs, int32_t B,
@@ -1102,15 +1150,24 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
 
   DevBuf& g = ctx->scratch[3];
   const size_t need = (size_t)(V + 1) * 16 + (size_t)E * 28 + (size_t)V * 16 + 2 * compat.size() + (size_t)V * 17 +
-                      (size_t)B * 40 + (size_t)V * B * 18 + zero_idx.size() * 8 + 24 * 16 + 512;
+                      (size_t)B * 40 + (cols ? 0 : (size_t)V * B * 8) + zero_idx.size() * 8 + 24 * 16 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
   int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
   double* d_cost = (double*)take((size_t)E * 8);
   double* d_xy = (double*)take((size_t)V * 16);
-  double* d_dist = (double*)take((size_t)V * B * 8);       // [node][belief]: the caller's layout
-  double* d_dist_cm = (double*)take((size_t)V * B * 8);    // [column][node]: the column solver's table
+  double* d_dist = cols ? nullptr : (double*)take((size_t)V * B * 8);   // [node][belief]: the table of the global sweeps
+  // the column solver's table ([column][node]), the node types and the column map outlive the call (lazy result, policy walk)
+  auto& R = ctx->bel;
+  R.V = 0; R.on_host = false;
+  CUDA_TRY(ctx, R.dev.ensure((size_t)V * B * 10 + (size_t)B * 4 + 4 * 16));
+  char* rb = R.dev.as<char>();
+  auto take_r = [&](size_t bytes) { char* p = rb; rb += (bytes + 15) & ~(size_t)15; return p; };
+  double* d_dist_cm = (double*)take_r((size_t)V * B * 8);
+  uint8_t* d_type = (uint8_t*)take_r((size_t)V * B);
+  uint8_t* d_type_cm = (uint8_t*)take_r((size_t)V * B);
+  int32_t* d_colpos = (int32_t*)take_r((size_t)B * 4);
   uint64_t* d_cmask = (uint64_t*)take((size_t)B * 32);
   int32_t* d_col = (int32_t*)take((size_t)E * 4);
   int32_t* d_evid = (int32_t*)take((size_t)E * 4);
@@ -1120,15 +1177,12 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   double* d_cost_t = (double*)take((size_t)E * 8);
   int32_t* d_nvid = (int32_t*)take((size_t)V * 4);
   int32_t* d_nset = (int32_t*)take((size_t)V * 4);
-  int32_t* d_colpos = (int32_t*)take((size_t)B * 4);
   int32_t* d_col_belief = (int32_t*)take((size_t)B * 4);
   int32_t* d_changed = (int32_t*)take(16);
   uint8_t* d_compat = (uint8_t*)take(compat.size());
   uint8_t* d_compat_t = (uint8_t*)take(compat.size());
   uint8_t* d_active = (uint8_t*)take((size_t)V);
   int32_t* d_epoch = (int32_t*)take((size_t)V * 4);
-  uint8_t* d_type = (uint8_t*)take((size_t)V * B);
-  uint8_t* d_type_cm = (uint8_t*)take((size_t)V * B);
   int64_t* d_zero = (int64_t*)take(zero_idx.size() * 8 + 8);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
   if (E) {
@@ -1198,8 +1252,6 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
       }
     }
     tmark(ctx);
-    belief_untranspose_kernel<<<dim3(div_up(V, 32), div_up(B, 32)), 256, 0, st>>>(d_dist_cm, V, d_colpos, V, B, d_dist);
-    LAUNCH_CHECK(ctx);
     unsigned long long offers = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&sweeps, d_changed, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(&offers, d_changed + 2, 8, cudaMemcpyDeviceToHost, st));
@@ -1225,60 +1277,32 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     }
   }
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
-  // results: to the caller and retained for porrt_extract_policy
-  auto& R = ctx->bel;
+  // results: retained for porrt_extract_policy / porrt_belief_result; to the caller if asked for
   R.V = V; R.B = B; R.n_worlds = nw; R.n_validities = n_validities;
   R.row_ptr.assign(row_ptr, row_ptr + V + 1);
   R.col.assign(col, col + E); R.edge_vid.assign(edge_vid, edge_vid + E);
   R.xy.assign(xy, xy + 2 * V);
   R.beliefs.assign(beliefs, beliefs + (size_t)B * nw);
-  CUDA_TRY(ctx, ctx->pin[3].ensure((size_t)V * B * 9 + 64));
-  double* h_dist = ctx->pin[3].as<double>();
-  uint8_t* h_type = (uint8_t*)(h_dist + (size_t)V * B);
-  R.dist = h_dist; R.type = h_type;
   R.node_obs_set = node_set; R.compat = compat;
   R.succ_ptr.resize(sets.size() * (size_t)B + 1); R.succ_belief.resize((size_t)succ.n_succ);   // the policy walk reads them on the host
   CUDA_TRY(ctx, cudaMemcpyAsync(R.succ_ptr.data(), succ.succ_ptr, R.succ_ptr.size() * 8, cudaMemcpyDeviceToHost, st));
   if (succ.n_succ) CUDA_TRY(ctx, cudaMemcpyAsync(R.succ_belief.data(), succ.succ_b, (size_t)succ.n_succ * 4, cudaMemcpyDeviceToHost, st));
   type_finish_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_type, V * (int64_t)B);
   LAUNCH_CHECK(ctx);
-  std::vector<int32_t> nvid(node_vid, node_vid + V);
-  {
-    // The table comes back by DMA into the pinned retained copy in pieces; host threads hand each piece on to the caller's
-    // buffer as soon as its event has fired, so the second copy (172 MB at B = 4095) hides behind the first.
-    const size_t nb = (size_t)V * B;
-    const int n_pieces = nb > (1u << 20) ? 8 : 1;
-    for (int k = 0; k < n_pieces; ++k) {
-      const size_t lo = nb * (size_t)k / (size_t)n_pieces, hi = nb * (size_t)(k + 1) / (size_t)n_pieces;
-      CUDA_TRY(ctx, cudaMemcpyAsync(h_dist + lo, d_dist + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(ctx, cudaMemcpyAsync(h_type + lo, d_type + lo, hi - lo, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_t[k], st));
-    }
-    const int nt = n_pieces > 1 ? 4 : 1;
-    std::vector<int> bad((size_t)nt, 0);
-    auto hand_on = [&](int t) {
-      for (int k = t; k < n_pieces; k += nt) {
-        if (cudaEventSynchronize(ctx->ev_t[k]) != cudaSuccess) { bad[(size_t)t] = 1; return; }
-        const size_t lo = nb * (size_t)k / (size_t)n_pieces, hi = nb * (size_t)(k + 1) / (size_t)n_pieces;
-        if (out_dist) memcpy(out_dist + lo, h_dist + lo, (hi - lo) * 8);
-        if (out_type) memcpy(out_type + lo, h_type + lo, hi - lo);
-      }
-    };
-    if (nt == 1) hand_on(0);
-    else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < nt; ++t) th.emplace_back(hand_on, t);
-      for (auto& t : th) t.join();
-    }
+  R.d_dist_cm = cols ? d_dist_cm : nullptr; R.d_type_cm = cols ? d_type_cm : nullptr; R.d_type = d_type; R.d_colpos = d_colpos;
+  R.colpos = colpos;
+  R.col_dist.assign((size_t)B, std::vector<double>()); R.col_type.assign((size_t)B, std::vector<uint8_t>());
+  R.dist = nullptr; R.type = nullptr;
+  ctx->bel_node_vid.assign(node_vid, node_vid + V);
+  if (!cols || out_dist || out_type) {
+    int32_t rc = belief_download_full(ctx, d_dist, out_dist, out_type);
+    if (rc) return rc;
+  } else {
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    for (int x : bad) if (x) return porrt_fail(ctx, PORRT_ERR_CUDA, "belief_vi: result copy failed");
   }
   if (out_sweeps) *out_sweeps = sweeps;
   t1 = now_ms(); ph[3] = t1 - t0;
   if (out_phase_ms) memcpy(out_phase_ms, ph, sizeof(ph));
-  // keep node/edge validity ids for the policy walk
-  R.edge_vid.assign(edge_vid, edge_vid + E);
-  ctx->bel_node_vid = nvid;
   return PORRT_OK;
 }
 
@@ -1287,6 +1311,11 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
 PORRT_API int32_t porrt_belief_result(porrt_ctx* ctx, const double** out_dist, const uint8_t** out_type, int64_t* out_V, int32_t* out_B) {
   CTX_CHECK(ctx);
   if (ctx->bel.V <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "belief_result: run porrt_belief_vi first");
+  if (!ctx->bel.on_host) {   // the table is still on the device only: bring it over now
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int32_t rc = belief_download_full(ctx, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+  }
   if (out_dist) *out_dist = ctx->bel.dist;
   if (out_type) *out_type = ctx->bel.type;
   if (out_V) *out_V = ctx->bel.V;
@@ -1302,6 +1331,31 @@ PORRT_API int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_
   if (R.V <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "extract_policy: run porrt_belief_vi first");
   const int B = R.B, nw = R.n_worlds, nv = R.n_validities;
   const std::vector<int32_t>& nvid = ctx->bel_node_vid;
+  // values / types of belief node id = node * B + belief.  When the table is still on the device only, the walk fetches the
+  // columns (beliefs) it visits -- a policy touches a few dozen of the B columns, 8 * V bytes each
+  bool fetch_failed = false;
+  auto column = [&](int b) {
+    if (R.col_dist[(size_t)b].empty()) {
+      R.col_dist[(size_t)b].resize((size_t)R.V); R.col_type[(size_t)b].resize((size_t)R.V);
+      cudaSetDevice(ctx->device);
+      if (cudaMemcpyAsync(R.col_dist[(size_t)b].data(), R.d_dist_cm + (size_t)R.colpos[(size_t)b] * R.V, (size_t)R.V * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaMemcpyAsync(R.col_type[(size_t)b].data(), R.d_type_cm + (size_t)R.colpos[(size_t)b] * R.V, (size_t)R.V, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        fetch_failed = true;
+    }
+  };
+  auto dist_at = [&](int64_t id) -> double {
+    if (R.on_host) return R.dist[(size_t)id];
+    const int b = (int)(id % B);
+    column(b);
+    return R.col_dist[(size_t)b][(size_t)(id / B)];
+  };
+  auto type_at = [&](int64_t id) -> uint8_t {
+    if (R.on_host) return R.type[(size_t)id];
+    const int b = (int)(id % B);
+    column(b);
+    return R.col_type[(size_t)b][(size_t)(id / B)];
+  };
   auto state = [&](int64_t n) { return &R.xy[2 * n]; };
   auto norm2 = [&](const double* a, const double* b) {
     double d2 = 0.0;
@@ -1321,21 +1375,21 @@ PORRT_API int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_
     const int b = (int)(bn % B);
     // children of the belief node in stored order (observation edges first if Observation, else action edges)
     std::map<int32_t, std::vector<Child>> by_belief;  // BTreeMap keyed by child.belief_id (belief_graph.rs:228-241)
-    const uint8_t ty = R.type[(size_t)bn];
+    const uint8_t ty = type_at(bn);
     if (ty == PORRT_NODE_OBSERVATION) {
       const int64_t sp = (int64_t)R.node_obs_set[n] * B + b;
       for (int64_t k = R.succ_ptr[sp]; k < R.succ_ptr[sp + 1]; ++k) {
         const int32_t cb = R.succ_belief[k];
         if (!R.compat[(size_t)cb * nv + nvid[n]]) continue;
         const int64_t cid = n * B + cb;
-        by_belief[cb].push_back({cid, norm2(state(n), state(n)), R.dist[(size_t)cid]});
+        by_belief[cb].push_back({cid, norm2(state(n), state(n)), dist_at(cid)});
       }
     } else if (ty == PORRT_NODE_ACTION) {
       for (int64_t e = R.row_ptr[n]; e < R.row_ptr[n + 1]; ++e) {
         const int32_t c = R.col[e];
         if (!R.compat[(size_t)b * nv + nvid[c]] || !R.compat[(size_t)b * nv + R.edge_vid[e]]) continue;
         const int64_t cid = (int64_t)c * B + b;
-        by_belief[b].push_back({cid, norm2(state(n), state(c)), R.dist[(size_t)cid]});
+        by_belief[b].push_back({cid, norm2(state(n), state(c)), dist_at(cid)});
       }
     }
     for (auto& kv : by_belief) {
@@ -1347,8 +1401,9 @@ PORRT_API int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_
         const double cost = p * (c.cost_to_child + c.expected_from_child);
         if (cost < best_cost) { best_cost = cost; best_id = c.id; }
       }
-      if (!(p * R.dist[(size_t)best_id] <= R.dist[(size_t)bn])) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p * cost[best] <= cost[node]) (belief_graph.rs:261)");
-      const bool leaf = R.dist[(size_t)best_id] == 0.0;
+      if (fetch_failed) return porrt_fail(ctx, PORRT_ERR_CUDA, "extract_policy: fetching a value column failed");
+      if (!(p * dist_at(best_id) <= dist_at(bn))) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p * cost[best] <= cost[node]) (belief_graph.rs:261)");
+      const bool leaf = dist_at(best_id) == 0.0;
       const int64_t pid = (int64_t)pol.size();
       pol.push_back({(int32_t)(best_id / B), (int32_t)(best_id % B), (int32_t)top.first, (uint8_t)leaf});
       if (!leaf) lifo.push_back({pid, best_id});
@@ -1356,7 +1411,7 @@ PORRT_API int32_t porrt_extract_policy(porrt_ctx* ctx, int32_t* out_node, int32_
     }
   }
   if (out_n) *out_n = (int64_t)pol.size();
-  if (out_expected_cost) *out_expected_cost = R.dist[0];
+  if (out_expected_cost) *out_expected_cost = dist_at(0);
   if ((int64_t)pol.size() > cap || !out_node || !out_belief || !out_parent || !out_is_leaf) return porrt_fail(ctx, PORRT_ERR_CAPACITY, "extract_policy: cap too small");
   for (size_t k = 0; k < pol.size(); ++k) { out_node[k] = pol[k].node; out_belief[k] = pol[k].belief; out_parent[k] = pol[k].parent; out_is_leaf[k] = pol[k].leaf; }
   return PORRT_OK;

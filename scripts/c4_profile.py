@@ -24,5 +24,5 @@ fm = P.words_from_bits(fin_bits)
 for rep in range(4):
     t0=time.perf_counter(); bel = pmap.reachable_belief_states(b0); t1=time.perf_counter()
     vis, st = pmap.visible_zones(xy); t2=time.perf_counter()
-    plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, fm, beliefs=bel, copy=(rep == 0)); t3=time.perf_counter()
+    plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, fm, beliefs=bel, copy=(True if rep == 0 else False if rep == 1 else None)); t3=time.perf_counter()
     print("reachable %.1f ms, visible %.1f ms, plan(with beliefs given) %.1f ms, phases %s sweeps %d" % (1e3*(t1-t0),1e3*(t2-t1),1e3*(t3-t2),[round(float(x),1) for x in plan.phase_ms], plan.sweeps))
