@@ -1109,16 +1109,36 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   }
   // column order for colsolve.cu: beliefs sorted by the size of their support (observations only ever split it, so a column
   // reads Observation values from columns that come earlier), level by level
-  std::vector<int32_t> level((size_t)B, 0), colpos((size_t)B), col_belief((size_t)B);
+  std::vector<int32_t> level((size_t)B, 0), colpos((size_t)B), by_level((size_t)B);
   for (int b2 = 0; b2 < B; ++b2)
     for (int k = 0; k < mask_words; ++k) level[(size_t)b2] += __builtin_popcountll(support[(size_t)b2 * mask_words + k]);
-  for (int b2 = 0; b2 < B; ++b2) col_belief[(size_t)b2] = b2;
-  std::stable_sort(col_belief.begin(), col_belief.end(), [&](int32_t x, int32_t y) { return level[(size_t)x] < level[(size_t)y]; });
-  for (int c = 0; c < B; ++c) colpos[(size_t)col_belief[(size_t)c]] = c;
-  std::vector<int32_t> level_start;   // columns [level_start[k], level_start[k+1]) share a level
-  for (int c = 0; c < B; ++c)
-    if (c == 0 || level[(size_t)col_belief[(size_t)c]] != level[(size_t)col_belief[(size_t)c - 1]]) level_start.push_back(c);
-  level_start.push_back(B);
+  for (int b2 = 0; b2 < B; ++b2) by_level[(size_t)b2] = b2;
+  std::stable_sort(by_level.begin(), by_level.end(), [&](int32_t x, int32_t y) { return level[(size_t)x] < level[(size_t)y]; });
+  // Column positions.  On one GPU the columns of a level are simply consecutive.  With a communicator every level is cut into
+  // `world` shards of EQUAL width (the last columns of a shard may be unused padding) so that the exchange after a level is one
+  // plain ncclAllGather instead of a group of ragged broadcasts; rank r owns the columns [lo + r * per, lo + r * per + count_r).
+  const int shards = ctx->comm_world > 1 ? ctx->comm_world : 1;
+  struct Level { int lo, per, n_real; };
+  std::vector<Level> levels;
+  std::vector<int32_t> col_belief;   // belief of a column position, -1 = padding
+  for (int c = 0; c < B;) {
+    int e = c;
+    while (e < B && level[(size_t)by_level[(size_t)e]] == level[(size_t)by_level[(size_t)c]]) ++e;
+    const int n_real = e - c, per = (n_real + shards - 1) / shards, lo = (int)col_belief.size();
+    col_belief.resize((size_t)lo + (size_t)per * shards, -1);
+    for (int r = 0; r < shards; ++r) {
+      int64_t a2, b2;
+      comm_shard_range(n_real, r, shards, &a2, &b2);
+      for (int64_t j = a2; j < b2; ++j) {
+        const int pos = lo + r * per + (int)(j - a2);
+        col_belief[(size_t)pos] = by_level[(size_t)(c + j)];
+        colpos[(size_t)by_level[(size_t)(c + j)]] = pos;
+      }
+    }
+    levels.push_back({lo, per, n_real});
+    c = e;
+  }
+  const int Bp = (int)col_belief.size();   // columns incl. padding (== B on one GPU)
   // observation successor tables, one entry per (set, belief), built on the device (belief_tables.cu)
   BeliefSuccDev succ = {};
   {
@@ -1139,10 +1159,10 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
 
   const bool cols = colsolve_fits(V, E, n_validities) && !ctx->force_global_sweeps && succ.levels_ok;
   const bool sharded = cols && ctx->comm_world > 1;   // the global sweeps are not sharded: every rank then computes the whole table
-  std::vector<uint64_t> cmask((size_t)B * 4, 0);
+  std::vector<uint64_t> cmask((size_t)Bp * 4, 0);
   if (cols)
-    for (int c = 0; c < B; ++c)
-      for (int v = 0; v < n_validities; ++v)
+    for (int c = 0; c < Bp; ++c)
+      for (int v = 0; col_belief[(size_t)c] >= 0 && v < n_validities; ++v)
         if (compat[(size_t)col_belief[(size_t)c] * n_validities + v]) cmask[(size_t)c * 4 + v / 64] |= (uint64_t)1 << (v % 64);
   // final belief nodes as indices into the table the backups run on ([column][node] for the column solver, else [node][belief])
   if (cols)
@@ -1150,7 +1170,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
 
   DevBuf& g = ctx->scratch[3];
   const size_t need = (size_t)(V + 1) * 16 + (size_t)E * 28 + (size_t)V * 16 + 2 * compat.size() + (size_t)V * 17 +
-                      (size_t)B * 40 + (cols ? 0 : (size_t)V * B * 8) + zero_idx.size() * 8 + 24 * 16 + 512;
+                      (size_t)Bp * 40 + (cols ? 0 : (size_t)V * B * 8) + zero_idx.size() * 8 + 24 * 16 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
@@ -1161,14 +1181,14 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   // the column solver's table ([column][node]), the node types and the column map outlive the call (lazy result, policy walk)
   auto& R = ctx->bel;
   R.V = 0; R.on_host = false;
-  CUDA_TRY(ctx, R.dev.ensure((size_t)V * B * 10 + (size_t)B * 4 + 4 * 16));
+  CUDA_TRY(ctx, R.dev.ensure((size_t)V * Bp * 9 + (size_t)V * B + (size_t)B * 4 + 4 * 16));
   char* rb = R.dev.as<char>();
   auto take_r = [&](size_t bytes) { char* p = rb; rb += (bytes + 15) & ~(size_t)15; return p; };
-  double* d_dist_cm = (double*)take_r((size_t)V * B * 8);
+  double* d_dist_cm = (double*)take_r((size_t)V * Bp * 8);
   uint8_t* d_type = (uint8_t*)take_r((size_t)V * B);
-  uint8_t* d_type_cm = (uint8_t*)take_r((size_t)V * B);
+  uint8_t* d_type_cm = (uint8_t*)take_r((size_t)V * Bp);
   int32_t* d_colpos = (int32_t*)take_r((size_t)B * 4);
-  uint64_t* d_cmask = (uint64_t*)take((size_t)B * 32);
+  uint64_t* d_cmask = (uint64_t*)take((size_t)Bp * 32);
   int32_t* d_col = (int32_t*)take((size_t)E * 4);
   int32_t* d_evid = (int32_t*)take((size_t)E * 4);
   uint32_t* d_ce = (uint32_t*)take((size_t)E * 4);
@@ -1177,7 +1197,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   double* d_cost_t = (double*)take((size_t)E * 8);
   int32_t* d_nvid = (int32_t*)take((size_t)V * 4);
   int32_t* d_nset = (int32_t*)take((size_t)V * 4);
-  int32_t* d_col_belief = (int32_t*)take((size_t)B * 4);
+  int32_t* d_col_belief = (int32_t*)take((size_t)Bp * 4);
   int32_t* d_changed = (int32_t*)take(16);
   uint8_t* d_compat = (uint8_t*)take(compat.size());
   uint8_t* d_compat_t = (uint8_t*)take(compat.size());
@@ -1194,7 +1214,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   CUDA_TRY(ctx, cudaMemcpyAsync(d_nset, node_set.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, compat.data(), compat.size(), cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_colpos, colpos.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_col_belief, col_belief.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_col_belief, col_belief.data(), (size_t)Bp * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_cmask, cmask.data(), cmask.size() * 8, cudaMemcpyHostToDevice, st));
   std::vector<uint8_t> compat_t;
   if (!cols) {   // the sweeps read the table transposed: the threads of a node (consecutive beliefs) read consecutive bytes
@@ -1205,7 +1225,7 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     CUDA_TRY(ctx, cudaMemsetAsync(d_epoch, 0, (size_t)V * 4, st));
   }
   double* d_table = cols ? d_dist_cm : d_dist;
-  fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_table, V * (int64_t)B);
+  fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_table, V * (int64_t)(cols ? Bp : B));
   LAUNCH_CHECK(ctx);
   if (!zero_idx.empty()) {
     CUDA_TRY(ctx, cudaMemcpyAsync(d_zero, zero_idx.data(), zero_idx.size() * 8, cudaMemcpyHostToDevice, st));
@@ -1235,18 +1255,15 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     ca.succ_col = succ.succ_col; ca.succ_p = succ.succ_p; ca.B = B; ca.sweeps_out = d_changed;
     ca.offers_out = (unsigned long long*)(d_changed + 2);
     tstart(ctx);
-    for (size_t lv = 0; lv + 1 < level_start.size(); ++lv) {
-      const int lo = level_start[lv], hi = level_start[lv + 1];
-      int64_t mlo = 0, mhi = hi - lo;
-      if (sharded) comm_shard_range(hi - lo, ctx->comm_rank, ctx->comm_world, &mlo, &mhi);
-      int32_t rc = colsolve_level(ctx, ca, COLSOLVE_BELIEF, lo + (int)mlo, lo + (int)mhi, st);
+    for (const Level& L : levels) {
+      int64_t a2 = 0, b2 = L.n_real;
+      if (sharded) comm_shard_range(L.n_real, ctx->comm_rank, ctx->comm_world, &a2, &b2);
+      const int mine = L.lo + (sharded ? ctx->comm_rank * L.per : 0);
+      int32_t rc = colsolve_level(ctx, ca, COLSOLVE_BELIEF, mine, mine + (int)(b2 - a2), st);
       if (rc) return rc;
       if (sharded) {
         std::vector<int64_t> off(ctx->comm_world + 1);
-        for (int r = 0; r < ctx->comm_world; ++r) {
-          int64_t a2, b2; comm_shard_range(hi - lo, r, ctx->comm_world, &a2, &b2);
-          off[r] = (lo + a2) * V * 8; off[r + 1] = (lo + b2) * V * 8;
-        }
+        for (int r = 0; r <= ctx->comm_world; ++r) off[r] = (int64_t)(L.lo + r * L.per) * V * 8;   // equal shards: one ncclAllGather
         rc = comm_all_gatherv_dev(ctx, nullptr, d_dist_cm, off.data(), st);
         if (rc) return rc;
       }
