@@ -102,39 +102,63 @@ __global__ void __launch_bounds__(256) sf_classify_kernel(SfArgs a, int round) {
     a.thr[(round + 1) % 3] = thr;
   }
   unsigned long long my_far = 0x7ff0000000000000ull;
-  for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_cur; qi += gridDim.x * blockDim.x) {
-    const int32_t v = a.list[cur][qi];
-    a.inq[cur][v] = 0;
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  // (the loop runs the same number of times for every lane of a warp: the appends below are aggregated per warp -- one atomicAdd on
+  // the list counters per warp instead of one per entry; 8e7 same-address atomics were a third of the run time at PRM scale)
+  for (int q0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; q0 < n_cur; q0 += stride) {
+    const int qi = q0 + lane;
+    const bool live = qi < n_cur;
+    const int32_t v = live ? a.list[cur][qi] : 0;
+    if (live) a.inq[cur][v] = 0;
     bool again = false;
     for (int k = 0; k < a.words; ++k) {
-      unsigned long long m = atomicExch(&a.dirty[cur][(int64_t)v * a.words + k], 0ull);
-      if (!m) continue;
+      unsigned long long m = live ? atomicExch(&a.dirty[cur][(int64_t)v * a.words + k], 0ull) : 0ull;
       __threadfence();   // the values are read after the mask was taken: a later improvement marks v again
-      unsigned long long keep = 0;
-      for (; m; m &= m - 1) {
-        const int w = k * 64 + __ffsll((long long)m) - 1;
-        const double dv = fabs(*(volatile double*)(a.dist + (int64_t)v * a.W + w));
-        bool near = dv <= thr;
-        if (near) {
-          const int at = atomicAdd(&a.pair_count[round & 1], 1);
-          if (at < a.pair_cap) a.pairs[at] = make_int2(v, w);
-          else near = false;   // push list full: wait a round
-        }
-        if (!near) {
-          keep |= 1ull << (w & 63);
+      unsigned long long near = 0, keep = 0;
+      for (unsigned long long mm = m; mm; mm &= mm - 1) {
+        const int b = __ffsll((long long)mm) - 1;
+        const double dv = fabs(*(volatile double*)(a.dist + (int64_t)v * a.W + k * 64 + b));
+        if (dv <= thr) near |= 1ull << b;
+        else {
+          keep |= 1ull << b;
           const unsigned long long bits = (unsigned long long)__double_as_longlong(dv);
           if (bits < my_far) my_far = bits;
         }
       }
+      // this warp's near pairs go to one reserved stretch of the push list
+      const int cnt = __popcll(near);
+      int incl = cnt;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&a.pair_count[round & 1], total);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        for (unsigned long long mm = near; mm; mm &= mm - 1) {
+          const int b = __ffsll((long long)mm) - 1;
+          if (base < a.pair_cap) a.pairs[base] = make_int2(v, k * 64 + b);
+          else keep |= 1ull << b;   // push list full: wait a round
+          ++base;
+        }
+      }
       if (keep) { atomicOr(&a.dirty[nxt][(int64_t)v * a.words + k], keep); again = true; }
     }
-    if (again && atomicExch(&a.inq[nxt][v], 1) == 0) a.list[nxt][atomicAdd(&a.counter[(round + 1) % 3], 1)] = v;
+    const bool first = again && atomicExch(&a.inq[nxt][v], 1) == 0;
+    const unsigned fm = __ballot_sync(0xffffffffu, first);
+    if (fm) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&a.counter[(round + 1) % 3], __popc(fm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (first) a.list[nxt][base + __popc(fm & ((1u << lane) - 1u))] = v;
+    }
   }
   for (int s2 = 16; s2 > 0; s2 >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, my_far, s2); if (o < my_far) my_far = o; }
   if ((threadIdx.x & 31) == 0 && my_far < *(volatile unsigned long long*)&a.min_far[(round + 1) % 3]) atomicMin(&a.min_far[(round + 1) % 3], my_far);
 }
 
 // Round r, step 2 (one WARP per (node, world) pair of the push list): offer  norm2(u, v) + dist[v][w]  to every parent u.
+// (8 lanes per pair, four pairs per warp in flight, was slower: 172 against 150 ms at PRM scale -- the record loads lose their coalescing.)
 __global__ void __launch_bounds__(256) sf_push_kernel(SfArgs a, int round) {
   const int nxt = (round & 1) ^ 1;
   const int n_pairs = min(a.pair_count[round & 1], a.pair_cap);
@@ -148,18 +172,31 @@ __global__ void __launch_bounds__(256) sf_push_kernel(SfArgs a, int round) {
     const int w = vw.y, k = w >> 6;
     const double dv = fabs(*(volatile double*)(a.dist + (int64_t)v * a.W + w));
     const int64_t e1 = a.row_t[v + 1];
-    for (int64_t e = a.row_t[v] + lane; e < e1; e += 32) {
-      const int32_t u = __ldg(a.col_t + e);
-      const double alt = __dadd_rn(__ldg(a.cost_t + e), dv);   // norm2(u, v) + dist[v], pto_graph.rs:293
-      double* du = a.dist + (int64_t)u * a.W + w;
-      ++n_off;
-      if (alt < *du) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(alt);
-        const unsigned long long old = atomicMin(reinterpret_cast<unsigned long long*>(du), bits);
-        if (bits < old) {
-          atomicOr(&a.dirty[nxt][(int64_t)u * a.words + k], 1ull << (w & 63));
-          if (atomicExch(&a.inq[nxt][u], 1) == 0) a.list[nxt][atomicAdd(&a.counter[(round + 1) % 3], 1)] = u;
+    for (int64_t e0 = a.row_t[v]; e0 < e1; e0 += 32) {
+      const int64_t e = e0 + lane;
+      bool first = false;
+      int32_t u = 0;
+      if (e < e1) {
+        u = __ldg(a.col_t + e);
+        const double alt = __dadd_rn(__ldg(a.cost_t + e), dv);   // norm2(u, v) + dist[v], pto_graph.rs:293
+        double* du = a.dist + (int64_t)u * a.W + w;
+        ++n_off;
+        if (alt < *du) {
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(alt);
+          const unsigned long long old = atomicMin(reinterpret_cast<unsigned long long*>(du), bits);
+          if (bits < old) {
+            const unsigned long long was = atomicOr(&a.dirty[nxt][(int64_t)u * a.words + k], 1ull << (w & 63));
+            // only the one who turned a clean word dirty can be the first to queue the node
+            first = was == 0 && atomicExch(&a.inq[nxt][u], 1) == 0;
+          }
         }
+      }
+      const unsigned fm = __ballot_sync(0xffffffffu, first);
+      if (fm) {   // one atomicAdd on the list counter per warp
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&a.counter[(round + 1) % 3], __popc(fm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (first) a.list[nxt][base + __popc(fm & ((1u << lane) - 1u))] = u;
       }
     }
   }
