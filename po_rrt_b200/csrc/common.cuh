@@ -150,6 +150,7 @@ struct porrt_ctx {
   int64_t prm_n = 0, prm_edges = 0;
   const int64_t* prm_row_ptr = nullptr;
   const int32_t* prm_col = nullptr;
+  const void* radii_ptr = nullptr; int64_t radii_lo = 0, radii_n = 0; double radii_ms = 0, radii_sr = 0;   // what pin[1] holds: heuristic_radius(k + 1) for k in [radii_lo, radii_n)
   DevBuf d_prm_row, d_prm_col;         // dedicated: the retained CSR must survive later calls that reuse the shared scratch
 
   // ---- last multi-modal PRM result (mmprm.cu): the explicit belief graph, kept for porrt_mmprm_fetch_graph

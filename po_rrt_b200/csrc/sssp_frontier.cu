@@ -6,8 +6,10 @@
 // At PRM scale (1e6 nodes, 5.3e7 directed edges, 64 worlds) a Bellman-Ford sweep touches E * W = 3.4e9 (edge, world) pairs and the
 // roadmap's diameter is several hundred hops: the order-free Jacobi sweeps of round 1 were never run at that size.  Here only
 // values that moved do work:
-//   * dist[v][w] (world fastest) holds the value; entries of nodes that are invalid in world w carry the sign bit (fixed, read
-//     through |.|, compare below every offer) -- the same encoding as colsolve.cu;
+//   * nodes are renumbered along a Morton curve and dist[w][v] is world-major, so the parents of a node (its spatial neighbours)
+//     sit in a few short runs of one world's row: the push step is bound by random 32-byte reads of this table;
+//   * entries of nodes that are invalid in world w carry the sign bit (fixed, read through |.|, compare below every offer) -- the
+//     same encoding as colsolve.cu;
 //   * dirty[v] = worlds whose value at v improved since v last pushed; a round's worklist holds the nodes with a non-empty mask;
 //   * one warp takes a worklist node v, clears its mask and, for every dirty world w, offers  norm2(u, v) + dist[v][w]  to every
 //     parent u (transposed adjacency; norm2 is symmetric bit for bit) with a 64-bit atomicMin (non-negative doubles order like
@@ -23,46 +25,90 @@
 
 namespace {
 
-__global__ void sf_count_kernel(const int32_t* __restrict__ col, int64_t E, int32_t* __restrict__ cnt) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < E) atomicAdd(&cnt[col[e]], 1);
+// ---- Morton numbering: pos = rank of the node's interleaved 16 + 16 bit cell coordinates
+__device__ __forceinline__ unsigned long long sf_ord(double x) {   // order-preserving bits
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
-// transposed records: row v lists (parent u, norm2(u, v)); one warp per row u of the forward CSR
-__global__ void sf_fill_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy, int64_t V,
-                               const int64_t* __restrict__ row_t, int32_t* __restrict__ cursor, int32_t* __restrict__ col_t,
-                               double* __restrict__ cost_t) {
+__device__ __forceinline__ double sf_unord(unsigned long long e) {
+  return __longlong_as_double((long long)((e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e));
+}
+__global__ void sf_bbox_kernel(const double2* __restrict__ xy, int64_t V, unsigned long long* __restrict__ box /* min x, min y, max x, max y */) {
+  unsigned long long lo_x = ~0ull, lo_y = ~0ull, hi_x = 0, hi_y = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 p = xy[i];
+    const unsigned long long ex = sf_ord(p.x), ey = sf_ord(p.y);
+    lo_x = min(lo_x, ex); hi_x = max(hi_x, ex); lo_y = min(lo_y, ey); hi_y = max(hi_y, ey);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
+    hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&box[0], lo_x); atomicMin(&box[1], lo_y); atomicMax(&box[2], hi_x); atomicMax(&box[3], hi_y); }
+}
+__device__ __forceinline__ unsigned sf_spread16(unsigned v) {
+  v &= 0xffffu; v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+__global__ void sf_morton_kernel(const double2* __restrict__ xy, int64_t V, const unsigned long long* __restrict__ box,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const double x0 = sf_unord(box[0]), y0 = sf_unord(box[1]), x1 = sf_unord(box[2]), y1 = sf_unord(box[3]);
+  const double2 p = xy[i];
+  const double fx = x1 > x0 ? (p.x - x0) / (x1 - x0) : 0.0, fy = y1 > y0 ? (p.y - y0) / (y1 - y0) : 0.0;   // (a schedule parameter only)
+  const unsigned cx = (unsigned)fmin(fmax(fx * 65535.0, 0.0), 65535.0), cy = (unsigned)fmin(fmax(fy * 65535.0, 0.0), 65535.0);
+  keys[i] = (uint64_t)(sf_spread16(cx) | (sf_spread16(cy) << 1));
+  vals[i] = (uint32_t)i;
+}
+__global__ void sf_perm_kernel(const uint32_t* __restrict__ order, int64_t V, int32_t* __restrict__ perm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < V) perm[order[i]] = (int32_t)i;
+}
+
+__global__ void sf_count_kernel(const int32_t* __restrict__ col, const int32_t* __restrict__ perm, int64_t E, int32_t* __restrict__ cnt) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) atomicAdd(&cnt[perm[col[e]]], 1);
+}
+// transposed records in the new numbering: row perm[v] lists (perm[u], norm2(u, v)); one warp per row u of the forward CSR
+__global__ void sf_fill_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy,
+                               const int32_t* __restrict__ perm, int64_t V, const int64_t* __restrict__ row_t, int32_t* __restrict__ cursor,
+                               int32_t* __restrict__ col_t, double* __restrict__ cost_t) {
   const int lane = threadIdx.x & 31;
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (u >= V) return;
   const double2 a = xy[u];
+  const int32_t pu = perm[u];
   for (int64_t e = row_ptr[u] + lane; e < row_ptr[u + 1]; e += 32) {
     const int32_t v = col[e];
     const double2 c = xy[v];
     const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
-    const int64_t pos = row_t[v] + atomicAdd(&cursor[v], 1);
-    col_t[pos] = (int32_t)u;
+    const int32_t pv = perm[v];
+    const int64_t pos = row_t[pv] + atomicAdd(&cursor[pv], 1);
+    col_t[pos] = pu;
     cost_t[pos] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // norm2(u, v), common.rs:203-213
   }
 }
 
-// dist[v][w] = +inf, or -inf where node v is invalid in world wlo + w (PTOGraphWorldView::parents filters by the parent node)
-__global__ void sf_init_kernel(const int32_t* __restrict__ node_vid, const uint64_t* __restrict__ validities, int mask_words, int64_t V,
-                               int W, int wlo, double* __restrict__ dist) {
+// dist[w][pos] = +inf, or -inf where the node is invalid in world wlo + w (PTOGraphWorldView::parents filters by the parent node)
+__global__ void sf_init_kernel(const int32_t* __restrict__ node_vid, const uint64_t* __restrict__ validities, int mask_words,
+                               const uint32_t* __restrict__ order, int64_t V, int W, int wlo, double* __restrict__ dist) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V * W) return;
-  const int64_t u = t / W;
-  const int wg = wlo + (int)(t - u * W);
-  const bool ok = node_vid ? ((validities[(int64_t)node_vid[u] * mask_words + (wg >> 6)] >> (wg & 63)) & 1) != 0 : true;
+  const int w = (int)(t / V);
+  const int64_t pos = t - (int64_t)w * V;
+  const int wg = wlo + w;
+  const bool ok = node_vid ? ((validities[(int64_t)node_vid[order[pos]] * mask_words + (wg >> 6)] >> (wg & 63)) & 1) != 0 : true;
   dist[t] = ok ? INFINITY : -INFINITY;
 }
 // finals: value 0 (keeping the sign), dirty in that world, on the first worklist
-__global__ void sf_seed_kernel(const int32_t* __restrict__ fin_node, const int32_t* __restrict__ fin_world, int64_t n, int W, int words,
-                               double* __restrict__ dist, unsigned long long* __restrict__ dirty, int32_t* __restrict__ inq,
+__global__ void sf_seed_kernel(const int32_t* __restrict__ fin_node, const int32_t* __restrict__ fin_world, int64_t n, const int32_t* __restrict__ perm,
+                               int64_t V, int words, double* __restrict__ dist, unsigned long long* __restrict__ dirty, int32_t* __restrict__ inq,
                                int32_t* __restrict__ list, int32_t* __restrict__ counter) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int32_t v = fin_node[i], w = fin_world[i];
-  double* d = dist + (int64_t)v * W + w;
+  const int32_t v = perm[fin_node[i]], w = fin_world[i];
+  double* d = dist + (int64_t)w * V + v;
   *d = (__double_as_longlong(*d) < 0) ? -0.0 : 0.0;
   atomicOr(&dirty[(int64_t)v * words + (w >> 6)], 1ull << (w & 63));
   if (atomicExch(&inq[v], 1) == 0) list[atomicAdd(counter, 1)] = v;
@@ -70,7 +116,7 @@ __global__ void sf_seed_kernel(const int32_t* __restrict__ fin_node, const int32
 
 struct SfArgs {
   const int64_t* row_t; const int32_t* col_t; const double* cost_t;
-  double* dist; int32_t W, words;
+  double* dist; int64_t V; int32_t W, words;   // dist[w * V + v], v in Morton numbering
   unsigned long long* dirty[2];   // [V * words] each
   int32_t* inq[2];                // [V] each: node already on that round's worklist
   int32_t* list[2];               // [V] each
@@ -118,7 +164,7 @@ __global__ void __launch_bounds__(256) sf_classify_kernel(SfArgs a, int round) {
       unsigned long long near = 0, keep = 0;
       for (unsigned long long mm = m; mm; mm &= mm - 1) {
         const int b = __ffsll((long long)mm) - 1;
-        const double dv = fabs(*(volatile double*)(a.dist + (int64_t)v * a.W + k * 64 + b));
+        const double dv = fabs(*(volatile double*)(a.dist + (int64_t)(k * 64 + b) * a.V + v));
         if (dv <= thr) near |= 1ull << b;
         else {
           keep |= 1ull << b;
@@ -170,7 +216,7 @@ __global__ void __launch_bounds__(256) sf_push_kernel(SfArgs a, int round) {
     const int2 vw = a.pairs[qi];
     const int32_t v = vw.x;
     const int w = vw.y, k = w >> 6;
-    const double dv = fabs(*(volatile double*)(a.dist + (int64_t)v * a.W + w));
+    const double dv = fabs(*(volatile double*)(a.dist + (int64_t)w * a.V + v));
     const int64_t e1 = a.row_t[v + 1];
     for (int64_t e0 = a.row_t[v]; e0 < e1; e0 += 32) {
       const int64_t e = e0 + lane;
@@ -179,7 +225,7 @@ __global__ void __launch_bounds__(256) sf_push_kernel(SfArgs a, int round) {
       if (e < e1) {
         u = __ldg(a.col_t + e);
         const double alt = __dadd_rn(__ldg(a.cost_t + e), dv);   // norm2(u, v) + dist[v], pto_graph.rs:293
-        double* du = a.dist + (int64_t)u * a.W + w;
+        double* du = a.dist + (int64_t)w * a.V + u;
         ++n_off;
         if (alt < *du) {
           const unsigned long long bits = (unsigned long long)__double_as_longlong(alt);
@@ -213,23 +259,43 @@ __global__ void sf_sum_kernel(const double* __restrict__ x, int64_t n, double* _
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);   // only the order of magnitude matters (a schedule parameter, not a result)
 }
 
-__global__ void sf_out_kernel(const double* __restrict__ dist /* [V][W] */, int64_t V, int W, double* __restrict__ out /* [W][V] */) {
+__global__ void sf_out_kernel(const double* __restrict__ dist /* [W][V] Morton numbering */, const int32_t* __restrict__ perm, int64_t V, int W,
+                              double* __restrict__ out /* [W][V] caller's numbering */) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V * W) return;
-  const int64_t u = t / W;
-  const int w = (int)(t - u * W);
-  out[(int64_t)w * V + u] = fabs(dist[t]);
+  const int w = (int)(t / V);
+  const int64_t u = t - (int64_t)w * V;
+  out[t] = fabs(dist[(int64_t)w * V + perm[u]]);
 }
 }  // namespace
 
 // All pointers are device pointers.  fin_node / fin_world: the finals of the worlds [wlo, wlo + W) as (node, local world) pairs.
-// out_wv receives rows [0, W) of the [world][node] table.  Uses ctx->scratch[6..8] as work space.
+// out_wv receives rows [0, W) of the [world][node] table.  Uses ctx->scratch[5..10] as work space.
 int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d_col, const double* d_xy, int64_t V, int64_t E,
                           const int32_t* d_node_vid, const uint64_t* d_validities, int32_t mask_words, int32_t wlo, int32_t W,
                           const int32_t* d_fin_node, const int32_t* d_fin_world, int64_t n_fin, double* d_out_wv, int32_t* out_rounds,
                           double* out_offers, cudaStream_t st) {
   if (V > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "sssp: more than 2^31 nodes");
   const int words = (W + 63) / 64;
+  // ---- Morton numbering (scratch[5]): order[pos] = node, perm[node] = pos
+  DevBuf& ob = ctx->scratch[5];
+  CUDA_TRY(ctx, ob.ensure((size_t)V * 16 + 64 + 4 * 16));
+  uint64_t* d_keys = ob.as<uint64_t>();
+  uint32_t* d_order = (uint32_t*)(ob.as<char>() + (((size_t)V * 8 + 15) & ~(size_t)15));
+  int32_t* d_perm = (int32_t*)((char*)d_order + (((size_t)V * 4 + 15) & ~(size_t)15));
+  unsigned long long* d_box = (unsigned long long*)((char*)d_perm + (((size_t)V * 4 + 15) & ~(size_t)15));
+  {
+    const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_box, init, 32, cudaMemcpyHostToDevice, st));
+    sf_bbox_kernel<<<ctx->sm_count * 4, 256, 0, st>>>((const double2*)d_xy, V, d_box);
+    LAUNCH_CHECK(ctx);
+    sf_morton_kernel<<<div_up(V, 256), 256, 0, st>>>((const double2*)d_xy, V, d_box, d_keys, d_order);
+    LAUNCH_CHECK(ctx);
+    int32_t rc0 = radix_sort_pairs(ctx, d_keys, d_order, V, 32);   // (runs on ctx->stream == st; its work space is scratch[8..10])
+    if (rc0) return rc0;
+    sf_perm_kernel<<<div_up(V, 256), 256, 0, st>>>(d_order, V, d_perm);
+    LAUNCH_CHECK(ctx);
+  }
   // ---- transposed adjacency (scratch[6])
   DevBuf& tb = ctx->scratch[6];
   CUDA_TRY(ctx, tb.ensure((size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 4 + 4 * 16 + 64));
@@ -241,14 +307,14 @@ int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d
   int32_t* d_cnt = (int32_t*)take((size_t)V * 4);
   CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)V * 4, st));
   if (E > 0) {
-    sf_count_kernel<<<div_up(E, 256), 256, 0, st>>>(d_col, E, d_cnt);
+    sf_count_kernel<<<div_up(E, 256), 256, 0, st>>>(d_col, d_perm, E, d_cnt);
     LAUNCH_CHECK(ctx);
   }
   int32_t rc = scan_exclusive_i64(ctx, d_cnt, V, d_row_t);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)V * 4, st));
   if (E > 0) {
-    sf_fill_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_row_t, d_cnt, d_col_t, d_cost_t);
+    sf_fill_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, d_perm, V, d_row_t, d_cnt, d_col_t, d_cost_t);
     LAUNCH_CHECK(ctx);
   }
   // ---- value table + frontier state (scratch[7])
@@ -257,7 +323,7 @@ int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d
                           (size_t)std::min<int64_t>(V * (int64_t)W, std::max<int64_t>(4 << 20, 4 * V)) * 8));
   p = sb.as<char>();
   SfArgs a = {};
-  a.row_t = d_row_t; a.col_t = d_col_t; a.cost_t = d_cost_t; a.W = W; a.words = words;
+  a.row_t = d_row_t; a.col_t = d_col_t; a.cost_t = d_cost_t; a.V = V; a.W = W; a.words = words;
   a.dist = (double*)take((size_t)V * W * 8);
   a.dirty[0] = (unsigned long long*)take((size_t)V * words * 8);
   a.dirty[1] = (unsigned long long*)take((size_t)V * words * 8);
@@ -291,10 +357,10 @@ int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d
     // 13.9 full sweeps' worth of pairs in 592 / 400 / 304 / 240 / 224 / 240 rounds; no ordering at all: 19.1
     a.delta = E > 0 && sum > 0.0 && std::isfinite(sum) ? sum / (double)E : 1.0;
   }
-  sf_init_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(d_node_vid, d_validities, mask_words, V, W, wlo, a.dist);
+  sf_init_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(d_node_vid, d_validities, mask_words, d_order, V, W, wlo, a.dist);
   LAUNCH_CHECK(ctx);
   if (n_fin > 0) {
-    sf_seed_kernel<<<div_up(n_fin, 256), 256, 0, st>>>(d_fin_node, d_fin_world, n_fin, W, words, a.dist, a.dirty[0], a.inq[0], a.list[0], a.counter);
+    sf_seed_kernel<<<div_up(n_fin, 256), 256, 0, st>>>(d_fin_node, d_fin_world, n_fin, d_perm, V, words, a.dist, a.dirty[0], a.inq[0], a.list[0], a.counter);
     LAUNCH_CHECK(ctx);
   }
   // ---- rounds: a fixed grid strides over the worklist, whose length lives on the device; the host checks every CHECK rounds
@@ -314,7 +380,7 @@ int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d
     if (counters[round % 3] == 0) break;   // the worklist of the next round is empty: nothing is dirty any more
     if (round > 64 * V + 1024) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp: no convergence");
   }
-  sf_out_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(a.dist, V, W, d_out_wv);
+  sf_out_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(a.dist, d_perm, V, W, d_out_wv);
   LAUNCH_CHECK(ctx);
   if (out_rounds) *out_rounds = round;
   if (out_offers) {
