@@ -284,6 +284,18 @@ int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy, const in
                                      const uint8_t* compat_rows, int32_t n_iterations, uint64_t sampler_seed,
                                      int32_t* out_commits, int32_t* out_waves);
 
+/* PTOPolicyRefiner::refine_solution(RefinmentStrategy::PartialShortCut(n_iterations)) (pto_policy_refiner.rs:85-133), the last step
+ * of every PTO run in the reference's main.rs (:442 PartialShortCut(1500)), on a policy of the last porrt_belief_vi of this ctx
+ * given as porrt_extract_policy returned it (pol_node / pol_belief / pol_parent in creation order): Policy::decompose
+ * (common.rs:85-129), build_path_piece + partial_shortcut per piece (all pieces in one device batch), recompose (:324-393) and
+ * compute_expected_costs_to_goals (common.rs:131-153).  Output = the refined policy, nodes in recompose's creation order:
+ * out_xy[2k..] refined state, out_node / out_belief (original_node_id = node * B + belief), out_parent (-1 = root or a piece
+ * recompose leaves unconnected, see the source), out_is_leaf.  cap < *out_n: PORRT_ERR_CAPACITY.  out_commits: accepted shortcuts. */
+int32_t porrt_refine_policy_shortcut(porrt_ctx* ctx, const int32_t* pol_node, const int32_t* pol_belief, const int32_t* pol_parent,
+                                     int64_t n_pol, int32_t n_iterations, uint64_t sampler_seed, double* out_xy, int32_t* out_node,
+                                     int32_t* out_belief, int32_t* out_parent, uint8_t* out_is_leaf, int64_t cap, int64_t* out_n,
+                                     double* out_expected_cost, int64_t* out_commits);
+
 /* reachable_belief_states (map_io.rs:515-546 / map_shelves_io.rs:490-520): host-side closure over the uploaded map's
  * zones; out[cap * n_worlds]; *out_B = count (PORRT_ERR_CAPACITY if > cap). */
 int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B);

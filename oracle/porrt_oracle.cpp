@@ -3,6 +3,7 @@
 #include "porrt_oracle.hpp"
 
 #include <algorithm>
+#include <deque>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -971,6 +972,113 @@ int64_t refiner_partial_shortcut(const GridMap& m, std::vector<State>& states, c
     }
   }
   return commits;
+}
+
+// Policy::decompose (common.rs:85-129)
+void policy_decompose(const Policy& p, std::vector<std::pair<size_t, std::vector<size_t>>>& pieces, std::vector<std::vector<size_t>>& skeleton) {
+  pieces.clear(); skeleton.clear();
+  size_t n_pieces = 0;
+  std::deque<size_t> fifo;
+  fifo.push_back(0);                                                 // :91
+  while (!fifo.empty()) {
+    const size_t id = fifo.front(); fifo.pop_front();                // :94
+    std::vector<size_t> ids, successors;
+    size_t current_id = id;
+    for (;;) {
+      ids.push_back(current_id);                                     // :103 (the assert_eq on the belief states, :101, is a debug check)
+      const auto& ch = p.nodes[current_id].children;
+      if (ch.empty()) break;                                         // :106 final node
+      if (ch.size() == 1) { current_id = ch[0]; continue; }          // :107 simple forward
+      for (size_t child_id : ch) {                                   // :108-114 branching
+        fifo.push_back(child_id);
+        n_pieces += 1;
+        successors.push_back(n_pieces);
+      }
+      break;
+    }
+    pieces.push_back({p.nodes[id].belief_id, ids});                  // :119-124
+    skeleton.push_back(successors);
+  }
+}
+
+// Policy::compute_expected_costs_to_goals_from (common.rs:135-153)
+static double policy_expected_from(const Policy& p, const BeliefGraph& g, double prob, size_t id) {
+  double expected_future_costs = 0.0;
+  const PolicyNode& node = p.nodes[id];
+  for (size_t child_id : node.children) {
+    const PolicyNode& child = p.nodes[child_id];
+    const double q = transition_probability(g.reachable_belief_states[node.belief_id], g.reachable_belief_states[child.belief_id]);
+    const double cost = norm2(node.state, child.state);
+    expected_future_costs += prob * q * cost + policy_expected_from(p, g, prob * q, child_id);   // :149
+  }
+  return expected_future_costs;
+}
+double policy_expected_costs(const Policy& p, const BeliefGraph& g) { return policy_expected_from(p, g, 1.0, 0); }
+
+bool refiner_refine_shortcut(const GridMap& m, const Policy& policy, const BeliefGraph& g, size_t n_iterations, Policy& out) {
+  std::vector<std::vector<bool>> compat(g.reachable_belief_states.size(), std::vector<bool>(m.world_validities.size(), false));   // refiner :79, common.rs:266-276
+  for (size_t b = 0; b < compat.size(); ++b)
+    for (size_t v = 0; v < m.world_validities.size(); ++v) compat[b][v] = is_compatible(g.reachable_belief_states[b], m.world_validities[v]);
+  std::vector<std::pair<size_t, std::vector<size_t>>> path_pieces;
+  std::vector<std::vector<size_t>> skeleton;
+  policy_decompose(policy, path_pieces, skeleton);                                                                     // :94
+  struct TreeNode { State state; int64_t parent; size_t belief_graph_id; };
+  struct Tree { std::vector<TreeNode> nodes; size_t belief_state_id = 0, leaf = 0; };
+  std::vector<Tree> trees;
+  for (const auto& piece : path_pieces) {                                                                               // :97
+    const std::vector<size_t>& path = piece.second;
+    Tree tree;                                                                                                         // build_path_piece :136-156
+    const size_t root_bg = policy.nodes[path.front()].original_node_id;
+    tree.nodes.push_back({g.nodes[root_bg].state, -1, root_bg});
+    for (size_t k = 0; k + 1 < path.size(); ++k) {
+      const size_t next_bg = policy.nodes[path[k + 1]].original_node_id;
+      tree.nodes.push_back({g.nodes[next_bg].state, (int64_t)tree.nodes.size() - 1, next_bg});
+    }
+    tree.belief_state_id = g.nodes[root_bg].belief_id;
+    tree.leaf = tree.nodes.size() - 1;
+    std::vector<State> states;                                                                                         // partial_shortcut :158-206
+    for (const TreeNode& n : tree.nodes) states.push_back(n.state);
+    if (refiner_partial_shortcut(m, states, compat[tree.belief_state_id], n_iterations) < 0) return false;
+    for (size_t k = 0; k < states.size(); ++k) tree.nodes[k].state = states[k];
+    trees.push_back(tree);
+  }
+  // recompose :324-393
+  out = Policy();
+  const int64_t NONE = -1;
+  std::vector<std::pair<int64_t, int64_t>> pieces_start_end(skeleton.size(), {NONE, NONE});
+  auto add_node = [&](const State& s, size_t belief_graph_id) {
+    out.nodes.push_back({s, g.nodes[belief_graph_id].belief_id, -1, {}, belief_graph_id});
+    return (int64_t)out.nodes.size() - 1;
+  };
+  auto add_edge = [&](int64_t parent, int64_t child) { out.nodes[(size_t)parent].children.push_back((size_t)child); out.nodes[(size_t)child].parent = parent; };
+  for (size_t i = 0; i < trees.size(); ++i) {
+    const Tree& tree = trees[i];
+    std::vector<const TreeNode*> node_path;                                                                            // :337-345
+    const TreeNode* node = &tree.nodes[tree.leaf];
+    node_path.push_back(node);
+    while (node->parent >= 0) { node = &tree.nodes[(size_t)node->parent]; node_path.push_back(node); }
+    std::reverse(node_path.begin(), node_path.end());
+    int64_t previous_id = NONE;
+    for (size_t j = 0; j < node_path.size(); ++j) {                                                                    // :348-367
+      const bool is_start = j == 0, is_end = j == node_path.size() - 1;
+      const int64_t id = add_node(node_path[j]->state, node_path[j]->belief_graph_id);
+      if (is_start) pieces_start_end[i].first = id;                // (a one-node piece is a start only: its end stays None)
+      else if (is_end) { add_edge(previous_id, id); pieces_start_end[i].second = id; }
+      else add_edge(previous_id, id);
+      previous_id = id;
+    }
+  }
+  for (size_t i = 0; i < skeleton.size(); ++i) {                                                                       // :371-381
+    const int64_t from_end = pieces_start_end[i].second;
+    for (size_t next_piece : skeleton[i]) {
+      const int64_t to_start = pieces_start_end[next_piece].first;
+      if (from_end != NONE && to_start != NONE) add_edge(from_end, to_start);
+    }
+  }
+  for (size_t i = 0; i < out.nodes.size(); ++i)                                                                        // :384-389
+    if (out.nodes[i].children.empty()) out.leafs.push_back(i);
+  out.expected_costs = policy_expected_costs(out, g);                                                                  // :391
+  return true;
 }
 
 // ============================================================== map_shelves_tamp_prm.rs

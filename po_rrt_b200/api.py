@@ -521,6 +521,23 @@ def plan_belief_space(fns, row_ptr, col, edge_vid, xy, node_vid, start_belief, f
     return plan
 
 
+def refine_policy_shortcut(ctx, plan, n_iterations, sampler_seed=0):
+    """PTOPolicyRefiner::refine_solution(PartialShortCut(n)) on a BeliefPlan of the ctx's last plan_belief_space
+    -> dict(xy, node, belief, parent, is_leaf, expected_cost, commits)"""
+    n_pol = len(plan.policy_node)
+    cap = n_pol
+    xy = np.empty((cap, 2))
+    node, belief, parent = (np.empty(cap, np.int32) for _ in range(3))
+    leaf = np.empty(cap, np.uint8)
+    n, cost, commits = C.c_int64(), C.c_double(), C.c_int64()
+    pn, pb, pp = (np.ascontiguousarray(a, np.int32) for a in (plan.policy_node, plan.policy_belief, plan.policy_parent))
+    ctx.check(ctx.lib.porrt_refine_policy_shortcut(ctx.h, _p(pn), _p(pb), _p(pp), n_pol, int(n_iterations), int(sampler_seed), _p(xy), _p(node),
+                                                   _p(belief), _p(parent), _p(leaf), cap, C.byref(n), C.byref(cost), C.byref(commits)))
+    k = n.value
+    return {"xy": xy[:k], "node": node[:k], "belief": belief[:k], "parent": parent[:k], "is_leaf": leaf[:k], "expected_cost": cost.value,
+            "commits": commits.value}
+
+
 class BeliefGraph:
     """src/belief_graph.rs BeliefGraph as arrays: belief node k = (state xy[k], belief_id[k], node_type[k]); children adjacency
     as CSR in add_edge order.  conditional_dijkstra / extract_policy are the reference's free functions (:89-267)."""

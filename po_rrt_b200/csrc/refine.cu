@@ -265,3 +265,118 @@ PORRT_API int32_t porrt_partial_shortcut(porrt_ctx* ctx, double* states_xy, int3
   const int32_t ptr[2] = {0, n_states};
   return porrt_partial_shortcut_batch(ctx, states_xy, ptr, 1, compat_row, n_iterations, sampler_seed, out_commits, out_waves);
 }
+
+// ================================================================================================ refine_solution(PartialShortCut(n))
+// PTOPolicyRefiner::refine_solution with RefinmentStrategy::PartialShortCut (pto_policy_refiner.rs:85-133; what every PTO run of
+// the reference's main.rs ends with, e.g. :442 PartialShortCut(1500)) on the policy porrt_extract_policy produced from the last
+// porrt_belief_vi of this ctx:
+//   Policy::decompose (common.rs:85-129)  ->  build_path_piece (:135-156) + partial_shortcut (:158-206) per piece, all pieces in one
+//   batch on the device (porrt_partial_shortcut_batch)  ->  recompose (:324-393) incl. compute_expected_costs_to_goals (common.rs:131-153).
+// Everything around the batch is sequential host logic, written here over flat arrays: a policy is (node, belief, parent) per policy
+// node in creation order, children of a node = its later nodes in creation order (Policy::add_edge is called right after add_node).
+// A piece of ONE node is a start but not an end in recompose (:356-361): its successors are never connected -- kept as is.
+PORRT_API int32_t porrt_refine_policy_shortcut(porrt_ctx* ctx, const int32_t* pol_node, const int32_t* pol_belief, const int32_t* pol_parent,
+                                               int64_t n_pol, int32_t n_iterations, uint64_t sampler_seed, double* out_xy, int32_t* out_node,
+                                               int32_t* out_belief, int32_t* out_parent, uint8_t* out_is_leaf, int64_t cap, int64_t* out_n,
+                                               double* out_expected_cost, int64_t* out_commits) {
+  CTX_CHECK(ctx);
+  auto& R = ctx->bel;
+  if (R.V <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "refine_policy_shortcut: run porrt_belief_vi / porrt_extract_policy first");
+  if (n_pol <= 0 || !pol_node || !pol_belief || !pol_parent || n_iterations < 0 || !out_n)
+    return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "refine_policy_shortcut: bad arguments");
+  const int B = R.B, nw = R.n_worlds, nv = R.n_validities;
+  for (int64_t k = 0; k < n_pol; ++k)
+    if (pol_node[k] < 0 || pol_node[k] >= R.V || pol_belief[k] < 0 || pol_belief[k] >= B || pol_parent[k] >= k || (k > 0 && pol_parent[k] < 0) || (k == 0 && pol_parent[k] != -1))
+      return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "refine_policy_shortcut: not a policy in creation order");
+  // children in creation order
+  std::vector<int64_t> ch_ptr((size_t)n_pol + 1, 0);
+  for (int64_t k = 1; k < n_pol; ++k) ++ch_ptr[(size_t)pol_parent[k] + 1];
+  for (int64_t k = 0; k < n_pol; ++k) ch_ptr[(size_t)k + 1] += ch_ptr[(size_t)k];
+  std::vector<int64_t> ch((size_t)std::max<int64_t>(n_pol - 1, 0)), fill(ch_ptr.begin(), ch_ptr.end() - 1);
+  for (int64_t k = 1; k < n_pol; ++k) ch[(size_t)fill[(size_t)pol_parent[k]]++] = k;
+  // ---- decompose: FIFO over piece starts; a piece runs until a leaf or a branching node
+  std::vector<int32_t> piece_ptr(1, 0);
+  std::vector<int64_t> piece_nodes;                   // policy node ids, piece after piece
+  std::vector<std::vector<int32_t>> successors;       // skeleton
+  {
+    std::vector<int64_t> fifo(1, 0);
+    int32_t n_pieces = 0;
+    for (size_t head = 0; head < fifo.size(); ++head) {
+      int64_t cur = fifo[head];
+      std::vector<int32_t> succ;
+      for (;;) {
+        piece_nodes.push_back(cur);
+        const int64_t nc = ch_ptr[(size_t)cur + 1] - ch_ptr[(size_t)cur];
+        if (nc == 0) break;
+        if (nc == 1) { cur = ch[(size_t)ch_ptr[(size_t)cur]]; continue; }
+        for (int64_t e = ch_ptr[(size_t)cur]; e < ch_ptr[(size_t)cur + 1]; ++e) { fifo.push_back(ch[(size_t)e]); succ.push_back(++n_pieces); }
+        break;
+      }
+      piece_ptr.push_back((int32_t)piece_nodes.size());
+      successors.push_back(succ);
+    }
+  }
+  const int32_t n_pieces = (int32_t)successors.size();
+  const int64_t n_out = (int64_t)piece_nodes.size();   // every policy node ends up in exactly one piece
+  *out_n = n_out;
+  if (n_out > cap || !out_xy || !out_node || !out_belief || !out_parent || !out_is_leaf)
+    return porrt_fail(ctx, PORRT_ERR_CAPACITY, "refine_policy_shortcut: cap too small");
+  // ---- build_path_piece: the pieces' states back to back; the piece's belief is the one of its first node
+  std::vector<uint8_t> rows((size_t)n_pieces * nv);
+  for (int64_t k = 0; k < n_out; ++k) {
+    const int64_t pn = piece_nodes[(size_t)k];
+    out_xy[2 * k] = R.xy[2 * (size_t)pol_node[pn]]; out_xy[2 * k + 1] = R.xy[2 * (size_t)pol_node[pn] + 1];
+    out_node[k] = pol_node[pn]; out_belief[k] = pol_belief[pn];
+  }
+  for (int32_t p = 0; p < n_pieces; ++p)
+    memcpy(&rows[(size_t)p * nv], &R.compat[(size_t)pol_belief[piece_nodes[(size_t)piece_ptr[p]]] * nv], (size_t)nv);
+  // ---- partial_shortcut on all pieces (device batch, sequential semantics)
+  std::vector<int32_t> commits((size_t)n_pieces, 0);
+  int32_t rc = porrt_partial_shortcut_batch(ctx, out_xy, piece_ptr.data(), n_pieces, rows.data(), n_iterations, sampler_seed, commits.data(), nullptr);
+  if (rc) return rc;
+  if (out_commits) { *out_commits = 0; for (int32_t c : commits) *out_commits += c; }
+  // ---- recompose: chains inside the pieces, then end of piece i -> start of its successors (an end exists only for >= 2 nodes)
+  for (int32_t p = 0; p < n_pieces; ++p)
+    for (int32_t k = piece_ptr[p]; k < piece_ptr[p + 1]; ++k) out_parent[k] = k == piece_ptr[p] ? -1 : k - 1;
+  for (int32_t p = 0; p < n_pieces; ++p) {
+    if (piece_ptr[p + 1] - piece_ptr[p] < 2) continue;
+    for (int32_t q : successors[(size_t)p]) out_parent[piece_ptr[q]] = piece_ptr[p + 1] - 1;
+  }
+  // children of the recomposed policy in add_edge order: the chain edge, or -- at a piece's end -- the successors in skeleton order
+  // (successor pieces come later in the arrays, so increasing index = add_edge order); leaves = nodes without children
+  std::vector<int32_t> n_children((size_t)n_out, 0);
+  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) ++n_children[(size_t)out_parent[k]];
+  for (int64_t k = 0; k < n_out; ++k) out_is_leaf[k] = n_children[(size_t)k] == 0;
+  // ---- compute_expected_costs_to_goals: probabilities top down, costs bottom up; children are visited in increasing index
+  auto transition_probability = [&](int pb, int cb) {
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s = s + (R.beliefs[(size_t)cb * nw + i] > 0.0 ? R.beliefs[(size_t)pb * nw + i] : 0.0);
+    return s;
+  };
+  std::vector<double> prob((size_t)n_out, 0.0), pq((size_t)n_out, 0.0), edge_term((size_t)n_out, 0.0), below((size_t)n_out, 0.0);
+  prob[0] = 1.0;
+  for (int64_t k = 1; k < n_out; ++k) {
+    const int32_t par = out_parent[k];
+    if (par < 0) continue;   // a piece that recompose left unconnected: not under the root
+    const double q = transition_probability(out_belief[par], out_belief[k]);
+    const double dx = out_xy[2 * k] - out_xy[2 * (size_t)par], dy = out_xy[2 * k + 1] - out_xy[2 * (size_t)par + 1];
+    const double cost = std::sqrt(dx * dx + dy * dy);   // norm2(parent, child), common.rs:203-213
+    pq[(size_t)k] = prob[(size_t)par] * q;              // p * q
+    prob[(size_t)k] = pq[(size_t)k];
+    edge_term[(size_t)k] = pq[(size_t)k] * cost;        // (p * q) * cost
+  }
+  // expected_future_costs(parent) += p * q * cost + expected_future_costs(child), children in order (common.rs:149): a child's own sum
+  // is complete before its parent folds it in -- fold the children of each node in increasing index, nodes in decreasing index
+  std::vector<int64_t> oc_ptr((size_t)n_out + 1, 0);
+  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) ++oc_ptr[(size_t)out_parent[k] + 1];
+  for (int64_t k = 0; k < n_out; ++k) oc_ptr[(size_t)k + 1] += oc_ptr[(size_t)k];
+  std::vector<int64_t> oc((size_t)oc_ptr[(size_t)n_out]), ofill(oc_ptr.begin(), oc_ptr.end() - 1);
+  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) oc[(size_t)ofill[(size_t)out_parent[k]]++] = k;
+  for (int64_t k = n_out - 1; k >= 0; --k) {
+    double acc = 0.0;
+    for (int64_t e = oc_ptr[(size_t)k]; e < oc_ptr[(size_t)k + 1]; ++e) { const int64_t c = oc[(size_t)e]; acc += edge_term[(size_t)c] + below[(size_t)c]; }
+    below[(size_t)k] = acc;
+  }
+  if (out_expected_cost) *out_expected_cost = below[0];
+  return PORRT_OK;
+}

@@ -1362,3 +1362,34 @@ def test_qmdp_on_resident_prm(ctx):
         want = og.dijkstra(finals[w], world=w) if finals[w] else np.full(V, np.inf)
         np.testing.assert_array_equal(got[w], want, err_msg="world %d" % w)
     assert np.isfinite(got).any() and np.isinf(got[5]).all()
+
+
+@pytest.mark.parametrize("kind,Z,n_min", [("shelf", 4, 1500), ("door", 2, 2500)])
+def test_refine_solution_partial_shortcut(ctx, kind, Z, n_min):
+    """PTOPolicyRefiner::refine_solution(RefinmentStrategy::PartialShortCut(n)) (pto_policy_refiner.rs:85-133; main.rs:442 runs it with
+    n = 1500 after every PTO plan): Policy::decompose, build_path_piece + partial_shortcut per piece, recompose and the policy's
+    expected cost -- states bit for bit, same tree, same leaves, same expected cost as the oracle's restatement."""
+    if kind == "shelf":
+        occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+        zp = omap.zone_positions()
+        goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
+        pto = _grow_pto(omap, (0.0, -0.9), goals, 0.1, 2.0, n_min)
+        b0 = [1.0 / Z] * Z
+    else:
+        occ, zones = util.planning_door_map(200)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+        pto = _grow_pto(omap, (-0.8, -0.8), [((0.8, 0.8), [1, 1, 1, 1])], 0.05, 5.0, n_min)
+        b0 = [0.1, 0.1, 0.1, 0.7]
+    plan, _, _ = _belief_compare(ctx, omap, pmap, pto, b0)
+    B = len(plan.beliefs)
+    for n_it in (0, 300, 1500):
+        want = pto.refine_policy_shortcut(n_it)
+        got = P.refine_policy_shortcut(ctx, plan, n_it)
+        assert got["xy"].tobytes() == want.xy.tobytes(), n_it                       # refined states, bit for bit
+        np.testing.assert_array_equal(got["node"].astype(np.int64) * B + got["belief"], want.original)
+        np.testing.assert_array_equal(got["belief"], want.belief_id)
+        np.testing.assert_array_equal(got["parent"], want.parent)
+        np.testing.assert_array_equal(np.nonzero(got["is_leaf"])[0], want.leafs)
+        assert got["expected_cost"] == want.expected_costs, n_it
+    assert got["commits"] > 0 and got["expected_cost"] <= plan.expected_cost + 1e-9
