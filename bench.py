@@ -519,6 +519,14 @@ def belief_measurement(ctx, Z=8, n_min=5000, visibility=0.5, max_step=0.1, searc
         out["cpu_oracle_ms[build_belief_graph,conditional_dijkstra,extract_policy]"] = [round(1e3 * t_build, 1), round(1e3 * t_dp, 1), round(1e3 * t_pol, 2)]
         out["bit_exact"] = bool(np.array_equal(plan.dist.reshape(-1), want) and
                                 np.array_equal(plan.policy_node.astype(np.int64) * B + plan.policy_belief, opol.original))
+        # the run's last step in the reference (main.rs:442): refine_solution(PartialShortCut(1500))
+        P.refine_policy_shortcut(ctx, plan, 1500)
+        t0 = time.perf_counter(); ref = P.refine_policy_shortcut(ctx, plan, 1500); t_ref = time.perf_counter() - t0
+        t0 = time.perf_counter(); oref = pto.refine_policy_shortcut(1500); t_oref = time.perf_counter() - t0
+        out["refine_shortcut_1500"] = {"gpu_ms": 1e3 * t_ref, "cpu_oracle_ms_1thread": 1e3 * t_oref, "pieces_nodes": int(len(ref["node"])),
+                                       "commits": int(ref["commits"]), "expected_cost_before": float(plan.expected_cost),
+                                       "expected_cost_after": float(ref["expected_cost"]),
+                                       "bit_exact": bool(ref["xy"].tobytes() == oref.xy.tobytes() and ref["expected_cost"] == oref.expected_costs)}
     else:
         keep = plan.dist.copy()
         ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 1)
