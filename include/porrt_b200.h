@@ -271,15 +271,16 @@ int32_t porrt_transition_valid(porrt_ctx* ctx, const double* from_xy, const doub
                                const uint8_t* compat_row, uint8_t* out_valid, int32_t* out_status);
 /* PTOPolicyRefiner::partial_shortcut (pto_policy_refiner.rs:158-206) on one path piece: states_xy[2 * n_states] is updated in
  * place.  The trial sequence is the one a DiscreteSampler seeded with sampler_seed draws (the reference uses
- * DiscreteSampler::new(), seed 0); trials are evaluated in speculative waves on the device and replayed in order, so states
- * and *out_commits equal the sequential result.  *out_waves (nullable) = device round trips used.
- * PORRT_ERR_PANIC if a transition check hits a reference panic. */
+ * DiscreteSampler::new(), seed 0).  The whole trial loop runs on the device (one CTA per piece, the path in shared memory, the
+ * transitions of a trial checked by its warps, commit decided in the reference's `&&` order), so states and *out_commits equal the
+ * sequential result and there is ONE device round trip per call (*out_waves, nullable).  At most 1024 states per piece.
+ * PORRT_ERR_PANIC if a transition check hits a reference panic (the states are then left untouched). */
 int32_t porrt_partial_shortcut(porrt_ctx* ctx, double* states_xy, int32_t n_states, const uint8_t* compat_row,
                                int32_t n_iterations, uint64_t sampler_seed, int32_t* out_commits, int32_t* out_waves);
 /* The same for all path pieces of a policy at once (refine_solution's loop, pto_policy_refiner.rs:102-115): piece p owns the
  * states piece_ptr[p] .. piece_ptr[p+1]-1 of states_xy and the compatibility row compat_rows[p * n_validities ..] of its belief
- * state; every piece draws from its own fresh sampler (same seed), exactly like the reference.  The waves of all pieces share
- * one device batch, so the number of device round trips is that of the slowest piece.  out_commits[n_pieces] (nullable). */
+ * state; every piece draws from its own fresh sampler (same seed), exactly like the reference.  The pieces run side by side on
+ * different SMs.  out_commits[n_pieces] (nullable). */
 int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy, const int32_t* piece_ptr, int32_t n_pieces,
                                      const uint8_t* compat_rows, int32_t n_iterations, uint64_t sampler_seed,
                                      int32_t* out_commits, int32_t* out_waves);

@@ -19,65 +19,6 @@
 #include "common.cuh"
 #include "map_dev.cuh"
 
-// Warp-cooperative walk of one edge; every lane returns the same result.
-template <int KIND>
-__device__ __forceinline__ int32_t walk_warp(const MapDev& m, const EdgeSetup& s, int lane) {
-  if (s.flags & 1) return PORRT_PANIC_OOB;  // the first pixel read already panics
-  Walker w;
-  w.load(s);
-  bool slow = (s.flags & 2) != 0;           // end pixel outside: order of events matters -> sequential
-  int32_t result = R_FREE;
-  if (!slow) {
-    const int32_t n_px = w.dxo + 1;
-    int32_t zone_seen = -1;
-    uint32_t lowest = 255;
-    bool done = false;
-    for (int32_t k0 = 0; k0 < n_px && !done; k0 += 128) {
-      uint32_t code[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        int32_t k = k0 + c * 32 + lane;
-        code[c] = 255;
-        if (k < n_px) {
-          int32_t i, j;
-          w.pixel(k, i, j);
-          code[c] = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (done) break;
-        if (KIND == PORRT_DOMAIN_SHELF) {
-          lowest = min(lowest, __reduce_min_sync(0xffffffffu, code[c]));
-          if (lowest == 0) done = true;
-        } else {
-          uint32_t ob = __ballot_sync(0xffffffffu, code[c] == 0);
-          uint32_t before = ob ? ((1u << (__ffs(ob) - 1)) - 1u) : 0xffffffffu;  // lanes ahead of the first obstacle
-          bool is_gray = code[c] != 0 && code[c] != 255 && ((before >> lane) & 1u);
-          uint32_t gray = __ballot_sync(0xffffffffu, is_gray);
-          if (gray) {
-            uint32_t zmin = __reduce_min_sync(0xffffffffu, is_gray ? code[c] : 255u);
-            uint32_t zmax = __reduce_max_sync(0xffffffffu, is_gray ? code[c] : 0u);
-            if (zmin != zmax || zmax == 254u || (zone_seen >= 0 && zone_seen != (int32_t)zmin - 1)) { slow = true; done = true; }
-            zone_seen = (int32_t)zmin - 1;
-          }
-          if (ob && !slow) { result = R_BLOCKED; done = true; }
-        }
-      }
-    }
-    if (!slow) {
-      if (KIND == PORRT_DOMAIN_SHELF) result = lowest == 255 ? R_FREE : (lowest >= 127 ? R_LOW : R_BLOCKED);
-      else if (result != R_BLOCKED) result = zone_seen >= 0 ? zone_seen : R_FREE;
-    }
-  }
-  if (slow) {
-    int32_t r = 0;
-    if (lane == 0) r = walk_sequential<KIND>(m, w);
-    result = __shfl_sync(0xffffffffu, r, 0);
-  }
-  return result;
-}
-
 // ------------------------------------------------------------------------------------------------ kernels
 #define EDGE_BLOCK 256
 
@@ -374,17 +315,8 @@ __global__ void __launch_bounds__(EDGE_BLOCK, V2_MINB) edge_validity_v2_kernel(M
 __global__ void state_validity_kernel(MapDev m, const double2* __restrict__ xy, int64_t n, int32_t* __restrict__ out_vid) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  double2 p = xy[t];
-  uint32_t i, j;
-  to_pixel(m, p.x, p.y, i, j);
-  int32_t vid;
-  if (i >= (uint32_t)m.H || j >= (uint32_t)m.W) vid = PORRT_PANIC_OOB;
-  else {
-    uint32_t c = __ldg(m.grid + tile_addr((int)i, (int)j, m.tiles_x));
-    if (m.kind == PORRT_DOMAIN_SHELF) vid = c == 255 ? m.free_vid : PORRT_INVALID;
-    else vid = c == 255 ? m.free_vid : (c == 0 ? PORRT_INVALID : (c == 254 ? PORRT_PANIC_ZONE_UNWRAP : (int32_t)c - 1));
-  }
-  out_vid[t] = vid;
+  const double2 p = xy[t];
+  out_vid[t] = state_validity_of(m, p.x, p.y);
 }
 
 // observe_impl's geometric test (map_io.rs:285-288 / map_shelves_io.rs:259-265); one warp per state, zones in turn

@@ -106,6 +106,65 @@ __device__ __noinline__ int32_t walk_sequential(const MapDev& m, const Walker& w
   return prev >= 0 ? prev : R_FREE;
 }
 
+// Warp-cooperative walk of one edge; every lane returns the same result.
+template <int KIND>
+__device__ __forceinline__ int32_t walk_warp(const MapDev& m, const EdgeSetup& s, int lane) {
+  if (s.flags & 1) return PORRT_PANIC_OOB;  // the first pixel read already panics
+  Walker w;
+  w.load(s);
+  bool slow = (s.flags & 2) != 0;           // end pixel outside: order of events matters -> sequential
+  int32_t result = R_FREE;
+  if (!slow) {
+    const int32_t n_px = w.dxo + 1;
+    int32_t zone_seen = -1;
+    uint32_t lowest = 255;
+    bool done = false;
+    for (int32_t k0 = 0; k0 < n_px && !done; k0 += 128) {
+      uint32_t code[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int32_t k = k0 + c * 32 + lane;
+        code[c] = 255;
+        if (k < n_px) {
+          int32_t i, j;
+          w.pixel(k, i, j);
+          code[c] = __ldg(m.grid + tile_addr(i, j, m.tiles_x));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (done) break;
+        if (KIND == PORRT_DOMAIN_SHELF) {
+          lowest = min(lowest, __reduce_min_sync(0xffffffffu, code[c]));
+          if (lowest == 0) done = true;
+        } else {
+          uint32_t ob = __ballot_sync(0xffffffffu, code[c] == 0);
+          uint32_t before = ob ? ((1u << (__ffs(ob) - 1)) - 1u) : 0xffffffffu;  // lanes ahead of the first obstacle
+          bool is_gray = code[c] != 0 && code[c] != 255 && ((before >> lane) & 1u);
+          uint32_t gray = __ballot_sync(0xffffffffu, is_gray);
+          if (gray) {
+            uint32_t zmin = __reduce_min_sync(0xffffffffu, is_gray ? code[c] : 255u);
+            uint32_t zmax = __reduce_max_sync(0xffffffffu, is_gray ? code[c] : 0u);
+            if (zmin != zmax || zmax == 254u || (zone_seen >= 0 && zone_seen != (int32_t)zmin - 1)) { slow = true; done = true; }
+            zone_seen = (int32_t)zmin - 1;
+          }
+          if (ob && !slow) { result = R_BLOCKED; done = true; }
+        }
+      }
+    }
+    if (!slow) {
+      if (KIND == PORRT_DOMAIN_SHELF) result = lowest == 255 ? R_FREE : (lowest >= 127 ? R_LOW : R_BLOCKED);
+      else if (result != R_BLOCKED) result = zone_seen >= 0 ? zone_seen : R_FREE;
+    }
+  }
+  if (slow) {
+    int32_t r = 0;
+    if (lane == 0) r = walk_sequential<KIND>(m, w);
+    result = __shfl_sync(0xffffffffu, r, 0);
+  }
+  return result;
+}
+
 __device__ __forceinline__ int32_t walk_to_validity(const MapDev& m, int32_t r) {
   if (r >= 0) return r;                    // Zone(z) -> Some(z)
   if (r == R_FREE) return m.free_vid;      // Free -> Some(world_validities.len() - 1)
@@ -113,6 +172,16 @@ __device__ __forceinline__ int32_t walk_to_validity(const MapDev& m, int32_t r) 
   return r;                                // blocked (-1) or panic code
 }
 
+
+// is_state_valid + state_validity (map_io.rs:165-174,487-493 / map_shelves_io.rs:158-163,464-469) of one state
+__device__ __forceinline__ int32_t state_validity_of(const MapDev& m, double x, double y) {
+  uint32_t i, j;
+  to_pixel(m, x, y, i, j);
+  if (i >= (uint32_t)m.H || j >= (uint32_t)m.W) return PORRT_PANIC_OOB;
+  const uint32_t c = __ldg(m.grid + tile_addr((int)i, (int)j, m.tiles_x));
+  if (m.kind == PORRT_DOMAIN_SHELF) return c == 255 ? m.free_vid : PORRT_INVALID;
+  return c == 255 ? m.free_vid : (c == 0 ? PORRT_INVALID : (c == 254 ? PORRT_PANIC_ZONE_UNWRAP : (int32_t)c - 1));
+}
 
 // One edge's outputs: the validity id as int32 or as a signed byte (ids are < 128: n_validities <= 65; the negative codes
 // are the same), and optionally its per-world bitvec = world_validities[id] (map_io.rs:548-550), all zero when invalid.

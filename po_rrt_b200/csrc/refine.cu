@@ -2,16 +2,16 @@
 //
 //  * porrt_transition_valid : PTOPolicyRefiner::is_transition_valid (reference src/pto_policy_refiner.rs:395-423), batched:
 //                             state validity of both ends + transition validity + belief/validity compatibility.
-//  * porrt_partial_shortcut : PTOPolicyRefiner::partial_shortcut (:158-206) on one path piece.  The reference runs
-//                             n_iterations SEQUENTIAL trials, each a handful of short edge checks -- a per-trial GPU round trip
-//                             could never beat that (SURVEY 8(b) granularity caveat).  But the random choices of a trial
-//                             (joint, interval) come from a fresh DiscreteSampler::new() and depend only on the piece length,
-//                             so the whole trial sequence is known up front.  Trials are therefore evaluated in speculative
-//                             WAVES: the next WAVE trials are built on a speculative copy of the path (each trial assumed to
-//                             end like most recent ones did), their transitions are checked in one device batch, and the
-//                             wave is replayed in order on the real path; a trial's results are used iff the states it read
-//                             are bit-identical to the real ones, the first trial that fails this starts the next wave.
-//                             The result -- states and commit count -- is exactly the sequential one.
+//  * porrt_partial_shortcut : PTOPolicyRefiner::partial_shortcut (:158-206) on path pieces.  The reference runs n_iterations
+//                             SEQUENTIAL trials per piece, each a handful of short edge checks whose outcome decides what the
+//                             next trial sees -- a device round trip per trial (or per speculative wave of trials: round 1,
+//                             157-250 round trips, slower than one CPU core on small maps) cannot win.  So the whole loop runs
+//                             ON the device: one CTA per piece keeps the path in shared memory and works through the trial list
+//                             (joint, interval: drawn on the host from a fresh DiscreteSampler, they depend on the piece length
+//                             only); per trial its warps check the transitions of the shortcut in parallel (state validity of
+//                             both ends, warp-cooperative edge walk, belief/validity compatibility), then the CTA applies the
+//                             reference's short-circuit `&&` chain in order and commits or not.  Pieces run side by side on
+//                             different SMs; there is no host round trip inside a call.
 // The sampler is rand_pcg 0.3 Pcg64 (Lcg128Xsl64) seeded by rand_core 0.6 seed_from_u64 and rand 0.8's
 // UniformInt<usize>::sample_single, restated from their published algorithms (the crates are not vendored in the reference).
 #include <algorithm>
@@ -20,6 +20,7 @@
 
 #include "pcg64.h"
 #include "common.cuh"
+#include "map_dev.cuh"
 
 // ------------------------------------------------------------------------------------------------ device
 // valid / status from the three validity codes, in the reference's evaluation order
@@ -86,24 +87,81 @@ PORRT_API int32_t porrt_transition_valid(porrt_ctx* ctx, const double* from_xy, 
   return PORRT_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ sampler (host)
-namespace {
-struct Trial { int joint, a, b; };
-}  // namespace
+// ------------------------------------------------------------------------------------------------ the trial loop on the device
+#define SHORTCUT_MAX_STATES 1024      // states of one piece (shared memory: path + shortcut states + per-transition results)
+#define SHORTCUT_THREADS 128
 
-#define SHORTCUT_WAVE 64
-
-namespace {
-struct Piece {                       // one path piece of the policy (pto_policy_refiner.rs:127-156 build_path_piece)
-  double* st; int L;                 // its states (in the caller's array), number of states
-  std::vector<Trial> trials;
-  int i0 = 0, K = 0, recent = 0, commits = 0;   // next trial, trials in the current wave, outcome predictor, committed shortcuts
-  std::vector<double> spec, snap;    // speculative path; per trial of the wave the states it read (a..b) when it was built
-  std::vector<size_t> first, snap_at;
-  size_t base = 0;                   // first transition of this piece in the wave's batch
-};
-inline double interpolate(double x, double y, double lambda) { return x * (1.0 - lambda) + y * lambda; }   // :159-161
-}  // namespace
+// trial = joint | a << 1 | b << 16 (a, b < 1024)
+template <int KIND>
+__global__ void __launch_bounds__(SHORTCUT_THREADS) shortcut_loop_kernel(MapDev m, double2* __restrict__ states, const int32_t* __restrict__ piece_ptr,
+                                                                         const int32_t* __restrict__ piece_list, const uint32_t* __restrict__ trials,
+                                                                         int n_iterations, const uint8_t* __restrict__ compat_rows, int n_validities,
+                                                                         int32_t* __restrict__ out_commits, int32_t* __restrict__ out_status) {
+  __shared__ double2 s_path[SHORTCUT_MAX_STATES];
+  __shared__ double2 s_cut[SHORTCUT_MAX_STATES];
+  __shared__ int32_t s_res[SHORTCUT_MAX_STATES];   // per transition: 1 valid, 0 invalid, < -1 the panic its check hits
+  __shared__ int32_t s_decision;
+  const int piece = piece_list[blockIdx.x];
+  const int p0 = piece_ptr[piece], L = piece_ptr[piece + 1] - p0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = SHORTCUT_THREADS / 32;
+  const uint8_t* compat = compat_rows + (size_t)piece * n_validities;
+  const uint32_t* my_trials = trials + (size_t)blockIdx.x * n_iterations;
+  for (int j = tid; j < L; j += SHORTCUT_THREADS) s_path[j] = states[p0 + j];
+  __syncthreads();
+  int commits = 0, panic = 0;
+  for (int it = 0; it < n_iterations; ++it) {
+    const uint32_t t = my_trials[it];
+    const int joint = (int)(t & 1u), a = (int)((t >> 1) & 0x7fffu), b = (int)(t >> 16);
+    const int n_tr = b - a;                                  // transitions: cut[0]->cut[1] .. cut[n-2]->cut[n-1], cut[n-1]->path[b]
+    // shortcut states: state j with its `joint` coordinate interpolated between the interval's ends (:182-190)
+    const double sa = joint ? s_path[a].y : s_path[a].x, sb = joint ? s_path[b].y : s_path[b].x;
+    for (int j = a + tid; j < b; j += SHORTCUT_THREADS) {
+      const double lambda = __ddiv_rn((double)(j - a), (double)(b - a));
+      const double v = __dadd_rn(__dmul_rn(sa, __dsub_rn(1.0, lambda)), __dmul_rn(sb, lambda));   // a * (1 - lambda) + b * lambda (:160)
+      double2 s = s_path[j];
+      if (joint) s.y = v; else s.x = v;
+      s_cut[j - a] = s;
+    }
+    __syncthreads();
+    // is_transition_valid of every transition (:395-423), one warp each
+    for (int k = warp; k < n_tr; k += n_warps) {
+      const double2 from = s_cut[k], to = k + 1 < n_tr ? s_cut[k + 1] : s_path[b];
+      const int32_t f = state_validity_of(m, from.x, from.y), g = state_validity_of(m, to.x, to.y);
+      int32_t res = 0;
+      if (f < -1) res = f;                 // state_validity(from) panics first (:396)
+      else if (g < -1) res = g;            // then state_validity(to) (:397)
+      else if (f >= 0 && g >= 0) {         // only then is the transition looked at (:399-414)
+        const EdgeSetup es = make_setup(m, from.x, from.y, to.x, to.y);
+        const int32_t e = walk_to_validity(m, walk_warp<KIND>(m, es, lane));
+        if (e < -1) res = e;
+        else if (e >= 0) res = compat[e] ? 1 : 0;
+      }
+      if (lane == 0) s_res[k] = res;
+    }
+    __syncthreads();
+    // should_commit = t_0 && t_1 && ... (:193-197): the chain stops at the first false, a panic counts only if it is reached
+    if (warp == 0) {
+      int decision = 1;
+      for (int k0 = 0; k0 < n_tr && decision == 1; k0 += 32) {
+        const int k = k0 + lane;
+        const int32_t r = k < n_tr ? s_res[k] : 1;
+        const unsigned stop = __ballot_sync(0xffffffffu, r != 1);
+        if (stop) decision = __shfl_sync(0xffffffffu, r, __ffs(stop) - 1);   // 0: no commit, < -1: the reference panics here
+      }
+      if (lane == 0) s_decision = decision;
+    }
+    __syncthreads();
+    const int decision = s_decision;
+    if (decision < -1) { panic = decision; break; }
+    if (decision == 1) {                                                     // :200-204
+      for (int j = a + tid; j < b; j += SHORTCUT_THREADS) s_path[j] = s_cut[j - a];
+      ++commits;
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < L; j += SHORTCUT_THREADS) states[p0 + j] = s_path[j];
+  if (tid == 0) { out_commits[piece] = commits; out_status[piece] = panic; }
+}
 
 PORRT_API int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy, const int32_t* piece_ptr, int32_t n_pieces,
                                                const uint8_t* compat_rows, int32_t n_iterations, uint64_t sampler_seed,
@@ -115,147 +173,66 @@ PORRT_API int32_t porrt_partial_shortcut_batch(porrt_ctx* ctx, double* states_xy
   if (out_waves) *out_waves = 0;
   for (int p = 0; p < n_pieces; ++p) {
     if (out_commits) out_commits[p] = 0;
-    if (piece_ptr[p + 1] < piece_ptr[p]) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_partial_shortcut_batch: piece_ptr must be non-decreasing");
+    if (piece_ptr[p + 1] < piece_ptr[p] || piece_ptr[p] < 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "porrt_partial_shortcut_batch: piece_ptr must be non-decreasing");
+    if (piece_ptr[p + 1] - piece_ptr[p] > SHORTCUT_MAX_STATES) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "porrt_partial_shortcut_batch: a piece has more than 1024 states");
   }
   if (n_pieces == 0 || n_iterations == 0) return PORRT_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const size_t nv = (size_t)ctx->n_validities;
-
   // every piece draws the same kind of sequence from a fresh sampler (:169 DiscreteSampler::new()): joint, interval start,
-  // interval end (:172-174) depend on the piece length only, so all trials are known before anything is checked
-  std::vector<Piece> pieces;
-  std::vector<int> piece_of;           // index into the caller's arrays
-  size_t cap = 0;
+  // interval end (:172-174) depend on the piece length only, so the whole trial list is known before anything is checked
+  std::vector<int32_t> list;
+  std::vector<uint32_t> trials;
   for (int p = 0; p < n_pieces; ++p) {
     const int L = piece_ptr[p + 1] - piece_ptr[p];
     if (L <= 2) continue;              // :163-165: can't shortcut with only 2 states or less
-    Piece pc;
-    pc.st = states_xy + 2 * (size_t)piece_ptr[p]; pc.L = L;
-    pc.trials.resize((size_t)n_iterations);
+    list.push_back(p);
     Pcg64 rng = Pcg64::seed_from_u64(sampler_seed);
     for (int i = 0; i < n_iterations; ++i) {
-      Trial t;
-      t.joint = (int)rng.below(2);
-      t.a = (int)rng.below((uint64_t)(L - 2));
-      t.b = t.a + 2 + (int)rng.below((uint64_t)(L - t.a - 2));
-      pc.trials[(size_t)i] = t;
+      const uint32_t joint = (uint32_t)rng.below(2);
+      const uint32_t a = (uint32_t)rng.below((uint64_t)(L - 2));
+      const uint32_t b = a + 2 + (uint32_t)rng.below((uint64_t)(L - a - 2));
+      trials.push_back(joint | (a << 1) | (b << 16));
     }
-    pc.spec.resize((size_t)2 * L);
-    pc.first.resize(SHORTCUT_WAVE + 1); pc.snap_at.resize(SHORTCUT_WAVE + 1);
-    cap += (size_t)SHORTCUT_WAVE * (size_t)(L - 1);      // a wave has at most SHORTCUT_WAVE * (L - 1) transitions per piece
-    pieces.push_back(std::move(pc));
-    piece_of.push_back(p);
   }
-  if (pieces.empty()) return PORRT_OK;
-  CUDA_TRY(ctx, ctx->pin[2].ensure(cap * (32 + 4 + 4 + 1)));
-  CUDA_TRY(ctx, ctx->scratch[3].ensure(cap * (32 + 12 + 4 + 4 + 1) + (size_t)n_pieces * nv + 64));
-  double* h_from = ctx->pin[2].as<double>();
-  double* h_to = h_from + 2 * cap;
-  int32_t* h_row = (int32_t*)(h_to + 2 * cap);
-  int32_t* h_status = h_row + cap;
-  uint8_t* h_valid = (uint8_t*)(h_status + cap);
-  char* b = ctx->scratch[3].as<char>();
-  double* d_from = (double*)b; b += cap * 16;
-  double* d_to = (double*)b; b += cap * 16;
-  int32_t* d_tmp = (int32_t*)b; b += cap * 12;
-  int32_t* d_row = (int32_t*)b; b += cap * 4;
-  int32_t* d_status = (int32_t*)b; b += cap * 4;
-  uint8_t* d_valid = (uint8_t*)b; b += cap;
-  uint8_t* d_compat = (uint8_t*)b;
+  if (list.empty()) return PORRT_OK;
+  const int64_t n_states = piece_ptr[n_pieces];
+  const size_t n_active = list.size();
+  DevBuf& g = ctx->scratch[3];
+  CUDA_TRY(ctx, g.ensure((size_t)n_states * 16 + (size_t)(n_pieces + 1) * 4 + n_active * 4 + trials.size() * 4 + (size_t)n_pieces * (nv + 8) + 8 * 16));
+  char* b = g.as<char>();
+  auto take = [&](size_t bytes) { char* q = b; b += (bytes + 15) & ~(size_t)15; return q; };
+  double2* d_states = (double2*)take((size_t)n_states * 16);
+  int32_t* d_ptr = (int32_t*)take((size_t)(n_pieces + 1) * 4);
+  int32_t* d_list = (int32_t*)take(n_active * 4);
+  uint32_t* d_trials = (uint32_t*)take(trials.size() * 4);
+  uint8_t* d_compat = (uint8_t*)take((size_t)n_pieces * nv);
+  int32_t* d_commits = (int32_t*)take((size_t)n_pieces * 4);
+  int32_t* d_status = (int32_t*)take((size_t)n_pieces * 4);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_states, states_xy, (size_t)n_states * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_ptr, piece_ptr, (size_t)(n_pieces + 1) * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_list, list.data(), n_active * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_trials, trials.data(), trials.size() * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, compat_rows, (size_t)n_pieces * nv, cudaMemcpyHostToDevice, st));
-
-  int waves = 0;
-  double t_build = 0, t_dev = 0, t_replay = 0;
-  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  for (;;) {
-    const double tb0 = now();
-    // ---- build: the next <= SHORTCUT_WAVE trials of every unfinished piece, on a SPECULATIVE copy of its path: every trial
-    // is assumed to end like most recent ones did (commit / reject), so later trials of the wave see the states they will
-    // most likely see.  Shortcut states (:182-190) and transitions (:193-197) of all pieces form one device batch.
-    size_t m = 0;
-    for (size_t q = 0; q < pieces.size(); ++q) {
-      Piece& pc = pieces[q];
-      pc.K = std::min(SHORTCUT_WAVE, n_iterations - pc.i0);
-      if (pc.K <= 0) { pc.K = 0; continue; }
-      const bool predict_commit = pc.recent >= 0;
-      std::copy(pc.st, pc.st + 2 * pc.L, pc.spec.begin());
-      pc.snap.clear();
-      pc.base = m;
-      double* spec = pc.spec.data();
-      for (int w = 0; w < pc.K; ++w) {
-        const Trial& t = pc.trials[(size_t)(pc.i0 + w)];
-        pc.first[(size_t)w] = m;
-        pc.snap_at[(size_t)w] = pc.snap.size();
-        pc.snap.insert(pc.snap.end(), spec + 2 * t.a, spec + 2 * (t.b + 1));
-        const double sa = spec[2 * t.a + t.joint], sb = spec[2 * t.b + t.joint];
-        double prev[2] = {0, 0};
-        for (int j = t.a; j < t.b; ++j) {
-          const double lambda = (double)(j - t.a) / (double)(t.b - t.a);
-          double s2[2] = {spec[2 * j], spec[2 * j + 1]};
-          s2[t.joint] = interpolate(sa, sb, lambda);
-          if (j > t.a) { h_from[2 * m] = prev[0]; h_from[2 * m + 1] = prev[1]; h_to[2 * m] = s2[0]; h_to[2 * m + 1] = s2[1]; h_row[m] = piece_of[q]; ++m; }
-          prev[0] = s2[0]; prev[1] = s2[1];
-          if (predict_commit) spec[2 * j + t.joint] = s2[t.joint];   // in place is fine: sa / sb were read before, state a maps to itself
-        }
-        h_from[2 * m] = prev[0]; h_from[2 * m + 1] = prev[1];                     // last shortcut state -> interval end (:197)
-        h_to[2 * m] = spec[2 * t.b]; h_to[2 * m + 1] = spec[2 * t.b + 1];
-        h_row[m] = piece_of[q];
-        ++m;
-      }
-      pc.first[(size_t)pc.K] = m;
-      pc.snap_at[(size_t)pc.K] = pc.snap.size();
-    }
-    if (m == 0) break;                 // every piece has run all its trials
-    const double tb1 = now();
-    t_build += tb1 - tb0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_from, h_from, m * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_to, h_to, m * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_row, h_row, m * 4, cudaMemcpyHostToDevice, st));
-    int32_t rc = transition_valid_dev(ctx, d_from, d_to, (int64_t)m, d_compat, d_row, (int32_t)nv, d_tmp, d_valid, d_status);
-    if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_valid, d_valid, m, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_status, d_status, m * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    ++waves;
-    const double tb2 = now();
-    t_dev += tb2 - tb1;
-    // ---- replay, piece by piece, in trial order on the REAL path.  A trial's device results are usable iff the states it
-    // read while the wave was built are bit-identical to the real ones now; the first trial that fails this test starts
-    // the piece's next wave.
-    for (size_t q = 0; q < pieces.size(); ++q) {
-      Piece& pc = pieces[q];
-      int w = 0;
-      for (; w < pc.K; ++w) {
-        const Trial& t = pc.trials[(size_t)(pc.i0 + w)];
-        if (!std::equal(pc.snap.begin() + pc.snap_at[(size_t)w], pc.snap.begin() + pc.snap_at[(size_t)w + 1], pc.st + 2 * t.a,
-                        [](double x, double y) { return memcmp(&x, &y, 8) == 0; }))
-          break;
-        bool should_commit = true;
-        for (size_t k = pc.first[(size_t)w]; k < pc.first[(size_t)w + 1]; ++k) {
-          if (!h_valid[k]) {
-            if (h_status[k] < -1) {                // the reference panics here (the `&&` chain evaluates up to the first false)
-              if (out_waves) *out_waves = waves;
-              return porrt_fail(ctx, PORRT_ERR_PANIC, "partial_shortcut: a transition check hit a reference panic (code " + std::to_string(h_status[k]) + ")");
-            }
-            should_commit = false;
-            break;
-          }
-        }
-        if (should_commit) {                       // :200-204
-          const double sa = pc.st[2 * t.a + t.joint], sb = pc.st[2 * t.b + t.joint];
-          for (int j = t.a; j < t.b; ++j) pc.st[2 * j + t.joint] = interpolate(sa, sb, (double)(j - t.a) / (double)(t.b - t.a));
-          ++pc.commits;
-        }
-        pc.recent = std::max(-4, std::min(4, pc.recent + (should_commit ? 1 : -1)));
-      }
-      pc.i0 += w;                      // w >= 1 whenever K >= 1: the first trial of a wave is built from the real path
-      if (out_commits) out_commits[piece_of[q]] = pc.commits;
-    }
-    t_replay += now() - tb2;
-  }
-  if (getenv("PORRT_DEBUG")) fprintf(stderr, "[porrt] partial_shortcut: %d waves, build %.2f ms, device %.2f ms, replay %.2f ms\n", waves, t_build, t_dev, t_replay);
-  if (out_waves) *out_waves = waves;
+  CUDA_TRY(ctx, cudaMemsetAsync(d_commits, 0, (size_t)n_pieces * 8 + 16, st));   // commits and status (adjacent, 16-byte aligned)
+  if (ctx->map.kind == PORRT_DOMAIN_SHELF)
+    shortcut_loop_kernel<PORRT_DOMAIN_SHELF><<<(int)n_active, SHORTCUT_THREADS, 0, st>>>(ctx->map, d_states, d_ptr, d_list, d_trials, n_iterations, d_compat, (int)nv, d_commits, d_status);
+  else
+    shortcut_loop_kernel<PORRT_DOMAIN_DOOR><<<(int)n_active, SHORTCUT_THREADS, 0, st>>>(ctx->map, d_states, d_ptr, d_list, d_trials, n_iterations, d_compat, (int)nv, d_commits, d_status);
+  LAUNCH_CHECK(ctx);
+  std::vector<int32_t> commits((size_t)n_pieces), status((size_t)n_pieces);
+  std::vector<double> refined((size_t)n_states * 2);
+  CUDA_TRY(ctx, cudaMemcpyAsync(refined.data(), d_states, (size_t)n_states * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(commits.data(), d_commits, (size_t)n_pieces * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), d_status, (size_t)n_pieces * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (out_waves) *out_waves = 1;       // device round trips of the call
+  for (int p = 0; p < n_pieces; ++p)
+    if (status[(size_t)p] < -1)        // the caller's states stay untouched, like a panic leaves nothing behind
+      return porrt_fail(ctx, PORRT_ERR_PANIC, "partial_shortcut: a transition check hit a reference panic (code " + std::to_string(status[(size_t)p]) + ")");
+  memcpy(states_xy, refined.data(), (size_t)n_states * 16);
+  if (out_commits) memcpy(out_commits, commits.data(), (size_t)n_pieces * 4);
   return PORRT_OK;
 }
 
