@@ -372,12 +372,88 @@ PORRT_API int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n) {
 }
 
 // ================================================================================================ radius query
+// Prefix-restricted queries that cover many cells (the early nodes of a PRM: radius up to max_step over a grid whose cell is the
+// LAST node's radius, 100-800 cells, almost all of them answered by one id comparison because the list is id-ascending and the
+// limit small) are a chain of dependent loads per cell: a thread per query walks them one after the other (the tail of the PRM's
+// radius phase), a WARP per query takes 32 cells at a time.  Same hits in the same order (cell rows outer, cells inner).
+#define RADIUS_WIDE_CELLS 64   // (24: the wide kernels then cost more than they save -- 1.78 against 1.29 ms for both passes at 1e6 nodes)
+__global__ void radius_wide_list_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius, int64_t m,
+                                        const int32_t* __restrict__ list, int32_t* __restrict__ wide, int32_t* __restrict__ n_wide) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  if (list) t = list[t];
+  const double2 p = q[t];
+  const double r = radius[t];
+  if (!(radius_threshold(r) >= 0.0) || !(p.x == p.x && p.y == p.y)) return;
+  const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);
+  const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
+  const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
+  if ((int64_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1) > RADIUS_WIDE_CELLS) wide[atomicAdd(n_wide, 1)] = (int32_t)t;
+}
+template <bool FILL>
+__global__ void __launch_bounds__(128) radius_wide_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius,
+                                                          const int32_t* __restrict__ wide, const int32_t* __restrict__ n_wide,
+                                                          const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
+                                                          const uint32_t* __restrict__ world, int32_t* __restrict__ counts,
+                                                          const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids,
+                                                          const uint32_t* __restrict__ prefix_lo) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int qi = warp; qi < *n_wide; qi += n_warps) {
+    const int32_t t = wide[qi];
+    const double2 p = q[t];
+    const double r = radius[t];
+    const double T = radius_threshold(r);
+    const uint32_t limit = prefix[t];
+    const uint32_t lo_limit = prefix_lo ? prefix_lo[t] : 0u;
+    const uint32_t wq = (reach && world) ? world[t] : 0u;
+    const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);
+    const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
+    const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
+    const int nx = cx1 - cx0 + 1;
+    const int64_t n_cells = (int64_t)nx * (cy1 - cy0 + 1);
+    int32_t* out = FILL ? out_ids + offsets[t] : nullptr;
+    int32_t run = 0;
+    for (int64_t c0 = 0; c0 < n_cells; c0 += 32) {
+      const int64_t ci = c0 + lane;
+      int64_t k0 = 0, e = 0;
+      if (ci < n_cells) {
+        const int64_t c = (int64_t)(cy0 + (int)(ci / nx)) * g.cells_x + (cx0 + (int)(ci % nx));
+        k0 = g.cell_start[c]; e = g.cell_start[c + 1];
+        if (lo_limit) {   // grouped vertex sets: jump to the first id of the query's own group
+          int64_t hi = e;
+          while (k0 < hi) { const int64_t mid = (k0 + hi) >> 1; if ((uint32_t)g.vid[mid] < lo_limit) k0 = mid + 1; else hi = mid; }
+        }
+      }
+      int32_t mine = 0;
+      for (int64_t k = k0; k < e; ++k) {
+        const uint32_t id = (uint32_t)g.vid[k];
+        if (id >= limit) break;
+        if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || reach_bit(reach, g.reach_words, id, wq))) ++mine;
+      }
+      int32_t incl = mine;
+      for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (FILL && mine) {
+        int32_t at = run + incl - mine;
+        for (int64_t k = k0; k < e; ++k) {
+          const uint32_t id = (uint32_t)g.vid[k];
+          if (id >= limit) break;
+          if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || reach_bit(reach, g.reach_words, id, wq))) out[at++] = (int32_t)id;
+        }
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (!FILL && lane == 0) counts[t] = run;
+  }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius, int64_t m,
                                                      const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
                                                      const uint32_t* __restrict__ world, int32_t* __restrict__ counts,
                                                      const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids,
-                                                     const int32_t* __restrict__ list, const uint32_t* __restrict__ prefix_lo) {
+                                                     const int32_t* __restrict__ list, const uint32_t* __restrict__ prefix_lo,
+                                                     bool skip_wide = false) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
   if (list) t = list[t];   // m = length of the list: the queries nn_tile.cu left to this kernel
@@ -392,6 +468,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
     const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);  // conservative cell cover
     const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
     const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
+    if (skip_wide && prefix && (int64_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1) > RADIUS_WIDE_CELLS) return;   // radius_wide_kernel's
     int32_t* out = FILL ? out_ids + offsets[t] : nullptr;
     for (int cy = cy0; cy <= cy1; ++cy) {
       if (prefix) {
@@ -453,16 +530,39 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   const int32_t* fb_list = nullptr;
   const int32_t* staging = nullptr;
   int32_t fb_n = 0;
+  // prefix-restricted queries over many cells get a warp each (radius_wide_kernel); the list is built once for both passes
+  const bool wide = prefix_dev != nullptr && m >= 1024;
+  int32_t* wide_list = nullptr;
+  int32_t* n_wide = nullptr;
+  if (wide) {
+    CUDA_TRY(ctx, ctx->scratch[9].ensure((size_t)m * 4 + 64));
+    n_wide = ctx->scratch[9].as<int32_t>();
+    wide_list = n_wide + 16;
+    CUDA_TRY(ctx, cudaMemsetAsync(n_wide, 0, 4, st));
+  }
+  const int wide_grid = ctx->sm_count * 8;
   if (tiles) {
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)m * 4, st));
     int32_t rc = nn_tile_radius_collect(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, stg_off, &staging, &fb_list, &fb_n);
     if (rc) return rc;
     if (fb_n > 0) {
-      radius_kernel<false><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, fb_list, prefix_lo_dev);
+      if (wide) {
+        radius_wide_list_kernel<<<div_up(fb_n, 256), 256, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, fb_list, wide_list, n_wide);
+        LAUNCH_CHECK(ctx);
+        radius_wide_kernel<false><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, prefix_lo_dev);
+        LAUNCH_CHECK(ctx);
+      }
+      radius_kernel<false><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, fb_list, prefix_lo_dev, wide);
       LAUNCH_CHECK(ctx);
     }
   } else {
-    radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, nullptr, prefix_lo_dev);
+    if (wide) {
+      radius_wide_list_kernel<<<div_up(m, 256), 256, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, nullptr, wide_list, n_wide);
+      LAUNCH_CHECK(ctx);
+      radius_wide_kernel<false><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, prefix_lo_dev);
+      LAUNCH_CHECK(ctx);
+    }
+    radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, nullptr, prefix_lo_dev, wide);
     LAUNCH_CHECK(ctx);
   }
   int32_t rc = scan_exclusive_i64(ctx, counts, m, offsets_dev);
@@ -477,7 +577,11 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
       rc = nn_tile_radius_place(ctx, staging, stg_off, offsets_dev, m, ids_buf->as<int32_t>());
       if (rc) return rc;
       if (fb_n > 0) {
-        radius_kernel<true><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), fb_list, prefix_lo_dev);
+        if (wide) {
+          radius_wide_kernel<true><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), prefix_lo_dev);
+          LAUNCH_CHECK(ctx);
+        }
+        radius_kernel<true><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), fb_list, prefix_lo_dev, wide);
         LAUNCH_CHECK(ctx);
         if (sort_ids) {
           rc = segments_sort_by_key_dev(ctx, offsets_dev, m, ids_buf->as<int32_t>(), nullptr, g.n, fb_list, fb_n);
@@ -485,7 +589,11 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
         }
       }
     } else {
-      radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), nullptr, prefix_lo_dev);
+      if (wide) {
+        radius_wide_kernel<true><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), prefix_lo_dev);
+        LAUNCH_CHECK(ctx);
+      }
+      radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), nullptr, prefix_lo_dev, wide);
       LAUNCH_CHECK(ctx);
       if (sort_ids) {
         rc = segments_sort_by_key_dev(ctx, offsets_dev, m, ids_buf->as<int32_t>(), nullptr, g.n);
