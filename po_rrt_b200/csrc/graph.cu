@@ -308,7 +308,33 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   // multi-GPU (comm.cu): this rank answers the queries of new nodes [lo, hi) only -- and needs only their radii
   const int world = ctx->comm_world;
   int64_t lo = 0, hi = n;
-  if (world > 1) comm_shard_range(n, ctx->comm_rank, world, &lo, &hi);
+  // Shard boundaries by estimated WORK, not by count: node k's query covers ~(2 r(k) / cell + 1)^2 cells of a grid whose cell is the
+  // last node's radius, so the first nodes cost hundreds of times more than the last ones (equal counts left rank 0 with 2.2 ms of
+  // radius queries at 8 GPUs while the others were done in 0.3).  Every rank computes the same boundaries from the same closed form.
+  std::vector<int64_t> bnd((size_t)world + 1, 0);
+  bnd[(size_t)world] = n;
+  if (world > 1) {
+    const double r_n = n > 2 ? search_radius * std::sqrt(std::log((double)n) / (double)n) : max_step;
+    const double cell_est = std::max(1e-12, std::min(r_n, max_step > 0 ? max_step : r_n));
+    auto cost = [&](double k) {   // cells covered + a constant for the candidates that are always looked at
+      const double r = k < 2 ? 0.0 : std::min(search_radius * std::sqrt(std::log(k + 1.0) / (k + 1.0)), max_step > 0 ? max_step : 1e300);
+      const double side = 2.0 * r / cell_est + 1.0;
+      return 40.0 + side * side;
+    };
+    std::vector<double> ks, cum;   // cumulative cost on a geometric grid of node indices
+    for (double k = 1.0; k < (double)n; k = std::max(k + 1.0, k * 1.01)) ks.push_back(k);
+    ks.push_back((double)n);
+    cum.assign(ks.size(), 0.0);
+    for (size_t i = 1; i < ks.size(); ++i) cum[i] = cum[i - 1] + 0.5 * (cost(ks[i - 1]) + cost(ks[i])) * (ks[i] - ks[i - 1]);
+    for (int r = 1; r < world; ++r) {
+      const double want = cum.back() * (double)r / (double)world;
+      const size_t i = (size_t)(std::upper_bound(cum.begin(), cum.end(), want) - cum.begin());
+      double k = (double)n;
+      if (i > 0 && i < ks.size()) k = ks[i - 1] + (ks[i] - ks[i - 1]) * (want - cum[i - 1]) / std::max(1e-300, cum[i] - cum[i - 1]);
+      bnd[(size_t)r] = std::max<int64_t>(bnd[(size_t)r - 1], std::min<int64_t>(n, (int64_t)k));
+    }
+    lo = bnd[(size_t)ctx->comm_rank]; hi = bnd[(size_t)ctx->comm_rank + 1];
+  }
   const int64_t m = hi - lo;
   std::vector<std::thread> th;
   // heuristic_radius is a pure function of (k, max_step, search_radius): a ctx that builds roadmaps of the same parameters again
@@ -482,7 +508,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
     rc = comm_all_gatherv_dev(ctx, nullptr, d_summary, off16.data(), st);
     if (rc) return rc;
     std::vector<int64_t> cnt_off(world + 1);
-    for (int r = 0; r < world; ++r) { int64_t a, b2; comm_shard_range(n, r, world, &a, &b2); cnt_off[r] = a * 4; cnt_off[r + 1] = b2 * 4; }
+    for (int r = 0; r <= world; ++r) cnt_off[r] = bnd[(size_t)r] * 4;
     rc = comm_all_gatherv_dev(ctx, nullptr, d_early_cnt, cnt_off.data(), st);
     if (rc) return rc;
     std::vector<int64_t> summary(2 * world);
