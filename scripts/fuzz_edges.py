@@ -22,7 +22,7 @@ for it in range(rounds):
         i, j = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
         occ[i:i + h, j:j + w] = 0 if (kind == P.DOOR or rng.random() < 0.6) else int(rng.integers(127, 255))
     zones = np.full((H, W), 255, np.uint8)
-    nz = int(rng.integers(1, 7))
+    nz = int(rng.integers(1, 9)) if kind == P.DOOR else int(rng.integers(1, 13))   # 7-8 door zones: 128 / 256 worlds, two / four mask words
     for z in range(nz):
         h, w = int(rng.integers(2, max(3, H // 8))), int(rng.integers(2, max(3, W // 8)))
         i, j = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
