@@ -147,7 +147,7 @@ int32_t belief_succ_tables(porrt_ctx* ctx, const double* beliefs_host, int32_t B
   std::vector<int32_t> sid((size_t)B);
   for (int b = 0; b < B; ++b) { sh[(size_t)b] = sorted[(size_t)b].first; sid[(size_t)b] = sorted[(size_t)b].second; }
 
-  // ---- inputs + work space (scratch[4]); outputs (scratch[5]) are sized after the scan
+  // ---- inputs + work space (scratch[4]); outputs (ctx->d_bel_succ) are sized after the scan
   DevBuf& wsb = ctx->scratch[4];
   const size_t zw = ctx->zone_world_masks.size();
   const size_t in_bytes = (size_t)B * nw * 8 + (size_t)n_sets * 8 + (size_t)(n_sets + 1) * 8 + zw * 8 + (size_t)B * 28 + 16 * 16;
@@ -199,7 +199,7 @@ int32_t belief_succ_tables(porrt_ctx* ctx, const double* beliefs_host, int32_t B
   if (err & 1) return porrt_fail(ctx, PORRT_ERR_PANIC, "no id corresponding to this belief state! (belief_graph.rs:69)");
   if (err & 2) return porrt_fail(ctx, PORRT_ERR_PANIC, "assert!(p > 0.0) (belief_graph.rs:130)");
   const int64_t n_sb = (int64_t)n_sets * B;
-  DevBuf& ob = ctx->scratch[5];
+  DevBuf& ob = ctx->d_bel_succ;   // dedicated: the tables are read until the last level is done (sssp_frontier.cu owns scratch[5..7])
   CUDA_TRY(ctx, ob.ensure((size_t)(n_sb + 1) * 8 + (size_t)n_succ * 16 + 4 * 16 + 16));
   char* o = ob.as<char>();
   auto take_o = [&](size_t bytes) { char* q = o; o += (bytes + 15) & ~(size_t)15; return q; };

@@ -146,6 +146,7 @@ struct porrt_ctx {
     std::vector<std::vector<uint8_t>> col_type;
   } bel;
   std::vector<int32_t> bel_node_vid;
+  DevBuf d_bel_succ;                   // observation successor tables of the running / last porrt_belief_vi (belief_tables.cu)
   // last PRM result, kept on the device (valid until the next call on this ctx)
   int64_t prm_n = 0, prm_edges = 0;
   const int64_t* prm_row_ptr = nullptr;

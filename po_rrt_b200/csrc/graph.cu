@@ -932,7 +932,6 @@ struct BeliefDev {
   const int64_t* row_ptr; const int32_t* col; const int32_t* edge_vid; const double* cost;
   const int32_t* node_vid; const int32_t* node_set;
   const uint8_t* compat;      // [B][n_validities]
-  const uint8_t* compat_t;    // [n_validities][B]: the threads of a node (consecutive beliefs) read consecutive bytes
   const int64_t* succ_ptr;    // [n_sets * B + 1]
   const int32_t* succ_belief; const double* succ_p;
   int64_t V; int32_t B, n_validities;
@@ -967,57 +966,48 @@ __global__ void type_finish_kernel(uint8_t* __restrict__ type, int64_t n) {
     if (type[i] == 255) type[i] = PORRT_NODE_UNKNOWN;
 }
 
-// One pull sweep of conditional_dijkstra's backup (belief_graph.rs:117-146):
-//   Action     : alt = min_v  norm2(u,v) + dist[v]                      (:121-124)
-//   Observation: alt = sum_vv p(u->vv) * (0.0 + dist[vv]) in stored order (:125-135; obs edges keep the state => cost 0.0)
-// Work skipping: a backup can only change if one of its inputs changed since it was last evaluated.  node_epoch[n] = last sweep
-// in which any belief of node n changed; before sweep s, belief_active_kernel marks the nodes with a child (action edges) or
-// themselves (observation edges stay on the node) changed in sweep s-1; all other nodes saw their inputs' final values when they
-// were evaluated in sweep s-1 (kernel boundary) and are skipped.  Sweep 1 evaluates everything.
-__global__ void belief_active_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int64_t V,
-                                     const int32_t* __restrict__ node_epoch, int32_t sweep, uint8_t* __restrict__ active) {
-  const int lane = threadIdx.x & 31;
-  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (n >= V) return;
-  bool a = sweep <= 1 || node_epoch[n] == sweep - 1;
-  if (!a)
-    for (int64_t e = row_ptr[n] + lane; e < row_ptr[n + 1]; e += 32) a |= node_epoch[col[e]] == sweep - 1;
-  a = __any_sync(0xffffffffu, a);
-  if (lane == 0) active[n] = a ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(256) belief_sweep_kernel(BeliefDev g, const uint8_t* __restrict__ type, double* __restrict__ dist,
-                                                           int32_t* __restrict__ changed, const uint8_t* __restrict__ active,
-                                                           int32_t* __restrict__ node_epoch, int32_t sweep) {
+// ---- belief columns through the frontier relaxation (sssp_frontier.cu): roadmaps whose column does not fit in shared memory.
+// Initial values of the columns [c_lo, c_hi) of one level in the Morton-numbered table: +inf, 0 at the finals (already scattered),
+// the Observation value  sum_k p_k * (0.0 + dist[n][succ_k])  (belief_graph.rs:125-135) from the finished columns; the sign bit on
+// everything that is not an Action node (never relaxed).
+__global__ void belief_level_init_kernel(int64_t V, int B, int c_lo, int c_hi, const uint32_t* __restrict__ order, const uint8_t* __restrict__ type_cm,
+                                         const int32_t* __restrict__ nvid, const int32_t* __restrict__ node_set, const int32_t* __restrict__ col_belief,
+                                         const int64_t* __restrict__ succ_ptr, const int32_t* __restrict__ succ_col, const double* __restrict__ succ_p,
+                                         const uint64_t* __restrict__ cmask, double* __restrict__ table) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= g.V * g.B) return;
-  const int64_t n = t / g.B;
-  if (active && !active[n]) return;
-  const uint8_t ty = type[t];
-  if (ty != PORRT_NODE_ACTION && ty != PORRT_NODE_OBSERVATION) return;
-  const int b = (int)(t - n * g.B);
-  const double old = dist[t];
-  double alt;
+  if (t >= (int64_t)(c_hi - c_lo) * V) return;
+  const int c = c_lo + (int)(t / V);
+  const int64_t pos = t - (int64_t)(c - c_lo) * V;
+  if (col_belief[c] < 0) return;                       // padding column
+  const int64_t n = order[pos];
+  const uint8_t ty = type_cm[(int64_t)c * V + n];
+  double v = table[(int64_t)c * V + pos];
   if (ty == PORRT_NODE_OBSERVATION) {
-    const int32_t nv = g.node_vid[n];
-    const int64_t sp = (int64_t)g.node_set[n] * g.B + b;
-    alt = 0.0;
-    for (int64_t k = g.succ_ptr[sp]; k < g.succ_ptr[sp + 1]; ++k) {
-      const int32_t cb = g.succ_belief[k];
-      if (!g.compat[(int64_t)cb * g.n_validities + nv]) continue;
-      alt = __dadd_rn(alt, __dmul_rn(g.succ_p[k], __dadd_rn(0.0, dist[n * g.B + cb])));
+    const int32_t nv = nvid[n];
+    const int64_t sp = (int64_t)node_set[n] * B + col_belief[c];
+    double alt = 0.0;
+    for (int64_t k = succ_ptr[sp]; k < succ_ptr[sp + 1]; ++k) {
+      const int32_t cc = succ_col[k];
+      if (!((cmask[(int64_t)cc * 4 + (nv >> 6)] >> (nv & 63)) & 1)) continue;   // successor belief node does not exist here
+      alt = __dadd_rn(alt, __dmul_rn(succ_p[k], __dadd_rn(0.0, fabs(table[(int64_t)cc * V + pos]))));
     }
-  } else {
-    alt = INFINITY;
-    const uint8_t* cm = g.compat_t + b;
-    for (int64_t e = g.row_ptr[n]; e < g.row_ptr[n + 1]; ++e) {
-      const int32_t c = g.col[e];
-      if (!cm[(int64_t)g.node_vid[c] * g.B] || !cm[(int64_t)g.edge_vid[e] * g.B]) continue;
-      const double a = __dadd_rn(g.cost[e], dist[(int64_t)c * g.B + b]);
-      if (a < alt) alt = a;
-    }
+    if (alt < v) v = alt;
   }
-  if (alt < old) { dist[t] = alt; *changed = 1; if (node_epoch) node_epoch[n] = sweep; }
+  table[(int64_t)c * V + pos] = ty != PORRT_NODE_ACTION ? -v : v;
+}
+// finals: 0 in the Morton-numbered table; idx = column * V + node (caller's numbering)
+__global__ void scatter_zero_perm_kernel(double* __restrict__ table, const int64_t* __restrict__ idx, int64_t n, const int32_t* __restrict__ perm, int64_t V) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t c = idx[i] / V, node = idx[i] - c * V;
+  table[c * V + perm[node]] = 0.0;
+}
+// table (Morton numbering, signs) -> dist_cm[column][node]
+__global__ void belief_unpermute_kernel(const double* __restrict__ table, const int32_t* __restrict__ perm, int64_t V, int64_t n_cols, double* __restrict__ dist_cm) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cols * V) return;
+  const int64_t c = t / V, n = t - c * V;
+  dist_cm[t] = fabs(table[c * V + perm[n]]);
 }
 
 // dist_cm[colpos[b]][n] -> dist[n][b] through a 32 x 32 tile (both sides coalesced)
@@ -1189,26 +1179,27 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   t1 = now_ms(); ph[0] = t1 - t0; t0 = t1;
 
   const bool cols = colsolve_fits(V, E, n_validities) && !ctx->force_global_sweeps && succ.levels_ok;
-  const bool sharded = cols && ctx->comm_world > 1;   // the global sweeps are not sharded: every rank then computes the whole table
+  const bool sharded = ctx->comm_world > 1;
+  if (!succ.levels_ok) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "belief_vi: an observation does not split the belief's support (the level order of the backups does not apply)");
   std::vector<uint64_t> cmask((size_t)Bp * 4, 0);
-  if (cols)
+  {
     for (int c = 0; c < Bp; ++c)
       for (int v = 0; col_belief[(size_t)c] >= 0 && v < n_validities; ++v)
         if (compat[(size_t)col_belief[(size_t)c] * n_validities + v]) cmask[(size_t)c * 4 + v / 64] |= (uint64_t)1 << (v % 64);
-  // final belief nodes as indices into the table the backups run on ([column][node] for the column solver, else [node][belief])
-  if (cols)
-    for (int64_t& z : zero_idx) { const int64_t f = z / B; const int b2 = (int)(z % B); z = (int64_t)colpos[(size_t)b2] * V + f; }
+  }
+  // final belief nodes as indices into the [column][node] table the backups run on
+  for (int64_t& z : zero_idx) { const int64_t f = z / B; const int b2 = (int)(z % B); z = (int64_t)colpos[(size_t)b2] * V + f; }
 
   DevBuf& g = ctx->scratch[3];
   const size_t need = (size_t)(V + 1) * 16 + (size_t)E * 28 + (size_t)V * 16 + 2 * compat.size() + (size_t)V * 17 +
-                      (size_t)Bp * 40 + (cols ? 0 : (size_t)V * B * 8) + zero_idx.size() * 8 + 24 * 16 + 512;
+                      (size_t)Bp * 40 + (cols ? 0 : (size_t)V * Bp * 8) + zero_idx.size() * 8 + 24 * 16 + 512;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
   int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
   double* d_cost = (double*)take((size_t)E * 8);
   double* d_xy = (double*)take((size_t)V * 16);
-  double* d_dist = cols ? nullptr : (double*)take((size_t)V * B * 8);   // [node][belief]: the table of the global sweeps
+  double* d_table_m = cols ? nullptr : (double*)take((size_t)V * Bp * 8);   // frontier path: the table in Morton numbering, [column][pos]
   // the column solver's table ([column][node]), the node types and the column map outlive the call (lazy result, policy walk)
   auto& R = ctx->bel;
   R.V = 0; R.on_host = false;
@@ -1231,9 +1222,6 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   int32_t* d_col_belief = (int32_t*)take((size_t)Bp * 4);
   int32_t* d_changed = (int32_t*)take(16);
   uint8_t* d_compat = (uint8_t*)take(compat.size());
-  uint8_t* d_compat_t = (uint8_t*)take(compat.size());
-  uint8_t* d_active = (uint8_t*)take((size_t)V);
-  int32_t* d_epoch = (int32_t*)take((size_t)V * 4);
   int64_t* d_zero = (int64_t*)take(zero_idx.size() * 8 + 8);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
   if (E) {
@@ -1247,27 +1235,25 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   CUDA_TRY(ctx, cudaMemcpyAsync(d_colpos, colpos.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_col_belief, col_belief.data(), (size_t)Bp * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_cmask, cmask.data(), cmask.size() * 8, cudaMemcpyHostToDevice, st));
-  std::vector<uint8_t> compat_t;
-  if (!cols) {   // the sweeps read the table transposed: the threads of a node (consecutive beliefs) read consecutive bytes
-    compat_t.resize(compat.size());
-    for (int bb = 0; bb < B; ++bb)
-      for (int v = 0; v < n_validities; ++v) compat_t[(size_t)v * B + bb] = compat[(size_t)bb * n_validities + v];
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_compat_t, compat_t.data(), compat_t.size(), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(d_epoch, 0, (size_t)V * 4, st));
+  SfGraph sfg = {};
+  if (!cols) {   // Morton numbering + transposed adjacency with edge validity ids (sssp_frontier.cu)
+    int32_t rc = sf_build_graph(ctx, d_row, d_col, d_evid, d_xy, V, E, &sfg, st);
+    if (rc) return rc;
   }
-  double* d_table = cols ? d_dist_cm : d_dist;
-  fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_table, V * (int64_t)(cols ? Bp : B));
+  double* d_table = cols ? d_dist_cm : d_table_m;
+  fill_inf_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_table, V * (int64_t)Bp);
   LAUNCH_CHECK(ctx);
   if (!zero_idx.empty()) {
     CUDA_TRY(ctx, cudaMemcpyAsync(d_zero, zero_idx.data(), zero_idx.size() * 8, cudaMemcpyHostToDevice, st));
-    scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_table, d_zero, (int64_t)zero_idx.size());
+    if (cols) scatter_zero_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_table, d_zero, (int64_t)zero_idx.size());
+    else scatter_zero_perm_kernel<<<div_up((int64_t)zero_idx.size(), 256), 256, 0, st>>>(d_table, d_zero, (int64_t)zero_idx.size(), sfg.perm, V);
     LAUNCH_CHECK(ctx);
   }
   edge_cost_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, V, d_cost);
   LAUNCH_CHECK(ctx);
-  BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, d_compat_t, succ.succ_ptr, succ.succ_b, succ.succ_p, V, B, n_validities};
+  BeliefDev gd = {d_row, d_col, d_evid, d_cost, d_nvid, d_nset, d_compat, succ.succ_ptr, succ.succ_b, succ.succ_p, V, B, n_validities};
   const int blocks = div_up(V * (int64_t)B, 256);
-  belief_type_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_colpos, cols ? d_type_cm : nullptr);
+  belief_type_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_colpos, d_type_cm);
   LAUNCH_CHECK(ctx);
   if (cols) {
     int32_t rc = colsolve_pack(ctx, d_row, d_col, d_evid, d_cost, V, E, d_rs, d_ce, d_cost_t, d_cursor, st);
@@ -1307,22 +1293,39 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
     tfinish(ctx);   // porrt_ctx_last_phase_ms: [0] device ms of the column solver (all levels), [1] edge records it worked through
     ctx->last_ms[1] = (double)offers; ctx->n_last = 2;
   } else {
-    const int BATCH = 8;   // sweeps between two convergence checks
-    for (;;) {
-      CUDA_TRY(ctx, cudaMemsetAsync(d_changed, 0, 4, st));
-      for (int k = 0; k < BATCH; ++k) {
-        ++sweeps;
-        belief_active_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, V, d_epoch, sweeps, d_active);
+    // The same levels through the frontier relaxation over global memory (sssp_frontier.cu): a level's columns get their initial
+    // values (finals, Observation values from the finished levels, sign bit on everything that is not an Action node) and are
+    // relaxed together; shards and exchange as above.  The table is kept in Morton numbering until the end.
+    double offers_total = 0.0;
+    tstart(ctx);
+    for (const Level& L : levels) {
+      int64_t a2 = 0, b2 = L.n_real;
+      if (sharded) comm_shard_range(L.n_real, ctx->comm_rank, ctx->comm_world, &a2, &b2);
+      const int mine = L.lo + (sharded ? ctx->comm_rank * L.per : 0), n_mine = (int)(b2 - a2);
+      if (n_mine > 0) {
+        belief_level_init_kernel<<<div_up((int64_t)n_mine * V, 256), 256, 0, st>>>(V, B, mine, mine + n_mine, sfg.order, d_type_cm, d_nvid, d_nset,
+                                                                                    d_col_belief, succ.succ_ptr, succ.succ_col, succ.succ_p, d_cmask, d_table_m);
         LAUNCH_CHECK(ctx);
-        belief_sweep_kernel<<<blocks, 256, 0, st>>>(gd, d_type, d_dist, d_changed, d_active, d_epoch, sweeps);
-        LAUNCH_CHECK(ctx);
+        int32_t rounds = 0;
+        double offers = 0.0;
+        int32_t rc = sf_relax(ctx, sfg, d_table_m + (int64_t)mine * V, n_mine, d_cmask + (int64_t)mine * 4, &rounds, &offers, st);
+        if (rc) return rc;
+        sweeps = std::max(sweeps, (int)rounds);
+        offers_total += offers;
       }
-      int32_t changed = 0;
-      CUDA_TRY(ctx, cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(ctx, cudaStreamSynchronize(st));
-      if (!changed) break;
-      if (sweeps > 4 * V * (int64_t)B + 64) return porrt_fail(ctx, PORRT_ERR_CUDA, "belief_vi: no convergence");
+      if (sharded) {
+        std::vector<int64_t> off(ctx->comm_world + 1);
+        for (int r = 0; r <= ctx->comm_world; ++r) off[r] = (int64_t)(L.lo + r * L.per) * V * 8;
+        int32_t rc = comm_all_gatherv_dev(ctx, nullptr, d_table_m, off.data(), st);
+        if (rc) return rc;
+      }
     }
+    tmark(ctx);
+    belief_unpermute_kernel<<<div_up((int64_t)Bp * V, 256), 256, 0, st>>>(d_table_m, sfg.perm, V, Bp, d_dist_cm);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    tfinish(ctx);
+    ctx->last_ms[1] = offers_total; ctx->n_last = 2;
   }
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
   // results: retained for porrt_extract_policy / porrt_belief_result; to the caller if asked for
@@ -1337,13 +1340,13 @@ PORRT_API int32_t porrt_belief_vi(porrt_ctx* ctx, int64_t V, const int64_t* row_
   if (succ.n_succ) CUDA_TRY(ctx, cudaMemcpyAsync(R.succ_belief.data(), succ.succ_b, (size_t)succ.n_succ * 4, cudaMemcpyDeviceToHost, st));
   type_finish_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_type, V * (int64_t)B);
   LAUNCH_CHECK(ctx);
-  R.d_dist_cm = cols ? d_dist_cm : nullptr; R.d_type_cm = cols ? d_type_cm : nullptr; R.d_type = d_type; R.d_colpos = d_colpos;
+  R.d_dist_cm = d_dist_cm; R.d_type_cm = d_type_cm; R.d_type = d_type; R.d_colpos = d_colpos;
   R.colpos = colpos;
   R.col_dist.assign((size_t)B, std::vector<double>()); R.col_type.assign((size_t)B, std::vector<uint8_t>());
   R.dist = nullptr; R.type = nullptr;
   ctx->bel_node_vid.assign(node_vid, node_vid + V);
-  if (!cols || out_dist || out_type) {
-    int32_t rc = belief_download_full(ctx, d_dist, out_dist, out_type);
+  if (out_dist || out_type) {
+    int32_t rc = belief_download_full(ctx, nullptr, out_dist, out_type);
     if (rc) return rc;
   } else {
     CUDA_TRY(ctx, cudaStreamSynchronize(st));

@@ -71,9 +71,10 @@ __global__ void sf_count_kernel(const int32_t* __restrict__ col, const int32_t* 
   if (e < E) atomicAdd(&cnt[perm[col[e]]], 1);
 }
 // transposed records in the new numbering: row perm[v] lists (perm[u], norm2(u, v)); one warp per row u of the forward CSR
-__global__ void sf_fill_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy,
-                               const int32_t* __restrict__ perm, int64_t V, const int64_t* __restrict__ row_t, int32_t* __restrict__ cursor,
-                               int32_t* __restrict__ col_t, double* __restrict__ cost_t) {
+__global__ void sf_fill_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const int32_t* __restrict__ evid,
+                               const double2* __restrict__ xy, const int32_t* __restrict__ perm, int64_t V, const int64_t* __restrict__ row_t,
+                               int32_t* __restrict__ cursor, int32_t* __restrict__ col_t, double* __restrict__ cost_t,
+                               uint16_t* __restrict__ evid_t) {
   const int lane = threadIdx.x & 31;
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (u >= V) return;
@@ -86,6 +87,7 @@ __global__ void sf_fill_kernel(const int64_t* __restrict__ row_ptr, const int32_
     const int32_t pv = perm[v];
     const int64_t pos = row_t[pv] + atomicAdd(&cursor[pv], 1);
     col_t[pos] = pu;
+    if (evid) evid_t[pos] = (uint16_t)evid[e];
     cost_t[pos] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // norm2(u, v), common.rs:203-213
   }
 }
@@ -101,21 +103,10 @@ __global__ void sf_init_kernel(const int32_t* __restrict__ node_vid, const uint6
   const bool ok = node_vid ? ((validities[(int64_t)node_vid[order[pos]] * mask_words + (wg >> 6)] >> (wg & 63)) & 1) != 0 : true;
   dist[t] = ok ? INFINITY : -INFINITY;
 }
-// finals: value 0 (keeping the sign), dirty in that world, on the first worklist
-__global__ void sf_seed_kernel(const int32_t* __restrict__ fin_node, const int32_t* __restrict__ fin_world, int64_t n, const int32_t* __restrict__ perm,
-                               int64_t V, int words, double* __restrict__ dist, unsigned long long* __restrict__ dirty, int32_t* __restrict__ inq,
-                               int32_t* __restrict__ list, int32_t* __restrict__ counter) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t v = perm[fin_node[i]], w = fin_world[i];
-  double* d = dist + (int64_t)w * V + v;
-  *d = (__double_as_longlong(*d) < 0) ? -0.0 : 0.0;
-  atomicOr(&dirty[(int64_t)v * words + (w >> 6)], 1ull << (w & 63));
-  if (atomicExch(&inq[v], 1) == 0) list[atomicAdd(counter, 1)] = v;
-}
-
 struct SfArgs {
   const int64_t* row_t; const int32_t* col_t; const double* cost_t;
+  const uint16_t* evid_t;         // validity id of the transposed record's edge (nullable)
+  const uint64_t* cmask;          // [W][4] admissible validity ids per column (nullable: every edge admissible)
   double* dist; int64_t V; int32_t W, words;   // dist[w * V + v], v in Morton numbering
   unsigned long long* dirty[2];   // [V * words] each
   int32_t* inq[2];                // [V] each: node already on that round's worklist
@@ -224,10 +215,12 @@ __global__ void __launch_bounds__(256) sf_push_kernel(SfArgs a, int round) {
       int32_t u = 0;
       if (e < e1) {
         u = __ldg(a.col_t + e);
-        const double alt = __dadd_rn(__ldg(a.cost_t + e), dv);   // norm2(u, v) + dist[v], pto_graph.rs:293
+        const double alt = __dadd_rn(__ldg(a.cost_t + e), dv);   // norm2(u, v) + dist[v], pto_graph.rs:293 / belief_graph.rs:121-124
         double* du = a.dist + (int64_t)w * a.V + u;
         ++n_off;
-        if (alt < *du) {
+        bool admissible = true;
+        if (a.cmask) { const unsigned ev = a.evid_t[e]; admissible = (a.cmask[(int64_t)w * 4 + (ev >> 6)] >> (ev & 63)) & 1; }
+        if (admissible && alt < *du) {
           const unsigned long long bits = (unsigned long long)__double_as_longlong(alt);
           const unsigned long long old = atomicMin(reinterpret_cast<unsigned long long*>(du), bits);
           if (bits < old) {
@@ -267,64 +260,110 @@ __global__ void sf_out_kernel(const double* __restrict__ dist /* [W][V] Morton n
   const int64_t u = t - (int64_t)w * V;
   out[t] = fabs(dist[(int64_t)w * V + perm[u]]);
 }
+// ---- seeding: every entry that holds a finite value (finals, Observation values) is a source
+__global__ void sf_seed_all_kernel(SfArgs a) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool any = false;
+  if (v < a.V) {
+    for (int k = 0; k < a.words; ++k) {
+      unsigned long long m = 0;
+      for (int b = 0; b < 64 && k * 64 + b < a.W; ++b)
+        if (fabs(a.dist[(int64_t)(k * 64 + b) * a.V + v]) < INFINITY) m |= 1ull << b;
+      if (m) { a.dirty[0][v * a.words + k] = m; any = true; }
+    }
+    if (any) a.inq[0][v] = 1;
+  }
+  const unsigned fm = __ballot_sync(0xffffffffu, any);
+  if (fm) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&a.counter[0], __popc(fm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (any) a.list[0][base + __popc(fm & ((1u << lane) - 1u))] = (int32_t)v;
+  }
+}
+__global__ void sf_zero_finals_kernel(const int32_t* __restrict__ fin_node, const int32_t* __restrict__ fin_world, int64_t n,
+                                      const int32_t* __restrict__ perm, int64_t V, double* __restrict__ dist) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* d = dist + (int64_t)fin_world[i] * V + perm[fin_node[i]];
+  *d = (__double_as_longlong(*d) < 0) ? -0.0 : 0.0;   // (several finals may name the same entry: same value)
+}
 }  // namespace
 
-// All pointers are device pointers.  fin_node / fin_world: the finals of the worlds [wlo, wlo + W) as (node, local world) pairs.
-// out_wv receives rows [0, W) of the [world][node] table.  Uses ctx->scratch[5..10] as work space.
-int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d_col, const double* d_xy, int64_t V, int64_t E,
-                          const int32_t* d_node_vid, const uint64_t* d_validities, int32_t mask_words, int32_t wlo, int32_t W,
-                          const int32_t* d_fin_node, const int32_t* d_fin_world, int64_t n_fin, double* d_out_wv, int32_t* out_rounds,
-                          double* out_offers, cudaStream_t st) {
-  if (V > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "sssp: more than 2^31 nodes");
-  const int words = (W + 63) / 64;
-  // ---- Morton numbering (scratch[5]): order[pos] = node, perm[node] = pos
+// Morton numbering + transposed adjacency of a roadmap on the device (work space: scratch[5], scratch[6]; radix sort: scratch[8..10]).
+int32_t sf_build_graph(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d_col, const int32_t* d_evid, const double* d_xy, int64_t V,
+                       int64_t E, SfGraph* out, cudaStream_t st) {
+  if (V > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "value backups: more than 2^31 nodes");
   DevBuf& ob = ctx->scratch[5];
   CUDA_TRY(ctx, ob.ensure((size_t)V * 16 + 64 + 4 * 16));
   uint64_t* d_keys = ob.as<uint64_t>();
   uint32_t* d_order = (uint32_t*)(ob.as<char>() + (((size_t)V * 8 + 15) & ~(size_t)15));
   int32_t* d_perm = (int32_t*)((char*)d_order + (((size_t)V * 4 + 15) & ~(size_t)15));
   unsigned long long* d_box = (unsigned long long*)((char*)d_perm + (((size_t)V * 4 + 15) & ~(size_t)15));
-  {
-    const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_box, init, 32, cudaMemcpyHostToDevice, st));
-    sf_bbox_kernel<<<ctx->sm_count * 4, 256, 0, st>>>((const double2*)d_xy, V, d_box);
-    LAUNCH_CHECK(ctx);
-    sf_morton_kernel<<<div_up(V, 256), 256, 0, st>>>((const double2*)d_xy, V, d_box, d_keys, d_order);
-    LAUNCH_CHECK(ctx);
-    int32_t rc0 = radix_sort_pairs(ctx, d_keys, d_order, V, 32);   // (runs on ctx->stream == st; its work space is scratch[8..10])
-    if (rc0) return rc0;
-    sf_perm_kernel<<<div_up(V, 256), 256, 0, st>>>(d_order, V, d_perm);
-    LAUNCH_CHECK(ctx);
-  }
-  // ---- transposed adjacency (scratch[6])
+  const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_box, init, 32, cudaMemcpyHostToDevice, st));
+  sf_bbox_kernel<<<ctx->sm_count * 4, 256, 0, st>>>((const double2*)d_xy, V, d_box);
+  LAUNCH_CHECK(ctx);
+  sf_morton_kernel<<<div_up(V, 256), 256, 0, st>>>((const double2*)d_xy, V, d_box, d_keys, d_order);
+  LAUNCH_CHECK(ctx);
+  int32_t rc = radix_sort_pairs(ctx, d_keys, d_order, V, 32);   // (runs on ctx->stream == st)
+  if (rc) return rc;
+  sf_perm_kernel<<<div_up(V, 256), 256, 0, st>>>(d_order, V, d_perm);
+  LAUNCH_CHECK(ctx);
   DevBuf& tb = ctx->scratch[6];
-  CUDA_TRY(ctx, tb.ensure((size_t)(V + 1) * 8 + (size_t)E * 12 + (size_t)V * 4 + 4 * 16 + 64));
+  CUDA_TRY(ctx, tb.ensure((size_t)(V + 1) * 8 + (size_t)E * 14 + (size_t)V * 4 + 6 * 16 + 64));
   char* p = tb.as<char>();
   auto take = [&](size_t bytes) { char* q = p; p += (bytes + 15) & ~(size_t)15; return q; };
   int64_t* d_row_t = (int64_t*)take((size_t)(V + 1) * 8);
   double* d_cost_t = (double*)take((size_t)E * 8);
   int32_t* d_col_t = (int32_t*)take((size_t)E * 4 + 4);
+  uint16_t* d_evid_t = (uint16_t*)take((size_t)E * 2 + 4);
   int32_t* d_cnt = (int32_t*)take((size_t)V * 4);
+  double* d_sum = (double*)take(16);
   CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)V * 4, st));
   if (E > 0) {
     sf_count_kernel<<<div_up(E, 256), 256, 0, st>>>(d_col, d_perm, E, d_cnt);
     LAUNCH_CHECK(ctx);
   }
-  int32_t rc = scan_exclusive_i64(ctx, d_cnt, V, d_row_t);
+  rc = scan_exclusive_i64(ctx, d_cnt, V, d_row_t);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)V * 4, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_sum, 0, 8, st));
   if (E > 0) {
-    sf_fill_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, d_perm, V, d_row_t, d_cnt, d_col_t, d_cost_t);
+    sf_fill_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, d_evid, (const double2*)d_xy, d_perm, V, d_row_t, d_cnt, d_col_t, d_cost_t, d_evid_t);
+    LAUNCH_CHECK(ctx);
+    sf_sum_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_cost_t, E, d_sum);
     LAUNCH_CHECK(ctx);
   }
-  // ---- value table + frontier state (scratch[7])
+  double sum = 0.0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&sum, d_sum, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  out->V = V; out->E = E; out->row_t = d_row_t; out->col_t = d_col_t; out->cost_t = d_cost_t; out->evid_t = d_evid ? d_evid_t : nullptr;
+  out->order = d_order; out->perm = d_perm;
+  // delta of the near / far ordering = the mean edge length of the roadmap (one hop of a front).  Measured at PRM scale (1e6 nodes, 64
+  // worlds): delta = 0.5 / 0.75 / 1 / 1.5 / 2 / 4 mean edge lengths -> 1.05 / 1.12 / 1.27 / 2.6 / 5.5 / 13.9 full sweeps' worth of pairs in
+  // 592 / 400 / 304 / 240 / 224 / 240 rounds; no ordering at all: 19.1
+  out->delta = E > 0 && sum > 0.0 && std::isfinite(sum) ? sum / (double)E : 1.0;
+  return PORRT_OK;
+}
+
+// Relaxes W value columns to their fixed point.  dist[w * V + pos] (Morton numbering) holds the initial values on entry -- +inf, the
+// sources' values, the sign bit on every entry that must not be relaxed -- and the result on exit (signs kept).  cmask (nullable):
+// [W][4] validity ids an edge must carry to be admissible in column w (needs g.evid_t).  Work space: scratch[7].
+int32_t sf_relax(porrt_ctx* ctx, const SfGraph& g, double* dist, int32_t W, const uint64_t* cmask, int32_t* out_rounds, double* out_offers,
+                 cudaStream_t st) {
+  const int64_t V = g.V;
+  const int words = (W + 63) / 64;
+  if (W <= 0) { if (out_rounds) *out_rounds = 0; if (out_offers) *out_offers = 0.0; return PORRT_OK; }
+  const int64_t pair_cap = std::min<int64_t>(V * (int64_t)W, std::max<int64_t>(4 << 20, 4 * V));
   DevBuf& sb = ctx->scratch[7];
-  CUDA_TRY(ctx, sb.ensure((size_t)V * W * 8 + 2 * (size_t)V * words * 8 + 4 * (size_t)V * 4 + 192 + 14 * 16 +
-                          (size_t)std::min<int64_t>(V * (int64_t)W, std::max<int64_t>(4 << 20, 4 * V)) * 8));
-  p = sb.as<char>();
+  CUDA_TRY(ctx, sb.ensure(2 * (size_t)V * words * 8 + 4 * (size_t)V * 4 + 192 + 14 * 16 + (size_t)pair_cap * 8));
+  char* p = sb.as<char>();
+  auto take = [&](size_t bytes) { char* q = p; p += (bytes + 15) & ~(size_t)15; return q; };
   SfArgs a = {};
-  a.row_t = d_row_t; a.col_t = d_col_t; a.cost_t = d_cost_t; a.V = V; a.W = W; a.words = words;
-  a.dist = (double*)take((size_t)V * W * 8);
+  a.row_t = g.row_t; a.col_t = g.col_t; a.cost_t = g.cost_t; a.evid_t = g.evid_t; a.cmask = cmask; a.V = V; a.W = W; a.words = words;
+  a.dist = dist; a.delta = g.delta;
   a.dirty[0] = (unsigned long long*)take((size_t)V * words * 8);
   a.dirty[1] = (unsigned long long*)take((size_t)V * words * 8);
   a.inq[0] = (int32_t*)take((size_t)V * 4); a.inq[1] = (int32_t*)take((size_t)V * 4);
@@ -334,35 +373,16 @@ int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d
   a.thr = (double*)take(32);
   a.min_far = (unsigned long long*)take(32);
   a.pair_count = (int32_t*)take(16);
-  a.pair_cap = (int32_t)std::min<int64_t>(V * (int64_t)W, std::max<int64_t>(4 << 20, 4 * V));
-  a.pairs = (int2*)take((size_t)a.pair_cap * 8);
+  a.pair_cap = (int32_t)pair_cap;
+  a.pairs = (int2*)take((size_t)pair_cap * 8);
   CUDA_TRY(ctx, cudaMemsetAsync(a.dirty[0], 0, 2 * (((size_t)V * words * 8 + 15) & ~(size_t)15), st));
   CUDA_TRY(ctx, cudaMemsetAsync(a.inq[0], 0, 2 * (((size_t)V * 4 + 15) & ~(size_t)15), st));
   CUDA_TRY(ctx, cudaMemsetAsync(a.counter, 0, 32 + 32, st));   // counters, offers, thresholds (0.0)
   CUDA_TRY(ctx, cudaMemsetAsync(a.pair_count, 0, 16, st));
-  {
-    // delta = the mean edge length of the roadmap (one hop of a front); min_far starts at +inf
-    const unsigned long long inf3[4] = {0x7ff0000000000000ull, 0x7ff0000000000000ull, 0x7ff0000000000000ull, 0};
-    CUDA_TRY(ctx, cudaMemcpyAsync(a.min_far, inf3, 32, cudaMemcpyHostToDevice, st));
-    double* d_sum = (double*)take(16);
-    CUDA_TRY(ctx, cudaMemsetAsync(d_sum, 0, 8, st));
-    if (E > 0) {
-      sf_sum_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_cost_t, E, d_sum);
-      LAUNCH_CHECK(ctx);
-    }
-    double sum = 0.0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&sum, d_sum, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    // measured at PRM scale (1e6 nodes, 64 worlds): delta = 0.5 / 0.75 / 1 / 1.5 / 2 / 4 mean edge lengths -> 1.05 / 1.12 / 1.27 / 2.6 / 5.5 /
-    // 13.9 full sweeps' worth of pairs in 592 / 400 / 304 / 240 / 224 / 240 rounds; no ordering at all: 19.1
-    a.delta = E > 0 && sum > 0.0 && std::isfinite(sum) ? sum / (double)E : 1.0;
-  }
-  sf_init_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(d_node_vid, d_validities, mask_words, d_order, V, W, wlo, a.dist);
+  const unsigned long long inf3[4] = {0x7ff0000000000000ull, 0x7ff0000000000000ull, 0x7ff0000000000000ull, 0};
+  CUDA_TRY(ctx, cudaMemcpyAsync(a.min_far, inf3, 32, cudaMemcpyHostToDevice, st));
+  sf_seed_all_kernel<<<div_up(V, 256), 256, 0, st>>>(a);
   LAUNCH_CHECK(ctx);
-  if (n_fin > 0) {
-    sf_seed_kernel<<<div_up(n_fin, 256), 256, 0, st>>>(d_fin_node, d_fin_world, n_fin, d_perm, V, words, a.dist, a.dirty[0], a.inq[0], a.list[0], a.counter);
-    LAUNCH_CHECK(ctx);
-  }
   // ---- rounds: a fixed grid strides over the worklist, whose length lives on the device; the host checks every CHECK rounds
   const int grid = ctx->sm_count * 8;
   const int CHECK = 16;
@@ -378,10 +398,8 @@ int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d
     CUDA_TRY(ctx, cudaMemcpyAsync(counters, a.counter, 12, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (counters[round % 3] == 0) break;   // the worklist of the next round is empty: nothing is dirty any more
-    if (round > 64 * V + 1024) return porrt_fail(ctx, PORRT_ERR_CUDA, "sssp: no convergence");
+    if (round > 64 * V + 1024) return porrt_fail(ctx, PORRT_ERR_CUDA, "value backups: no convergence");
   }
-  sf_out_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(a.dist, d_perm, V, W, d_out_wv);
-  LAUNCH_CHECK(ctx);
   if (out_rounds) *out_rounds = round;
   if (out_offers) {
     unsigned long long off = 0;
@@ -389,5 +407,33 @@ int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     *out_offers = (double)off;
   }
+  return PORRT_OK;
+}
+
+// plan_qmdp's world columns.  All pointers are device pointers.  fin_node / fin_world: the finals of the worlds [wlo, wlo + W) as
+// (node, local world) pairs.  out_wv receives rows [0, W) of the [world][node] table.  Work space: scratch[5..10].
+int32_t sssp_frontier_run(porrt_ctx* ctx, const int64_t* d_row, const int32_t* d_col, const double* d_xy, int64_t V, int64_t E,
+                          const int32_t* d_node_vid, const uint64_t* d_validities, int32_t mask_words, int32_t wlo, int32_t W,
+                          const int32_t* d_fin_node, const int32_t* d_fin_world, int64_t n_fin, double* d_out_wv, int32_t* out_rounds,
+                          double* out_offers, cudaStream_t st) {
+  SfGraph g;
+  int32_t rc = sf_build_graph(ctx, d_row, d_col, nullptr, d_xy, V, E, &g, st);
+  if (rc) return rc;
+  // the value table lives behind the frontier state of sf_relax in scratch[7]: sized here so that sf_relax's ensure() does not move it
+  const int words = (W + 63) / 64;
+  const int64_t pair_cap = std::min<int64_t>(V * (int64_t)W, std::max<int64_t>(4 << 20, 4 * V));
+  const size_t state_bytes = 2 * (size_t)V * words * 8 + 4 * (size_t)V * 4 + 192 + 14 * 16 + (size_t)pair_cap * 8;
+  CUDA_TRY(ctx, ctx->scratch[7].ensure(state_bytes + (size_t)V * W * 8 + 64));
+  double* dist = (double*)(ctx->scratch[7].as<char>() + ((state_bytes + 63) & ~(size_t)63));
+  sf_init_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(d_node_vid, d_validities, mask_words, g.order, V, W, wlo, dist);
+  LAUNCH_CHECK(ctx);
+  if (n_fin > 0) {
+    sf_zero_finals_kernel<<<div_up(n_fin, 256), 256, 0, st>>>(d_fin_node, d_fin_world, n_fin, g.perm, V, dist);
+    LAUNCH_CHECK(ctx);
+  }
+  rc = sf_relax(ctx, g, dist, W, nullptr, out_rounds, out_offers, st);
+  if (rc) return rc;
+  sf_out_kernel<<<div_up(V * (int64_t)W, 256), 256, 0, st>>>(dist, g.perm, V, W, d_out_wv);
+  LAUNCH_CHECK(ctx);
   return PORRT_OK;
 }

@@ -26,3 +26,8 @@ for rep in range(4):
     vis, st = pmap.visible_zones(xy); t2=time.perf_counter()
     plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, fm, beliefs=bel, copy=(True if rep == 0 else False if rep == 1 else None)); t3=time.perf_counter()
     print("reachable %.1f ms, visible %.1f ms, plan(with beliefs given) %.1f ms, phases %s sweeps %d" % (1e3*(t1-t0),1e3*(t2-t1),1e3*(t3-t2),[round(float(x),1) for x in plan.phase_ms], plan.sweeps))
+ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 1)
+for rep in range(2):
+    t2 = time.perf_counter(); plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, fm, beliefs=bel, copy=None); t3 = time.perf_counter()
+    print("global-memory frontier path: plan %.1f ms, phases %s rounds %d, device %.1f ms, pairs %.3g" % (1e3 * (t3 - t2), [round(float(x), 1) for x in plan.phase_ms], plan.sweeps, ctx.last_phase_ms()[0], ctx.last_phase_ms()[1]))
+ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 0)
