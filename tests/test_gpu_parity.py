@@ -1393,3 +1393,22 @@ def test_refine_solution_partial_shortcut(ctx, kind, Z, n_min):
         np.testing.assert_array_equal(np.nonzero(got["is_leaf"])[0], want.leafs)
         assert got["expected_cost"] == want.expected_costs, n_it
     assert got["commits"] > 0 and got["expected_cost"] <= plan.expected_cost + 1e-9
+
+
+def test_value_backups_on_a_roadmap_beyond_shared_memory(ctx):
+    """27 k roadmap nodes: a value column no longer fits in shared memory, so belief-space planning and plan_qmdp run through the
+    frontier relaxation over global memory (sssp_frontier.cu) WITHOUT any option being set -- against the oracle, bit for bit."""
+    Z = 3
+    occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+    zp = omap.zone_positions()
+    goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
+    pto = _grow_pto(omap, (0.0, -0.9), goals, 0.05, 5.0, 29000)
+    assert pto.graph.n_nodes() > 26000
+    plan, want, typ = _belief_compare(ctx, omap, pmap, pto, [0.5, 0.3, 0.2])
+    assert len(plan.beliefs) == 7 and np.isfinite(want[0])
+    xy, nvid, rp, col, ev = pto.graph.export(0)
+    finals = [pto.reach.get_final_nodes_for_world(w) for w in range(Z)]
+    got, rounds = P.dijkstra_worlds(ctx, rp, col, xy, nvid, pmap.world_validities_words(), finals)
+    np.testing.assert_array_equal(got, pto.plan_qmdp())
+    assert rounds > 0
