@@ -34,15 +34,19 @@ static double now_ms() {
 // with; all of them descend one level per round (so the split axis is the round parity), and the child slot (node, side)
 // goes to the smallest id that wants it (atomicMin) -- exactly the point that sequential insertion would have put there.
 // Subtree sizes are counted on the way down; ranks follow top-down, one depth per launch.
+// axis < 0: the split axis is the parity of the depth of the node the point is compared with (points sit at different depths after
+// the two-phase start below); axis >= 0: all points are at the same depth, the round's parity
 template <bool AGGREGATE>
 __global__ void kd_descend_kernel(const double2* __restrict__ xy, int64_t n, int axis, const int32_t* __restrict__ cur,
-                                  int32_t* __restrict__ child, int32_t* __restrict__ size, uint8_t* __restrict__ side) {
+                                  int32_t* __restrict__ child, int32_t* __restrict__ size, uint8_t* __restrict__ side,
+                                  const int32_t* __restrict__ node_depth = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t c = i < n ? cur[i] : -1;
   int s = 0;
   if (c >= 0) {
     const double2 p = xy[i], q = xy[c];
-    s = (axis ? p.y < q.y : p.x < q.x) ? 0 : 1;   // strictly-less goes left (nearest_neighbor.rs:32)
+    const int ax = axis >= 0 ? axis : (node_depth[c] & 1);
+    s = (ax ? p.y < q.y : p.x < q.x) ? 0 : 1;   // strictly-less goes left (nearest_neighbor.rs:32)
     side[i] = (uint8_t)s;
   }
   if (AGGREGATE) {
@@ -61,16 +65,55 @@ __global__ void kd_descend_kernel(const double2* __restrict__ xy, int64_t n, int
     atomicAdd(&size[c], 1);
   }
 }
-__global__ void kd_place_kernel(int64_t n, int depth, int32_t* __restrict__ cur, const int32_t* __restrict__ child,
+__global__ void kd_place_kernel(int64_t n, int32_t* __restrict__ cur, const int32_t* __restrict__ child,
                                 const uint8_t* __restrict__ side, int32_t* __restrict__ parent, int32_t* __restrict__ node_depth,
-                                int32_t* __restrict__ remaining) {
+                                int32_t* __restrict__ remaining, int32_t* __restrict__ max_depth) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t placed_at = 0;
+  if (i < n) {
+    const int32_t c = cur[i];
+    if (c >= 0) {
+      const int32_t w = child[2 * (int64_t)c + side[i]];
+      if (w == (int32_t)i) { parent[i] = c; placed_at = node_depth[c] + 1; node_depth[i] = placed_at; cur[i] = -1; }
+      else { cur[i] = w; if (remaining) atomicAdd(remaining, 1); }
+    }
+  }
+  placed_at = __reduce_max_sync(0xffffffffu, placed_at);
+  if (placed_at > 0 && (threadIdx.x & 31) == 0) atomicMax(max_depth, placed_at);
+}
+// Two-phase start (single trees of many points): the tree of the first M points does not depend on the later ones, so it is built
+// first (the same rounds, on M points); then every later point walks down that finished top tree on its own -- read-only, no
+// atomics, no barrier per level -- to the node where it would next compete for an empty child slot.  The rounds that follow work
+// on ~n / M points per slot instead of n points on a handful of slots (those first 14 rounds were 1.6 of the rank's 3 ms at 1e6).
+__global__ void kd_walk_kernel(const double2* __restrict__ xy, int64_t first, int64_t n, const int32_t* __restrict__ child,
+                               const int32_t* __restrict__ node_depth, int32_t* __restrict__ cur, int32_t* __restrict__ exits) {
+  const int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int32_t c = cur[i];
-  if (c < 0) return;
-  const int32_t w = child[2 * (int64_t)c + side[i]];
-  if (w == (int32_t)i) { parent[i] = c; node_depth[i] = depth + 1; cur[i] = -1; }
-  else { cur[i] = w; if (remaining) atomicAdd(remaining, 1); }
+  const double2 p = xy[i];
+  int32_t c = 0;
+  for (;;) {
+    const double2 q = xy[c];
+    const int s = ((node_depth[c] & 1) ? p.y < q.y : p.x < q.x) ? 0 : 1;
+    const int32_t w = child[2 * (int64_t)c + s];
+    if (w == 0x7fffffff) break;
+    c = w;
+  }
+  cur[i] = c;
+  atomicAdd(&exits[c], 1);
+}
+// subtree sizes of the top tree: the later points that pass THROUGH a top node (they leave the top tree below one of its
+// children) were never counted by a round at that node; one pass per depth, deepest first.  up[c] = later points below c.
+__global__ void kd_top_sizes_kernel(int64_t m, int depth, const int32_t* __restrict__ node_depth, const int32_t* __restrict__ child,
+                                    const int32_t* __restrict__ exits, int32_t* __restrict__ up, int32_t* __restrict__ size) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m || node_depth[c] != depth) return;
+  int32_t through = 0;
+  for (int s = 0; s < 2; ++s) {
+    const int32_t ch = child[2 * c + s];
+    if (ch != 0x7fffffff) through += up[ch];
+  }
+  up[c] = exits[c] + through;
+  size[c] += through;
 }
 __global__ void kd_rank_kernel(int64_t n, int depth, const int32_t* __restrict__ node_depth, const int32_t* __restrict__ parent,
                                const uint8_t* __restrict__ side, const int32_t* __restrict__ child, const int32_t* __restrict__ size,
@@ -111,34 +154,65 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
 #define KD_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(#expr, _e); } while (0)
 #define KD_LAUNCHED() do { ++launches; KD_TRY(cudaGetLastError()); } while (0)
   if (n <= 0) return PORRT_OK;
-  KD_TRY(ctx->kd_buf.ensure((size_t)n * 4 * 6 + (size_t)n + 64));
+  KD_TRY(ctx->kd_buf.ensure((size_t)n * 4 * 8 + (size_t)n + 128));
   char* b = ctx->kd_buf.as<char>();
   int32_t* cur = (int32_t*)b; b += (size_t)n * 4;
   int32_t* child = (int32_t*)b; b += (size_t)n * 8;
   int32_t* size = (int32_t*)b; b += (size_t)n * 4;
   int32_t* parent = (int32_t*)b; b += (size_t)n * 4;
   int32_t* node_depth = (int32_t*)b; b += (size_t)n * 4;
+  int32_t* exits = (int32_t*)b; b += (size_t)n * 4;     // two-phase start only
+  int32_t* up = (int32_t*)b; b += (size_t)n * 4;
   int32_t* remaining = (int32_t*)b; b += 16;
+  int32_t* max_depth = remaining + 1;
   uint8_t* side = (uint8_t*)b;
   const int blocks = div_up(n, 256);
   kd_init_kernel<<<blocks, 256, 0, st>>>(n, cur, child, size, node_depth, out_rank_dev, root_of_dev);
   KD_LAUNCHED();
-  int depth = 0;
-  for (;; ++depth) {
-    if ((depth & 3) == 0) KD_TRY(cudaMemsetAsync(remaining, 0, 4, st));
-    if (depth < 14) kd_descend_kernel<true><<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
-    else kd_descend_kernel<false><<<blocks, 256, 0, st>>>((const double2*)xy_dev, n, depth & 1, cur, child, size, side);
+  KD_TRY(cudaMemsetAsync(remaining, 0, 8, st));
+  // level-synchronous rounds over the first m points until all of them are placed; lockstep = every unplaced point is at depth `d`
+  auto rounds = [&](int64_t m, bool lockstep) -> int32_t {
+    const int mb = div_up(m, 256);
+    for (int d = 0;; ++d) {
+      if ((d & 3) == 0) KD_TRY(cudaMemsetAsync(remaining, 0, 4, st));
+      if (lockstep && d < 14 && m > 8192) kd_descend_kernel<true><<<mb, 256, 0, st>>>((const double2*)xy_dev, m, d & 1, cur, child, size, side);
+      else kd_descend_kernel<false><<<mb, 256, 0, st>>>((const double2*)xy_dev, m, lockstep ? (d & 1) : -1, cur, child, size, side, node_depth);
+      KD_LAUNCHED();
+      kd_place_kernel<<<mb, 256, 0, st>>>(m, cur, child, side, parent, node_depth, (d & 3) == 3 ? remaining : nullptr, max_depth);
+      KD_LAUNCHED();
+      if ((d & 3) != 3) continue;      // the host looks at the number of unplaced points every fourth level only
+      int32_t rem = 0;
+      KD_TRY(cudaMemcpyAsync(&rem, remaining, 4, cudaMemcpyDeviceToHost, st));
+      KD_TRY(cudaStreamSynchronize(st));
+      if (rem == 0) return PORRT_OK;
+      if (d > m + 4) return fail("no convergence", cudaErrorUnknown);
+    }
+  };
+  const int64_t KD_TOP = 65536;
+  const bool two_phase = !root_of_dev && n >= 8 * KD_TOP;
+  if (two_phase) {
+    int32_t rc = rounds(KD_TOP, true);                  // the top tree: points 0 .. KD_TOP-1 (later points have cur == root but are not looked at)
+    if (rc) return rc;
+    int32_t top_depth = 0;
+    KD_TRY(cudaMemcpyAsync(&top_depth, max_depth, 4, cudaMemcpyDeviceToHost, st));
+    KD_TRY(cudaMemsetAsync(exits, 0, (size_t)KD_TOP * 4, st));
+    kd_walk_kernel<<<div_up(n - KD_TOP, 256), 256, 0, st>>>((const double2*)xy_dev, KD_TOP, n, child, node_depth, cur, exits);
     KD_LAUNCHED();
-    kd_place_kernel<<<blocks, 256, 0, st>>>(n, depth, cur, child, side, parent, node_depth, (depth & 3) == 3 ? remaining : nullptr);
-    KD_LAUNCHED();
-    if ((depth & 3) != 3) continue;      // the host looks at the number of unplaced points every fourth level only
-    int32_t rem = 0;
-    KD_TRY(cudaMemcpyAsync(&rem, remaining, 4, cudaMemcpyDeviceToHost, st));
     KD_TRY(cudaStreamSynchronize(st));
-    if (rem == 0) break;
-    if (depth > n + 4) return fail("no convergence", cudaErrorUnknown);
+    for (int d = top_depth; d >= 0; --d) {
+      kd_top_sizes_kernel<<<div_up(KD_TOP, 256), 256, 0, st>>>(KD_TOP, d, node_depth, child, exits, up, size);
+      KD_LAUNCHED();
+    }
+    rc = rounds(n, false);                              // everybody else, from where the walk left them
+    if (rc) return rc;
+  } else {
+    int32_t rc = rounds(n, true);
+    if (rc) return rc;
   }
-  for (int d = 1; d <= depth + 1; ++d) {
+  int32_t depth = 0;
+  KD_TRY(cudaMemcpyAsync(&depth, max_depth, 4, cudaMemcpyDeviceToHost, st));
+  KD_TRY(cudaStreamSynchronize(st));
+  for (int d = 1; d <= depth; ++d) {
     kd_rank_kernel<<<blocks, 256, 0, st>>>(n, d, node_depth, parent, side, child, size, out_rank_dev);
     KD_LAUNCHED();
   }

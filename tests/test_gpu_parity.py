@@ -339,6 +339,21 @@ def test_kd_preorder_rank_device(ctx):
     np.testing.assert_array_equal(P.KdTree(ctx, chain).preorder_rank(), np.arange(2000))
 
 
+def test_kd_preorder_rank_two_phase_start(ctx):
+    """single trees of >= 8 * 65536 points are built top tree first, then everybody else from where a read-only walk leaves
+    them (graph.cu: kd_walk_kernel); the order must still be the one of sequential insertion (nearest_neighbor.rs:29-46)"""
+    rng = np.random.default_rng(18)
+    n = 600_000
+    pts = rng.uniform(-1, 1, (n, 2))
+    pts[70_000:70_500] = pts[0:500]                       # duplicates of top-tree points among the later ones
+    pts[200_000:200_400] = pts[100_000:100_400]           # duplicates among the later points
+    pts[300_000:301_000, 0] = pts[5, 0]                   # a run with a top-tree node's x
+    pts[400_000:400_800] = np.round(pts[400_000:400_800] * 8) / 8
+    rank = P.KdTree(ctx, pts).preorder_rank()
+    order = _oracle_tree(pts).nearest_neighbors([0.0, 0.0], 10.0)
+    np.testing.assert_array_equal(np.argsort(rank), order)
+
+
 def test_radius_threshold_boundary(ctx):
     """inclusive `<=` on the sqrt-ed distance: hits at exactly r, misses one ulp below"""
     pts = np.array([[0.0, 0.0], [3.0, 4.0], [1.0, 1.0], [-0.3, 0.4]])
