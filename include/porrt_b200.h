@@ -47,6 +47,7 @@ extern "C" {
 #define PORRT_NODE_UNKNOWN 0
 #define PORRT_NODE_ACTION 1
 #define PORRT_NODE_OBSERVATION 2
+#define PORRT_MAX_STATE_DIM 16 /* porrt_*_nd entry points */
 
 typedef struct porrt_ctx porrt_ctx;
 
@@ -231,6 +232,16 @@ int32_t porrt_conditional_dijkstra(porrt_ctx* ctx, int64_t V, const int64_t* row
                                    const uint8_t* node_type, const int32_t* belief_id, const double* beliefs, int32_t B,
                                    int32_t n_worlds, const int32_t* finals, int32_t n_finals, double* out_dist,
                                    int32_t* out_sweeps /* nullable */);
+/* The same for states of `dim` doubles (1 <= dim <= PORRT_MAX_STATE_DIM; xy[dim * k ..]): the reference's planner is generic over
+ * the state dimension (pto_c.rs:226-241 instantiates N = 2, 3, 7, 9); norm2 sums dx * dx in dimension order (common.rs:203-213). */
+int32_t porrt_conditional_dijkstra_nd(porrt_ctx* ctx, int32_t dim, int64_t V, const int64_t* row_ptr, const int32_t* col,
+                                      const double* xy, const uint8_t* node_type, const int32_t* belief_id, const double* beliefs,
+                                      int32_t B, int32_t n_worlds, const int32_t* finals, int32_t n_finals, double* out_dist,
+                                      int32_t* out_sweeps /* nullable */);
+int32_t porrt_extract_policy_graph_nd(porrt_ctx* ctx, int32_t dim, int64_t V, const int64_t* row_ptr, const int32_t* col,
+                                      const double* xy, const uint8_t* node_type, const int32_t* belief_id, const double* beliefs,
+                                      int32_t B, int32_t n_worlds, const double* dist, int32_t* out_belief_node, int32_t* out_parent,
+                                      uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost);
 /* extract_policy (belief_graph.rs:184-267) on the same explicit graph and the dist of porrt_conditional_dijkstra: host walk from
  * belief node 0.  Policy nodes in creation order: out_belief_node[k], out_parent[k] (-1 = root), out_is_leaf[k].
  * PORRT_ERR_PANIC where the reference's asserts (:250, :261) fire; PORRT_ERR_CAPACITY (with *out_n) when cap is too small. */

@@ -67,6 +67,8 @@ SIGNATURES = {
     "porrt_extract_policy": (i32, [vp, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),
     "porrt_conditional_dijkstra": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, pp(i32)]),
     "porrt_extract_policy_graph": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),
+    "porrt_conditional_dijkstra_nd": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, pp(i32)]),
+    "porrt_extract_policy_graph_nd": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, pp(i64), pp(f64)]),
     "porrt_mmprm_plan": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, pp(i64), pp(i32), vp]),
     "porrt_mmprm_fetch_graph": (i32, [vp, vp, vp, i64, vp, vp]),
     "porrt_qmdp_react": (i32, [vp, i64, vp, vp, vp, i32, vp, i64, vp, i32, f64, vp, vp, i64, pp(i64), pp(i64)]),

@@ -23,21 +23,24 @@
 namespace {
 
 // per CSR edge u -> v: cost = norm2(state u, state v); p = transition_probability(belief u, belief v) for Observation rows
-__global__ void bx_edge_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double2* __restrict__ xy,
+// (states of `dim` doubles; norm2 accumulates dx * dx in dimension order from 0.0, common.rs:203-213 -- 0.0 + x is exact, so the
+// two-dimensional case is the dx*dx + dy*dy it always was)
+__global__ void bx_edge_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ xy, int dim,
                                const uint8_t* __restrict__ type, const int32_t* __restrict__ belief_id, const double* __restrict__ beliefs,
                                int nw, int64_t V, double* __restrict__ cost, double* __restrict__ prob, uint8_t* __restrict__ frozen) {
   const int lane = threadIdx.x & 31;
   const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (u >= V) return;
-  const double2 a = xy[u];
+  const double* a = xy + u * dim;
   const uint8_t ty = type[u];
   const double* bu = beliefs + (int64_t)belief_id[u] * nw;
   bool bad = false;
   for (int64_t e = row_ptr[u] + lane; e < row_ptr[u + 1]; e += 32) {
     const int32_t v = col[e];
-    const double2 c = xy[v];
-    const double dx = __dsub_rn(c.x, a.x), dy = __dsub_rn(c.y, a.y);
-    cost[e] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    const double* c = xy + (int64_t)v * dim;
+    double d2 = 0.0;
+    for (int k = 0; k < dim; ++k) { const double dx = __dsub_rn(c[k], a[k]); d2 = __dadd_rn(d2, __dmul_rn(dx, dx)); }
+    cost[e] = __dsqrt_rn(d2);
     double p = 0.0;
     if (ty == PORRT_NODE_OBSERVATION) {
       const double* bv = beliefs + (int64_t)belief_id[v] * nw;
@@ -99,7 +102,8 @@ __global__ void bx_finals_kernel(double* __restrict__ dist, const int32_t* __res
 }
 
 bool graph_args_ok(int64_t V, const int64_t* row_ptr, const int32_t* col, const double* xy, const uint8_t* type,
-                   const int32_t* belief_id, const double* beliefs, int32_t B, int32_t nw) {
+                   const int32_t* belief_id, const double* beliefs, int32_t B, int32_t nw, int32_t dim = 2) {
+  if (dim <= 0 || dim > PORRT_MAX_STATE_DIM) return false;
   if (V <= 0 || !row_ptr || !xy || !type || !belief_id || !beliefs || B <= 0 || nw <= 0) return false;
   if (row_ptr[0] != 0 || (row_ptr[V] > 0 && !col)) return false;
   for (int64_t u = 0; u < V; ++u) {
@@ -115,8 +119,15 @@ PORRT_API int32_t porrt_conditional_dijkstra(porrt_ctx* ctx, int64_t V, const in
                                              const uint8_t* node_type, const int32_t* belief_id, const double* beliefs, int32_t B,
                                              int32_t n_worlds, const int32_t* finals, int32_t n_finals, double* out_dist,
                                              int32_t* out_sweeps) {
+  return porrt_conditional_dijkstra_nd(ctx, 2, V, row_ptr, col, xy, node_type, belief_id, beliefs, B, n_worlds, finals, n_finals, out_dist, out_sweeps);
+}
+
+PORRT_API int32_t porrt_conditional_dijkstra_nd(porrt_ctx* ctx, int32_t dim, int64_t V, const int64_t* row_ptr, const int32_t* col,
+                                                const double* xy, const uint8_t* node_type, const int32_t* belief_id, const double* beliefs,
+                                                int32_t B, int32_t n_worlds, const int32_t* finals, int32_t n_finals, double* out_dist,
+                                                int32_t* out_sweeps) {
   CTX_CHECK(ctx);
-  if (!out_dist || n_finals < 0 || (n_finals > 0 && !finals) || !graph_args_ok(V, row_ptr, col, xy, node_type, belief_id, beliefs, B, n_worlds))
+  if (!out_dist || n_finals < 0 || (n_finals > 0 && !finals) || !graph_args_ok(V, row_ptr, col, xy, node_type, belief_id, beliefs, B, n_worlds, dim))
     return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "conditional_dijkstra: bad arguments");
   if (V > 0x7fffffff) return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "conditional_dijkstra: more than 2^31 belief nodes");
   for (int32_t k = 0; k < n_finals; ++k)
@@ -125,12 +136,12 @@ PORRT_API int32_t porrt_conditional_dijkstra(porrt_ctx* ctx, int64_t V, const in
   cudaStream_t st = ctx->stream;
   const int64_t E = row_ptr[V];
   DevBuf& g = ctx->scratch[3];
-  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 20 + (size_t)V * (16 + 8 + 4 + 2) + (size_t)B * n_worlds * 8 + (size_t)n_finals * 4 + 1024;
+  const size_t need = (size_t)(V + 1) * 8 + (size_t)E * 20 + (size_t)V * ((size_t)dim * 8 + 16 + 8 + 4 + 2) + (size_t)B * n_worlds * 8 + (size_t)n_finals * 4 + 1024;
   CUDA_TRY(ctx, g.ensure(need));
   char* b = g.as<char>();
   auto take = [&](size_t bytes) { char* p = b; b += (bytes + 15) & ~(size_t)15; return p; };
   int64_t* d_row = (int64_t*)take((size_t)(V + 1) * 8);
-  double* d_xy = (double*)take((size_t)V * 16);
+  double* d_xy = (double*)take((size_t)V * dim * 8);
   double* d_cost = (double*)take((size_t)E * 8);
   double* d_prob = (double*)take((size_t)E * 8);
   double* d_dist = (double*)take((size_t)V * 8);
@@ -143,14 +154,14 @@ PORRT_API int32_t porrt_conditional_dijkstra(porrt_ctx* ctx, int64_t V, const in
   uint8_t* d_frozen = (uint8_t*)take((size_t)V);
   CUDA_TRY(ctx, cudaMemcpyAsync(d_row, row_ptr, (size_t)(V + 1) * 8, cudaMemcpyHostToDevice, st));
   if (E) CUDA_TRY(ctx, cudaMemcpyAsync(d_col, col, (size_t)E * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_xy, xy, (size_t)V * dim * 8, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_bid, belief_id, (size_t)V * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_type, node_type, (size_t)V, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_beliefs, beliefs, (size_t)B * n_worlds * 8, cudaMemcpyHostToDevice, st));
   if (n_finals) CUDA_TRY(ctx, cudaMemcpyAsync(d_finals, finals, (size_t)n_finals * 4, cudaMemcpyHostToDevice, st));
   const int32_t flags0[2] = {0, 0x7fffffff};
   CUDA_TRY(ctx, cudaMemcpyAsync(d_flags, flags0, 8, cudaMemcpyHostToDevice, st));
-  bx_edge_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, (const double2*)d_xy, d_type, d_bid, d_beliefs, n_worlds, V, d_cost, d_prob, d_frozen);
+  bx_edge_kernel<<<div_up(V * 32, 256), 256, 0, st>>>(d_row, d_col, d_xy, dim, d_type, d_bid, d_beliefs, n_worlds, V, d_cost, d_prob, d_frozen);
   LAUNCH_CHECK(ctx);
   bx_init_kernel<<<div_up(V, 256), 256, 0, st>>>(d_dist, V, d_finals, n_finals);
   LAUNCH_CHECK(ctx);
@@ -193,14 +204,22 @@ PORRT_API int32_t porrt_extract_policy_graph(porrt_ctx* ctx, int64_t V, const in
                                              const uint8_t* node_type, const int32_t* belief_id, const double* beliefs, int32_t B,
                                              int32_t n_worlds, const double* dist, int32_t* out_belief_node, int32_t* out_parent,
                                              uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost) {
+  return porrt_extract_policy_graph_nd(ctx, 2, V, row_ptr, col, xy, node_type, belief_id, beliefs, B, n_worlds, dist, out_belief_node, out_parent,
+                                       out_is_leaf, cap, out_n, out_expected_cost);
+}
+
+PORRT_API int32_t porrt_extract_policy_graph_nd(porrt_ctx* ctx, int32_t dim, int64_t V, const int64_t* row_ptr, const int32_t* col,
+                                                const double* xy, const uint8_t* node_type, const int32_t* belief_id, const double* beliefs,
+                                                int32_t B, int32_t n_worlds, const double* dist, int32_t* out_belief_node, int32_t* out_parent,
+                                                uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost) {
   CTX_CHECK(ctx);
   if (V <= 0) return porrt_fail(ctx, PORRT_ERR_PANIC, "no belief state graph! (belief_graph.rs:186)");
-  if (!dist || !graph_args_ok(V, row_ptr, col, xy, node_type, belief_id, beliefs, B, n_worlds))
+  if (!dist || !graph_args_ok(V, row_ptr, col, xy, node_type, belief_id, beliefs, B, n_worlds, dim))
     return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "extract_policy_graph: bad arguments");
   const int nw = n_worlds;
   auto norm2 = [&](int64_t a, int64_t c) {
     double d2 = 0.0;
-    for (int k = 0; k < 2; ++k) { const double dx = xy[2 * c + k] - xy[2 * a + k]; d2 += dx * dx; }
+    for (int k = 0; k < dim; ++k) { const double dx = xy[dim * c + k] - xy[dim * a + k]; d2 += dx * dx; }
     return std::sqrt(d2);
   };
   auto tp = [&](int64_t parent, int64_t child) {

@@ -18,6 +18,10 @@ struct Pcg64 {
       const uint32_t x = (uint32_t)(((s >> 18) ^ s) >> 27), rot = (uint32_t)(s >> 59);
       w[c] = (x >> rot) | (x << ((32 - rot) & 31));
     }
+    return from_seed_words(w);
+  }
+  // SeedableRng::from_seed for Lcg128Xsl64: 32 seed bytes, little endian: state (16 bytes) | stream (16 bytes, forced odd)
+  static Pcg64 from_seed_words(const uint32_t w[8]) {
     Pcg64 p;
     p.state = (u128)((uint64_t)w[0] | ((uint64_t)w[1] << 32)) | ((u128)((uint64_t)w[2] | ((uint64_t)w[3] << 32)) << 64);
     p.inc = ((u128)((uint64_t)w[4] | ((uint64_t)w[5] << 32)) | ((u128)((uint64_t)w[6] | ((uint64_t)w[7] << 32)) << 64)) | 1;
