@@ -308,6 +308,19 @@ int32_t porrt_refine_policy_shortcut(porrt_ctx* ctx, const int32_t* pol_node, co
                                      int32_t* out_belief, int32_t* out_parent, uint8_t* out_is_leaf, int64_t cap, int64_t* out_n,
                                      double* out_expected_cost, int64_t* out_commits);
 
+/* PTOPolicyRefiner::refine_solution(RefinmentStrategy::Reparent(radius)) (pto_policy_refiner.rs:85-133; main.rs:221,270 run
+ * Reparent(0.3)) on the same kind of policy: Policy::decompose, per piece build_tree (:208-280: the piece plus every belief-graph
+ * descendant within `radius` of one of its nodes) and reparent with radius / 2 (:282-322), recompose.  The trees' states never change,
+ * so every (tree node, neighbour) transition the label-correcting loop can test goes through is_transition_valid in ONE device batch
+ * (*out_transitions of them); the loop itself runs on the host over those answers, popping in the order of the reference's priority
+ * queue (priority-queue 1.0.5, restated: the order among equal priorities is not pinned by any reference test).  Outputs as for
+ * porrt_refine_policy_shortcut (the recomposed policy may have fewer or more nodes than the input: size query by PORRT_ERR_CAPACITY
+ * and *out_n); *out_tree_nodes = nodes of all trees. */
+int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* pol_node, const int32_t* pol_belief, const int32_t* pol_parent,
+                                     int64_t n_pol, double radius, double* out_xy, int32_t* out_node, int32_t* out_belief,
+                                     int32_t* out_parent, uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost,
+                                     int64_t* out_tree_nodes /* nullable */, int64_t* out_transitions /* nullable */);
+
 /* reachable_belief_states (map_io.rs:515-546 / map_shelves_io.rs:490-520): host-side closure over the uploaded map's
  * zones; out[cap * n_worlds]; *out_B = count (PORRT_ERR_CAPACITY if > cap). */
 int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B);

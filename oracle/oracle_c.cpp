@@ -503,6 +503,15 @@ API void* orc_pto_refine_shortcut(void* p, uint64_t n_iterations) {
   if (!refiner_refine_shortcut(*pto->fns, pol, pto->belief_graph, (size_t)n_iterations, h->p)) { delete h; return nullptr; }
   return h;
 }
+// refine_solution(Reparent(radius)) on the PTO's last extracted policy (main.rs:221,270: Reparent(0.3))
+API void* orc_pto_refine_reparent(void* p, double radius) {
+  PTO* pto = (PTO*)p;
+  Policy pol;
+  if (!extract_policy(pto->belief_graph, pto->expected_costs, pol)) return nullptr;
+  PolicyHandle* h = new PolicyHandle();
+  if (!refiner_refine_reparent(*pto->fns, pol, pto->belief_graph, radius, h->p)) { delete h; return nullptr; }
+  return h;
+}
 API int orc_pto_plan_qmdp(void* p, double* out /* [n_worlds][n_nodes] */) {
   PTO* pto = (PTO*)p;
   int rc = pto->plan_qmdp();

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <limits>
 #include <queue>
+#include <unordered_set>
 
 namespace orc {
 
@@ -1015,24 +1016,39 @@ static double policy_expected_from(const Policy& p, const BeliefGraph& g, double
 }
 double policy_expected_costs(const Policy& p, const BeliefGraph& g) { return policy_expected_from(p, g, 1.0, 0); }
 
-bool refiner_refine_shortcut(const GridMap& m, const Policy& policy, const BeliefGraph& g, size_t n_iterations, Policy& out) {
-  std::vector<std::vector<bool>> compat(g.reachable_belief_states.size(), std::vector<bool>(m.world_validities.size(), false));   // refiner :79, common.rs:266-276
+namespace {
+struct TreeNode { State state; int64_t parent; size_t belief_graph_id; double parent_cost = 0.0; };   // RefinmentNode :33-38 (parent: Option<Edge{id, cost}>)
+struct Tree {                                                                                          // RefinmentTree :40-63
+  std::vector<TreeNode> nodes; size_t belief_state_id = 0, leaf = 0;
+  double dist_from_root(size_t id) const {                                                             // :53-62: summed from the node upwards
+    double cost = 0.0;
+    for (size_t k = id; nodes[k].parent >= 0; k = (size_t)nodes[k].parent) cost += nodes[k].parent_cost;
+    return cost;
+  }
+};
+std::vector<std::vector<bool>> refiner_compat(const GridMap& m, const BeliefGraph& g) {                // refiner :79, common.rs:266-276
+  std::vector<std::vector<bool>> compat(g.reachable_belief_states.size(), std::vector<bool>(m.world_validities.size(), false));
   for (size_t b = 0; b < compat.size(); ++b)
     for (size_t v = 0; v < m.world_validities.size(); ++v) compat[b][v] = is_compatible(g.reachable_belief_states[b], m.world_validities[v]);
+  return compat;
+}
+void refiner_recompose(const std::vector<Tree>& trees, const std::vector<std::vector<size_t>>& skeleton, const BeliefGraph& g, Policy& out);
+}  // namespace
+
+bool refiner_refine_shortcut(const GridMap& m, const Policy& policy, const BeliefGraph& g, size_t n_iterations, Policy& out) {
+  const std::vector<std::vector<bool>> compat = refiner_compat(m, g);
   std::vector<std::pair<size_t, std::vector<size_t>>> path_pieces;
   std::vector<std::vector<size_t>> skeleton;
   policy_decompose(policy, path_pieces, skeleton);                                                                     // :94
-  struct TreeNode { State state; int64_t parent; size_t belief_graph_id; };
-  struct Tree { std::vector<TreeNode> nodes; size_t belief_state_id = 0, leaf = 0; };
   std::vector<Tree> trees;
   for (const auto& piece : path_pieces) {                                                                               // :97
     const std::vector<size_t>& path = piece.second;
     Tree tree;                                                                                                         // build_path_piece :136-156
     const size_t root_bg = policy.nodes[path.front()].original_node_id;
-    tree.nodes.push_back({g.nodes[root_bg].state, -1, root_bg});
+    tree.nodes.push_back({g.nodes[root_bg].state, -1, root_bg, 0.0});
     for (size_t k = 0; k + 1 < path.size(); ++k) {
       const size_t next_bg = policy.nodes[path[k + 1]].original_node_id;
-      tree.nodes.push_back({g.nodes[next_bg].state, (int64_t)tree.nodes.size() - 1, next_bg});
+      tree.nodes.push_back({g.nodes[next_bg].state, (int64_t)tree.nodes.size() - 1, next_bg, 0.0});
     }
     tree.belief_state_id = g.nodes[root_bg].belief_id;
     tree.leaf = tree.nodes.size() - 1;
@@ -1042,7 +1058,13 @@ bool refiner_refine_shortcut(const GridMap& m, const Policy& policy, const Belie
     for (size_t k = 0; k < states.size(); ++k) tree.nodes[k].state = states[k];
     trees.push_back(tree);
   }
-  // recompose :324-393
+  refiner_recompose(trees, skeleton, g, out);
+  return true;
+}
+
+namespace {
+// recompose :324-393
+void refiner_recompose(const std::vector<Tree>& trees, const std::vector<std::vector<size_t>>& skeleton, const BeliefGraph& g, Policy& out) {
   out = Policy();
   const int64_t NONE = -1;
   std::vector<std::pair<int64_t, int64_t>> pieces_start_end(skeleton.size(), {NONE, NONE});
@@ -1078,6 +1100,139 @@ bool refiner_refine_shortcut(const GridMap& m, const Policy& policy, const Belie
   for (size_t i = 0; i < out.nodes.size(); ++i)                                                                        // :384-389
     if (out.nodes[i].children.empty()) out.leafs.push_back(i);
   out.expected_costs = policy_expected_costs(out, g);                                                                  // :391
+}
+
+// priority-queue 1.0.5 `PriorityQueue<usize, Priority>` as the refiner uses it (push / pop / is_empty), restated from the crate's
+// published algorithm (the crate is a crates.io dependency, Cargo.toml:18, not vendored): an indexed binary heap -- `heap` holds
+// item slots, a NEW item is appended and bubbles up while `parent < new`, an item pushed AGAIN gets its priority replaced, bubbles up
+// by the same rule and is then sifted down (`heapify`), pop moves the LAST heap entry to the root and sifts it down, looking at the
+// left child first and preferring a child only when it is strictly `>`.  Priority's Ord (common.rs:231-251) never says Equal:
+// a.cmp(b) = Greater iff a.prio < b.prio, else Less -- so `a < b` means !(a.prio < b.prio) and `a > b` means a.prio < b.prio, which is
+// what decides the order among equal priorities.  PARITY UNPINNED: no test of the reference fixes this order.
+struct RefPriorityQueue {
+  std::vector<size_t> heap;            // item ids
+  std::vector<int64_t> pos;            // item id -> heap position, -1 = not queued
+  std::vector<double> prio;
+  explicit RefPriorityQueue(size_t n_items) : pos(n_items, -1), prio(n_items, 0.0) {}
+  static bool lt(double a, double b) { return !(a < b); }   // Priority{a} < Priority{b}
+  static bool gt(double a, double b) { return a < b; }      // Priority{a} > Priority{b}
+  bool empty() const { return heap.empty(); }
+  void bubble_up(size_t i, size_t item) {
+    while (i > 0 && lt(prio[heap[(i - 1) / 2]], prio[item])) {
+      heap[i] = heap[(i - 1) / 2]; pos[heap[i]] = (int64_t)i;
+      i = (i - 1) / 2;
+    }
+    heap[i] = item; pos[item] = (int64_t)i;
+  }
+  void heapify(size_t i) {
+    for (;;) {
+      const size_t l = 2 * i + 1, r = 2 * i + 2;
+      size_t largest = (l < heap.size() && gt(prio[heap[l]], prio[heap[i]])) ? l : i;
+      if (r < heap.size() && gt(prio[heap[r]], prio[heap[largest]])) largest = r;
+      if (largest == i) return;
+      std::swap(heap[i], heap[largest]);
+      pos[heap[i]] = (int64_t)i; pos[heap[largest]] = (int64_t)largest;
+      i = largest;
+    }
+  }
+  void push(size_t item, double p) {
+    prio[item] = p;
+    if (pos[item] >= 0) {                      // already queued: change_priority
+      const size_t at = (size_t)pos[item];
+      bubble_up(at, item);
+      heapify((size_t)pos[item]);
+      return;
+    }
+    heap.push_back(item);
+    bubble_up(heap.size() - 1, item);
+  }
+  size_t pop() {
+    const size_t head = heap[0];
+    pos[head] = -1;
+    heap[0] = heap.back();
+    heap.pop_back();
+    if (!heap.empty()) { pos[heap[0]] = 0; heapify(0); }
+    return head;
+  }
+};
+}  // namespace
+
+// PTOPolicyRefiner::refine_solution(RefinmentStrategy::Reparent(radius)) (pto_policy_refiner.rs:85-133): per path piece build_tree
+// (:208-280) and reparent with half the radius (:282-322), then recompose.
+bool refiner_refine_reparent(const GridMap& m, const Policy& policy, const BeliefGraph& g, double radius, Policy& out) {
+  const std::vector<std::vector<bool>> compat = refiner_compat(m, g);
+  std::vector<std::pair<size_t, std::vector<size_t>>> path_pieces;
+  std::vector<std::vector<size_t>> skeleton;
+  policy_decompose(policy, path_pieces, skeleton);
+  std::vector<Tree> trees;
+  for (const auto& piece : path_pieces) {
+    const std::vector<size_t>& path = piece.second;
+    // ---- build_tree :209-280
+    std::unordered_set<size_t> visited;
+    Tree tree;
+    const size_t root_bg = policy.nodes[path.front()].original_node_id;
+    tree.nodes.push_back({g.nodes[root_bg].state, -1, root_bg, 0.0});
+    KdTree kdtree(g.nodes[root_bg].state);
+    visited.insert(root_bg);
+    for (size_t k = 0; k + 1 < path.size(); ++k) {                                           // :227-242
+      const size_t prev_bg = policy.nodes[path[k]].original_node_id, next_bg = policy.nodes[path[k + 1]].original_node_id;
+      tree.nodes.push_back({g.nodes[next_bg].state, (int64_t)tree.nodes.size() - 1, next_bg, norm2(g.nodes[prev_bg].state, g.nodes[next_bg].state)});
+      kdtree.add(g.nodes[next_bg].state, tree.nodes.size() - 1);
+      visited.insert(next_bg);
+    }
+    tree.belief_state_id = g.nodes[root_bg].belief_id;
+    tree.leaf = tree.nodes.size() - 1;
+    const std::vector<TreeNode> nodes = tree.nodes;                                          // :247 clone: only the path nodes seed the search
+    for (size_t node_id = 0; node_id < nodes.size(); ++node_id) {                            // :248-277
+      const TreeNode& node = nodes[node_id];
+      std::deque<std::pair<size_t, size_t>> q;
+      q.push_back({node_id, node.belief_graph_id});
+      while (!q.empty()) {
+        const std::pair<size_t, size_t> top = q.front(); q.pop_front();
+        const size_t tree_id = top.first;
+        for (size_t child_id : g.nodes[top.second].children) {
+          const BeliefNode& child = g.nodes[child_id];
+          if (!visited.count(child_id) && norm2(node.state, child.state) <= radius) {        // distance to the SEED node of the search
+            tree.nodes.push_back({child.state, (int64_t)tree_id, child_id, norm2(node.state, child.state)});   // (cost from the seed too, :259-262)
+            const size_t new_tree_id = tree.nodes.size() - 1;
+            kdtree.add(child.state, new_tree_id);
+            visited.insert(child_id);
+            for (size_t cc : child.children)
+              if (!visited.count(cc)) q.push_back({new_tree_id, cc});                        // :268-272: the CHILDREN of cc are looked at next
+          }
+        }
+      }
+    }
+    // ---- reparent :282-322 with radius / 2
+    {
+      const double r2 = 0.5 * radius;
+      RefPriorityQueue q(tree.nodes.size());
+      for (size_t id = 0; id < tree.nodes.size(); ++id) q.push(id, tree.dist_from_root(id));
+      while (!q.empty()) {
+        const size_t node_id = q.pop();
+        const State node_state = tree.nodes[node_id].state;
+        std::vector<size_t> neighbor_ids;
+        for (const KdTree::Node* kn : kdtree.nearest_neighbors(node_state, r2)) {
+          const int64_t ok = refiner_is_transition_valid(m, node_state, kn->state, compat[tree.belief_state_id]);
+          if (ok < 0) return false;
+          if (ok) neighbor_ids.push_back(kn->id);
+        }
+        const double distance_from_root = tree.dist_from_root(node_id);
+        std::vector<std::pair<size_t, double>> nd;
+        for (size_t id : neighbor_ids) nd.push_back({id, tree.dist_from_root(id)});          // all read BEFORE any reparenting of this pop
+        for (const auto& kv : nd) {
+          const double cost = norm2(node_state, tree.nodes[kv.first].state);
+          if (distance_from_root + cost < kv.second) {
+            tree.nodes[kv.first].parent = (int64_t)node_id;
+            tree.nodes[kv.first].parent_cost = cost;
+            q.push(kv.first, distance_from_root + cost);
+          }
+        }
+      }
+    }
+    trees.push_back(tree);
+  }
+  refiner_recompose(trees, skeleton, g, out);
   return true;
 }
 

@@ -203,6 +203,9 @@ double policy_expected_costs(const Policy& p, const BeliefGraph& g);
 // PTOPolicyRefiner::refine_solution(RefinmentStrategy::PartialShortCut(n)) (pto_policy_refiner.rs:85-133,135-206,324-393): decompose,
 // build_path_piece + partial_shortcut per piece, recompose.  Returns false on a reference panic.
 bool refiner_refine_shortcut(const GridMap& m, const Policy& policy, const BeliefGraph& g, size_t n_iterations, Policy& out);
+// refine_solution(RefinmentStrategy::Reparent(radius)) (pto_policy_refiner.rs:85-133,208-322): build_tree + reparent(radius / 2) per
+// piece, recompose.  The pop order among equal priorities follows priority-queue 1.0.5's heap (restated; parity unpinned).
+bool refiner_refine_reparent(const GridMap& m, const Policy& policy, const BeliefGraph& g, double radius, Policy& out);
 
 struct PRM {  // prm.rs
   const GridMap* fns;

@@ -538,6 +538,29 @@ def refine_policy_shortcut(ctx, plan, n_iterations, sampler_seed=0):
             "commits": commits.value}
 
 
+def refine_policy_reparent(ctx, plan, radius):
+    """PTOPolicyRefiner::refine_solution(Reparent(radius)) on a BeliefPlan of the ctx's last plan_belief_space
+    -> dict(xy, node, belief, parent, is_leaf, expected_cost, tree_nodes, transitions)"""
+    n_pol = len(plan.policy_node)
+    pn, pb, pp = (np.ascontiguousarray(a, np.int32) for a in (plan.policy_node, plan.policy_belief, plan.policy_parent))
+    cap = max(n_pol, 64)
+    while True:
+        xy = np.empty((cap, 2))
+        node, belief, parent = (np.empty(cap, np.int32) for _ in range(3))
+        leaf = np.empty(cap, np.uint8)
+        n, cost, tn, tr = C.c_int64(), C.c_double(), C.c_int64(), C.c_int64()
+        rc = ctx.lib.porrt_refine_policy_reparent(ctx.h, _p(pn), _p(pb), _p(pp), n_pol, float(radius), _p(xy), _p(node), _p(belief), _p(parent),
+                                                  _p(leaf), cap, C.byref(n), C.byref(cost), C.byref(tn), C.byref(tr))
+        if rc == 4 and n.value > cap:   # PORRT_ERR_CAPACITY
+            cap = n.value
+            continue
+        ctx.check(rc)
+        break
+    k = n.value
+    return {"xy": xy[:k], "node": node[:k], "belief": belief[:k], "parent": parent[:k], "is_leaf": leaf[:k], "expected_cost": cost.value,
+            "tree_nodes": tn.value, "transitions": tr.value}
+
+
 class BeliefGraph:
     """src/belief_graph.rs BeliefGraph as arrays: belief node k = (state xy[k], belief_id[k], node_type[k]); children adjacency
     as CSR in add_edge order.  conditional_dijkstra / extract_policy are the reference's free functions (:89-267)."""

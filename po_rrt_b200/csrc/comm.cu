@@ -9,6 +9,8 @@
 // (torch.distributed / MPI / a file: any 128-byte broadcast).
 #include <dlfcn.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -29,11 +31,17 @@ struct NcclApi {
   std::string why;
 };
 
+void nccl_load(NcclApi* out);
+
 NcclApi* nccl_api() {
   static NcclApi api;
-  static bool tried = false;
-  if (tried) return &api;
-  tried = true;
+  static std::once_flag once;   // two ranks' host threads of one process may get here together
+  std::call_once(once, [] { nccl_load(&api); });
+  return &api;
+}
+
+void nccl_load(NcclApi* out) {
+  NcclApi& api = *out;
   const char* names[] = {getenv("PORRT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) {
     if (!nm || !*nm) continue;
@@ -41,7 +49,7 @@ NcclApi* nccl_api() {
     if (api.handle) break;
     api.why = dlerror();
   }
-  if (!api.handle) return &api;
+  if (!api.handle) return;
   bool ok = true;
   auto sym = [&](const char* s) { void* p = dlsym(api.handle, s); if (!p) { ok = false; api.why = std::string("missing symbol ") + s; } return p; };
   api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
@@ -54,7 +62,6 @@ NcclApi* nccl_api() {
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
   api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
   if (!ok) { dlclose(api.handle); api.handle = nullptr; }
-  return &api;
 }
 
 int32_t nccl_fail(porrt_ctx* ctx, const char* what, int rc) {

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <unordered_set>
 
 #include "pcg64.h"
 #include "common.cuh"
@@ -243,6 +244,40 @@ PORRT_API int32_t porrt_partial_shortcut(porrt_ctx* ctx, double* states_xy, int3
   return porrt_partial_shortcut_batch(ctx, states_xy, ptr, 1, compat_row, n_iterations, sampler_seed, out_commits, out_waves);
 }
 
+// Policy::compute_expected_costs_to_goals (common.rs:131-153) over flat arrays: a policy as (state, belief, parent) per node in
+// creation order; children are folded in increasing index, a child's own sum is complete before its parent adds it.
+static double policy_expected_cost_flat(const double* beliefs, int nw, const double* out_xy, const int32_t* out_belief, const int32_t* out_parent, int64_t n_out) {
+  auto transition_probability = [&](int pb, int cb) {
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s = s + (beliefs[(size_t)cb * nw + i] > 0.0 ? beliefs[(size_t)pb * nw + i] : 0.0);
+    return s;
+  };
+  std::vector<double> prob((size_t)n_out, 0.0), pq((size_t)n_out, 0.0), edge_term((size_t)n_out, 0.0), below((size_t)n_out, 0.0);
+  prob[0] = 1.0;
+  for (int64_t k = 1; k < n_out; ++k) {
+    const int32_t par = out_parent[k];
+    if (par < 0) continue;   // a piece that recompose left unconnected: not under the root
+    const double q = transition_probability(out_belief[par], out_belief[k]);
+    const double dx = out_xy[2 * k] - out_xy[2 * (size_t)par], dy = out_xy[2 * k + 1] - out_xy[2 * (size_t)par + 1];
+    const double cost = std::sqrt(dx * dx + dy * dy);   // norm2(parent, child), common.rs:203-213
+    pq[(size_t)k] = prob[(size_t)par] * q;              // p * q
+    prob[(size_t)k] = pq[(size_t)k];
+    edge_term[(size_t)k] = pq[(size_t)k] * cost;        // (p * q) * cost
+  }
+  // expected_future_costs(parent) += p * q * cost + expected_future_costs(child), children in order (common.rs:149)
+  std::vector<int64_t> oc_ptr((size_t)n_out + 1, 0);
+  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) ++oc_ptr[(size_t)out_parent[k] + 1];
+  for (int64_t k = 0; k < n_out; ++k) oc_ptr[(size_t)k + 1] += oc_ptr[(size_t)k];
+  std::vector<int64_t> oc((size_t)oc_ptr[(size_t)n_out]), ofill(oc_ptr.begin(), oc_ptr.end() - 1);
+  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) oc[(size_t)ofill[(size_t)out_parent[k]]++] = k;
+  for (int64_t k = n_out - 1; k >= 0; --k) {
+    double acc = 0.0;
+    for (int64_t e = oc_ptr[(size_t)k]; e < oc_ptr[(size_t)k + 1]; ++e) { const int64_t c = oc[(size_t)e]; acc += edge_term[(size_t)c] + below[(size_t)c]; }
+    below[(size_t)k] = acc;
+  }
+  return below[0];
+}
+
 // ================================================================================================ refine_solution(PartialShortCut(n))
 // PTOPolicyRefiner::refine_solution with RefinmentStrategy::PartialShortCut (pto_policy_refiner.rs:85-133; what every PTO run of
 // the reference's main.rs ends with, e.g. :442 PartialShortCut(1500)) on the policy porrt_extract_policy produced from the last
@@ -324,36 +359,330 @@ PORRT_API int32_t porrt_refine_policy_shortcut(porrt_ctx* ctx, const int32_t* po
   std::vector<int32_t> n_children((size_t)n_out, 0);
   for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) ++n_children[(size_t)out_parent[k]];
   for (int64_t k = 0; k < n_out; ++k) out_is_leaf[k] = n_children[(size_t)k] == 0;
-  // ---- compute_expected_costs_to_goals: probabilities top down, costs bottom up; children are visited in increasing index
-  auto transition_probability = [&](int pb, int cb) {
-    double s = 0.0;
-    for (int i = 0; i < nw; ++i) s = s + (R.beliefs[(size_t)cb * nw + i] > 0.0 ? R.beliefs[(size_t)pb * nw + i] : 0.0);
-    return s;
+  if (out_expected_cost) *out_expected_cost = policy_expected_cost_flat(R.beliefs.data(), nw, out_xy, out_belief, out_parent, n_out);
+  return PORRT_OK;
+}
+
+// ================================================================================================ refine_solution(Reparent(radius))
+// PTOPolicyRefiner::refine_solution with RefinmentStrategy::Reparent (pto_policy_refiner.rs:85-133; main.rs:221,270 run Reparent(0.3))
+// on the policy of the last porrt_belief_vi / porrt_extract_policy of this ctx.  Per path piece the reference
+//   build_tree (:208-280)  grows a tree out of the piece: the path nodes, then every belief-graph descendant within `radius` of a path
+//                          node (breadth first from each path node; quirks kept: distances and edge costs are measured from the SEED
+//                          path node, and a grandchild enters the queue as a node whose CHILDREN are looked at next),
+//   reparent (:282-322)    pops tree nodes by distance from the root and offers itself as parent to every tree node within
+//                          radius / 2 it has a valid transition to (is_transition_valid, :395-423) -- label correcting, re-queueing,
+// and recompose (:324-393) reads the new path leaf -> root.
+// Here: the trees are built on the host from the retained belief-graph description (the implicit graph's children in the reference's
+// order); the states of a tree never change, so EVERY (node, neighbour) pair reparent can ever test is known up front: all pairs of
+// all pieces go through state validity + the edge kernel + the compatibility row in ONE device batch (the hot path; the reference
+// re-evaluates them at every pop).  The label-correcting loop itself is sequential and cheap: host, over the precomputed answers,
+// with the pop order of the reference's priority queue (priority-queue 1.0.5's indexed binary heap and Priority's never-Equal Ord,
+// common.rs:231-251 -- restated from the published algorithm, parity unpinned: no test of the reference fixes the order among equal
+// priorities, which do occur: Observation children share their parent's state).
+namespace {
+struct ReparentHeap {                   // see the comment above; lt / gt are Priority's `<` / `>`
+  std::vector<int32_t> heap, pos;
+  std::vector<double> prio;
+  explicit ReparentHeap(size_t n) : pos(n, -1), prio(n, 0.0) {}
+  static bool lt(double a, double b) { return !(a < b); }
+  static bool gt(double a, double b) { return a < b; }
+  void up(size_t i, int32_t item) {
+    while (i > 0 && lt(prio[(size_t)heap[(i - 1) / 2]], prio[(size_t)item])) { heap[i] = heap[(i - 1) / 2]; pos[(size_t)heap[i]] = (int32_t)i; i = (i - 1) / 2; }
+    heap[i] = item; pos[(size_t)item] = (int32_t)i;
+  }
+  void down(size_t i) {
+    for (;;) {
+      const size_t l = 2 * i + 1, r = l + 1;
+      size_t big = (l < heap.size() && gt(prio[(size_t)heap[l]], prio[(size_t)heap[i]])) ? l : i;
+      if (r < heap.size() && gt(prio[(size_t)heap[r]], prio[(size_t)heap[big]])) big = r;
+      if (big == i) return;
+      std::swap(heap[i], heap[big]);
+      pos[(size_t)heap[i]] = (int32_t)i; pos[(size_t)heap[big]] = (int32_t)big;
+      i = big;
+    }
+  }
+  void push(int32_t item, double p) {
+    prio[(size_t)item] = p;
+    if (pos[(size_t)item] >= 0) { up((size_t)pos[(size_t)item], item); down((size_t)pos[(size_t)item]); return; }
+    heap.push_back(item);
+    up(heap.size() - 1, item);
+  }
+  int32_t pop() {
+    const int32_t head = heap[0];
+    pos[(size_t)head] = -1;
+    heap[0] = heap.back();
+    heap.pop_back();
+    if (!heap.empty()) { pos[(size_t)heap[0]] = 0; down(0); }
+    return head;
+  }
+};
+
+struct PieceTree {
+  std::vector<double> xy;               // 2 per tree node
+  std::vector<int32_t> parent;          // -1 = root
+  std::vector<double> parent_cost;
+  std::vector<int64_t> bgid;            // belief-graph id = node * B + belief
+  std::vector<int32_t> kd_left, kd_right;
+  int32_t belief = 0, leaf = 0;
+  size_t size() const { return parent.size(); }
+  int32_t add(const double* s, int32_t par, double cost, int64_t id) {
+    xy.push_back(s[0]); xy.push_back(s[1]); parent.push_back(par); parent_cost.push_back(cost); bgid.push_back(id);
+    kd_left.push_back(-1); kd_right.push_back(-1);
+    const int32_t me = (int32_t)size() - 1;
+    if (me > 0) {                        // KdTree::add (nearest_neighbor.rs:29-46), kd node = tree node
+      int32_t cur = 0;
+      for (int axis = 0;; axis ^= 1) {
+        int32_t& next = s[axis] < xy[2 * (size_t)cur + axis] ? kd_left[(size_t)cur] : kd_right[(size_t)cur];
+        if (next >= 0) cur = next; else { next = me; break; }
+      }
+    }
+    return me;
+  }
+  double dist_from_root(int32_t id) const {   // :53-62, summed from the node upwards
+    double c = 0.0;
+    for (int32_t k = id; parent[(size_t)k] >= 0; k = parent[(size_t)k]) c += parent_cost[(size_t)k];
+    return c;
+  }
+  // nearest_neighbors (:94-126): ids in the reference's visit order
+  void radius(const double* s, double r, std::vector<int32_t>& out) const {
+    struct F { int32_t node; int axis; int stage; };
+    std::vector<F> st(1, F{0, 0, 0});
+    while (!st.empty()) {
+      F& f = st.back();
+      const double* fs = &xy[2 * (size_t)f.node];
+      if (f.stage == 0) {
+        const double dx = s[0] - fs[0], dy = s[1] - fs[1];     // norm2(from.state, a.state)
+        if (std::sqrt(dx * dx + dy * dy) <= r) out.push_back(f.node);
+      }
+      if (f.stage >= 2) { st.pop_back(); continue; }
+      const int stage = f.stage++, axis = f.axis;
+      int32_t child = -1;
+      if (stage == 0) { if (s[axis] - r <= fs[axis]) child = kd_left[(size_t)f.node]; }
+      else { if (s[axis] + r >= fs[axis]) child = kd_right[(size_t)f.node]; }
+      if (child >= 0) st.push_back(F{child, axis ^ 1, 0});
+    }
+  }
+};
+}  // namespace
+
+PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* pol_node, const int32_t* pol_belief, const int32_t* pol_parent,
+                                               int64_t n_pol, double radius, double* out_xy, int32_t* out_node, int32_t* out_belief,
+                                               int32_t* out_parent, uint8_t* out_is_leaf, int64_t cap, int64_t* out_n,
+                                               double* out_expected_cost, int64_t* out_tree_nodes, int64_t* out_transitions) {
+  CTX_CHECK(ctx);
+  auto& R = ctx->bel;
+  if (R.V <= 0) return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "refine_policy_reparent: run porrt_belief_vi / porrt_extract_policy first");
+  if (!ctx->has_map) return porrt_fail(ctx, PORRT_ERR_NO_MAP, "no map uploaded");
+  if (n_pol <= 0 || !pol_node || !pol_belief || !pol_parent || !(radius >= 0.0) || !out_n)
+    return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "refine_policy_reparent: bad arguments");
+  const int B = R.B, nw = R.n_worlds, nv = R.n_validities;
+  const std::vector<int32_t>& nvid = ctx->bel_node_vid;
+  for (int64_t k = 0; k < n_pol; ++k)
+    if (pol_node[k] < 0 || pol_node[k] >= R.V || pol_belief[k] < 0 || pol_belief[k] >= B || pol_parent[k] >= k || (k > 0 && pol_parent[k] < 0) || (k == 0 && pol_parent[k] != -1))
+      return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "refine_policy_reparent: not a policy in creation order");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // node types of the belief graph: from the host table, or column by column from the device (as the policy walk does)
+  bool fetch_failed = false;
+  auto type_at = [&](int64_t id) -> uint8_t {
+    if (R.on_host) return R.type[(size_t)id];
+    const int b = (int)(id % B);
+    if (R.col_dist[(size_t)b].empty()) {
+      R.col_dist[(size_t)b].resize((size_t)R.V); R.col_type[(size_t)b].resize((size_t)R.V);
+      if (cudaMemcpyAsync(R.col_dist[(size_t)b].data(), R.d_dist_cm + (size_t)R.colpos[(size_t)b] * R.V, (size_t)R.V * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(R.col_type[(size_t)b].data(), R.d_type_cm + (size_t)R.colpos[(size_t)b] * R.V, (size_t)R.V, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+        fetch_failed = true;
+    }
+    return R.col_type[(size_t)b][(size_t)(id / B)];
   };
-  std::vector<double> prob((size_t)n_out, 0.0), pq((size_t)n_out, 0.0), edge_term((size_t)n_out, 0.0), below((size_t)n_out, 0.0);
-  prob[0] = 1.0;
-  for (int64_t k = 1; k < n_out; ++k) {
-    const int32_t par = out_parent[k];
-    if (par < 0) continue;   // a piece that recompose left unconnected: not under the root
-    const double q = transition_probability(out_belief[par], out_belief[k]);
-    const double dx = out_xy[2 * k] - out_xy[2 * (size_t)par], dy = out_xy[2 * k + 1] - out_xy[2 * (size_t)par + 1];
-    const double cost = std::sqrt(dx * dx + dy * dy);   // norm2(parent, child), common.rs:203-213
-    pq[(size_t)k] = prob[(size_t)par] * q;              // p * q
-    prob[(size_t)k] = pq[(size_t)k];
-    edge_term[(size_t)k] = pq[(size_t)k] * cost;        // (p * q) * cost
+  // children of a belief node in the reference's stored order (pto.rs:206-255): observation edges, or action edges
+  auto for_children = [&](int64_t bn, auto&& fn) {
+    const int64_t n = bn / B;
+    const int b = (int)(bn % B);
+    const uint8_t ty = type_at(bn);
+    if (ty == PORRT_NODE_OBSERVATION) {
+      const int64_t sp = (int64_t)R.node_obs_set[(size_t)n] * B + b;
+      for (int64_t k = R.succ_ptr[(size_t)sp]; k < R.succ_ptr[(size_t)sp + 1]; ++k) {
+        const int32_t cb = R.succ_belief[(size_t)k];
+        if (R.compat[(size_t)cb * nv + nvid[(size_t)n]]) fn(n * B + cb);
+      }
+    } else if (ty == PORRT_NODE_ACTION) {
+      for (int64_t e = R.row_ptr[(size_t)n]; e < R.row_ptr[(size_t)n + 1]; ++e) {
+        const int32_t c = R.col[(size_t)e];
+        if (R.compat[(size_t)b * nv + nvid[(size_t)c]] && R.compat[(size_t)b * nv + R.edge_vid[(size_t)e]]) fn((int64_t)c * B + b);
+      }
+    }
+  };
+  // ---- Policy::decompose (common.rs:85-129), as in porrt_refine_policy_shortcut
+  std::vector<int64_t> ch_ptr((size_t)n_pol + 1, 0);
+  for (int64_t k = 1; k < n_pol; ++k) ++ch_ptr[(size_t)pol_parent[k] + 1];
+  for (int64_t k = 0; k < n_pol; ++k) ch_ptr[(size_t)k + 1] += ch_ptr[(size_t)k];
+  std::vector<int64_t> ch((size_t)std::max<int64_t>(n_pol - 1, 0)), fill(ch_ptr.begin(), ch_ptr.end() - 1);
+  for (int64_t k = 1; k < n_pol; ++k) ch[(size_t)fill[(size_t)pol_parent[k]]++] = k;
+  std::vector<std::vector<int64_t>> pieces;
+  std::vector<std::vector<int32_t>> successors;
+  {
+    std::vector<int64_t> fifo(1, 0);
+    int32_t n_pieces = 0;
+    for (size_t head = 0; head < fifo.size(); ++head) {
+      int64_t cur = fifo[head];
+      std::vector<int64_t> ids;
+      std::vector<int32_t> succ;
+      for (;;) {
+        ids.push_back(cur);
+        const int64_t nc = ch_ptr[(size_t)cur + 1] - ch_ptr[(size_t)cur];
+        if (nc == 0) break;
+        if (nc == 1) { cur = ch[(size_t)ch_ptr[(size_t)cur]]; continue; }
+        for (int64_t e = ch_ptr[(size_t)cur]; e < ch_ptr[(size_t)cur + 1]; ++e) { fifo.push_back(ch[(size_t)e]); succ.push_back(++n_pieces); }
+        break;
+      }
+      pieces.push_back(ids);
+      successors.push_back(succ);
+    }
   }
-  // expected_future_costs(parent) += p * q * cost + expected_future_costs(child), children in order (common.rs:149): a child's own sum
-  // is complete before its parent folds it in -- fold the children of each node in increasing index, nodes in decreasing index
-  std::vector<int64_t> oc_ptr((size_t)n_out + 1, 0);
-  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) ++oc_ptr[(size_t)out_parent[k] + 1];
-  for (int64_t k = 0; k < n_out; ++k) oc_ptr[(size_t)k + 1] += oc_ptr[(size_t)k];
-  std::vector<int64_t> oc((size_t)oc_ptr[(size_t)n_out]), ofill(oc_ptr.begin(), oc_ptr.end() - 1);
-  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) oc[(size_t)ofill[(size_t)out_parent[k]]++] = k;
-  for (int64_t k = n_out - 1; k >= 0; --k) {
-    double acc = 0.0;
-    for (int64_t e = oc_ptr[(size_t)k]; e < oc_ptr[(size_t)k + 1]; ++e) { const int64_t c = oc[(size_t)e]; acc += edge_term[(size_t)c] + below[(size_t)c]; }
-    below[(size_t)k] = acc;
+  // ---- build_tree per piece
+  auto norm2 = [](const double* a, const double* b) { const double dx = b[0] - a[0], dy = b[1] - a[1]; return std::sqrt(dx * dx + dy * dy); };
+  std::vector<PieceTree> trees(pieces.size());
+  int64_t tree_nodes = 0;
+  for (size_t p = 0; p < pieces.size(); ++p) {
+    PieceTree& T = trees[p];
+    std::unordered_set<int64_t> visited;
+    for (size_t k = 0; k < pieces[p].size(); ++k) {
+      const int64_t pn = pieces[p][k];
+      const int64_t bg = (int64_t)pol_node[pn] * B + pol_belief[pn];
+      const double* s = &R.xy[2 * (size_t)pol_node[pn]];
+      T.add(s, (int32_t)k - 1, k ? norm2(&R.xy[2 * (size_t)pol_node[pieces[p][k - 1]]], s) : 0.0, bg);
+      visited.insert(bg);
+    }
+    T.belief = pol_belief[pieces[p][0]];
+    T.leaf = (int32_t)T.size() - 1;
+    const size_t n_seed = T.size();
+    std::vector<std::pair<int32_t, int64_t>> q;
+    for (size_t seed = 0; seed < n_seed; ++seed) {
+      const double sx[2] = {T.xy[2 * seed], T.xy[2 * seed + 1]};
+      q.assign(1, {(int32_t)seed, T.bgid[seed]});
+      for (size_t head = 0; head < q.size(); ++head) {
+        const int32_t tree_id = q[head].first;
+        const int64_t from_bg = q[head].second;
+        for_children(from_bg, [&](int64_t child) {
+          const double* cs = &R.xy[2 * (size_t)(child / B)];
+          if (visited.count(child)) return;
+          const double d = norm2(sx, cs);
+          if (!(d <= radius)) return;
+          const int32_t me = T.add(cs, tree_id, d, child);
+          visited.insert(child);
+          for_children(child, [&](int64_t cc) { if (!visited.count(cc)) q.push_back({me, cc}); });
+        });
+        if (fetch_failed) return porrt_fail(ctx, PORRT_ERR_CUDA, "refine_policy_reparent: fetching a value column failed");
+        if ((int64_t)T.size() > (int64_t)R.V * B) return porrt_fail(ctx, PORRT_ERR_PANIC, "refine_policy_reparent: tree larger than the belief graph");
+      }
+    }
+    tree_nodes += (int64_t)T.size();
   }
-  if (out_expected_cost) *out_expected_cost = below[0];
+  if (out_tree_nodes) *out_tree_nodes = tree_nodes;
+  // ---- every (node, neighbour within radius / 2) pair of every tree: ONE device batch of is_transition_valid
+  const double r2 = 0.5 * radius;
+  std::vector<int64_t> nb_ptr(1, 0);     // per tree node (trees back to back)
+  std::vector<int32_t> nb_ids, pair_row;
+  std::vector<double> pair_from, pair_to;
+  {
+    std::vector<int32_t> nb;
+    for (size_t p = 0; p < trees.size(); ++p) {
+      const PieceTree& T = trees[p];
+      for (size_t u = 0; u < T.size(); ++u) {
+        nb.clear();
+        T.radius(&T.xy[2 * u], r2, nb);
+        for (int32_t v : nb) {
+          nb_ids.push_back(v); pair_row.push_back(T.belief);
+          pair_from.push_back(T.xy[2 * u]); pair_from.push_back(T.xy[2 * u + 1]);
+          pair_to.push_back(T.xy[2 * (size_t)v]); pair_to.push_back(T.xy[2 * (size_t)v + 1]);
+        }
+        nb_ptr.push_back((int64_t)nb_ids.size());
+      }
+    }
+  }
+  const int64_t n_pairs = (int64_t)nb_ids.size();
+  if (out_transitions) *out_transitions = n_pairs;
+  std::vector<uint8_t> valid((size_t)std::max<int64_t>(n_pairs, 1));
+  std::vector<int32_t> status((size_t)std::max<int64_t>(n_pairs, 1), 0);
+  if (n_pairs > 0) {
+    const size_t n = (size_t)n_pairs, nrows = (size_t)B * nv;
+    CUDA_TRY(ctx, ctx->scratch[3].ensure(n * (32 + 12 + 4 + 4 + 1) + nrows + 256));
+    char* b = ctx->scratch[3].as<char>();
+    double* d_from = (double*)b; b += n * 16;
+    double* d_to = (double*)b; b += n * 16;
+    int32_t* d_tmp = (int32_t*)b; b += n * 12;
+    int32_t* d_status = (int32_t*)b; b += n * 4;
+    int32_t* d_row = (int32_t*)b; b += n * 4;
+    uint8_t* d_valid = (uint8_t*)b; b += (n + 15) & ~(size_t)15;
+    uint8_t* d_compat = (uint8_t*)b;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_from, pair_from.data(), n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_to, pair_to.data(), n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_row, pair_row.data(), n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, R.compat.data(), nrows, cudaMemcpyHostToDevice, st));
+    const int32_t rc = transition_valid_dev(ctx, d_from, d_to, n_pairs, d_compat, d_row, nv, d_tmp, d_valid, d_status);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(valid.data(), d_valid, n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), d_status, n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    for (int64_t k = 0; k < n_pairs; ++k)   // every node is popped at least once and tests all its pairs: a panic anywhere is reached
+      if (status[(size_t)k] < 0) return porrt_fail(ctx, PORRT_ERR_PANIC, "refine_policy_reparent: is_transition_valid panics (code " + std::to_string(status[(size_t)k]) + ")");
+  }
+  // ---- reparent (:282-322)
+  {
+    int64_t base = 0;                    // first tree node of the piece in nb_ptr
+    std::vector<std::pair<int32_t, double>> nd;
+    for (PieceTree& T : trees) {
+      ReparentHeap q(T.size());
+      for (size_t id = 0; id < T.size(); ++id) q.push((int32_t)id, T.dist_from_root((int32_t)id));
+      while (!q.heap.empty()) {
+        const int32_t u = q.pop();
+        const double du = T.dist_from_root(u);
+        nd.clear();
+        for (int64_t k = nb_ptr[(size_t)(base + u)]; k < nb_ptr[(size_t)(base + u) + 1]; ++k)
+          if (valid[(size_t)k]) nd.push_back({nb_ids[(size_t)k], T.dist_from_root(nb_ids[(size_t)k])});   // all read before this pop reparents anybody
+        for (const auto& kv : nd) {
+          const double cost = norm2(&T.xy[2 * (size_t)u], &T.xy[2 * (size_t)kv.first]);
+          if (du + cost < kv.second) {
+            T.parent[(size_t)kv.first] = u; T.parent_cost[(size_t)kv.first] = cost;
+            q.push(kv.first, du + cost);
+          }
+        }
+      }
+      base += (int64_t)T.size();
+    }
+  }
+  // ---- recompose (:324-393): leaf -> root of every tree, reversed; then piece ends -> successor piece starts
+  std::vector<std::vector<int32_t>> paths(trees.size());
+  int64_t n_out = 0;
+  for (size_t p = 0; p < trees.size(); ++p) {
+    for (int32_t k = trees[p].leaf; k >= 0; k = trees[p].parent[(size_t)k]) paths[p].push_back(k);
+    std::reverse(paths[p].begin(), paths[p].end());
+    n_out += (int64_t)paths[p].size();
+  }
+  *out_n = n_out;
+  if (n_out > cap || !out_xy || !out_node || !out_belief || !out_parent || !out_is_leaf)
+    return porrt_fail(ctx, PORRT_ERR_CAPACITY, "refine_policy_reparent: cap too small");
+  std::vector<int32_t> p_start(trees.size()), p_end(trees.size(), -1);
+  {
+    int32_t o = 0;
+    for (size_t p = 0; p < trees.size(); ++p) {
+      p_start[p] = o;
+      for (size_t j = 0; j < paths[p].size(); ++j, ++o) {
+        const int32_t k = paths[p][j];
+        out_xy[2 * (size_t)o] = trees[p].xy[2 * (size_t)k]; out_xy[2 * (size_t)o + 1] = trees[p].xy[2 * (size_t)k + 1];
+        out_node[o] = (int32_t)(trees[p].bgid[(size_t)k] / B); out_belief[o] = (int32_t)(trees[p].bgid[(size_t)k] % B);
+        out_parent[o] = j == 0 ? -1 : o - 1;
+      }
+      if (paths[p].size() >= 2) p_end[p] = o - 1;
+    }
+    for (size_t p = 0; p < trees.size(); ++p)
+      if (p_end[p] >= 0) for (int32_t q : successors[p]) out_parent[p_start[(size_t)q]] = p_end[p];
+  }
+  std::vector<int32_t> n_children((size_t)n_out, 0);
+  for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) ++n_children[(size_t)out_parent[k]];
+  for (int64_t k = 0; k < n_out; ++k) out_is_leaf[k] = n_children[(size_t)k] == 0;
+  if (out_expected_cost) *out_expected_cost = policy_expected_cost_flat(R.beliefs.data(), nw, out_xy, out_belief, out_parent, n_out);
   return PORRT_OK;
 }

@@ -1410,6 +1410,41 @@ def test_refine_solution_partial_shortcut(ctx, kind, Z, n_min):
     assert got["commits"] > 0 and got["expected_cost"] <= plan.expected_cost + 1e-9
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,Z,n_min", [("shelf", 4, 1500), ("shelf", 3, 2500), ("door", 2, 2500)])
+def test_refine_solution_reparent(ctx, kind, Z, n_min):
+    """PTOPolicyRefiner::refine_solution(RefinmentStrategy::Reparent(radius)) (pto_policy_refiner.rs:85-133,208-322; main.rs:221,270
+    run Reparent(0.3)): build_tree + reparent(radius / 2) per piece, recompose -- all candidate transitions in one device batch, the
+    label-correcting loop on the host; the recomposed policy equals the oracle's restatement node for node, cost bit for bit."""
+    if kind == "shelf":
+        occ, zones = synth.shelf_map(200, n_rects=10, n_zones=Z, seed=5)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.SHELF, 0.5)
+        zp = omap.zone_positions()
+        goals = [((float(zp[z][0]) - 0.08, float(zp[z][1])), [1 if k == z else 0 for k in range(Z)]) for z in range(Z)]
+        pto = _grow_pto(omap, (0.0, -0.9), goals, 0.1, 2.0, n_min)
+        b0 = [1.0 / Z] * Z
+    else:
+        occ, zones = util.planning_door_map(200)
+        omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+        pto = _grow_pto(omap, (-0.8, -0.8), [((0.8, 0.8), [1, 1, 1, 1])], 0.05, 5.0, n_min)
+        b0 = [0.1, 0.1, 0.1, 0.7]
+    plan, _, _ = _belief_compare(ctx, omap, pmap, pto, b0)
+    B = len(plan.beliefs)
+    improved = False
+    for radius in (0.0, 0.05, 0.15, 0.3):
+        want = pto.refine_policy_reparent(radius)
+        got = P.refine_policy_reparent(ctx, plan, radius)
+        assert got["xy"].tobytes() == want.xy.tobytes(), radius
+        np.testing.assert_array_equal(got["node"].astype(np.int64) * B + got["belief"], want.original)
+        np.testing.assert_array_equal(got["belief"], want.belief_id)
+        np.testing.assert_array_equal(got["parent"], want.parent)
+        np.testing.assert_array_equal(np.nonzero(got["is_leaf"])[0], want.leafs)
+        assert got["expected_cost"] == want.expected_costs, radius
+        assert got["tree_nodes"] >= len(plan.policy_node) and got["transitions"] >= got["tree_nodes"]   # every node is its own neighbour
+        improved |= got["expected_cost"] != plan.expected_cost
+    assert improved   # at least one radius changes the policy
+
+
 def test_value_backups_on_a_roadmap_beyond_shared_memory(ctx):
     """27 k roadmap nodes: a value column no longer fits in shared memory, so belief-space planning and plan_qmdp run through the
     frontier relaxation over global memory (sssp_frontier.cu) WITHOUT any option being set -- against the oracle, bit for bit."""

@@ -261,11 +261,13 @@ def test_plan_matches_the_oracle_pipeline(kind):
 def test_plan_true_random_streams_reach_the_goals():
     """without set_sampler_seed the streams come from the OS like the reference's new_true_random: two runs differ, both solve"""
     lib = _lib()
-    omap, goals, b0, start = _shelf_problem()
+    occ, zones = util.planning_door_map(200)
+    omap = O.GridMap(occ, zones, util.LOW, util.UP, O.DOOR, 0.3)
+    goals, b0, start = [((0.8, 0.8), [1, 1, 1, 1])], [0.1, 0.1, 0.1, 0.7], (-0.8, -0.8)
     costs = []
     for _ in range(2):
         c = Client(lib, omap, goals, 0.05, b0)
-        assert c.plan(start, 400, 20000, 0.05, 5.0, 50, seed=None) is None
+        assert c.plan(start, 700, 200000, 0.05, 5.0, 50, seed=None) is None
         paths, cost = c.paths()
         assert len(paths) >= 1 and np.isfinite(cost) and cost > 0
         for path in paths:
