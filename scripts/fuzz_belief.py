@@ -1,6 +1,6 @@
 """Differential fuzz of the value backups against the oracle: random shelf / door maps, random roadmap sizes and start beliefs;
 belief-space planning (table, node types, policy), plan_qmdp through both backup paths (on chip / global frontier), the QMDP on
-the same roadmap and refine_solution(PartialShortCut).  usage: fuzz_belief.py [rounds] [seed]"""
+the same roadmap, refine_solution(PartialShortCut) and refine_solution(Reparent).  usage: fuzz_belief.py [rounds] [seed]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -72,8 +72,20 @@ for it in range(rounds):
     P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits), copy=None)   # (the refiner reads the ctx's last plan)
     got, ow = P.refine_policy_shortcut(ctx, plan, n_it), pto.refine_policy_shortcut(n_it)
     oks["refine"] = got["xy"].tobytes() == ow.xy.tobytes() and np.array_equal(got["parent"], ow.parent) and got["expected_cost"] == ow.expected_costs
+    radius = float(rng.choice([0.05, 0.1, 0.2, 0.3, 0.4]))
+    try:
+        orp = pto.refine_policy_reparent(radius)
+    except RuntimeError:
+        orp = None   # a reference panic inside is_transition_valid: the product must refuse as well
+    try:
+        grp = P.refine_policy_reparent(ctx, plan, radius)
+    except P.PorrtError:
+        grp = None
+    oks["reparent"] = (orp is None and grp is None) or (orp is not None and grp is not None and grp["xy"].tobytes() == orp.xy.tobytes() and
+                                                        np.array_equal(grp["parent"], orp.parent) and np.array_equal(grp["belief"], orp.belief_id) and
+                                                        grp["expected_cost"] == orp.expected_costs)
     ok = all(oks.values())
     bad += 0 if ok else 1
-    print("round %2d %s V=%d B=%d policy %d nodes, refine %d trials: %s" % (it, "SHELF" if shelf else "DOOR ", len(xy), B, len(plan.policy_node), n_it, oks), flush=True)
+    print("round %2d %s V=%d B=%d policy %d nodes, refine %d trials, reparent r=%.2f: %s" % (it, "SHELF" if shelf else "DOOR ", len(xy), B, len(plan.policy_node), n_it, radius, oks), flush=True)
 print("FUZZ", "FAILED (%d rounds)" % bad if bad else "ok")
 sys.exit(1 if bad else 0)
