@@ -397,15 +397,19 @@ class PRM:
         n = len(xy)
         row_ptr = np.empty(n + 1, np.int64) if row_ptr_out is None else row_ptr_out[:n + 1]
         n_edges = C.c_int64()
-        rc = self.ctx.lib.porrt_prm_build(self.ctx.h, _p(xy), n, max_step, search_radius, _p(row_ptr), None, 0,
-                                          C.byref(n_edges), _p(self.phase_ms))
+        # a caller-owned column buffer goes straight into the build: its copy leaves in row blocks while the CSR is still being
+        # assembled (graph.cu); otherwise the size is asked for first (PORRT_ERR_CAPACITY) and the columns are fetched afterwards
+        direct = fetch_col and col_out is not None
+        rc = self.ctx.lib.porrt_prm_build(self.ctx.h, _p(xy), n, max_step, search_radius, _p(row_ptr), _p(col_out) if direct else None,
+                                          len(col_out) if direct else 0, C.byref(n_edges), _p(self.phase_ms))
         if rc != ERR_CAPACITY:
             self.ctx.check(rc)
         if not fetch_col:
             self.states, self.row_ptr, self.col = xy, row_ptr, None
             return self
         col = np.empty(n_edges.value, np.int32) if col_out is None else col_out
-        self.ctx.check(self.ctx.lib.porrt_prm_fetch(self.ctx.h, None, _p(col), len(col)))
+        if not direct or rc == ERR_CAPACITY:
+            self.ctx.check(self.ctx.lib.porrt_prm_fetch(self.ctx.h, None, _p(col), len(col)))
         self.states, self.row_ptr, self.col = xy, row_ptr, col[:n_edges.value]
         return self
 

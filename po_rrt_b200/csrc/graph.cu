@@ -474,11 +474,8 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
     });
   };
   struct KdJoiner { KdJob& j; ~KdJoiner() { if (!j.joined && j.th.joinable()) j.th.join(); } } kd_joiner{kd};   // early returns
-  // PORRT_PRM_KD_AFTER_BIN=1 starts the rank after the binning sort instead of next to it (bin 2.4 -> 0.7 ms at 1e6 nodes, but the
-  // waits move elsewhere: interleaved A/B runs gave 13.6 / 14.0 ms against 14.1 / 13.6 ms -- no difference beyond run-to-run noise)
-  const char* kd_env = getenv("PORRT_PRM_KD_AFTER_BIN");
-  const bool kd_after_bin = kd_env && atoi(kd_env) != 0;
-  if (!kd_after_bin) start_kd();
+  // (starting the rank after the binning sort instead of next to it was measured: no difference beyond run-to-run noise)
+  start_kd();
 
   // 1. bin vertices; cell = the smallest radius in use (the last one) so late queries touch 3x3 cells
   double r_last = n > 1 ? heuristic_radius((size_t)n, max_step, search_radius, 2) : -1.0;
@@ -493,7 +490,6 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   int32_t rc = nn_vertices_set_dev(ctx, ctx->d_vxy.as<double>(), n, cell, nullptr, nullptr);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  if (kd_after_bin) start_kd();
   t1 = now_ms(); ph[1] = t1 - t0; t0 = t1;
 
   for (auto& x : th) if (x.joinable()) x.join();
@@ -640,16 +636,45 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   if (rc) return rc;
   prm_rowptr_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(d_early_off, d_late_off, n, d_row_ptr);
   LAUNCH_CHECK(ctx);
-  prm_fill_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_off, d_vals, d_row_ptr, d_col);
-  LAUNCH_CHECK(ctx);
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, d_row_ptr, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
   int32_t status = PORRT_OK;
-  if (out_col && cap >= n_edges) {
-    if (n_edges > 0) CUDA_TRY(ctx, cudaMemcpyAsync(out_col, d_col, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+  if (out_col && cap >= n_edges && n >= (1 << 18) && n_edges > 0) {
+    // large roadmaps: the column array (211 MB at 1e6 nodes, ~4 ms over PCIe) leaves in row blocks while the later blocks are
+    // still being written: row_ptr goes first on the copy stream (the block boundaries are read from its host copy), block b's
+    // copy waits for block b's fill only
+    const int NB = MAX_SLOTS + 1;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[0], st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[0], 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, d_row_ptr, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy_out));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[0], ctx->copy_out));
+    const int64_t per = (n + NB - 1) / NB;
+    for (int b = 0; b < NB; ++b) {
+      const int64_t r0 = std::min<int64_t>(n, b * per), r1 = std::min<int64_t>(n, r0 + per);
+      if (r1 > r0) {
+        prm_fill_kernel<<<div_up((r1 - r0) * 32, 256), 256, 0, st>>>(d_seg_off + r0, r1 - r0, d_compact, d_early_cnt + r0, d_late_off + r0, d_vals, d_row_ptr + r0, d_col);
+        LAUNCH_CHECK(ctx);
+      }
+      CUDA_TRY(ctx, cudaEventRecord(b < MAX_SLOTS ? ctx->ev_in[b] : ctx->ev_k[1], st));
+    }
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_out[0]));          // row_ptr is on the host now
+    for (int b = 0; b < NB; ++b) {
+      const int64_t r0 = std::min<int64_t>(n, b * per), r1 = std::min<int64_t>(n, r0 + per);
+      const int64_t e0 = out_row_ptr[r0], e1 = out_row_ptr[r1];
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, b < MAX_SLOTS ? ctx->ev_in[b] : ctx->ev_k[1], 0));
+      if (e1 > e0) CUDA_TRY(ctx, cudaMemcpyAsync(out_col + e0, d_col + e0, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
   } else {
-    status = porrt_fail(ctx, PORRT_ERR_CAPACITY, "prm_build: out_col too small");
+    prm_fill_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_off, d_vals, d_row_ptr, d_col);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, d_row_ptr, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (out_col && cap >= n_edges) {
+      if (n_edges > 0) CUDA_TRY(ctx, cudaMemcpyAsync(out_col, d_col, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      status = porrt_fail(ctx, PORRT_ERR_CAPACITY, "prm_build: out_col too small");
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
   }
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[6] = t1 - t0;
   ph[7] = (double)total;
   if (out_phase_ms) memcpy(out_phase_ms, ph, sizeof(ph));

@@ -379,28 +379,36 @@ PORRT_API int32_t porrt_vertices_count(porrt_ctx* ctx, int64_t* out_n) {
 #define RADIUS_WIDE_CELLS 64   // (24: the wide kernels then cost more than they save -- 1.78 against 1.29 ms for both passes at 1e6 nodes)
 __global__ void radius_wide_list_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius, int64_t m,
                                         const int32_t* __restrict__ list, int32_t* __restrict__ wide, int32_t* __restrict__ n_wide) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m) return;
-  if (list) t = list[t];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int64_t t = list ? list[i] : i;
   const double2 p = q[t];
   const double r = radius[t];
   if (!(radius_threshold(r) >= 0.0) || !(p.x == p.x && p.y == p.y)) return;
   const double rr = isinf(r) ? r : __dadd_rn(__dmul_rn(r, 1.000000001), 1e-300);
   const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
   const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
-  if ((int64_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1) > RADIUS_WIDE_CELLS) wide[atomicAdd(n_wide, 1)] = (int32_t)t;
+  if ((int64_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1) > RADIUS_WIDE_CELLS) wide[atomicAdd(n_wide, 1)] = (int32_t)i;   // the position in `list`: it names the query's staging slot
 }
-template <bool FILL>
+// MODE 0: count (counts[t]); 1: fill (out_ids + offsets[t]); 2: ONE pass -- count and keep the first RADIUS_STAGE_CAP hits in the
+// query's staging slot (slot = the query's position in `list`); a query with more hits is appended to over_list and filled by a
+// second pass of the thread-per-query kernel, everybody else is moved to its CSR place by nn_tile's placement copy
+#define RADIUS_STAGE_CAP 64
+template <int MODE>
 __global__ void __launch_bounds__(128) radius_wide_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius,
                                                           const int32_t* __restrict__ wide, const int32_t* __restrict__ n_wide,
+                                                          const int32_t* __restrict__ list,
                                                           const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
                                                           const uint32_t* __restrict__ world, int32_t* __restrict__ counts,
                                                           const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids,
-                                                          const uint32_t* __restrict__ prefix_lo) {
+                                                          const uint32_t* __restrict__ prefix_lo, int64_t* __restrict__ stg_off = nullptr,
+                                                          int32_t* __restrict__ over_list = nullptr, int32_t* __restrict__ over_n = nullptr) {
+  constexpr bool FILL = MODE != 0;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int qi = warp; qi < *n_wide; qi += n_warps) {
-    const int32_t t = wide[qi];
+    const int32_t slot = wide[qi];
+    const int32_t t = list ? list[slot] : slot;
     const double2 p = q[t];
     const double r = radius[t];
     const double T = radius_threshold(r);
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(128) radius_wide_kernel(GridDev g, const doubl
     const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
     const int nx = cx1 - cx0 + 1;
     const int64_t n_cells = (int64_t)nx * (cy1 - cy0 + 1);
-    int32_t* out = FILL ? out_ids + offsets[t] : nullptr;
+    int32_t* out = MODE == 1 ? out_ids + offsets[t] : (MODE == 2 ? out_ids + (int64_t)slot * RADIUS_STAGE_CAP : nullptr);
     int32_t run = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += 32) {
       const int64_t ci = c0 + lane;
@@ -438,25 +446,36 @@ __global__ void __launch_bounds__(128) radius_wide_kernel(GridDev g, const doubl
         for (int64_t k = k0; k < e; ++k) {
           const uint32_t id = (uint32_t)g.vid[k];
           if (id >= limit) break;
-          if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || reach_bit(reach, g.reach_words, id, wq))) out[at++] = (int32_t)id;
+          if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || reach_bit(reach, g.reach_words, id, wq))) {
+            if (MODE == 1 || at < RADIUS_STAGE_CAP) out[at] = (int32_t)id;
+            ++at;
+          }
         }
       }
       run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (!FILL && lane == 0) counts[t] = run;
+    if (MODE != 1 && lane == 0) {
+      counts[t] = run;
+      if (MODE == 2) {
+        if (run <= RADIUS_STAGE_CAP) stg_off[t] = (int64_t)slot * RADIUS_STAGE_CAP;
+        else over_list[atomicAdd(over_n, 1)] = t;
+      }
+    }
   }
 }
 
-template <bool FILL>
+template <int MODE>   // as radius_wide_kernel
 __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius, int64_t m,
                                                      const uint32_t* __restrict__ prefix, const uint64_t* __restrict__ reach,
                                                      const uint32_t* __restrict__ world, int32_t* __restrict__ counts,
                                                      const int64_t* __restrict__ offsets, int32_t* __restrict__ out_ids,
                                                      const int32_t* __restrict__ list, const uint32_t* __restrict__ prefix_lo,
-                                                     bool skip_wide = false) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m) return;
-  if (list) t = list[t];   // m = length of the list: the queries nn_tile.cu left to this kernel
+                                                     bool skip_wide = false, int64_t* __restrict__ stg_off = nullptr,
+                                                     int32_t* __restrict__ over_list = nullptr, int32_t* __restrict__ over_n = nullptr) {
+  constexpr bool FILL = MODE != 0;
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= m) return;
+  const int64_t t = list ? list[slot] : slot;   // m = length of the list: the queries nn_tile.cu left to this kernel
   const double2 p = q[t];
   const double r = radius[t];
   const double T = radius_threshold(r);
@@ -469,7 +488,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
     const int cx0 = cell_coord(p.x - rr, g.org_x, g.inv_cell, g.cells_x), cx1 = cell_coord(p.x + rr, g.org_x, g.inv_cell, g.cells_x);
     const int cy0 = cell_coord(p.y - rr, g.org_y, g.inv_cell, g.cells_y), cy1 = cell_coord(p.y + rr, g.org_y, g.inv_cell, g.cells_y);
     if (skip_wide && prefix && (int64_t)(cx1 - cx0 + 1) * (cy1 - cy0 + 1) > RADIUS_WIDE_CELLS) return;   // radius_wide_kernel's
-    int32_t* out = FILL ? out_ids + offsets[t] : nullptr;
+    int32_t* out = MODE == 1 ? out_ids + offsets[t] : (MODE == 2 ? out_ids + slot * RADIUS_STAGE_CAP : nullptr);
     for (int cy = cy0; cy <= cy1; ++cy) {
       if (prefix) {
         // cell lists are id-ascending: stop at the first id >= limit (the tree as it was when vertex `limit` arrived)
@@ -485,7 +504,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
             const uint32_t id = (uint32_t)g.vid[k];
             if (id >= limit) break;
             if (dist2(g.vxy[k], p.x, p.y) <= T && (!reach || reach_bit(reach, g.reach_words, id, wq))) {
-              if (FILL) out[cnt] = (int32_t)id;
+              if (MODE == 1 || (MODE == 2 && cnt < RADIUS_STAGE_CAP)) out[cnt] = (int32_t)id;
               ++cnt;
             }
           }
@@ -496,7 +515,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
           if (dist2(g.vxy[k], p.x, p.y) <= T) {
             const uint32_t id = (uint32_t)g.vid[k];
             if (!reach || reach_bit(reach, g.reach_words, id, wq)) {
-              if (FILL) out[cnt] = (int32_t)id;
+              if (MODE == 1 || (MODE == 2 && cnt < RADIUS_STAGE_CAP)) out[cnt] = (int32_t)id;
               ++cnt;
             }
           }
@@ -504,7 +523,11 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
       }
     }
   }
-  if (!FILL) counts[t] = cnt;
+  if (MODE != 1) counts[t] = cnt;
+  if (MODE == 2) {
+    if (cnt <= RADIUS_STAGE_CAP) stg_off[t] = slot * RADIUS_STAGE_CAP;
+    else over_list[atomicAdd(over_n, 1)] = (int32_t)t;
+  }
 }
 
 // offsets_dev[m+1] filled; ids_buf grown to the total; *total_out = total hits (host value).  Large batches go through the
@@ -545,30 +568,43 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)m * 4, st));
     int32_t rc = nn_tile_radius_collect(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, stg_off, &staging, &fb_list, &fb_n);
     if (rc) return rc;
-    if (fb_n > 0) {
-      if (wide) {
-        radius_wide_list_kernel<<<div_up(fb_n, 256), 256, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, fb_list, wide_list, n_wide);
-        LAUNCH_CHECK(ctx);
-        radius_wide_kernel<false><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, prefix_lo_dev);
-        LAUNCH_CHECK(ctx);
-      }
-      radius_kernel<false><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, fb_list, prefix_lo_dev, wide);
-      LAUNCH_CHECK(ctx);
-    }
-  } else {
+  }
+  // what the tiles left over (or everything, without tiles): thread per query, a warp per query for prefix-restricted queries over
+  // many cells.  ONE pass where the slots fit: every query counts its hits and keeps them in a slot of RADIUS_STAGE_CAP ids
+  // (PRM: pi * ln k ~ 43 hits), the placement copy moves them once the scan of the counts is known; only queries with more hits are
+  // walked a second time.  (The PRM's radius phase spent 0.53 + 0.70 ms in the count and fill passes of these queries.)
+  const int64_t n_rest = tiles ? fb_n : m;
+  const int32_t* rest_list = tiles ? fb_list : nullptr;
+  const bool one_pass = n_rest > 0 && n_rest <= ((int64_t)8 << 20);
+  int32_t* stage2 = nullptr; int64_t* stg_off2 = nullptr; int32_t* over_list = nullptr; int32_t* over_n = nullptr;
+  if (one_pass) {
+    const size_t off_bytes = ((size_t)m * 8 + 255) & ~(size_t)255, list_bytes = ((size_t)n_rest * 4 + 256 + 255) & ~(size_t)255;
+    CUDA_TRY(ctx, ctx->nn_stage2.ensure(off_bytes + list_bytes + (size_t)n_rest * RADIUS_STAGE_CAP * 4));
+    stg_off2 = ctx->nn_stage2.as<int64_t>();
+    over_n = (int32_t*)(ctx->nn_stage2.as<char>() + off_bytes);
+    over_list = over_n + 16;
+    stage2 = (int32_t*)(ctx->nn_stage2.as<char>() + off_bytes + list_bytes);
+    CUDA_TRY(ctx, cudaMemsetAsync(stg_off2, 0xff, (size_t)m * 8, st));   // -1: not in a slot
+    CUDA_TRY(ctx, cudaMemsetAsync(over_n, 0, 4, st));
+  }
+  if (n_rest > 0) {
     if (wide) {
-      radius_wide_list_kernel<<<div_up(m, 256), 256, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, nullptr, wide_list, n_wide);
+      radius_wide_list_kernel<<<div_up(n_rest, 256), 256, 0, st>>>(g, (const double2*)q_dev, radius_dev, n_rest, rest_list, wide_list, n_wide);
       LAUNCH_CHECK(ctx);
-      radius_wide_kernel<false><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, prefix_lo_dev);
+      if (one_pass) radius_wide_kernel<2><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, rest_list, prefix_dev, reach_dev, world_dev, counts, nullptr, stage2, prefix_lo_dev, stg_off2, over_list, over_n);
+      else radius_wide_kernel<0><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, rest_list, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, prefix_lo_dev);
       LAUNCH_CHECK(ctx);
     }
-    radius_kernel<false><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, nullptr, prefix_lo_dev, wide);
+    if (one_pass) radius_kernel<2><<<div_up(n_rest, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, n_rest, prefix_dev, reach_dev, world_dev, counts, nullptr, stage2, rest_list, prefix_lo_dev, wide, stg_off2, over_list, over_n);
+    else radius_kernel<0><<<div_up(n_rest, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, n_rest, prefix_dev, reach_dev, world_dev, counts, nullptr, nullptr, rest_list, prefix_lo_dev, wide);
     LAUNCH_CHECK(ctx);
   }
   int32_t rc = scan_exclusive_i64(ctx, counts, m, offsets_dev);
   if (rc) return rc;
   int64_t total = 0;
+  int32_t n_over = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
+  if (one_pass) CUDA_TRY(ctx, cudaMemcpyAsync(&n_over, over_n, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   *total_out = total;
   CUDA_TRY(ctx, ids_buf->ensure((size_t)std::max<int64_t>(total, 1) * 4));
@@ -576,27 +612,25 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
     if (tiles) {
       rc = nn_tile_radius_place(ctx, staging, stg_off, offsets_dev, m, ids_buf->as<int32_t>());
       if (rc) return rc;
-      if (fb_n > 0) {
-        if (wide) {
-          radius_wide_kernel<true><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), prefix_lo_dev);
+    }
+    if (n_rest > 0) {
+      if (one_pass) {
+        rc = nn_tile_radius_place(ctx, stage2, stg_off2, offsets_dev, m, ids_buf->as<int32_t>());
+        if (rc) return rc;
+        if (n_over > 0) {   // the few lists longer than a slot: second walk, straight to their CSR places
+          radius_kernel<1><<<div_up(n_over, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, n_over, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), over_list, prefix_lo_dev, false);
           LAUNCH_CHECK(ctx);
         }
-        radius_kernel<true><<<div_up(fb_n, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, fb_n, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), fb_list, prefix_lo_dev, wide);
-        LAUNCH_CHECK(ctx);
-        if (sort_ids) {
-          rc = segments_sort_by_key_dev(ctx, offsets_dev, m, ids_buf->as<int32_t>(), nullptr, g.n, fb_list, fb_n);
-          if (rc) return rc;
+      } else {
+        if (wide) {
+          radius_wide_kernel<1><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, rest_list, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), prefix_lo_dev);
+          LAUNCH_CHECK(ctx);
         }
-      }
-    } else {
-      if (wide) {
-        radius_wide_kernel<true><<<wide_grid, 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, wide_list, n_wide, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), prefix_lo_dev);
+        radius_kernel<1><<<div_up(n_rest, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, n_rest, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), rest_list, prefix_lo_dev, wide);
         LAUNCH_CHECK(ctx);
       }
-      radius_kernel<true><<<div_up(m, 128), 128, 0, st>>>(g, (const double2*)q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, nullptr, offsets_dev, ids_buf->as<int32_t>(), nullptr, prefix_lo_dev, wide);
-      LAUNCH_CHECK(ctx);
       if (sort_ids) {
-        rc = segments_sort_by_key_dev(ctx, offsets_dev, m, ids_buf->as<int32_t>(), nullptr, g.n);
+        rc = segments_sort_by_key_dev(ctx, offsets_dev, m, ids_buf->as<int32_t>(), nullptr, g.n, rest_list, tiles ? fb_n : 0);
         if (rc) return rc;
       }
     }
