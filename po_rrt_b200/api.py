@@ -569,11 +569,13 @@ class BeliefGraph:
     """src/belief_graph.rs BeliefGraph as arrays: belief node k = (state xy[k], belief_id[k], node_type[k]); children adjacency
     as CSR in add_edge order.  conditional_dijkstra / extract_policy are the reference's free functions (:89-267)."""
 
-    def __init__(self, ctx, row_ptr, col, xy, node_type, belief_id, beliefs):
+    def __init__(self, ctx, row_ptr, col, xy, node_type, belief_id, beliefs, dim=2):
+        """dim: state dimension (BeliefGraph<N>; 2 -> the two-dimensional entry points, else porrt_*_nd)"""
         self.ctx = ctx
+        self.dim = int(dim)
         self.row_ptr = np.ascontiguousarray(row_ptr, np.int64)
         self.col = np.ascontiguousarray(col, np.int32)
-        self.xy = _f64(xy, 2)
+        self.xy = _f64(xy, self.dim)
         self.node_type = np.ascontiguousarray(node_type, np.uint8)
         self.belief_id = np.ascontiguousarray(belief_id, np.int32)
         self.beliefs = np.ascontiguousarray(np.atleast_2d(np.asarray(beliefs, np.float64)))
@@ -589,7 +591,10 @@ class BeliefGraph:
         out = np.empty(self.V)
         sweeps = C.c_int32()
         c = self.ctx
-        c.check(c.lib.porrt_conditional_dijkstra(c.h, *self._graph_args(), _p(fin), len(fin), _p(out), C.byref(sweeps)))
+        if self.dim == 2:
+            c.check(c.lib.porrt_conditional_dijkstra(c.h, *self._graph_args(), _p(fin), len(fin), _p(out), C.byref(sweeps)))
+        else:
+            c.check(c.lib.porrt_conditional_dijkstra_nd(c.h, self.dim, *self._graph_args(), _p(fin), len(fin), _p(out), C.byref(sweeps)))
         self.sweeps = sweeps.value
         return out
 
@@ -602,8 +607,12 @@ class BeliefGraph:
         while True:
             node, parent = np.empty(cap, np.int32), np.empty(cap, np.int32)
             leaf = np.empty(cap, np.uint8)
-            rc = c.lib.porrt_extract_policy_graph(c.h, *self._graph_args(), _p(dist), _p(node), _p(parent), _p(leaf), cap,
-                                                  C.byref(n), C.byref(cost))
+            if self.dim == 2:
+                rc = c.lib.porrt_extract_policy_graph(c.h, *self._graph_args(), _p(dist), _p(node), _p(parent), _p(leaf), cap,
+                                                      C.byref(n), C.byref(cost))
+            else:
+                rc = c.lib.porrt_extract_policy_graph_nd(c.h, self.dim, *self._graph_args(), _p(dist), _p(node), _p(parent), _p(leaf), cap,
+                                                         C.byref(n), C.byref(cost))
             if rc == ERR_CAPACITY:
                 cap = max(n.value, 2 * cap)
                 continue

@@ -1379,6 +1379,101 @@ def test_qmdp_on_resident_prm(ctx):
     assert np.isfinite(got).any() and np.isinf(got[5]).all()
 
 
+def _py_conditional_dijkstra(row_ptr, col, xs, node_type, belief_id, beliefs, finals):
+    """conditional_dijkstra's fixed point (belief_graph.rs:89-182) in plain Python floats, any state dimension: chaotic iteration from
+    +inf with the reference's operand order per backup (norm2 summed in dimension order from 0.0, Observation sums in stored child
+    order from 0.0) -- monotone, so it ends at the same bits as the heap version"""
+    import math
+    V = len(xs)
+    dist = [math.inf] * V
+    for f in finals:
+        dist[f] = 0.0
+
+    def norm2(a, b):
+        d2 = 0.0
+        for xa, xb in zip(a, b):
+            dx = xb - xa
+            d2 += dx * dx
+        return math.sqrt(d2)
+
+    def tp(pb, cb):
+        s = 0.0
+        for p, q in zip(beliefs[cb], beliefs[pb]):
+            s = s + (q if p > 0.0 else 0.0)
+        return s
+    xs = [list(map(float, x)) for x in xs]
+    cost = [[norm2(xs[u], xs[v]) for v in col[row_ptr[u]:row_ptr[u + 1]]] for u in range(V)]
+    changed = True
+    while changed:
+        changed = False
+        for u in range(V):
+            kids = col[row_ptr[u]:row_ptr[u + 1]]
+            if len(kids) == 0:
+                continue
+            if node_type[u] == O.ACTION:
+                alt = min(c + dist[v] for c, v in zip(cost[u], kids))
+            else:
+                alt = 0.0
+                for c, v in zip(cost[u], kids):
+                    alt += tp(belief_id[u], belief_id[v]) * (c + dist[v])
+            if alt < dist[u]:
+                dist[u] = alt
+                changed = True
+    return np.array(dist)
+
+
+@pytest.mark.parametrize("dim", [3, 7, 9])
+def test_conditional_dijkstra_nd(ctx, dim):
+    """BeliefGraph<N> for the other state dimensions the reference's planner is instantiated with (pto_c.rs:236-240):
+    porrt_conditional_dijkstra_nd / porrt_extract_policy_graph_nd against the fixed point in plain Python floats (bit for bit), and
+    -- with the extra coordinates held at zero -- against the two-dimensional entry points"""
+    rng = np.random.default_rng(100 + dim)
+    nb, nw, n_base = 4, 3, 120
+    beliefs = np.array([[0.5, 0.3, 0.2], [0.625, 0.375, 0.0], [0.0, 0.0, 1.0], [0.0, 1.0, 0.0]])
+    for flat in (False, True):
+        pts = rng.uniform(-1, 1, (n_base, dim))
+        if flat:
+            pts[:, 2:] = 0.0
+        xs, btype, bid = [], [], []
+        for k in range(n_base):
+            for b in range(nb):
+                xs.append(pts[k]); btype.append(O.ACTION); bid.append(b)
+        idx = lambda k, b: k * nb + b
+        children = [[] for _ in range(n_base * nb)]
+        obs = set(rng.choice(np.arange(1, n_base), n_base // 8, replace=False).tolist())
+        for k in obs:                                   # belief 0 splits into {worlds 0, 1} and {world 2}
+            btype[idx(k, 0)] = O.OBSERVATION
+            children[idx(k, 0)] = [idx(k, 1), idx(k, 2)]
+        d2 = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+        thr = np.sort(d2, axis=1)[:, 7].max()
+        for k in range(n_base):
+            near = np.nonzero((d2[k] <= thr) & (np.arange(n_base) != k))[0][:12]
+            for b in range(nb):
+                if btype[idx(k, b)] == O.ACTION:
+                    children[idx(k, b)] = [idx(int(j), b) for j in near]
+        row_ptr = np.zeros(len(children) + 1, np.int64)
+        row_ptr[1:] = np.cumsum([len(c) for c in children])
+        col = np.array([c for ch in children for c in ch], np.int32)
+        finals = [idx(int(k), b) for b in (1, 2, 3) for k in rng.choice(n_base, 2, replace=False)]
+        xs = np.array(xs)
+        g = P.BeliefGraph(ctx, row_ptr, col, xs, btype, bid, beliefs, dim=dim)
+        got = g.conditional_dijkstra(finals)
+        want = _py_conditional_dijkstra(row_ptr.tolist(), col.tolist(), xs, btype, bid, beliefs.tolist(), finals)
+        np.testing.assert_array_equal(got, want)
+        assert np.isfinite(got[0]) and np.isfinite(got).sum() > n_base
+        node, parent, leaf, cost = g.extract_policy(got)
+        assert cost == got[0] and node[0] == 0 and parent[0] == -1 and leaf.sum() >= 1
+        for k in range(1, len(node)):                   # every policy edge is an edge of the graph
+            assert node[k] in col[row_ptr[node[parent[k]]]:row_ptr[node[parent[k]] + 1]]
+        if flat:
+            g2 = P.BeliefGraph(ctx, row_ptr, col, xs[:, :2].copy(), btype, bid, beliefs)
+            d2d = g2.conditional_dijkstra(finals)
+            np.testing.assert_array_equal(got, d2d)
+            n2, p2, l2, c2 = g2.extract_policy(d2d)
+            np.testing.assert_array_equal(node, n2); np.testing.assert_array_equal(parent, p2); np.testing.assert_array_equal(leaf, l2)
+            assert cost == c2
+
+
 @pytest.mark.parametrize("kind,Z,n_min", [("shelf", 4, 1500), ("door", 2, 2500)])
 def test_refine_solution_partial_shortcut(ctx, kind, Z, n_min):
     """PTOPolicyRefiner::refine_solution(RefinmentStrategy::PartialShortCut(n)) (pto_policy_refiner.rs:85-133; main.rs:442 runs it with

@@ -275,3 +275,31 @@ def test_plan_true_random_streams_reach_the_goals():
         costs.append(cost)
         c.close()
     assert costs[0] != costs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [3, 7])
+def test_plan_in_more_dimensions(dim):
+    """state_dim 3 and 7 (two of the reference's instantiations, pto_c.rs:236-240): the world model looks at the first two coordinates,
+    the others are free.  No oracle exists for N != 2: the plan must solve the problem and every step of every returned path must
+    be a transition the caller's own callbacks accept, in a belief the policy can be in"""
+    lib = _lib()
+    occ, zones = util.planning_door_map(200)
+    omap = O.GridMap(occ, zones, util.LOW, util.UP, O.DOOR, 0.3)
+    goals, b0, start = [((0.8, 0.8), [1, 1, 1, 1])], [0.1, 0.1, 0.1, 0.7], (-0.8, -0.8) + (0.0,) * (dim - 2)
+    c = Client(lib, omap, goals, 0.05, b0, dim=dim)
+    err = c.plan(start, 1500, 300000, 0.1 * dim, 5.0, 100, seed=3)
+    assert err is None, err
+    paths, cost = c.paths()
+    n_nodes, n_bn, n_be, sweeps, n_pol = c.sizes()
+    assert len(paths) >= 1 and np.isfinite(cost) and cost > 0 and sweeps > 0 and n_bn == n_nodes * len(c.beliefs)
+    for path in paths:
+        assert len(path[0]) == dim and path[0] == start
+        assert abs(path[-1][0] - 0.8) + abs(path[-1][1] - 0.8) < 0.05          # a goal state
+        for a, b in zip(path[:-1], path[1:]):
+            assert omap.state_validity([[a[0], a[1]]])[0] >= 0 and omap.state_validity([[b[0], b[1]]])[0] >= 0
+            assert omap.edge_validity([[a[0], a[1]]], [[b[0], b[1]]])[0] >= 0
+    # the expected cost is a probability-weighted mean of the paths' lengths
+    lengths = [sum(float(np.linalg.norm(np.subtract(a, b))) for a, b in zip(p[:-1], p[1:])) for p in paths]
+    assert min(lengths) - 1e-9 <= cost <= max(lengths) + 1e-9
+    c.close()
