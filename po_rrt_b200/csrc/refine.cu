@@ -599,6 +599,8 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
           pair_to.push_back(T.xy[2 * (size_t)v]); pair_to.push_back(T.xy[2 * (size_t)v + 1]);
         }
         nb_ptr.push_back((int64_t)nb_ids.size());
+        if (nb_ids.size() > ((size_t)1 << 26))   // 64 M candidate transitions = 2 GB of endpoints: a radius far beyond what the reference is run with
+          return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "refine_policy_reparent: more than 2^26 candidate transitions (radius too large for this roadmap)");
       }
     }
   }
