@@ -169,6 +169,7 @@ struct porrt_ctx {
   cudaStream_t aux_stream = nullptr;   // second compute stream (created on first use): kd rank next to radius / edge batches
   DevBuf scratch[12];
   PinBuf pin[6];
+  PinBuf pin_flags;      // a few counters the kernels write straight into host memory (no DMA engine: see read_flags_dev, nn.cu)
 };
 
 #define CTX_CHECK(ctx) do { if (!(ctx)) return PORRT_ERR_INVALID_ARG; } while (0)
@@ -250,8 +251,9 @@ int32_t nn_flush_appended(porrt_ctx* ctx);   // re-bins the vertex set if porrt_
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
                                  int64_t* offsets_dev /* [m+1] */, DevBuf* ids_buf, int64_t* total_out,
-                                 const uint32_t* prefix_lo_dev = nullptr, bool sort_ids = false);
+                                 const uint32_t* prefix_lo_dev = nullptr, bool sort_ids = false, bool allow_tiles = true);
 int32_t scan_exclusive_i64(porrt_ctx* ctx, const int32_t* counts_dev, int64_t n, int64_t* out_dev /* [n+1] */);
+int32_t read_flags_dev(porrt_ctx* ctx, const int32_t* flags_dev, int n, int32_t* out, cudaStream_t st);   // n <= 16; synchronises st
 int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev,
                                  const int32_t* key_of_id_dev, int64_t key_limit, const int32_t* seg_list_dev = nullptr, int64_t n_listed = 0);
 int32_t radix_sort_pairs(porrt_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);

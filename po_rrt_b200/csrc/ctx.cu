@@ -25,10 +25,11 @@ PORRT_API int32_t porrt_ctx_create(int32_t device, porrt_ctx** out_ctx) {
   ctx->sm_count = prop.multiProcessorCount;
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-  // the main compute stream outranks the helper stream (graph.cu: kd rank next to the radius / edge batches); the opposite order
-  // was measured too (the build waits ~0.2 ms for the helper's ~200 tiny kernels): 10.94-11.08 against 10.98-11.19 ms, within noise
-  bool ok = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
-            cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+  // the helper stream (graph.cu: kd rank next to the radius / edge batches) outranks the main compute stream: its ~170 tiny,
+  // latency-bound kernels are what the PRM build ends up waiting for, and they cost the long kernels next to them almost nothing
+  // (measured at 1e6 nodes, interleaved: 9.97-10.04 ms against 10.11-10.20 ms with the priorities the other way round)
+  bool ok = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
   for (int s = 0; ok && s < MAX_SLOTS; ++s)
@@ -57,6 +58,7 @@ PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
   ctx->kd_buf.release(); ctx->d_prm_row.release(); ctx->d_prm_col.release(); ctx->d_bel_succ.release(); ctx->bel.dev.release();
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   for (PinBuf& b : ctx->pin) b.release();
+  ctx->pin_flags.release();
   for (int s = 0; s < MAX_SLOTS; ++s) {
     if (ctx->ev_in[s]) cudaEventDestroy(ctx->ev_in[s]);
     if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);

@@ -128,6 +128,32 @@ __global__ void kd_rank_kernel(int64_t n, int depth, const int32_t* __restrict__
   }
   rank[i] = r;
 }
+// Pre-order ranks by pointer jumping: rank[i] = rank[root] + sum over the path i -> root of off[a], off[a] = 1 (+ the size of the left
+// sibling's subtree + 1 for a right child).  ceil(log2(depth + 1)) rounds over all nodes instead of one launch per tree depth
+// (47 launches of 8.7 us at 1e6 points).  Ping-pong buffers: a round reads the previous round's (jump, acc) only.
+__global__ void kd_rank_init_kernel(int64_t n, const int32_t* __restrict__ parent, const uint8_t* __restrict__ side,
+                                    const int32_t* __restrict__ child, const int32_t* __restrict__ size, const int32_t* __restrict__ node_depth,
+                                    const int32_t* __restrict__ rank0, int32_t* __restrict__ jump, int32_t* __restrict__ acc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (node_depth[i] == 0) { jump[i] = -1; acc[i] = rank0[i]; return; }   // a root: its rank is where its tree's ranks start
+  const int32_t p = parent[i];
+  int32_t off = 1;
+  if (side[i]) {                                    // right child: the whole left subtree of the parent comes first
+    const int32_t l = child[2 * (int64_t)p];
+    if (l != 0x7fffffff) off += size[l] + 1;
+  }
+  jump[i] = p; acc[i] = off;
+}
+__global__ void kd_rank_jump_kernel(int64_t n, const int32_t* __restrict__ jump_in, const int32_t* __restrict__ acc_in,
+                                    int32_t* __restrict__ jump_out, int32_t* __restrict__ acc_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t j = jump_in[i];
+  int32_t a = acc_in[i], nj = -1;
+  if (j >= 0) { a += acc_in[j]; nj = jump_in[j]; }
+  jump_out[i] = nj; acc_out[i] = a;
+}
 // root_of (nullable): several independent trees in one id space (the modes of a multi-modal PRM): point i belongs to the tree
 // rooted at root_of[i] (= the first id of its group); ranks then start at the root's id, so that the ranks of all trees
 // together are still a permutation of 0..n-1 (tree g occupies the id range of group g)
@@ -171,7 +197,8 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
   KD_LAUNCHED();
   KD_TRY(cudaMemsetAsync(remaining, 0, 8, st));
   // level-synchronous rounds over the first m points until all of them are placed; lockstep = every unplaced point is at depth `d`
-  auto rounds = [&](int64_t m, bool lockstep) -> int32_t {
+  // first_check: the host does not look before that round (a random tree of m points is ~3 ln m deep at least)
+  auto rounds = [&](int64_t m, bool lockstep, int first_check) -> int32_t {
     const int mb = div_up(m, 256);
     for (int d = 0;; ++d) {
       if ((d & 3) == 0) KD_TRY(cudaMemsetAsync(remaining, 0, 4, st));
@@ -180,7 +207,7 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
       KD_LAUNCHED();
       kd_place_kernel<<<mb, 256, 0, st>>>(m, cur, child, side, parent, node_depth, (d & 3) == 3 ? remaining : nullptr, max_depth);
       KD_LAUNCHED();
-      if ((d & 3) != 3) continue;      // the host looks at the number of unplaced points every fourth level only
+      if ((d & 3) != 3 || d < first_check) continue;      // the host looks at the number of unplaced points every fourth level only
       int32_t rem = 0;
       KD_TRY(cudaMemcpyAsync(&rem, remaining, 4, cudaMemcpyDeviceToHost, st));
       KD_TRY(cudaStreamSynchronize(st));
@@ -191,7 +218,7 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
   const int64_t KD_TOP = 65536;
   const bool two_phase = !root_of_dev && n >= 8 * KD_TOP;
   if (two_phase) {
-    int32_t rc = rounds(KD_TOP, true);                  // the top tree: points 0 .. KD_TOP-1 (later points have cur == root but are not looked at)
+    int32_t rc = rounds(KD_TOP, true, 27);              // the top tree: points 0 .. KD_TOP-1 (later points have cur == root but are not looked at)
     if (rc) return rc;
     int32_t top_depth = 0;
     KD_TRY(cudaMemcpyAsync(&top_depth, max_depth, 4, cudaMemcpyDeviceToHost, st));
@@ -203,18 +230,33 @@ int32_t kd_preorder_rank_dev(porrt_ctx* ctx, const double* xy_dev, int64_t n, in
       kd_top_sizes_kernel<<<div_up(KD_TOP, 256), 256, 0, st>>>(KD_TOP, d, node_depth, child, exits, up, size);
       KD_LAUNCHED();
     }
-    rc = rounds(n, false);                              // everybody else, from where the walk left them
+    rc = rounds(n, false, 7);                           // everybody else, from where the walk left them
     if (rc) return rc;
   } else {
-    int32_t rc = rounds(n, true);
+    int32_t rc = rounds(n, true, n >= 4096 ? 11 : 0);
     if (rc) return rc;
   }
   int32_t depth = 0;
   KD_TRY(cudaMemcpyAsync(&depth, max_depth, 4, cudaMemcpyDeviceToHost, st));
   KD_TRY(cudaStreamSynchronize(st));
-  for (int d = 1; d <= depth; ++d) {
-    kd_rank_kernel<<<blocks, 256, 0, st>>>(n, d, node_depth, parent, side, child, size, out_rank_dev);
+  if (depth <= 8) {
+    for (int d = 1; d <= depth; ++d) {
+      kd_rank_kernel<<<blocks, 256, 0, st>>>(n, d, node_depth, parent, side, child, size, out_rank_dev);
+      KD_LAUNCHED();
+    }
+  } else {
+    // cur / exits / up are free now; node_depth is read by the init only, so it serves as the fourth buffer afterwards
+    int32_t* jump_a = cur; int32_t* acc_a = exits; int32_t* jump_b = up; int32_t* acc_b = node_depth;
+    kd_rank_init_kernel<<<blocks, 256, 0, st>>>(n, parent, side, child, size, node_depth, out_rank_dev, jump_a, acc_a);
     KD_LAUNCHED();
+    int covered = 1;                                  // path length a node's acc spans after the rounds so far
+    while (covered <= depth) {
+      kd_rank_jump_kernel<<<blocks, 256, 0, st>>>(n, jump_a, acc_a, jump_b, acc_b);
+      KD_LAUNCHED();
+      std::swap(jump_a, jump_b); std::swap(acc_a, acc_b);
+      covered *= 2;
+    }
+    KD_TRY(cudaMemcpyAsync(out_rank_dev, acc_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
   }
 #undef KD_TRY
 #undef KD_LAUNCHED
@@ -503,7 +545,7 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   // 3. prefix-restricted radius queries: neighbours(k) = { j < k : norm2(x_j, x_k) <= r_k }
   int64_t total = 0;
   rc = nn_radius_count_fill_dev(ctx, ctx->d_vxy.as<double>() + 2 * lo, d_radius + lo, m, d_prefix + lo, nullptr, nullptr, d_off, &ctx->scratch[2], &total,
-                                d_group_base ? d_group_base + lo : nullptr);
+                                d_group_base ? d_group_base + lo : nullptr, false, false);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   t1 = now_ms(); ph[2] = t1 - t0; t0 = t1;
@@ -630,41 +672,51 @@ int32_t prm_build_impl(porrt_ctx* ctx, const double* samples_xy, int64_t n, doub
   LAUNCH_CHECK(ctx);
   rc = scan_exclusive_i64(ctx, d_late_cnt, n, d_late_off);
   if (rc) return rc;
-  prm_late_scatter_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_off, d_cursor, d_vals);
-  LAUNCH_CHECK(ctx);
-  rc = segments_sort_by_key_dev(ctx, d_late_off, n, d_vals, nullptr, n);   // later nodes ascending
-  if (rc) return rc;
-  prm_rowptr_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(d_early_off, d_late_off, n, d_row_ptr);
+  prm_rowptr_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(d_early_off, d_late_off, n, d_row_ptr);   // row lengths are known: early + late counts
   LAUNCH_CHECK(ctx);
   int32_t status = PORRT_OK;
   if (out_col && cap >= n_edges && n >= (1 << 18) && n_edges > 0) {
     // large roadmaps: the column array (211 MB at 1e6 nodes, ~4 ms over PCIe) leaves in row blocks while the later blocks are
-    // still being written: row_ptr goes first on the copy stream (the block boundaries are read from its host copy), block b's
-    // copy waits for block b's fill only
-    const int NB = MAX_SLOTS + 1;
+    // still being sorted and written.  row_ptr goes first on the copy stream, next to the scatter of the late lists (the block
+    // boundaries are read from its host copy); block b = sort of its rows' late lists, fill, copy -- the copy waits for block b only
+    // (small blocks first: the copy engine is the critical path from the moment the first block is ready)
+    const int NB = 5;
+    const int64_t cut[NB + 1] = {0, n / 16, n / 8, n / 4, n / 2, n};
+    cudaEvent_t evs[NB] = {ctx->ev_in[0], ctx->ev_in[1], ctx->ev_in[2], ctx->ev_k[1], ctx->ev_k[2]};
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[0], st));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[0], 0));
     CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, d_row_ptr, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy_out));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[0], ctx->copy_out));
-    const int64_t per = (n + NB - 1) / NB;
+    prm_late_scatter_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_off, d_cursor, d_vals);
+    LAUNCH_CHECK(ctx);
+    const bool dbg = getenv("PORRT_DEBUG") != nullptr;
+    const double td0 = now_ms();
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_out[0]));          // row_ptr is on the host now
+    if (dbg) fprintf(stderr, "[porrt] prm tail: since phase start %.3f ms, row_ptr wait %.3f ms\n", td0 - t0, now_ms() - td0);
     for (int b = 0; b < NB; ++b) {
-      const int64_t r0 = std::min<int64_t>(n, b * per), r1 = std::min<int64_t>(n, r0 + per);
+      const int64_t r0 = cut[b], r1 = cut[b + 1];
       if (r1 > r0) {
+        rc = segments_sort_by_key_dev(ctx, d_late_off + r0, r1 - r0, d_vals, nullptr, n);   // later nodes ascending
+        if (rc) return rc;
         prm_fill_kernel<<<div_up((r1 - r0) * 32, 256), 256, 0, st>>>(d_seg_off + r0, r1 - r0, d_compact, d_early_cnt + r0, d_late_off + r0, d_vals, d_row_ptr + r0, d_col);
         LAUNCH_CHECK(ctx);
       }
-      CUDA_TRY(ctx, cudaEventRecord(b < MAX_SLOTS ? ctx->ev_in[b] : ctx->ev_k[1], st));
-    }
-    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_out[0]));          // row_ptr is on the host now
-    for (int b = 0; b < NB; ++b) {
-      const int64_t r0 = std::min<int64_t>(n, b * per), r1 = std::min<int64_t>(n, r0 + per);
+      cudaEvent_t ev = evs[b];
+      CUDA_TRY(ctx, cudaEventRecord(ev, st));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, ev, 0));
       const int64_t e0 = out_row_ptr[r0], e1 = out_row_ptr[r1];
-      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_out, b < MAX_SLOTS ? ctx->ev_in[b] : ctx->ev_k[1], 0));
       if (e1 > e0) CUDA_TRY(ctx, cudaMemcpyAsync(out_col + e0, d_col + e0, (size_t)(e1 - e0) * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+      if (dbg) fprintf(stderr, "[porrt] prm tail: block %d enqueued at %.3f ms (%lld edges)\n", b, now_ms() - t0, (long long)(e1 - e0));
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (dbg) fprintf(stderr, "[porrt] prm tail: kernels done at %.3f ms\n", now_ms() - t0);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_out));
+    if (dbg) fprintf(stderr, "[porrt] prm tail: copies done at %.3f ms\n", now_ms() - t0);
   } else {
+    prm_late_scatter_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_off, d_cursor, d_vals);
+    LAUNCH_CHECK(ctx);
+    rc = segments_sort_by_key_dev(ctx, d_late_off, n, d_vals, nullptr, n);   // later nodes ascending
+    if (rc) return rc;
     prm_fill_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(d_seg_off, n, d_compact, d_early_cnt, d_late_off, d_vals, d_row_ptr, d_col);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(out_row_ptr, d_row_ptr, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));

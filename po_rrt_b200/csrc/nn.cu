@@ -393,7 +393,7 @@ __global__ void radius_wide_list_kernel(GridDev g, const double2* __restrict__ q
 // MODE 0: count (counts[t]); 1: fill (out_ids + offsets[t]); 2: ONE pass -- count and keep the first RADIUS_STAGE_CAP hits in the
 // query's staging slot (slot = the query's position in `list`); a query with more hits is appended to over_list and filled by a
 // second pass of the thread-per-query kernel, everybody else is moved to its CSR place by nn_tile's placement copy
-#define RADIUS_STAGE_CAP 64
+#define RADIUS_STAGE_CAP 96
 template <int MODE>
 __global__ void __launch_bounds__(128) radius_wide_kernel(GridDev g, const double2* __restrict__ q, const double* __restrict__ radius,
                                                           const int32_t* __restrict__ wide, const int32_t* __restrict__ n_wide,
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(128) radius_kernel(GridDev g, const double2* _
 // vertex sets (prefix_lo) are answered by the thread-per-query kernel above in cell order -- sort_ids puts those in id order too.
 int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const double* radius_dev, int64_t m,
                                  const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev,
-                                 int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out, const uint32_t* prefix_lo_dev, bool sort_ids) {
+                                 int64_t* offsets_dev, DevBuf* ids_buf, int64_t* total_out, const uint32_t* prefix_lo_dev, bool sort_ids, bool allow_tiles) {
   cudaStream_t st = ctx->stream;
   if (m <= 0) {   // an empty shard of a sharded batch
     CUDA_TRY(ctx, cudaMemsetAsync(offsets_dev, 0, 8, st));
@@ -549,7 +549,9 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   int32_t* counts = (int32_t*)(stg_off + m);
   // grouped vertex sets (prefix_lo): the other groups' vertices share the cells, staging them all would only cost; the
   // thread-per-query kernel skips to its own group inside each cell list
-  const bool tiles = nn_tile_usable(ctx, m) && !prefix_lo_dev;
+  // allow_tiles = false (the PRM build): the radii there are LARGER than the cell (cell = the last, smallest radius), so the tiles could
+  // serve a quarter of the queries only -- not worth their merge scripts (0.28 ms per vertex set) and binning
+  const bool tiles = allow_tiles && nn_tile_usable(ctx, m) && !prefix_lo_dev;
   const int32_t* fb_list = nullptr;
   const int32_t* staging = nullptr;
   int32_t fb_n = 0;
@@ -818,6 +820,22 @@ __global__ void invert_perm_kernel(const int32_t* __restrict__ key_of_id, int64_
 }
 
 // key_limit: all keys (ids or key_of_id values) are < key_limit; key_of_id (if given) is a permutation of 0..key_limit-1
+// A handful of device counters for the host WITHOUT the copy engine: a one-warp kernel stores them into pinned host memory (mapped
+// under unified addressing), the stream is synchronised, the host reads them.  A cudaMemcpyAsync of 8 bytes would queue behind
+// whatever the D2H engine is busy with -- the PRM build's 50 MB result blocks held every per-block segment sort up for a millisecond.
+__global__ void flags_to_host_kernel(const int32_t* __restrict__ d, int n, volatile int32_t* h) {
+  if ((int)threadIdx.x < n) h[threadIdx.x] = d[threadIdx.x];
+}
+int32_t read_flags_dev(porrt_ctx* ctx, const int32_t* flags_dev, int n, int32_t* out, cudaStream_t st) {
+  CUDA_TRY(ctx, ctx->pin_flags.ensure(64));
+  volatile int32_t* h = ctx->pin_flags.as<int32_t>();
+  flags_to_host_kernel<<<1, 32, 0, st>>>(flags_dev, n, h);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  for (int k = 0; k < n; ++k) out[k] = h[k];
+  return PORRT_OK;
+}
+
 int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int64_t m, int32_t* ids_dev, const int32_t* key_of_id_dev, int64_t key_limit,
                                  const int32_t* seg_list_dev, int64_t n_listed) {
   // seg_list_dev (nullable): only the n_listed segments named there need sorting (of m segments in all); the rare global radix
@@ -843,8 +861,7 @@ int32_t segments_sort_by_key_dev(porrt_ctx* ctx, const int64_t* offsets_dev, int
     }
     LAUNCH_CHECK(ctx);
     int32_t cnt[2] = {0, 0};
-    CUDA_TRY(ctx, cudaMemcpyAsync(cnt, d_big, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    { const int32_t rcf = read_flags_dev(ctx, d_big, 2, cnt, st); if (rcf) return rcf; }
     n_mid = cnt[0]; n_big = cnt[1];
     if (n_mid > 0 && n_big == 0) {
       if (key_of_id_dev) seg_sort_mid_kernel<true><<<n_mid, 256, 0, st>>>(offsets_dev, d_mid_list, ids_dev, key_of_id_dev, d_inv);
