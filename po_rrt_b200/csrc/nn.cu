@@ -566,9 +566,10 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
     CUDA_TRY(ctx, cudaMemsetAsync(n_wide, 0, 4, st));
   }
   const int wide_grid = ctx->sm_count * 8;
+  int64_t staged_total = -1;   // >= 0: the tiles served every query and this is the number of hits
   if (tiles) {
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)m * 4, st));
-    int32_t rc = nn_tile_radius_collect(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, stg_off, &staging, &fb_list, &fb_n);
+    int32_t rc = nn_tile_radius_collect(ctx, g, q_dev, radius_dev, m, prefix_dev, reach_dev, world_dev, counts, stg_off, &staging, &fb_list, &fb_n, &staged_total);
     if (rc) return rc;
   }
   // what the tiles left over (or everything, without tiles): thread per query, a warp per query for prefix-restricted queries over
@@ -603,11 +604,13 @@ int32_t nn_radius_count_fill_dev(porrt_ctx* ctx, const double* q_dev, const doub
   }
   int32_t rc = scan_exclusive_i64(ctx, counts, m, offsets_dev);
   if (rc) return rc;
-  int64_t total = 0;
+  int64_t total = staged_total;
   int32_t n_over = 0;
-  CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
-  if (one_pass) CUDA_TRY(ctx, cudaMemcpyAsync(&n_over, over_n, 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (staged_total < 0) {   // (otherwise the scan and the placement copy follow the search without a host round trip)
+    CUDA_TRY(ctx, cudaMemcpyAsync(&total, offsets_dev + m, 8, cudaMemcpyDeviceToHost, st));
+    if (one_pass) CUDA_TRY(ctx, cudaMemcpyAsync(&n_over, over_n, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
   *total_out = total;
   CUDA_TRY(ctx, ids_buf->ensure((size_t)std::max<int64_t>(total, 1) * 4));
   if (total > 0) {

@@ -688,7 +688,8 @@ static int32_t nn_tile_build_scripts(porrt_ctx* ctx, const GridDev& g) {
 // the offsets are known.  *fb_list_out / *fb_n_out: the queries left to the thread-per-query kernels.
 int32_t nn_tile_radius_collect(porrt_ctx* ctx, const GridDev& g, const double* q_dev, const double* radius_dev, int64_t m,
                                const uint32_t* prefix_dev, const uint64_t* reach_dev, const uint32_t* world_dev, int32_t* counts_dev,
-                               int64_t* stg_off_dev, const int32_t** staging_out, const int32_t** fb_list_out, int32_t* fb_n_out) {
+                               int64_t* stg_off_dev, const int32_t** staging_out, const int32_t** fb_list_out, int32_t* fb_n_out,
+                               int64_t* staged_total_out) {
   cudaStream_t st = ctx->stream;
   NtBins B;
   int32_t rc = nn_tile_build_scripts(ctx, g);
@@ -713,11 +714,15 @@ int32_t nn_tile_radius_collect(porrt_ctx* ctx, const GridDev& g, const double* q
                                                                B.tiles_per_row, B.n_tiles, counts_dev, stg_off_dev, staging, cursor, stg_cap,
                                                                B.fb_list, B.fb_n);
   LAUNCH_CHECK(ctx);
+  unsigned long long staged = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->nn_fb_n, B.fb_n, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(&staged, cursor, 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   *staging_out = staging;
   *fb_list_out = B.fb_list;
   *fb_n_out = ctx->nn_fb_n;
+  // with nothing left over every reserved slot holds a hit: the cursor IS the total, the caller need not wait for its scan
+  if (staged_total_out) *staged_total_out = ctx->nn_fb_n == 0 ? (int64_t)staged : -1;
   if (getenv("PORRT_DEBUG")) fprintf(stderr, "[porrt] nn tiles: %lld queries, %d left to the thread-per-query kernels\n", (long long)m, ctx->nn_fb_n);
   return PORRT_OK;
 }
