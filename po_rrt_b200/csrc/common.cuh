@@ -121,6 +121,7 @@ struct porrt_ctx {
   DevBuf d_nbr_start, d_nbr_script;   // nn_tile.cu: per-cell merge scripts of the 3 x 3 neighbourhood (built lazily per vertex set)
   bool nbr_ready = false;
   DevBuf nn_stage;       // nn_tile.cu: tile-ordered staging of the radius lists + per-query staging offsets
+  DevBuf comm_tmp;       // comm.cu: staging of the padded all-gather behind ragged exchanges
   DevBuf nn_stage2;      // nn.cu: fixed-size slots of the thread- / warp-per-query radius kernels (one pass: count + stage)
   int32_t nn_fb_n = 0;   // queries of the last tile pass left to the thread-per-query kernels
   int32_t reach_words = 1;  // u64 words per vertex of the reachability filter of the running NN call

@@ -53,7 +53,7 @@ PORRT_API int32_t porrt_ctx_destroy(porrt_ctx* ctx) {
   ctx->d_vxy_sorted.release(); ctx->d_vid_sorted.release(); ctx->d_cell_start.release();
   ctx->d_vxy.release(); ctx->d_vcell.release();
   for (DevBuf& b : ctx->nn_tmp) b.release();
-  ctx->nn_stage.release(); ctx->nn_stage2.release(); ctx->d_nbr_start.release(); ctx->d_nbr_script.release();
+  ctx->nn_stage.release(); ctx->nn_stage2.release(); ctx->comm_tmp.release(); ctx->d_nbr_start.release(); ctx->d_nbr_script.release();
   for (DevBuf& b : ctx->scratch) b.release();
   ctx->kd_buf.release(); ctx->d_prm_row.release(); ctx->d_prm_col.release(); ctx->d_bel_succ.release(); ctx->bel.dev.release();
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

@@ -149,18 +149,26 @@ __device__ __forceinline__ void tile_stage(const GridDev& g, const Tile& T, doub
 //   C  warp per 32 queries: one atomicAdd reserves the warp's slots of a staging buffer, then the lanes write each query's ids
 //      side by side (128-byte lines instead of 32 partial sectors per store).
 // A second, pure copy kernel moves the lists to their CSR places once the global scan of the counts is known.
-// The kernel is persistent and the tile staging double-buffered: while the CTA works on tile i the bulk-async copies of tile
-// i + 1 are in flight into the other buffer (two mbarriers, byte-count completion).
+// The kernel is persistent (as many CTAs as fit an SM, each striding over the tiles).  The tile staging can be double-buffered
+// (NR_BUFS = 2: while the CTA works on tile i the bulk-async copies of tile i + 1 are in flight into the other buffer, two
+// mbarriers, byte-count completion) -- measured against ONE buffer with two more resident CTAs per SM, the latter wins (see NR_BUFS).
 // Queries whose list would not fit (> NR_LCAP hits), cells with more than NR_CCAP candidates, tiles too dense to stage and warps
 // that find the staging buffer full are appended to the fallback list and answered by nn.cu's thread-per-query kernels -- same
 // bits, only slower.
 #define NR_THREADS 128
-#define NR_CAP 768           // staged vertices per tile and buffer: 12 KiB + 3 KiB ids (c5 shape: ~440 per tile)
+#ifndef NR_CAP
+#define NR_CAP 704           // staged vertices per tile and buffer: 11 KiB + 3 KiB ids (c5 shape: ~440 per tile)
 #define NR_CCAP 176          // merged candidates per query cell (3 x 3 cells; c5 shape: 131 +- 11)
 #define NR_LCAP 80           // hits per query kept in the thread's row
 #define NR_LSTRIDE 84        // bytes per row (list positions fit a byte): 21 words, odd -> the lanes' rows fall into different banks
+#define NR_CTAS_PER_SM 6
+// staging buffers per CTA.  2 = the next tile's bulk copies fly while this one is worked on (two mbarriers): 55 KiB, 4 CTAs per SM,
+// 0.58 ms for the whole query at V = Q = 1e6.  1 = one buffer, 37 KiB, 6 CTAs per SM whose other warps cover the copy: 0.545 ms
+// (interleaved A/B on one box; 5 CTAs with one buffer: 0.57-0.60).  More resident warps beat the explicit prefetch here.
+#define NR_BUFS 1
+#endif
 #define NR_RUNS 9
-#define NR_SMEM (2 * (NR_CAP * 16 + (NR_CAP + 24) * 4 + NT_W * NR_CCAP * 2) + NT_W * NR_CCAP * 6 + NR_THREADS * NR_LSTRIDE)
+#define NR_SMEM (NR_BUFS * (NR_CAP * 16 + (NR_CAP + 24) * 4 + NT_W * NR_CCAP * 2) + NT_W * NR_CCAP * 6 + NR_THREADS * NR_LSTRIDE)
 
 __device__ __forceinline__ void nt_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nt_smem_u32(bar)) : "memory");
@@ -270,11 +278,11 @@ __global__ void __launch_bounds__(NR_THREADS) nt_radius_collect_kernel(
     unsigned long long* __restrict__ stg_cursor, int64_t stg_cap, int32_t* __restrict__ fb_list, int32_t* __restrict__ fb_n) {
   extern __shared__ __align__(128) unsigned char nr_smem[];
   double2* const s_xy0 = (double2*)nr_smem;                    // two staging buffers: coordinates | ids | merge scripts
-  double2* const s_xy1 = s_xy0 + NR_CAP;
+  double2* const s_xy1 = NR_BUFS == 2 ? s_xy0 + NR_CAP : s_xy0;
   int32_t* const s_id0 = (int32_t*)(s_xy1 + NR_CAP);
-  int32_t* const s_id1 = s_id0 + NR_CAP + 24;
+  int32_t* const s_id1 = NR_BUFS == 2 ? s_id0 + NR_CAP + 24 : s_id0;
   uint16_t* const s_sc0 = (uint16_t*)(s_id1 + NR_CAP + 24);
-  uint16_t* const s_sc1 = s_sc0 + NT_W * NR_CCAP;
+  uint16_t* const s_sc1 = NR_BUFS == 2 ? s_sc0 + NT_W * NR_CCAP : s_sc0;
   int32_t* s_cid = (int32_t*)(s_sc1 + NT_W * NR_CCAP);         // [NT_W][NR_CCAP] merged candidate ids ...
   uint16_t* s_cxy = (uint16_t*)(s_cid + NT_W * NR_CCAP);       // [NT_W][NR_CCAP] ... and where their coordinates are staged
   uint8_t* s_lst = (uint8_t*)(s_cxy + NT_W * NR_CCAP);         // [NR_THREADS][NR_LSTRIDE] list positions of a query's hits
@@ -306,18 +314,23 @@ __global__ void __launch_bounds__(NR_THREADS) nt_radius_collect_kernel(
     if (sc_bytes) nt_bulk_g2s(d_sc, script + nbr_start[ca], sc_bytes, bar);
   };
   int it = 0;
-  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+  if (NR_BUFS == 2 && tid == 0 && (int)blockIdx.x < n_tiles) {
     const Tile T0 = tile_setup_at(g, qstart, tiles_per_row, NR_CAP, blockIdx.x);
     stage(T0, s_xy0, s_id0, s_sc0, &s_bar[0]);
   }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
+    const int buf = NR_BUFS == 2 ? (it & 1) : 0;
     const Tile T = tile_setup_at(g, qstart, tiles_per_row, NR_CAP, tile);
-    if (tid == 0 && tile + (int)gridDim.x < n_tiles) {   // prefetch the next tile into the other buffer (free since the last barrier)
-      const Tile Tn = tile_setup_at(g, qstart, tiles_per_row, NR_CAP, tile + gridDim.x);
-      stage(Tn, buf ? s_xy0 : s_xy1, buf ? s_id0 : s_id1, buf ? s_sc0 : s_sc1, &s_bar[buf ^ 1]);
+    if (NR_BUFS == 2) {
+      if (tid == 0 && tile + (int)gridDim.x < n_tiles) {   // prefetch the next tile into the other buffer (free since the last barrier)
+        const Tile Tn = tile_setup_at(g, qstart, tiles_per_row, NR_CAP, tile + gridDim.x);
+        stage(Tn, buf ? s_xy0 : s_xy1, buf ? s_id0 : s_id1, buf ? s_sc0 : s_sc1, &s_bar[buf ^ 1]);
+      }
+      nt_mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
+    } else {                                               // one buffer: the other resident CTAs cover the copy
+      if (tid == 0) stage(T, s_xy0, s_id0, s_sc0, &s_bar[0]);
+      nt_mbar_wait(&s_bar[0], (uint32_t)(it & 1));
     }
-    nt_mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
     const double2* xy = buf ? s_xy1 : s_xy0;
     const int32_t* sid = buf ? s_id1 : s_id0;
     const uint16_t* ssc = buf ? s_sc1 : s_sc0;
@@ -708,7 +721,7 @@ int32_t nn_tile_radius_collect(porrt_ctx* ctx, const GridDev& g, const double* q
     CUDA_TRY(ctx, cudaFuncSetAttribute(nt_radius_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NR_SMEM));
     attr_set[ctx->device & 15] = true;
   }
-  const int ctas = (int)std::min<int64_t>(B.n_tiles, (int64_t)ctx->sm_count * 4);   // persistent: 4 CTAs of 55 KiB per SM
+  const int ctas = (int)std::min<int64_t>(B.n_tiles, (int64_t)ctx->sm_count * NR_CTAS_PER_SM);   // persistent: as many CTAs as fit an SM
   nt_radius_collect_kernel<<<ctas, NR_THREADS, NR_SMEM, st>>>(g, (const double2*)q_dev, radius_dev, prefix_dev, reach_dev, world_dev, B.qorder,
                                                                B.qstart, ctx->d_nbr_start.as<int64_t>(), ctx->d_nbr_script.as<uint16_t>(),
                                                                B.tiles_per_row, B.n_tiles, counts_dev, stg_off_dev, staging, cursor, stg_cap,
