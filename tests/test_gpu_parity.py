@@ -495,6 +495,30 @@ def test_prm_build_wide_rows(ctx):
     assert np.diff(prm.row_ptr).max() > 600
 
 
+def test_prm_build_large_result_in_row_blocks(ctx):
+    """>= 2^18 nodes: the one-pass thread- / warp-per-query radius kernels, kd ranks by pointer jumping and, with a caller-owned
+    column buffer, the result copy in row blocks that overlaps the CSR assembly -- against the oracle's sequential add_sample
+    (280 k nodes, 1.2e7 directed edges) and against the fetch-afterwards path"""
+    n_iter = 280_000
+    occ, zones = util.small_door_map(1024, 3)
+    prm, oprm = _prm_compare(ctx, occ, zones, P.DOOR, n_iter, 0.1, 2.0)      # columns fetched after the build
+    samples = O.Pcg64(0).sample_states(util.LOW, util.UP, n_iter)
+    omap, pmap = util.make_pair(ctx, occ, zones, P.DOOR, 0.3)
+    col_out = np.full(len(prm.col) + 1000, -7, np.int32)
+    row_out = np.zeros(n_iter + 2, np.int64)
+    prm2 = P.PRM(pmap)
+    prm2.init((0.0, 0.0))
+    prm2.grow_graph(samples, 0.1, 2.0, col_out=col_out, row_ptr_out=row_out)  # columns leave in row blocks during the build
+    np.testing.assert_array_equal(prm2.row_ptr, prm.row_ptr)
+    np.testing.assert_array_equal(prm2.col, prm.col)
+    assert (col_out[len(prm.col):] == -7).all()                               # nothing written past the last edge
+    small = np.empty(1000, np.int32)                                          # a buffer that is too small: size query + fetch
+    prm3 = P.PRM(pmap)
+    prm3.init((0.0, 0.0))
+    with pytest.raises(P.PorrtError):
+        prm3.grow_graph(samples, 0.1, 2.0, col_out=small)
+
+
 def test_prm_plan_path(ctx):
     occ, zones = synth.shelf_map(200, n_zones=2)
     prm, oprm = _prm_compare(ctx, occ, zones, P.SHELF, 2500, 0.1, 5.0)
