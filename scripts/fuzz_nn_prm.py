@@ -41,7 +41,7 @@ for it in range(rounds):
     # ---------------- radius / nearest
     n = int(rng.integers(1, 30_000))
     pts = vertex_set(n)
-    m = int(rng.integers(1, 600))
+    m = int(rng.integers(1, 600)) if it % 4 else int(rng.integers(2048, 6000))   # every fourth round is large enough for the tile kernels
     q = np.ascontiguousarray(np.concatenate([rng.uniform(-1.2, 1.2, (m, 2)), pts[rng.integers(0, n, max(1, m // 4))]]))
     m = len(q)
     r = rng.choice([0.0, 1e-9, 0.003, 0.02, 0.1, 0.5, 3.0], m, p=[0.1, 0.05, 0.2, 0.3, 0.2, 0.1, 0.05]) * rng.uniform(0.5, 1.5, m)
