@@ -303,3 +303,16 @@ def test_plan_in_more_dimensions(dim):
     lengths = [sum(float(np.linalg.norm(np.subtract(a, b))) for a, b in zip(p[:-1], p[1:])) for p in paths]
     assert min(lengths) - 1e-9 <= cost <= max(lengths) + 1e-9
     c.close()
+
+
+@pytest.mark.gpu
+def test_c_client():
+    """tests/pto_c_client.c: the planner API driven from plain C (gcc -std=c99) with the world model in C callbacks, three-dimensional
+    states, malloc()ed observer arrays the planner frees -- the policy branches on the observed door as it must"""
+    _lib()
+    exe = os.path.join(ROOT, "tests", "_pto_c_client")
+    libdir = os.path.join(ROOT, "po_rrt_b200")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "pto_c_client.c"), "-o", exe, "-L", libdir, "-lpo_rrt_c", "-lm", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pto_c_client: ok" in r.stdout, r.stdout + r.stderr
