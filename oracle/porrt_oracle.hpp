@@ -13,7 +13,8 @@
 //    common.rs) -- tests/test_oracle_golden.py transcribes them.
 //  * Third-party arithmetic restated from the published algorithms, PARITY UNPINNED:
 //      line_drawing 0.8 (Bresenham + Octant), rand 0.8 / rand_pcg 0.3 (Pcg64, seed_from_u64,
-//      gen_range), image 0.23 (PNM decode).  The Pcg64 core is checked against the official
+//      gen_range), image 0.23 (PNM decode), priority-queue 1.0.5 (pop order among equal priorities in the
+//      refiner's reparent).  The Pcg64 core is checked against the official
 //      PCG known-answer vector; the Bresenham restatement against the crate's doc example.
 #pragma once
 #include <array>
