@@ -541,6 +541,14 @@ def belief_measurement(ctx, Z=8, n_min=5000, visibility=0.5, max_step=0.1, searc
                                        "commits": int(ref["commits"]), "expected_cost_before": float(plan.expected_cost),
                                        "expected_cost_after": float(ref["expected_cost"]),
                                        "bit_exact": bool(ref["xy"].tobytes() == oref.xy.tobytes() and ref["expected_cost"] == oref.expected_costs)}
+        # the other strategy (main.rs:221,270): refine_solution(Reparent(0.3)) -- every candidate transition of every tree in one device batch
+        P.refine_policy_reparent(ctx, plan, 0.3)
+        t0 = time.perf_counter(); rep = P.refine_policy_reparent(ctx, plan, 0.3); t_rep = time.perf_counter() - t0
+        t0 = time.perf_counter(); orep = pto.refine_policy_reparent(0.3); t_orep = time.perf_counter() - t0
+        out["refine_reparent_0.3"] = {"gpu_ms": 1e3 * t_rep, "cpu_oracle_ms_1thread": 1e3 * t_orep, "tree_nodes": int(rep["tree_nodes"]),
+                                      "transitions_checked": int(rep["transitions"]), "policy_nodes_after": int(len(rep["node"])),
+                                      "bit_exact": bool(rep["xy"].tobytes() == orep.xy.tobytes() and np.array_equal(rep["parent"], orep.parent) and
+                                                        rep["expected_cost"] == orep.expected_costs)}
     else:
         keep = plan.dist.copy()
         ctx.set_option(P.OPT_FORCE_GLOBAL_SWEEPS, 1)

@@ -379,6 +379,18 @@ PORRT_API int32_t porrt_refine_policy_shortcut(porrt_ctx* ctx, const int32_t* po
 // with the pop order of the reference's priority queue (priority-queue 1.0.5's indexed binary heap and Priority's never-Equal Ord,
 // common.rs:231-251 -- restated from the published algorithm, parity unpinned: no test of the reference fixes the order among equal
 // priorities, which do occur: Observation children share their parent's state).
+// one warp per tree node u: the endpoints of its candidate transitions u -> v and the belief row of its piece
+__global__ void reparent_pairs_kernel(const int64_t* __restrict__ nb_ptr, const int32_t* __restrict__ nb, const double2* __restrict__ xy,
+                                      const int32_t* __restrict__ node_base, const int32_t* __restrict__ node_row, int64_t n_nodes,
+                                      double2* __restrict__ from, double2* __restrict__ to, int32_t* __restrict__ row) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= n_nodes) return;
+  const double2 a = xy[u];
+  const int32_t base = node_base[u], r = node_row[u];
+  for (int64_t k = nb_ptr[u] + lane; k < nb_ptr[u + 1]; k += 32) { from[k] = a; to[k] = xy[base + nb[k]]; row[k] = r; }
+}
+
 namespace {
 struct ReparentHeap {                   // see the comment above; lt / gt are Priority's `<` / `>`
   std::vector<int32_t> heap, pos;
@@ -444,9 +456,10 @@ struct PieceTree {
     return c;
   }
   // nearest_neighbors (:94-126): ids in the reference's visit order
+  struct F { int32_t node; int axis; int stage; };
+  mutable std::vector<F> st;
   void radius(const double* s, double r, std::vector<int32_t>& out) const {
-    struct F { int32_t node; int axis; int stage; };
-    std::vector<F> st(1, F{0, 0, 0});
+    st.assign(1, F{0, 0, 0});
     while (!st.empty()) {
       F& f = st.back();
       const double* fs = &xy[2 * (size_t)f.node];
@@ -542,12 +555,21 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
     }
   }
   // ---- build_tree per piece
+  const bool dbg = getenv("PORRT_DEBUG") != nullptr;
+  auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tph[6] = {now_ms(), 0, 0, 0, 0, 0};
   auto norm2 = [](const double* a, const double* b) { const double dx = b[0] - a[0], dy = b[1] - a[1]; return std::sqrt(dx * dx + dy * dy); };
   std::vector<PieceTree> trees(pieces.size());
   int64_t tree_nodes = 0;
+  std::vector<uint32_t> stamp((size_t)R.V * B, 0);   // visited set of build_tree: stamp == piece + 1
+  struct Visited {
+    std::vector<uint32_t>& s; uint32_t tag;
+    bool count(int64_t id) const { return s[(size_t)id] == tag; }
+    void insert(int64_t id) { s[(size_t)id] = tag; }
+  };
   for (size_t p = 0; p < pieces.size(); ++p) {
     PieceTree& T = trees[p];
-    std::unordered_set<int64_t> visited;
+    Visited visited{stamp, (uint32_t)p + 1};
     for (size_t k = 0; k < pieces[p].size(); ++k) {
       const int64_t pn = pieces[p][k];
       const int64_t bg = (int64_t)pol_node[pn] * B + pol_belief[pn];
@@ -581,48 +603,65 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
     tree_nodes += (int64_t)T.size();
   }
   if (out_tree_nodes) *out_tree_nodes = tree_nodes;
+  tph[1] = now_ms();
   // ---- every (node, neighbour within radius / 2) pair of every tree: ONE device batch of is_transition_valid
   const double r2 = 0.5 * radius;
   std::vector<int64_t> nb_ptr(1, 0);     // per tree node (trees back to back)
-  std::vector<int32_t> nb_ids, pair_row;
-  std::vector<double> pair_from, pair_to;
+  std::vector<int32_t> nb_ids;           // neighbour = tree node index inside its own tree
+  std::vector<int32_t> node_base, node_row;   // per tree node: first node of its tree, belief of its piece
+  std::vector<double> node_xy;
   {
     std::vector<int32_t> nb;
+    int32_t base = 0;
     for (size_t p = 0; p < trees.size(); ++p) {
       const PieceTree& T = trees[p];
+      node_xy.insert(node_xy.end(), T.xy.begin(), T.xy.end());
       for (size_t u = 0; u < T.size(); ++u) {
+        node_base.push_back(base); node_row.push_back(T.belief);
         nb.clear();
         T.radius(&T.xy[2 * u], r2, nb);
-        for (int32_t v : nb) {
-          nb_ids.push_back(v); pair_row.push_back(T.belief);
-          pair_from.push_back(T.xy[2 * u]); pair_from.push_back(T.xy[2 * u + 1]);
-          pair_to.push_back(T.xy[2 * (size_t)v]); pair_to.push_back(T.xy[2 * (size_t)v + 1]);
-        }
+        nb_ids.insert(nb_ids.end(), nb.begin(), nb.end());
         nb_ptr.push_back((int64_t)nb_ids.size());
-        if (nb_ids.size() > ((size_t)1 << 26))   // 64 M candidate transitions = 2 GB of endpoints: a radius far beyond what the reference is run with
+        if (nb_ids.size() > ((size_t)1 << 26))   // 64 M candidate transitions: a radius far beyond what the reference is run with
           return porrt_fail(ctx, PORRT_ERR_UNSUPPORTED, "refine_policy_reparent: more than 2^26 candidate transitions (radius too large for this roadmap)");
       }
+      base += (int32_t)T.size();
     }
   }
   const int64_t n_pairs = (int64_t)nb_ids.size();
+  const int64_t n_nodes_all = (int64_t)node_base.size();
+  tph[2] = now_ms();
   if (out_transitions) *out_transitions = n_pairs;
   std::vector<uint8_t> valid((size_t)std::max<int64_t>(n_pairs, 1));
   std::vector<int32_t> status((size_t)std::max<int64_t>(n_pairs, 1), 0);
   if (n_pairs > 0) {
-    const size_t n = (size_t)n_pairs, nrows = (size_t)B * nv;
-    CUDA_TRY(ctx, ctx->scratch[3].ensure(n * (32 + 12 + 4 + 4 + 1) + nrows + 256));
+    // the device expands (node, neighbour) index pairs into endpoint coordinates itself: 4 bytes per pair cross the bus, not 36
+    const size_t n = (size_t)n_pairs, nn = (size_t)n_nodes_all, nrows = (size_t)B * nv;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    CUDA_TRY(ctx, ctx->scratch[3].ensure(al(n * 16) * 2 + al(n * 12) + al(n * 4) * 3 + al(n) + al(nn * 16) + al((nn + 1) * 8) + al(nn * 4) * 2 + al(nrows) + 256));
     char* b = ctx->scratch[3].as<char>();
-    double* d_from = (double*)b; b += n * 16;
-    double* d_to = (double*)b; b += n * 16;
-    int32_t* d_tmp = (int32_t*)b; b += n * 12;
-    int32_t* d_status = (int32_t*)b; b += n * 4;
-    int32_t* d_row = (int32_t*)b; b += n * 4;
-    uint8_t* d_valid = (uint8_t*)b; b += (n + 15) & ~(size_t)15;
-    uint8_t* d_compat = (uint8_t*)b;
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_from, pair_from.data(), n * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_to, pair_to.data(), n * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_row, pair_row.data(), n * 4, cudaMemcpyHostToDevice, st));
+    auto take = [&](size_t bytes) { char* q = b; b += al(bytes); return q; };
+    double* d_from = (double*)take(n * 16);
+    double* d_to = (double*)take(n * 16);
+    int32_t* d_tmp = (int32_t*)take(n * 12);
+    int32_t* d_status = (int32_t*)take(n * 4);
+    int32_t* d_row = (int32_t*)take(n * 4);
+    int32_t* d_nb = (int32_t*)take(n * 4);
+    uint8_t* d_valid = (uint8_t*)take(n);
+    double* d_nxy = (double*)take(nn * 16);
+    int64_t* d_nptr = (int64_t*)take((nn + 1) * 8);
+    int32_t* d_nbase = (int32_t*)take(nn * 4);
+    int32_t* d_nrow = (int32_t*)take(nn * 4);
+    uint8_t* d_compat = (uint8_t*)take(nrows);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_nb, nb_ids.data(), n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_nxy, node_xy.data(), nn * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_nptr, nb_ptr.data(), (nn + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_nbase, node_base.data(), nn * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_nrow, node_row.data(), nn * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_compat, R.compat.data(), nrows, cudaMemcpyHostToDevice, st));
+    reparent_pairs_kernel<<<div_up(n_nodes_all * 32, 256), 256, 0, st>>>(d_nptr, d_nb, (const double2*)d_nxy, d_nbase, d_nrow, n_nodes_all,
+                                                                          (double2*)d_from, (double2*)d_to, d_row);
+    LAUNCH_CHECK(ctx);
     const int32_t rc = transition_valid_dev(ctx, d_from, d_to, n_pairs, d_compat, d_row, nv, d_tmp, d_valid, d_status);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(valid.data(), d_valid, n, cudaMemcpyDeviceToHost, st));
@@ -631,6 +670,7 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
     for (int64_t k = 0; k < n_pairs; ++k)   // every node is popped at least once and tests all its pairs: a panic anywhere is reached
       if (status[(size_t)k] < 0) return porrt_fail(ctx, PORRT_ERR_PANIC, "refine_policy_reparent: is_transition_valid panics (code " + std::to_string(status[(size_t)k]) + ")");
   }
+  tph[3] = now_ms();
   // ---- reparent (:282-322)
   {
     int64_t base = 0;                    // first tree node of the piece in nb_ptr
@@ -655,6 +695,9 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
       base += (int64_t)T.size();
     }
   }
+  tph[4] = now_ms();
+  if (dbg) fprintf(stderr, "[porrt] reparent: trees %.2f ms, candidate pairs %.2f ms (%lld), device batch %.2f ms, label-correcting loop %.2f ms\n",
+                   tph[1] - tph[0], tph[2] - tph[1], (long long)n_pairs, tph[3] - tph[2], tph[4] - tph[3]);
   // ---- recompose (:324-393): leaf -> root of every tree, reversed; then piece ends -> successor piece starts
   std::vector<std::vector<int32_t>> paths(trees.size());
   int64_t n_out = 0;
