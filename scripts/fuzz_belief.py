@@ -45,7 +45,16 @@ for it in range(rounds):
     except RuntimeError as e:
         print("round %2d: reference panic (%s), skipped" % (it, e)); continue
     typ, _, _, _ = pto.belief_graph.export()
-    opol = pto.extract_policy()
+    try:
+        opol = pto.extract_policy()
+    except RuntimeError as e:   # infinite costs at the root: the reference's walk would not return
+        try:
+            P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
+            refused = False
+        except P.PorrtError:
+            refused = True
+        bad += 0 if refused else 1
+        print("round %2d: the reference's extract_policy would not return; product refuses: %s" % (it, refused)); continue
     oks = {}
     plan = P.plan_belief_space(pmap, rp, col, ev, xy, nvid, b0, fin_ids, P.words_from_bits(fin_bits))
     B = len(plan.beliefs)
