@@ -64,6 +64,7 @@ class ClockSampler:
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
         self.rows = []          # (t, sm_mhz, max_mhz, power_w, [4 reason flags])
         self.stop_flag = False
         self.p = None
@@ -75,6 +76,7 @@ class ClockSampler:
             phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
             self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            float(pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM))   # a box whose NVML cannot be read goes to nvidia-smi below
             self.source = "nvml"
             self.t = threading.Thread(target=self._poll_nvml, daemon=True)
             self.t.start()
@@ -95,8 +97,14 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:   # (one query failing must not cost the clock sample)
+                    r = 0
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = 0.0
                 self.rows.append((time.perf_counter(), sm, self.max_mhz, pw, [bool(r & m) for m in masks]))
             except Exception:
                 pass
@@ -116,6 +124,15 @@ class ClockSampler:
             self.p.terminate()
         if self.source is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        if not self.rows:   # the poll never produced a row: one nvidia-smi query right after the region is better than no clock record
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
+                r = [x.strip() for x in out.split(",")]
+                self.rows.append((t1, float(r[0]), float(r[1]), float(r[2]), [x.lower().startswith("active") for x in r[3:7]]))
+                self.source = "nvidia-smi (one query right after the timed region; the in-process poll returned nothing)"
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock poll returned nothing"], "samples": 0, "source": self.source}
         rows = [r for r in self.rows if t0 <= r[0] <= t1]
         in_region = len(rows)
         if not rows:    # nothing landed inside (should not happen with the 2 ms poll): nearest samples around the region
