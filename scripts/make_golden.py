@@ -69,3 +69,12 @@ out2 = {"mm_" + k: v for k, v in sch.items()}
 out2.update(mm_policy=np.asarray(tpol.original), mm_policy_parent=np.asarray(tpol.parent), mm_policy_cost=np.float64(tpol.expected_costs))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "standin_v2.npz"), **out2)
 print("wrote tests/golden/standin_v2.npz:", {k: np.asarray(v).shape for k, v in out2.items()})
+
+# ---- v3: both refinement strategies on the belief-space policy of the planning map (pto_policy_refiner.rs:85-133)
+sc = pto.refine_policy_shortcut(300)
+rp3 = pto.refine_policy_reparent(0.3)
+out3 = dict(sc_xy=sc.xy, sc_parent=sc.parent, sc_belief=sc.belief_id, sc_original=sc.original, sc_cost=np.float64(sc.expected_costs),
+            rp_xy=rp3.xy, rp_parent=rp3.parent, rp_belief=rp3.belief_id, rp_original=rp3.original, rp_leafs=rp3.leafs,
+            rp_cost=np.float64(rp3.expected_costs))
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "standin_v3.npz"), **out3)
+print("wrote tests/golden/standin_v3.npz:", {k: np.asarray(v).shape for k, v in out3.items()})

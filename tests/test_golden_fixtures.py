@@ -120,3 +120,51 @@ def test_cuda_reproduces_golden_mmprm():
         assert cost == float(G2["mm_policy_cost"])
     finally:
         ctx.close()
+
+
+G3 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "standin_v3.npz"))
+
+
+def _refined_matches(prefix, xy, parent, belief, original, cost):
+    np.testing.assert_array_equal(np.asarray(xy), G3[prefix + "_xy"])
+    np.testing.assert_array_equal(np.asarray(parent, np.int64), G3[prefix + "_parent"])
+    np.testing.assert_array_equal(np.asarray(belief, np.int64), G3[prefix + "_belief"])
+    np.testing.assert_array_equal(np.asarray(original, np.int64), G3[prefix + "_original"])
+    assert cost == float(G3[prefix + "_cost"])
+
+
+def test_oracle_reproduces_golden_refiners():
+    """refine_solution(PartialShortCut(300)) and refine_solution(Reparent(0.3)) on the planning map's belief-space policy: pins the
+    refiners' restatement (sampler stream, decompose / recompose, the priority queue's pop order) against drift"""
+    import porrt_testutil as util
+    pocc, pzones = util.planning_door_map(200)
+    pmap = O.GridMap(pocc, pzones, LOW, UP, O.DOOR, 0.5)
+    pto = O.PTO(pmap, LOW, UP, seed=0)
+    assert pto.grow_graph((-0.8, -0.8), O.SquareGoal([((0.8, 0.8), [1, 1, 1, 1])], 0.05), 0.05, 5.0, 1500, 100000) == 0
+    pto.build_belief_graph(list(G["bel_b0"])); pto.compute_expected_costs_to_goals(); pto.extract_policy()
+    sc = pto.refine_policy_shortcut(300)
+    _refined_matches("sc", sc.xy, sc.parent, sc.belief_id, sc.original, sc.expected_costs)
+    rp = pto.refine_policy_reparent(0.3)
+    _refined_matches("rp", rp.xy, rp.parent, rp.belief_id, rp.original, rp.expected_costs)
+    np.testing.assert_array_equal(rp.leafs, G3["rp_leafs"])
+    assert len(rp.xy) < len(sc.xy)      # reparenting straightens the pieces: fewer policy nodes
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_refiners():
+    import po_rrt_b200 as P
+    import porrt_testutil as util
+    ctx = P.Context(0)
+    try:
+        pocc, pzones = util.planning_door_map(200)
+        bmap = P.Map(ctx, pocc, LOW, UP); bmap.add_zones(pzones, 0.5)
+        plan = P.plan_belief_space(bmap, G["bel_row_ptr"], G["bel_col"], G["bel_ev"], G["bel_xy"], G["bel_nvid"], list(G["bel_b0"]),
+                                   list(G["bel_fin_ids"]), P.words_from_bits(G["bel_fin_bits"]))
+        B = len(plan.beliefs)
+        sc = P.refine_policy_shortcut(ctx, plan, 300)
+        _refined_matches("sc", sc["xy"], sc["parent"], sc["belief"], sc["node"].astype(np.int64) * B + sc["belief"], sc["expected_cost"])
+        rp = P.refine_policy_reparent(ctx, plan, 0.3)
+        _refined_matches("rp", rp["xy"], rp["parent"], rp["belief"], rp["node"].astype(np.int64) * B + rp["belief"], rp["expected_cost"])
+        np.testing.assert_array_equal(np.nonzero(rp["is_leaf"])[0], G3["rp_leafs"])
+    finally:
+        ctx.close()
