@@ -562,6 +562,8 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
   std::vector<PieceTree> trees(pieces.size());
   int64_t tree_nodes = 0;
   std::vector<uint32_t> stamp((size_t)R.V * B, 0);   // visited set of build_tree: stamp == piece + 1
+  std::vector<uint32_t> expanded((size_t)R.V * B, 0);  // belief nodes already expanded in the running search (tag per seed)
+  uint32_t expand_tag = 0;
   struct Visited {
     std::vector<uint32_t>& s; uint32_t tag;
     bool count(int64_t id) const { return s[(size_t)id] == tag; }
@@ -584,9 +586,14 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
     for (size_t seed = 0; seed < n_seed; ++seed) {
       const double sx[2] = {T.xy[2 * seed], T.xy[2 * seed + 1]};
       q.assign(1, {(int32_t)seed, T.bgid[seed]});
+      ++expand_tag;
       for (size_t head = 0; head < q.size(); ++head) {
         const int32_t tree_id = q[head].first;
         const int64_t from_bg = q[head].second;
+        // the reference's queue holds a belief node once per parent that pushed it; only the FIRST entry can add anything (what it
+        // leaves behind is visited or beyond the seed's radius for every later one too), so the others are skipped unexpanded
+        if (expanded[(size_t)from_bg] == expand_tag) continue;
+        expanded[(size_t)from_bg] = expand_tag;
         for_children(from_bg, [&](int64_t child) {
           const double* cs = &R.xy[2 * (size_t)(child / B)];
           if (visited.count(child)) return;
