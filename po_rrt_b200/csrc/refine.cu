@@ -643,9 +643,12 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
         nb.clear();
         if (brute) {                      // hits in kd visit order = the nodes within r2 in pre-order of the kd tree
           const double qx = T.xy[2 * u], qy = T.xy[2 * u + 1];
+          // the square root only where it can matter: d2 beyond r2^2 by more than a few ulps is a miss whatever sqrt rounds to
+          const double pre = r2 * r2 * (1.0 + 1e-12) + 1e-300;
           for (size_t k = 0; k < T.size(); ++k) {
             const double dx = qx - oxy[2 * k], dy = qy - oxy[2 * k + 1];
-            if (std::sqrt(dx * dx + dy * dy) <= r2) nb.push_back(order[k]);
+            const double d2 = dx * dx + dy * dy;
+            if (d2 <= pre && std::sqrt(d2) <= r2) nb.push_back(order[k]);
           }
         } else {
           T.radius(&T.xy[2 * u], r2, nb);
