@@ -104,5 +104,11 @@ def test_rust_build_script_lists_the_makefile_sources():
         if h.startswith(".."):
             continue
         assert '"%s"' % h in rs, h
-    for f in ("b200_ffi.rs", "b200.rs", "prm_b200.rs", "qmdp_b200.rs", "pto_b200.rs"):
+    for f in ("b200_ffi.rs", "b200.rs", "prm_b200.rs", "qmdp_b200.rs", "pto_b200.rs", "refiner_b200.rs"):
         assert os.path.exists(os.path.join(ROOT, "integration", "rust", "src", f))
+    # every library function the hand-written Rust files call is declared in the generated FFI block
+    ffi = open(os.path.join(ROOT, "integration", "rust", "src", "b200_ffi.rs")).read()
+    for f in ("b200.rs", "prm_b200.rs", "qmdp_b200.rs", "pto_b200.rs", "refiner_b200.rs"):
+        src = open(os.path.join(ROOT, "integration", "rust", "src", f)).read()
+        for name in sorted(set(re.findall(r"\b(porrt_[a-z0-9_]+)\s*\(", src))):
+            assert ("pub fn %s(" % name) in ffi, (f, name)
