@@ -321,3 +321,36 @@ def test_c_client():
                     os.path.join(ROOT, "tests", "pto_c_client.c"), "-o", exe, "-L", libdir, "-lpo_rrt_c", "-lm", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "pto_c_client: ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_planner_reports_the_references_panics():
+    """where pto_c.rs would panic -- and with it abort the calling process -- plan() records the message instead (host-side checks:
+    none of these reaches the device)"""
+    lib = _lib()
+    omap, goals, b0, start = _shelf_problem()
+    c = Client(lib, omap, goals, 0.05, b0)
+    s3 = (C.c_double * 3)(0.0, 0.0, 0.0)
+    lib.set_search_parameters(c.h, 10, 10, 0.05, 5.0)
+    lib.plan(c.h, s3, 3)                                                     # assert_eq!(start_size, state_dim), pto_c.rs:229
+    assert b"start_size" in lib.get_planning_error(c.h)
+    assert "Start from a valid state" in c.plan((5.0, 5.0), 10, 10, 0.05, 5.0, 0)           # pto.rs:61
+    assert "final nodes are not reached" in c.plan(start, 5, 5, 0.05, 5.0, 0)               # pto_c.rs:214 .expect(..)
+    paths, cost = c.paths()
+    assert paths == [] and cost == 0.0                                       # outputs stay empty after a failed plan
+    lib.set_problem_dimensions(c.h, 2, 0)
+    assert "n_worlds" in c.plan(start, 5, 5, 0.05, 5.0, 0)
+    lib.set_problem_dimensions(c.h, 17, c.nw)
+    big = (C.c_double * 17)(*([0.0] * 17))
+    lib.plan(c.h, big, 17)
+    assert b"case not yet handled" in lib.get_planning_error(c.h)            # pto_c.rs:238
+    c.close()
+    # a problem without callbacks: Option::unwrap() on None in the reference
+    h = lib.new_planning_problem()
+    lib.set_problem_dimensions(h, 2, 2)
+    lo, up = (C.c_double * 2)(-1, -1), (C.c_double * 2)(1, 1)
+    lib.set_lower_sampling_bound(h, lo, 2); lib.set_upper_sampling_bound(h, up, 2)
+    s2 = (C.c_double * 2)(0.0, 0.0)
+    lib.plan(h, s2, 2)
+    assert b"callback is missing" in lib.get_planning_error(h)
+    lib.delete_planning_problem(h)
+    lib.delete_planning_problem(None)                                        # delete_planning_problem(None) is a no-op there too (:103)
