@@ -354,3 +354,27 @@ def test_planner_reports_the_references_panics():
     assert b"callback is missing" in lib.get_planning_error(h)
     lib.delete_planning_problem(h)
     lib.delete_planning_problem(None)                                        # delete_planning_problem(None) is a no-op there too (:103)
+
+
+def test_growth_matches_the_oracle_without_a_device():
+    """PTO::grow_graph inside the planner is host code (N-dimensional kd-tree, steer, reachability, the two sampler streams, the
+    caller's callbacks): on a box without a GPU plan() stops at the value backups, but the roadmap it grew must already be the
+    oracle's -- same number of iterations, same number of nodes -- on a shelf and a door problem"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: test_plan_matches_the_oracle_pipeline covers the whole pipeline")
+    lib = _lib()
+    omap, goals, b0, start = _shelf_problem()
+    problems = [(omap, goals, b0, start, (500, 20000, 0.05, 5.0))]
+    occ, zones = util.planning_door_map(200)
+    problems.append((O.GridMap(occ, zones, util.LOW, util.UP, O.DOOR, 0.3), [((0.8, 0.8), [1, 1, 1, 1])], [0.1, 0.1, 0.1, 0.7], (-0.8, -0.8),
+                     (700, 20000, 0.05, 5.0)))
+    for omap, goals, b0, start, (n_min, n_max, max_step, search_radius) in problems:
+        c = Client(lib, omap, goals, 0.05, b0)
+        err = c.plan(start, n_min, n_max, max_step, search_radius, 0)
+        assert err and "no CPU fallback" in err
+        pto = O.PTO(omap, util.LOW, util.UP, seed=0)
+        assert pto.grow_graph(start, O.SquareGoal(goals, 0.05), max_step, search_radius, n_min, n_max) == 0
+        assert c.metrics()[0] == pto.n_it() and c.sizes()[0] == pto.graph.n_nodes()
+        assert c.sizes()[1] == pto.graph.n_nodes() * len(c.beliefs)          # the belief graph was built (observer callbacks) before the device step
+        c.close()
