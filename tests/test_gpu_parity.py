@@ -1526,6 +1526,7 @@ def test_refine_solution_partial_shortcut(ctx, kind, Z, n_min):
         np.testing.assert_array_equal(got["parent"], want.parent)
         np.testing.assert_array_equal(np.nonzero(got["is_leaf"])[0], want.leafs)
         assert got["expected_cost"] == want.expected_costs, n_it
+        assert int(got["is_leaf"].sum()) == int(plan.policy_leaf.sum())   # the reference's own check: pto_policy_refiner.rs:448 (leafs preserved)
     assert got["commits"] > 0 and got["expected_cost"] <= plan.expected_cost + 1e-9
 
 
@@ -1559,6 +1560,7 @@ def test_refine_solution_reparent(ctx, kind, Z, n_min):
         np.testing.assert_array_equal(got["parent"], want.parent)
         np.testing.assert_array_equal(np.nonzero(got["is_leaf"])[0], want.leafs)
         assert got["expected_cost"] == want.expected_costs, radius
+        assert int(got["is_leaf"].sum()) == int(plan.policy_leaf.sum())   # the reference's own check: pto_policy_refiner.rs:477,507 (leafs preserved)
         assert got["tree_nodes"] >= len(plan.policy_node) and got["transitions"] >= got["tree_nodes"]   # every node is its own neighbour
         improved |= got["expected_cost"] != plan.expected_cost
     assert improved   # at least one radius changes the policy
