@@ -344,6 +344,8 @@ int32_t porrt_qmdp_react(porrt_ctx* ctx, int64_t V, const int64_t* row_ptr, cons
 int32_t porrt_heuristic_radius(int64_t n_nodes, double max_step, double search_radius, int32_t dim, double* out_radius);
 /* steer (common.rs:215-225), batched: to_xy[k] is pulled towards from_xy[k] when norm1(from, to) > max_step (in place) */
 int32_t porrt_steer(const double* from_xy, double* to_xy, int64_t n, double max_step);
+/* the same for states of `dim` doubles (1 <= dim <= PORRT_MAX_STATE_DIM; the reference instantiates steer<N> for N = 2, 3, 7, 9) */
+int32_t porrt_steer_nd(const double* from, double* to, int64_t n, int32_t dim, double max_step);
 
 /* ContinuousSampler / DiscreteSampler (sample_space.rs:6-60): one Pcg64::seed_from_u64(seed) stream per handle (the reference
  * seeds with 0; PTO keeps one continuous and one discrete sampler, two independent streams with the same seed, pto.rs:141-149) */

@@ -75,6 +75,7 @@ SIGNATURES = {
     "porrt_qmdp_react": (i32, [vp, i64, vp, vp, vp, i32, vp, i64, vp, i32, f64, vp, vp, i64, pp(i64), pp(i64)]),
     "porrt_heuristic_radius": (i32, [i64, f64, f64, i32, pp(f64)]),
     "porrt_steer": (i32, [vp, vp, i64, f64]),
+    "porrt_steer_nd": (i32, [vp, vp, i64, i32, f64]),
     "porrt_sampler_create": (i32, [C.c_uint64, pp(vp)]),
     "porrt_sampler_destroy": (i32, [vp]),
     "porrt_sampler_continuous": (i32, [vp, vp, vp, i32, i64, vp]),

@@ -675,10 +675,13 @@ def heuristic_radius(n_nodes, max_step, search_radius, dim=2):
     return out.value
 
 
-def steer(from_xy, to_xy, max_step):
-    """common.rs:215-225, batched; returns the steered copies of to_xy"""
-    f, t = _f64(from_xy, 2), _f64(to_xy, 2).copy()
-    rc = _lib.load().porrt_steer(_p(f), _p(t), len(f), float(max_step))
+def steer(from_xy, to_xy, max_step, dim=2):
+    """common.rs:215-225, batched; returns the steered copies of to_xy (dim: state dimension, steer<N>)"""
+    f, t = _f64(from_xy, dim), _f64(to_xy, dim).copy()
+    if dim == 2:
+        rc = _lib.load().porrt_steer(_p(f), _p(t), len(f), float(max_step))
+    else:
+        rc = _lib.load().porrt_steer_nd(_p(f), _p(t), len(f), int(dim), float(max_step))
     if rc:
         raise PorrtError(rc, "porrt_steer")
     return t

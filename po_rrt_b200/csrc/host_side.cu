@@ -23,15 +23,19 @@ PORRT_API int32_t porrt_heuristic_radius(int64_t n_nodes, double max_step, doubl
 }
 
 PORRT_API int32_t porrt_steer(const double* from_xy, double* to_xy, int64_t n, double max_step) {
-  if (n < 0 || (n > 0 && (!from_xy || !to_xy))) return PORRT_ERR_INVALID_ARG;
+  return porrt_steer_nd(from_xy, to_xy, n, 2, max_step);
+}
+// steer<N> for states of `dim` doubles (the reference instantiates N = 2, 3, 7, 9)
+PORRT_API int32_t porrt_steer_nd(const double* from, double* to, int64_t n, int32_t dim, double max_step) {
+  if (n < 0 || dim <= 0 || dim > PORRT_MAX_STATE_DIM || (n > 0 && (!from || !to))) return PORRT_ERR_INVALID_ARG;
   for (int64_t k = 0; k < n; ++k) {
-    const double* f = from_xy + 2 * k;
-    double* t = to_xy + 2 * k;
+    const double* f = from + (size_t)dim * k;
+    double* t = to + (size_t)dim * k;
     double step = 0.0;                                        // norm1(from, to): sum of |to - from| in dimension order
-    for (int d = 0; d < 2; ++d) step += std::fabs(t[d] - f[d]);
+    for (int d = 0; d < dim; ++d) step += std::fabs(t[d] - f[d]);
     if (step > max_step) {
       const double lambda = max_step / step;
-      for (int d = 0; d < 2; ++d) t[d] = f[d] + (t[d] - f[d]) * lambda;
+      for (int d = 0; d < dim; ++d) t[d] = f[d] + (t[d] - f[d]) * lambda;
     }
   }
   return PORRT_OK;

@@ -117,6 +117,16 @@ def test_steer_and_radius():
         assert P.heuristic_radius(n, 0.1, 2.0, 2) == O.lib().orc_heuristic_radius(n, 0.1, 2.0, 2)
         assert P.heuristic_radius(n, 0.05, 5.0, 2) == O.lib().orc_heuristic_radius(n, 0.05, 5.0, 2)
     assert P.heuristic_radius(1, 0.1, 2.0, 2) == 0.0
+    # steer<N> for the other state dimensions (common.rs:215-225 is generic): plain Python floats in the reference's operation order
+    for dim in (3, 7, 9):
+        f, t = rng.uniform(-1, 1, (300, dim)), rng.uniform(-1, 1, (300, dim))
+        got = P.steer(f, t, 0.3, dim=dim)
+        for k in range(300):
+            step = 0.0
+            for a, b in zip(f[k].tolist(), t[k].tolist()):
+                step += abs(b - a)
+            want = [a + (b - a) * (0.3 / step) for a, b in zip(f[k].tolist(), t[k].tolist())] if step > 0.3 else t[k].tolist()
+            assert got[k].tolist() == want
 
 
 # ------------------------------------------------------------------ sample_space.rs
