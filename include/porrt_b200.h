@@ -321,6 +321,16 @@ int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* pol_node, co
                                      int32_t* out_parent, uint8_t* out_is_leaf, int64_t cap, int64_t* out_n, double* out_expected_cost,
                                      int64_t* out_tree_nodes /* nullable */, int64_t* out_transitions /* nullable */);
 
+/* Policy::decompose (common.rs:85-129) and Policy::compute_expected_costs_to_goals (common.rs:131-153), the two pieces of common.rs the
+ * refiners are built around, as host-side rows (no device, no ctx).  A policy = parent[k] per node in creation order (parent[0] = -1,
+ * parent[k] < k; children in add_edge order = increasing index).  decompose: pieces back to back (out_piece_ptr[n_pieces + 1],
+ * out_piece_nodes[n]) and the skeleton as a CSR (nullable); PORRT_ERR_CAPACITY + *out_n_pieces when cap_pieces is too small.
+ * expected_cost: xy[2k..] states, belief_id[k] into beliefs[B * n_worlds], cost = norm2; the reference's summation order. */
+int32_t porrt_policy_decompose(const int32_t* parent, int64_t n, int32_t* out_piece_ptr, int32_t* out_piece_nodes, int32_t* out_succ_ptr,
+                               int32_t* out_succ, int32_t cap_pieces, int32_t* out_n_pieces);
+int32_t porrt_policy_expected_cost(const double* xy, const int32_t* belief_id, const int32_t* parent, int64_t n, const double* beliefs,
+                                   int32_t B, int32_t n_worlds, double* out_expected_cost);
+
 /* reachable_belief_states (map_io.rs:515-546 / map_shelves_io.rs:490-520): host-side closure over the uploaded map's
  * zones; out[cap * n_worlds]; *out_B = count (PORRT_ERR_CAPACITY if > cap). */
 int32_t porrt_reachable_belief_states(porrt_ctx* ctx, const double* start_belief, double* out, int32_t cap, int32_t* out_B);

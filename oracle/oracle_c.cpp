@@ -503,6 +503,24 @@ API void* orc_pto_refine_shortcut(void* p, uint64_t n_iterations) {
   if (!refiner_refine_shortcut(*pto->fns, pol, pto->belief_graph, (size_t)n_iterations, h->p)) { delete h; return nullptr; }
   return h;
 }
+// Policy::decompose + compute_expected_costs_to_goals on a policy given as arrays (common.rs:85-153; the reference's tests :425-489)
+API int64_t orc_policy_decompose_count(const int64_t* parent, uint64_t n) {
+  Policy p;
+  for (uint64_t k = 0; k < n; ++k) p.nodes.push_back({State{0.0, 0.0}, 0, parent[k], {}, 0});
+  for (uint64_t k = 1; k < n; ++k) p.nodes[(size_t)parent[k]].children.push_back(k);
+  std::vector<std::pair<size_t, std::vector<size_t>>> pieces;
+  std::vector<std::vector<size_t>> skeleton;
+  policy_decompose(p, pieces, skeleton);
+  return (int64_t)pieces.size();
+}
+API double orc_policy_expected_cost(const double* xy, const int64_t* belief_id, const int64_t* parent, uint64_t n, const double* beliefs, uint64_t B, uint64_t nw) {
+  BeliefGraph g;
+  for (uint64_t b = 0; b < B; ++b) g.reachable_belief_states.push_back(BeliefState(beliefs + b * nw, beliefs + (b + 1) * nw));
+  Policy p;
+  for (uint64_t k = 0; k < n; ++k) p.nodes.push_back({State{xy[2 * k], xy[2 * k + 1]}, (size_t)belief_id[k], parent[k], {}, 0});
+  for (uint64_t k = 1; k < n; ++k) if (parent[k] >= 0) p.nodes[(size_t)parent[k]].children.push_back(k);
+  return policy_expected_costs(p, g);
+}
 // refine_solution(Reparent(radius)) on the PTO's last extracted policy (main.rs:221,270: Reparent(0.3))
 API void* orc_pto_refine_reparent(void* p, double radius) {
   PTO* pto = (PTO*)p;

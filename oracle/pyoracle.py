@@ -70,7 +70,8 @@ _SIGS = {
     "orc_pto_set_validities": (None, [vp, vp, u64, u64]), "orc_pto_build_belief_graph": (C.c_int, [vp, vp, u64]),
     "orc_pto_n_beliefs": (i64, [vp]), "orc_pto_beliefs": (None, [vp, vp]),
     "orc_pto_compute_expected_costs": (C.c_int, [vp, vp]), "orc_pto_final_belief_nodes": (i64, [vp, vp, i64]),
-    "orc_pto_extract_policy": (vp, [vp]), "orc_pto_plan_qmdp": (C.c_int, [vp, vp]), "orc_pto_refine_shortcut": (vp, [vp, C.c_uint64]), "orc_pto_refine_reparent": (vp, [vp, f64]),
+    "orc_pto_extract_policy": (vp, [vp]), "orc_pto_plan_qmdp": (C.c_int, [vp, vp]), "orc_pto_refine_shortcut": (vp, [vp, C.c_uint64]), "orc_pto_refine_reparent": (vp, [vp, f64]), "orc_policy_decompose_count": (i64, [vp, u64]),
+    "orc_policy_expected_cost": (f64, [vp, vp, vp, u64, vp, u64, u64]),
     "orc_pto_react_qmdp": (i64, [vp, vp, vp, f64, vp, vp, i64]),
     "orc_refiner_transition_valid_batch": (None, [vp, vp, vp, i64, vp, u64, vp]),
     "orc_refiner_partial_shortcut": (i64, [vp, vp, u64, vp, u64, u64]),

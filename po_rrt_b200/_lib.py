@@ -61,6 +61,8 @@ SIGNATURES = {
     "porrt_prm_fetch": (i32, [vp, vp, vp, i64]),
     "porrt_sssp_worlds_prm": (i32, [vp, vp, vp, vp, pp(i32)]),
     "porrt_sssp_worlds": (i32, [vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, pp(i32)]),
+    "porrt_policy_decompose": (i32, [vp, i64, vp, vp, vp, vp, i32, pp(i32)]),
+    "porrt_policy_expected_cost": (i32, [vp, vp, vp, i64, vp, i32, i32, pp(f64)]),
     "porrt_refine_policy_reparent": (i32, [vp, vp, vp, vp, i64, f64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
     "porrt_refine_policy_shortcut": (i32, [vp, vp, vp, vp, i64, i32, C.c_uint64, vp, vp, vp, vp, vp, i64, vp, vp, vp]),
     "porrt_belief_result": (i32, [vp, vp, vp, vp, vp]),

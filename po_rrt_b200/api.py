@@ -542,6 +542,32 @@ def refine_policy_shortcut(ctx, plan, n_iterations, sampler_seed=0):
             "commits": commits.value}
 
 
+def policy_decompose(parent):
+    """Policy::decompose (common.rs:85-129) -> (pieces: list of node-id arrays, skeleton: list of successor-piece lists)"""
+    par = np.ascontiguousarray(parent, np.int32)
+    n = len(par)
+    lib = _lib.load()
+    piece_ptr, nodes = np.empty(n + 2, np.int32), np.empty(max(n, 1), np.int32)
+    succ_ptr, succ = np.empty(n + 2, np.int32), np.empty(max(n, 1), np.int32)
+    npc = C.c_int32()
+    rc = lib.porrt_policy_decompose(_p(par), n, _p(piece_ptr), _p(nodes), _p(succ_ptr), _p(succ), n + 1, C.byref(npc))
+    if rc:
+        raise PorrtError(rc, "porrt_policy_decompose")
+    k = npc.value
+    return ([nodes[piece_ptr[p]:piece_ptr[p + 1]].copy() for p in range(k)], [succ[succ_ptr[p]:succ_ptr[p + 1]].tolist() for p in range(k)])
+
+
+def policy_expected_cost(xy, belief_id, parent, beliefs):
+    """Policy::compute_expected_costs_to_goals (common.rs:131-153) with cost = norm2"""
+    x, bid, par = _f64(xy, 2), np.ascontiguousarray(belief_id, np.int32), np.ascontiguousarray(parent, np.int32)
+    bel = np.ascontiguousarray(np.atleast_2d(np.asarray(beliefs, np.float64)))
+    out = C.c_double()
+    rc = _lib.load().porrt_policy_expected_cost(_p(x), _p(bid), _p(par), len(par), _p(bel), bel.shape[0], bel.shape[1], C.byref(out))
+    if rc:
+        raise PorrtError(rc, "porrt_policy_expected_cost")
+    return out.value
+
+
 def refine_policy_reparent(ctx, plan, radius):
     """PTOPolicyRefiner::refine_solution(Reparent(radius)) on a BeliefPlan of the ctx's last plan_belief_space
     -> dict(xy, node, belief, parent, is_leaf, expected_cost, tree_nodes, transitions)"""

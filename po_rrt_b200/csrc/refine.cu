@@ -244,6 +244,40 @@ PORRT_API int32_t porrt_partial_shortcut(porrt_ctx* ctx, double* states_xy, int3
   return porrt_partial_shortcut_batch(ctx, states_xy, ptr, 1, compat_row, n_iterations, sampler_seed, out_commits, out_waves);
 }
 
+// Policy::decompose (common.rs:85-129) over flat arrays: a policy as parent[] per node in creation order (parent[0] = -1, parent[k] < k;
+// the children of a node in add_edge order = its later nodes in increasing index).  FIFO over piece starts; a piece runs until a leaf
+// or a branching node.  piece_ptr / piece_nodes: the pieces back to back; successors[p]: the pieces that start at p's branching.
+static void policy_decompose_flat(const int32_t* parent, int64_t n_pol, std::vector<int32_t>& piece_ptr, std::vector<int64_t>& piece_nodes,
+                                  std::vector<std::vector<int32_t>>& successors) {
+  std::vector<int64_t> ch_ptr((size_t)n_pol + 1, 0);
+  for (int64_t k = 1; k < n_pol; ++k) ++ch_ptr[(size_t)parent[k] + 1];
+  for (int64_t k = 0; k < n_pol; ++k) ch_ptr[(size_t)k + 1] += ch_ptr[(size_t)k];
+  std::vector<int64_t> ch((size_t)std::max<int64_t>(n_pol - 1, 0)), fill(ch_ptr.begin(), ch_ptr.end() - 1);
+  for (int64_t k = 1; k < n_pol; ++k) ch[(size_t)fill[(size_t)parent[k]]++] = k;
+  piece_ptr.assign(1, 0); piece_nodes.clear(); successors.clear();
+  std::vector<int64_t> fifo(1, 0);
+  int32_t n_pieces = 0;
+  for (size_t head = 0; head < fifo.size(); ++head) {
+    int64_t cur = fifo[head];
+    std::vector<int32_t> succ;
+    for (;;) {
+      piece_nodes.push_back(cur);
+      const int64_t nc = ch_ptr[(size_t)cur + 1] - ch_ptr[(size_t)cur];
+      if (nc == 0) break;
+      if (nc == 1) { cur = ch[(size_t)ch_ptr[(size_t)cur]]; continue; }
+      for (int64_t e = ch_ptr[(size_t)cur]; e < ch_ptr[(size_t)cur + 1]; ++e) { fifo.push_back(ch[(size_t)e]); succ.push_back(++n_pieces); }
+      break;
+    }
+    piece_ptr.push_back((int32_t)piece_nodes.size());
+    successors.push_back(succ);
+  }
+}
+static bool policy_parents_ok(const int32_t* parent, int64_t n) {
+  if (n <= 0 || !parent || parent[0] != -1) return false;
+  for (int64_t k = 1; k < n; ++k) if (parent[k] < 0 || parent[k] >= k) return false;
+  return true;
+}
+
 // Policy::compute_expected_costs_to_goals (common.rs:131-153) over flat arrays: a policy as (state, belief, parent) per node in
 // creation order; children are folded in increasing index, a child's own sum is complete before its parent adds it.
 static double policy_expected_cost_flat(const double* beliefs, int nw, const double* out_xy, const int32_t* out_belief, const int32_t* out_parent, int64_t n_out) {
@@ -300,34 +334,11 @@ PORRT_API int32_t porrt_refine_policy_shortcut(porrt_ctx* ctx, const int32_t* po
   for (int64_t k = 0; k < n_pol; ++k)
     if (pol_node[k] < 0 || pol_node[k] >= R.V || pol_belief[k] < 0 || pol_belief[k] >= B || pol_parent[k] >= k || (k > 0 && pol_parent[k] < 0) || (k == 0 && pol_parent[k] != -1))
       return porrt_fail(ctx, PORRT_ERR_INVALID_ARG, "refine_policy_shortcut: not a policy in creation order");
-  // children in creation order
-  std::vector<int64_t> ch_ptr((size_t)n_pol + 1, 0);
-  for (int64_t k = 1; k < n_pol; ++k) ++ch_ptr[(size_t)pol_parent[k] + 1];
-  for (int64_t k = 0; k < n_pol; ++k) ch_ptr[(size_t)k + 1] += ch_ptr[(size_t)k];
-  std::vector<int64_t> ch((size_t)std::max<int64_t>(n_pol - 1, 0)), fill(ch_ptr.begin(), ch_ptr.end() - 1);
-  for (int64_t k = 1; k < n_pol; ++k) ch[(size_t)fill[(size_t)pol_parent[k]]++] = k;
-  // ---- decompose: FIFO over piece starts; a piece runs until a leaf or a branching node
-  std::vector<int32_t> piece_ptr(1, 0);
+  // ---- decompose
+  std::vector<int32_t> piece_ptr;
   std::vector<int64_t> piece_nodes;                   // policy node ids, piece after piece
   std::vector<std::vector<int32_t>> successors;       // skeleton
-  {
-    std::vector<int64_t> fifo(1, 0);
-    int32_t n_pieces = 0;
-    for (size_t head = 0; head < fifo.size(); ++head) {
-      int64_t cur = fifo[head];
-      std::vector<int32_t> succ;
-      for (;;) {
-        piece_nodes.push_back(cur);
-        const int64_t nc = ch_ptr[(size_t)cur + 1] - ch_ptr[(size_t)cur];
-        if (nc == 0) break;
-        if (nc == 1) { cur = ch[(size_t)ch_ptr[(size_t)cur]]; continue; }
-        for (int64_t e = ch_ptr[(size_t)cur]; e < ch_ptr[(size_t)cur + 1]; ++e) { fifo.push_back(ch[(size_t)e]); succ.push_back(++n_pieces); }
-        break;
-      }
-      piece_ptr.push_back((int32_t)piece_nodes.size());
-      successors.push_back(succ);
-    }
-  }
+  policy_decompose_flat(pol_parent, n_pol, piece_ptr, piece_nodes, successors);
   const int32_t n_pieces = (int32_t)successors.size();
   const int64_t n_out = (int64_t)piece_nodes.size();   // every policy node ends up in exactly one piece
   *out_n = n_out;
@@ -527,32 +538,14 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
       }
     }
   };
-  // ---- Policy::decompose (common.rs:85-129), as in porrt_refine_policy_shortcut
-  std::vector<int64_t> ch_ptr((size_t)n_pol + 1, 0);
-  for (int64_t k = 1; k < n_pol; ++k) ++ch_ptr[(size_t)pol_parent[k] + 1];
-  for (int64_t k = 0; k < n_pol; ++k) ch_ptr[(size_t)k + 1] += ch_ptr[(size_t)k];
-  std::vector<int64_t> ch((size_t)std::max<int64_t>(n_pol - 1, 0)), fill(ch_ptr.begin(), ch_ptr.end() - 1);
-  for (int64_t k = 1; k < n_pol; ++k) ch[(size_t)fill[(size_t)pol_parent[k]]++] = k;
+  // ---- Policy::decompose (common.rs:85-129)
   std::vector<std::vector<int64_t>> pieces;
   std::vector<std::vector<int32_t>> successors;
   {
-    std::vector<int64_t> fifo(1, 0);
-    int32_t n_pieces = 0;
-    for (size_t head = 0; head < fifo.size(); ++head) {
-      int64_t cur = fifo[head];
-      std::vector<int64_t> ids;
-      std::vector<int32_t> succ;
-      for (;;) {
-        ids.push_back(cur);
-        const int64_t nc = ch_ptr[(size_t)cur + 1] - ch_ptr[(size_t)cur];
-        if (nc == 0) break;
-        if (nc == 1) { cur = ch[(size_t)ch_ptr[(size_t)cur]]; continue; }
-        for (int64_t e = ch_ptr[(size_t)cur]; e < ch_ptr[(size_t)cur + 1]; ++e) { fifo.push_back(ch[(size_t)e]); succ.push_back(++n_pieces); }
-        break;
-      }
-      pieces.push_back(ids);
-      successors.push_back(succ);
-    }
+    std::vector<int32_t> piece_ptr;
+    std::vector<int64_t> piece_nodes;
+    policy_decompose_flat(pol_parent, n_pol, piece_ptr, piece_nodes, successors);
+    for (size_t p = 0; p + 1 < piece_ptr.size(); ++p) pieces.emplace_back(piece_nodes.begin() + piece_ptr[p], piece_nodes.begin() + piece_ptr[p + 1]);
   }
   // ---- build_tree per piece
   const bool dbg = getenv("PORRT_DEBUG") != nullptr;
@@ -762,5 +755,37 @@ PORRT_API int32_t porrt_refine_policy_reparent(porrt_ctx* ctx, const int32_t* po
   for (int64_t k = 0; k < n_out; ++k) if (out_parent[k] >= 0) ++n_children[(size_t)out_parent[k]];
   for (int64_t k = 0; k < n_out; ++k) out_is_leaf[k] = n_children[(size_t)k] == 0;
   if (out_expected_cost) *out_expected_cost = policy_expected_cost_flat(R.beliefs.data(), nw, out_xy, out_belief, out_parent, n_out);
+  return PORRT_OK;
+}
+
+// ================================================================================================ Policy::decompose / expected cost (host)
+// The two pieces of common.rs the refiners are built around, as host-side rows of the ABI (no device, no ctx): they are what the
+// reference's own map-free tests pin (common.rs:425-489: three pieces; 1 + 0.4 sqrt 2 + 0.6 * 2 sqrt 2).
+PORRT_API int32_t porrt_policy_decompose(const int32_t* parent, int64_t n, int32_t* out_piece_ptr, int32_t* out_piece_nodes, int32_t* out_succ_ptr,
+                                         int32_t* out_succ, int32_t cap_pieces, int32_t* out_n_pieces) {
+  if (!policy_parents_ok(parent, n) || !out_n_pieces || n > 0x7fffffff) return PORRT_ERR_INVALID_ARG;
+  std::vector<int32_t> piece_ptr;
+  std::vector<int64_t> piece_nodes;
+  std::vector<std::vector<int32_t>> successors;
+  policy_decompose_flat(parent, n, piece_ptr, piece_nodes, successors);
+  const int32_t np = (int32_t)successors.size();
+  *out_n_pieces = np;
+  if (np > cap_pieces || !out_piece_ptr || !out_piece_nodes) return PORRT_ERR_CAPACITY;
+  for (int32_t p = 0; p <= np; ++p) out_piece_ptr[p] = piece_ptr[(size_t)p];
+  for (size_t k = 0; k < piece_nodes.size(); ++k) out_piece_nodes[k] = (int32_t)piece_nodes[k];
+  if (out_succ_ptr && out_succ) {           // skeleton as a CSR: successor pieces of piece p (at most np - 1 entries in all)
+    int32_t o = 0;
+    for (int32_t p = 0; p < np; ++p) { out_succ_ptr[p] = o; for (int32_t q : successors[(size_t)p]) out_succ[o++] = q; }
+    out_succ_ptr[np] = o;
+  }
+  return PORRT_OK;
+}
+
+PORRT_API int32_t porrt_policy_expected_cost(const double* xy, const int32_t* belief_id, const int32_t* parent, int64_t n, const double* beliefs,
+                                             int32_t B, int32_t n_worlds, double* out_expected_cost) {
+  if (!xy || !belief_id || !beliefs || B <= 0 || n_worlds <= 0 || !out_expected_cost || n <= 0 || !parent || parent[0] != -1) return PORRT_ERR_INVALID_ARG;
+  for (int64_t k = 0; k < n; ++k)
+    if (belief_id[k] < 0 || belief_id[k] >= B || parent[k] >= k || (k > 0 && parent[k] < -1)) return PORRT_ERR_INVALID_ARG;   // (-1 beyond node 0: an unconnected piece)
+  *out_expected_cost = policy_expected_cost_flat(beliefs, n_worlds, xy, belief_id, parent, n);
   return PORRT_OK;
 }

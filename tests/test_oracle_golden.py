@@ -309,6 +309,39 @@ def test_norms_and_steer():
     assert list(to) == [0.25, 0.25]
 
 
+def _reference_policy(beliefs0, last):
+    """the policy of common.rs:425-489: 0 -> 1 -> {2, 3}, 2 -> 4, 3 -> 5 (nodes 1, 2, 3 share a state: the observation)"""
+    xy = np.array([[0.0, 0.0], [0.0, 1.0], [0.0, 1.0], [0.0, 1.0], [-1.0, 2.0], last])
+    beliefs = np.array([beliefs0, [1.0, 0.0], [0.0, 1.0]])
+    belief_id = np.array([0, 0, 1, 2, 1, 2], np.int64)
+    parent = np.array([-1, 0, 1, 1, 2, 3], np.int64)
+    return xy, beliefs, belief_id, parent
+
+
+def test_policy_decomposition():  # common.rs:425-457
+    xy, beliefs, belief_id, parent = _reference_policy([0.5, 0.5], [1.0, 2.0])
+    assert O.lib().orc_policy_decompose_count(O.P(parent), len(parent)) == 3
+    import po_rrt_b200 as P                                   # the product's host-side row (no device needed)
+    pieces, skeleton = P.policy_decompose(parent)
+    assert len(pieces) == 3
+    assert [p.tolist() for p in pieces] == [[0, 1], [2, 4], [3, 5]] and skeleton == [[1, 2], [], []]
+
+
+def test_policy_expected_cost_computation():  # common.rs:459-489
+    xy, beliefs, belief_id, parent = _reference_policy([0.4, 0.6], [2.0, 3.0])
+    want = 1.0 + 0.4 * 2.0 ** 0.5 + 0.6 * 2.0 * 2.0 ** 0.5    # assert_eq!(policy.expected_costs, 1.0 + 0.4 * sqrt 2 + 0.6 * 2.0 * sqrt 2)
+    got = O.lib().orc_policy_expected_cost(O.P(np.ascontiguousarray(xy)), O.P(belief_id), O.P(parent), len(parent), O.P(np.ascontiguousarray(beliefs)), 3, 2)
+    assert got == want
+    import po_rrt_b200 as P
+    assert P.policy_expected_cost(xy, belief_id, parent, beliefs) == want
+
+
+def test_wm_contains():  # common.rs:413-423 (contains() is used by nobody on the hot path; restated here only)
+    contains = lambda a, b: all(x or not y for x, y in zip(a, b))
+    assert contains([1, 1], [1, 1]) and contains([1, 1], [1, 0]) and contains([1, 1], [0, 1]) and contains([1, 1], [0, 0])
+    assert contains([1, 0], [1, 0]) and not contains([1, 0], [0, 1]) and not contains([0, 0], [0, 1])
+
+
 def test_heuristic_radius():  # common.rs:357-369 (test only prints; we pin the formula against libm)
     for n in (2, 10, 100, 1000, 10000, 1000000):
         s = 2.0 * (math.log(n) / n) ** 0.5
