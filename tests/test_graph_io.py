@@ -89,3 +89,17 @@ def test_reader_accepts_any_key_order_and_compact_json(tmp_path):
         p.write_text(bad)
         with pytest.raises(ValueError):
             graph_io.load_pto_graph(str(p))
+
+
+def test_graph_serialization(tmp_path):  # pto_graph.rs:566-572: save + load of create_minimal_graph (:434-444), 0 -> 1
+    g = graph_io.PTOGraphArrays([[0.0, 0.0], [1.0, 0.0]], [0, 0], [0, 1, 1], [1], [0], [0, 0, 1], [0], [0], [[1]])
+    p = tmp_path / "test_graph_serialization.json"
+    graph_io.save_pto_graph(str(p), g)
+    doc = json.loads(p.read_text())
+    assert doc["validities"] == [[True]]
+    assert [n["state"] for n in doc["nodes"]] == [[0.0, 0.0], [1.0, 0.0]]
+    assert doc["nodes"][0]["children"] == [{"id": 1, "validity_id": 0}] and doc["nodes"][0]["parents"] == []
+    assert doc["nodes"][1]["parents"] == [{"id": 0, "validity_id": 0}] and doc["nodes"][1]["children"] == []
+    h = graph_io.load_pto_graph(str(p))
+    for a in ("xy", "node_vid", "row_ptr", "col", "edge_vid", "p_row_ptr", "p_col", "p_edge_vid", "validities"):
+        np.testing.assert_array_equal(getattr(h, a), getattr(g, a), err_msg=a)

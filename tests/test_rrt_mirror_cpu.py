@@ -76,3 +76,34 @@ def test_pto_growth_hooks_plumbing():
     assert pto.n_it() == ref.n_it()
     for a, b in zip(pto.graph.export(0), ref.graph.export(0)):
         np.testing.assert_array_equal(a, b)
+
+
+def test_plan_empty_space():  # rrt.rs:254-268
+    """the reference's own map-free RRT test: default RTTFuncs (everything valid), SquareGoal([0.9, 0.9], 0.05),
+    plan([0, 0], 0.1, 1.0, 1000, 10000) finds a path of more than two states -- here over the oracle's kd-tree with an
+    always-valid world, with get_best_solution (:183-193) restated on the mirror's tree"""
+    class EmptySpace(R.OracleBackend):
+        def __init__(self, start):
+            self.tree = O.KdTree(start, 0)
+
+        def state_valid(self, q):
+            return True
+
+        def edges_valid(self, froms, to):
+            return [True] * len(froms)
+
+    start = [0.0, 0.0]
+    goal = O.SquareGoal([((0.9, 0.9), [1])], 0.05)
+    samples = O.Pcg64(0).sample_states([-1.0, -1.0], [1.0, 1.0], 10000)
+    st, par, dist, fin = R.grow_tree(EmptySpace(start), samples, start, goal, 0.1, 1.0, 1000, 10000)
+    assert fin, "No path found!"
+
+    def path_to(k):                        # RRTTree::get_path_to (:48-60)
+        out = []
+        while k >= 0:
+            out.append(st[k])
+            k = par[k]
+        return out[::-1]
+    best = min((sum(R.norm2(a, b) for a, b in zip(p[:-1], p[1:])), len(p)) for p in (path_to(f) for f in fin))
+    assert best[1] > 2
+    assert best[0] >= R.norm2(start, [0.9, 0.9]) - 0.05 * 2 ** 0.5 - 1e-9      # no path beats the straight line to the goal region
